@@ -1,0 +1,108 @@
+// extern "C" surface of libblobs_b200.so (include/blobs_b200.h). Thin forwarding only.
+#include <new>
+
+#include "world.hpp"
+
+using blobs::World;
+
+struct BlobsWorld {
+    World w;
+    explicit BlobsWorld(const BlobsParams& p) : w(p) {}
+};
+
+#define W_OR_INVALID(p) \
+    if (!(p)) return BLOBS_ERR_INVALID
+
+extern "C" {
+
+int32_t blobs_abi_version(void) { return BLOBS_ABI_VERSION; }
+
+static thread_local char g_create_error[512] = "";
+
+int32_t blobs_world_create(const BlobsParams* params, BlobsWorld** out) {
+    if (!params || !out) return BLOBS_ERR_INVALID;
+    BlobsWorld* w = new (std::nothrow) BlobsWorld(*params);
+    if (!w) return BLOBS_ERR_CAPACITY;
+    const int rc = w->w.init();
+    if (rc) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", w->w.last_error());
+        delete w;
+        *out = nullptr;
+        return rc;
+    }
+    *out = w;
+    return BLOBS_OK;
+}
+int32_t blobs_world_destroy(BlobsWorld* w) {
+    delete w;
+    return BLOBS_OK;
+}
+int32_t blobs_world_reset(BlobsWorld* w) { W_OR_INVALID(w); return w->w.reset(); }
+const char* blobs_last_error(const BlobsWorld* w) { return w ? w->w.last_error() : g_create_error; }
+int32_t blobs_world_set_param(BlobsWorld* w, int32_t id, double v) { W_OR_INVALID(w); return w->w.set_param(id, v); }
+int32_t blobs_world_get_param(const BlobsWorld* w, int32_t id, double* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.get_param(id, out); }
+
+int32_t blobs_body_insert(BlobsWorld* w, const BlobsBodyDesc* d, BlobsHandle* out) { W_OR_INVALID(w); W_OR_INVALID(d); return w->w.body_insert(*d, out); }
+int32_t blobs_body_insert_many(BlobsWorld* w, size_t n, const BlobsBodyDesc* d, BlobsHandle* out) {
+    W_OR_INVALID(w);
+    if (n && !d) return BLOBS_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const int rc = w->w.body_insert(d[i], out ? out + i : nullptr);
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
+int32_t blobs_body_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.body_remove(h); }
+int32_t blobs_body_get(BlobsWorld* w, BlobsHandle h, BlobsBodyState* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.body_get(h, out); }
+int32_t blobs_body_set(BlobsWorld* w, BlobsHandle h, const BlobsBodyState* s, uint32_t mask) { W_OR_INVALID(w); W_OR_INVALID(s); return w->w.body_set(h, *s, mask); }
+int32_t blobs_body_count(const BlobsWorld* w, uint64_t* out) { W_OR_INVALID(w); *out = w->w.body_count(); return BLOBS_OK; }
+int32_t blobs_body_translate(BlobsWorld* w, BlobsHandle h, BlobsVec2 off) { W_OR_INVALID(w); return w->w.body_translate(h, off); }
+int32_t blobs_body_apply_force(BlobsWorld* w, BlobsHandle h, BlobsVec2 f) { W_OR_INVALID(w); return w->w.body_apply_force(h, f); }
+int32_t blobs_body_colliders(const BlobsWorld* w, BlobsHandle h, BlobsHandle* out, size_t cap, size_t* n) { W_OR_INVALID(w); W_OR_INVALID(n); return w->w.body_colliders(h, out, cap, n); }
+
+int32_t blobs_collider_insert(BlobsWorld* w, const BlobsColliderDesc* d, BlobsHandle parent, BlobsHandle* out) { W_OR_INVALID(w); W_OR_INVALID(d); return w->w.collider_insert(*d, parent, out); }
+int32_t blobs_collider_insert_many(BlobsWorld* w, size_t n, const BlobsColliderDesc* d, const BlobsHandle* parents, BlobsHandle* out) {
+    W_OR_INVALID(w);
+    if (n && (!d || !parents)) return BLOBS_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const int rc = w->w.collider_insert(d[i], parents[i], out ? out + i : nullptr);
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
+int32_t blobs_collider_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.collider_remove(h); }
+int32_t blobs_collider_get(BlobsWorld* w, BlobsHandle h, BlobsColliderState* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.collider_get(h, out); }
+int32_t blobs_collider_count(const BlobsWorld* w, uint64_t* out) { W_OR_INVALID(w); *out = w->w.collider_count(); return BLOBS_OK; }
+
+int32_t blobs_spring_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, float rest, float k, float c, BlobsHandle* out) { W_OR_INVALID(w); return w->w.spring_insert(a, b, rest, k, c, out); }
+int32_t blobs_spring_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.spring_remove(h); }
+int32_t blobs_joint_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, BlobsVec2 aa, BlobsVec2 ab, float dist, BlobsHandle* out) { W_OR_INVALID(w); return w->w.joint_insert(a, b, aa, ab, dist, out); }
+int32_t blobs_joint_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.joint_remove(h); }
+int32_t blobs_constraint_push(BlobsWorld* w, BlobsVec2 p, float r) { W_OR_INVALID(w); return w->w.constraint_push(p, r); }
+int32_t blobs_constraint_clear(BlobsWorld* w) { W_OR_INVALID(w); return w->w.constraint_clear(); }
+
+int32_t blobs_step(BlobsWorld* w, double delta, BlobsStepStats* stats) { W_OR_INVALID(w); return w->w.step(delta, 1, stats); }
+int32_t blobs_fixed_step(BlobsWorld* w, double frame_time, BlobsStepStats* stats) { W_OR_INVALID(w); return w->w.fixed_step(frame_time, stats); }
+int32_t blobs_step_n(BlobsWorld* w, double delta, uint32_t n, BlobsStepStats* stats) { W_OR_INVALID(w); return w->w.step(delta, n, stats); }
+
+int32_t blobs_body_slots(const BlobsWorld* w, uint64_t* out) { W_OR_INVALID(w); *out = w->w.body_slots(); return BLOBS_OK; }
+int32_t blobs_collider_slots(const BlobsWorld* w, uint64_t* out) { W_OR_INVALID(w); *out = w->w.collider_slots(); return BLOBS_OK; }
+int32_t blobs_download_bodies(BlobsWorld* w, BlobsBodyState* st, BlobsHandle* h, size_t cap) { W_OR_INVALID(w); return w->w.download_bodies(st, h, cap); }
+int32_t blobs_download_colliders(BlobsWorld* w, BlobsColliderState* st, BlobsHandle* h, size_t cap) { W_OR_INVALID(w); return w->w.download_colliders(st, h, cap); }
+int32_t blobs_read_body_positions(BlobsWorld* w, float* xy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(xy); return w->w.read_body_vec(0, xy, cap); }
+int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(xy); return w->w.read_body_vec(1, xy, cap); }
+int32_t blobs_apply_forces(BlobsWorld* w, const float* f, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(f); return w->w.apply_forces(f, cap); }
+int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(cx); W_OR_INVALID(cy); return w->w.download_cell_coords(cx, cy, cap); }
+
+int32_t blobs_record_contacts(BlobsWorld* w, int32_t mode, size_t cap) { W_OR_INVALID(w); return w->w.record_contacts(mode, cap); }
+int32_t blobs_events_drain(BlobsWorld* w, BlobsCollisionEvent* buf, size_t cap, size_t* n) { W_OR_INVALID(w); return w->w.events_drain(buf, cap, n); }
+int32_t blobs_pairs_drain(BlobsWorld* w, uint32_t* a, uint32_t* b, size_t cap, size_t* n, uint64_t* se, size_t se_cap, size_t* n_sub) {
+    W_OR_INVALID(w);
+    return w->w.pairs_drain(a, b, cap, n, se, se_cap, n_sub);
+}
+
+int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.kernel_info(out); }
+int32_t blobs_profile_enable(BlobsWorld* w, int32_t on) { W_OR_INVALID(w); return w->w.profile_enable(on); }
+int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n) { W_OR_INVALID(w); return w->w.profile_read(ms, launches, n); }
+
+}  // extern "C"

@@ -1,0 +1,826 @@
+// Device code of libblobs_b200: the per-substep kernels of Physics::integrate (reference
+// blobs/src/physics.rs:397-422) for sm_100a.
+//
+// Arithmetic contract: every f32 operation on the parity path is written with the
+// explicit round-to-nearest intrinsics (__fadd_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn). nvcc never
+// contracts those into FMA, so evaluation order and rounding match Rust/glam (scalar IEEE f32, no
+// FMA) irrespective of compiler flags. The TU is additionally built with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "types.cuh"
+
+namespace blobs {
+
+// ------------------------------------------------------------------------------------------------
+// exact f32 helpers (glam::Vec2 semantics: per-component scalar ops)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// glam Vec2::length = sqrt(x*x + y*y)
+__device__ __forceinline__ float vlen(float x, float y) { return __fsqrt_rn(fadd(fmul(x, x), fmul(y, y))); }
+
+// ------------------------------------------------------------------------------------------------
+// data layout
+// ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// cell arithmetic — SpatialHash::get_cell_coords (spatial.rs:57-62): floor(x / cs) as i32.
+// __float2int_rd rounds toward -inf, saturates and maps NaN to 0 exactly like Rust's `as i32`.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_coord(float v, float cs) { return __float2int_rd(fdiv(v, cs)); }
+// order-preserving int32 -> uint32, then modulo: a toroidal mapping where neighbouring cells stay neighbours
+__device__ __forceinline__ uint32_t ubias(int c) { return (uint32_t)c ^ 0x80000000u; }
+__device__ __forceinline__ uint32_t cell_index(const GridDesc& g, int cx, int cy) {
+    return (ubias(cy) % g.H) * g.W + (ubias(cx) % g.W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// neighbourhood walk: calls f(const Rec&) for every record in the cells that can hold a partner of a
+// sphere at (x, y) with radius r. Coverage proof: a contact needs
+// fl(dist) < fl(ra+rb) which implies |xa-xb| < r + rmax in real arithmetic; the cell range is
+// computed from directed-rounding bounds of x -/+ (r + rmax), and cell_coord is monotonic.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, float x, float y, float r, F&& f) {
+    const float reach = __fadd_ru(r, g.rmax);
+    const int cx0 = cell_coord(__fsub_rd(x, reach), g.cell), cx1 = cell_coord(__fadd_ru(x, reach), g.cell);
+    const int cy0 = cell_coord(__fsub_rd(y, reach), g.cell), cy1 = cell_coord(__fadd_ru(y, reach), g.cell);
+    // spans (>= 1); an empty/NaN range degenerates to one cell
+    uint32_t nx = (cx1 >= cx0) ? (uint32_t)cx1 - (uint32_t)cx0 + 1u : 1u;
+    uint32_t ny = (cy1 >= cy0) ? (uint32_t)cy1 - (uint32_t)cy0 + 1u : 1u;
+    uint32_t c0 = ubias(cx0) % g.W;
+    if (nx == 0u || nx >= g.W) { nx = g.W; c0 = 0; }
+    uint32_t r0 = ubias(cy0) % g.H;
+    if (ny == 0u || ny >= g.H) { ny = g.H; r0 = 0; }
+    const uint32_t n1 = min(nx, g.W - c0);  // cells before the row wraps
+    for (uint32_t j = 0; j < ny; ++j) {
+        uint32_t row = r0 + j;
+        if (row >= g.H) row -= g.H;
+        const uint32_t base = row * g.W;
+        uint32_t lo = __ldg(bp.tab + base + c0), hi = __ldg(bp.tab + base + c0 + n1);
+        for (uint32_t k = lo; k < hi; ++k) f(bp.rec[k]);
+        if (n1 < nx) {  // wrapped part of the row
+            lo = __ldg(bp.tab + base);
+            hi = __ldg(bp.tab + base + (nx - n1));
+            for (uint32_t k = lo; k < hi; ++k) f(bp.rec[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ Rec load_rec(const Rec* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = __ldg(q), b = __ldg(q + 1);
+    Rec r;
+    r.x = a.x; r.y = a.y; r.r = a.z; r.m = a.w;
+    r.memb = __float_as_uint(b.x); r.filt = __float_as_uint(b.y); r.parent = __float_as_uint(b.z); r.slot_sensor = __float_as_uint(b.w);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// narrowphase for one (self collider, candidate record). Restates the pair-loop body of
+// brute_force_collisions (physics.rs:250-312) from the point of view of ONE of the two bodies.
+// Returns false if there is no contact. On contact: key orders the contribution inside the reference's
+// (i, j<i) loop; (cx, cy) is what the reference adds to THIS body's position.
+// ------------------------------------------------------------------------------------------------
+struct SelfCol {
+    float x, y, r, m;
+    uint32_t memb, filt;
+    uint32_t body;   // parent body slot
+    uint32_t slot;   // collider slot
+    bool sensor;
+};
+
+struct Contact {
+    float cx, cy;
+    bool push;         // false for sensor pairs (physics.rs:291)
+    bool coincident;   // distance < 1e-6 branch (physics.rs:272-286)
+    bool i_am_a;       // this collider is `col_a` (the later slot)
+    uint32_t other;    // partner collider slot
+};
+
+__device__ __forceinline__ bool narrowphase(const SelfCol& s, const Rec& o, Contact& c) {
+    if (o.parent == s.body) return false;                                           // physics.rs:260 (also skips self)
+    if (!((s.memb & o.filt) != 0u && (o.memb & s.filt) != 0u)) return false;        // groups.rs:52-57
+    const uint32_t oslot = o.slot_sensor & 0x7fffffffu;
+    const bool osens = (o.slot_sensor >> 31) != 0u;
+    const bool i_am_a = s.slot > oslot;                                             // physics.rs:248-249 (a = later slot)
+    // axis = abs_a - abs_b (physics.rs:264); x - y == -(y - x) exactly, so compute from self and flip
+    float ax = i_am_a ? fsub(s.x, o.x) : fsub(o.x, s.x);
+    float ay = i_am_a ? fsub(s.y, o.y) : fsub(o.y, s.y);
+    float dist = vlen(ax, ay);
+    const float min_dist = i_am_a ? fadd(s.r, o.r) : fadd(o.r, s.r);                // physics.rs:267
+    if (!(dist < min_dist)) return false;                                           // physics.rs:269
+    c.coincident = false;
+    c.i_am_a = i_am_a;
+    c.other = oslot;
+    if (dist < 1e-6f) {                                                             // physics.rs:272-286
+        // Jacobi restatement of the push-out: a moves +0.01 x, b moves -0.01 x, snapshots follow.
+        // (The reference reads live positions here; exact only when neither body was touched earlier
+        // in the same pass — counted in stats.coincident_pairs, see DESIGN.md.)
+        c.coincident = true;
+        const float xa = i_am_a ? s.x : o.x, xb = i_am_a ? o.x : s.x;
+        ax = fsub(fadd(xa, 0.01f), fsub(xb, 0.01f));
+        dist = vlen(ax, ay);
+    }
+    c.push = !(s.sensor || osens);                                                  // physics.rs:291
+    c.cx = 0.f;
+    c.cy = 0.f;
+    if (c.push) {
+        const float nx = fdiv(ax, dist), ny = fdiv(ay, dist);                       // physics.rs:292
+        const float delta = fsub(min_dist, dist);                                   // physics.rs:294
+        const float ma = i_am_a ? s.m : o.m, mb = i_am_a ? o.m : s.m;
+        const float ratio = fsub(1.0f, fdiv(ma, fadd(ma, mb)));                     // physics.rs:319-321
+        if (i_am_a) {                                                               // physics.rs:298
+            const float k = fmul(ratio, delta);
+            c.cx = fmul(k, nx);
+            c.cy = fmul(k, ny);
+        } else {                                                                    // physics.rs:299 (p -= v == p += -v)
+            const float k = fmul(fsub(1.0f, ratio), delta);
+            c.cx = -fmul(k, nx);
+            c.cy = -fmul(k, ny);
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ordered contact list. The reference adds contributions to a body in pair-loop order:
+// lexicographic (later slot, earlier slot). Key = later << 32 | earlier.
+// ------------------------------------------------------------------------------------------------
+constexpr int LIST_CAP = 24;
+
+struct ContactList {
+    unsigned long long key[LIST_CAP];
+    float cx[LIST_CAP], cy[LIST_CAP];
+    int n;
+    bool overflow;
+    __device__ __forceinline__ void clear() { n = 0; overflow = false; }
+    __device__ __forceinline__ void insert(unsigned long long k, float x, float y) {
+        if (n == LIST_CAP) { overflow = true; return; }
+        int i = n++;
+        while (i > 0 && key[i - 1] > k) {
+            key[i] = key[i - 1]; cx[i] = cx[i - 1]; cy[i] = cy[i - 1];
+            --i;
+        }
+        key[i] = k; cx[i] = x; cy[i] = y;
+    }
+};
+
+__device__ __forceinline__ unsigned long long pair_key(uint32_t s, uint32_t o, bool coincident) {
+    const uint32_t hi = s > o ? s : o, lo = s > o ? o : s;
+    // bit 0 orders the coincident push-out (physics.rs:275-276) just before the contact push of the same pair
+    return ((unsigned long long)hi << 33) | ((unsigned long long)lo << 1) | (coincident ? 0ull : 1ull);
+}
+
+__device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned int v) {
+    // one atomic per warp; all 32 lanes must call
+    unsigned int s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// contact pass for one collider: gathers its ordered contributions into `list` (ordered mode) or sums them
+// directly (fast mode). Counts pairs once (from the later-slot side).
+// ------------------------------------------------------------------------------------------------
+template <bool ORDERED>
+__device__ __forceinline__ void gather_contacts(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList& list,
+                                                float& fx, float& fy, unsigned int& n_pairs, unsigned int& n_coinc,
+                                                const Recording& rec, const uint32_t* __restrict__ cparent_of_slot,
+                                                const float2* __restrict__ vel, DeviceStats* stats) {
+    for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& raw) {
+        const Rec o = load_rec(&raw);
+        Contact c;
+        if (!narrowphase(s, o, c)) return;
+        if (c.i_am_a) {
+            n_pairs++;
+            if (c.coincident) n_coinc++;
+            if (rec.mode) {
+                unsigned long long idx = atomicAdd(rec.count, 1ull);
+                if (idx < rec.cap) {
+                    rec.pairs[idx] = make_uint2(s.slot, c.other);
+                    if (rec.mode == 2u) {
+                        const float2 va = vel[s.body], vb = vel[o.parent];
+                        rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
+                    }
+                } else {
+                    atomicAdd(&stats->rec_dropped, 1ull);
+                }
+            }
+        }
+        if (c.coincident) {
+            const float px = c.i_am_a ? 0.01f : -0.01f;
+            if (ORDERED) list.insert(pair_key(s.slot, c.other, true), px, 0.0f);
+            else fx = fadd(fx, px);
+        }
+        if (c.push) {
+            if (ORDERED) list.insert(pair_key(s.slot, c.other, false), c.cx, c.cy);
+            else { fx = fadd(fx, c.cx); fy = fadd(fy, c.cy); }
+        }
+    });
+}
+
+// Rare path when a body has more than LIST_CAP contributions: repeated selection of the next key in
+// order (k+1 neighbourhood scans, no storage). Applies directly to (px, py).
+__device__ __noinline__ void apply_contacts_rescan(const GridDesc& g, const Broadphase& bp, const SelfCol* cols, int ncols,
+                                                   float& px, float& py) {
+    bool have_last = false;
+    unsigned long long last = 0;
+    for (;;) {
+        bool found = false;
+        unsigned long long best = 0;
+        float bx = 0.f, by = 0.f;
+        for (int ci = 0; ci < ncols; ++ci) {
+            const SelfCol& s = cols[ci];
+            for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& raw) {
+                const Rec o = load_rec(&raw);
+                Contact c;
+                if (!narrowphase(s, o, c)) return;
+                if (c.coincident) {
+                    const unsigned long long k = pair_key(s.slot, c.other, true);
+                    if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.i_am_a ? 0.01f : -0.01f; by = 0.f; }
+                }
+                if (c.push) {
+                    const unsigned long long k = pair_key(s.slot, c.other, false);
+                    if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.cx; by = c.cy; }
+                }
+            });
+        }
+        if (!found) break;
+        px = fadd(px, bx);
+        py = fadd(py, by);
+        last = best;
+        have_last = true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// update_objects for one body (physics.rs:326-358) + gravity (physics.rs:369-375) + circle constraints
+// (physics.rs:377-395). (px, py) is the body position after contacts/joints. Returns the pre-clamp position in
+// (sx, sy): that is what the collider snapshot is built from (physics.rs:360-366 runs before apply_constraints).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void integrate_body(const SubstepParams& P, const Constraints& K, const BodyArrays& B, uint32_t b,
+                                               uint32_t flags, float px, float py, float& sx, float& sy, float& rot_out,
+                                               DeviceStats* stats) {
+    float rot = 0.0f;
+    if (flags & BF_ROT) rot = B.rot[b];
+    if (flags & BF_STATIC) {                                     // physics.rs:327-332
+        B.pos_old[b] = make_float2(px, py);
+        B.acc[b] = make_float2(0.f, 0.f);
+        B.vel[b] = make_float2(0.f, 0.f);
+    } else {
+        float2 po = B.pos_old[b];
+        if (B.has_vreq[b]) {                                     // physics.rs:334-336
+            const float2 v = B.vreq[b];
+            po.x = fsub(px, fmul(v.x, P.dt));
+            po.y = fsub(py, fmul(v.y, P.dt));
+            B.has_vreq[b] = 0;
+        }
+        const float ratio = (b == P.first_dynamic) ? P.ratio_first : P.ratio_rest;   // physics.rs:338-339
+        const float dx = fmul(fsub(px, po.x), ratio), dy = fmul(fsub(py, po.y), ratio);
+        float2 a = B.acc[b];
+        if (!(flags & BF_SPRINGS)) {                             // gravity; spring bodies got it in k_springs
+            const float gm = B.gmod[b];
+            a.x = fadd(a.x, fmul(P.gx, gm));
+            a.y = fadd(a.y, fmul(P.gy, gm));
+        }
+        B.pos_old[b] = make_float2(px, py);                      // physics.rs:343
+        px = fadd(px, fadd(dx, fmul(fmul(a.x, P.dt), P.dt)));    // physics.rs:344
+        py = fadd(py, fadd(dy, fmul(fmul(a.y, P.dt), P.dt)));
+        if (flags & BF_ROT) {                                    // physics.rs:346-355
+            float w = B.angvel[b];
+            w = fadd(w, fmul(fdiv(B.torque[b], B.inertia[b]), P.dt));
+            rot = fadd(rot, fmul(w, P.dt));
+            B.angvel[b] = w;
+            B.rot[b] = rot;
+            B.torque[b] = 0.0f;
+        }
+        B.acc[b] = make_float2(0.f, 0.f);
+        B.vel[b] = make_float2(fdiv(dx, P.dt), fdiv(dy, P.dt));  // physics.rs:357
+    }
+    sx = px;
+    sy = py;
+    rot_out = rot;
+    for (int i = 0; i < K.n; ++i) {                              // physics.rs:377-395
+        const float tx = fsub(px, K.x[i]), ty = fsub(py, K.y[i]);
+        const float d = vlen(tx, ty);
+        if (d > K.r[i]) {
+            px = fadd(K.x[i], fmul(fdiv(tx, d), K.r[i]));
+            py = fadd(K.y[i], fmul(fdiv(ty, d), K.r[i]));
+        }
+    }
+    if (px != px || py != py) stats->nan_flag = 1u;
+    B.pos[b] = make_float2(px, py);
+}
+
+// Collider snapshot (physics.rs:360-366): abs.translation = M(rot) * offset.translation + pos, with
+// glam's Mat2::from_angle columns (cos, sin), (-sin, cos) and M*v = x_axis*v.x + y_axis*v.y.
+// Then bins the collider into the next broadphase table.
+__device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t c,
+                                                 float sx, float sy, float rot) {
+    const float2 off = Cc.coff[c];
+    float sn = 0.0f, cs = 1.0f;
+    if (rot != 0.0f) sincosf(rot, &sn, &cs);
+    const float ax = fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx);
+    const float ay = fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy);
+    Cc.cabs[c] = make_float2(ax, ay);
+    const uint32_t cell = cell_index(g, cell_coord(ax, g.cell), cell_coord(ay, g.cell));
+    const uint32_t rank = atomicAdd(tab_next + cell, 1u);
+    Cc.ccell[c] = make_uint2(cell, rank);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-main: one thread per body slot. Contacts (gather, ordered) [+ verlet + snapshot + clamp + binning when FUSED].
+// Handles bodies with zero or one collider; multi-collider bodies go to k_multi.
+// ------------------------------------------------------------------------------------------------
+template <bool FUSED, bool ORDERED>
+__global__ void __launch_bounds__(256) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                              Broadphase bp, Recording rec, DeviceStats* stats) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int n_pairs = 0, n_coinc = 0, n_over = 0;
+    if (b < P.n_bodies) {
+        const uint32_t flags = B.bflags[b];
+        const int32_t col = B.body_col[b];
+        if ((flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
+            float2 p = B.pos[b];
+            if (col >= 0 && P.collisions_enabled) {
+                const uint32_t c = (uint32_t)col;
+                const uint32_t cf = Cc.cflags[c];
+                if (cf & CF_ACTIVE) {
+                    SelfCol s;
+                    const float2 a = Cc.cabs[c];
+                    const uint2 gr = Cc.cgroups[c];
+                    s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = B.mass[b];
+                    s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+                    ContactList list;
+                    list.clear();
+                    float fx = 0.f, fy = 0.f;
+                    gather_contacts<ORDERED>(g, bp, s, list, fx, fy, n_pairs, n_coinc, rec, Cc.cparent, B.vel, stats);
+                    if (ORDERED) {
+                        if (!list.overflow) {
+                            for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
+                        } else {
+                            n_over = 1;
+                            apply_contacts_rescan(g, bp, &s, 1, p.x, p.y);
+                        }
+                    } else {
+                        p.x = fadd(p.x, fx);
+                        p.y = fadd(p.y, fy);
+                    }
+                }
+            }
+            if (FUSED) {
+                float sx, sy, rot;
+                integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
+                if (col >= 0 && (Cc.cflags[col] & CF_ACTIVE)) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, sx, sy, rot);
+            } else {
+                B.pos[b] = p;
+            }
+        }
+    }
+    warp_add_u64(&stats->collisions, n_pairs);
+    if (__any_sync(0xffffffffu, n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, n_coinc);
+        unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
+        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-multi: bodies with more than one distinct collider. One thread per such body; the contributions of all its
+// colliders are merged into one ordered list (order = (later slot, earlier slot) over the union).
+// ------------------------------------------------------------------------------------------------
+constexpr int MULTI_MAX_INLINE = 8;  // colliders staged per pass for the rescan path
+
+template <bool FUSED, bool ORDERED>
+__global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                               Broadphase bp, Recording rec, DeviceStats* stats, const uint32_t* __restrict__ mb_body,
+                                               const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols,
+                                               uint32_t n_multi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int n_pairs = 0, n_coinc = 0, n_over = 0;
+    if (i < n_multi) {
+        const uint32_t b = mb_body[i];
+        const uint32_t flags = B.bflags[b];
+        const uint32_t c0 = mb_off[i], c1 = mb_off[i + 1];
+        float2 p = B.pos[b];
+        if (P.collisions_enabled) {
+            ContactList list;
+            list.clear();
+            float fx = 0.f, fy = 0.f;
+            const float m = B.mass[b];
+            for (uint32_t k = c0; k < c1; ++k) {
+                const uint32_t c = mb_cols[k];
+                const uint32_t cf = Cc.cflags[c];
+                if (!(cf & CF_ACTIVE)) continue;
+                SelfCol s;
+                const float2 a = Cc.cabs[c];
+                const uint2 gr = Cc.cgroups[c];
+                s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
+                s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+                gather_contacts<ORDERED>(g, bp, s, list, fx, fy, n_pairs, n_coinc, rec, Cc.cparent, B.vel, stats);
+            }
+            if (ORDERED) {
+                if (!list.overflow) {
+                    for (int j = 0; j < list.n; ++j) { p.x = fadd(p.x, list.cx[j]); p.y = fadd(p.y, list.cy[j]); }
+                } else {
+                    // rescan path over all colliders of the body, MULTI_MAX_INLINE at a time is not order-safe, so
+                    // stage all of them; bodies with more colliders than fit fall back to the fast (unordered) sum.
+                    n_over = 1;
+                    SelfCol cols[MULTI_MAX_INLINE];
+                    int nc = 0;
+                    bool fits = true;
+                    for (uint32_t k = c0; k < c1; ++k) {
+                        const uint32_t c = mb_cols[k];
+                        const uint32_t cf = Cc.cflags[c];
+                        if (!(cf & CF_ACTIVE)) continue;
+                        if (nc == MULTI_MAX_INLINE) { fits = false; break; }
+                        const float2 a = Cc.cabs[c];
+                        const uint2 gr = Cc.cgroups[c];
+                        SelfCol& s = cols[nc++];
+                        s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
+                        s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+                    }
+                    if (fits) {
+                        apply_contacts_rescan(g, bp, cols, nc, p.x, p.y);
+                    } else {
+                        ContactList dummy;
+                        dummy.clear();
+                        unsigned int d0 = 0, d1 = 0;
+                        Recording off = rec;
+                        off.mode = 0;
+                        for (uint32_t k = c0; k < c1; ++k) {
+                            const uint32_t c = mb_cols[k];
+                            const uint32_t cf = Cc.cflags[c];
+                            if (!(cf & CF_ACTIVE)) continue;
+                            SelfCol s;
+                            const float2 a = Cc.cabs[c];
+                            const uint2 gr = Cc.cgroups[c];
+                            s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
+                            s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+                            gather_contacts<false>(g, bp, s, dummy, fx, fy, d0, d1, off, Cc.cparent, B.vel, stats);
+                        }
+                        p.x = fadd(p.x, fx);
+                        p.y = fadd(p.y, fy);
+                    }
+                }
+            } else {
+                p.x = fadd(p.x, fx);
+                p.y = fadd(p.y, fy);
+            }
+        }
+        if (FUSED) {
+            float sx, sy, rot;
+            integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
+            for (uint32_t k = c0; k < c1; ++k) {
+                const uint32_t c = mb_cols[k];
+                if (Cc.cflags[c] & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, c, sx, sy, rot);
+            }
+        } else {
+            B.pos[b] = p;
+        }
+    }
+    warp_add_u64(&stats->collisions, n_pairs);
+    if (__any_sync(0xffffffffu, n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, n_coinc);
+        unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
+        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-integrate (split pipeline, used when joints or event recording forbid fusion): update_objects + snapshot +
+// constraints + binning for every body.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                                   uint32_t* tab_next, DeviceStats* stats, const uint32_t* __restrict__ mb_off,
+                                                   const uint32_t* __restrict__ mb_cols) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.n_bodies) return;
+    const uint32_t flags = B.bflags[b];
+    if (!(flags & BF_ALIVE)) return;
+    const int32_t col = B.body_col[b];
+    const float2 p = B.pos[b];
+    float sx, sy, rot;
+    integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
+    if (col >= 0) {
+        if (Cc.cflags[col] & CF_ACTIVE) publish_collider(g, Cc, tab_next, (uint32_t)col, sx, sy, rot);
+    } else if (col <= -2) {
+        const uint32_t i = (uint32_t)(-(col + 2));
+        for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
+            const uint32_t c = mb_cols[k];
+            if (Cc.cflags[c] & CF_ACTIVE) publish_collider(g, Cc, tab_next, c, sx, sy, rot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-count: bins every active collider from its current snapshot (used when the broadphase is (re)built outside a step).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, uint32_t* tab_next, uint32_t n_colliders) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_colliders) return;
+    if (!(Cc.cflags[c] & CF_ACTIVE)) return;
+    const float2 a = Cc.cabs[c];
+    const uint32_t cell = cell_index(g, cell_coord(a.x, g.cell), cell_coord(a.y, g.cell));
+    const uint32_t rank = atomicAdd(tab_next + cell, 1u);
+    Cc.ccell[c] = make_uint2(cell, rank);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-scan: single-pass exclusive prefix sum (decoupled look-back) over the cell counts, in place; entry [n-1] is the
+// sentinel (count 0) and ends up holding the total. Also zeroes `zero_me` (the table that becomes tab_next next round).
+// status word: epoch[63:34] | flag[33:32] | value[31:0]; stale epochs read as "not ready", so no per-launch memset.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, uint32_t flag, uint32_t v) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ zero_me,
+                                                       uint32_t n_zero, unsigned long long* status, uint32_t epoch) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    __shared__ uint32_t tile_excl;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    uint32_t v[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+        const uint4 a = *reinterpret_cast<const uint4*>(data + base);
+        const uint4 b = *reinterpret_cast<const uint4*>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? data[base + i] : 0u;
+    }
+    // zero the other table (same index space)
+    if (base + SCAN_ITEMS <= n_zero) {
+        *reinterpret_cast<uint4*>(zero_me + base) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(zero_me + base + 4) = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < n_zero) zero_me[base + i] = 0u;
+    }
+
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) tsum += v[i];
+    // warp inclusive scan of thread sums
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const uint32_t s = warp_sums[w];
+        if (w < (int)warp) warp_off += s;
+        block_sum += s;
+    }
+    // publish the tile aggregate, then look back
+    if (warp == 0) {
+        volatile unsigned long long* st = status;
+        if (lane == 0) st[tile] = scan_pack(epoch, tile == 0 ? 2u : 1u, block_sum);
+        uint32_t excl = 0;
+        int pred = (int)tile - 1;
+        while (pred >= 0) {
+            const int idx = pred - (int)lane;
+            unsigned long long s = scan_pack(epoch, 2u, 0u);  // lanes past tile 0 read as an inclusive zero
+            if (idx >= 0) {
+                do { s = st[idx]; } while ((uint32_t)(s >> 34) != epoch || ((s >> 32) & 3ull) == 0ull);
+            }
+            const uint32_t flag = (uint32_t)(s >> 32) & 3u;
+            const uint32_t val = (uint32_t)s;
+            const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+            if (incl_mask) {
+                const int first = __ffs(incl_mask) - 1;   // nearest predecessor holding an inclusive prefix
+                const uint32_t contrib = ((int)lane <= first) ? val : 0u;
+                excl += __reduce_add_sync(0xffffffffu, contrib);
+                break;
+            }
+            excl += __reduce_add_sync(0xffffffffu, val);
+            pred -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) st[tile] = scan_pack(epoch, 2u, excl + block_sum);
+            tile_excl = excl;
+        }
+    }
+    __syncthreads();
+    uint32_t run = tile_excl + warp_off + (incl - tsum);
+    uint32_t o[SCAN_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) { o[i] = run; run += v[i]; }
+    if (base + SCAN_ITEMS <= n) {
+        *reinterpret_cast<uint4*>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i)
+            if (base + i < n) data[base + i] = o[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-scatter: writes the 32-byte record of every active collider at cell_start[cell] + rank (one full sector each).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float* __restrict__ mass, const uint32_t* __restrict__ tab,
+                                                 Rec* __restrict__ out, uint32_t n_colliders) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_colliders) return;
+    const uint32_t cf = Cc.cflags[c];
+    if (!(cf & CF_ACTIVE)) return;
+    const uint2 cr = Cc.ccell[c];
+    const float2 a = Cc.cabs[c];
+    const uint2 gr = Cc.cgroups[c];
+    const uint32_t parent = Cc.cparent[c];
+    const uint32_t dst = __ldg(tab + cr.x) + cr.y;
+    float4* q = reinterpret_cast<float4*>(out + dst);
+    q[0] = make_float4(a.x, a.y, Cc.crad[c], mass[parent]);
+    q[1] = make_float4(__uint_as_float(gr.x), __uint_as_float(gr.y), __uint_as_float(parent),
+                       __uint_as_float(c | ((cf & CF_SENSOR) ? 0x80000000u : 0u)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-springs: gravity + Spring::apply_force (springs.rs:25-47) for bodies with incident springs. One thread per such
+// body; its springs are visited in spring-slot order (the order the reference accumulates into `acceleration`).
+// edge = spring index << 1 | side (0: this body is rigid_body_a, 1: rigid_body_b)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_springs(SubstepParams P, BodyArrays B, const uint32_t* __restrict__ sb_body,
+                                                 const uint32_t* __restrict__ sb_off, const uint32_t* __restrict__ sb_edge,
+                                                 const SpringParams* __restrict__ springs, uint32_t n_sb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sb) return;
+    const uint32_t b = sb_body[i];
+    const uint32_t flags = B.bflags[b];
+    if (flags & BF_STATIC) return;  // no gravity (physics.rs:371), apply_force ignored (rigid_body.rs:156)
+    float2 a = B.acc[b];
+    const float gm = B.gmod[b];
+    a.x = fadd(a.x, fmul(P.gx, gm));   // apply_gravity runs before the springs (physics.rs:404-408)
+    a.y = fadd(a.y, fmul(P.gy, gm));
+    const float m = B.mass[b];
+    for (uint32_t e = sb_off[i]; e < sb_off[i + 1]; ++e) {
+        const uint32_t ed = sb_edge[e];
+        const SpringParams sp = springs[ed >> 1];
+        const float2 pa = B.pos[sp.a], pb = B.pos[sp.b];
+        const float2 va = B.vel[sp.a], vb = B.vel[sp.b];
+        const float dx = fsub(pb.x, pa.x), dy = fsub(pb.y, pa.y);             // springs.rs:31
+        const float dist = vlen(dx, dy);
+        const float ux = fdiv(dx, dist), uy = fdiv(dy, dist);                 // springs.rs:33
+        const float rvx = fsub(va.x, vb.x), rvy = fsub(va.y, vb.y);           // springs.rs:38
+        const float dd = fmul(sp.c, fadd(fmul(rvx, ux), fmul(rvy, uy)));      // damping * rel.dot(dir)
+        const float dfx = fmul(dd, ux), dfy = fmul(dd, uy);                   // springs.rs:39
+        const float s = fmul(sp.k, fsub(dist, sp.rest));
+        const float fmx = fsub(s, dfx), fmy = fsub(s, dfy);                   // f32 - Vec2 (springs.rs:41, Q7)
+        float fx = fmul(ux, fmx), fy = fmul(uy, fmy);                         // springs.rs:43
+        if (ed & 1u) { fx = -fx; fy = -fy; }                                  // rbd_b.apply_force(-force)
+        a.x = fadd(a.x, fdiv(fx, m));                                         // rigid_body.rs:158
+        a.y = fadd(a.y, fdiv(fy, m));
+    }
+    B.acc[b] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-joints: solve_fixed_joints (physics.rs:424-477). Sequential Gauss-Seidel is order dependent, so every connected
+// component ("island") of the joint graph is solved by ONE thread, joints in slot order, joint_iterations sweeps —
+// identical operation order to the reference within the island; islands are independent of each other.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, const uint32_t* __restrict__ isl_off,
+                                                const uint32_t* __restrict__ isl_joint, const JointParams* __restrict__ joints,
+                                                uint32_t n_islands, uint32_t iterations, DeviceStats* stats) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_islands) return;
+    const uint32_t j0 = isl_off[i], j1 = isl_off[i + 1];
+    bool bad = false;
+    for (uint32_t it = 0; it < iterations; ++it) {
+        for (uint32_t e = j0; e < j1; ++e) {
+            const JointParams jp = joints[isl_joint[e]];
+            float2 pa = B.pos[jp.a], pb = B.pos[jp.b];
+            const float wax = fadd(pa.x, jp.aax), way = fadd(pa.y, jp.aay);          // physics.rs:434-435
+            const float wbx = fadd(pb.x, jp.abx), wby = fadd(pb.y, jp.aby);
+            const float dx = fsub(wbx, wax), dy = fsub(wby, way);                    // physics.rs:437
+            const float dist = vlen(dx, dy);
+            if (dist < 1e-6f) continue;                                              // physics.rs:440-442
+            const float off_by = fsub(dist, jp.distance);
+            const float cx = fdiv(fmul(off_by, dx), dist), cy = fdiv(fmul(off_by, dy), dist);   // physics.rs:445
+            const float ma = B.mass[jp.a], mb = B.mass[jp.b];
+            const float ima = fdiv(1.0f, ma), imb = fdiv(1.0f, mb);
+            const float ims = fadd(ima, imb);                                        // physics.rs:450
+            const uint32_t fa = B.bflags[jp.a], fb = B.bflags[jp.b];
+            if (fa & BF_STATIC) {                                                    // physics.rs:452-453
+                pb.x = fsub(pb.x, fmul(ims, cx)); pb.y = fsub(pb.y, fmul(ims, cy));
+                B.pos[jp.b] = pb;
+            } else if (fb & BF_STATIC) {                                             // physics.rs:454-455
+                pa.x = fadd(pa.x, fmul(ims, cx)); pa.y = fadd(pa.y, fmul(ims, cy));
+                B.pos[jp.a] = pa;
+            } else {                                                                 // physics.rs:456-461
+                const float ratio = fdiv(ima, ims);
+                pa.x = fadd(pa.x, fmul(ratio, cx)); pa.y = fadd(pa.y, fmul(ratio, cy));
+                const float r1 = fsub(1.0f, ratio);
+                pb.x = fsub(pb.x, fmul(r1, cx)); pb.y = fsub(pb.y, fmul(r1, cy));
+                B.pos[jp.a] = pa;
+                B.pos[jp.b] = pb;
+            }
+            const float angle_a = atan2f(dy, dx);                                    // physics.rs:463
+            const float angle_b = -atan2f(dy, -dx);                                  // physics.rs:464
+            const float rc = fmul(fsub(fsub(angle_b, angle_a), jp.target), 0.5f);    // physics.rs:465-466
+            const float ra = fadd(B.rot[jp.a], fmul(rc, P.dt));                      // physics.rs:468-469
+            const float rb = fsub(B.rot[jp.b], fmul(rc, P.dt));
+            B.rot[jp.a] = ra;
+            B.rot[jp.b] = rb;
+            if (!(fabsf(ra) <= 3.4028235e38f) || !(fabsf(rb) <= 3.4028235e38f)) bad = true;   // physics.rs:471-474
+        }
+    }
+    if (bad) stats->nan_flag = 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------
+// bbox of the collider snapshot in broadphase cells (drives the table dimensions; host reads it with the stats)
+__global__ void __launch_bounds__(256) k_bbox(ColliderArrays Cc, float cell, uint32_t n_colliders, DeviceStats* stats) {
+    __shared__ int s_min_x[8], s_min_y[8], s_max_x[8], s_max_y[8];
+    int mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
+        if (!(Cc.cflags[c] & CF_ACTIVE)) continue;
+        const float2 a = Cc.cabs[c];
+        if (!(fabsf(a.x) < 1e30f) || !(fabsf(a.y) < 1e30f)) continue;   // ignore runaway / NaN points
+        const int cx = cell_coord(a.x, cell), cy = cell_coord(a.y, cell);
+        mnx = min(mnx, cx); mny = min(mny, cy); mxx = max(mxx, cx); mxy = max(mxy, cy);
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+    mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_min_x[w] = mnx; s_min_y[w] = mny; s_max_x[w] = mxx; s_max_y[w] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+            mnx = min(mnx, s_min_x[i]); mny = min(mny, s_min_y[i]); mxx = max(mxx, s_max_x[i]); mxy = max(mxy, s_max_y[i]);
+        }
+        if (mnx <= mxx) {
+            atomicMin(&stats->bb_min_x, mnx); atomicMin(&stats->bb_min_y, mny);
+            atomicMax(&stats->bb_max_x, mxx); atomicMax(&stats->bb_max_y, mxy);
+        }
+    }
+}
+
+// SpatialHash::get_cell_coords of every collider snapshot with the reference's cell size (spatial.rs:57-62)
+__global__ void __launch_bounds__(256) k_cell_coords(const float2* __restrict__ cabs, float cell_size, uint32_t n, int* __restrict__ cx,
+                                                     int* __restrict__ cy) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const float2 a = cabs[c];
+    cx[c] = cell_coord(a.x, cell_size);
+    cy[c] = cell_coord(a.y, cell_size);
+}
+
+
+__global__ void __launch_bounds__(256) k_apply_body_writes(BodyArrays B, const BodyWrite* __restrict__ w, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BodyWrite x = w[i];
+    const uint32_t s = x.slot;
+    if (x.mask & BW_POS) B.pos[s] = x.pos;
+    if (x.mask & BW_TRANSLATE) { float2 p = B.pos[s]; p.x = fadd(p.x, x.pos.x); p.y = fadd(p.y, x.pos.y); B.pos[s] = p; }
+    if (x.mask & BW_POS_OLD) B.pos_old[s] = x.pos_old;
+    if (x.mask & BW_ACC) B.acc[s] = x.acc;
+    if (x.mask & BW_ADD_ACC) { float2 a = B.acc[s]; a.x = fadd(a.x, x.acc.x); a.y = fadd(a.y, x.acc.y); B.acc[s] = a; }
+    if (x.mask & BW_VEL) B.vel[s] = x.vel;
+    if (x.mask & BW_VREQ) { B.vreq[s] = x.vreq; B.has_vreq[s] = (uint8_t)x.has_vreq; }
+    if (x.mask & BW_ROT) B.rot[s] = x.rot;
+    if (x.mask & BW_ANGVEL) B.angvel[s] = x.angvel;
+    if (x.mask & BW_TORQUE) B.torque[s] = x.torque;
+}
+
+__global__ void __launch_bounds__(256) k_apply_col_writes(float2* cabs, const ColWrite* __restrict__ w, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cabs[w[i].slot] = w[i].cabs;
+}
+
+// per-slot RigidBody::apply_force (rigid_body.rs:155-160): acc += force / calculated_mass for non-static bodies
+__global__ void __launch_bounds__(256) k_apply_forces(BodyArrays B, const float2* __restrict__ force, uint32_t n) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint32_t f = B.bflags[b];
+    if (!(f & BF_ALIVE) || (f & BF_STATIC)) return;
+    const float2 F = force[b];
+    const float m = B.mass[b];
+    float2 a = B.acc[b];
+    a.x = fadd(a.x, fdiv(F.x, m));
+    a.y = fadd(a.y, fdiv(F.y, m));
+    B.acc[b] = a;
+}
+
+}  // namespace blobs

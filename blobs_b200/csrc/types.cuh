@@ -1,0 +1,128 @@
+// POD types shared by the host orchestration (world.cu, capi.cu) and the device code (kernels.cuh).
+// No functions here, so it can be included from several translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace blobs {
+
+// body flags (host-authoritative, bflags[])
+enum : uint32_t {
+    BF_ALIVE = 1u << 0,
+    BF_STATIC = 1u << 1,       // RigidBodyType::Static
+    BF_SPRINGS = 1u << 2,      // has incident springs: gravity + spring forces are summed by k_springs
+    BF_ROT = 1u << 3,          // angular state may be non-zero / rotation matters (torque, joints, rotated)
+    BF_JOINTED = 1u << 4,
+};
+// collider flags (host-authoritative, cflags[])
+enum : uint32_t {
+    CF_ACTIVE = 1u << 0,  // alive AND parent handle resolves to a live body (physics.rs:252-253,270)
+    CF_SENSOR = 1u << 1,
+};
+constexpr uint32_t NO_SLOT = 0xffffffffu;
+constexpr int32_t BODY_NO_COLLIDER = -1;  // body_col[] encoding; <= -2 : multi-collider body (handled by k_multi)
+
+// One broadphase record per active collider, cell-sorted. 32 B = one L2 sector.
+struct __align__(16) Rec {
+    float x, y, r, m;          // snapshot translation (physics.rs:360-366), radius, parent body's calculated_mass
+    uint32_t memb, filt;       // InteractionGroups (groups.rs:7-12)
+    uint32_t parent;           // parent body slot
+    uint32_t slot_sensor;      // collider slot | is_sensor << 31
+};
+static_assert(sizeof(Rec) == 32, "Rec must be one 32-byte sector");
+
+struct GridDesc {
+    uint32_t W, H;       // toroidal table dims (cells)
+    uint32_t ncells;     // W * H
+    float cell;          // broadphase cell edge
+    float rmax;          // max radius over active colliders (search reach = r + rmax)
+};
+
+struct Constraints {       // lib.rs:189-193; small by-value copy, spill to global beyond MAXC
+    static constexpr int MAXC = 8;
+    int n;
+    float x[MAXC], y[MAXC], r[MAXC];
+};
+
+struct DeviceStats {       // accumulated per blobs_step* call, read back once
+    unsigned long long collisions;
+    unsigned long long coincident;
+    unsigned long long rec_dropped;
+    unsigned int nan_flag;
+    unsigned int list_overflow;
+    int bb_min_x, bb_min_y, bb_max_x, bb_max_y;   // bbox of collider snapshot cells (k_bbox)
+    unsigned int pad[2];
+};
+
+struct SubstepParams {
+    float dt;
+    float ratio_first, ratio_rest;  // dt/old_dt for the first non-static body, dt/dt for the rest (physics.rs:338-339, Q2)
+    uint32_t first_dynamic;         // slot of the first non-static body in arena order, NO_SLOT if none
+    float gx, gy;
+    uint32_t collisions_enabled;
+    uint32_t n_bodies;              // body slots
+    uint32_t n_colliders;           // collider slots
+};
+
+struct BodyArrays {
+    float2* pos;
+    float2* pos_old;
+    float2* acc;
+    float2* vel;
+    float2* vreq;
+    uint8_t* has_vreq;
+    float* rot;
+    float* angvel;
+    float* torque;
+    const float* inertia;
+    const float* mass;
+    const float* gmod;
+    const uint32_t* bflags;
+    const int32_t* body_col;
+};
+
+struct ColliderArrays {
+    float2* cabs;            // snapshot translation
+    const float2* coff;      // offset.translation
+    const float* crad;
+    const uint2* cgroups;    // (memberships, filter)
+    const uint32_t* cparent; // body slot
+    const uint32_t* cflags;
+    uint2* ccell;            // (cell index, rank within cell) for the next table
+};
+
+struct Broadphase {
+    const Rec* rec;          // current, read-only during the contact pass
+    const uint32_t* tab;     // current cell starts, ncells + 1 entries
+    uint32_t* tab_next;      // counts for the next table (zeroed)
+};
+
+struct Recording {           // optional pair/event output
+    uint32_t mode;           // 0 off, 1 pairs, 2 events
+    uint32_t cap;
+    unsigned long long* count;
+    uint2* pairs;            // (slot_a, slot_b), a > b
+    float4* vels;            // events: (vel_a.xy, vel_b.xy)
+};
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+struct SpringParams { uint32_t a, b; float rest, k, c; };
+
+struct JointParams { uint32_t a, b; float aax, aay, abx, aby, distance, target; };
+
+// staged host writes to device-authoritative body state (insert_rbd / get_mut_rbd mutations)
+struct BodyWrite {
+    uint32_t slot, mask;
+    float2 pos, pos_old, acc, vel, vreq;
+    float rot, angvel, torque;
+    uint32_t has_vreq;
+};
+enum : uint32_t { BW_POS = 1, BW_POS_OLD = 2, BW_ACC = 4, BW_VEL = 8, BW_VREQ = 16, BW_ROT = 32, BW_ANGVEL = 64, BW_TORQUE = 128,
+                  BW_TRANSLATE = 256, BW_ADD_ACC = 512 };
+
+struct ColWrite { uint32_t slot; float2 cabs; };
+
+}  // namespace blobs

@@ -1,0 +1,1158 @@
+// Host orchestration of the GPU-resident world. See world.hpp / kernels.cuh.
+#include "world.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+
+namespace blobs {
+
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+static inline uint32_t h_slot(uint64_t h) { return (uint32_t)h; }
+static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
+
+int World::cuda_fail(cudaError_t e, const char* what) {
+    err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return BLOBS_ERR_CUDA;
+}
+
+World::World(const BlobsParams& p) : params(p) {
+    gx = p.gravity.x;
+    gy = p.gravity.y;
+    use_spatial_hash = p.use_spatial_hash != 0;
+}
+
+int World::init() {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BLOBS_ERR_CUDA, std::string("no usable CUDA device (libblobs_b200 has no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (params.device >= 0) {
+        CU(cudaSetDevice(params.device));
+        device = params.device;
+    } else {
+        CU(cudaGetDevice(&device));
+    }
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&d_stats, sizeof(DeviceStats)));
+    CU(cudaMallocHost(&h_stats, sizeof(DeviceStats)));
+    CU(cudaMalloc(&d_rec_count, sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
+    CU(cudaEventCreate(&ev_step0));
+    CU(cudaEventCreate(&ev_step1));
+    if (params.body_capacity_hint) {
+        const size_t n = params.body_capacity_hint;
+        CU(pos.ensure(n, stream)); CU(pos_old.ensure(n, stream)); CU(acc.ensure(n, stream)); CU(vel.ensure(n, stream));
+        CU(vreq.ensure(n, stream)); CU(has_vreq.ensure(n, stream)); CU(rot.ensure(n, stream)); CU(angvel.ensure(n, stream));
+        CU(torque.ensure(n, stream));
+    }
+    if (params.collider_capacity_hint) {
+        const size_t n = params.collider_capacity_hint;
+        CU(cabs.ensure(n, stream)); CU(ccell.ensure(n, stream));
+    }
+    return BLOBS_OK;
+}
+
+World::~World() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (ev_step0) cudaEventDestroy(ev_step0);
+    if (ev_step1) cudaEventDestroy(ev_step1);
+    mass.d.release(); inertia.d.release(); gmod.d.release(); bflags.d.release(); body_col.d.release();
+    coff.d.release(); crad.d.release(); cgroups.d.release(); cparent.d.release(); cflags.d.release();
+    pos.release(); pos_old.release(); acc.release(); vel.release(); vreq.release(); cabs.release();
+    has_vreq.release(); rot.release(); angvel.release(); torque.release(); ccell.release();
+    d_pending.release(); d_pending_col.release();
+    mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
+    isl_off.release(); isl_joint.release(); d_springs.release(); d_joints.release();
+    rec_a.release(); rec_b.release(); tab_a.release(); tab_b.release(); scan_status.release();
+    rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_cellx.release(); d_celly.release();
+    if (d_stats) cudaFree(d_stats);
+    if (h_stats) cudaFreeHost(h_stats);
+    if (d_rec_count) cudaFree(d_rec_count);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// ---------------------------------------------------------------------------------------------- params
+int World::set_param(int id, double v) {
+    switch (id) {
+        case BLOBS_PARAM_GRAVITY_X: gx = (float)v; break;
+        case BLOBS_PARAM_GRAVITY_Y: gy = (float)v; break;
+        case BLOBS_PARAM_SUBSTEPS: substeps = (uint32_t)v; break;
+        case BLOBS_PARAM_JOINT_ITERATIONS: joint_iterations = (uint32_t)v; break;
+        case BLOBS_PARAM_USE_SPATIAL_HASH: use_spatial_hash = v != 0; break;
+        case BLOBS_PARAM_COLLISIONS_ENABLED: collisions_enabled = v != 0; break;
+        case BLOBS_PARAM_ACCUMULATOR: accumulator = v; break;
+        case BLOBS_PARAM_TIME: time = v; break;
+        case BLOBS_PARAM_OLD_DT: old_dt = (float)v; break;
+        case BLOBS_PARAM_CELL_SIZE: cell_size = (float)v; break;
+        case BLOBS_PARAM_BROADPHASE_CELL: bp_cell_override = (float)v; bp_dirty = true; break;
+        case BLOBS_PARAM_CONTACT_MODE: contact_mode = (int)v; break;
+        case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
+        default: return fail(BLOBS_ERR_INVALID, "unknown param id");
+    }
+    return BLOBS_OK;
+}
+
+int World::get_param(int id, double* out) const {
+    switch (id) {
+        case BLOBS_PARAM_GRAVITY_X: *out = gx; break;
+        case BLOBS_PARAM_GRAVITY_Y: *out = gy; break;
+        case BLOBS_PARAM_SUBSTEPS: *out = substeps; break;
+        case BLOBS_PARAM_JOINT_ITERATIONS: *out = joint_iterations; break;
+        case BLOBS_PARAM_USE_SPATIAL_HASH: *out = use_spatial_hash; break;
+        case BLOBS_PARAM_COLLISIONS_ENABLED: *out = collisions_enabled; break;
+        case BLOBS_PARAM_ACCUMULATOR: *out = accumulator; break;
+        case BLOBS_PARAM_TIME: *out = time; break;
+        case BLOBS_PARAM_OLD_DT: *out = old_dt; break;
+        case BLOBS_PARAM_CELL_SIZE: *out = cell_size; break;
+        case BLOBS_PARAM_BROADPHASE_CELL: *out = bp_cell_override; break;
+        case BLOBS_PARAM_CONTACT_MODE: *out = contact_mode; break;
+        case BLOBS_PARAM_FUSED: *out = allow_fused; break;
+        default: return BLOBS_ERR_INVALID;
+    }
+    return BLOBS_OK;
+}
+
+// Physics::reset (physics.rs:71-76): clears the four arenas; constraints, time, old_dt stay.
+int World::reset() {
+    bodies.clear(); cols.clear(); springs.clear(); joints.clear();
+    for (auto& b : hb) b = HBody{};
+    pending.clear();
+    std::fill(pending_idx.begin(), pending_idx.end(), -1);
+    pending_col.clear();
+    topo_dirty = bp_dirty = true;
+    shadow_valid = false;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- staging
+BodyWrite& World::stage(uint32_t slot) {
+    if (pending_idx.size() < bodies.slots()) pending_idx.resize(bodies.slots(), -1);
+    int32_t i = pending_idx[slot];
+    if (i < 0) {
+        i = (int32_t)pending.size();
+        pending_idx[slot] = i;
+        BodyWrite w{};
+        w.slot = slot;
+        pending.push_back(w);
+    }
+    return pending[i];
+}
+
+int World::flush_writes() {
+    if (!pending.empty()) {
+        CU(d_pending.ensure(pending.size(), stream));
+        CU(cudaMemcpyAsync(d_pending.d, pending.data(), pending.size() * sizeof(BodyWrite), cudaMemcpyHostToDevice, stream));
+        k_apply_body_writes<<<cdiv(pending.size(), 256), 256, 0, stream>>>(body_arrays(), d_pending.d, (uint32_t)pending.size());
+        launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(stream));  // pending is pageable host memory
+        for (auto& w : pending) pending_idx[w.slot] = -1;
+        pending.clear();
+    }
+    if (!pending_col.empty()) {
+        CU(d_pending_col.ensure(pending_col.size(), stream));
+        CU(cudaMemcpyAsync(d_pending_col.d, pending_col.data(), pending_col.size() * sizeof(ColWrite), cudaMemcpyHostToDevice, stream));
+        k_apply_col_writes<<<cdiv(pending_col.size(), 256), 256, 0, stream>>>(cabs.d, d_pending_col.d, (uint32_t)pending_col.size());
+        launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(stream));
+        pending_col.clear();
+    }
+    return BLOBS_OK;
+}
+
+BodyArrays World::body_arrays() {
+    BodyArrays B;
+    B.pos = pos.d; B.pos_old = pos_old.d; B.acc = acc.d; B.vel = vel.d; B.vreq = vreq.d; B.has_vreq = has_vreq.d;
+    B.rot = rot.d; B.angvel = angvel.d; B.torque = torque.d; B.inertia = inertia.d.d; B.mass = mass.d.d; B.gmod = gmod.d.d;
+    B.bflags = bflags.d.d; B.body_col = body_col.d.d;
+    return B;
+}
+ColliderArrays World::col_arrays() {
+    ColliderArrays C;
+    C.cabs = cabs.d; C.coff = coff.d.d; C.crad = crad.d.d; C.cgroups = cgroups.d.d; C.cparent = cparent.d.d;
+    C.cflags = cflags.d.d; C.ccell = ccell.d;
+    return C;
+}
+Constraints World::constraints_pod() const {
+    Constraints K;
+    K.n = (int)con_pos.size();
+    for (int i = 0; i < K.n && i < Constraints::MAXC; ++i) { K.x[i] = con_pos[i].x; K.y[i] = con_pos[i].y; K.r[i] = con_r[i]; }
+    for (int i = K.n; i < Constraints::MAXC; ++i) { K.x[i] = K.y[i] = K.r[i] = 0.f; }
+    return K;
+}
+
+// ---------------------------------------------------------------------------------------------- bodies
+int World::body_insert(const BlobsBodyDesc& d, uint64_t* out) {
+    const uint64_t h = bodies.insert();
+    const uint32_t s = h_slot(h);
+    if (hb.size() < bodies.slots()) hb.resize(bodies.slots());
+    HBody& b = hb[s];
+    b = HBody{};
+    b.ud_lo = d.user_data_lo; b.ud_hi = d.user_data_hi;
+    b.scale = d.scale;
+    b.type = d.body_type;
+    b.rot_active = d.rotation != 0.0f;
+    const size_t n = bodies.slots();
+    mass.resize(n, 1.0f); inertia.resize(n, 1.0f); gmod.resize(n, 1.0f); bflags.resize(n, 0u); body_col.resize(n, BODY_NO_COLLIDER);
+    mass.set(s, 1.0f);     // RigidBodyBuilder::build rigid_body.rs:385-388
+    inertia.set(s, 1.0f);
+    gmod.set(s, d.gravity_mod);
+    BodyWrite& w = stage(s);
+    w.mask = BW_POS | BW_POS_OLD | BW_ACC | BW_VEL | BW_VREQ | BW_ROT | BW_ANGVEL | BW_TORQUE;
+    w.pos = make_float2(d.position.x, d.position.y);
+    w.pos_old = make_float2(d.position_old.x, d.position_old.y);
+    w.acc = make_float2(d.acceleration.x, d.acceleration.y);
+    w.vel = make_float2(d.calculated_velocity.x, d.calculated_velocity.y);
+    w.vreq = make_float2(d.velocity_request.x, d.velocity_request.y);
+    w.has_vreq = d.has_velocity_request ? 1u : 0u;
+    w.rot = d.rotation; w.angvel = 0.f; w.torque = 0.f;
+    if (shadow_valid) {
+        if (sh_pos.size() < n) { sh_pos.resize(n); sh_rot.resize(n); }
+        sh_pos[s] = w.pos;
+        sh_rot[s] = w.rot;
+    }
+    topo_dirty = true;
+    if (out) *out = h;
+    return BLOBS_OK;
+}
+
+// rigid_body.rs:96-128
+void World::update_mass_and_inertia(uint32_t bs) {
+    HBody& b = hb[bs];
+    float m = 0.0f, in = 0.0f;
+    float wx = 0.0f, wy = 0.0f;
+    for (uint64_t ch : b.colliders) {
+        if (!cols.valid(ch)) continue;
+        const BlobsColliderDesc& c = hc[h_slot(ch)].desc;
+        if (c.is_sensor) continue;
+        const float cm = c.has_mass_override ? c.mass_override : c.radius * 2.0f;   // collider.rs:40-42
+        const float ox = c.offset.translation.x, oy = c.offset.translation.y;
+        const float dlen = std::sqrt(ox * ox + oy * oy);
+        const float ci = 0.5f * cm * (c.radius * c.radius);                         // collider.rs:44-50
+        m += cm;
+        in += ci + cm * (dlen * dlen);
+        wx += ox * cm;
+        wy += oy * cm;
+    }
+    if (m == 0.0f) m = 1.0f;
+    if (in == 0.0f) in = 1.0f;
+    b.com = BlobsVec2{wx / m, wy / m};
+    mass.set(bs, m);
+    inertia.set(bs, in);
+    bp_dirty = true;  // records carry the parent's mass
+}
+
+int World::body_remove(uint64_t h) {
+    if (!bodies.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "removing a non-existent rigid body");  // rigid_body.rs:266-275
+    const uint32_t s = h_slot(h);
+    for (uint64_t ch : hb[s].colliders)
+        if (cols.valid(ch)) cols.remove_slot(h_slot(ch));  // remove_ignoring_parent (physics.rs:165-167)
+    hb[s] = HBody{};
+    bodies.remove_slot(s);
+    topo_dirty = bp_dirty = true;
+    return BLOBS_OK;
+}
+
+int World::ensure_shadow() {
+    int rc = flush();
+    if (rc) return rc;
+    if (!shadow_valid) {
+        const size_t n = bodies.slots();
+        sh_pos.resize(n);
+        sh_rot.resize(n);
+        if (n) {
+            CU(cudaMemcpyAsync(sh_pos.data(), pos.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+            CU(cudaMemcpyAsync(sh_rot.data(), rot.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        shadow_valid = true;
+    }
+    return BLOBS_OK;
+}
+
+int World::body_get(uint64_t h, BlobsBodyState* out) {
+    if (!bodies.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "get_rbd: None");
+    int rc = flush();
+    if (rc) return rc;
+    const uint32_t s = h_slot(h);
+    float2 p, po, a, v, vr;
+    float r, w, t;
+    uint8_t hv;
+    CU(cudaMemcpyAsync(&p, pos.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&po, pos_old.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&a, acc.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&v, vel.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&vr, vreq.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&r, rot.d + s, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&w, angvel.d + s, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&t, torque.d + s, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(&hv, has_vreq.d + s, 1, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const HBody& b = hb[s];
+    std::memset(out, 0, sizeof(*out));
+    out->position = {p.x, p.y}; out->position_old = {po.x, po.y}; out->acceleration = {a.x, a.y};
+    out->calculated_velocity = {v.x, v.y}; out->velocity_request = {vr.x, vr.y}; out->has_velocity_request = hv;
+    out->rotation = r; out->angular_velocity = w; out->torque = t;
+    out->center_of_mass = b.com; out->scale = b.scale;
+    out->calculated_mass = mass.h[s]; out->inertia = inertia.h[s]; out->gravity_mod = gmod.h[s];
+    out->body_type = b.type; out->user_data_lo = b.ud_lo; out->user_data_hi = b.ud_hi;
+    return BLOBS_OK;
+}
+
+int World::body_set(uint64_t h, const BlobsBodyState& s, uint32_t mask) {
+    if (!bodies.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "get_mut_rbd: None");
+    const uint32_t slot = h_slot(h);
+    HBody& b = hb[slot];
+    const uint32_t dev_mask = BLOBS_BODY_POSITION | BLOBS_BODY_POSITION_OLD | BLOBS_BODY_ACCELERATION | BLOBS_BODY_VELOCITY_REQUEST |
+                              BLOBS_BODY_CALC_VELOCITY | BLOBS_BODY_ROTATION | BLOBS_BODY_ANGULAR_VELOCITY | BLOBS_BODY_TORQUE;
+    if (mask & dev_mask) {
+        {
+            BodyWrite& w0 = stage(slot);
+            if (w0.mask & (BW_TRANSLATE | BW_ADD_ACC)) {  // keep read-modify-write ops ordered
+                int rc = flush_writes();
+                if (rc) return rc;
+            }
+        }
+        BodyWrite& w = stage(slot);
+        if (mask & BLOBS_BODY_POSITION) { w.mask |= BW_POS; w.pos = make_float2(s.position.x, s.position.y); if (shadow_valid) sh_pos[slot] = w.pos; }
+        if (mask & BLOBS_BODY_POSITION_OLD) { w.mask |= BW_POS_OLD; w.pos_old = make_float2(s.position_old.x, s.position_old.y); }
+        if (mask & BLOBS_BODY_ACCELERATION) { w.mask |= BW_ACC; w.acc = make_float2(s.acceleration.x, s.acceleration.y); }
+        if (mask & BLOBS_BODY_CALC_VELOCITY) { w.mask |= BW_VEL; w.vel = make_float2(s.calculated_velocity.x, s.calculated_velocity.y); }
+        if (mask & BLOBS_BODY_VELOCITY_REQUEST) {
+            w.mask |= BW_VREQ;
+            w.vreq = make_float2(s.velocity_request.x, s.velocity_request.y);
+            w.has_vreq = s.has_velocity_request ? 1u : 0u;
+        }
+        if (mask & BLOBS_BODY_ROTATION) { w.mask |= BW_ROT; w.rot = s.rotation; if (shadow_valid) sh_rot[slot] = w.rot; if (s.rotation != 0.f) b.rot_active = true; }
+        if (mask & BLOBS_BODY_ANGULAR_VELOCITY) { w.mask |= BW_ANGVEL; w.angvel = s.angular_velocity; if (s.angular_velocity != 0.f) b.rot_active = true; }
+        if (mask & BLOBS_BODY_TORQUE) { w.mask |= BW_TORQUE; w.torque = s.torque; if (s.torque != 0.f) b.rot_active = true; }
+        if (b.rot_active && !(bflags.h[slot] & BF_ROT)) topo_dirty = true;
+    }
+    if (mask & BLOBS_BODY_MASS) { mass.set(slot, s.calculated_mass); bp_dirty = true; }
+    if (mask & BLOBS_BODY_INERTIA) inertia.set(slot, s.inertia);
+    if (mask & BLOBS_BODY_GRAVITY_MOD) gmod.set(slot, s.gravity_mod);
+    if (mask & BLOBS_BODY_TYPE) { if (b.type != s.body_type) { b.type = s.body_type; topo_dirty = true; } }
+    if (mask & BLOBS_BODY_USER_DATA) { b.ud_lo = s.user_data_lo; b.ud_hi = s.user_data_hi; }
+    if (mask & BLOBS_BODY_SCALE) b.scale = s.scale;
+    if (mask & BLOBS_BODY_CENTER_OF_MASS) b.com = s.center_of_mass;
+    return BLOBS_OK;
+}
+
+// update_rigid_body_position (physics.rs:174-182): position += offset
+int World::body_translate(uint64_t h, BlobsVec2 off) {
+    if (!bodies.valid(h)) return BLOBS_OK;  // `if let Some(..)`: silently ignored
+    const uint32_t slot = h_slot(h);
+    if (stage(slot).mask & (BW_TRANSLATE | BW_POS)) {
+        int rc = flush_writes();
+        if (rc) return rc;
+    }
+    BodyWrite& w = stage(slot);
+    w.mask |= BW_TRANSLATE;
+    w.pos = make_float2(off.x, off.y);
+    shadow_valid = false;
+    return BLOBS_OK;
+}
+
+// RigidBody::apply_force (rigid_body.rs:155-160)
+int World::body_apply_force(uint64_t h, BlobsVec2 f) {
+    if (!bodies.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "apply_force: stale handle");
+    const uint32_t slot = h_slot(h);
+    if (hb[slot].type == BLOBS_BODY_STATIC) return BLOBS_OK;
+    if (stage(slot).mask & (BW_ADD_ACC | BW_ACC)) {
+        int rc = flush_writes();
+        if (rc) return rc;
+    }
+    BodyWrite& w = stage(slot);
+    w.mask |= BW_ADD_ACC;
+    const float m = mass.h[slot];
+    w.acc = make_float2(f.x / m, f.y / m);
+    return BLOBS_OK;
+}
+
+int World::body_colliders(uint64_t h, uint64_t* out, size_t cap, size_t* n) const {
+    if (!bodies.valid(h)) return BLOBS_ERR_STALE_HANDLE;
+    const auto& v = hb[h_slot(h)].colliders;
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    *n = v.size();
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- colliders
+int World::collider_insert(const BlobsColliderDesc& d, uint64_t parent, uint64_t* out) {
+    if (!bodies.valid(parent)) return fail(BLOBS_ERR_STALE_HANDLE, "parent rigid body must exist when inserting collider");  // physics.rs:142
+    const uint64_t h = cols.insert();
+    const uint32_t s = h_slot(h);
+    if (hc.size() < cols.slots()) hc.resize(cols.slots());
+    hc[s].desc = d;
+    hc[s].parent = parent;
+    const size_t n = cols.slots();
+    coff.resize(n, make_float2(0.f, 0.f)); crad.resize(n, 0.f); cgroups.resize(n, make_uint2(0, 0));
+    cparent.resize(n, NO_SLOT); cflags.resize(n, 0u);
+    coff.set(s, make_float2(d.offset.translation.x, d.offset.translation.y));
+    crad.set(s, d.radius);
+    cgroups.set(s, make_uint2(d.memberships, d.filter));
+    pending_col.push_back(ColWrite{s, make_float2(d.absolute_transform.translation.x, d.absolute_transform.translation.y)});
+    HBody& b = hb[h_slot(parent)];
+    b.colliders.push_back(h);  // collider.rs:179-181
+    b.colliders.push_back(h);  // physics.rs:144
+    b.cols.push_back(s);
+    update_mass_and_inertia(h_slot(parent));  // physics.rs:146
+    topo_dirty = bp_dirty = true;
+    if (out) *out = h;
+    return BLOBS_OK;
+}
+
+// remove_col (physics.rs:159-161 -> collider.rs:134-164)
+int World::collider_remove(uint64_t h) {
+    if (!cols.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "remove_col: collider not found");
+    const uint32_t s = h_slot(h);
+    const uint64_t parent = hc[s].parent;
+    if (parent != 0 && bodies.valid(parent)) {
+        const uint32_t bs = h_slot(parent);
+        HBody& b = hb[bs];
+        b.colliders.erase(std::remove(b.colliders.begin(), b.colliders.end(), h), b.colliders.end());
+        b.cols.erase(std::remove(b.cols.begin(), b.cols.end(), s), b.cols.end());
+        update_mass_and_inertia(bs);
+        if (b.colliders.empty()) {  // "rbd removed because colliders.len() == 0" (collider.rs:143-158)
+            hb[bs] = HBody{};
+            bodies.remove_slot(bs);
+        }
+    }
+    cols.remove_slot(s);
+    topo_dirty = bp_dirty = true;
+    return BLOBS_OK;
+}
+
+int World::collider_get(uint64_t h, BlobsColliderState* out) {
+    if (!cols.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "get_col: None");
+    int rc = flush();
+    if (rc) return rc;
+    const uint32_t s = h_slot(h);
+    float2 a;
+    CU(cudaMemcpyAsync(&a, cabs.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    out->desc = hc[s].desc;
+    out->desc.absolute_transform.translation = {a.x, a.y};
+    out->parent = hc[s].parent;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- springs / joints
+int World::spring_insert(uint64_t a, uint64_t b, float rest, float k, float c, uint64_t* out) {
+    const uint64_t h = springs.insert();
+    if (hs.size() < springs.slots()) hs.resize(springs.slots());
+    hs[h_slot(h)] = HSpring{a, b, rest, k, c};
+    topo_dirty = true;
+    if (out) *out = h;
+    return BLOBS_OK;
+}
+int World::spring_remove(uint64_t h) {
+    if (!springs.valid(h)) return BLOBS_ERR_STALE_HANDLE;
+    springs.remove_slot(h_slot(h));
+    topo_dirty = true;
+    return BLOBS_OK;
+}
+
+int World::joint_insert(uint64_t a, uint64_t b, BlobsVec2 aa, BlobsVec2 ab, float dist, uint64_t* out) {
+    if (h_slot(a) == h_slot(b) && bodies.valid(a) && bodies.valid(b)) return fail(BLOBS_ERR_SAME_BODY, "get2_mut called with identical indices");
+    if (!bodies.valid(a) || !bodies.valid(b)) return fail(BLOBS_ERR_STALE_HANDLE, "create_fixed_joint: unwrap on None");
+    int rc = ensure_shadow();
+    if (rc) return rc;
+    const uint32_t sa = h_slot(a), sb = h_slot(b);
+    if (std::isnan(dist)) {  // create_fixed_joint (physics.rs:198)
+        const float2 pa = sh_pos[sa], pb = sh_pos[sb];
+        const float x = ((pa.x + aa.x) - pb.x) - ab.x, y = ((pa.y + aa.y) - pb.y) - ab.y;
+        dist = std::sqrt(x * x + y * y);
+    }
+    const uint64_t h = joints.insert();
+    if (hj.size() < joints.slots()) hj.resize(joints.slots());
+    hj[h_slot(h)] = HJoint{a, b, aa, ab, dist, sh_rot[sb] - sh_rot[sa]};  // physics.rs:230
+    hb[sa].joints.push_back(h);
+    hb[sb].joints.push_back(h);
+    topo_dirty = true;
+    if (out) *out = h;
+    return BLOBS_OK;
+}
+int World::joint_remove(uint64_t h) {
+    if (!joints.valid(h)) return BLOBS_ERR_STALE_HANDLE;
+    joints.remove_slot(h_slot(h));
+    topo_dirty = true;
+    return BLOBS_OK;
+}
+
+int World::constraint_push(BlobsVec2 p, float r) {
+    if ((int)con_pos.size() >= Constraints::MAXC) return fail(BLOBS_ERR_CAPACITY, "at most 8 circle constraints are supported");
+    con_pos.push_back(p);
+    con_r.push_back(r);
+    return BLOBS_OK;
+}
+int World::constraint_clear() {
+    con_pos.clear();
+    con_r.clear();
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- topology
+template <class T>
+static cudaError_t upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
+    cudaError_t e = d.ensure(std::max<size_t>(h.size(), 1), st);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpyAsync(d.d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+int World::rebuild_topology() {
+    const size_t nb = bodies.slots(), nc = cols.slots();
+    topo_error = 0;
+    topo_error_msg.clear();
+    bflags.resize(nb, 0u); body_col.resize(nb, BODY_NO_COLLIDER); mass.resize(nb, 1.0f); inertia.resize(nb, 1.0f); gmod.resize(nb, 1.0f);
+    coff.resize(nc, make_float2(0.f, 0.f)); crad.resize(nc, 0.f); cgroups.resize(nc, make_uint2(0, 0)); cparent.resize(nc, NO_SLOT); cflags.resize(nc, 0u);
+
+    // springs (slot order) -> per-body CSR in spring order
+    std::vector<SpringParams> sp;
+    for (auto& b : hb) { b.n_springs = 0; b.n_joints = 0; }
+    for (uint32_t s = 0; s < springs.slots(); ++s) {
+        if (!springs.alive[s]) continue;
+        const HSpring& x = hs[s];
+        if (!bodies.valid(x.a) || !bodies.valid(x.b)) { topo_error = BLOBS_ERR_DANGLING; topo_error_msg = "spring references a removed rigid body (zip_unwrap on None, springs.rs:26-29)"; continue; }
+        if (h_slot(x.a) == h_slot(x.b)) { topo_error = BLOBS_ERR_SAME_BODY; topo_error_msg = "spring: get2_mut called with identical indices"; continue; }
+        sp.push_back(SpringParams{h_slot(x.a), h_slot(x.b), x.rest, x.k, x.c});
+        hb[h_slot(x.a)].n_springs++;
+        hb[h_slot(x.b)].n_springs++;
+    }
+    n_springs_live = (uint32_t)sp.size();
+    std::vector<uint32_t> v_sb_body, v_sb_off, v_sb_edge;
+    {
+        std::vector<int32_t> idx(nb, -1);
+        for (uint32_t b = 0; b < nb; ++b)
+            if (bodies.alive[b] && hb[b].n_springs) { idx[b] = (int32_t)v_sb_body.size(); v_sb_body.push_back(b); }
+        v_sb_off.assign(v_sb_body.size() + 1, 0);
+        for (size_t i = 0; i < v_sb_body.size(); ++i) v_sb_off[i + 1] = v_sb_off[i] + hb[v_sb_body[i]].n_springs;
+        v_sb_edge.resize(v_sb_off.back());
+        std::vector<uint32_t> fill(v_sb_off.begin(), v_sb_off.end() - 1);
+        for (uint32_t i = 0; i < sp.size(); ++i) {
+            v_sb_edge[fill[idx[sp[i].a]]++] = (i << 1) | 0u;
+            v_sb_edge[fill[idx[sp[i].b]]++] = (i << 1) | 1u;
+        }
+    }
+    n_sb = (uint32_t)v_sb_body.size();
+
+    // joints (slot order) -> islands via union-find, joints of an island stay in slot order
+    std::vector<JointParams> jp;
+    std::vector<uint32_t> v_isl_off{0}, v_isl_joint;
+    {
+        std::vector<uint32_t> uf(nb);
+        std::iota(uf.begin(), uf.end(), 0u);
+        auto find = [&](uint32_t x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+        for (uint32_t s = 0; s < joints.slots(); ++s) {
+            if (!joints.alive[s]) continue;
+            const HJoint& x = hj[s];
+            if (!bodies.valid(x.a) || !bodies.valid(x.b)) { topo_error = BLOBS_ERR_DANGLING; topo_error_msg = "joint references a removed rigid body (unwrap on None, physics.rs:427-432)"; continue; }
+            const uint32_t a = h_slot(x.a), b = h_slot(x.b);
+            if (!(mass.h[a] > 0.0f) || !(mass.h[b] > 0.0f)) { topo_error = BLOBS_ERR_MASS; topo_error_msg = "assertion failed: calculated_mass > 0.0 (physics.rs:447-448)"; }
+            jp.push_back(JointParams{a, b, x.aa.x, x.aa.y, x.ab.x, x.ab.y, x.distance, x.target});
+            hb[a].n_joints++;
+            hb[b].n_joints++;
+            uf[find(a)] = find(b);
+        }
+        std::vector<int32_t> isl_of(nb, -1);
+        std::vector<uint32_t> cnt;
+        for (const auto& j : jp) {
+            const uint32_t r = find(j.a);
+            if (isl_of[r] < 0) { isl_of[r] = (int32_t)cnt.size(); cnt.push_back(0); }
+            cnt[isl_of[r]]++;
+        }
+        v_isl_off.assign(cnt.size() + 1, 0);
+        for (size_t i = 0; i < cnt.size(); ++i) v_isl_off[i + 1] = v_isl_off[i] + cnt[i];
+        v_isl_joint.resize(jp.size());
+        std::vector<uint32_t> fill(v_isl_off.begin(), v_isl_off.end() - 1);
+        for (uint32_t i = 0; i < jp.size(); ++i) v_isl_joint[fill[isl_of[find(jp[i].a)]]++] = i;
+        n_islands = (uint32_t)cnt.size();
+    }
+    n_joints_live = (uint32_t)jp.size();
+
+    // colliders: parent resolution
+    r_max = 0.f;
+    n_active_cols = 0;
+    for (uint32_t c = 0; c < nc; ++c) {
+        uint32_t f = 0, p = NO_SLOT;
+        if (cols.alive[c]) {
+            const HCollider& x = hc[c];
+            if (x.parent != 0 && bodies.valid(x.parent)) {
+                f |= CF_ACTIVE;
+                p = h_slot(x.parent);
+                r_max = std::max(r_max, x.desc.radius);
+                n_active_cols++;
+            }
+            if (x.desc.is_sensor) f |= CF_SENSOR;
+        }
+        cflags.set(c, f);
+        cparent.set(c, p);
+    }
+
+    // bodies
+    std::vector<uint32_t> v_mb_body, v_mb_off{0}, v_mb_cols;
+    first_dynamic = NO_SLOT;
+    n_simple = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        uint32_t f = 0;
+        int32_t bc = BODY_NO_COLLIDER;
+        if (bodies.alive[b]) {
+            HBody& x = hb[b];
+            f |= BF_ALIVE;
+            if (x.type == BLOBS_BODY_STATIC) f |= BF_STATIC;
+            else if (first_dynamic == NO_SLOT) first_dynamic = b;
+            if (x.n_springs) f |= BF_SPRINGS;
+            if (x.n_joints) f |= BF_JOINTED | BF_ROT;
+            if (x.rot_active) f |= BF_ROT;
+            // distinct live colliders parented to this body, ascending slot
+            auto& cs = x.cols;
+            cs.erase(std::remove_if(cs.begin(), cs.end(), [&](uint32_t c) { return !cols.alive[c] || hc[c].parent != bodies.handle_at(b); }), cs.end());
+            if (cs.size() == 1) { bc = (int32_t)cs[0]; n_simple++; }
+            else if (cs.size() > 1) {
+                std::sort(cs.begin(), cs.end());
+                bc = -(int32_t)v_mb_body.size() - 2;
+                v_mb_body.push_back(b);
+                v_mb_cols.insert(v_mb_cols.end(), cs.begin(), cs.end());
+                v_mb_off.push_back((uint32_t)v_mb_cols.size());
+            } else n_simple++;
+        }
+        bflags.set(b, f);
+        body_col.set(b, bc);
+    }
+    n_multi = (uint32_t)v_mb_body.size();
+
+    CU(upload(mb_body, v_mb_body, stream)); CU(upload(mb_off, v_mb_off, stream)); CU(upload(mb_cols, v_mb_cols, stream));
+    CU(upload(sb_body, v_sb_body, stream)); CU(upload(sb_off, v_sb_off, stream)); CU(upload(sb_edge, v_sb_edge, stream));
+    CU(upload(isl_off, v_isl_off, stream)); CU(upload(isl_joint, v_isl_joint, stream));
+    CU(upload(d_springs, sp, stream)); CU(upload(d_joints, jp, stream));
+    CU(cudaStreamSynchronize(stream));  // the staging vectors above are locals
+    topo_dirty = false;
+    return BLOBS_OK;
+}
+
+int World::flush() {
+    const size_t nb = bodies.slots(), nc = cols.slots();
+    CU(pos.ensure(nb, stream)); CU(pos_old.ensure(nb, stream)); CU(acc.ensure(nb, stream)); CU(vel.ensure(nb, stream));
+    CU(vreq.ensure(nb, stream)); CU(has_vreq.ensure(nb, stream)); CU(rot.ensure(nb, stream)); CU(angvel.ensure(nb, stream));
+    CU(torque.ensure(nb, stream)); CU(cabs.ensure(nc, stream)); CU(ccell.ensure(nc, stream));
+    if (topo_dirty) {
+        int rc = rebuild_topology();
+        if (rc) return rc;
+    }
+    CU(mass.flush(stream)); CU(inertia.flush(stream)); CU(gmod.flush(stream)); CU(bflags.flush(stream)); CU(body_col.flush(stream));
+    CU(coff.flush(stream)); CU(crad.flush(stream)); CU(cgroups.flush(stream)); CU(cparent.flush(stream)); CU(cflags.flush(stream));
+    int rc = flush_writes();
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));  // Mirrored uploads read pageable host vectors
+    if (bp_dirty) {
+        rc = rebuild_broadphase();
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- broadphase
+int World::choose_grid(bool) {
+    const size_t nc = cols.slots();
+    float cs = bp_cell_override > 0.f ? bp_cell_override : (r_max > 0.f ? 2.0f * r_max : 1.0f);
+    if (!(cs > 0.f) || !std::isfinite(cs)) cs = 1.0f;
+    DeviceStats init{};
+    init.bb_min_x = init.bb_min_y = INT32_MAX;
+    init.bb_max_x = init.bb_max_y = INT32_MIN;
+    *h_stats = init;
+    CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
+    if (nc) {
+        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), cs, (uint32_t)nc, d_stats);
+        launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(h_stats, d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    long long ex = 1, ey = 1;
+    if (h_stats->bb_min_x <= h_stats->bb_max_x) {
+        ex = (long long)h_stats->bb_max_x - h_stats->bb_min_x + 1;
+        ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;
+    }
+    // a little slack so slow drift does not alias immediately; aliasing is harmless for correctness (toroidal table)
+    double W = (double)ex + std::max(4.0, ex / 16.0), H = (double)ey + std::max(4.0, ey / 16.0);
+    const double cap = std::max<double>(4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1));
+    if (W * H > cap) {
+        const double sc = std::sqrt(cap / (W * H));
+        W = std::max(1.0, std::floor(W * sc));
+        H = std::max(1.0, std::floor(H * sc));
+    }
+    grid.W = (uint32_t)W;
+    grid.H = (uint32_t)H;
+    grid.ncells = grid.W * grid.H;
+    grid.cell = cs;
+    grid.rmax = r_max;
+    bb[0] = h_stats->bb_min_x; bb[1] = h_stats->bb_min_y; bb[2] = h_stats->bb_max_x; bb[3] = h_stats->bb_max_y;
+    return BLOBS_OK;
+}
+
+int World::rebuild_broadphase() {
+    int rc = choose_grid(true);
+    if (rc) return rc;
+    const size_t nc = cols.slots();
+    const size_t tn = (size_t)grid.ncells + 1;
+    CU(tab_a.ensure(tn + SCAN_ITEMS, stream)); CU(tab_b.ensure(tn + SCAN_ITEMS, stream));
+    CU(rec_a.ensure(std::max<size_t>(nc, 1), stream)); CU(rec_b.ensure(std::max<size_t>(nc, 1), stream));
+    CU(scan_status.ensure(cdiv(tn, SCAN_TILE) + 1, stream));
+    CU(cudaMemsetAsync(tab_a.d, 0, tn * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(tab_b.d, 0, tn * sizeof(uint32_t), stream));
+    uint32_t* tab_next = cur_is_a ? tab_b.d : tab_a.d;
+    uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
+    Rec* rec_next = cur_is_a ? rec_b.d : rec_a.d;
+    if (nc) {
+        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), tab_next, (uint32_t)nc);
+        launches++;
+    }
+    if (++scan_epoch >= (1u << 30)) { scan_epoch = 1; CU(cudaMemsetAsync(scan_status.d, 0, scan_status.cap * sizeof(unsigned long long), stream)); }
+    k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch);
+    launches++;
+    if (nc) {
+        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), mass.d.d, tab_next, rec_next, (uint32_t)nc);
+        launches++;
+    }
+    CU(cudaGetLastError());
+    cur_is_a = !cur_is_a;
+    bp_dirty = false;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stepping
+template <class F>
+int World::timed(KClass k, F&& f) {
+    EvPair* ep = nullptr;
+    if (profiling) {
+        if (ev_used == ev_pool.size()) {
+            EvPair p{};
+            CU(cudaEventCreate(&p.a));
+            CU(cudaEventCreate(&p.b));
+            ev_pool.push_back(p);
+        }
+        ep = &ev_pool[ev_used++];
+        ep->k = k;
+        CU(cudaEventRecord(ep->a, stream));
+    }
+    f();
+    launches++;
+    if (ep) CU(cudaEventRecord(ep->b, stream));
+    CU(cudaGetLastError());
+    return BLOBS_OK;
+}
+
+int World::collect_profile() {
+    for (size_t i = 0; i < ev_used; ++i) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b));
+        prof_ms[ev_pool[i].k] += ms;
+        prof_launches[ev_pool[i].k]++;
+    }
+    ev_used = 0;
+    return BLOBS_OK;
+}
+
+int World::launch_substep(const SubstepParams& P) {
+    const BodyArrays B = body_arrays();
+    const ColliderArrays C = col_arrays();
+    const Constraints K = constraints_pod();
+    Broadphase bp;
+    bp.rec = cur_is_a ? rec_a.d : rec_b.d;
+    bp.tab = cur_is_a ? tab_a.d : tab_b.d;
+    bp.tab_next = cur_is_a ? tab_b.d : tab_a.d;
+    uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
+    Rec* rec_next = cur_is_a ? rec_b.d : rec_a.d;
+    Recording R;
+    R.mode = (uint32_t)rec_mode;
+    R.cap = (uint32_t)std::min<size_t>(rec_cap, 0xffffffffu);
+    R.count = d_rec_count;
+    R.pairs = rec_pairs.d;
+    R.vels = rec_vels.d;
+    const bool fused = allow_fused && n_joints_live == 0 && rec_mode != BLOBS_RECORD_EVENTS;
+    const bool ordered = contact_mode == 0;
+    last_fused = fused;
+    const uint32_t nb = P.n_bodies, nc = P.n_colliders;
+    int rc;
+    if (n_sb) {
+        rc = timed(KC_SPRINGS, [&] { k_springs<<<cdiv(n_sb, 128), 128, 0, stream>>>(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
+        if (rc) return rc;
+    }
+    if (nb) {
+        rc = timed(KC_MAIN, [&] {
+            const unsigned g = cdiv(nb, 256);
+            if (fused) {
+                if (ordered) k_main<true, true><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
+                else k_main<true, false><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
+            } else {
+                if (ordered) k_main<false, true><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
+                else k_main<false, false><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
+            }
+        });
+        if (rc) return rc;
+    }
+    if (n_multi) {
+        rc = timed(KC_MAIN, [&] {
+            const unsigned g = cdiv(n_multi, 128);
+            if (fused) {
+                if (ordered) k_multi<true, true><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                else k_multi<true, false><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+            } else {
+                if (ordered) k_multi<false, true><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                else k_multi<false, false><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+            }
+        });
+        if (rc) return rc;
+    }
+    if (!fused) {
+        if (n_islands && joint_iterations) {
+            rc = timed(KC_JOINTS, [&] { k_joints<<<cdiv(n_islands, 128), 128, 0, stream>>>(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
+            if (rc) return rc;
+        }
+        if (nb) {
+            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, d_stats, mb_off.d, mb_cols.d); });
+            if (rc) return rc;
+        }
+    }
+    const size_t tn = (size_t)grid.ncells + 1;
+    if (++scan_epoch >= (1u << 30)) { scan_epoch = 1; CU(cudaMemsetAsync(scan_status.d, 0, scan_status.cap * sizeof(unsigned long long), stream)); }
+    rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch); });
+    if (rc) return rc;
+    if (nc) {
+        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, mass.d.d, bp.tab_next, rec_next, nc); });
+        if (rc) return rc;
+    }
+    cur_is_a = !cur_is_a;
+    if (rec_mode && sub_recorded < d_sub_end.cap) {
+        CU(cudaMemcpyAsync(d_sub_end.d + sub_recorded, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+        sub_recorded++;
+    }
+    return BLOBS_OK;
+}
+
+// Physics::integrate (physics.rs:397-422)
+int World::integrate(uint32_t nsub, float delta) {
+    const float step_delta = delta / (float)nsub;
+    for (uint32_t i = 0; i < nsub; ++i) {
+        SubstepParams P;
+        P.dt = step_delta;
+        P.ratio_first = step_delta / old_dt;        // physics.rs:338
+        P.ratio_rest = step_delta / step_delta;     // every later body sees old_dt == dt (Q2)
+        P.first_dynamic = first_dynamic;
+        P.gx = gx;
+        P.gy = gy;
+        P.collisions_enabled = collisions_enabled ? 1u : 0u;
+        P.n_bodies = (uint32_t)bodies.slots();
+        P.n_colliders = (uint32_t)cols.slots();
+        int rc = launch_substep(P);
+        if (rc) return rc;
+        if (first_dynamic != NO_SLOT) old_dt = step_delta;  // physics.rs:339
+    }
+    return BLOBS_OK;
+}
+
+int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run) {
+    const size_t nc = cols.slots();
+    if (nc) {
+        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), grid.cell, (uint32_t)nc, d_stats);
+        launches++;
+    }
+    CU(cudaEventRecord(ev_step1, stream));
+    CU(cudaMemcpyAsync(h_stats, d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_step0, ev_step1);
+    if (profiling) { int rc = collect_profile(); if (rc) return rc; }
+    if (out) {
+        out->collisions = h_stats->collisions;
+        out->coincident_pairs = h_stats->coincident;
+        out->events_dropped = h_stats->rec_dropped;
+        out->nan_detected = h_stats->nan_flag;
+        out->steps_run = steps;
+        out->substeps_run = substeps_run;
+        out->list_overflow = h_stats->list_overflow;
+        out->gpu_ms = ms;
+    }
+    // table re-dimensioning: only when the snapshot outgrew (aliasing) or vastly undershoots the table
+    if (h_stats->bb_min_x <= h_stats->bb_max_x) {
+        const long long ex = (long long)h_stats->bb_max_x - h_stats->bb_min_x + 1, ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;
+        const double cap = std::max<double>(4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1));
+        const bool aliased = (ex > grid.W || ey > grid.H) && (double)grid.ncells < 0.5 * cap;
+        const bool oversized = (double)grid.W * grid.H > 4096.0 && ((double)ex * 3 < grid.W && (double)ey * 3 < grid.H);
+        if (aliased || oversized) bp_dirty = true;
+    }
+    if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");
+    return BLOBS_OK;
+}
+
+int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
+    if (collisions_enabled && use_spatial_hash && substeps > 0) return fail(BLOBS_ERR_SPATIAL_HASH, "spatial collisions not supported right now");
+    int rc = flush();
+    if (rc) return rc;
+    if (topo_error) return fail(topo_error, topo_error_msg);
+    DeviceStats init{};
+    init.bb_min_x = init.bb_min_y = INT32_MAX;
+    init.bb_max_x = init.bb_max_y = INT32_MIN;
+    *h_stats = init;
+    CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
+    CU(cudaEventRecord(ev_step0, stream));
+    shadow_valid = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        rc = integrate(substeps, (float)delta);  // physics.rs:80
+        if (rc) return rc;
+        time += delta;                           // physics.rs:81
+    }
+    return finish_stats(stats, n, n * substeps);
+}
+
+// Physics::fixed_step (physics.rs:84-99)
+int World::fixed_step(double frame_time, BlobsStepStats* stats) {
+    if (collisions_enabled && use_spatial_hash && substeps > 0) return fail(BLOBS_ERR_SPATIAL_HASH, "spatial collisions not supported right now");
+    int rc = flush();
+    if (rc) return rc;
+    if (topo_error) return fail(topo_error, topo_error_msg);
+    DeviceStats init{};
+    init.bb_min_x = init.bb_min_y = INT32_MAX;
+    init.bb_max_x = init.bb_max_y = INT32_MIN;
+    *h_stats = init;
+    CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
+    CU(cudaEventRecord(ev_step0, stream));
+    shadow_valid = false;
+    accumulator += frame_time;
+    const double delta = 1.0 / 60.0;
+    int max_steps = 3;
+    uint32_t n = 0;
+    while (accumulator >= delta && max_steps > 0) {
+        rc = integrate(substeps, (float)delta);
+        if (rc) return rc;
+        accumulator -= delta;
+        time += delta;
+        max_steps -= 1;
+        n++;
+    }
+    return finish_stats(stats, n, n * substeps);
+}
+
+// ---------------------------------------------------------------------------------------------- bulk IO
+int World::download_bodies(BlobsBodyState* st, uint64_t* handles, size_t cap) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, bodies.slots());
+    std::vector<float2> p(n), po(n), a(n), v(n), vr(n);
+    std::vector<float> r(n), w(n), t(n);
+    std::vector<uint8_t> hv(n);
+    if (n && st) {
+        CU(cudaMemcpyAsync(p.data(), pos.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(po.data(), pos_old.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(a.data(), acc.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(v.data(), vel.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(vr.data(), vreq.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(r.data(), rot.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(w.data(), angvel.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(t.data(), torque.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(hv.data(), has_vreq.d, n, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    for (size_t s = 0; s < n; ++s) {
+        const bool alive = bodies.alive[s];
+        if (handles) handles[s] = alive ? bodies.handle_at((uint32_t)s) : 0;
+        if (!st) continue;
+        std::memset(&st[s], 0, sizeof(BlobsBodyState));
+        if (!alive) continue;
+        const HBody& b = hb[s];
+        BlobsBodyState& o = st[s];
+        o.position = {p[s].x, p[s].y}; o.position_old = {po[s].x, po[s].y}; o.acceleration = {a[s].x, a[s].y};
+        o.calculated_velocity = {v[s].x, v[s].y}; o.velocity_request = {vr[s].x, vr[s].y}; o.has_velocity_request = hv[s];
+        o.rotation = r[s]; o.angular_velocity = w[s]; o.torque = t[s];
+        o.center_of_mass = b.com; o.scale = b.scale;
+        o.calculated_mass = mass.h[s]; o.inertia = inertia.h[s]; o.gravity_mod = gmod.h[s];
+        o.body_type = b.type; o.user_data_lo = b.ud_lo; o.user_data_hi = b.ud_hi;
+    }
+    return BLOBS_OK;
+}
+
+int World::download_colliders(BlobsColliderState* st, uint64_t* handles, size_t cap) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, cols.slots());
+    std::vector<float2> a(n);
+    std::vector<float> r(bodies.slots());
+    if (n && st) {
+        CU(cudaMemcpyAsync(a.data(), cabs.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        if (!r.empty()) CU(cudaMemcpyAsync(r.data(), rot.d, r.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    for (size_t s = 0; s < n; ++s) {
+        const bool alive = cols.alive[s];
+        if (handles) handles[s] = alive ? cols.handle_at((uint32_t)s) : 0;
+        if (!st) continue;
+        std::memset(&st[s], 0, sizeof(BlobsColliderState));
+        if (!alive) continue;
+        st[s].desc = hc[s].desc;
+        st[s].desc.absolute_transform.translation = {a[s].x, a[s].y};
+        st[s].parent = hc[s].parent;
+    }
+    return BLOBS_OK;
+}
+
+int World::read_body_vec(int which, float* xy, size_t cap) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, bodies.slots());
+    if (!n) return BLOBS_OK;
+    const float2* src = which == 0 ? pos.d : vel.d;
+    CU(cudaMemcpyAsync(xy, src, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return BLOBS_OK;
+}
+
+int World::apply_forces(const float* f, size_t cap) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, bodies.slots());
+    if (!n) return BLOBS_OK;
+    CU(d_forces.ensure(n, stream));
+    CU(cudaMemcpyAsync(d_forces.d, f, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+    k_apply_forces<<<cdiv(n, 256), 256, 0, stream>>>(body_arrays(), d_forces.d, (uint32_t)n);
+    launches++;
+    CU(cudaGetLastError());
+    return BLOBS_OK;
+}
+
+int World::download_cell_coords(int32_t* cx, int32_t* cy, size_t cap) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, cols.slots());
+    if (!n) return BLOBS_OK;
+    CU(d_cellx.ensure(n, stream));
+    CU(d_celly.ensure(n, stream));
+    k_cell_coords<<<cdiv(n, 256), 256, 0, stream>>>(cabs.d, cell_size, (uint32_t)n, d_cellx.d, d_celly.d);
+    launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cx, d_cellx.d, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(cy, d_celly.d, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (size_t s = 0; s < n; ++s)
+        if (!cols.alive[s]) cx[s] = cy[s] = 0;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- recording
+int World::record_contacts(int mode, size_t cap) {
+    if (mode < 0 || mode > 2) return fail(BLOBS_ERR_INVALID, "bad record mode");
+    CU(cudaStreamSynchronize(stream));
+    rec_mode = mode;
+    rec_cap = mode ? std::max<size_t>(cap, 1) : 0;
+    if (mode) {
+        CU(rec_pairs.ensure(rec_cap, stream));
+        if (mode == BLOBS_RECORD_EVENTS) CU(rec_vels.ensure(rec_cap, stream));
+        CU(d_sub_end.ensure(8192, stream));
+    }
+    CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
+    sub_recorded = 0;
+    return BLOBS_OK;
+}
+
+int World::pairs_drain(uint32_t* a, uint32_t* b, size_t cap, size_t* n, uint64_t* sub_end, size_t sub_cap, size_t* n_sub) {
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_rec_count, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const size_t have = (size_t)std::min<unsigned long long>(cnt, rec_cap);
+    const size_t m = std::min(have, cap);
+    std::vector<uint2> tmp(m);
+    if (m) {
+        CU(cudaMemcpyAsync(tmp.data(), rec_pairs.d, m * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    for (size_t i = 0; i < m; ++i) {
+        if (a) a[i] = tmp[i].x;
+        if (b) b[i] = tmp[i].y;
+    }
+    if (n) *n = have;
+    const size_t ns = std::min<size_t>(sub_recorded, sub_cap);
+    if (sub_end && ns) {
+        std::vector<unsigned long long> se(ns);
+        CU(cudaMemcpyAsync(se.data(), d_sub_end.d, ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        for (size_t i = 0; i < ns; ++i) sub_end[i] = se[i];
+    }
+    if (n_sub) *n_sub = sub_recorded;
+    CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
+    sub_recorded = 0;
+    return BLOBS_OK;
+}
+
+int World::events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n) {
+    if (rec_mode != BLOBS_RECORD_EVENTS) return fail(BLOBS_ERR_INVALID, "event recording is not enabled");
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_rec_count, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const size_t have = (size_t)std::min<unsigned long long>(cnt, rec_cap);
+    const size_t m = std::min(have, cap);
+    std::vector<uint2> pr(m);
+    std::vector<float4> vl(m);
+    if (m) {
+        CU(cudaMemcpyAsync(pr.data(), rec_pairs.d, m * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(vl.data(), rec_vels.d, m * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    for (size_t i = 0; i < m; ++i) {
+        buf[i].col_handle_a = cols.handle_at(pr[i].x);
+        buf[i].col_handle_b = cols.handle_at(pr[i].y);
+        buf[i].impact_vel_a = {vl[i].x, vl[i].y};
+        buf[i].impact_vel_b = {vl[i].z, vl[i].w};
+    }
+    if (n) *n = have;
+    CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
+    sub_recorded = 0;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- introspection
+int World::kernel_info(BlobsKernelInfo* out) const {
+    out->launches = launches;
+    out->grid_w = grid.W;
+    out->grid_h = grid.H;
+    out->broadphase_cell = grid.cell;
+    out->r_max = r_max;
+    out->fused_path = last_fused ? 1u : 0u;
+    out->n_simple_bodies = n_simple;
+    out->n_multi_bodies = n_multi;
+    out->n_spring_bodies = n_sb;
+    out->n_islands = n_islands;
+    return BLOBS_OK;
+}
+
+int World::profile_enable(int on) {
+    CU(cudaStreamSynchronize(stream));
+    profiling = on != 0;
+    ev_used = 0;
+    for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0.f; prof_launches[i] = 0; }
+    return BLOBS_OK;
+}
+
+int World::profile_read(float* ms, uint64_t* nl, size_t n) {
+    CU(cudaStreamSynchronize(stream));
+    int rc = collect_profile();
+    if (rc) return rc;
+    for (size_t i = 0; i < n && i < (size_t)KC_COUNT; ++i) {
+        if (ms) ms[i] = prof_ms[i];
+        if (nl) nl[i] = prof_launches[i];
+    }
+    return BLOBS_OK;
+}
+
+}  // namespace blobs

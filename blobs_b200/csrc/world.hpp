@@ -1,0 +1,316 @@
+// Host side of libblobs_b200: the GPU-resident replacement for the reference's `Physics` struct
+// (blobs/src/physics.rs:3-34). Bodies and colliders live in slot-indexed SoA arrays in HBM; the host keeps
+// the thunderdome-compatible arenas (slot, generation, LIFO free list) plus the topology (who is whose parent,
+// springs, joints) and everything that only changes through the API.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/blobs_b200.h"
+#include "types.cuh"
+
+namespace blobs {
+
+// thunderdome::Arena bookkeeping (iteration = ascending slot, LIFO reuse, generation bump on reuse)
+struct HostArena {
+    std::vector<uint32_t> gen;
+    std::vector<uint8_t> alive;
+    std::vector<int64_t> next_free;
+    int64_t first_free = -1;
+    size_t len = 0;
+
+    uint64_t insert() {
+        len++;
+        if (first_free >= 0) {
+            const uint32_t s = (uint32_t)first_free;
+            first_free = next_free[s];
+            uint32_t g = gen[s] + 1;
+            if (g == 0) g = 1;
+            gen[s] = g;
+            alive[s] = 1;
+            return ((uint64_t)g << 32) | s;
+        }
+        gen.push_back(1);
+        alive.push_back(1);
+        next_free.push_back(-1);
+        return (1ull << 32) | (uint32_t)(gen.size() - 1);
+    }
+    bool valid(uint64_t h) const {
+        const uint32_t s = (uint32_t)h;
+        return s < gen.size() && alive[s] && gen[s] == (uint32_t)(h >> 32) && (h >> 32) != 0;
+    }
+    void remove_slot(uint32_t s) {
+        alive[s] = 0;
+        next_free[s] = first_free;
+        first_free = s;
+        len--;
+    }
+    void clear() {  // Arena::clear == drain
+        for (uint32_t s = 0; s < gen.size() && len > 0; ++s)
+            if (alive[s]) remove_slot(s);
+    }
+    size_t slots() const { return gen.size(); }
+    uint64_t handle_at(uint32_t s) const { return ((uint64_t)gen[s] << 32) | s; }
+};
+
+template <class T>
+struct DevBuf {
+    T* d = nullptr;
+    size_t cap = 0;
+    // grows geometrically, preserving contents; new tail is zero-filled
+    cudaError_t ensure(size_t n, cudaStream_t st) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 256;
+        while (ncap < n) ncap *= 2;
+        T* nd = nullptr;
+        cudaError_t e = cudaMalloc(&nd, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (cap) {
+            e = cudaMemcpyAsync(nd, d, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaMemsetAsync(nd + cap, 0, (ncap - cap) * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        if (d) {
+            cudaStreamSynchronize(st);
+            cudaFree(d);
+        }
+        d = nd;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (d) cudaFree(d);
+        d = nullptr;
+        cap = 0;
+    }
+};
+
+// host-authoritative array with a device copy; set() tracks a dirty range, flush() uploads it
+template <class T>
+struct Mirrored {
+    std::vector<T> h;
+    DevBuf<T> d;
+    size_t lo = SIZE_MAX, hi = 0;
+    void resize(size_t n, T fill = T{}) {
+        if (n > h.size()) {
+            const size_t old = h.size();
+            h.resize(n, fill);
+            mark(old, n);
+        }
+    }
+    void set(size_t i, const T& v) {
+        if (std::memcmp(&h[i], &v, sizeof(T)) != 0) {
+            h[i] = v;
+            mark(i, i + 1);
+        }
+    }
+    void mark(size_t a, size_t b) {
+        if (a < lo) lo = a;
+        if (b > hi) hi = b;
+    }
+    cudaError_t flush(cudaStream_t st) {
+        cudaError_t e = d.ensure(h.size(), st);
+        if (e != cudaSuccess) return e;
+        if (lo < hi) {
+            e = cudaMemcpyAsync(d.d + lo, h.data() + lo, (hi - lo) * sizeof(T), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        lo = SIZE_MAX;
+        hi = 0;
+        return cudaSuccess;
+    }
+};
+
+struct HBody {
+    std::vector<uint64_t> colliders;   // rbd.colliders (each handle twice)
+    std::vector<uint64_t> joints;      // rbd.connected_joints
+    std::vector<uint32_t> cols;        // distinct live collider slots whose parent is this body
+    uint64_t ud_lo = 0, ud_hi = 0;
+    BlobsVec2 scale{1.f, 1.f}, com{0.f, 0.f};
+    uint32_t type = 0;
+    bool rot_active = false;
+    uint32_t n_springs = 0, n_joints = 0;
+};
+
+struct HCollider {
+    BlobsColliderDesc desc;
+    uint64_t parent = 0;
+};
+
+struct HSpring { uint64_t a, b; float rest, k, c; };
+struct HJoint { uint64_t a, b; BlobsVec2 aa, ab; float distance, target; };
+
+enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_COUNT };
+
+class World {
+   public:
+    explicit World(const BlobsParams& p);
+    ~World();
+    int init();
+
+    // API (see include/blobs_b200.h)
+    int reset();
+    int set_param(int id, double v);
+    int get_param(int id, double* out) const;
+    int body_insert(const BlobsBodyDesc& d, uint64_t* out);
+    int body_remove(uint64_t h);
+    int body_get(uint64_t h, BlobsBodyState* out);
+    int body_set(uint64_t h, const BlobsBodyState& s, uint32_t mask);
+    int body_translate(uint64_t h, BlobsVec2 off);
+    int body_apply_force(uint64_t h, BlobsVec2 f);
+    int body_colliders(uint64_t h, uint64_t* out, size_t cap, size_t* n) const;
+    int collider_insert(const BlobsColliderDesc& d, uint64_t parent, uint64_t* out);
+    int collider_remove(uint64_t h);
+    int collider_get(uint64_t h, BlobsColliderState* out);
+    int spring_insert(uint64_t a, uint64_t b, float rest, float k, float c, uint64_t* out);
+    int spring_remove(uint64_t h);
+    int joint_insert(uint64_t a, uint64_t b, BlobsVec2 aa, BlobsVec2 ab, float dist, uint64_t* out);
+    int joint_remove(uint64_t h);
+    int constraint_push(BlobsVec2 p, float r);
+    int constraint_clear();
+    int step(double delta, uint32_t n, BlobsStepStats* stats);
+    int fixed_step(double frame_time, BlobsStepStats* stats);
+    int download_bodies(BlobsBodyState* st, uint64_t* handles, size_t cap);
+    int download_colliders(BlobsColliderState* st, uint64_t* handles, size_t cap);
+    int read_body_vec(int which, float* xy, size_t cap);
+    int apply_forces(const float* f, size_t cap);
+    int download_cell_coords(int32_t* cx, int32_t* cy, size_t cap);
+    int record_contacts(int mode, size_t cap);
+    int events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n);
+    int pairs_drain(uint32_t* a, uint32_t* b, size_t cap, size_t* n, uint64_t* sub_end, size_t sub_cap, size_t* n_sub);
+    int kernel_info(BlobsKernelInfo* out) const;
+    int profile_enable(int on);
+    int profile_read(float* ms, uint64_t* launches, size_t n);
+
+    size_t body_slots() const { return bodies.slots(); }
+    size_t collider_slots() const { return cols.slots(); }
+    size_t body_count() const { return bodies.len; }
+    size_t collider_count() const { return cols.len; }
+    const char* last_error() const { return err.c_str(); }
+
+   private:
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what);
+    int flush();
+    int rebuild_topology();
+    int rebuild_broadphase();
+    int choose_grid(bool force);
+    int integrate(uint32_t substeps, float delta);
+    int launch_substep(const SubstepParams& P);
+    int finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run);
+    int ensure_shadow();
+    void update_mass_and_inertia(uint32_t bslot);
+    BodyWrite& stage(uint32_t slot);
+    int flush_writes();
+    BodyArrays body_arrays();
+    ColliderArrays col_arrays();
+    Constraints constraints_pod() const;
+    template <class F>
+    int timed(KClass k, F&& f);
+    int collect_profile();
+
+    BlobsParams params;
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // pub fields of Physics
+    float gx = 0.f, gy = 0.f;
+    uint32_t substeps = 8, joint_iterations = 4;
+    bool use_spatial_hash = false, collisions_enabled = true;
+    double accumulator = 0.0, time = 0.0;
+    float old_dt = 1.0f;
+    float cell_size = 2.0f;         // spatial_hash.cell_size
+    float bp_cell_override = 0.0f;  // 0 = auto
+    int contact_mode = 0;           // 0 ordered, 1 fast
+    bool allow_fused = true;
+    std::vector<BlobsVec2> con_pos;
+    std::vector<float> con_r;
+
+    // arenas + host records
+    HostArena bodies, cols, springs, joints;
+    std::vector<HBody> hb;
+    std::vector<HCollider> hc;
+    std::vector<HSpring> hs;
+    std::vector<HJoint> hj;
+
+    // host-authoritative device arrays
+    Mirrored<float> mass, inertia, gmod;
+    Mirrored<uint32_t> bflags;
+    Mirrored<int32_t> body_col;
+    Mirrored<float2> coff;
+    Mirrored<float> crad;
+    Mirrored<uint2> cgroups;
+    Mirrored<uint32_t> cparent, cflags;
+    // device-authoritative body state
+    DevBuf<float2> pos, pos_old, acc, vel, vreq, cabs;
+    DevBuf<uint8_t> has_vreq;
+    DevBuf<float> rot, angvel, torque;
+    DevBuf<uint2> ccell;
+    // staged writes
+    std::vector<BodyWrite> pending;
+    std::vector<int32_t> pending_idx;
+    std::vector<ColWrite> pending_col;
+    DevBuf<BodyWrite> d_pending;
+    DevBuf<ColWrite> d_pending_col;
+    // host shadow of pos/rot (valid between a sync point and the next step)
+    bool shadow_valid = false;
+    std::vector<float2> sh_pos;
+    std::vector<float> sh_rot;
+
+    // derived topology
+    bool topo_dirty = true, bp_dirty = true;
+    int topo_error = 0;
+    std::string topo_error_msg;
+    uint32_t first_dynamic = NO_SLOT;
+    float r_max = 0.f;
+    uint32_t n_simple = 0, n_multi = 0, n_sb = 0, n_islands = 0, n_springs_live = 0, n_joints_live = 0, n_active_cols = 0;
+    DevBuf<uint32_t> mb_body, mb_off, mb_cols, sb_body, sb_off, sb_edge, isl_off, isl_joint;
+    DevBuf<SpringParams> d_springs;
+    DevBuf<JointParams> d_joints;
+
+    // broadphase
+    GridDesc grid{1, 1, 1, 1.0f, 0.f};
+    DevBuf<Rec> rec_a, rec_b;
+    DevBuf<uint32_t> tab_a, tab_b;
+    bool cur_is_a = true;
+    DevBuf<unsigned long long> scan_status;
+    uint32_t scan_epoch = 0;
+    int bb[4] = {0, 0, 0, 0};
+    bool bb_valid = false;
+
+    // stats / recording
+    DeviceStats* d_stats = nullptr;
+    DeviceStats* h_stats = nullptr;  // pinned
+    int rec_mode = 0;
+    size_t rec_cap = 0;
+    DevBuf<uint2> rec_pairs;
+    DevBuf<float4> rec_vels;
+    unsigned long long* d_rec_count = nullptr;
+    DevBuf<unsigned long long> d_sub_end;
+    std::vector<uint64_t> sub_end_host;  // running pair counts per substep since last drain
+    uint32_t sub_recorded = 0;
+    bool last_fused = false;
+
+    // profiling
+    uint64_t launches = 0;
+    bool profiling = false;
+    struct EvPair { cudaEvent_t a, b; int k; };
+    std::vector<EvPair> ev_pool;
+    size_t ev_used = 0;
+    float prof_ms[KC_COUNT] = {0};
+    uint64_t prof_launches[KC_COUNT] = {0};
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+    DevBuf<float2> d_forces;
+    DevBuf<int> d_cellx, d_celly;
+};
+
+}  // namespace blobs

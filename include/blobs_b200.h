@@ -1,0 +1,251 @@
+/* blobs_b200.h — C ABI of libblobs_b200.so: the B200-native drop-in for the per-step hot path of
+ * darthdeus/blobs (`blobs::Physics::step`, reference file blobs/src/physics.rs).
+ *
+ * The reference has no FFI layer; its boundary is the public Rust surface of `Physics`
+ * (physics.rs:36-239), the builders (rigid_body.rs:302-401, collider.rs:211-284) and the handle
+ * types. Each entry point below names the reference item it replaces (file:line relative to the
+ * reference checkout). A thin Rust shim (rust/) maps these 1:1 back onto the
+ * reference's names so `Physics::step` stays a drop-in.
+ *
+ * Conventions: plain pointers and sizes only; every call returns a BlobsStatus (0 = OK) unless noted;
+ * descriptors are copied, no borrowed pointer survives a call; a world is owned by one host thread
+ * (the reference's Physics is !Send + !Sync, physics.rs:4). There is NO CPU fallback: if no CUDA
+ * device is usable, blobs_world_create fails with BLOBS_ERR_CUDA.
+ *
+ * Handles are thunderdome::Index::to_bits(): generation << 32 | slot; 0 is never a valid handle.
+ */
+#ifndef BLOBS_B200_H
+#define BLOBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLOBS_ABI_VERSION 1
+
+typedef struct BlobsWorld BlobsWorld;
+typedef uint64_t BlobsHandle;
+
+typedef enum BlobsStatus {
+    BLOBS_OK = 0,
+    BLOBS_ERR_STALE_HANDLE = 1,   /* Option::None in the reference (arena lookup failed) */
+    BLOBS_ERR_SAME_BODY = 2,      /* thunderdome get2_mut panic: identical indices (physics.rs:191-196, springs.rs:26-29) */
+    BLOBS_ERR_NAN = 3,            /* assert!(!n.is_nan()) physics.rs:293; rotation asserts physics.rs:471-474 */
+    BLOBS_ERR_CUDA = 4,           /* CUDA runtime failure; see blobs_last_error */
+    BLOBS_ERR_INVALID = 5,        /* bad argument */
+    BLOBS_ERR_SPATIAL_HASH = 6,   /* panic!("spatial collisions not supported right now") physics.rs:412 */
+    BLOBS_ERR_MASS = 7,           /* assert!(calculated_mass > 0.0) physics.rs:447-448 */
+    BLOBS_ERR_DANGLING = 8,       /* spring/joint references a removed body: unwrap() panic physics.rs:427-432, springs.rs:26-29 */
+    BLOBS_ERR_CAPACITY = 9
+} BlobsStatus;
+
+typedef struct BlobsVec2 { float x, y; } BlobsVec2;
+
+/* glam::Affine2, column-major like glam: matrix2.x_axis, matrix2.y_axis, translation */
+typedef struct BlobsAffine2 { BlobsVec2 x_axis, y_axis, translation; } BlobsAffine2;
+
+/* RigidBodyType, rigid_body.rs:221-242 */
+enum { BLOBS_BODY_DYNAMIC = 0, BLOBS_BODY_STATIC = 1, BLOBS_BODY_KINEMATIC_POSITION = 2, BLOBS_BODY_KINEMATIC_VELOCITY = 3 };
+
+/* Physics::new(gravity, use_spatial_hash), physics.rs:37-69; defaults physics.rs:46-47,62-67 */
+typedef struct BlobsParams {
+    BlobsVec2 gravity;
+    int32_t use_spatial_hash;    /* kept for API parity; stepping with it set returns BLOBS_ERR_SPATIAL_HASH */
+    int32_t device;              /* CUDA device ordinal, -1 = current */
+    uint32_t body_capacity_hint; /* 0 = grow on demand */
+    uint32_t collider_capacity_hint;
+} BlobsParams;
+
+/* Runtime knobs that are `pub` fields on Physics (physics.rs:6-33) */
+typedef enum BlobsParamId {
+    BLOBS_PARAM_GRAVITY_X = 0,
+    BLOBS_PARAM_GRAVITY_Y = 1,
+    BLOBS_PARAM_SUBSTEPS = 2,            /* physics.rs:8  (default 8) */
+    BLOBS_PARAM_JOINT_ITERATIONS = 3,    /* physics.rs:9  (default 4) */
+    BLOBS_PARAM_USE_SPATIAL_HASH = 4,    /* physics.rs:20 */
+    BLOBS_PARAM_COLLISIONS_ENABLED = 5,  /* physics.rs:27 */
+    BLOBS_PARAM_ACCUMULATOR = 6,         /* physics.rs:30 */
+    BLOBS_PARAM_TIME = 7,                /* physics.rs:31 */
+    BLOBS_PARAM_OLD_DT = 8,              /* physics.rs:33 */
+    BLOBS_PARAM_CELL_SIZE = 9,           /* spatial_hash.cell_size, spatial.rs:32 (default 2.0, physics.rs:66) */
+    BLOBS_PARAM_BROADPHASE_CELL = 10,    /* GPU grid cell edge; 0 = auto (2 * max collider radius) */
+    BLOBS_PARAM_CONTACT_MODE = 11,       /* 0 = ordered (bit-exact summation order), 1 = fast (unordered) */
+    BLOBS_PARAM_FUSED = 12               /* 1 = allow the fused contact+verlet kernel (default), 0 = force split kernels */
+} BlobsParamId;
+
+/* RigidBodyBuilder, rigid_body.rs:287-401 */
+typedef struct BlobsBodyDesc {
+    BlobsVec2 position;
+    BlobsVec2 position_old;
+    float gravity_mod;
+    float rotation;
+    BlobsVec2 scale;
+    BlobsVec2 acceleration;
+    BlobsVec2 velocity_request;
+    BlobsVec2 calculated_velocity;
+    int32_t has_velocity_request;
+    uint32_t body_type;
+    uint64_t user_data_lo, user_data_hi;
+} BlobsBodyDesc;
+
+/* RigidBody, rigid_body.rs:41-74 (all fields are pub in the reference) */
+typedef struct BlobsBodyState {
+    BlobsVec2 position;
+    BlobsVec2 position_old;
+    BlobsVec2 center_of_mass;
+    BlobsVec2 scale;
+    BlobsVec2 acceleration;
+    BlobsVec2 velocity_request;
+    BlobsVec2 calculated_velocity;
+    float calculated_mass;
+    float gravity_mod;
+    float rotation;
+    float angular_velocity;
+    float torque;
+    float inertia;
+    int32_t has_velocity_request;
+    uint32_t body_type;
+    uint64_t user_data_lo, user_data_hi;
+} BlobsBodyState;
+
+/* field mask for blobs_body_set (the reference mutates through get_mut_rbd, physics.rs:109-111) */
+enum {
+    BLOBS_BODY_POSITION = 1u << 0,
+    BLOBS_BODY_POSITION_OLD = 1u << 1,
+    BLOBS_BODY_ACCELERATION = 1u << 2,
+    BLOBS_BODY_VELOCITY_REQUEST = 1u << 3,  /* set_velocity, rigid_body.rs:182-184 */
+    BLOBS_BODY_CALC_VELOCITY = 1u << 4,
+    BLOBS_BODY_ROTATION = 1u << 5,
+    BLOBS_BODY_ANGULAR_VELOCITY = 1u << 6,
+    BLOBS_BODY_TORQUE = 1u << 7,
+    BLOBS_BODY_MASS = 1u << 8,
+    BLOBS_BODY_INERTIA = 1u << 9,
+    BLOBS_BODY_GRAVITY_MOD = 1u << 10,
+    BLOBS_BODY_TYPE = 1u << 11,
+    BLOBS_BODY_USER_DATA = 1u << 12,
+    BLOBS_BODY_SCALE = 1u << 13,
+    BLOBS_BODY_CENTER_OF_MASS = 1u << 14,
+    BLOBS_BODY_ALL = 0x7fffu
+};
+
+/* ColliderBuilder, collider.rs:199-284. Shapes: only Ball exists in the reference (lib.rs:49-74). */
+typedef struct BlobsColliderDesc {
+    BlobsAffine2 offset;
+    BlobsAffine2 absolute_transform;
+    float radius;
+    float mass_override;
+    float shape_radius;          /* Ball::radius of `shape` (debug/AABB only, lib.rs:61-67) */
+    int32_t has_mass_override;
+    int32_t is_sensor;
+    uint32_t memberships, filter; /* InteractionGroups, groups.rs:7-12 */
+    uint64_t user_data_lo, user_data_hi;
+} BlobsColliderDesc;
+
+typedef struct BlobsColliderState {
+    BlobsColliderDesc desc;      /* absolute_transform is the live snapshot (physics.rs:360-366) */
+    BlobsHandle parent;          /* 0 = None */
+} BlobsColliderState;
+
+/* CollisionEvent, lib.rs:146-153 (sent once per contact per substep, physics.rs:304-311) */
+typedef struct BlobsCollisionEvent {
+    BlobsHandle col_handle_a, col_handle_b;
+    BlobsVec2 impact_vel_a, impact_vel_b;
+} BlobsCollisionEvent;
+
+typedef struct BlobsStepStats {
+    uint64_t collisions;        /* perf_counter_inc("collisions", count), physics.rs:316 — summed over substeps */
+    uint64_t coincident_pairs;  /* pairs that took the distance < 1e-6 branch, physics.rs:272-286 */
+    uint64_t events_dropped;    /* events/pairs that did not fit the recording buffer */
+    uint32_t nan_detected;      /* non-zero: a position/normal became NaN (reference would have panicked) */
+    uint32_t steps_run;         /* integrate() calls performed (fixed_step: 0..3, physics.rs:88-98) */
+    uint32_t substeps_run;
+    uint32_t list_overflow;     /* contact lists that exceeded the in-register capacity and took the rescan path */
+    float gpu_ms;               /* CUDA-event time of the kernels of this call */
+} BlobsStepStats;
+
+/* ---- world lifetime ------------------------------------------------------------------------ */
+int32_t blobs_abi_version(void);
+int32_t blobs_world_create(const BlobsParams* params, BlobsWorld** out);      /* Physics::new physics.rs:37 */
+int32_t blobs_world_destroy(BlobsWorld* w);
+int32_t blobs_world_reset(BlobsWorld* w);                                     /* Physics::reset physics.rs:71-76 */
+const char* blobs_last_error(const BlobsWorld* w);                            /* panic/expect message equivalent */
+int32_t blobs_world_set_param(BlobsWorld* w, int32_t id, double value);       /* pub fields physics.rs:6-33 */
+int32_t blobs_world_get_param(const BlobsWorld* w, int32_t id, double* out);
+
+/* ---- bodies ---------------------------------------------------------------------------------- */
+int32_t blobs_body_insert(BlobsWorld* w, const BlobsBodyDesc* desc, BlobsHandle* out);          /* insert_rbd physics.rs:121-128 */
+int32_t blobs_body_insert_many(BlobsWorld* w, size_t n, const BlobsBodyDesc* descs, BlobsHandle* out); /* n x insert_rbd */
+int32_t blobs_body_remove(BlobsWorld* w, BlobsHandle h);                                       /* remove_rbd physics.rs:163-172 */
+int32_t blobs_body_get(BlobsWorld* w, BlobsHandle h, BlobsBodyState* out);                      /* get_rbd physics.rs:105-107 */
+int32_t blobs_body_set(BlobsWorld* w, BlobsHandle h, const BlobsBodyState* s, uint32_t mask);   /* get_mut_rbd physics.rs:109-111 */
+int32_t blobs_body_count(const BlobsWorld* w, uint64_t* out);                                   /* rbd_count physics.rs:113-115 */
+int32_t blobs_body_translate(BlobsWorld* w, BlobsHandle h, BlobsVec2 offset);                   /* update_rigid_body_position physics.rs:174-182 */
+int32_t blobs_body_apply_force(BlobsWorld* w, BlobsHandle h, BlobsVec2 force);                  /* RigidBody::apply_force rigid_body.rs:155-160 */
+int32_t blobs_body_colliders(const BlobsWorld* w, BlobsHandle h, BlobsHandle* out, size_t cap, size_t* n); /* rbd.colliders (each handle appears twice) */
+
+/* ---- colliders --------------------------------------------------------------------------------- */
+int32_t blobs_collider_insert(BlobsWorld* w, const BlobsColliderDesc* desc, BlobsHandle parent, BlobsHandle* out); /* insert_collider_with_parent physics.rs:130-149 */
+int32_t blobs_collider_insert_many(BlobsWorld* w, size_t n, const BlobsColliderDesc* descs, const BlobsHandle* parents, BlobsHandle* out);
+int32_t blobs_collider_remove(BlobsWorld* w, BlobsHandle h);                                   /* remove_col physics.rs:159-161 */
+int32_t blobs_collider_get(BlobsWorld* w, BlobsHandle h, BlobsColliderState* out);              /* get_col physics.rs:117-119 */
+int32_t blobs_collider_count(const BlobsWorld* w, uint64_t* out);
+
+/* ---- springs, joints, constraints ------------------------------------------------------------- */
+int32_t blobs_spring_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, float rest_length, float stiffness, float damping, BlobsHandle* out); /* physics.springs.insert(Spring{..}) springs.rs:16-22 */
+int32_t blobs_spring_remove(BlobsWorld* w, BlobsHandle h);
+/* create_fixed_joint (physics.rs:184-207) when distance is NaN, else create_fixed_joint_with_distance (physics.rs:209-239) */
+int32_t blobs_joint_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, BlobsVec2 anchor_a, BlobsVec2 anchor_b, float distance_or_nan, BlobsHandle* out);
+int32_t blobs_joint_remove(BlobsWorld* w, BlobsHandle h);
+int32_t blobs_constraint_push(BlobsWorld* w, BlobsVec2 position, float radius);                 /* physics.constraints.push(Constraint{..}) lib.rs:189-193 */
+int32_t blobs_constraint_clear(BlobsWorld* w);
+
+/* ---- stepping ----------------------------------------------------------------------------------- */
+int32_t blobs_step(BlobsWorld* w, double delta, BlobsStepStats* stats);             /* Physics::step physics.rs:78-82 */
+int32_t blobs_fixed_step(BlobsWorld* w, double frame_time, BlobsStepStats* stats);  /* Physics::fixed_step physics.rs:84-99 */
+/* n back-to-back step(delta) calls enqueued without host synchronisation in between (throughput path) */
+int32_t blobs_step_n(BlobsWorld* w, double delta, uint32_t n, BlobsStepStats* stats);
+
+/* ---- bulk state transfer (slot-indexed; slot = low 32 bits of the handle) --------------------- */
+int32_t blobs_body_slots(const BlobsWorld* w, uint64_t* out);      /* arena storage length, incl. free slots */
+int32_t blobs_collider_slots(const BlobsWorld* w, uint64_t* out);
+/* handles[s] = 0 for a free slot; either pointer may be NULL */
+int32_t blobs_download_bodies(BlobsWorld* w, BlobsBodyState* states, BlobsHandle* handles, size_t cap);
+int32_t blobs_download_colliders(BlobsWorld* w, BlobsColliderState* states, BlobsHandle* handles, size_t cap);
+/* raw SoA fast paths: xy interleaved, `cap` slots; host buffers may be pinned */
+int32_t blobs_read_body_positions(BlobsWorld* w, float* xy, size_t cap);
+int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap);
+int32_t blobs_apply_forces(BlobsWorld* w, const float* force_xy, size_t cap);  /* per-slot RigidBody::apply_force rigid_body.rs:155-160 */
+/* SpatialHash::get_cell_coords (spatial.rs:57-62) of every collider snapshot, with BLOBS_PARAM_CELL_SIZE */
+int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap);
+
+/* ---- contact output ------------------------------------------------------------------------------ */
+enum { BLOBS_RECORD_OFF = 0, BLOBS_RECORD_PAIRS = 1, BLOBS_RECORD_EVENTS = 2 };
+/* collision_send / collision_recv, physics.rs:22-23,304-311. PAIRS records slots only. */
+int32_t blobs_record_contacts(BlobsWorld* w, int32_t mode, size_t capacity);
+int32_t blobs_events_drain(BlobsWorld* w, BlobsCollisionEvent* buf, size_t cap, size_t* n);
+/* slot pairs (a > b) recorded since the last drain; substep_end[i] = running pair count after substep i */
+int32_t blobs_pairs_drain(BlobsWorld* w, uint32_t* slot_a, uint32_t* slot_b, size_t cap, size_t* n,
+                          uint64_t* substep_end, size_t substep_cap, size_t* n_substeps);
+
+/* ---- introspection used by bench.py / tests ---------------------------------------------------- */
+typedef struct BlobsKernelInfo {
+    uint64_t launches;          /* kernels of this library launched so far on this world */
+    uint32_t grid_w, grid_h;    /* broadphase table dims */
+    float broadphase_cell;
+    float r_max;
+    uint32_t fused_path;        /* 1 if the last step used the fused contact+verlet kernel */
+    uint32_t n_simple_bodies, n_multi_bodies, n_spring_bodies, n_islands;
+} BlobsKernelInfo;
+int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out);
+/* CUDA-event timing of individual kernel classes during the next steps (0 = off). Used for the roofline. */
+int32_t blobs_profile_enable(BlobsWorld* w, int32_t on);
+/* ms accumulated per kernel class since enable: [0]=main/contacts, [1]=scan, [2]=scatter, [3]=springs, [4]=joints, [5]=integrate, [6]=other */
+int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOBS_B200_H */

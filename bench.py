@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — sphere-steps/sec of the blobs::Physics::step hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2]
+
+A "step" is one Physics::step(1/60) (8 substeps) over a synthetic scene. At N=1 the workload is BASELINE
+config #2 (1 048 576 single-collider spheres in one world). Prints ONE JSON line (rank 0).
+
+Timing: `value` is device time (CUDA events recorded by the library on its own stream around each step's
+kernels), inputs resident in HBM, max over ranks; between timed steps a 256 MiB buffer is rewritten to flush L2
+(outside the per-step events). `e2e` is wall-clock through the public C ABI with per-step pinned-host -> device forces
+and device -> pinned-host positions inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "sphere_steps_per_sec"
+UNIT = "sphere-steps/s"
+DT = 1.0 / 60.0
+# Algorithmic bytes per collider-substep
+B_MAIN = 64 + 52      # fused contact + verlet + snapshot + clamp + key kernel (dominant)
+B_PIPELINE = 236      # whole substep
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2_varied", "cfg2_dense", "cfg4", "cfg2_4m", "cfg2_16m"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def make_scene(name, seed=1):
+    from blobs_b200 import scenes as S
+
+    if name == "cfg1":
+        return S.cfg1(seed), "cfg1: 1024 spheres r~U[0.05,0.2) in a circle constraint R=8"
+    if name == "cfg2":
+        return S.cfg2(seed), "cfg2: 1048576 single-collider spheres r=0.5, jittered lattice pitch 1.05, circle constraint R=800, g=(0,-30)"
+    if name == "cfg2_varied":
+        return S.cfg2(seed, varied=True), "cfg2 variant: 1048576 spheres r~U[0.25,0.5)"
+    if name == "cfg2_dense":
+        return S.cfg2_dense(seed, side=1024), "cfg2 dense variant: 1048576 spheres r=0.5 pitch 0.9 (overlapping) in a tight circle"
+    if name == "cfg2_4m":
+        return S.cfg2(seed, side=2048), "cfg2 scaled: 4194304 spheres"
+    if name == "cfg2_16m":
+        return S.cfg2(seed, side=4096), "cfg5 single-GPU form: 16777216 spheres in one world"
+    if name == "cfg4":
+        return S.cfg4(100_000, 16, seed), "cfg4: 100000 soft blobs x 16 bodies, fixed joints + springs"
+    raise ValueError(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if one exists."""
+    p = os.path.join(REPO, "profiles", "k_main_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
+
+
+def cpu_reference_sample(budget_s, steps_hint=None, warmup=0):
+    """Times the reference's own algorithm (brute-force O(C^2) Physics::step, CPU oracle = faithful restatement, 1 thread —
+    the reference is !Send) on a bounded sample of cfg2: a side x side sub-block of the same lattice."""
+    from blobs_b200 import scenes as S
+    from oracle import oracle_py
+
+    def run(side, steps, wu):
+        sc = S.cfg2(seed=1, side=side)
+        o = oracle_py.OracleWorld(gravity=sc.gravity, maintain_spatial_hash=True, record_events=True)
+        S.build(o, sc)
+        if wu:
+            o.step_n_timed(DT, wu)
+            o.events_drain(); o.pairs_drain()
+        secs = o.step_n_timed(DT, steps)
+        return sc.n_colliders, secs
+
+    # calibrate the pair-test rate on a tiny block
+    n0, s0 = run(32, 2, 0)
+    rate = (n0 * n0 / 2.0) * 8 * 2 / max(s0, 1e-6)  # pair tests / s
+    if steps_hint is None:
+        side, steps = 96, 1
+        per_step = (side * side) ** 2 / 2.0 * 8 / rate
+        steps = max(1, int(budget_s / max(per_step, 1e-6)))
+        steps = min(steps, 50)
+    else:
+        steps = steps_hint
+        per_step_budget = budget_s / max(1, steps + warmup)
+        c = (2.0 * per_step_budget * rate / 8.0) ** 0.5
+        side = int(max(16, min(128, c ** 0.5)))
+    n, secs = run(side, steps, warmup)
+    full = 1048576
+    return {
+        "value": n * steps / secs, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{n} spheres ({side}x{side} sub-block of the cfg2 lattice) x {steps} Physics::step(1/60), brute-force O(C^2) pair loop as in the "
+                  f"reference (physics.rs:241-317), single thread, {secs:.2f} s; host has {os.cpu_count()} cores; the reference cannot be built here "
+                  f"(Rust), so this is the C++ oracle restatement. O(C^2): at the full {full} spheres the same loop would run ~{full / n:.0f}x slower per sphere",
+        "pair_tests_per_s": rate,
+    }, n, steps, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, n, steps, secs = cpu_reference_sample(120.0, steps_hint=args.steps, warmup=args.warmup)
+    v = cb["value"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 (bounded sample): " + cb["sample"]},
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; blobs_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import blobs_b200
+    from blobs_b200 import scenes as S
+
+    # N > 1: one independent cfg2 world per rank (no data-path collective; "replicas", weak scaling).
+    sc, desc = make_scene(args.workload, seed=1 + rank)
+    w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
+    S.build(w, sc)
+    n = sc.n_colliders
+    nb = sc.n_bodies
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    w.step(DT, n=W)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    forces = torch.zeros((nb, 2), dtype=torch.float32).pin_memory()
+    forces[:, 0] = 0.05
+    pos_out = torch.zeros((nb, 2), dtype=torch.float32).pin_memory()
+
+    # ---- device-timed region -----------------------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    w.profile_enable(True)
+    l0 = w.kernel_info()["launches"]
+    t_dev_ms, collisions, overflow = 0.0, 0, 0
+    for _ in range(K):
+        if flush is not None:
+            flush.zero_()
+            torch.cuda.synchronize()
+        st = w.step(DT)
+        t_dev_ms += st["gpu_ms"]
+        collisions += st["collisions"]
+        overflow += st["list_overflow"]
+    barrier()
+    prof = w.profile_read()
+    w.profile_enable(False)
+    info = w.kernel_info()
+    launches = info["launches"] - l0
+    clocks = sampler.stop()
+
+    # ---- end-to-end region (public C ABI, host buffers, copies inside) ------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        w.apply_forces_ptr(forces.data_ptr(), nb)      # pinned host -> device
+        w.step(DT)
+        w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    checksum = float(pos_out[:, 1].double().mean())
+
+    t = torch.tensor([t_dev_ms, t_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n), float(collisions), float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    t_dev_ms, t_e2e = float(t[0]), float(t[1])
+    n_total, coll_total, launches_total = float(tot[0]), float(tot[1]), int(tot[2])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        main_ms, main_n = prof["main"]
+        substeps = int(w.get_param(blobs_b200.abi.PARAM_SUBSTEPS))
+        achieved = (B_MAIN * n / 1e9) / (main_ms / max(main_n, 1) / 1e3) if main_n else None
+        value = n_total * K / (t_dev_ms / 1e3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc + ("" if world == 1 else f"; one independent world per GPU ({world} replicas, no collective)"),
+                       "spheres_per_gpu": n, "substeps": substeps, "contact_mode": "ordered (bit-exact summation order)",
+                       "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
+                       "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
+                       "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow},
+            "clocks": clocks,
+            "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nb * 8, "d2h_bytes_per_step": nb * 8, "ms_per_step": t_e2e / K * 1e3,
+                    "checksum_mean_y": checksum},
+            "gpu_launches": launches_total,
+            "roofline": {"bound": "hbm", "kernel": "k_main<fused,ordered> (contacts + verlet + snapshot + clamp + cell binning)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": B_MAIN * n, "avg_launch_ms": main_ms / max(main_n, 1),
+                         "traffic": ncu_traffic()},
+            "pipeline": {"algorithmic_gbps": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9,
+                         "frac_of_peak": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9 / (peak * world),
+                         "sphere_substeps_per_sec": value * substeps,
+                         "kernel_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1]}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_sample(args.cpu_budget)[0]
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,7 +148,19 @@ BodyWrite& World::stage(uint32_t slot) {
     return pending[i];
 }
 
+int World::ensure_capacity() {
+    const size_t nb = bodies.slots(), nc = cols.slots();
+    CU(pos.ensure(nb, stream)); CU(pos_old.ensure(nb, stream)); CU(acc.ensure(nb, stream)); CU(vel.ensure(nb, stream));
+    CU(vreq.ensure(nb, stream)); CU(has_vreq.ensure(nb, stream)); CU(rot.ensure(nb, stream)); CU(angvel.ensure(nb, stream));
+    CU(torque.ensure(nb, stream)); CU(cabs.ensure(nc, stream)); CU(ccell.ensure(nc, stream));
+    return BLOBS_OK;
+}
+
 int World::flush_writes() {
+    if (!pending.empty() || !pending_col.empty()) {
+        int rc = ensure_capacity();
+        if (rc) return rc;
+    }
     if (!pending.empty()) {
         CU(d_pending.ensure(pending.size(), stream));
         CU(cudaMemcpyAsync(d_pending.d, pending.data(), pending.size() * sizeof(BodyWrite), cudaMemcpyHostToDevice, stream));
@@ -643,10 +655,10 @@ int World::rebuild_topology() {
 }
 
 int World::flush() {
-    const size_t nb = bodies.slots(), nc = cols.slots();
-    CU(pos.ensure(nb, stream)); CU(pos_old.ensure(nb, stream)); CU(acc.ensure(nb, stream)); CU(vel.ensure(nb, stream));
-    CU(vreq.ensure(nb, stream)); CU(has_vreq.ensure(nb, stream)); CU(rot.ensure(nb, stream)); CU(angvel.ensure(nb, stream));
-    CU(torque.ensure(nb, stream)); CU(cabs.ensure(nc, stream)); CU(ccell.ensure(nc, stream));
+    {
+        int rc0 = ensure_capacity();
+        if (rc0) return rc0;
+    }
     if (topo_dirty) {
         int rc = rebuild_topology();
         if (rc) return rc;

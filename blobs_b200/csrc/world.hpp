@@ -210,6 +210,7 @@ class World {
     void update_mass_and_inertia(uint32_t bslot);
     BodyWrite& stage(uint32_t slot);
     int flush_writes();
+    int ensure_capacity();
     BodyArrays body_arrays();
     ColliderArrays col_arrays();
     Constraints constraints_pod() const;

@@ -1,0 +1,341 @@
+"""Scene-level parity: the CUDA library (through its C ABI) against the CPU oracle on identical seeded scenes.
+
+Bars (BASELINE.json north_star / SURVEY §8d): contact pair sets per substep — exact set equality; cell coords — exact;
+positions / velocities — bit-exact in ordered mode (the GPU applies each body's contributions in the reference's
+pair-loop order); rotation of jointed bodies — 1e-5 relative (GPU atan2f/sincosf differ from libm by ulps)."""
+import numpy as np
+import pytest
+
+from blobs_b200 import _abi as A
+from blobs_b200 import scenes as S
+
+from .helpers import assert_bodies_bit_equal, bits, sphere
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(gravity, scene, grid_oracle=False, **gpu_kw):
+    import blobs_b200
+    from oracle import oracle_py
+
+    g = blobs_b200.World(gravity=gravity, **gpu_kw)
+    o = oracle_py.OracleWorld(gravity=gravity, grid_pairs=grid_oracle, maintain_spatial_hash=False, record_events=False)
+    hg = S.build(g, scene)
+    ho = S.build(o, scene)
+    for k in ("bodies", "colliders"):
+        assert np.array_equal(hg[k], ho[k]), "handle assignment must match thunderdome's"
+    return g, o
+
+
+def _compare_step(g, o, fields=("position", "position_old", "calculated_velocity", "acceleration")):
+    sg, hg = g.download_bodies()
+    so, ho = o.download_bodies()
+    assert np.array_equal(hg, ho)
+    assert_bodies_bit_equal(sg, so, fields)
+    cg, _ = g.download_colliders()
+    co, _ = o.download_colliders()
+    for c in ("x", "y"):
+        assert np.array_equal(bits(cg["desc"]["absolute_transform"]["translation"][c]), bits(co["desc"]["absolute_transform"]["translation"][c])), "snapshot"
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_cfg1_pairs_and_positions_every_substep(seed):
+    """cfg1 (1024 spheres, r~U[0.05,0.2), circle container) vs the brute-force oracle: pair set each substep, state each step."""
+    sc = S.cfg1(seed)
+    g, o = _pair(sc.gravity, sc)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 20)
+    n_pairs = 0
+    for step in range(40):
+        rg = g.step(1 / 60)
+        o.step(1 / 60)
+        pg, po = g.pairs_drain(), o.pairs_drain()
+        assert len(pg) == len(po) == 8
+        for s, (x, y) in enumerate(zip(pg, po)):
+            assert np.array_equal(x, y), f"pair set differs at step {step} substep {s}: gpu {len(x)} oracle {len(y)}"
+            n_pairs += len(x)
+        assert rg["events_dropped"] == 0 and rg["nan_detected"] == 0
+        _compare_step(g, o)
+    assert n_pairs > 1000, "scene must actually collide"
+    assert o.coincident_total() == 0
+    cxg, cyg = g.cell_coords()
+    cxo, cyo = o.cell_coords()
+    assert np.array_equal(cxg, cxo) and np.array_equal(cyg, cyo)
+    assert g.kernel_info()["fused_path"] == 1
+
+
+def test_cfg1_long_run_600_steps():
+    """600 steps of cfg1: still bit-identical to the reference path at the end; collision counter agrees."""
+    sc = S.cfg1(1)
+    g, o = _pair(sc.gravity, sc)
+    tot = 0
+    for _ in range(6):
+        tot += g.step(1 / 60, n=100)["collisions"]
+        o.step(1 / 60, n=100)
+    _compare_step(g, o)
+    assert tot == o.step(1 / 60, n=0)["collisions"]
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("varied", [False, True])
+def test_dense_pile_vs_grid_oracle(fused, varied):
+    """16k overlapping spheres squeezed by a tight circle (busy contacts + clamps) vs the cell-list oracle, fused and
+    split pipelines."""
+    sc = S.lattice_scene(128, 128, 0.9, (0.0, 0.0), 7, 0.25 if varied else 0.5, 0.5, jitter=0.08, vel_disc=2.0, constraint_r=52.0,
+                         name="dense", cell_size=1.0)
+    g, o = _pair(sc.gravity, sc, grid_oracle=True)
+    g.set_param(A.PARAM_FUSED, fused)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 22)
+    for step in range(6):
+        r = g.step(1 / 60)
+        o.step(1 / 60)
+        pg, po = g.pairs_drain(), o.pairs_drain()
+        for x, y in zip(pg, po):
+            assert np.array_equal(x, y)
+        _compare_step(g, o)
+    assert r["collisions"] > 8 * 20000
+    assert g.kernel_info()["fused_path"] == fused
+    cxg, cyg = g.cell_coords()
+    cxo, cyo = o.cell_coords()
+    assert np.array_equal(cxg, cxo) and np.array_equal(cyg, cyo)
+
+
+def test_fast_mode_within_tolerance():
+    """contact_mode=1 sums a body's contributions in arrival order instead of the reference's pair-loop order: differs only
+    by float re-association. Stated tolerance (BASELINE.json north_star): 1e-5 relative over 1 step, on a calm scene (the
+    cfg1 transient is chaotic and amplifies ulps within a few substeps)."""
+    sc = S.lattice_scene(32, 32, 0.38, (0.0, 0.0), 4, 0.1, 0.2, jitter=0.05, vel_disc=1.0, constraint_r=9.0, name="calm")
+    g, o = _pair(sc.gravity, sc)
+    g.set_param(A.PARAM_CONTACT_MODE, 1)
+    r = g.step(1 / 60)
+    o.step(1 / 60)
+    assert r["collisions"] > 100
+    sg, _ = g.download_bodies()
+    so, _ = o.download_bodies()
+    for c in ("x", "y"):
+        np.testing.assert_allclose(sg["position"][c], so["position"][c], rtol=1e-5, atol=1e-5)
+
+
+def test_multi_collider_bodies_and_filters():
+    """Bodies with 1..4 colliders (offsets, no rotation), sensors, group filters, a static body and a collider-less body."""
+    rng = np.random.default_rng(5)
+    nb = 600
+    b = A.body_descs(nb)
+    side = 25
+    b["position"]["x"] = (np.arange(nb) % side) * 0.8 + rng.uniform(-0.05, 0.05, nb)
+    b["position"]["y"] = (np.arange(nb) // side) * 0.8 + rng.uniform(-0.05, 0.05, nb)
+    b["position_old"] = b["position"]
+    b["body_type"][::37] = A.BODY_STATIC
+    b["gravity_mod"] = rng.uniform(0.5, 1.5, nb).astype(np.float32)
+    ncol = rng.integers(0, 5, nb)
+    parent = np.repeat(np.arange(nb), ncol)
+    nc = len(parent)
+    c = A.collider_descs(nc)
+    c["radius"] = rng.uniform(0.1, 0.3, nc).astype(np.float32)
+    c["offset"]["translation"]["x"] = rng.uniform(-0.3, 0.3, nc).astype(np.float32)
+    c["offset"]["translation"]["y"] = rng.uniform(-0.3, 0.3, nc).astype(np.float32)
+    c["absolute_transform"]["translation"]["x"] = b["position"]["x"][parent] + c["offset"]["translation"]["x"]
+    c["absolute_transform"]["translation"]["y"] = b["position"]["y"][parent] + c["offset"]["translation"]["y"]
+    c["is_sensor"][::11] = 1
+    c["memberships"][::7] = 0b01
+    c["filter"][::5] = 0b10
+    c["has_mass_override"][::13] = 1
+    c["mass_override"][::13] = 3.5
+    sc = S.Scene("multi", gravity=(0.0, -30.0))
+    sc.bodies, sc.colliders, sc.col_parent = b, c, parent
+    sc.constraints.append((10.0, 10.0, 14.0))
+    g, o = _pair(sc.gravity, sc)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 20)
+    assert g.kernel_info()["n_multi_bodies"] == 0  # topology is built lazily at the first step
+    tot = 0
+    for _ in range(25):
+        g.step(1 / 60)
+        o.step(1 / 60)
+        for x, y in zip(g.pairs_drain(), o.pairs_drain()):
+            assert np.array_equal(x, y)
+            tot += len(x)
+        _compare_step(g, o)
+    assert tot > 500
+    assert g.kernel_info()["n_multi_bodies"] > 100
+
+
+def test_rotating_multi_collider_within_tolerance():
+    """Rotation enters the snapshot through sincosf: tolerance-checked, 1e-5 relative after one step."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    ws = [blobs_b200.World(gravity=(0.0, -30.0)), oracle_py.OracleWorld(gravity=(0.0, -30.0), maintain_spatial_hash=False)]
+    for w in ws:
+        b = A.body_descs(2)
+        b["position"]["x"] = [0.0, 1.3]
+        b["position_old"] = b["position"]
+        b["rotation"] = [0.3, -1.1]
+        bh = w.insert_bodies(b)
+        c = A.collider_descs(4)
+        c["radius"] = 0.3
+        c["offset"]["translation"]["x"] = [0.4, -0.4, 0.4, -0.4]
+        par = np.array([0, 0, 1, 1])
+        rot = b["rotation"][par]
+        # absolute = body.transform() * offset, as a caller would pass it (the first contact pass uses the caller's snapshot)
+        c["absolute_transform"]["translation"]["x"] = np.cos(rot) * c["offset"]["translation"]["x"] + b["position"]["x"][par]
+        c["absolute_transform"]["translation"]["y"] = np.sin(rot) * c["offset"]["translation"]["x"] + b["position"]["y"][par]
+        w.insert_colliders(c, bh[par])
+        st = w.body_get(bh[0]).copy()
+        st["torque"] = 2.0
+        w.body_set(bh[0], st, A.BODY_TORQUE)
+    ws[0].step(1 / 60)
+    ws[1].step(1 / 60)
+    sg, _ = ws[0].download_bodies()
+    so, _ = ws[1].download_bodies()
+    for f in ("position", "calculated_velocity"):
+        for c_ in ("x", "y"):
+            np.testing.assert_allclose(sg[f][c_], so[f][c_], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sg["rotation"], so["rotation"], rtol=1e-6)
+    np.testing.assert_allclose(sg["angular_velocity"], so["angular_velocity"], rtol=1e-6)
+    cg, _ = ws[0].download_colliders()
+    co, _ = ws[1].download_colliders()
+    for c_ in ("x", "y"):
+        np.testing.assert_allclose(cg["desc"]["absolute_transform"]["translation"][c_], co["desc"]["absolute_transform"]["translation"][c_], rtol=1e-5, atol=1e-6)
+
+
+def test_soft_blobs_springs_and_joints():
+    """cfg4 at 64 blobs x 16 bodies: springs (Jacobi) + fixed joints (per-island Gauss-Seidel in slot order) + contacts.
+    Positions stay bit-exact (anchors are not rotated, so rotation never feeds back into positions); rotation is
+    tolerance-checked because of atan2f."""
+    sc = S.cfg4(n_blobs=64, k=16, seed=3)
+    g, o = _pair(sc.gravity, sc)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 20)
+    for step in range(20):
+        g.step(1 / 60)
+        o.step(1 / 60)
+        for x, y in zip(g.pairs_drain(), o.pairs_drain()):
+            assert np.array_equal(x, y)
+        _compare_step(g, o)
+    info = g.kernel_info()
+    assert info["n_islands"] == 64 and info["n_spring_bodies"] == 64 * 16 and info["fused_path"] == 0
+    sg, _ = g.download_bodies()
+    so, _ = o.download_bodies()
+    np.testing.assert_allclose(sg["rotation"], so["rotation"], rtol=1e-5, atol=1e-6)
+
+
+def test_removal_and_reinsert_mid_simulation():
+    """Arena semantics under churn: remove bodies/colliders mid-run, re-insert into recycled slots (generation bump)."""
+    sc = S.cfg1(2)
+    g, o = _pair(sc.gravity, sc)
+    ws = (g, o)
+    for w in ws:
+        w.step(1 / 60, n=3)
+    _, hb = g.download_bodies()
+    _, hc = g.download_colliders()
+    for w in ws:
+        for s in (5, 17, 300, 1023):
+            w.remove_body(hb[s])
+        for s in (40, 41):
+            w.remove_collider(hc[s])  # removes the orphaned parents as well
+        w.step(1 / 60, n=2)
+    _compare_step(g, o)
+    new = []
+    for w in ws:
+        new.append([sphere(w, (0.1 * i, 5.0 + 0.3 * i), r=0.15, velocity_request=(1.0, -2.0)) for i in range(4)])
+        w.step(1 / 60, n=5)
+    assert new[0] == new[1]
+    assert new[0][0][0] >> 32 == 2
+    _compare_step(g, o)
+    assert g.body_count() == o.body_count() == 1024 - 6 + 4
+
+
+def test_body_set_and_translate_between_steps():
+    sc = S.cfg1(3)
+    g, o = _pair(sc.gravity, sc)
+    _, hb = g.download_bodies()
+    for w in (g, o):
+        w.step(1 / 60)
+        st = w.body_get(hb[10]).copy()
+        st["position"]["x"] += np.float32(0.25)
+        st["velocity_request"]["x"], st["velocity_request"]["y"] = 2.0, 1.0
+        st["has_velocity_request"] = 1
+        w.body_set(hb[10], st, A.BODY_POSITION | A.BODY_VELOCITY_REQUEST)
+        w.body_translate(hb[11], (0.125, -0.5))
+        w.body_apply_force(hb[12], (3.0, 9.0))
+        st = w.body_get(hb[13]).copy()
+        st["body_type"] = A.BODY_STATIC
+        w.body_set(hb[13], st, A.BODY_TYPE)
+        w.apply_forces(np.tile(np.array([[0.5, 0.25]], dtype=np.float32), (1024, 1)))
+        w.step(1 / 60, n=2)
+    _compare_step(g, o)
+
+
+def test_far_outlier_aliases_harmlessly():
+    """A body far outside the table's extent wraps around the toroidal grid: still exact."""
+    sc = S.cfg1(1)
+    g, o = _pair(sc.gravity, sc)
+    for w in (g, o):
+        sphere(w, (1.0e6, -3.0e5), r=0.2, gravity_mod=0.0)
+        sphere(w, (1.0e6 + 0.3, -3.0e5), r=0.2, gravity_mod=0.0)
+        w.step(1 / 60, n=3)
+    _compare_step(g, o)
+
+
+def test_collisions_disabled_and_variable_delta():
+    """collisions_enabled=false (physics.rs:25-27) and a delta that changes between steps (Q2 applies to the first body only)."""
+    sc = S.cfg1(1)
+    g, o = _pair(sc.gravity, sc)
+    for w in (g, o):
+        w.set_param(A.PARAM_COLLISIONS_ENABLED, 0)
+        w.step(1 / 60)
+        w.step(1 / 30)
+        w.set_param(A.PARAM_COLLISIONS_ENABLED, 1)
+        w.set_param(A.PARAM_SUBSTEPS, 3)
+        w.step(1 / 50)
+    _compare_step(g, o)
+    assert np.float32(g.get_param(A.PARAM_OLD_DT)) == np.float32(o.get_param(A.PARAM_OLD_DT))
+
+
+def test_events_match_reference_channel():
+    """CollisionEvent stream (physics.rs:304-311): same (a, b) handles and pre-update velocities, as a multiset per step."""
+    sc = S.cfg1(1, n_side=16)
+    g, o = _pair(sc.gravity, sc)
+    g.record_contacts(A.RECORD_EVENTS, 1 << 18)
+    o2 = None
+    from oracle import oracle_py
+
+    o2 = oracle_py.OracleWorld(gravity=sc.gravity, maintain_spatial_hash=False, record_events=True)
+    S.build(o2, sc)
+    n = 0
+    for _ in range(30):
+        g.step(1 / 60)
+        o2.step(1 / 60)
+        eg, eo = g.events_drain(), o2.events_drain()
+        assert len(eg) == len(eo)
+        key = lambda e: np.lexsort((e["col_handle_b"], e["col_handle_a"]))
+        eg, eo = eg[key(eg)], eo[key(eo)]
+        assert eg.tobytes() == eo.tobytes()
+        n += len(eg)
+    assert n > 50
+
+
+def test_full_size_cfg2_one_step_vs_grid_oracle():
+    """BASELINE config #2 at full size (1 048 576 spheres): one step (8 substeps) vs the cell-list oracle, bit-exact, then
+    size-independent properties over more steps: determinism across two GPU runs and bounded penetration."""
+    sc = S.cfg2(seed=1)
+    g, o = _pair(sc.gravity, sc, grid_oracle=True)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 24)
+    g.step(1 / 60)
+    o.step(1 / 60)
+    for x, y in zip(g.pairs_drain(), o.pairs_drain()):
+        assert np.array_equal(x, y)
+    _compare_step(g, o)
+    cxg, cyg = g.cell_coords()
+    cxo, cyo = o.cell_coords()
+    assert np.array_equal(cxg, cxo) and np.array_equal(cyg, cyo)
+    g.record_contacts(A.RECORD_OFF, 0)
+    import blobs_b200
+
+    g2 = blobs_b200.World(gravity=sc.gravity)
+    S.build(g2, sc)
+    g2.step(1 / 60)
+    r1 = g.step(1 / 60, n=10)
+    r2 = g2.step(1 / 60, n=10)
+    assert r1["collisions"] == r2["collisions"] > 0 and r1["nan_detected"] == 0
+    p1, p2 = g.read_positions(), g2.read_positions()
+    assert p1.tobytes() == p2.tobytes(), "ordered mode must be run-to-run deterministic despite atomic binning"
+    assert np.isfinite(p1).all()

@@ -24,60 +24,66 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 __device__ __forceinline__ float vlen(float x, float y) { return __fsqrt_rn(fadd(fmul(x, x), fmul(y, y))); }
 
 // ------------------------------------------------------------------------------------------------
-// data layout
-// ------------------------------------------------------------------------------------------------
-
-// ------------------------------------------------------------------------------------------------
 // cell arithmetic — SpatialHash::get_cell_coords (spatial.rs:57-62): floor(x / cs) as i32.
 // __float2int_rd rounds toward -inf, saturates and maps NaN to 0 exactly like Rust's `as i32`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cell_coord(float v, float cs) { return __float2int_rd(fdiv(v, cs)); }
 // order-preserving int32 -> uint32, then modulo: a toroidal mapping where neighbouring cells stay neighbours
 __device__ __forceinline__ uint32_t ubias(int c) { return (uint32_t)c ^ 0x80000000u; }
+// Lemire fastmod: n % d for any 32-bit n, d with M = 2^64 / d + 1
+__device__ __forceinline__ uint32_t fastmod(uint32_t n, unsigned long long M, uint32_t d) {
+    return (uint32_t)__umul64hi(M * (unsigned long long)n, (unsigned long long)d);
+}
 __device__ __forceinline__ uint32_t cell_index(const GridDesc& g, int cx, int cy) {
-    return (ubias(cy) % g.H) * g.W + (ubias(cx) % g.W);
+    return fastmod(ubias(cy), g.MH, g.H) * g.W + fastmod(ubias(cx), g.MW, g.W);
 }
 
-// ------------------------------------------------------------------------------------------------
-// neighbourhood walk: calls f(const Rec&) for every record in the cells that can hold a partner of a
-// sphere at (x, y) with radius r. Coverage proof: a contact needs
-// fl(dist) < fl(ra+rb) which implies |xa-xb| < r + rmax in real arithmetic; the cell range is
-// computed from directed-rounding bounds of x -/+ (r + rmax), and cell_coord is monotonic.
-// ------------------------------------------------------------------------------------------------
-template <class F>
-__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, float x, float y, float r, F&& f) {
+__device__ __forceinline__ Rec make_rec(const float4 h, const float4 c) {
+    Rec r;
+    r.x = h.x; r.y = h.y; r.r = h.z; r.slot_sensor = __float_as_uint(h.w);
+    r.m = c.x; r.memb = __float_as_uint(c.y); r.filt = __float_as_uint(c.z); r.parent = __float_as_uint(c.w);
+    return r;
+}
+
+// Cell range that can hold a partner of a sphere at (x, y) with radius r, on the toroidal table.
+// Coverage proof: a contact needs fl(dist) < fl(ra+rb), which implies |xa-xb| < r + rmax in
+// real arithmetic; the range is computed from directed-rounding bounds of x -/+ (r + rmax) and cell_coord is monotonic.
+struct CellRange {
+    uint32_t c0, nx;   // first column (wrapped), number of columns (<= W)
+    uint32_t r0, ny;   // first row (wrapped), number of rows (<= H)
+};
+__device__ __forceinline__ CellRange cell_range(const GridDesc& g, float x, float y, float r) {
     const float reach = __fadd_ru(r, g.rmax);
     const int cx0 = cell_coord(__fsub_rd(x, reach), g.cell), cx1 = cell_coord(__fadd_ru(x, reach), g.cell);
     const int cy0 = cell_coord(__fsub_rd(y, reach), g.cell), cy1 = cell_coord(__fadd_ru(y, reach), g.cell);
+    CellRange R;
     // spans (>= 1); an empty/NaN range degenerates to one cell
-    uint32_t nx = (cx1 >= cx0) ? (uint32_t)cx1 - (uint32_t)cx0 + 1u : 1u;
-    uint32_t ny = (cy1 >= cy0) ? (uint32_t)cy1 - (uint32_t)cy0 + 1u : 1u;
-    uint32_t c0 = ubias(cx0) % g.W;
-    if (nx == 0u || nx >= g.W) { nx = g.W; c0 = 0; }
-    uint32_t r0 = ubias(cy0) % g.H;
-    if (ny == 0u || ny >= g.H) { ny = g.H; r0 = 0; }
-    const uint32_t n1 = min(nx, g.W - c0);  // cells before the row wraps
-    for (uint32_t j = 0; j < ny; ++j) {
-        uint32_t row = r0 + j;
-        if (row >= g.H) row -= g.H;
-        const uint32_t base = row * g.W;
-        uint32_t lo = __ldg(bp.tab + base + c0), hi = __ldg(bp.tab + base + c0 + n1);
-        for (uint32_t k = lo; k < hi; ++k) f(bp.rec[k]);
-        if (n1 < nx) {  // wrapped part of the row
-            lo = __ldg(bp.tab + base);
-            hi = __ldg(bp.tab + base + (nx - n1));
-            for (uint32_t k = lo; k < hi; ++k) f(bp.rec[k]);
-        }
-    }
+    R.nx = (cx1 >= cx0) ? (uint32_t)cx1 - (uint32_t)cx0 + 1u : 1u;
+    R.ny = (cy1 >= cy0) ? (uint32_t)cy1 - (uint32_t)cy0 + 1u : 1u;
+    R.c0 = fastmod(ubias(cx0), g.MW, g.W);
+    if (R.nx == 0u || R.nx >= g.W) { R.nx = g.W; R.c0 = 0; }
+    R.r0 = fastmod(ubias(cy0), g.MH, g.H);
+    if (R.ny == 0u || R.ny >= g.H) { R.ny = g.H; R.r0 = 0; }
+    return R;
 }
 
-__device__ __forceinline__ Rec load_rec(const Rec* p) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    float4 a = __ldg(q), b = __ldg(q + 1);
-    Rec r;
-    r.x = a.x; r.y = a.y; r.r = a.z; r.m = a.w;
-    r.memb = __float_as_uint(b.x); r.filt = __float_as_uint(b.y); r.parent = __float_as_uint(b.z); r.slot_sensor = __float_as_uint(b.w);
-    return r;
+// Generic neighbourhood walk: calls f(const Rec&) for every record in the range (any span, row/column wrap).
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, float x, float y, float r, F&& f) {
+    const CellRange R = cell_range(g, x, y, r);
+    const uint32_t n1 = min(R.nx, g.W - R.c0);  // cells before the row wraps
+    for (uint32_t j = 0; j < R.ny; ++j) {
+        uint32_t row = R.r0 + j;
+        if (row >= g.H) row -= g.H;
+        const uint32_t base = row * g.W;
+        uint32_t lo = __ldg(bp.tab + base + R.c0), hi = __ldg(bp.tab + base + R.c0 + n1);
+        for (uint32_t k = lo; k < hi; ++k) f(make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)));
+        if (n1 < R.nx) {  // wrapped part of the row
+            lo = __ldg(bp.tab + base);
+            hi = __ldg(bp.tab + base + (R.nx - n1));
+            for (uint32_t k = lo; k < hi; ++k) f(make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)));
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -149,17 +155,21 @@ __device__ __forceinline__ bool narrowphase(const SelfCol& s, const Rec& o, Cont
 
 // ------------------------------------------------------------------------------------------------
 // Ordered contact list. The reference adds contributions to a body in pair-loop order:
-// lexicographic (later slot, earlier slot). Key = later << 32 | earlier.
+// lexicographic (later slot, earlier slot). KEY = uint64 (later << 33 | earlier << 1 | bit) for bodies with several
+// colliders; for a single-collider body the order degenerates to ascending partner slot, so a uint32 key
+// (partner << 1 | bit) is enough. bit 0 orders the coincident push-out (physics.rs:275-276) just before the contact
+// push of the same pair.
 // ------------------------------------------------------------------------------------------------
 constexpr int LIST_CAP = 24;
 
+template <class KEY>
 struct ContactList {
-    unsigned long long key[LIST_CAP];
+    KEY key[LIST_CAP];
     float cx[LIST_CAP], cy[LIST_CAP];
     int n;
     bool overflow;
     __device__ __forceinline__ void clear() { n = 0; overflow = false; }
-    __device__ __forceinline__ void insert(unsigned long long k, float x, float y) {
+    __device__ __forceinline__ void insert(KEY k, float x, float y) {
         if (n == LIST_CAP) { overflow = true; return; }
         int i = n++;
         while (i > 0 && key[i - 1] > k) {
@@ -170,10 +180,16 @@ struct ContactList {
     }
 };
 
-__device__ __forceinline__ unsigned long long pair_key(uint32_t s, uint32_t o, bool coincident) {
+template <class KEY>
+__device__ __forceinline__ KEY pair_key(uint32_t s, uint32_t o, bool coincident);
+template <>
+__device__ __forceinline__ unsigned long long pair_key<unsigned long long>(uint32_t s, uint32_t o, bool coincident) {
     const uint32_t hi = s > o ? s : o, lo = s > o ? o : s;
-    // bit 0 orders the coincident push-out (physics.rs:275-276) just before the contact push of the same pair
     return ((unsigned long long)hi << 33) | ((unsigned long long)lo << 1) | (coincident ? 0ull : 1ull);
+}
+template <>
+__device__ __forceinline__ uint32_t pair_key<uint32_t>(uint32_t, uint32_t o, bool coincident) {
+    return (o << 1) | (coincident ? 0u : 1u);
 }
 
 __device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned int v) {
@@ -182,52 +198,113 @@ __device__ __forceinline__ void warp_add_u64(unsigned long long* dst, unsigned i
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
 }
 
+struct GatherOut {
+    float fx, fy;              // fast-mode running sum
+    unsigned int n_pairs, n_coinc;
+};
 
-// ------------------------------------------------------------------------------------------------
-// contact pass for one collider: gathers its ordered contributions into `list` (ordered mode) or sums them
-// directly (fast mode). Counts pairs once (from the later-slot side).
-// ------------------------------------------------------------------------------------------------
-template <bool ORDERED>
-__device__ __forceinline__ void gather_contacts(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList& list,
-                                                float& fx, float& fy, unsigned int& n_pairs, unsigned int& n_coinc,
-                                                const Recording& rec, const uint32_t* __restrict__ cparent_of_slot,
-                                                const float2* __restrict__ vel, DeviceStats* stats) {
-    for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& raw) {
-        const Rec o = load_rec(&raw);
-        Contact c;
-        if (!narrowphase(s, o, c)) return;
-        if (c.i_am_a) {
-            n_pairs++;
-            if (c.coincident) n_coinc++;
-            if (rec.mode) {
-                unsigned long long idx = atomicAdd(rec.count, 1ull);
-                if (idx < rec.cap) {
-                    rec.pairs[idx] = make_uint2(s.slot, c.other);
-                    if (rec.mode == 2u) {
-                        const float2 va = vel[s.body], vb = vel[o.parent];
-                        rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
-                    }
-                } else {
-                    atomicAdd(&stats->rec_dropped, 1ull);
+// One confirmed candidate: narrowphase, bookkeeping, ordered insert (or fast-mode sum).
+template <bool ORDERED, class KEY>
+__device__ __forceinline__ void take_candidate(const SelfCol& s, const Rec& o, ContactList<KEY>& list, GatherOut& out,
+                                               const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
+    Contact c;
+    if (!narrowphase(s, o, c)) return;
+    if (c.i_am_a) {  // the later slot reports the pair, once, as (a, b) (physics.rs:302-311)
+        out.n_pairs++;
+        if (c.coincident) out.n_coinc++;
+        if (rec.mode) {
+            const unsigned long long idx = atomicAdd(rec.count, 1ull);
+            if (idx < rec.cap) {
+                rec.pairs[idx] = make_uint2(s.slot, c.other);
+                if (rec.mode == 2u) {
+                    // calculated_velocity before this substep's update (physics.rs:288-289); event mode always runs the
+                    // split pipeline, so vel[] is not being rewritten concurrently
+                    const float2 va = vel[s.body], vb = vel[o.parent];
+                    rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
                 }
+            } else {
+                atomicAdd(&stats->rec_dropped, 1ull);
             }
         }
-        if (c.coincident) {
-            const float px = c.i_am_a ? 0.01f : -0.01f;
-            if (ORDERED) list.insert(pair_key(s.slot, c.other, true), px, 0.0f);
-            else fx = fadd(fx, px);
-        }
-        if (c.push) {
-            if (ORDERED) list.insert(pair_key(s.slot, c.other, false), c.cx, c.cy);
-            else { fx = fadd(fx, c.cx); fy = fadd(fy, c.cy); }
-        }
-    });
+    }
+    if (c.coincident) {
+        const float px = c.i_am_a ? 0.01f : -0.01f;
+        if (ORDERED) list.insert(pair_key<KEY>(s.slot, c.other, true), px, 0.0f);
+        else out.fx = fadd(out.fx, px);
+    }
+    if (c.push) {
+        if (ORDERED) list.insert(pair_key<KEY>(s.slot, c.other, false), c.cx, c.cy);
+        else { out.fx = fadd(out.fx, c.cx); out.fy = fadd(out.fy, c.cy); }
+    }
 }
 
-// Rare path when a body has more than LIST_CAP contributions: repeated selection of the next key in
-// order (k+1 neighbourhood scans, no storage). Applies directly to (px, py).
-__device__ __noinline__ void apply_contacts_rescan(const GridDesc& g, const Broadphase& bp, const SelfCol* cols, int ncols,
-                                                   float& px, float& py) {
+// Generic gather (any cell span): used by k_multi and as the slow path of gather_single.
+template <bool ORDERED, class KEY>
+__device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
+                                               GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
+    for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
+}
+
+// Latency-oriented gather for the common case (<= 3 rows, no column wrap): the six cell-table reads are issued together,
+// then candidates are streamed in batches of 4 hot halves (16 B: x, y, r, slot); a conservative squared-distance
+// prefilter decides which cold halves (mass, groups, parent) are fetched at all.
+// Prefilter soundness: contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > md*md*1.0001 implies sqrt(d2) > md*(1+4e-5),
+// which rounding (2^-24) cannot bring below md. NaNs fail the '>' and fall through to the exact test.
+template <bool ORDERED, class KEY>
+__device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
+                                              GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
+    const CellRange R = cell_range(g, s.x, s.y, s.r);
+    if (R.ny > 3u || R.c0 + R.nx > g.W) {
+        gather_generic<ORDERED, KEY>(g, bp, s, list, out, rec, vel, stats);
+        return;
+    }
+    uint32_t lo[3], cnt[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint32_t row = R.r0 + j;
+        if (row >= g.H) row -= g.H;
+        const bool valid = (uint32_t)j < R.ny;
+        const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
+        const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
+        lo[j] = a;
+        cnt[j] = b - a;
+    }
+    const uint32_t n0 = cnt[0], n01 = cnt[0] + cnt[1], total = n01 + cnt[2];
+    for (uint32_t base = 0; base < total; base += 4u) {
+        float4 h[4];
+        uint32_t kk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t t = base + i;
+            const uint32_t k = t < n0 ? lo[0] + t : (t < n01 ? lo[1] + (t - n0) : lo[2] + (t - n01));
+            kk[i] = k;
+            if (t < total) h[i] = __ldg(bp.hot + k);
+            else h[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(s.slot));  // reads as "self": skipped
+        }
+        unsigned int pass = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
+            const float dx = s.x - h[i].x, dy = s.y - h[i].y;
+            const float d2 = dx * dx + dy * dy;
+            const float md = s.r + h[i].z;
+            if (oslot != s.slot && !(d2 > md * md * 1.0001f)) pass |= 1u << i;
+        }
+        if (pass) {
+            float4 c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (pass & (1u << i)) c[i] = __ldg(bp.cold + kk[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (pass & (1u << i)) take_candidate<ORDERED, KEY>(s, make_rec(h[i], c[i]), list, out, rec, vel, stats);
+        }
+    }
+}
+
+// Rare path when a body has more than LIST_CAP contributions: repeated selection of the next key in order
+// (k+1 neighbourhood scans, no storage). Everything by value so the callers keep their state in registers.
+__device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase bp, const SelfCol* cols, int ncols, float px, float py) {
     bool have_last = false;
     unsigned long long last = 0;
     for (;;) {
@@ -235,17 +312,16 @@ __device__ __noinline__ void apply_contacts_rescan(const GridDesc& g, const Broa
         unsigned long long best = 0;
         float bx = 0.f, by = 0.f;
         for (int ci = 0; ci < ncols; ++ci) {
-            const SelfCol& s = cols[ci];
-            for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& raw) {
-                const Rec o = load_rec(&raw);
+            const SelfCol s = cols[ci];
+            for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
                 if (c.coincident) {
-                    const unsigned long long k = pair_key(s.slot, c.other, true);
+                    const unsigned long long k = pair_key<unsigned long long>(s.slot, c.other, true);
                     if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.i_am_a ? 0.01f : -0.01f; by = 0.f; }
                 }
                 if (c.push) {
-                    const unsigned long long k = pair_key(s.slot, c.other, false);
+                    const unsigned long long k = pair_key<unsigned long long>(s.slot, c.other, false);
                     if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.cx; by = c.cy; }
                 }
             });
@@ -256,6 +332,7 @@ __device__ __noinline__ void apply_contacts_rescan(const GridDesc& g, const Broa
         last = best;
         have_last = true;
     }
+    return make_float2(px, py);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -306,14 +383,15 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
     sy = py;
     rot_out = rot;
     for (int i = 0; i < K.n; ++i) {                              // physics.rs:377-395
-        const float tx = fsub(px, K.x[i]), ty = fsub(py, K.y[i]);
+        const float4 k = __ldg(K.c + i);                         // (x, y, radius, -)
+        const float tx = fsub(px, k.x), ty = fsub(py, k.y);
         const float d = vlen(tx, ty);
-        if (d > K.r[i]) {
-            px = fadd(K.x[i], fmul(fdiv(tx, d), K.r[i]));
-            py = fadd(K.y[i], fmul(fdiv(ty, d), K.r[i]));
+        if (d > k.z) {
+            px = fadd(k.x, fmul(fdiv(tx, d), k.z));
+            py = fadd(k.y, fmul(fdiv(ty, d), k.z));
         }
     }
-    if (px != px || py != py) stats->nan_flag = 1u;
+    if (px != px || py != py) atomicOr(&stats->nan_flag, 1u);
     B.pos[b] = make_float2(px, py);
 }
 
@@ -338,53 +416,58 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
 // Handles bodies with zero or one collider; multi-collider bodies go to k_multi.
 // ------------------------------------------------------------------------------------------------
 template <bool FUSED, bool ORDERED>
-__global__ void __launch_bounds__(256) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+__global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                               Broadphase bp, Recording rec, DeviceStats* stats) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int n_pairs = 0, n_coinc = 0, n_over = 0;
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
+    unsigned int n_over = 0;
     if (b < P.n_bodies) {
         const uint32_t flags = B.bflags[b];
         const int32_t col = B.body_col[b];
         if ((flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
             float2 p = B.pos[b];
-            if (col >= 0 && P.collisions_enabled) {
+            bool active_col = false;
+            if (col >= 0) {
                 const uint32_t c = (uint32_t)col;
                 const uint32_t cf = Cc.cflags[c];
-                if (cf & CF_ACTIVE) {
+                active_col = (cf & CF_ACTIVE) != 0u;
+                if (active_col && P.collisions_enabled) {
                     SelfCol s;
                     const float2 a = Cc.cabs[c];
                     const uint2 gr = Cc.cgroups[c];
                     s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = B.mass[b];
                     s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
-                    ContactList list;
+                    ContactList<uint32_t> list;
                     list.clear();
-                    float fx = 0.f, fy = 0.f;
-                    gather_contacts<ORDERED>(g, bp, s, list, fx, fy, n_pairs, n_coinc, rec, Cc.cparent, B.vel, stats);
+                    gather_single<ORDERED, uint32_t>(g, bp, s, list, out, rec, B.vel, stats);
                     if (ORDERED) {
                         if (!list.overflow) {
                             for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
                         } else {
                             n_over = 1;
-                            apply_contacts_rescan(g, bp, &s, 1, p.x, p.y);
+                            SelfCol s2 = s;  // stack copy only on this rare path
+                            p = apply_contacts_rescan(g, bp, &s2, 1, p.x, p.y);
                         }
                     } else {
-                        p.x = fadd(p.x, fx);
-                        p.y = fadd(p.y, fy);
+                        p.x = fadd(p.x, out.fx);
+                        p.y = fadd(p.y, out.fy);
                     }
                 }
             }
             if (FUSED) {
                 float sx, sy, rot;
                 integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
-                if (col >= 0 && (Cc.cflags[col] & CF_ACTIVE)) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, sx, sy, rot);
+                if (active_col) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, sx, sy, rot);
             } else {
                 B.pos[b] = p;
             }
         }
     }
-    warp_add_u64(&stats->collisions, n_pairs);
-    if (__any_sync(0xffffffffu, n_coinc | n_over)) {
-        warp_add_u64(&stats->coincident, n_coinc);
+    warp_add_u64(&stats->collisions, out.n_pairs);
+    if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, out.n_coinc);
         unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
         if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
     }
@@ -394,7 +477,17 @@ __global__ void __launch_bounds__(256) k_main(SubstepParams P, GridDesc g, Const
 // K-multi: bodies with more than one distinct collider. One thread per such body; the contributions of all its
 // colliders are merged into one ordered list (order = (later slot, earlier slot) over the union).
 // ------------------------------------------------------------------------------------------------
-constexpr int MULTI_MAX_INLINE = 8;  // colliders staged per pass for the rescan path
+constexpr int MULTI_MAX_INLINE = 8;  // colliders staged for the rescan path
+
+__device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, uint32_t b, uint32_t c, float m, SelfCol& s) {
+    const uint32_t cf = Cc.cflags[c];
+    if (!(cf & CF_ACTIVE)) return false;
+    const float2 a = Cc.cabs[c];
+    const uint2 gr = Cc.cgroups[c];
+    s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
+    s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+    return true;
+}
 
 template <bool FUSED, bool ORDERED>
 __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
@@ -402,75 +495,62 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                                                const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols,
                                                uint32_t n_multi) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int n_pairs = 0, n_coinc = 0, n_over = 0;
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
+    unsigned int n_over = 0;
     if (i < n_multi) {
         const uint32_t b = mb_body[i];
         const uint32_t flags = B.bflags[b];
         const uint32_t c0 = mb_off[i], c1 = mb_off[i + 1];
         float2 p = B.pos[b];
         if (P.collisions_enabled) {
-            ContactList list;
+            ContactList<unsigned long long> list;
             list.clear();
-            float fx = 0.f, fy = 0.f;
             const float m = B.mass[b];
             for (uint32_t k = c0; k < c1; ++k) {
-                const uint32_t c = mb_cols[k];
-                const uint32_t cf = Cc.cflags[c];
-                if (!(cf & CF_ACTIVE)) continue;
                 SelfCol s;
-                const float2 a = Cc.cabs[c];
-                const uint2 gr = Cc.cgroups[c];
-                s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
-                s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
-                gather_contacts<ORDERED>(g, bp, s, list, fx, fy, n_pairs, n_coinc, rec, Cc.cparent, B.vel, stats);
+                if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
+                gather_generic<ORDERED, unsigned long long>(g, bp, s, list, out, rec, B.vel, stats);
             }
             if (ORDERED) {
                 if (!list.overflow) {
                     for (int j = 0; j < list.n; ++j) { p.x = fadd(p.x, list.cx[j]); p.y = fadd(p.y, list.cy[j]); }
                 } else {
-                    // rescan path over all colliders of the body, MULTI_MAX_INLINE at a time is not order-safe, so
-                    // stage all of them; bodies with more colliders than fit fall back to the fast (unordered) sum.
+                    // more than LIST_CAP contributions: order-preserving rescan over all colliders of the body; bodies
+                    // with more than MULTI_MAX_INLINE colliders fall back to the unordered sum (counted in list_overflow)
                     n_over = 1;
                     SelfCol cols[MULTI_MAX_INLINE];
                     int nc = 0;
                     bool fits = true;
                     for (uint32_t k = c0; k < c1; ++k) {
-                        const uint32_t c = mb_cols[k];
-                        const uint32_t cf = Cc.cflags[c];
-                        if (!(cf & CF_ACTIVE)) continue;
+                        SelfCol s;
+                        if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
                         if (nc == MULTI_MAX_INLINE) { fits = false; break; }
-                        const float2 a = Cc.cabs[c];
-                        const uint2 gr = Cc.cgroups[c];
-                        SelfCol& s = cols[nc++];
-                        s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
-                        s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+                        cols[nc++] = s;
                     }
                     if (fits) {
-                        apply_contacts_rescan(g, bp, cols, nc, p.x, p.y);
+                        p = apply_contacts_rescan(g, bp, cols, nc, p.x, p.y);
                     } else {
-                        ContactList dummy;
+                        ContactList<unsigned long long> dummy;
                         dummy.clear();
-                        unsigned int d0 = 0, d1 = 0;
+                        GatherOut o2;
+                        o2.fx = o2.fy = 0.f;
+                        o2.n_pairs = o2.n_coinc = 0;
                         Recording off = rec;
                         off.mode = 0;
                         for (uint32_t k = c0; k < c1; ++k) {
-                            const uint32_t c = mb_cols[k];
-                            const uint32_t cf = Cc.cflags[c];
-                            if (!(cf & CF_ACTIVE)) continue;
                             SelfCol s;
-                            const float2 a = Cc.cabs[c];
-                            const uint2 gr = Cc.cgroups[c];
-                            s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
-                            s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
-                            gather_contacts<false>(g, bp, s, dummy, fx, fy, d0, d1, off, Cc.cparent, B.vel, stats);
+                            if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
+                            gather_generic<false, unsigned long long>(g, bp, s, dummy, o2, off, B.vel, stats);
                         }
-                        p.x = fadd(p.x, fx);
-                        p.y = fadd(p.y, fy);
+                        p.x = fadd(p.x, o2.fx);
+                        p.y = fadd(p.y, o2.fy);
                     }
                 }
             } else {
-                p.x = fadd(p.x, fx);
-                p.y = fadd(p.y, fy);
+                p.x = fadd(p.x, out.fx);
+                p.y = fadd(p.y, out.fy);
             }
         }
         if (FUSED) {
@@ -484,9 +564,9 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             B.pos[b] = p;
         }
     }
-    warp_add_u64(&stats->collisions, n_pairs);
-    if (__any_sync(0xffffffffu, n_coinc | n_over)) {
-        warp_add_u64(&stats->coincident, n_coinc);
+    warp_add_u64(&stats->collisions, out.n_pairs);
+    if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, out.n_coinc);
         unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
         if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
     }
@@ -551,17 +631,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 
     uint32_t v[SCAN_ITEMS];
     if (base + SCAN_ITEMS <= n) {
-        const uint4 a = *reinterpret_cast<const uint4*>(data + base);
-        const uint4 b = *reinterpret_cast<const uint4*>(data + base + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+            const uint4 a = *reinterpret_cast<const uint4*>(data + base + 4 * q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? data[base + i] : 0u;
     }
     // zero the other table (same index space)
     if (base + SCAN_ITEMS <= n_zero) {
-        *reinterpret_cast<uint4*>(zero_me + base) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(zero_me + base + 4) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q) *reinterpret_cast<uint4*>(zero_me + base + 4 * q) = make_uint4(0, 0, 0, 0);
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i)
@@ -622,8 +704,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) { o[i] = run; run += v[i]; }
     if (base + SCAN_ITEMS <= n) {
-        *reinterpret_cast<uint4*>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+        for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+            *reinterpret_cast<uint4*>(data + base + 4 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     } else {
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i)
@@ -632,10 +715,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-scatter: writes the 32-byte record of every active collider at cell_start[cell] + rank (one full sector each).
+// K-scatter: writes the two 16-byte record halves of every active collider at cell_start[cell] + rank.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float* __restrict__ mass, const uint32_t* __restrict__ tab,
-                                                 Rec* __restrict__ out, uint32_t n_colliders) {
+                                                 float4* __restrict__ hot, float4* __restrict__ cold, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
     const uint32_t cf = Cc.cflags[c];
@@ -645,10 +728,8 @@ __global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float*
     const uint2 gr = Cc.cgroups[c];
     const uint32_t parent = Cc.cparent[c];
     const uint32_t dst = __ldg(tab + cr.x) + cr.y;
-    float4* q = reinterpret_cast<float4*>(out + dst);
-    q[0] = make_float4(a.x, a.y, Cc.crad[c], mass[parent]);
-    q[1] = make_float4(__uint_as_float(gr.x), __uint_as_float(gr.y), __uint_as_float(parent),
-                       __uint_as_float(c | ((cf & CF_SENSOR) ? 0x80000000u : 0u)));
+    hot[dst] = make_float4(a.x, a.y, Cc.crad[c], __uint_as_float(c | ((cf & CF_SENSOR) ? 0x80000000u : 0u)));
+    cold[dst] = make_float4(mass[parent], __uint_as_float(gr.x), __uint_as_float(gr.y), __uint_as_float(parent));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -743,7 +824,7 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
             if (!(fabsf(ra) <= 3.4028235e38f) || !(fabsf(rb) <= 3.4028235e38f)) bad = true;   // physics.rs:471-474
         }
     }
-    if (bad) stats->nan_flag = 1u;
+    if (bad) atomicOr(&stats->nan_flag, 2u);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -22,26 +22,27 @@ enum : uint32_t {
 constexpr uint32_t NO_SLOT = 0xffffffffu;
 constexpr int32_t BODY_NO_COLLIDER = -1;  // body_col[] encoding; <= -2 : multi-collider body (handled by k_multi)
 
-// One broadphase record per active collider, cell-sorted. 32 B = one L2 sector.
-struct __align__(16) Rec {
+// One broadphase record per active collider, cell-sorted, stored as two 16-byte halves in separate arrays:
+//   hot  = (x, y, r, slot | is_sensor << 31)   — enough for the self test and the distance prefilter
+//   cold = (m, memberships, filter, parent)    — only fetched for candidates that survive the prefilter
+struct Rec {
     float x, y, r, m;          // snapshot translation (physics.rs:360-366), radius, parent body's calculated_mass
     uint32_t memb, filt;       // InteractionGroups (groups.rs:7-12)
     uint32_t parent;           // parent body slot
     uint32_t slot_sensor;      // collider slot | is_sensor << 31
 };
-static_assert(sizeof(Rec) == 32, "Rec must be one 32-byte sector");
 
 struct GridDesc {
     uint32_t W, H;       // toroidal table dims (cells)
     uint32_t ncells;     // W * H
     float cell;          // broadphase cell edge
     float rmax;          // max radius over active colliders (search reach = r + rmax)
+    unsigned long long MW, MH;   // Lemire fastmod magics: 2^64 / W + 1, 2^64 / H + 1
 };
 
-struct Constraints {       // lib.rs:189-193; small by-value copy, spill to global beyond MAXC
-    static constexpr int MAXC = 8;
+struct Constraints {       // lib.rs:189-193: circle constraints, (x, y, radius, -) each, in global memory
     int n;
-    float x[MAXC], y[MAXC], r[MAXC];
+    const float4* c;
 };
 
 struct DeviceStats {       // accumulated per blobs_step* call, read back once
@@ -92,7 +93,8 @@ struct ColliderArrays {
 };
 
 struct Broadphase {
-    const Rec* rec;          // current, read-only during the contact pass
+    const float4* hot;       // current records (see Rec), read-only during the contact pass
+    const float4* cold;
     const uint32_t* tab;     // current cell starts, ncells + 1 entries
     uint32_t* tab_next;      // counts for the next table (zeroed)
 };
@@ -105,8 +107,8 @@ struct Recording {           // optional pair/event output
     float4* vels;            // events: (vel_a.xy, vel_b.xy)
 };
 
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct SpringParams { uint32_t a, b; float rest, k, c; };

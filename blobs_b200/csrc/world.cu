@@ -73,8 +73,8 @@ World::~World() {
     d_pending.release(); d_pending_col.release();
     mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
     isl_off.release(); isl_joint.release(); d_springs.release(); d_joints.release();
-    rec_a.release(); rec_b.release(); tab_a.release(); tab_b.release(); scan_status.release();
-    rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_cellx.release(); d_celly.release();
+    hot_a.release(); hot_b.release(); cold_a.release(); cold_b.release(); tab_a.release(); tab_b.release(); scan_status.release();
+    rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
     if (d_rec_count) cudaFree(d_rec_count);
@@ -199,8 +199,7 @@ ColliderArrays World::col_arrays() {
 Constraints World::constraints_pod() const {
     Constraints K;
     K.n = (int)con_pos.size();
-    for (int i = 0; i < K.n && i < Constraints::MAXC; ++i) { K.x[i] = con_pos[i].x; K.y[i] = con_pos[i].y; K.r[i] = con_r[i]; }
-    for (int i = K.n; i < Constraints::MAXC; ++i) { K.x[i] = K.y[i] = K.r[i] = 0.f; }
+    K.c = d_constraints.d;
     return K;
 }
 
@@ -504,14 +503,15 @@ int World::joint_remove(uint64_t h) {
 }
 
 int World::constraint_push(BlobsVec2 p, float r) {
-    if ((int)con_pos.size() >= Constraints::MAXC) return fail(BLOBS_ERR_CAPACITY, "at most 8 circle constraints are supported");
     con_pos.push_back(p);
     con_r.push_back(r);
+    con_dirty = true;
     return BLOBS_OK;
 }
 int World::constraint_clear() {
     con_pos.clear();
     con_r.clear();
+    con_dirty = true;
     return BLOBS_OK;
 }
 
@@ -665,6 +665,14 @@ int World::flush() {
     }
     CU(mass.flush(stream)); CU(inertia.flush(stream)); CU(gmod.flush(stream)); CU(bflags.flush(stream)); CU(body_col.flush(stream));
     CU(coff.flush(stream)); CU(crad.flush(stream)); CU(cgroups.flush(stream)); CU(cparent.flush(stream)); CU(cflags.flush(stream));
+    if (con_dirty) {
+        std::vector<float4> kc(con_pos.size());
+        for (size_t i = 0; i < kc.size(); ++i) kc[i] = make_float4(con_pos[i].x, con_pos[i].y, con_r[i], 0.f);
+        CU(d_constraints.ensure(std::max<size_t>(kc.size(), 1), stream));
+        if (!kc.empty()) CU(cudaMemcpyAsync(d_constraints.d, kc.data(), kc.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        con_dirty = false;
+    }
     int rc = flush_writes();
     if (rc) return rc;
     CU(cudaStreamSynchronize(stream));  // Mirrored uploads read pageable host vectors
@@ -710,6 +718,8 @@ int World::choose_grid(bool) {
     grid.ncells = grid.W * grid.H;
     grid.cell = cs;
     grid.rmax = r_max;
+    grid.MW = ~0ull / grid.W + 1ull;
+    grid.MH = ~0ull / grid.H + 1ull;
     bb[0] = h_stats->bb_min_x; bb[1] = h_stats->bb_min_y; bb[2] = h_stats->bb_max_x; bb[3] = h_stats->bb_max_y;
     return BLOBS_OK;
 }
@@ -720,13 +730,15 @@ int World::rebuild_broadphase() {
     const size_t nc = cols.slots();
     const size_t tn = (size_t)grid.ncells + 1;
     CU(tab_a.ensure(tn + SCAN_ITEMS, stream)); CU(tab_b.ensure(tn + SCAN_ITEMS, stream));
-    CU(rec_a.ensure(std::max<size_t>(nc, 1), stream)); CU(rec_b.ensure(std::max<size_t>(nc, 1), stream));
+    CU(hot_a.ensure(std::max<size_t>(nc, 1), stream)); CU(hot_b.ensure(std::max<size_t>(nc, 1), stream));
+    CU(cold_a.ensure(std::max<size_t>(nc, 1), stream)); CU(cold_b.ensure(std::max<size_t>(nc, 1), stream));
     CU(scan_status.ensure(cdiv(tn, SCAN_TILE) + 1, stream));
     CU(cudaMemsetAsync(tab_a.d, 0, tn * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(tab_b.d, 0, tn * sizeof(uint32_t), stream));
     uint32_t* tab_next = cur_is_a ? tab_b.d : tab_a.d;
     uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
-    Rec* rec_next = cur_is_a ? rec_b.d : rec_a.d;
+    float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
+    float4* cold_next = cur_is_a ? cold_b.d : cold_a.d;
     if (nc) {
         k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), tab_next, (uint32_t)nc);
         launches++;
@@ -735,7 +747,7 @@ int World::rebuild_broadphase() {
     k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch);
     launches++;
     if (nc) {
-        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), mass.d.d, tab_next, rec_next, (uint32_t)nc);
+        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), mass.d.d, tab_next, hot_next, cold_next, (uint32_t)nc);
         launches++;
     }
     CU(cudaGetLastError());
@@ -782,11 +794,13 @@ int World::launch_substep(const SubstepParams& P) {
     const ColliderArrays C = col_arrays();
     const Constraints K = constraints_pod();
     Broadphase bp;
-    bp.rec = cur_is_a ? rec_a.d : rec_b.d;
+    bp.hot = cur_is_a ? hot_a.d : hot_b.d;
+    bp.cold = cur_is_a ? cold_a.d : cold_b.d;
     bp.tab = cur_is_a ? tab_a.d : tab_b.d;
     bp.tab_next = cur_is_a ? tab_b.d : tab_a.d;
     uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
-    Rec* rec_next = cur_is_a ? rec_b.d : rec_a.d;
+    float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
+    float4* cold_next = cur_is_a ? cold_b.d : cold_a.d;
     Recording R;
     R.mode = (uint32_t)rec_mode;
     R.cap = (uint32_t)std::min<size_t>(rec_cap, 0xffffffffu);
@@ -843,7 +857,7 @@ int World::launch_substep(const SubstepParams& P) {
     rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch); });
     if (rc) return rc;
     if (nc) {
-        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, mass.d.d, bp.tab_next, rec_next, nc); });
+        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, mass.d.d, bp.tab_next, hot_next, cold_next, nc); });
         if (rc) return rc;
     }
     cur_is_a = !cur_is_a;

@@ -235,6 +235,8 @@ class World {
     bool allow_fused = true;
     std::vector<BlobsVec2> con_pos;
     std::vector<float> con_r;
+    bool con_dirty = true;
+    DevBuf<float4> d_constraints;
 
     // arenas + host records
     HostArena bodies, cols, springs, joints;
@@ -279,8 +281,8 @@ class World {
     DevBuf<JointParams> d_joints;
 
     // broadphase
-    GridDesc grid{1, 1, 1, 1.0f, 0.f};
-    DevBuf<Rec> rec_a, rec_b;
+    GridDesc grid{1, 1, 1, 1.0f, 0.f, 0ull, 0ull};
+    DevBuf<float4> hot_a, hot_b, cold_a, cold_b;
     DevBuf<uint32_t> tab_a, tab_b;
     bool cur_is_a = true;
     DevBuf<unsigned long long> scan_status;

@@ -28,6 +28,10 @@ __device__ __forceinline__ float vlen(float x, float y) { return __fsqrt_rn(fadd
 // __float2int_rd rounds toward -inf, saturates and maps NaN to 0 exactly like Rust's `as i32`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cell_coord(float v, float cs) { return __float2int_rd(fdiv(v, cs)); }
+// Broadphase binning only needs a MONOTONE map shared by the binning and the query (see cell_range): floor(v * (1/cs)).
+// (Identical to cell_coord whenever cs is a power of two, e.g. the cfg2 cell of 1.0.) The reference-exact
+// get_cell_coords is what k_cell_coords exports.
+__device__ __forceinline__ int bin_coord(float v, float inv_cs) { return __float2int_rd(v * inv_cs); }
 // order-preserving int32 -> uint32, then modulo: a toroidal mapping where neighbouring cells stay neighbours
 __device__ __forceinline__ uint32_t ubias(int c) { return (uint32_t)c ^ 0x80000000u; }
 // Lemire fastmod: n % d for any 32-bit n, d with M = 2^64 / d + 1
@@ -54,8 +58,8 @@ struct CellRange {
 };
 __device__ __forceinline__ CellRange cell_range(const GridDesc& g, float x, float y, float r) {
     const float reach = __fadd_ru(r, g.rmax);
-    const int cx0 = cell_coord(__fsub_rd(x, reach), g.cell), cx1 = cell_coord(__fadd_ru(x, reach), g.cell);
-    const int cy0 = cell_coord(__fsub_rd(y, reach), g.cell), cy1 = cell_coord(__fadd_ru(y, reach), g.cell);
+    const int cx0 = bin_coord(__fsub_rd(x, reach), g.inv_cell), cx1 = bin_coord(__fadd_ru(x, reach), g.inv_cell);
+    const int cy0 = bin_coord(__fsub_rd(y, reach), g.inv_cell), cy1 = bin_coord(__fadd_ru(y, reach), g.inv_cell);
     CellRange R;
     // spans (>= 1); an empty/NaN range degenerates to one cell
     R.nx = (cx1 >= cx0) ? (uint32_t)cx1 - (uint32_t)cx0 + 1u : 1u;
@@ -245,60 +249,66 @@ __device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadpha
     for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
 }
 
-// Latency-oriented gather for the common case (<= 3 rows, no column wrap): the six cell-table reads are issued together,
-// then candidates are streamed in batches of 4 hot halves (16 B: x, y, r, slot); a conservative squared-distance
-// prefilter decides which cold halves (mass, groups, parent) are fetched at all.
-// Prefilter soundness: contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > md*md*1.0001 implies sqrt(d2) > md*(1+4e-5),
+// Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap, <= 32 records per row span):
+//  1. the six cell-table reads are issued together;
+//  2. SCAN: hot halves (16 B: x, y, r, slot) are streamed in batches of 4 and a conservative squared-distance prefilter
+//     marks survivors in a per-row bitmask — no sqrt, no divide, no cold half;
+//  3. RESOLVE: survivors are popped in a loop that all lanes of the warp run together (trip count = max survivors per
+//     lane), each doing the exact narrowphase on hot + cold halves.
+// Prefilter soundness: a contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > md*md*1.0001 implies sqrt(d2) > md*(1+4e-5),
 // which rounding (2^-24) cannot bring below md. NaNs fail the '>' and fall through to the exact test.
 template <bool ORDERED, class KEY>
 __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
                                               GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
     const CellRange R = cell_range(g, s.x, s.y, s.r);
-    if (R.ny > 3u || R.c0 + R.nx > g.W) {
+    bool generic = R.ny > 3u || R.c0 + R.nx > g.W;
+    uint32_t lo[3], cnt[3];
+    if (!generic) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            uint32_t row = R.r0 + j;
+            if (row >= g.H) row -= g.H;
+            const bool valid = (uint32_t)j < R.ny;
+            const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
+            const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
+            lo[j] = a;
+            cnt[j] = b - a;
+        }
+        generic = (cnt[0] | cnt[1] | cnt[2]) > 32u;
+    }
+    if (generic) {
         gather_generic<ORDERED, KEY>(g, bp, s, list, out, rec, vel, stats);
         return;
     }
-    uint32_t lo[3], cnt[3];
+    uint32_t mask[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        uint32_t row = R.r0 + j;
-        if (row >= g.H) row -= g.H;
-        const bool valid = (uint32_t)j < R.ny;
-        const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
-        const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
-        lo[j] = a;
-        cnt[j] = b - a;
+        uint32_t m = 0;
+        for (uint32_t t = 0; t < cnt[j]; t += 4u) {
+            float4 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (t + i < cnt[j]) h[i] = __ldg(bp.hot + lo[j] + t + i);
+                else h[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(s.slot));  // reads as "self": skipped
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
+                const float dx = s.x - h[i].x, dy = s.y - h[i].y;
+                const float d2 = dx * dx + dy * dy;
+                const float md = s.r + h[i].z;
+                if (oslot != s.slot && !(d2 > md * md * 1.0001f)) m |= 1u << (t + i);
+            }
+        }
+        mask[j] = m;
     }
-    const uint32_t n0 = cnt[0], n01 = cnt[0] + cnt[1], total = n01 + cnt[2];
-    for (uint32_t base = 0; base < total; base += 4u) {
-        float4 h[4];
-        uint32_t kk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t t = base + i;
-            const uint32_t k = t < n0 ? lo[0] + t : (t < n01 ? lo[1] + (t - n0) : lo[2] + (t - n01));
-            kk[i] = k;
-            if (t < total) h[i] = __ldg(bp.hot + k);
-            else h[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(s.slot));  // reads as "self": skipped
-        }
-        unsigned int pass = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
-            const float dx = s.x - h[i].x, dy = s.y - h[i].y;
-            const float d2 = dx * dx + dy * dy;
-            const float md = s.r + h[i].z;
-            if (oslot != s.slot && !(d2 > md * md * 1.0001f)) pass |= 1u << i;
-        }
-        if (pass) {
-            float4 c[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (pass & (1u << i)) c[i] = __ldg(bp.cold + kk[i]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (pass & (1u << i)) take_candidate<ORDERED, KEY>(s, make_rec(h[i], c[i]), list, out, rec, vel, stats);
-        }
+    for (;;) {
+        uint32_t k;
+        if (mask[0]) { k = lo[0] + (uint32_t)__ffs(mask[0]) - 1u; mask[0] &= mask[0] - 1u; }
+        else if (mask[1]) { k = lo[1] + (uint32_t)__ffs(mask[1]) - 1u; mask[1] &= mask[1] - 1u; }
+        else if (mask[2]) { k = lo[2] + (uint32_t)__ffs(mask[2]) - 1u; mask[2] &= mask[2] - 1u; }
+        else break;
+        take_candidate<ORDERED, KEY>(s, make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)), list, out, rec, vel, stats);
     }
 }
 
@@ -348,7 +358,7 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
     if (flags & BF_STATIC) {                                     // physics.rs:327-332
         B.pos_old[b] = make_float2(px, py);
         B.acc[b] = make_float2(0.f, 0.f);
-        B.vel[b] = make_float2(0.f, 0.f);
+        if (P.write_vel) B.vel[b] = make_float2(0.f, 0.f);
     } else {
         float2 po = B.pos_old[b];
         if (B.has_vreq[b]) {                                     // physics.rs:334-336
@@ -377,7 +387,9 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
             B.torque[b] = 0.0f;
         }
         B.acc[b] = make_float2(0.f, 0.f);
-        B.vel[b] = make_float2(fdiv(dx, P.dt), fdiv(dy, P.dt));  // physics.rs:357
+        // calculated_velocity (physics.rs:357) is only observable through springs, events and host reads, so it is
+        // materialised on the substeps where one of those can see it (host sets write_vel)
+        if (P.write_vel) B.vel[b] = make_float2(fdiv(dx, P.dt), fdiv(dy, P.dt));
     }
     sx = px;
     sy = py;
@@ -385,10 +397,14 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
     for (int i = 0; i < K.n; ++i) {                              // physics.rs:377-395
         const float4 k = __ldg(K.c + i);                         // (x, y, radius, -)
         const float tx = fsub(px, k.x), ty = fsub(py, k.y);
-        const float d = vlen(tx, ty);
-        if (d > k.z) {
-            px = fadd(k.x, fmul(fdiv(tx, d), k.z));
-            py = fadd(k.y, fmul(fdiv(ty, d), k.z));
+        const float d2 = fadd(fmul(tx, tx), fmul(ty, ty));
+        // sqrt(d2) > R needs d2 > R*R*(1 - 1e-4) at the very least: skip the sqrt for bodies well inside the circle
+        if (k.z < 0.f || d2 > k.z * k.z * 0.9999f) {
+            const float d = __fsqrt_rn(d2);
+            if (d > k.z) {
+                px = fadd(k.x, fmul(fdiv(tx, d), k.z));
+                py = fadd(k.y, fmul(fdiv(ty, d), k.z));
+            }
         }
     }
     if (px != px || py != py) atomicOr(&stats->nan_flag, 1u);
@@ -406,7 +422,7 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
     const float ax = fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx);
     const float ay = fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy);
     Cc.cabs[c] = make_float2(ax, ay);
-    const uint32_t cell = cell_index(g, cell_coord(ax, g.cell), cell_coord(ay, g.cell));
+    const uint32_t cell = cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
     const uint32_t rank = atomicAdd(tab_next + cell, 1u);
     Cc.ccell[c] = make_uint2(cell, rank);
 }
@@ -606,7 +622,7 @@ __global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, ui
     if (c >= n_colliders) return;
     if (!(Cc.cflags[c] & CF_ACTIVE)) return;
     const float2 a = Cc.cabs[c];
-    const uint32_t cell = cell_index(g, cell_coord(a.x, g.cell), cell_coord(a.y, g.cell));
+    const uint32_t cell = cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
     const uint32_t rank = atomicAdd(tab_next + cell, 1u);
     Cc.ccell[c] = make_uint2(cell, rank);
 }

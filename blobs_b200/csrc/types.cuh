@@ -36,6 +36,7 @@ struct GridDesc {
     uint32_t W, H;       // toroidal table dims (cells)
     uint32_t ncells;     // W * H
     float cell;          // broadphase cell edge
+    float inv_cell;      // 1 / cell (binning uses the monotone map floor(v * inv_cell))
     float rmax;          // max radius over active colliders (search reach = r + rmax)
     unsigned long long MW, MH;   // Lemire fastmod magics: 2^64 / W + 1, 2^64 / H + 1
 };
@@ -63,6 +64,7 @@ struct SubstepParams {
     uint32_t collisions_enabled;
     uint32_t n_bodies;              // body slots
     uint32_t n_colliders;           // collider slots
+    uint32_t write_vel;             // materialise calculated_velocity this substep
 };
 
 struct BodyArrays {

@@ -717,6 +717,7 @@ int World::choose_grid(bool) {
     grid.H = (uint32_t)H;
     grid.ncells = grid.W * grid.H;
     grid.cell = cs;
+    grid.inv_cell = 1.0f / cs;
     grid.rmax = r_max;
     grid.MW = ~0ull / grid.W + 1ull;
     grid.MH = ~0ull / grid.H + 1ull;
@@ -869,7 +870,7 @@ int World::launch_substep(const SubstepParams& P) {
 }
 
 // Physics::integrate (physics.rs:397-422)
-int World::integrate(uint32_t nsub, float delta) {
+int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
     const float step_delta = delta / (float)nsub;
     for (uint32_t i = 0; i < nsub; ++i) {
         SubstepParams P;
@@ -882,6 +883,7 @@ int World::integrate(uint32_t nsub, float delta) {
         P.collisions_enabled = collisions_enabled ? 1u : 0u;
         P.n_bodies = (uint32_t)bodies.slots();
         P.n_colliders = (uint32_t)cols.slots();
+        P.write_vel = ((last_of_call && i + 1 == nsub) || n_sb > 0 || rec_mode == BLOBS_RECORD_EVENTS) ? 1u : 0u;
         int rc = launch_substep(P);
         if (rc) return rc;
         if (first_dynamic != NO_SLOT) old_dt = step_delta;  // physics.rs:339
@@ -937,7 +939,7 @@ int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
     CU(cudaEventRecord(ev_step0, stream));
     shadow_valid = false;
     for (uint32_t i = 0; i < n; ++i) {
-        rc = integrate(substeps, (float)delta);  // physics.rs:80
+        rc = integrate(substeps, (float)delta, i + 1 == n);  // physics.rs:80
         if (rc) return rc;
         time += delta;                           // physics.rs:81
     }
@@ -962,7 +964,7 @@ int World::fixed_step(double frame_time, BlobsStepStats* stats) {
     int max_steps = 3;
     uint32_t n = 0;
     while (accumulator >= delta && max_steps > 0) {
-        rc = integrate(substeps, (float)delta);
+        rc = integrate(substeps, (float)delta, max_steps == 1 || !(accumulator - delta >= delta));
         if (rc) return rc;
         accumulator -= delta;
         time += delta;

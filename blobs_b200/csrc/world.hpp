@@ -203,7 +203,7 @@ class World {
     int rebuild_topology();
     int rebuild_broadphase();
     int choose_grid(bool force);
-    int integrate(uint32_t substeps, float delta);
+    int integrate(uint32_t substeps, float delta, bool last_of_call);
     int launch_substep(const SubstepParams& P);
     int finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run);
     int ensure_shadow();
@@ -281,7 +281,7 @@ class World {
     DevBuf<JointParams> d_joints;
 
     // broadphase
-    GridDesc grid{1, 1, 1, 1.0f, 0.f, 0ull, 0ull};
+    GridDesc grid{1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};
     DevBuf<float4> hot_a, hot_b, cold_a, cold_b;
     DevBuf<uint32_t> tab_a, tab_b;
     bool cur_is_a = true;

@@ -249,66 +249,66 @@ __device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadpha
     for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
 }
 
-// Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap, <= 32 records per row span):
+// Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap):
 //  1. the six cell-table reads are issued together;
-//  2. SCAN: hot halves (16 B: x, y, r, slot) are streamed in batches of 4 and a conservative squared-distance prefilter
-//     marks survivors in a per-row bitmask — no sqrt, no divide, no cold half;
+//  2. SCAN: the three row spans are treated as one flattened candidate sequence; hot halves (16 B: x, y, r, slot) are
+//     fetched GATHER_BATCH at a time (all loads in flight before the first use) and a conservative squared-distance
+//     prefilter marks survivors in a 32-bit mask — no sqrt, no divide, no cold half;
 //  3. RESOLVE: survivors are popped in a loop that all lanes of the warp run together (trip count = max survivors per
 //     lane), each doing the exact narrowphase on hot + cold halves.
 // Prefilter soundness: a contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > md*md*1.0001 implies sqrt(d2) > md*(1+4e-5),
 // which rounding (2^-24) cannot bring below md. NaNs fail the '>' and fall through to the exact test.
+constexpr int GATHER_BATCH = 8;
+
 template <bool ORDERED, class KEY>
 __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
                                               GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
     const CellRange R = cell_range(g, s.x, s.y, s.r);
-    bool generic = R.ny > 3u || R.c0 + R.nx > g.W;
-    uint32_t lo[3], cnt[3];
-    if (!generic) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            uint32_t row = R.r0 + j;
-            if (row >= g.H) row -= g.H;
-            const bool valid = (uint32_t)j < R.ny;
-            const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
-            const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
-            lo[j] = a;
-            cnt[j] = b - a;
-        }
-        generic = (cnt[0] | cnt[1] | cnt[2]) > 32u;
-    }
-    if (generic) {
+    if (R.ny > 3u || R.c0 + R.nx > g.W) {
         gather_generic<ORDERED, KEY>(g, bp, s, list, out, rec, vel, stats);
         return;
     }
-    uint32_t mask[3];
+    uint32_t lo[3], cnt[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        uint32_t m = 0;
-        for (uint32_t t = 0; t < cnt[j]; t += 4u) {
-            float4 h[4];
+        uint32_t row = R.r0 + j;
+        if (row >= g.H) row -= g.H;
+        const bool valid = (uint32_t)j < R.ny;
+        const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
+        const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
+        lo[j] = a;
+        cnt[j] = b - a;
+    }
+    const uint32_t n0 = cnt[0], n01 = cnt[0] + cnt[1], total = n01 + cnt[2];
+    // flattened candidate index -> record index; rebased so that k = t + off_j inside row j
+    const uint32_t off0 = lo[0], off1 = lo[1] - n0, off2 = lo[2] - n01;
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t lim = min(32u, total - base);
+        uint32_t mask = 0;
+        for (uint32_t t0 = 0; t0 < lim; t0 += GATHER_BATCH) {
+            float4 h[GATHER_BATCH];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (t + i < cnt[j]) h[i] = __ldg(bp.hot + lo[j] + t + i);
+            for (int i = 0; i < GATHER_BATCH; ++i) {
+                const uint32_t t = base + t0 + i;
+                const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
+                if (t0 + i < lim) h[i] = __ldg(bp.hot + k);
                 else h[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(s.slot));  // reads as "self": skipped
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < GATHER_BATCH; ++i) {
                 const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
                 const float dx = s.x - h[i].x, dy = s.y - h[i].y;
                 const float d2 = dx * dx + dy * dy;
                 const float md = s.r + h[i].z;
-                if (oslot != s.slot && !(d2 > md * md * 1.0001f)) m |= 1u << (t + i);
+                if (oslot != s.slot && !(d2 > md * md * 1.0001f)) mask |= 1u << (t0 + i);
             }
         }
-        mask[j] = m;
-    }
-    for (;;) {
-        uint32_t k;
-        if (mask[0]) { k = lo[0] + (uint32_t)__ffs(mask[0]) - 1u; mask[0] &= mask[0] - 1u; }
-        else if (mask[1]) { k = lo[1] + (uint32_t)__ffs(mask[1]) - 1u; mask[1] &= mask[1] - 1u; }
-        else if (mask[2]) { k = lo[2] + (uint32_t)__ffs(mask[2]) - 1u; mask[2] &= mask[2] - 1u; }
-        else break;
-        take_candidate<ORDERED, KEY>(s, make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)), list, out, rec, vel, stats);
+        while (mask) {
+            const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
+            mask &= mask - 1u;
+            const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
+            take_candidate<ORDERED, KEY>(s, make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)), list, out, rec, vel, stats);
+        }
     }
 }
 
@@ -347,12 +347,14 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
 
 // ------------------------------------------------------------------------------------------------
 // update_objects for one body (physics.rs:326-358) + gravity (physics.rs:369-375) + circle constraints
-// (physics.rs:377-395). (px, py) is the body position after contacts/joints. Returns the pre-clamp position in
-// (sx, sy): that is what the collider snapshot is built from (physics.rs:360-366 runs before apply_constraints).
+// (physics.rs:377-395). (px, py) is the body position after contacts/joints; po / a / hv / gmod are the body's
+// position_old, acceleration, velocity_request flag and gravity_mod, pre-loaded by the caller so that their memory
+// latency overlaps the contact pass. Returns the pre-clamp position in (sx, sy): that is what the collider snapshot is
+// built from (physics.rs:360-366 runs before apply_constraints).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Constraints& K, const BodyArrays& B, uint32_t b,
-                                               uint32_t flags, float px, float py, float& sx, float& sy, float& rot_out,
-                                               DeviceStats* stats) {
+                                               uint32_t flags, float gmod, float px, float py, float2 po, float2 a, bool hv,
+                                               float& sx, float& sy, float& rot_out, DeviceStats* stats) {
     float rot = 0.0f;
     if (flags & BF_ROT) rot = B.rot[b];
     if (flags & BF_STATIC) {                                     // physics.rs:327-332
@@ -360,8 +362,7 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
         B.acc[b] = make_float2(0.f, 0.f);
         if (P.write_vel) B.vel[b] = make_float2(0.f, 0.f);
     } else {
-        float2 po = B.pos_old[b];
-        if (B.has_vreq[b]) {                                     // physics.rs:334-336
+        if (hv) {                                                // physics.rs:334-336
             const float2 v = B.vreq[b];
             po.x = fsub(px, fmul(v.x, P.dt));
             po.y = fsub(py, fmul(v.y, P.dt));
@@ -369,11 +370,9 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
         }
         const float ratio = (b == P.first_dynamic) ? P.ratio_first : P.ratio_rest;   // physics.rs:338-339
         const float dx = fmul(fsub(px, po.x), ratio), dy = fmul(fsub(py, po.y), ratio);
-        float2 a = B.acc[b];
         if (!(flags & BF_SPRINGS)) {                             // gravity; spring bodies got it in k_springs
-            const float gm = B.gmod[b];
-            a.x = fadd(a.x, fmul(P.gx, gm));
-            a.y = fadd(a.y, fmul(P.gy, gm));
+            a.x = fadd(a.x, fmul(P.gx, gmod));
+            a.y = fadd(a.y, fmul(P.gy, gmod));
         }
         B.pos_old[b] = make_float2(px, py);                      // physics.rs:343
         px = fadd(px, fadd(dx, fmul(fmul(a.x, P.dt), P.dt)));    // physics.rs:344
@@ -415,8 +414,9 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
 // glam's Mat2::from_angle columns (cos, sin), (-sin, cos) and M*v = x_axis*v.x + y_axis*v.y.
 // Then bins the collider into the next broadphase table.
 __device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t c,
-                                                 float sx, float sy, float rot) {
-    const float2 off = Cc.coff[c];
+                                                 uint32_t cflags, float sx, float sy, float rot) {
+    float2 off = make_float2(0.f, 0.f);
+    if (cflags & CF_OFFSET) off = Cc.coff[c];
     float sn = 0.0f, cs = 1.0f;
     if (rot != 0.0f) sincosf(rot, &sn, &cs);
     const float ax = fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx);
@@ -430,6 +430,10 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
 // ------------------------------------------------------------------------------------------------
 // K-main: one thread per body slot. Contacts (gather, ordered) [+ verlet + snapshot + clamp + binning when FUSED].
 // Handles bodies with zero or one collider; multi-collider bodies go to k_multi.
+// Memory-latency chain (the kernel is latency-, not bandwidth-bound): round 1 = every per-body array plus the collider
+// arrays at the SPECULATED slot c == b (insert_rbd + insert_collider_with_parent in lockstep gives identical slots);
+// round 2 = six cell-table entries; round 3 = hot record halves; round 4 = cold halves of prefilter survivors;
+// round 5 = the binning atomic.
 // ------------------------------------------------------------------------------------------------
 template <bool FUSED, bool ORDERED>
 __global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
@@ -439,46 +443,61 @@ __global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Co
     out.fx = out.fy = 0.f;
     out.n_pairs = out.n_coinc = 0;
     unsigned int n_over = 0;
-    if (b < P.n_bodies) {
-        const uint32_t flags = B.bflags[b];
-        const int32_t col = B.body_col[b];
-        if ((flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
-            float2 p = B.pos[b];
-            bool active_col = false;
-            if (col >= 0) {
-                const uint32_t c = (uint32_t)col;
-                const uint32_t cf = Cc.cflags[c];
-                active_col = (cf & CF_ACTIVE) != 0u;
-                if (active_col && P.collisions_enabled) {
-                    SelfCol s;
-                    const float2 a = Cc.cabs[c];
-                    const uint2 gr = Cc.cgroups[c];
-                    s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = B.mass[b];
-                    s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
-                    ContactList<uint32_t> list;
-                    list.clear();
-                    gather_single<ORDERED, uint32_t>(g, bp, s, list, out, rec, B.vel, stats);
-                    if (ORDERED) {
-                        if (!list.overflow) {
-                            for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
-                        } else {
-                            n_over = 1;
-                            SelfCol s2 = s;  // stack copy only on this rare path
-                            p = apply_contacts_rescan(g, bp, &s2, 1, p.x, p.y);
-                        }
+    const bool inb = b < P.n_bodies;
+    const uint32_t bl = inb ? b : 0u;
+    // round 1: everything that only needs b (tail threads read slot 0 and discard)
+    const uint2 info = B.binfo[bl];
+    const float2 mg = B.bmg[bl];
+    float2 p = B.pos[bl];
+    const float2 po = B.pos_old[bl];
+    const float2 acc0 = B.acc[bl];
+    const bool hv = B.has_vreq[bl] != 0;
+    uint32_t cs = 0;
+    uint4 cc = make_uint4(0u, 0u, 0u, 0u);
+    float2 ab = make_float2(0.f, 0.f);
+    if (P.n_colliders) {
+        cs = min(bl, P.n_colliders - 1u);
+        cc = Cc.cconst[cs];
+        ab = Cc.cabs[cs];
+    }
+    const uint32_t flags = info.x;
+    const int32_t col = (int32_t)info.y;
+    if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
+        bool active_col = false;
+        if (col >= 0) {
+            const uint32_t c = (uint32_t)col;
+            if (c != cs) {  // speculation missed: fetch the real collider
+                cc = Cc.cconst[c];
+                ab = Cc.cabs[c];
+            }
+            active_col = (cc.y & CF_ACTIVE) != 0u;
+            if (active_col && P.collisions_enabled) {
+                SelfCol s;
+                s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
+                s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.sensor = (cc.y & CF_SENSOR) != 0u;
+                ContactList<uint32_t> list;
+                list.clear();
+                gather_single<ORDERED, uint32_t>(g, bp, s, list, out, rec, B.vel, stats);
+                if (ORDERED) {
+                    if (!list.overflow) {
+                        for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
                     } else {
-                        p.x = fadd(p.x, out.fx);
-                        p.y = fadd(p.y, out.fy);
+                        n_over = 1;
+                        SelfCol s2 = s;  // stack copy only on this rare path
+                        p = apply_contacts_rescan(g, bp, &s2, 1, p.x, p.y);
                     }
+                } else {
+                    p.x = fadd(p.x, out.fx);
+                    p.y = fadd(p.y, out.fy);
                 }
             }
-            if (FUSED) {
-                float sx, sy, rot;
-                integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
-                if (active_col) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, sx, sy, rot);
-            } else {
-                B.pos[b] = p;
-            }
+        }
+        if (FUSED) {
+            float sx, sy, rot;
+            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+            if (active_col) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, cc.y, sx, sy, rot);
+        } else {
+            B.pos[b] = p;
         }
     }
     warp_add_u64(&stats->collisions, out.n_pairs);
@@ -496,12 +515,11 @@ __global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Co
 constexpr int MULTI_MAX_INLINE = 8;  // colliders staged for the rescan path
 
 __device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, uint32_t b, uint32_t c, float m, SelfCol& s) {
-    const uint32_t cf = Cc.cflags[c];
-    if (!(cf & CF_ACTIVE)) return false;
+    const uint4 cc = Cc.cconst[c];
+    if (!(cc.y & CF_ACTIVE)) return false;
     const float2 a = Cc.cabs[c];
-    const uint2 gr = Cc.cgroups[c];
-    s.x = a.x; s.y = a.y; s.r = Cc.crad[c]; s.m = m;
-    s.memb = gr.x; s.filt = gr.y; s.body = b; s.slot = c; s.sensor = (cf & CF_SENSOR) != 0u;
+    s.x = a.x; s.y = a.y; s.r = __uint_as_float(cc.x); s.m = m;
+    s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.sensor = (cc.y & CF_SENSOR) != 0u;
     return true;
 }
 
@@ -517,13 +535,17 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
     unsigned int n_over = 0;
     if (i < n_multi) {
         const uint32_t b = mb_body[i];
-        const uint32_t flags = B.bflags[b];
+        const uint32_t flags = B.binfo[b].x;
+        const float2 mg = B.bmg[b];
         const uint32_t c0 = mb_off[i], c1 = mb_off[i + 1];
         float2 p = B.pos[b];
+        const float2 po = B.pos_old[b];
+        const float2 acc0 = B.acc[b];
+        const bool hv = B.has_vreq[b] != 0;
         if (P.collisions_enabled) {
             ContactList<unsigned long long> list;
             list.clear();
-            const float m = B.mass[b];
+            const float m = mg.x;
             for (uint32_t k = c0; k < c1; ++k) {
                 SelfCol s;
                 if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
@@ -571,10 +593,11 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
         }
         if (FUSED) {
             float sx, sy, rot;
-            integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
+            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
             for (uint32_t k = c0; k < c1; ++k) {
                 const uint32_t c = mb_cols[k];
-                if (Cc.cflags[c] & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, c, sx, sy, rot);
+                const uint32_t cf = Cc.cconst[c].y;
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, c, cf, sx, sy, rot);
             }
         } else {
             B.pos[b] = p;
@@ -597,19 +620,22 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
                                                    const uint32_t* __restrict__ mb_cols) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.n_bodies) return;
-    const uint32_t flags = B.bflags[b];
+    const uint2 info = B.binfo[b];
+    const uint32_t flags = info.x;
     if (!(flags & BF_ALIVE)) return;
-    const int32_t col = B.body_col[b];
+    const int32_t col = (int32_t)info.y;
     const float2 p = B.pos[b];
     float sx, sy, rot;
-    integrate_body(P, K, B, b, flags, p.x, p.y, sx, sy, rot, stats);
+    integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
     if (col >= 0) {
-        if (Cc.cflags[col] & CF_ACTIVE) publish_collider(g, Cc, tab_next, (uint32_t)col, sx, sy, rot);
+        const uint32_t cf = Cc.cconst[col].y;
+        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, (uint32_t)col, cf, sx, sy, rot);
     } else if (col <= -2) {
         const uint32_t i = (uint32_t)(-(col + 2));
         for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
             const uint32_t c = mb_cols[k];
-            if (Cc.cflags[c] & CF_ACTIVE) publish_collider(g, Cc, tab_next, c, sx, sy, rot);
+            const uint32_t cf = Cc.cconst[c].y;
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, c, cf, sx, sy, rot);
         }
     }
 }
@@ -620,7 +646,7 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
 __global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, uint32_t* tab_next, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
-    if (!(Cc.cflags[c] & CF_ACTIVE)) return;
+    if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
     const float2 a = Cc.cabs[c];
     const uint32_t cell = cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
     const uint32_t rank = atomicAdd(tab_next + cell, 1u);
@@ -733,19 +759,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 // ------------------------------------------------------------------------------------------------
 // K-scatter: writes the two 16-byte record halves of every active collider at cell_start[cell] + rank.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float* __restrict__ mass, const uint32_t* __restrict__ tab,
+__global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float2* __restrict__ bmg, const uint32_t* __restrict__ tab,
                                                  float4* __restrict__ hot, float4* __restrict__ cold, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
-    const uint32_t cf = Cc.cflags[c];
-    if (!(cf & CF_ACTIVE)) return;
+    const uint4 cc = Cc.cconst[c];
+    if (!(cc.y & CF_ACTIVE)) return;
     const uint2 cr = Cc.ccell[c];
     const float2 a = Cc.cabs[c];
-    const uint2 gr = Cc.cgroups[c];
     const uint32_t parent = Cc.cparent[c];
     const uint32_t dst = __ldg(tab + cr.x) + cr.y;
-    hot[dst] = make_float4(a.x, a.y, Cc.crad[c], __uint_as_float(c | ((cf & CF_SENSOR) ? 0x80000000u : 0u)));
-    cold[dst] = make_float4(mass[parent], __uint_as_float(gr.x), __uint_as_float(gr.y), __uint_as_float(parent));
+    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
+    cold[dst] = make_float4(bmg[parent].x, __uint_as_float(cc.z), __uint_as_float(cc.w), __uint_as_float(parent));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -760,13 +785,14 @@ __global__ void __launch_bounds__(128) k_springs(SubstepParams P, BodyArrays B, 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_sb) return;
     const uint32_t b = sb_body[i];
-    const uint32_t flags = B.bflags[b];
+    const uint32_t flags = B.binfo[b].x;
     if (flags & BF_STATIC) return;  // no gravity (physics.rs:371), apply_force ignored (rigid_body.rs:156)
     float2 a = B.acc[b];
-    const float gm = B.gmod[b];
+    const float2 mg = B.bmg[b];
+    const float gm = mg.y;
     a.x = fadd(a.x, fmul(P.gx, gm));   // apply_gravity runs before the springs (physics.rs:404-408)
     a.y = fadd(a.y, fmul(P.gy, gm));
-    const float m = B.mass[b];
+    const float m = mg.x;
     for (uint32_t e = sb_off[i]; e < sb_off[i + 1]; ++e) {
         const uint32_t ed = sb_edge[e];
         const SpringParams sp = springs[ed >> 1];
@@ -812,10 +838,10 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
             if (dist < 1e-6f) continue;                                              // physics.rs:440-442
             const float off_by = fsub(dist, jp.distance);
             const float cx = fdiv(fmul(off_by, dx), dist), cy = fdiv(fmul(off_by, dy), dist);   // physics.rs:445
-            const float ma = B.mass[jp.a], mb = B.mass[jp.b];
+            const float ma = B.bmg[jp.a].x, mb = B.bmg[jp.b].x;
             const float ima = fdiv(1.0f, ma), imb = fdiv(1.0f, mb);
             const float ims = fadd(ima, imb);                                        // physics.rs:450
-            const uint32_t fa = B.bflags[jp.a], fb = B.bflags[jp.b];
+            const uint32_t fa = B.binfo[jp.a].x, fb = B.binfo[jp.b].x;
             if (fa & BF_STATIC) {                                                    // physics.rs:452-453
                 pb.x = fsub(pb.x, fmul(ims, cx)); pb.y = fsub(pb.y, fmul(ims, cy));
                 B.pos[jp.b] = pb;
@@ -851,7 +877,7 @@ __global__ void __launch_bounds__(256) k_bbox(ColliderArrays Cc, float cell, uin
     __shared__ int s_min_x[8], s_min_y[8], s_max_x[8], s_max_y[8];
     int mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
-        if (!(Cc.cflags[c] & CF_ACTIVE)) continue;
+        if (!(Cc.cconst[c].y & CF_ACTIVE)) continue;
         const float2 a = Cc.cabs[c];
         if (!(fabsf(a.x) < 1e30f) || !(fabsf(a.y) < 1e30f)) continue;   // ignore runaway / NaN points
         const int cx = cell_coord(a.x, cell), cy = cell_coord(a.y, cell);
@@ -910,10 +936,10 @@ __global__ void __launch_bounds__(256) k_apply_col_writes(float2* cabs, const Co
 __global__ void __launch_bounds__(256) k_apply_forces(BodyArrays B, const float2* __restrict__ force, uint32_t n) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
-    const uint32_t f = B.bflags[b];
+    const uint32_t f = B.binfo[b].x;
     if (!(f & BF_ALIVE) || (f & BF_STATIC)) return;
     const float2 F = force[b];
-    const float m = B.mass[b];
+    const float m = B.bmg[b].x;
     float2 a = B.acc[b];
     a.x = fadd(a.x, fdiv(F.x, m));
     a.y = fadd(a.y, fdiv(F.y, m));

@@ -18,6 +18,7 @@ enum : uint32_t {
 enum : uint32_t {
     CF_ACTIVE = 1u << 0,  // alive AND parent handle resolves to a live body (physics.rs:252-253,270)
     CF_SENSOR = 1u << 1,
+    CF_OFFSET = 1u << 2,  // offset.translation != 0 (snapshot needs coff)
 };
 constexpr uint32_t NO_SLOT = 0xffffffffu;
 constexpr int32_t BODY_NO_COLLIDER = -1;  // body_col[] encoding; <= -2 : multi-collider body (handled by k_multi)
@@ -68,6 +69,7 @@ struct SubstepParams {
 };
 
 struct BodyArrays {
+    // device-authoritative state
     float2* pos;
     float2* pos_old;
     float2* acc;
@@ -77,21 +79,19 @@ struct BodyArrays {
     float* rot;
     float* angvel;
     float* torque;
+    // host-authoritative, packed so that a body needs two 8-byte loads
     const float* inertia;
-    const float* mass;
-    const float* gmod;
-    const uint32_t* bflags;
-    const int32_t* body_col;
+    const uint2* binfo;      // (BF_* flags, body_col)
+    const float2* bmg;       // (calculated_mass, gravity_mod)
 };
 
 struct ColliderArrays {
-    float2* cabs;            // snapshot translation
-    const float2* coff;      // offset.translation
-    const float* crad;
-    const uint2* cgroups;    // (memberships, filter)
-    const uint32_t* cparent; // body slot
-    const uint32_t* cflags;
+    float2* cabs;            // snapshot translation (device-authoritative)
     uint2* ccell;            // (cell index, rank within cell) for the next table
+    // host-authoritative
+    const float2* coff;      // offset.translation (only read when CF_OFFSET is set)
+    const uint4* cconst;     // (radius bits, CF_* flags, memberships, filter)
+    const uint32_t* cparent; // body slot
 };
 
 struct Broadphase {

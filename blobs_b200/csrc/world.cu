@@ -66,8 +66,8 @@ World::~World() {
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
-    mass.d.release(); inertia.d.release(); gmod.d.release(); bflags.d.release(); body_col.d.release();
-    coff.d.release(); crad.d.release(); cgroups.d.release(); cparent.d.release(); cflags.d.release();
+    inertia.d.release(); binfo.d.release(); bmg.d.release();
+    coff.d.release(); cconst.d.release(); cparent.d.release();
     pos.release(); pos_old.release(); acc.release(); vel.release(); vreq.release(); cabs.release();
     has_vreq.release(); rot.release(); angvel.release(); torque.release(); ccell.release();
     d_pending.release(); d_pending_col.release();
@@ -186,14 +186,12 @@ int World::flush_writes() {
 BodyArrays World::body_arrays() {
     BodyArrays B;
     B.pos = pos.d; B.pos_old = pos_old.d; B.acc = acc.d; B.vel = vel.d; B.vreq = vreq.d; B.has_vreq = has_vreq.d;
-    B.rot = rot.d; B.angvel = angvel.d; B.torque = torque.d; B.inertia = inertia.d.d; B.mass = mass.d.d; B.gmod = gmod.d.d;
-    B.bflags = bflags.d.d; B.body_col = body_col.d.d;
+    B.rot = rot.d; B.angvel = angvel.d; B.torque = torque.d; B.inertia = inertia.d.d; B.binfo = binfo.d.d; B.bmg = bmg.d.d;
     return B;
 }
 ColliderArrays World::col_arrays() {
     ColliderArrays C;
-    C.cabs = cabs.d; C.coff = coff.d.d; C.crad = crad.d.d; C.cgroups = cgroups.d.d; C.cparent = cparent.d.d;
-    C.cflags = cflags.d.d; C.ccell = ccell.d;
+    C.cabs = cabs.d; C.ccell = ccell.d; C.coff = coff.d.d; C.cconst = cconst.d.d; C.cparent = cparent.d.d;
     return C;
 }
 Constraints World::constraints_pod() const {
@@ -215,10 +213,9 @@ int World::body_insert(const BlobsBodyDesc& d, uint64_t* out) {
     b.type = d.body_type;
     b.rot_active = d.rotation != 0.0f;
     const size_t n = bodies.slots();
-    mass.resize(n, 1.0f); inertia.resize(n, 1.0f); gmod.resize(n, 1.0f); bflags.resize(n, 0u); body_col.resize(n, BODY_NO_COLLIDER);
-    mass.set(s, 1.0f);     // RigidBodyBuilder::build rigid_body.rs:385-388
+    inertia.resize(n, 1.0f); bmg.resize(n, make_float2(1.0f, 1.0f)); binfo.resize(n, make_uint2(0u, (uint32_t)BODY_NO_COLLIDER));
+    bmg.set(s, make_float2(1.0f, d.gravity_mod));  // calculated_mass = 1: RigidBodyBuilder::build rigid_body.rs:385-388
     inertia.set(s, 1.0f);
-    gmod.set(s, d.gravity_mod);
     BodyWrite& w = stage(s);
     w.mask = BW_POS | BW_POS_OLD | BW_ACC | BW_VEL | BW_VREQ | BW_ROT | BW_ANGVEL | BW_TORQUE;
     w.pos = make_float2(d.position.x, d.position.y);
@@ -259,7 +256,7 @@ void World::update_mass_and_inertia(uint32_t bs) {
     if (m == 0.0f) m = 1.0f;
     if (in == 0.0f) in = 1.0f;
     b.com = BlobsVec2{wx / m, wy / m};
-    mass.set(bs, m);
+    set_mass(bs, m);
     inertia.set(bs, in);
     bp_dirty = true;  // records carry the parent's mass
 }
@@ -316,7 +313,7 @@ int World::body_get(uint64_t h, BlobsBodyState* out) {
     out->calculated_velocity = {v.x, v.y}; out->velocity_request = {vr.x, vr.y}; out->has_velocity_request = hv;
     out->rotation = r; out->angular_velocity = w; out->torque = t;
     out->center_of_mass = b.com; out->scale = b.scale;
-    out->calculated_mass = mass.h[s]; out->inertia = inertia.h[s]; out->gravity_mod = gmod.h[s];
+    out->calculated_mass = bmg.h[s].x; out->inertia = inertia.h[s]; out->gravity_mod = bmg.h[s].y;
     out->body_type = b.type; out->user_data_lo = b.ud_lo; out->user_data_hi = b.ud_hi;
     return BLOBS_OK;
 }
@@ -348,11 +345,11 @@ int World::body_set(uint64_t h, const BlobsBodyState& s, uint32_t mask) {
         if (mask & BLOBS_BODY_ROTATION) { w.mask |= BW_ROT; w.rot = s.rotation; if (shadow_valid) sh_rot[slot] = w.rot; if (s.rotation != 0.f) b.rot_active = true; }
         if (mask & BLOBS_BODY_ANGULAR_VELOCITY) { w.mask |= BW_ANGVEL; w.angvel = s.angular_velocity; if (s.angular_velocity != 0.f) b.rot_active = true; }
         if (mask & BLOBS_BODY_TORQUE) { w.mask |= BW_TORQUE; w.torque = s.torque; if (s.torque != 0.f) b.rot_active = true; }
-        if (b.rot_active && !(bflags.h[slot] & BF_ROT)) topo_dirty = true;
+        if (b.rot_active && !(binfo.h[slot].x & BF_ROT)) topo_dirty = true;
     }
-    if (mask & BLOBS_BODY_MASS) { mass.set(slot, s.calculated_mass); bp_dirty = true; }
+    if (mask & BLOBS_BODY_MASS) { set_mass(slot, s.calculated_mass); bp_dirty = true; }
     if (mask & BLOBS_BODY_INERTIA) inertia.set(slot, s.inertia);
-    if (mask & BLOBS_BODY_GRAVITY_MOD) gmod.set(slot, s.gravity_mod);
+    if (mask & BLOBS_BODY_GRAVITY_MOD) set_gmod(slot, s.gravity_mod);
     if (mask & BLOBS_BODY_TYPE) { if (b.type != s.body_type) { b.type = s.body_type; topo_dirty = true; } }
     if (mask & BLOBS_BODY_USER_DATA) { b.ud_lo = s.user_data_lo; b.ud_hi = s.user_data_hi; }
     if (mask & BLOBS_BODY_SCALE) b.scale = s.scale;
@@ -386,7 +383,7 @@ int World::body_apply_force(uint64_t h, BlobsVec2 f) {
     }
     BodyWrite& w = stage(slot);
     w.mask |= BW_ADD_ACC;
-    const float m = mass.h[slot];
+    const float m = bmg.h[slot].x;
     w.acc = make_float2(f.x / m, f.y / m);
     return BLOBS_OK;
 }
@@ -408,11 +405,13 @@ int World::collider_insert(const BlobsColliderDesc& d, uint64_t parent, uint64_t
     hc[s].desc = d;
     hc[s].parent = parent;
     const size_t n = cols.slots();
-    coff.resize(n, make_float2(0.f, 0.f)); crad.resize(n, 0.f); cgroups.resize(n, make_uint2(0, 0));
-    cparent.resize(n, NO_SLOT); cflags.resize(n, 0u);
+    coff.resize(n, make_float2(0.f, 0.f)); cconst.resize(n, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(n, NO_SLOT);
     coff.set(s, make_float2(d.offset.translation.x, d.offset.translation.y));
-    crad.set(s, d.radius);
-    cgroups.set(s, make_uint2(d.memberships, d.filter));
+    {
+        uint32_t rbits;
+        std::memcpy(&rbits, &d.radius, 4);
+        cconst.set(s, make_uint4(rbits, 0u, d.memberships, d.filter));  // flags are resolved in rebuild_topology
+    }
     pending_col.push_back(ColWrite{s, make_float2(d.absolute_transform.translation.x, d.absolute_transform.translation.y)});
     HBody& b = hb[h_slot(parent)];
     b.colliders.push_back(h);  // collider.rs:179-181
@@ -528,8 +527,8 @@ int World::rebuild_topology() {
     const size_t nb = bodies.slots(), nc = cols.slots();
     topo_error = 0;
     topo_error_msg.clear();
-    bflags.resize(nb, 0u); body_col.resize(nb, BODY_NO_COLLIDER); mass.resize(nb, 1.0f); inertia.resize(nb, 1.0f); gmod.resize(nb, 1.0f);
-    coff.resize(nc, make_float2(0.f, 0.f)); crad.resize(nc, 0.f); cgroups.resize(nc, make_uint2(0, 0)); cparent.resize(nc, NO_SLOT); cflags.resize(nc, 0u);
+    binfo.resize(nb, make_uint2(0u, (uint32_t)BODY_NO_COLLIDER)); bmg.resize(nb, make_float2(1.0f, 1.0f)); inertia.resize(nb, 1.0f);
+    coff.resize(nc, make_float2(0.f, 0.f)); cconst.resize(nc, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(nc, NO_SLOT);
 
     // springs (slot order) -> per-body CSR in spring order
     std::vector<SpringParams> sp;
@@ -572,7 +571,7 @@ int World::rebuild_topology() {
             const HJoint& x = hj[s];
             if (!bodies.valid(x.a) || !bodies.valid(x.b)) { topo_error = BLOBS_ERR_DANGLING; topo_error_msg = "joint references a removed rigid body (unwrap on None, physics.rs:427-432)"; continue; }
             const uint32_t a = h_slot(x.a), b = h_slot(x.b);
-            if (!(mass.h[a] > 0.0f) || !(mass.h[b] > 0.0f)) { topo_error = BLOBS_ERR_MASS; topo_error_msg = "assertion failed: calculated_mass > 0.0 (physics.rs:447-448)"; }
+            if (!(bmg.h[a].x > 0.0f) || !(bmg.h[b].x > 0.0f)) { topo_error = BLOBS_ERR_MASS; topo_error_msg = "assertion failed: calculated_mass > 0.0 (physics.rs:447-448)"; }
             jp.push_back(JointParams{a, b, x.aa.x, x.aa.y, x.ab.x, x.ab.y, x.distance, x.target});
             hb[a].n_joints++;
             hb[b].n_joints++;
@@ -608,8 +607,13 @@ int World::rebuild_topology() {
                 n_active_cols++;
             }
             if (x.desc.is_sensor) f |= CF_SENSOR;
+            if (x.desc.offset.translation.x != 0.0f || x.desc.offset.translation.y != 0.0f) f |= CF_OFFSET;
         }
-        cflags.set(c, f);
+        {
+            uint4 e = cconst.h[c];
+            e.y = f;
+            cconst.set(c, e);
+        }
         cparent.set(c, p);
     }
 
@@ -640,8 +644,7 @@ int World::rebuild_topology() {
                 v_mb_off.push_back((uint32_t)v_mb_cols.size());
             } else n_simple++;
         }
-        bflags.set(b, f);
-        body_col.set(b, bc);
+        binfo.set(b, make_uint2(f, (uint32_t)bc));
     }
     n_multi = (uint32_t)v_mb_body.size();
 
@@ -663,8 +666,8 @@ int World::flush() {
         int rc = rebuild_topology();
         if (rc) return rc;
     }
-    CU(mass.flush(stream)); CU(inertia.flush(stream)); CU(gmod.flush(stream)); CU(bflags.flush(stream)); CU(body_col.flush(stream));
-    CU(coff.flush(stream)); CU(crad.flush(stream)); CU(cgroups.flush(stream)); CU(cparent.flush(stream)); CU(cflags.flush(stream));
+    CU(inertia.flush(stream)); CU(binfo.flush(stream)); CU(bmg.flush(stream));
+    CU(coff.flush(stream)); CU(cconst.flush(stream)); CU(cparent.flush(stream));
     if (con_dirty) {
         std::vector<float4> kc(con_pos.size());
         for (size_t i = 0; i < kc.size(); ++i) kc[i] = make_float4(con_pos[i].x, con_pos[i].y, con_r[i], 0.f);
@@ -748,7 +751,7 @@ int World::rebuild_broadphase() {
     k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch);
     launches++;
     if (nc) {
-        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), mass.d.d, tab_next, hot_next, cold_next, (uint32_t)nc);
+        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), bmg.d.d, tab_next, hot_next, cold_next, (uint32_t)nc);
         launches++;
     }
     CU(cudaGetLastError());
@@ -858,7 +861,7 @@ int World::launch_substep(const SubstepParams& P) {
     rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch); });
     if (rc) return rc;
     if (nc) {
-        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, mass.d.d, bp.tab_next, hot_next, cold_next, nc); });
+        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, bmg.d.d, bp.tab_next, hot_next, cold_next, nc); });
         if (rc) return rc;
     }
     cur_is_a = !cur_is_a;
@@ -1006,7 +1009,7 @@ int World::download_bodies(BlobsBodyState* st, uint64_t* handles, size_t cap) {
         o.calculated_velocity = {v[s].x, v[s].y}; o.velocity_request = {vr[s].x, vr[s].y}; o.has_velocity_request = hv[s];
         o.rotation = r[s]; o.angular_velocity = w[s]; o.torque = t[s];
         o.center_of_mass = b.com; o.scale = b.scale;
-        o.calculated_mass = mass.h[s]; o.inertia = inertia.h[s]; o.gravity_mod = gmod.h[s];
+        o.calculated_mass = bmg.h[s].x; o.inertia = inertia.h[s]; o.gravity_mod = bmg.h[s].y;
         o.body_type = b.type; o.user_data_lo = b.ud_lo; o.user_data_hi = b.ud_hi;
     }
     return BLOBS_OK;

@@ -246,13 +246,15 @@ class World {
     std::vector<HJoint> hj;
 
     // host-authoritative device arrays
-    Mirrored<float> mass, inertia, gmod;
-    Mirrored<uint32_t> bflags;
-    Mirrored<int32_t> body_col;
+    Mirrored<float> inertia;
+    Mirrored<uint2> binfo;    // (BF_* flags, body_col)
+    Mirrored<float2> bmg;     // (calculated_mass, gravity_mod)
     Mirrored<float2> coff;
-    Mirrored<float> crad;
-    Mirrored<uint2> cgroups;
-    Mirrored<uint32_t> cparent, cflags;
+    Mirrored<uint4> cconst;   // (radius bits, CF_* flags, memberships, filter)
+    Mirrored<uint32_t> cparent;
+    float mass_of(uint32_t s) const { return bmg.h[s].x; }
+    void set_mass(uint32_t s, float m) { float2 e = bmg.h[s]; e.x = m; bmg.set(s, e); }
+    void set_gmod(uint32_t s, float g) { float2 e = bmg.h[s]; e.y = g; bmg.set(s, e); }
     // device-authoritative body state
     DevBuf<float2> pos, pos_old, acc, vel, vreq, cabs;
     DevBuf<uint8_t> has_vreq;

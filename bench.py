@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2_varied", "cfg2_dense", "cfg4", "cfg2_4m", "cfg2_16m"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--tune", type=int, default=0, help="kernel variant selector (BLOBS_PARAM_TUNE)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     return ap.parse_args()
 
@@ -54,7 +55,7 @@ def make_scene(name, seed=1):
     if name == "cfg2_varied":
         return S.cfg2(seed, varied=True), "cfg2 variant: 1048576 spheres r~U[0.25,0.5)"
     if name == "cfg2_dense":
-        return S.cfg2_dense(seed, side=1024), "cfg2 dense variant: 1048576 spheres r=0.5 pitch 0.9 (overlapping) in a tight circle"
+        return S.cfg2_dense(seed, side=1024), "cfg2 dense variant: 1048576 spheres r=0.5 on a pitch-0.9 lattice (every sphere starts overlapping its 4 neighbours)"
     if name == "cfg2_4m":
         return S.cfg2(seed, side=2048), "cfg2 scaled: 4194304 spheres"
     if name == "cfg2_16m":
@@ -206,6 +207,8 @@ def run_ours(args):
     sc, desc = make_scene(args.workload, seed=1 + rank)
     w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
     S.build(w, sc)
+    if args.tune:
+        w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
     n = sc.n_colliders
     nb = sc.n_bodies
 

@@ -42,11 +42,15 @@ __device__ __forceinline__ uint32_t cell_index(const GridDesc& g, int cx, int cy
     return fastmod(ubias(cy), g.MH, g.H) * g.W + fastmod(ubias(cx), g.MW, g.W);
 }
 
-__device__ __forceinline__ Rec make_rec(const float4 h, const float4 c) {
+__device__ __forceinline__ Rec make_rec(const float4 h, const uint4 c) {
     Rec r;
     r.x = h.x; r.y = h.y; r.r = h.z; r.slot_sensor = __float_as_uint(h.w);
-    r.m = c.x; r.memb = __float_as_uint(c.y); r.filt = __float_as_uint(c.z); r.parent = __float_as_uint(c.w);
+    r.m = __uint_as_float(c.x); r.memb = c.y; r.filt = c.z; r.parent = c.w;
     return r;
+}
+__device__ __forceinline__ Rec load_rec(const Broadphase& bp, const uint4* __restrict__ ccold, uint32_t k) {
+    const float4 h = __ldg(bp.hot + k);
+    return make_rec(h, __ldg(ccold + (__float_as_uint(h.w) & 0x7fffffffu)));
 }
 
 // Cell range that can hold a partner of a sphere at (x, y) with radius r, on the toroidal table.
@@ -73,7 +77,8 @@ __device__ __forceinline__ CellRange cell_range(const GridDesc& g, float x, floa
 
 // Generic neighbourhood walk: calls f(const Rec&) for every record in the range (any span, row/column wrap).
 template <class F>
-__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, float x, float y, float r, F&& f) {
+__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, float x, float y,
+                                                   float r, F&& f) {
     const CellRange R = cell_range(g, x, y, r);
     const uint32_t n1 = min(R.nx, g.W - R.c0);  // cells before the row wraps
     for (uint32_t j = 0; j < R.ny; ++j) {
@@ -81,11 +86,11 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broa
         if (row >= g.H) row -= g.H;
         const uint32_t base = row * g.W;
         uint32_t lo = __ldg(bp.tab + base + R.c0), hi = __ldg(bp.tab + base + R.c0 + n1);
-        for (uint32_t k = lo; k < hi; ++k) f(make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)));
+        for (uint32_t k = lo; k < hi; ++k) f(load_rec(bp, ccold, k));
         if (n1 < R.nx) {  // wrapped part of the row
             lo = __ldg(bp.tab + base);
             hi = __ldg(bp.tab + base + (R.nx - n1));
-            for (uint32_t k = lo; k < hi; ++k) f(make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)));
+            for (uint32_t k = lo; k < hi; ++k) f(load_rec(bp, ccold, k));
         }
     }
 }
@@ -244,28 +249,29 @@ __device__ __forceinline__ void take_candidate(const SelfCol& s, const Rec& o, C
 
 // Generic gather (any cell span): used by k_multi and as the slow path of gather_single.
 template <bool ORDERED, class KEY>
-__device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
-                                               GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
-    for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
+__device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, const SelfCol& s,
+                                               ContactList<KEY>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
+                                               DeviceStats* stats) {
+    for_each_candidate(g, bp, ccold, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
 }
 
 // Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap):
 //  1. the six cell-table reads are issued together;
 //  2. SCAN: the three row spans are treated as one flattened candidate sequence; hot halves (16 B: x, y, r, slot) are
-//     fetched GATHER_BATCH at a time (all loads in flight before the first use) and a conservative squared-distance
+//     fetched BATCH at a time (all loads in flight before the first use) and a conservative squared-distance
 //     prefilter marks survivors in a 32-bit mask — no sqrt, no divide, no cold half;
 //  3. RESOLVE: survivors are popped in a loop that all lanes of the warp run together (trip count = max survivors per
 //     lane), each doing the exact narrowphase on hot + cold halves.
-// Prefilter soundness: a contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > md*md*1.0001 implies sqrt(d2) > md*(1+4e-5),
-// which rounding (2^-24) cannot bring below md. NaNs fail the '>' and fall through to the exact test.
-constexpr int GATHER_BATCH = 8;
-
-template <bool ORDERED, class KEY>
-__device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphase& bp, const SelfCol& s, ContactList<KEY>& list,
-                                              GatherOut& out, const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
+// Prefilter soundness: a contact needs fl(sqrt(d2)) < md (md = fl(ra+rb)); d2 > (md*1.00005)^2 implies sqrt(d2) > md*(1+4e-5)
+// even after the ~1e-7 relative rounding of the (FMA-contracted, order-free) prefilter arithmetic, which rounding of the
+// exact path (2^-24) cannot bring below md. NaNs fail the '>' and fall through to the exact test.
+template <bool ORDERED, class KEY, int BATCH>
+__device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, const SelfCol& s,
+                                              ContactList<KEY>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
+                                              DeviceStats* stats) {
     const CellRange R = cell_range(g, s.x, s.y, s.r);
     if (R.ny > 3u || R.c0 + R.nx > g.W) {
-        gather_generic<ORDERED, KEY>(g, bp, s, list, out, rec, vel, stats);
+        gather_generic<ORDERED, KEY>(g, bp, ccold, s, list, out, rec, vel, stats);
         return;
     }
     uint32_t lo[3], cnt[3];
@@ -282,39 +288,40 @@ __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphas
     const uint32_t n0 = cnt[0], n01 = cnt[0] + cnt[1], total = n01 + cnt[2];
     // flattened candidate index -> record index; rebased so that k = t + off_j inside row j
     const uint32_t off0 = lo[0], off1 = lo[1] - n0, off2 = lo[2] - n01;
+    const float srk = s.r * 1.00005f;
     for (uint32_t base = 0; base < total; base += 32u) {
         const uint32_t lim = min(32u, total - base);
         uint32_t mask = 0;
-        for (uint32_t t0 = 0; t0 < lim; t0 += GATHER_BATCH) {
-            float4 h[GATHER_BATCH];
+        for (uint32_t t0 = 0; t0 < lim; t0 += BATCH) {
+            float4 h[BATCH];
 #pragma unroll
-            for (int i = 0; i < GATHER_BATCH; ++i) {
+            for (int i = 0; i < BATCH; ++i) {
                 const uint32_t t = base + t0 + i;
                 const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-                if (t0 + i < lim) h[i] = __ldg(bp.hot + k);
-                else h[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(s.slot));  // reads as "self": skipped
+                h[i] = __ldg(bp.hot + (t0 + i < lim ? k : lo[0]));  // out-of-range slots re-read a valid record (arrays are padded by 1)
             }
 #pragma unroll
-            for (int i = 0; i < GATHER_BATCH; ++i) {
+            for (int i = 0; i < BATCH; ++i) {
                 const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
                 const float dx = s.x - h[i].x, dy = s.y - h[i].y;
-                const float d2 = dx * dx + dy * dy;
-                const float md = s.r + h[i].z;
-                if (oslot != s.slot && !(d2 > md * md * 1.0001f)) mask |= 1u << (t0 + i);
+                const float d2 = __fmaf_rn(dx, dx, dy * dy);
+                const float mdk = __fmaf_rn(h[i].z, 1.00005f, srk);  // (ra + rb) * 1.00005
+                if (t0 + i < lim && oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << (t0 + i);
             }
         }
         while (mask) {
             const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
             mask &= mask - 1u;
             const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-            take_candidate<ORDERED, KEY>(s, make_rec(__ldg(bp.hot + k), __ldg(bp.cold + k)), list, out, rec, vel, stats);
+            take_candidate<ORDERED, KEY>(s, load_rec(bp, ccold, k), list, out, rec, vel, stats);
         }
     }
 }
 
 // Rare path when a body has more than LIST_CAP contributions: repeated selection of the next key in order
 // (k+1 neighbourhood scans, no storage). Everything by value so the callers keep their state in registers.
-__device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase bp, const SelfCol* cols, int ncols, float px, float py) {
+__device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase bp, const uint4* __restrict__ ccold, const SelfCol* cols, int ncols,
+                                                        float px, float py) {
     bool have_last = false;
     unsigned long long last = 0;
     for (;;) {
@@ -323,7 +330,7 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
         float bx = 0.f, by = 0.f;
         for (int ci = 0; ci < ncols; ++ci) {
             const SelfCol s = cols[ci];
-            for_each_candidate(g, bp, s.x, s.y, s.r, [&](const Rec& o) {
+            for_each_candidate(g, bp, ccold, s.x, s.y, s.r, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
                 if (c.coincident) {
@@ -413,8 +420,18 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
 // Collider snapshot (physics.rs:360-366): abs.translation = M(rot) * offset.translation + pos, with
 // glam's Mat2::from_angle columns (cos, sin), (-sin, cos) and M*v = x_axis*v.x + y_axis*v.y.
 // Then bins the collider into the next broadphase table.
-__device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t c,
-                                                 uint32_t cflags, float sx, float sy, float rot) {
+// Bins one collider: rank within its cell (atomic on the cell counter) + warp-aggregated add to the counter of the
+// scan tile that owns the cell (lanes of a warp mostly share a tile, so this is ~1 extra atomic per warp).
+__device__ __forceinline__ uint32_t bin_collider(uint32_t* tab_next, uint32_t* tile_next, uint32_t cell) {
+    const uint32_t rank = atomicAdd(tab_next + cell, 1u);
+    const uint32_t tile = cell >> SCAN_TILE_SHIFT;
+    const unsigned int peers = __match_any_sync(__activemask(), tile);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(tile_next + tile, (uint32_t)__popc(peers));
+    return rank;
+}
+
+__device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t* tile_next,
+                                                 uint32_t c, uint32_t cflags, float sx, float sy, float rot) {
     float2 off = make_float2(0.f, 0.f);
     if (cflags & CF_OFFSET) off = Cc.coff[c];
     float sn = 0.0f, cs = 1.0f;
@@ -423,8 +440,7 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
     const float ay = fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy);
     Cc.cabs[c] = make_float2(ax, ay);
     const uint32_t cell = cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
-    const uint32_t rank = atomicAdd(tab_next + cell, 1u);
-    Cc.ccell[c] = make_uint2(cell, rank);
+    Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,8 +451,8 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
 // round 2 = six cell-table entries; round 3 = hot record halves; round 4 = cold halves of prefilter survivors;
 // round 5 = the binning atomic.
 // ------------------------------------------------------------------------------------------------
-template <bool FUSED, bool ORDERED>
-__global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+template <bool FUSED, bool ORDERED, int BATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                               Broadphase bp, Recording rec, DeviceStats* stats) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
@@ -477,14 +493,14 @@ __global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Co
                 s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.sensor = (cc.y & CF_SENSOR) != 0u;
                 ContactList<uint32_t> list;
                 list.clear();
-                gather_single<ORDERED, uint32_t>(g, bp, s, list, out, rec, B.vel, stats);
+                gather_single<ORDERED, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
                 if (ORDERED) {
                     if (!list.overflow) {
                         for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
                     } else {
                         n_over = 1;
                         SelfCol s2 = s;  // stack copy only on this rare path
-                        p = apply_contacts_rescan(g, bp, &s2, 1, p.x, p.y);
+                        p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
                     }
                 } else {
                     p.x = fadd(p.x, out.fx);
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(256, 3) k_main(SubstepParams P, GridDesc g, Co
         if (FUSED) {
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
-            if (active_col) publish_collider(g, Cc, bp.tab_next, (uint32_t)col, cc.y, sx, sy, rot);
+            if (active_col) publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, sx, sy, rot);
         } else {
             B.pos[b] = p;
         }
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             for (uint32_t k = c0; k < c1; ++k) {
                 SelfCol s;
                 if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
-                gather_generic<ORDERED, unsigned long long>(g, bp, s, list, out, rec, B.vel, stats);
+                gather_generic<ORDERED, unsigned long long>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
             if (ORDERED) {
                 if (!list.overflow) {
@@ -568,7 +584,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                         cols[nc++] = s;
                     }
                     if (fits) {
-                        p = apply_contacts_rescan(g, bp, cols, nc, p.x, p.y);
+                        p = apply_contacts_rescan(g, bp, Cc.ccold, cols, nc, p.x, p.y);
                     } else {
                         ContactList<unsigned long long> dummy;
                         dummy.clear();
@@ -580,7 +596,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                         for (uint32_t k = c0; k < c1; ++k) {
                             SelfCol s;
                             if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
-                            gather_generic<false, unsigned long long>(g, bp, s, dummy, o2, off, B.vel, stats);
+                            gather_generic<false, unsigned long long>(g, bp, Cc.ccold, s, dummy, o2, off, B.vel, stats);
                         }
                         p.x = fadd(p.x, o2.fx);
                         p.y = fadd(p.y, o2.fy);
@@ -597,7 +613,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             for (uint32_t k = c0; k < c1; ++k) {
                 const uint32_t c = mb_cols[k];
                 const uint32_t cf = Cc.cconst[c].y;
-                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, c, cf, sx, sy, rot);
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, sx, sy, rot);
             }
         } else {
             B.pos[b] = p;
@@ -616,8 +632,8 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
 // constraints + binning for every body.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                   uint32_t* tab_next, DeviceStats* stats, const uint32_t* __restrict__ mb_off,
-                                                   const uint32_t* __restrict__ mb_cols) {
+                                                   uint32_t* tab_next, uint32_t* tile_next, DeviceStats* stats,
+                                                   const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.n_bodies) return;
     const uint2 info = B.binfo[b];
@@ -629,13 +645,13 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
     integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
     if (col >= 0) {
         const uint32_t cf = Cc.cconst[col].y;
-        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, (uint32_t)col, cf, sx, sy, rot);
+        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, sx, sy, rot);
     } else if (col <= -2) {
         const uint32_t i = (uint32_t)(-(col + 2));
         for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
             const uint32_t c = mb_cols[k];
             const uint32_t cf = Cc.cconst[c].y;
-            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, c, cf, sx, sy, rot);
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, sx, sy, rot);
         }
     }
 }
@@ -643,30 +659,26 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
 // ------------------------------------------------------------------------------------------------
 // K-count: bins every active collider from its current snapshot (used when the broadphase is (re)built outside a step).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, uint32_t* tab_next, uint32_t n_colliders) {
+__global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, uint32_t* tab_next, uint32_t* tile_next, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
     if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
     const float2 a = Cc.cabs[c];
     const uint32_t cell = cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
-    const uint32_t rank = atomicAdd(tab_next + cell, 1u);
-    Cc.ccell[c] = make_uint2(cell, rank);
+    Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-scan: single-pass exclusive prefix sum (decoupled look-back) over the cell counts, in place; entry [n-1] is the
-// sentinel (count 0) and ends up holding the total. Also zeroes `zero_me` (the table that becomes tab_next next round).
-// status word: epoch[63:34] | flag[33:32] | value[31:0]; stale epochs read as "not ready", so no per-launch memset.
+// K-scan: exclusive prefix sum over the cell counts, in place; entry [n-1] is the sentinel (count 0) and ends up holding the
+// total. One block per tile of SCAN_TILE cells; the tile totals were accumulated by the binning itself (bin_collider), so each
+// block derives its own starting offset by summing the totals of the tiles before it — no inter-block dependency, no
+// look-back spinning. Also zeroes `zero_me` and `tile_zero` (the table / tile totals that become "next" after the swap).
 // ------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, uint32_t flag, uint32_t v) {
-    return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | v;
-}
-
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ zero_me,
-                                                       uint32_t n_zero, unsigned long long* status, uint32_t epoch) {
+                                                       uint32_t n_zero, const uint32_t* __restrict__ tile_cur,
+                                                       uint32_t* __restrict__ tile_zero) {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-    __shared__ uint32_t tile_excl;
+    __shared__ uint32_t warp_pre[SCAN_THREADS / 32];
     const uint32_t tile = blockIdx.x;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -682,7 +694,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 #pragma unroll
         for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? data[base + i] : 0u;
     }
-    // zero the other table (same index space)
+    // totals of the tiles before this one
+    uint32_t pre = 0;
+    for (uint32_t i = threadIdx.x; i < tile; i += SCAN_THREADS) pre += tile_cur[i];
+    pre = __reduce_add_sync(0xffffffffu, pre);
+    // zero the buffers that become "next"
     if (base + SCAN_ITEMS <= n_zero) {
 #pragma unroll
         for (int q = 0; q < SCAN_ITEMS / 4; ++q) *reinterpret_cast<uint4*>(zero_me + base + 4 * q) = make_uint4(0, 0, 0, 0);
@@ -691,57 +707,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
         for (int i = 0; i < SCAN_ITEMS; ++i)
             if (base + i < n_zero) zero_me[base + i] = 0u;
     }
+    if (threadIdx.x == 0) tile_zero[tile] = 0u;
 
     uint32_t tsum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) tsum += v[i];
-    // warp inclusive scan of thread sums
-    uint32_t incl = tsum;
+    uint32_t incl = tsum;  // warp inclusive scan of thread sums
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
     if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 0) warp_pre[warp] = pre;
     __syncthreads();
-    uint32_t warp_off = 0, block_sum = 0;
+    uint32_t off = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        const uint32_t s = warp_sums[w];
-        if (w < (int)warp) warp_off += s;
-        block_sum += s;
+        off += warp_pre[w];
+        if (w < (int)warp) off += warp_sums[w];
     }
-    // publish the tile aggregate, then look back
-    if (warp == 0) {
-        volatile unsigned long long* st = status;
-        if (lane == 0) st[tile] = scan_pack(epoch, tile == 0 ? 2u : 1u, block_sum);
-        uint32_t excl = 0;
-        int pred = (int)tile - 1;
-        while (pred >= 0) {
-            const int idx = pred - (int)lane;
-            unsigned long long s = scan_pack(epoch, 2u, 0u);  // lanes past tile 0 read as an inclusive zero
-            if (idx >= 0) {
-                do { s = st[idx]; } while ((uint32_t)(s >> 34) != epoch || ((s >> 32) & 3ull) == 0ull);
-            }
-            const uint32_t flag = (uint32_t)(s >> 32) & 3u;
-            const uint32_t val = (uint32_t)s;
-            const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
-            if (incl_mask) {
-                const int first = __ffs(incl_mask) - 1;   // nearest predecessor holding an inclusive prefix
-                const uint32_t contrib = ((int)lane <= first) ? val : 0u;
-                excl += __reduce_add_sync(0xffffffffu, contrib);
-                break;
-            }
-            excl += __reduce_add_sync(0xffffffffu, val);
-            pred -= 32;
-        }
-        if (lane == 0) {
-            if (tile != 0) st[tile] = scan_pack(epoch, 2u, excl + block_sum);
-            tile_excl = excl;
-        }
-    }
-    __syncthreads();
-    uint32_t run = tile_excl + warp_off + (incl - tsum);
+    uint32_t run = off + (incl - tsum);
     uint32_t o[SCAN_ITEMS];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) { o[i] = run; run += v[i]; }
@@ -757,20 +743,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-scatter: writes the two 16-byte record halves of every active collider at cell_start[cell] + rank.
+// K-scatter: writes the 16-byte hot half of every active collider at cell_start[cell] + rank (the cold half is static).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const float2* __restrict__ bmg, const uint32_t* __restrict__ tab,
-                                                 float4* __restrict__ hot, float4* __restrict__ cold, uint32_t n_colliders) {
+__global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const uint32_t* __restrict__ tab, float4* __restrict__ hot,
+                                                 uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
     const uint4 cc = Cc.cconst[c];
-    if (!(cc.y & CF_ACTIVE)) return;
     const uint2 cr = Cc.ccell[c];
     const float2 a = Cc.cabs[c];
-    const uint32_t parent = Cc.cparent[c];
+    if (!(cc.y & CF_ACTIVE)) return;
     const uint32_t dst = __ldg(tab + cr.x) + cr.y;
     hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
-    cold[dst] = make_float4(bmg[parent].x, __uint_as_float(cc.z), __uint_as_float(cc.w), __uint_as_float(parent));
 }
 
 // ------------------------------------------------------------------------------------------------

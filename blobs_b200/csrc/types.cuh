@@ -23,9 +23,11 @@ enum : uint32_t {
 constexpr uint32_t NO_SLOT = 0xffffffffu;
 constexpr int32_t BODY_NO_COLLIDER = -1;  // body_col[] encoding; <= -2 : multi-collider body (handled by k_multi)
 
-// One broadphase record per active collider, cell-sorted, stored as two 16-byte halves in separate arrays:
-//   hot  = (x, y, r, slot | is_sensor << 31)   — enough for the self test and the distance prefilter
-//   cold = (m, memberships, filter, parent)    — only fetched for candidates that survive the prefilter
+// Broadphase record of an active collider, as seen by the narrowphase. It is stored as two 16-byte halves:
+//   hot  = (x, y, r, slot | is_sensor << 31)   — cell-sorted array rebuilt every substep; enough for the self test and the
+//                                                 distance prefilter
+//   cold = (m, memberships, filter, parent)    — static per-collider array (ccold[slot]), only fetched for candidates that
+//                                                 survive the prefilter
 struct Rec {
     float x, y, r, m;          // snapshot translation (physics.rs:360-366), radius, parent body's calculated_mass
     uint32_t memb, filt;       // InteractionGroups (groups.rs:7-12)
@@ -92,13 +94,14 @@ struct ColliderArrays {
     const float2* coff;      // offset.translation (only read when CF_OFFSET is set)
     const uint4* cconst;     // (radius bits, CF_* flags, memberships, filter)
     const uint32_t* cparent; // body slot
+    const uint4* ccold;      // (parent's calculated_mass bits, memberships, filter, parent slot) — Rec cold half
 };
 
 struct Broadphase {
-    const float4* hot;       // current records (see Rec), read-only during the contact pass
-    const float4* cold;
+    const float4* hot;       // current cell-sorted hot halves (see Rec), read-only during the contact pass
     const uint32_t* tab;     // current cell starts, ncells + 1 entries
     uint32_t* tab_next;      // counts for the next table (zeroed)
+    uint32_t* tile_next;     // per-scan-tile totals of tab_next (zeroed), so k_scan needs no inter-block dependency
 };
 
 struct Recording {           // optional pair/event output
@@ -112,6 +115,8 @@ struct Recording {           // optional pair/event output
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_TILE_SHIFT = 13;
+static_assert((1 << SCAN_TILE_SHIFT) == SCAN_TILE, "tile shift");
 
 struct SpringParams { uint32_t a, b; float rest, k, c; };
 

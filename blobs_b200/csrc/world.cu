@@ -67,13 +67,13 @@ World::~World() {
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     inertia.d.release(); binfo.d.release(); bmg.d.release();
-    coff.d.release(); cconst.d.release(); cparent.d.release();
+    coff.d.release(); cconst.d.release(); cparent.d.release(); ccold.d.release();
     pos.release(); pos_old.release(); acc.release(); vel.release(); vreq.release(); cabs.release();
     has_vreq.release(); rot.release(); angvel.release(); torque.release(); ccell.release();
     d_pending.release(); d_pending_col.release();
     mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
     isl_off.release(); isl_joint.release(); d_springs.release(); d_joints.release();
-    hot_a.release(); hot_b.release(); cold_a.release(); cold_b.release(); tab_a.release(); tab_b.release(); scan_status.release();
+    hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
@@ -97,6 +97,7 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_BROADPHASE_CELL: bp_cell_override = (float)v; bp_dirty = true; break;
         case BLOBS_PARAM_CONTACT_MODE: contact_mode = (int)v; break;
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
+        case BLOBS_PARAM_TUNE: tune = (int)v; break;
         default: return fail(BLOBS_ERR_INVALID, "unknown param id");
     }
     return BLOBS_OK;
@@ -117,6 +118,7 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_BROADPHASE_CELL: *out = bp_cell_override; break;
         case BLOBS_PARAM_CONTACT_MODE: *out = contact_mode; break;
         case BLOBS_PARAM_FUSED: *out = allow_fused; break;
+        case BLOBS_PARAM_TUNE: *out = tune; break;
         default: return BLOBS_ERR_INVALID;
     }
     return BLOBS_OK;
@@ -191,7 +193,7 @@ BodyArrays World::body_arrays() {
 }
 ColliderArrays World::col_arrays() {
     ColliderArrays C;
-    C.cabs = cabs.d; C.ccell = ccell.d; C.coff = coff.d.d; C.cconst = cconst.d.d; C.cparent = cparent.d.d;
+    C.cabs = cabs.d; C.ccell = ccell.d; C.coff = coff.d.d; C.cconst = cconst.d.d; C.cparent = cparent.d.d; C.ccold = ccold.d.d;
     return C;
 }
 Constraints World::constraints_pod() const {
@@ -258,7 +260,7 @@ void World::update_mass_and_inertia(uint32_t bs) {
     b.com = BlobsVec2{wx / m, wy / m};
     set_mass(bs, m);
     inertia.set(bs, in);
-    bp_dirty = true;  // records carry the parent's mass
+    topo_dirty = true;  // ccold[] carries the parent's mass
 }
 
 int World::body_remove(uint64_t h) {
@@ -347,7 +349,7 @@ int World::body_set(uint64_t h, const BlobsBodyState& s, uint32_t mask) {
         if (mask & BLOBS_BODY_TORQUE) { w.mask |= BW_TORQUE; w.torque = s.torque; if (s.torque != 0.f) b.rot_active = true; }
         if (b.rot_active && !(binfo.h[slot].x & BF_ROT)) topo_dirty = true;
     }
-    if (mask & BLOBS_BODY_MASS) { set_mass(slot, s.calculated_mass); bp_dirty = true; }
+    if (mask & BLOBS_BODY_MASS) { set_mass(slot, s.calculated_mass); topo_dirty = true; }
     if (mask & BLOBS_BODY_INERTIA) inertia.set(slot, s.inertia);
     if (mask & BLOBS_BODY_GRAVITY_MOD) set_gmod(slot, s.gravity_mod);
     if (mask & BLOBS_BODY_TYPE) { if (b.type != s.body_type) { b.type = s.body_type; topo_dirty = true; } }
@@ -406,6 +408,7 @@ int World::collider_insert(const BlobsColliderDesc& d, uint64_t parent, uint64_t
     hc[s].parent = parent;
     const size_t n = cols.slots();
     coff.resize(n, make_float2(0.f, 0.f)); cconst.resize(n, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(n, NO_SLOT);
+    ccold.resize(n, make_uint4(0u, 0u, 0u, NO_SLOT));
     coff.set(s, make_float2(d.offset.translation.x, d.offset.translation.y));
     {
         uint32_t rbits;
@@ -529,6 +532,7 @@ int World::rebuild_topology() {
     topo_error_msg.clear();
     binfo.resize(nb, make_uint2(0u, (uint32_t)BODY_NO_COLLIDER)); bmg.resize(nb, make_float2(1.0f, 1.0f)); inertia.resize(nb, 1.0f);
     coff.resize(nc, make_float2(0.f, 0.f)); cconst.resize(nc, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(nc, NO_SLOT);
+    ccold.resize(nc, make_uint4(0u, 0u, 0u, NO_SLOT));
 
     // springs (slot order) -> per-body CSR in spring order
     std::vector<SpringParams> sp;
@@ -615,6 +619,12 @@ int World::rebuild_topology() {
             cconst.set(c, e);
         }
         cparent.set(c, p);
+        {
+            uint32_t mbits = 0;
+            if (p != NO_SLOT) { const float m = bmg.h[p].x; std::memcpy(&mbits, &m, 4); }
+            const uint4 e = cconst.h[c];
+            ccold.set(c, make_uint4(mbits, e.z, e.w, p));
+        }
     }
 
     // bodies
@@ -667,7 +677,7 @@ int World::flush() {
         if (rc) return rc;
     }
     CU(inertia.flush(stream)); CU(binfo.flush(stream)); CU(bmg.flush(stream));
-    CU(coff.flush(stream)); CU(cconst.flush(stream)); CU(cparent.flush(stream));
+    CU(coff.flush(stream)); CU(cconst.flush(stream)); CU(cparent.flush(stream)); CU(ccold.flush(stream));
     if (con_dirty) {
         std::vector<float4> kc(con_pos.size());
         for (size_t i = 0; i < kc.size(); ++i) kc[i] = make_float4(con_pos[i].x, con_pos[i].y, con_r[i], 0.f);
@@ -734,24 +744,26 @@ int World::rebuild_broadphase() {
     const size_t nc = cols.slots();
     const size_t tn = (size_t)grid.ncells + 1;
     CU(tab_a.ensure(tn + SCAN_ITEMS, stream)); CU(tab_b.ensure(tn + SCAN_ITEMS, stream));
-    CU(hot_a.ensure(std::max<size_t>(nc, 1), stream)); CU(hot_b.ensure(std::max<size_t>(nc, 1), stream));
-    CU(cold_a.ensure(std::max<size_t>(nc, 1), stream)); CU(cold_b.ensure(std::max<size_t>(nc, 1), stream));
-    CU(scan_status.ensure(cdiv(tn, SCAN_TILE) + 1, stream));
+    CU(hot_a.ensure(nc + 1, stream)); CU(hot_b.ensure(nc + 1, stream));   // +1: the scan may re-read index == #records
+    const unsigned ntiles = cdiv(tn, SCAN_TILE);
+    CU(tile_a.ensure(ntiles, stream)); CU(tile_b.ensure(ntiles, stream));
     CU(cudaMemsetAsync(tab_a.d, 0, tn * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(tab_b.d, 0, tn * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(tile_a.d, 0, tile_a.cap * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(tile_b.d, 0, tile_b.cap * sizeof(uint32_t), stream));
     uint32_t* tab_next = cur_is_a ? tab_b.d : tab_a.d;
     uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
+    uint32_t* tile_next = cur_is_a ? tile_b.d : tile_a.d;
+    uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
-    float4* cold_next = cur_is_a ? cold_b.d : cold_a.d;
     if (nc) {
-        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), tab_next, (uint32_t)nc);
+        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), tab_next, tile_next, (uint32_t)nc);
         launches++;
     }
-    if (++scan_epoch >= (1u << 30)) { scan_epoch = 1; CU(cudaMemsetAsync(scan_status.d, 0, scan_status.cap * sizeof(unsigned long long), stream)); }
-    k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch);
+    k_scan<<<ntiles, SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur);
     launches++;
     if (nc) {
-        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), bmg.d.d, tab_next, hot_next, cold_next, (uint32_t)nc);
+        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), tab_next, hot_next, (uint32_t)nc);
         launches++;
     }
     CU(cudaGetLastError());
@@ -799,12 +811,12 @@ int World::launch_substep(const SubstepParams& P) {
     const Constraints K = constraints_pod();
     Broadphase bp;
     bp.hot = cur_is_a ? hot_a.d : hot_b.d;
-    bp.cold = cur_is_a ? cold_a.d : cold_b.d;
     bp.tab = cur_is_a ? tab_a.d : tab_b.d;
     bp.tab_next = cur_is_a ? tab_b.d : tab_a.d;
+    bp.tile_next = cur_is_a ? tile_b.d : tile_a.d;
+    uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
-    float4* cold_next = cur_is_a ? cold_b.d : cold_a.d;
     Recording R;
     R.mode = (uint32_t)rec_mode;
     R.cap = (uint32_t)std::min<size_t>(rec_cap, 0xffffffffu);
@@ -822,14 +834,27 @@ int World::launch_substep(const SubstepParams& P) {
     }
     if (nb) {
         rc = timed(KC_MAIN, [&] {
-            const unsigned g = cdiv(nb, 256);
-            if (fused) {
-                if (ordered) k_main<true, true><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
-                else k_main<true, false><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
-            } else {
-                if (ordered) k_main<false, true><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
-                else k_main<false, false><<<g, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats);
+            const unsigned gdim = cdiv(nb, 256);
+#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats)
+#define BLOBS_MAIN_VARIANT(BT, MB)                                   \
+    do {                                                             \
+        if (fused) {                                                 \
+            if (ordered) BLOBS_LAUNCH_MAIN(true, true, BT, MB);      \
+            else BLOBS_LAUNCH_MAIN(true, false, BT, MB);             \
+        } else {                                                     \
+            if (ordered) BLOBS_LAUNCH_MAIN(false, true, BT, MB);     \
+            else BLOBS_LAUNCH_MAIN(false, false, BT, MB);            \
+        }                                                            \
+    } while (0)
+            switch (tune) {
+                case 2: BLOBS_MAIN_VARIANT(8, 4); break;
+                case 3: BLOBS_MAIN_VARIANT(4, 5); break;
+                case 4: BLOBS_MAIN_VARIANT(4, 3); break;
+                case 5: BLOBS_MAIN_VARIANT(8, 3); break;
+                default: BLOBS_MAIN_VARIANT(4, 4); break;
             }
+#undef BLOBS_MAIN_VARIANT
+#undef BLOBS_LAUNCH_MAIN
         });
         if (rc) return rc;
     }
@@ -852,16 +877,15 @@ int World::launch_substep(const SubstepParams& P) {
             if (rc) return rc;
         }
         if (nb) {
-            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, d_stats, mb_off.d, mb_cols.d); });
+            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d); });
             if (rc) return rc;
         }
     }
     const size_t tn = (size_t)grid.ncells + 1;
-    if (++scan_epoch >= (1u << 30)) { scan_epoch = 1; CU(cudaMemsetAsync(scan_status.d, 0, scan_status.cap * sizeof(unsigned long long), stream)); }
-    rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, scan_status.d, scan_epoch); });
+    rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, bp.tile_next, tile_cur); });
     if (rc) return rc;
     if (nc) {
-        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, bmg.d.d, bp.tab_next, hot_next, cold_next, nc); });
+        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, bp.tab_next, hot_next, nc); });
         if (rc) return rc;
     }
     cur_is_a = !cur_is_a;

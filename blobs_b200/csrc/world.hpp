@@ -233,6 +233,7 @@ class World {
     float bp_cell_override = 0.0f;  // 0 = auto
     int contact_mode = 0;           // 0 ordered, 1 fast
     bool allow_fused = true;
+    int tune = 0;                   // kernel-variant selector (benchmarking aid)
     std::vector<BlobsVec2> con_pos;
     std::vector<float> con_r;
     bool con_dirty = true;
@@ -252,6 +253,7 @@ class World {
     Mirrored<float2> coff;
     Mirrored<uint4> cconst;   // (radius bits, CF_* flags, memberships, filter)
     Mirrored<uint32_t> cparent;
+    Mirrored<uint4> ccold;    // (parent mass bits, memberships, filter, parent slot)
     float mass_of(uint32_t s) const { return bmg.h[s].x; }
     void set_mass(uint32_t s, float m) { float2 e = bmg.h[s]; e.x = m; bmg.set(s, e); }
     void set_gmod(uint32_t s, float g) { float2 e = bmg.h[s]; e.y = g; bmg.set(s, e); }
@@ -284,11 +286,10 @@ class World {
 
     // broadphase
     GridDesc grid{1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};
-    DevBuf<float4> hot_a, hot_b, cold_a, cold_b;
+    DevBuf<float4> hot_a, hot_b;
+    DevBuf<uint32_t> tile_a, tile_b;   // per-scan-tile totals, paired with tab_a / tab_b
     DevBuf<uint32_t> tab_a, tab_b;
     bool cur_is_a = true;
-    DevBuf<unsigned long long> scan_status;
-    uint32_t scan_epoch = 0;
     int bb[4] = {0, 0, 0, 0};
     bool bb_valid = false;
 

@@ -128,9 +128,10 @@ def cfg2(seed=1, side=1024, varied=False):
 
 
 def cfg2_dense(seed=1, side=256):
-    """cfg2 variant that starts overlapping (pitch < 2r) inside a tight circle, so contacts and clamps are busy."""
+    """Contact-rich cfg2 variant: the lattice starts overlapping (pitch 0.9 < 2r), so every sphere has ~4 contacts per
+    substep while the block relaxes; the circle is roomy enough to contain the lattice corners."""
     return lattice_scene(side, side, 0.9, (0.0, 0.0), seed, 0.5, 0.5, jitter=0.08, vel_disc=2.0,
-                         constraint_r=0.9 * side * 0.5, name=f"cfg2_dense_{side * side}", cell_size=1.0)
+                         constraint_r=0.9 * side * 0.75, name=f"cfg2_dense_{side * side}", cell_size=1.0)
 
 
 def cfg4(n_blobs=100_000, k=16, seed=1):

@@ -73,7 +73,8 @@ typedef enum BlobsParamId {
     BLOBS_PARAM_CELL_SIZE = 9,           /* spatial_hash.cell_size, spatial.rs:32 (default 2.0, physics.rs:66) */
     BLOBS_PARAM_BROADPHASE_CELL = 10,    /* GPU grid cell edge; 0 = auto (2 * max collider radius) */
     BLOBS_PARAM_CONTACT_MODE = 11,       /* 0 = ordered (bit-exact summation order), 1 = fast (unordered) */
-    BLOBS_PARAM_FUSED = 12               /* 1 = allow the fused contact+verlet kernel (default), 0 = force split kernels */
+    BLOBS_PARAM_FUSED = 12,              /* 1 = allow the fused contact+verlet kernel (default), 0 = force split kernels */
+    BLOBS_PARAM_TUNE = 13                /* kernel-variant selector for benchmarking (0 = default); never changes results */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

@@ -1,7 +1,7 @@
 """ctypes / numpy mirrors of the C structs in include/blobs_b200.h.
 
 The same layouts are used by the CUDA library (libblobs_b200.so) and, in tests only, by the CPU
-oracle (oracle/liboracle.so), so one scene description can be fed to both.
+checker, so one scene description can be fed to both.
 """
 import ctypes as C
 

@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's public Rust API (blobs/src/physics.rs, rigid_body.rs, collider.rs, joints.rs,
+springs.rs, groups.rs, lib.rs) over the C ABI — same names, argument meaning and error behaviour, so code and tests read
+like the reference's. All state lives in the GPU world; this module only builds descriptors and forwards calls."""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi as A
+from .world import BlobsError, World
+
+
+class RigidBodyType:  # rigid_body.rs:221-242
+    Dynamic, Static, KinematicPositionBased, KinematicVelocityBased = range(4)
+
+
+@dataclass
+class InteractionGroups:  # groups.rs:7-57
+    memberships: int = 0xFFFFFFFF
+    filter: int = 0xFFFFFFFF
+
+    @staticmethod
+    def all():
+        return InteractionGroups()
+
+    @staticmethod
+    def none():
+        return InteractionGroups(0, 0)
+
+    def test(self, rhs):
+        return (self.memberships & rhs.filter) != 0 and (rhs.memberships & self.filter) != 0
+
+
+def groups(memberships, filter):  # groups.rs:3-5
+    return InteractionGroups(int(memberships), int(filter))
+
+
+@dataclass
+class Affine2:  # glam::Affine2 (columns)
+    x_axis: tuple = (1.0, 0.0)
+    y_axis: tuple = (0.0, 1.0)
+    translation: tuple = (0.0, 0.0)
+
+    @staticmethod
+    def from_translation(t):
+        return Affine2(translation=(float(t[0]), float(t[1])))
+
+    @staticmethod
+    def from_angle_translation(angle, t):
+        s, c = math.sin(angle), math.cos(angle)
+        return Affine2((c, s), (-s, c), (float(t[0]), float(t[1])))
+
+
+@dataclass
+class RigidBody:  # the builder's output (rigid_body.rs:376-400)
+    position: tuple = (0.0, 0.0)
+    position_old: tuple = (0.0, 0.0)
+    gravity_mod: float = 1.0
+    rotation: float = 0.0
+    scale: tuple = (1.0, 1.0)
+    acceleration: tuple = (0.0, 0.0)
+    velocity_request: tuple = None
+    calculated_velocity: tuple = (0.0, 0.0)
+    user_data: int = 0
+    body_type: int = RigidBodyType.Dynamic
+
+
+class RigidBodyBuilder:  # rigid_body.rs:287-401
+    def __init__(self):
+        self._b = RigidBody()
+
+    def position(self, p):
+        self._b.position = self._b.position_old = (float(p[0]), float(p[1]))
+        return self
+
+    def gravity_mod(self, x):
+        self._b.gravity_mod = float(x)
+        return self
+
+    def rotation(self, x):
+        self._b.rotation = float(x)
+        return self
+
+    def scale(self, x):
+        self._b.scale = tuple(x)
+        return self
+
+    def acceleration(self, x):
+        self._b.acceleration = tuple(x)
+        return self
+
+    def velocity_request(self, x):
+        self._b.velocity_request = tuple(x)
+        return self
+
+    def calculated_velocity(self, x):
+        self._b.calculated_velocity = tuple(x)
+        return self
+
+    def user_data(self, x):
+        self._b.user_data = int(x)
+        return self
+
+    def body_type(self, x):
+        self._b.body_type = int(x)
+        return self
+
+    def build(self):
+        return self._b
+
+
+@dataclass
+class ColliderFlags:
+    is_sensor: bool = False
+
+
+@dataclass
+class Collider:  # collider.rs:3-20
+    offset: Affine2 = field(default_factory=Affine2)
+    absolute_transform: Affine2 = field(default_factory=Affine2)
+    user_data: int = 0
+    radius: float = 0.5
+    mass_override: float = None
+    flags: ColliderFlags = field(default_factory=ColliderFlags)
+    collision_groups: InteractionGroups = field(default_factory=InteractionGroups)
+
+
+class ColliderBuilder:  # collider.rs:199-284
+    def __init__(self):
+        self._c = Collider()
+
+    def offset(self, x):
+        self._c.offset = x
+        return self
+
+    def absolute_transform(self, x):
+        self._c.absolute_transform = x
+        return self
+
+    def mass_override(self, x):
+        self._c.mass_override = float(x)
+        return self
+
+    def user_data(self, x):
+        self._c.user_data = int(x)
+        return self
+
+    def radius(self, x):
+        self._c.radius = float(x)
+        return self
+
+    def flags(self, x):
+        self._c.flags = x
+        return self
+
+    def collision_groups(self, x):
+        self._c.collision_groups = x
+        return self
+
+    def build(self):
+        return self._c
+
+
+@dataclass
+class Spring:  # springs.rs:16-22
+    rigid_body_a: int
+    rigid_body_b: int
+    rest_length: float
+    stiffness: float
+    damping: float
+
+
+@dataclass
+class Constraint:  # lib.rs:189-193
+    position: tuple
+    radius: float
+
+
+@dataclass
+class CollisionEvent:  # lib.rs:146-153
+    col_handle_a: int
+    col_handle_b: int
+    impact_vel_a: tuple
+    impact_vel_b: tuple
+
+
+def _body_desc(rbd):
+    d = A.body_descs(1)
+    d["position"]["x"], d["position"]["y"] = rbd.position
+    d["position_old"]["x"], d["position_old"]["y"] = rbd.position_old
+    d["gravity_mod"] = rbd.gravity_mod
+    d["rotation"] = rbd.rotation
+    d["scale"]["x"], d["scale"]["y"] = rbd.scale
+    d["acceleration"]["x"], d["acceleration"]["y"] = rbd.acceleration
+    if rbd.velocity_request is not None:
+        d["has_velocity_request"] = 1
+        d["velocity_request"]["x"], d["velocity_request"]["y"] = rbd.velocity_request
+    d["calculated_velocity"]["x"], d["calculated_velocity"]["y"] = rbd.calculated_velocity
+    d["user_data_lo"] = rbd.user_data & 0xFFFFFFFFFFFFFFFF
+    d["user_data_hi"] = rbd.user_data >> 64
+    d["body_type"] = rbd.body_type
+    return d
+
+
+def _collider_desc(c):
+    d = A.collider_descs(1)
+    for name, a in (("offset", c.offset), ("absolute_transform", c.absolute_transform)):
+        d[name]["x_axis"]["x"], d[name]["x_axis"]["y"] = a.x_axis
+        d[name]["y_axis"]["x"], d[name]["y_axis"]["y"] = a.y_axis
+        d[name]["translation"]["x"], d[name]["translation"]["y"] = a.translation
+    d["radius"] = c.radius
+    d["shape_radius"] = c.radius
+    if c.mass_override is not None:
+        d["has_mass_override"] = 1
+        d["mass_override"] = c.mass_override
+    d["is_sensor"] = int(c.flags.is_sensor)
+    d["memberships"] = c.collision_groups.memberships
+    d["filter"] = c.collision_groups.filter
+    d["user_data_lo"] = c.user_data & 0xFFFFFFFFFFFFFFFF
+    d["user_data_hi"] = c.user_data >> 64
+    return d
+
+
+class Physics:
+    """blobs::Physics (physics.rs:3-34). Handles are thunderdome Index bits (ints)."""
+
+    def __init__(self, gravity=(0.0, 0.0), use_spatial_hash=False, device=-1, event_capacity=1 << 20):
+        self._w = World(gravity=gravity, use_spatial_hash=use_spatial_hash, device=device)
+        self._w.record_contacts(A.RECORD_EVENTS, event_capacity)  # the reference always feeds collision_send (physics.rs:304-311)
+        self._events = []
+
+    # ---- pub fields (physics.rs:6-33)
+    def _prop(pid, cast=float):
+        return property(lambda self: cast(self._w.get_param(pid)), lambda self, v: self._w.set_param(pid, v))
+
+    substeps = _prop(A.PARAM_SUBSTEPS, int)
+    joint_iterations = _prop(A.PARAM_JOINT_ITERATIONS, int)
+    use_spatial_hash = _prop(A.PARAM_USE_SPATIAL_HASH, lambda v: bool(int(v)))
+    collisions_enabled = _prop(A.PARAM_COLLISIONS_ENABLED, lambda v: bool(int(v)))
+    accumulator = _prop(A.PARAM_ACCUMULATOR)
+    time = _prop(A.PARAM_TIME)
+    old_dt = _prop(A.PARAM_OLD_DT)
+
+    @property
+    def gravity(self):
+        return (self._w.get_param(A.PARAM_GRAVITY_X), self._w.get_param(A.PARAM_GRAVITY_Y))
+
+    @gravity.setter
+    def gravity(self, g):
+        self._w.set_param(A.PARAM_GRAVITY_X, g[0])
+        self._w.set_param(A.PARAM_GRAVITY_Y, g[1])
+
+    def constraints_push(self, c):
+        self._w.constraint_push(c.position, c.radius)
+
+    def constraints_clear(self):
+        self._w.constraint_clear()
+
+    # ---- methods
+    def reset(self):  # physics.rs:71-76
+        self._w.reset()
+
+    def _pump(self):
+        for e in self._w.events_drain():
+            self._events.append(CollisionEvent(int(e["col_handle_a"]), int(e["col_handle_b"]),
+                                               (float(e["impact_vel_a"]["x"]), float(e["impact_vel_a"]["y"])),
+                                               (float(e["impact_vel_b"]["x"]), float(e["impact_vel_b"]["y"]))))
+
+    def step(self, delta):  # physics.rs:78-82; panics become RuntimeError with the reference's message
+        st = self._w.step(delta)
+        self._pump()
+        return st
+
+    def fixed_step(self, frame_time):  # physics.rs:84-99
+        st = self._w.fixed_step(frame_time)
+        self._pump()
+        return st
+
+    def collision_recv(self):
+        """Drains the CollisionEvent channel (demo/src/demos/balls.rs:104-106)."""
+        ev, self._events = self._events, []
+        return ev
+
+    def insert_rbd(self, rbd):  # physics.rs:121-128
+        return int(self._w.insert_bodies(_body_desc(rbd))[0])
+
+    def insert_collider_with_parent(self, collider, rbd_handle):  # physics.rs:130-149
+        return int(self._w.insert_colliders(_collider_desc(collider), np.array([rbd_handle], dtype=np.uint64))[0])
+
+    def remove_rbd(self, handle):  # physics.rs:163-172 (a missing body only pushes an event in the reference)
+        try:
+            self._w.remove_body(handle)
+        except BlobsError:
+            pass
+
+    def remove_col(self, handle):  # physics.rs:159-161
+        try:
+            self._w.remove_collider(handle)
+        except BlobsError:
+            pass
+
+    def rbd_count(self):  # physics.rs:113-115
+        return self._w.body_count()
+
+    def get_rbd(self, handle):  # physics.rs:105-107 -> Option
+        try:
+            return self._w.body_get(handle)
+        except BlobsError:
+            return None
+
+    def get_rbd_data(self, handle):  # physics.rs:101-103, RigidBodyData rigid_body.rs:18-26
+        s = self.get_rbd(handle)
+        if s is None:
+            return None
+        return {"position": (float(s["position"]["x"]), float(s["position"]["y"])),
+                "velocity": (float(s["calculated_velocity"]["x"]), float(s["calculated_velocity"]["y"])),
+                "angular_velocity": float(s["angular_velocity"]), "rotation": float(s["rotation"]),
+                "center_of_mass": (float(s["center_of_mass"]["x"]), float(s["center_of_mass"]["y"])), "mass": float(s["calculated_mass"])}
+
+    def set_rbd(self, handle, state, mask):  # get_mut_rbd physics.rs:109-111: write back the fields in `mask`
+        self._w.body_set(handle, state, mask)
+
+    def get_col(self, handle):  # physics.rs:117-119
+        try:
+            return self._w.collider_get(handle)
+        except BlobsError:
+            return None
+
+    def rbd_position(self, handle):  # physics.rs:151-153
+        s = self.get_rbd(handle)
+        return None if s is None else (float(s["position"]["x"]), float(s["position"]["y"]))
+
+    def col_position(self, handle):  # physics.rs:155-157
+        s = self.get_col(handle)
+        if s is None:
+            return None
+        t = s["desc"]["absolute_transform"]["translation"]
+        return (float(t["x"]), float(t["y"]))
+
+    def update_rigid_body_position(self, handle, offset):  # physics.rs:174-182
+        self._w.body_translate(handle, offset)
+
+    def create_fixed_joint(self, a, b, anchor_a=(0.0, 0.0), anchor_b=(0.0, 0.0)):  # physics.rs:184-207
+        return self._w.joint_insert(a, b, anchor_a, anchor_b)
+
+    def create_fixed_joint_with_distance(self, a, b, anchor_a, anchor_b, distance):  # physics.rs:209-239
+        return self._w.joint_insert(a, b, anchor_a, anchor_b, distance)
+
+    def springs_insert(self, spring):  # physics.springs.insert(Spring{..}) (demo/src/demos/joints.rs:59-66)
+        return self._w.spring_insert(spring.rigid_body_a, spring.rigid_body_b, spring.rest_length, spring.stiffness, spring.damping)
+
+    def debug_data(self):  # physics.rs:479-481 / debug.rs:34-91
+        bodies, bh = self._w.download_bodies()
+        cols, ch = self._w.download_colliders()
+        live_b, live_c = bh != 0, ch != 0
+        return {
+            "bodies": [Affine2.from_angle_translation(float(r), (float(x), float(y)))
+                       for r, x, y in zip(bodies["rotation"][live_b], bodies["position"]["x"][live_b], bodies["position"]["y"][live_b])],
+            "colliders": [((float(x), float(y)), float(r)) for x, y, r in zip(cols["desc"]["absolute_transform"]["translation"]["x"][live_c],
+                                                                             cols["desc"]["absolute_transform"]["translation"]["y"][live_c],
+                                                                             cols["desc"]["shape_radius"][live_c])],
+        }

@@ -1,0 +1,152 @@
+//! Drop-in `blobs::Physics` over libblobs_b200.so. Same names / argument meaning / panics as the reference
+//! (blobs/src/physics.rs); the world lives on the GPU, the shim keeps only handles and a per-frame host mirror.
+//! NOT compiled in this repository's image (no cargo/rustc) — mechanical by construction, see INTEGRATION.md.
+mod ffi;
+use ffi::*;
+use glam::{Affine2, Mat2, Vec2};
+use std::ffi::CStr;
+use std::sync::mpsc::{channel, Receiver, Sender};
+use thunderdome::Index;
+
+#[derive(Copy, Clone, Debug, Hash, PartialEq, Eq)] pub struct RigidBodyHandle(pub Index);
+#[derive(Copy, Clone, Debug, Hash, PartialEq, Eq)] pub struct ColliderHandle(pub Index);
+#[derive(Copy, Clone, Debug, Hash, PartialEq, Eq)] pub struct JointHandle(pub Index);
+#[derive(Copy, Clone, Debug)] pub struct SpringHandle(pub Index);
+
+#[derive(Copy, Clone, Debug)]
+pub struct CollisionEvent { pub col_handle_a: ColliderHandle, pub col_handle_b: ColliderHandle, pub impact_vel_a: Vec2, pub impact_vel_b: Vec2 }
+pub struct Constraint { pub position: Vec2, pub radius: f32 }
+pub struct Spring { pub rigid_body_a: RigidBodyHandle, pub rigid_body_b: RigidBodyHandle, pub rest_length: f32, pub stiffness: f32, pub damping: f32 }
+
+fn v(a: Vec2) -> BlobsVec2 { BlobsVec2 { x: a.x, y: a.y } }
+fn g(a: BlobsVec2) -> Vec2 { Vec2::new(a.x, a.y) }
+fn aff(a: Affine2) -> BlobsAffine2 { BlobsAffine2 { x_axis: v(a.matrix2.x_axis), y_axis: v(a.matrix2.y_axis), translation: v(a.translation) } }
+fn idx(h: u64) -> Index { Index::from_bits(h).expect("valid handle bits") }
+
+pub struct Physics {
+    w: *mut BlobsWorld,
+    pub collision_send: Sender<CollisionEvent>,
+    pub collision_recv: Receiver<CollisionEvent>,
+}
+
+impl Physics {
+    /// Physics::new (physics.rs:37-69)
+    pub fn new(gravity: Vec2, use_spatial_hash: bool) -> Self {
+        let p = BlobsParams { gravity: v(gravity), use_spatial_hash: use_spatial_hash as i32, device: -1, body_capacity_hint: 0, collider_capacity_hint: 0 };
+        let mut w = std::ptr::null_mut();
+        let rc = unsafe { blobs_world_create(&p, &mut w) };
+        assert!(rc == BLOBS_OK, "blobs_world_create failed: {}", unsafe { CStr::from_ptr(blobs_last_error(std::ptr::null())) }.to_string_lossy());
+        unsafe { blobs_record_contacts(w, BLOBS_RECORD_EVENTS, 1 << 20) }; // the reference always feeds collision_send
+        let (collision_send, collision_recv) = channel();
+        Self { w, collision_send, collision_recv }
+    }
+    fn ck(&self, rc: i32) { if rc != BLOBS_OK { panic!("{}", unsafe { CStr::from_ptr(blobs_last_error(self.w)) }.to_string_lossy()); } }
+    fn param(&self, id: i32) -> f64 { let mut x = 0.0; unsafe { blobs_world_get_param(self.w, id, &mut x) }; x }
+
+    // pub fields of the reference become accessor pairs (physics.rs:6-33)
+    pub fn substeps(&self) -> u32 { self.param(BLOBS_PARAM_SUBSTEPS) as u32 }
+    pub fn set_substeps(&mut self, n: u32) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_SUBSTEPS, n as f64) }; }
+    pub fn joint_iterations(&self) -> u32 { self.param(BLOBS_PARAM_JOINT_ITERATIONS) as u32 }
+    pub fn set_joint_iterations(&mut self, n: u32) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_JOINT_ITERATIONS, n as f64) }; }
+    pub fn set_gravity(&mut self, gv: Vec2) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_X, gv.x as f64); blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_Y, gv.y as f64) }; }
+    pub fn set_collisions_enabled(&mut self, on: bool) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_COLLISIONS_ENABLED, on as i32 as f64) }; }
+    pub fn time(&self) -> f64 { self.param(BLOBS_PARAM_TIME) }
+    pub fn push_constraint(&mut self, c: Constraint) { self.ck(unsafe { blobs_constraint_push(self.w, v(c.position), c.radius) }); }
+
+    /// Physics::reset (physics.rs:71-76)
+    pub fn reset(&mut self) { self.ck(unsafe { blobs_world_reset(self.w) }); }
+
+    fn pump_events(&mut self) {
+        let mut buf = vec![BlobsCollisionEvent::default(); 1 << 16];
+        loop {
+            let mut n = 0usize;
+            self.ck(unsafe { blobs_events_drain(self.w, buf.as_mut_ptr(), buf.len(), &mut n) });
+            for e in &buf[..n.min(buf.len())] {
+                let _ = self.collision_send.send(CollisionEvent { col_handle_a: ColliderHandle(idx(e.col_handle_a)), col_handle_b: ColliderHandle(idx(e.col_handle_b)),
+                                                                  impact_vel_a: g(e.impact_vel_a), impact_vel_b: g(e.impact_vel_b) });
+            }
+            if n <= buf.len() { break; }
+        }
+    }
+    /// Physics::step (physics.rs:78-82)
+    pub fn step(&mut self, delta: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_step(self.w, delta, &mut st) }); self.pump_events(); }
+    /// Physics::fixed_step (physics.rs:84-99)
+    pub fn fixed_step(&mut self, frame_time: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_fixed_step(self.w, frame_time, &mut st) }); self.pump_events(); }
+
+    /// insert_rbd (physics.rs:121-128); `RigidBody` is the builder output (rigid_body.rs:376-400)
+    pub fn insert_rbd(&mut self, rbd: RigidBody) -> RigidBodyHandle {
+        let d = BlobsBodyDesc { position: v(rbd.position), position_old: v(rbd.position_old), gravity_mod: rbd.gravity_mod, rotation: rbd.rotation, scale: v(rbd.scale),
+            acceleration: v(rbd.acceleration), velocity_request: v(rbd.velocity_request.unwrap_or(Vec2::ZERO)), calculated_velocity: v(rbd.calculated_velocity),
+            has_velocity_request: rbd.velocity_request.is_some() as i32, body_type: rbd.body_type as u32, user_data_lo: rbd.user_data as u64, user_data_hi: (rbd.user_data >> 64) as u64 };
+        let mut h = 0u64;
+        self.ck(unsafe { blobs_body_insert(self.w, &d, &mut h) });
+        RigidBodyHandle(idx(h))
+    }
+    /// insert_collider_with_parent (physics.rs:130-149); panics "parent rigid body must exist when inserting collider"
+    pub fn insert_collider_with_parent(&mut self, c: Collider, parent: RigidBodyHandle) -> ColliderHandle {
+        let d = BlobsColliderDesc { offset: aff(c.offset), absolute_transform: aff(c.absolute_transform), radius: c.radius, mass_override: c.mass_override.unwrap_or(0.0),
+            shape_radius: c.radius, has_mass_override: c.mass_override.is_some() as i32, is_sensor: c.flags.is_sensor as i32,
+            memberships: c.collision_groups.memberships, filter: c.collision_groups.filter, user_data_lo: c.user_data as u64, user_data_hi: (c.user_data >> 64) as u64 };
+        let mut h = 0u64;
+        self.ck(unsafe { blobs_collider_insert(self.w, &d, parent.0.to_bits(), &mut h) });
+        ColliderHandle(idx(h))
+    }
+    pub fn remove_rbd(&mut self, h: RigidBodyHandle) { unsafe { blobs_body_remove(self.w, h.0.to_bits()) }; }     // physics.rs:163-172 (missing body: event only)
+    pub fn remove_col(&mut self, h: ColliderHandle) { unsafe { blobs_collider_remove(self.w, h.0.to_bits()) }; } // physics.rs:159-161
+    pub fn rbd_count(&self) -> usize { let mut n = 0u64; unsafe { blobs_body_count(self.w, &mut n) }; n as usize }
+    pub fn get_rbd_state(&mut self, h: RigidBodyHandle) -> Option<BlobsBodyState> { let mut s = BlobsBodyState::default(); (unsafe { blobs_body_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then_some(s) }
+    pub fn rbd_position(&mut self, h: RigidBodyHandle) -> Option<Vec2> { self.get_rbd_state(h).map(|s| g(s.position)) }              // physics.rs:151-153
+    pub fn col_position(&mut self, h: ColliderHandle) -> Option<Vec2> { let mut s = BlobsColliderState::default(); (unsafe { blobs_collider_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then(|| g(s.desc.absolute_transform.translation)) }
+    pub fn update_rigid_body_position(&mut self, id: u64, offset: Vec2) { unsafe { blobs_body_translate(self.w, id, v(offset)) }; }   // physics.rs:174-182
+    /// get_mut_rbd (physics.rs:109-111): mutate a copy, write back the fields named in `mask`
+    pub fn set_rbd_state(&mut self, h: RigidBodyHandle, s: &BlobsBodyState, mask: u32) { self.ck(unsafe { blobs_body_set(self.w, h.0.to_bits(), s, mask) }); }
+    /// create_fixed_joint (physics.rs:184-207)
+    pub fn create_fixed_joint(&mut self, a: RigidBodyHandle, b: RigidBodyHandle, anchor_a: Vec2, anchor_b: Vec2) -> JointHandle { self.create_fixed_joint_with_distance(a, b, anchor_a, anchor_b, f32::NAN) }
+    /// create_fixed_joint_with_distance (physics.rs:209-239)
+    pub fn create_fixed_joint_with_distance(&mut self, a: RigidBodyHandle, b: RigidBodyHandle, anchor_a: Vec2, anchor_b: Vec2, distance: f32) -> JointHandle {
+        let mut h = 0u64; self.ck(unsafe { blobs_joint_insert(self.w, a.0.to_bits(), b.0.to_bits(), v(anchor_a), v(anchor_b), distance, &mut h) }); JointHandle(idx(h))
+    }
+    /// physics.springs.insert(Spring{..}) (demo/src/demos/joints.rs:59-66)
+    pub fn insert_spring(&mut self, s: Spring) -> SpringHandle { let mut h = 0u64; self.ck(unsafe { blobs_spring_insert(self.w, s.rigid_body_a.0.to_bits(), s.rigid_body_b.0.to_bits(), s.rest_length, s.stiffness, s.damping, &mut h) }); SpringHandle(idx(h)) }
+}
+impl Drop for Physics { fn drop(&mut self) { unsafe { blobs_world_destroy(self.w) }; } }
+
+// ---- builders: field-for-field the reference's (rigid_body.rs:287-401, collider.rs:199-284) ------------------------
+#[derive(Copy, Clone, Debug, PartialEq, Eq)] pub enum RigidBodyType { Dynamic = 0, Static = 1, KinematicPositionBased = 2, KinematicVelocityBased = 3 }
+#[derive(Copy, Clone, Debug, PartialEq, Eq)] pub struct InteractionGroups { pub memberships: u32, pub filter: u32 }
+impl Default for InteractionGroups { fn default() -> Self { Self { memberships: u32::MAX, filter: u32::MAX } } }
+#[derive(Copy, Clone, Debug, Default, PartialEq, Eq)] pub struct ColliderFlags { pub is_sensor: bool }
+
+pub struct RigidBody { pub position: Vec2, pub position_old: Vec2, pub gravity_mod: f32, pub rotation: f32, pub scale: Vec2, pub acceleration: Vec2,
+    pub velocity_request: Option<Vec2>, pub calculated_velocity: Vec2, pub user_data: u128, pub body_type: RigidBodyType }
+pub struct RigidBodyBuilder(RigidBody);
+impl RigidBodyBuilder {
+    pub fn new() -> Self { Self(RigidBody { position: Vec2::ZERO, position_old: Vec2::ZERO, gravity_mod: 1.0, rotation: 0.0, scale: Vec2::ONE, acceleration: Vec2::ZERO,
+        velocity_request: None, calculated_velocity: Vec2::ZERO, user_data: 0, body_type: RigidBodyType::Dynamic }) }
+    pub fn position(mut self, p: Vec2) -> Self { self.0.position_old = p; self.0.position = p; self }
+    pub fn gravity_mod(mut self, x: f32) -> Self { self.0.gravity_mod = x; self }
+    pub fn rotation(mut self, x: f32) -> Self { self.0.rotation = x; self }
+    pub fn scale(mut self, x: Vec2) -> Self { self.0.scale = x; self }
+    pub fn acceleration(mut self, x: Vec2) -> Self { self.0.acceleration = x; self }
+    pub fn velocity_request(mut self, x: Vec2) -> Self { self.0.velocity_request = Some(x); self }
+    pub fn calculated_velocity(mut self, x: Vec2) -> Self { self.0.calculated_velocity = x; self }
+    pub fn user_data(mut self, x: u128) -> Self { self.0.user_data = x; self }
+    pub fn body_type(mut self, x: RigidBodyType) -> Self { self.0.body_type = x; self }
+    pub fn build(self) -> RigidBody { self.0 }
+}
+pub struct Collider { pub offset: Affine2, pub absolute_transform: Affine2, pub user_data: u128, pub radius: f32, pub mass_override: Option<f32>,
+    pub flags: ColliderFlags, pub collision_groups: InteractionGroups }
+pub struct ColliderBuilder(Collider);
+impl ColliderBuilder {
+    pub fn new() -> Self { Self(Collider { offset: Affine2::IDENTITY, absolute_transform: Affine2::IDENTITY, user_data: 0, radius: 0.5, mass_override: None,
+        flags: ColliderFlags::default(), collision_groups: InteractionGroups::default() }) }
+    pub fn offset(mut self, x: Affine2) -> Self { self.0.offset = x; self }
+    pub fn absolute_transform(mut self, x: Affine2) -> Self { self.0.absolute_transform = x; self }
+    pub fn mass_override(mut self, x: f32) -> Self { self.0.mass_override = Some(x); self }
+    pub fn user_data(mut self, x: u128) -> Self { self.0.user_data = x; self }
+    pub fn radius(mut self, x: f32) -> Self { self.0.radius = x; self }
+    pub fn flags(mut self, x: ColliderFlags) -> Self { self.0.flags = x; self }
+    pub fn collision_groups(mut self, x: InteractionGroups) -> Self { self.0.collision_groups = x; self }
+    pub fn build(self) -> Collider { self.0 }
+}
+#[allow(dead_code)] fn _unused(_: Mat2) {}

@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2_varied", "cfg2_dense", "cfg4", "cfg2_4m", "cfg2_16m"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2_varied", "cfg2_dense", "cfg3", "cfg4", "cfg2_4m", "cfg2_16m"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--tune", type=int, default=0, help="kernel variant selector (BLOBS_PARAM_TUNE)")
@@ -203,14 +203,26 @@ def run_ours(args):
     import blobs_b200
     from blobs_b200 import scenes as S
 
-    # N > 1: one independent cfg2 world per rank (no data-path collective; "replicas", weak scaling).
-    sc, desc = make_scene(args.workload, seed=1 + rank)
-    w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
-    S.build(w, sc)
+    scaling = "weak"
+    if args.workload == "cfg3":
+        # BASELINE config #3: 4096 independent worlds x 256 bodies, block-partitioned over the ranks, no collective (strong scaling)
+        n_worlds_total = 4096
+        lo, hi = rank * n_worlds_total // world, (rank + 1) * n_worlds_total // world
+        worlds = [S.cfg1(1 + wid, n_side=16) for wid in range(lo, hi)]
+        w = blobs_b200.World(gravity=worlds[0].gravity, device=local, body_capacity=256 * (hi - lo), collider_capacity=256 * (hi - lo))
+        S.build_batch(w, worlds)
+        n = nb = 256 * (hi - lo)
+        desc = f"cfg3: {n_worlds_total} batched independent worlds x 256 bodies (cfg1 at 16x16, circle R=4), worlds {lo}..{hi - 1} on this rank"
+        scaling = "strong"
+    else:
+        # N > 1: one independent world per rank (no data-path collective; "replicas", weak scaling).
+        sc, desc = make_scene(args.workload, seed=1 + rank)
+        w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
+        S.build(w, sc)
+        n = sc.n_colliders
+        nb = sc.n_bodies
     if args.tune:
         w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
-    n = sc.n_colliders
-    nb = sc.n_bodies
 
     def barrier():
         if dist is not None:
@@ -273,7 +285,7 @@ def run_ours(args):
         value = n_total * K / (t_dev_ms / 1e3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev_ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + ("" if world == 1 else f"; one independent world per GPU ({world} replicas, no collective)"),
                        "spheres_per_gpu": n, "substeps": substeps, "contact_mode": "ordered (bit-exact summation order)",
                        "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",

@@ -77,14 +77,14 @@ __device__ __forceinline__ CellRange cell_range(const GridDesc& g, float x, floa
 
 // Generic neighbourhood walk: calls f(const Rec&) for every record in the range (any span, row/column wrap).
 template <class F>
-__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, float x, float y,
-                                                   float r, F&& f) {
+__device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, uint32_t wbase,
+                                                   float x, float y, float r, F&& f) {
     const CellRange R = cell_range(g, x, y, r);
     const uint32_t n1 = min(R.nx, g.W - R.c0);  // cells before the row wraps
     for (uint32_t j = 0; j < R.ny; ++j) {
         uint32_t row = R.r0 + j;
         if (row >= g.H) row -= g.H;
-        const uint32_t base = row * g.W;
+        const uint32_t base = wbase + row * g.W;
         uint32_t lo = __ldg(bp.tab + base + R.c0), hi = __ldg(bp.tab + base + R.c0 + n1);
         for (uint32_t k = lo; k < hi; ++k) f(load_rec(bp, ccold, k));
         if (n1 < R.nx) {  // wrapped part of the row
@@ -106,6 +106,7 @@ struct SelfCol {
     uint32_t memb, filt;
     uint32_t body;   // parent body slot
     uint32_t slot;   // collider slot
+    uint32_t wbase;  // first table entry of this body's (batched) world
     bool sensor;
 };
 
@@ -252,7 +253,7 @@ template <bool ORDERED, class KEY>
 __device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, const SelfCol& s,
                                                ContactList<KEY>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
                                                DeviceStats* stats) {
-    for_each_candidate(g, bp, ccold, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
+    for_each_candidate(g, bp, ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
 }
 
 // Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap):
@@ -280,7 +281,7 @@ __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphas
         uint32_t row = R.r0 + j;
         if (row >= g.H) row -= g.H;
         const bool valid = (uint32_t)j < R.ny;
-        const uint32_t idx = valid ? row * g.W + R.c0 : 0u;
+        const uint32_t idx = s.wbase + (valid ? row * g.W + R.c0 : 0u);
         const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (valid ? R.nx : 0u));
         lo[j] = a;
         cnt[j] = b - a;
@@ -330,7 +331,7 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
         float bx = 0.f, by = 0.f;
         for (int ci = 0; ci < ncols; ++ci) {
             const SelfCol s = cols[ci];
-            for_each_candidate(g, bp, ccold, s.x, s.y, s.r, [&](const Rec& o) {
+            for_each_candidate(g, bp, ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
                 if (c.coincident) {
@@ -375,7 +376,7 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
             po.y = fsub(py, fmul(v.y, P.dt));
             B.has_vreq[b] = 0;
         }
-        const float ratio = (b == P.first_dynamic) ? P.ratio_first : P.ratio_rest;   // physics.rs:338-339
+        const float ratio = (flags & BF_FIRST_DYN) ? P.ratio_first : P.ratio_rest;   // physics.rs:338-339
         const float dx = fmul(fsub(px, po.x), ratio), dy = fmul(fsub(py, po.y), ratio);
         if (!(flags & BF_SPRINGS)) {                             // gravity; spring bodies got it in k_springs
             a.x = fadd(a.x, fmul(P.gx, gmod));
@@ -431,7 +432,7 @@ __device__ __forceinline__ uint32_t bin_collider(uint32_t* tab_next, uint32_t* t
 }
 
 __device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t* tile_next,
-                                                 uint32_t c, uint32_t cflags, float sx, float sy, float rot) {
+                                                 uint32_t c, uint32_t cflags, uint32_t wbase, float sx, float sy, float rot) {
     float2 off = make_float2(0.f, 0.f);
     if (cflags & CF_OFFSET) off = Cc.coff[c];
     float sn = 0.0f, cs = 1.0f;
@@ -439,7 +440,7 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
     const float ax = fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx);
     const float ay = fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy);
     Cc.cabs[c] = make_float2(ax, ay);
-    const uint32_t cell = cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
+    const uint32_t cell = wbase + cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
     Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
 
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
     const float2 po = B.pos_old[bl];
     const float2 acc0 = B.acc[bl];
     const bool hv = B.has_vreq[bl] != 0;
+    const uint32_t wbase = g.n_worlds > 1u ? B.bworld[bl] * g.ncells : 0u;
     uint32_t cs = 0;
     uint4 cc = make_uint4(0u, 0u, 0u, 0u);
     float2 ab = make_float2(0.f, 0.f);
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
             if (active_col && P.collisions_enabled) {
                 SelfCol s;
                 s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
-                s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.sensor = (cc.y & CF_SENSOR) != 0u;
+                s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
                 ContactList<uint32_t> list;
                 list.clear();
                 gather_single<ORDERED, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
         if (FUSED) {
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
-            if (active_col) publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, sx, sy, rot);
+            if (active_col) publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
         } else {
             B.pos[b] = p;
         }
@@ -530,12 +532,13 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
 // ------------------------------------------------------------------------------------------------
 constexpr int MULTI_MAX_INLINE = 8;  // colliders staged for the rescan path
 
-__device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, uint32_t b, uint32_t c, float m, SelfCol& s) {
+__device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, uint32_t b, uint32_t c, float m, uint32_t wbase,
+                                          SelfCol& s) {
     const uint4 cc = Cc.cconst[c];
     if (!(cc.y & CF_ACTIVE)) return false;
     const float2 a = Cc.cabs[c];
     s.x = a.x; s.y = a.y; s.r = __uint_as_float(cc.x); s.m = m;
-    s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.sensor = (cc.y & CF_SENSOR) != 0u;
+    s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
     return true;
 }
 
@@ -558,13 +561,14 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
         const float2 po = B.pos_old[b];
         const float2 acc0 = B.acc[b];
         const bool hv = B.has_vreq[b] != 0;
+        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
         if (P.collisions_enabled) {
             ContactList<unsigned long long> list;
             list.clear();
             const float m = mg.x;
             for (uint32_t k = c0; k < c1; ++k) {
                 SelfCol s;
-                if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
+                if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
                 gather_generic<ORDERED, unsigned long long>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
             if (ORDERED) {
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                     bool fits = true;
                     for (uint32_t k = c0; k < c1; ++k) {
                         SelfCol s;
-                        if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
+                        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
                         if (nc == MULTI_MAX_INLINE) { fits = false; break; }
                         cols[nc++] = s;
                     }
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                         off.mode = 0;
                         for (uint32_t k = c0; k < c1; ++k) {
                             SelfCol s;
-                            if (!load_self(B, Cc, b, mb_cols[k], m, s)) continue;
+                            if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
                             gather_generic<false, unsigned long long>(g, bp, Cc.ccold, s, dummy, o2, off, B.vel, stats);
                         }
                         p.x = fadd(p.x, o2.fx);
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             for (uint32_t k = c0; k < c1; ++k) {
                 const uint32_t c = mb_cols[k];
                 const uint32_t cf = Cc.cconst[c].y;
-                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, sx, sy, rot);
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, wbase, sx, sy, rot);
             }
         } else {
             B.pos[b] = p;
@@ -641,17 +645,18 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
     if (!(flags & BF_ALIVE)) return;
     const int32_t col = (int32_t)info.y;
     const float2 p = B.pos[b];
+    const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
     float sx, sy, rot;
     integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
     if (col >= 0) {
         const uint32_t cf = Cc.cconst[col].y;
-        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, sx, sy, rot);
+        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, wbase, sx, sy, rot);
     } else if (col <= -2) {
         const uint32_t i = (uint32_t)(-(col + 2));
         for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
             const uint32_t c = mb_cols[k];
             const uint32_t cf = Cc.cconst[c].y;
-            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, sx, sy, rot);
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, wbase, sx, sy, rot);
         }
     }
 }
@@ -659,12 +664,14 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
 // ------------------------------------------------------------------------------------------------
 // K-count: bins every active collider from its current snapshot (used when the broadphase is (re)built outside a step).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, uint32_t* tab_next, uint32_t* tile_next, uint32_t n_colliders) {
+__global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, uint32_t* tab_next,
+                                               uint32_t* tile_next, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
     if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
     const float2 a = Cc.cabs[c];
-    const uint32_t cell = cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
+    const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
+    const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
     Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
 

@@ -13,6 +13,7 @@ enum : uint32_t {
     BF_SPRINGS = 1u << 2,      // has incident springs: gravity + spring forces are summed by k_springs
     BF_ROT = 1u << 3,          // angular state may be non-zero / rotation matters (torque, joints, rotated)
     BF_JOINTED = 1u << 4,
+    BF_FIRST_DYN = 1u << 5,    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
 };
 // collider flags (host-authoritative, cflags[])
 enum : uint32_t {
@@ -37,7 +38,8 @@ struct Rec {
 
 struct GridDesc {
     uint32_t W, H;       // toroidal table dims (cells)
-    uint32_t ncells;     // W * H
+    uint32_t ncells;     // W * H (per batched world)
+    uint32_t n_worlds;   // batched independent worlds share one table: index = world * ncells + cell
     float cell;          // broadphase cell edge
     float inv_cell;      // 1 / cell (binning uses the monotone map floor(v * inv_cell))
     float rmax;          // max radius over active colliders (search reach = r + rmax)
@@ -62,7 +64,6 @@ struct DeviceStats {       // accumulated per blobs_step* call, read back once
 struct SubstepParams {
     float dt;
     float ratio_first, ratio_rest;  // dt/old_dt for the first non-static body, dt/dt for the rest (physics.rs:338-339, Q2)
-    uint32_t first_dynamic;         // slot of the first non-static body in arena order, NO_SLOT if none
     float gx, gy;
     uint32_t collisions_enabled;
     uint32_t n_bodies;              // body slots
@@ -85,6 +86,7 @@ struct BodyArrays {
     const float* inertia;
     const uint2* binfo;      // (BF_* flags, body_col)
     const float2* bmg;       // (calculated_mass, gravity_mod)
+    const uint32_t* bworld;  // batched-world id per body (only read when GridDesc::n_worlds > 1)
 };
 
 struct ColliderArrays {

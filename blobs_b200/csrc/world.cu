@@ -66,7 +66,7 @@ World::~World() {
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
-    inertia.d.release(); binfo.d.release(); bmg.d.release();
+    inertia.d.release(); binfo.d.release(); bmg.d.release(); bworld.d.release();
     coff.d.release(); cconst.d.release(); cparent.d.release(); ccold.d.release();
     pos.release(); pos_old.release(); acc.release(); vel.release(); vreq.release(); cabs.release();
     has_vreq.release(); rot.release(); angvel.release(); torque.release(); ccell.release();
@@ -98,6 +98,10 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_CONTACT_MODE: contact_mode = (int)v; break;
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
         case BLOBS_PARAM_TUNE: tune = (int)v; break;
+        case BLOBS_PARAM_BATCH_WORLD:
+            if (v < 0 || v >= 1048576.0) return fail(BLOBS_ERR_INVALID, "batch world id out of range");
+            cur_world = (uint32_t)v;
+            break;
         default: return fail(BLOBS_ERR_INVALID, "unknown param id");
     }
     return BLOBS_OK;
@@ -119,6 +123,7 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_CONTACT_MODE: *out = contact_mode; break;
         case BLOBS_PARAM_FUSED: *out = allow_fused; break;
         case BLOBS_PARAM_TUNE: *out = tune; break;
+        case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         default: return BLOBS_ERR_INVALID;
     }
     return BLOBS_OK;
@@ -188,7 +193,7 @@ int World::flush_writes() {
 BodyArrays World::body_arrays() {
     BodyArrays B;
     B.pos = pos.d; B.pos_old = pos_old.d; B.acc = acc.d; B.vel = vel.d; B.vreq = vreq.d; B.has_vreq = has_vreq.d;
-    B.rot = rot.d; B.angvel = angvel.d; B.torque = torque.d; B.inertia = inertia.d.d; B.binfo = binfo.d.d; B.bmg = bmg.d.d;
+    B.rot = rot.d; B.angvel = angvel.d; B.torque = torque.d; B.inertia = inertia.d.d; B.binfo = binfo.d.d; B.bmg = bmg.d.d; B.bworld = bworld.d.d;
     return B;
 }
 ColliderArrays World::col_arrays() {
@@ -214,8 +219,12 @@ int World::body_insert(const BlobsBodyDesc& d, uint64_t* out) {
     b.scale = d.scale;
     b.type = d.body_type;
     b.rot_active = d.rotation != 0.0f;
+    b.world = cur_world;
+    if (cur_world + 1 > n_worlds) { n_worlds = cur_world + 1; bp_dirty = true; }
     const size_t n = bodies.slots();
     inertia.resize(n, 1.0f); bmg.resize(n, make_float2(1.0f, 1.0f)); binfo.resize(n, make_uint2(0u, (uint32_t)BODY_NO_COLLIDER));
+    bworld.resize(n, 0u);
+    bworld.set(s, cur_world);
     bmg.set(s, make_float2(1.0f, d.gravity_mod));  // calculated_mass = 1: RigidBodyBuilder::build rigid_body.rs:385-388
     inertia.set(s, 1.0f);
     BodyWrite& w = stage(s);
@@ -531,6 +540,7 @@ int World::rebuild_topology() {
     topo_error = 0;
     topo_error_msg.clear();
     binfo.resize(nb, make_uint2(0u, (uint32_t)BODY_NO_COLLIDER)); bmg.resize(nb, make_float2(1.0f, 1.0f)); inertia.resize(nb, 1.0f);
+    bworld.resize(nb, 0u);
     coff.resize(nc, make_float2(0.f, 0.f)); cconst.resize(nc, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(nc, NO_SLOT);
     ccold.resize(nc, make_uint4(0u, 0u, 0u, NO_SLOT));
 
@@ -629,7 +639,8 @@ int World::rebuild_topology() {
 
     // bodies
     std::vector<uint32_t> v_mb_body, v_mb_off{0}, v_mb_cols;
-    first_dynamic = NO_SLOT;
+    any_dynamic = false;
+    std::vector<uint8_t> world_has_first(n_worlds, 0);
     n_simple = 0;
     for (uint32_t b = 0; b < nb; ++b) {
         uint32_t f = 0;
@@ -638,7 +649,10 @@ int World::rebuild_topology() {
             HBody& x = hb[b];
             f |= BF_ALIVE;
             if (x.type == BLOBS_BODY_STATIC) f |= BF_STATIC;
-            else if (first_dynamic == NO_SLOT) first_dynamic = b;
+            else {
+                any_dynamic = true;
+                if (!world_has_first[x.world]) { world_has_first[x.world] = 1; f |= BF_FIRST_DYN; }
+            }
             if (x.n_springs) f |= BF_SPRINGS;
             if (x.n_joints) f |= BF_JOINTED | BF_ROT;
             if (x.rot_active) f |= BF_ROT;
@@ -676,7 +690,7 @@ int World::flush() {
         int rc = rebuild_topology();
         if (rc) return rc;
     }
-    CU(inertia.flush(stream)); CU(binfo.flush(stream)); CU(bmg.flush(stream));
+    CU(inertia.flush(stream)); CU(binfo.flush(stream)); CU(bmg.flush(stream)); CU(bworld.flush(stream));
     CU(coff.flush(stream)); CU(cconst.flush(stream)); CU(cparent.flush(stream)); CU(ccold.flush(stream));
     if (con_dirty) {
         std::vector<float4> kc(con_pos.size());
@@ -720,7 +734,9 @@ int World::choose_grid(bool) {
     }
     // a little slack so slow drift does not alias immediately; aliasing is harmless for correctness (toroidal table)
     double W = (double)ex + std::max(4.0, ex / 16.0), H = (double)ey + std::max(4.0, ey / 16.0);
-    const double cap = std::max<double>(4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1));
+    // table budget: ~4 cells per collider (per batched world), at most 2^30 entries overall
+    double cap = std::max<double>(n_worlds > 1 ? 64.0 : 4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1) / (double)n_worlds);
+    cap = std::min(cap, 1073741824.0 / (double)n_worlds);
     if (W * H > cap) {
         const double sc = std::sqrt(cap / (W * H));
         W = std::max(1.0, std::floor(W * sc));
@@ -729,6 +745,7 @@ int World::choose_grid(bool) {
     grid.W = (uint32_t)W;
     grid.H = (uint32_t)H;
     grid.ncells = grid.W * grid.H;
+    grid.n_worlds = n_worlds;
     grid.cell = cs;
     grid.inv_cell = 1.0f / cs;
     grid.rmax = r_max;
@@ -742,7 +759,7 @@ int World::rebuild_broadphase() {
     int rc = choose_grid(true);
     if (rc) return rc;
     const size_t nc = cols.slots();
-    const size_t tn = (size_t)grid.ncells + 1;
+    const size_t tn = table_entries();
     CU(tab_a.ensure(tn + SCAN_ITEMS, stream)); CU(tab_b.ensure(tn + SCAN_ITEMS, stream));
     CU(hot_a.ensure(nc + 1, stream)); CU(hot_b.ensure(nc + 1, stream));   // +1: the scan may re-read index == #records
     const unsigned ntiles = cdiv(tn, SCAN_TILE);
@@ -757,7 +774,7 @@ int World::rebuild_broadphase() {
     uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
     if (nc) {
-        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), tab_next, tile_next, (uint32_t)nc);
+        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc);
         launches++;
     }
     k_scan<<<ntiles, SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur);
@@ -881,7 +898,7 @@ int World::launch_substep(const SubstepParams& P) {
             if (rc) return rc;
         }
     }
-    const size_t tn = (size_t)grid.ncells + 1;
+    const size_t tn = table_entries();
     rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, bp.tile_next, tile_cur); });
     if (rc) return rc;
     if (nc) {
@@ -904,7 +921,6 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
         P.dt = step_delta;
         P.ratio_first = step_delta / old_dt;        // physics.rs:338
         P.ratio_rest = step_delta / step_delta;     // every later body sees old_dt == dt (Q2)
-        P.first_dynamic = first_dynamic;
         P.gx = gx;
         P.gy = gy;
         P.collisions_enabled = collisions_enabled ? 1u : 0u;
@@ -913,7 +929,7 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
         P.write_vel = ((last_of_call && i + 1 == nsub) || n_sb > 0 || rec_mode == BLOBS_RECORD_EVENTS) ? 1u : 0u;
         int rc = launch_substep(P);
         if (rc) return rc;
-        if (first_dynamic != NO_SLOT) old_dt = step_delta;  // physics.rs:339
+        if (any_dynamic) old_dt = step_delta;  // physics.rs:339
     }
     return BLOBS_OK;
 }
@@ -944,9 +960,9 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     // table re-dimensioning: only when the snapshot outgrew (aliasing) or vastly undershoots the table
     if (h_stats->bb_min_x <= h_stats->bb_max_x) {
         const long long ex = (long long)h_stats->bb_max_x - h_stats->bb_min_x + 1, ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;
-        const double cap = std::max<double>(4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1));
+        const double cap = std::max<double>(n_worlds > 1 ? 64.0 : 4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1) / (double)n_worlds);
         const bool aliased = (ex > grid.W || ey > grid.H) && (double)grid.ncells < 0.5 * cap;
-        const bool oversized = (double)grid.W * grid.H > 4096.0 && ((double)ex * 3 < grid.W && (double)ey * 3 < grid.H);
+        const bool oversized = (double)grid.W * grid.H > (n_worlds > 1 ? 64.0 : 4096.0) && ((double)ex * 3 < grid.W && (double)ey * 3 < grid.H);
         if (aliased || oversized) bp_dirty = true;
     }
     if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");

@@ -135,6 +135,7 @@ struct HBody {
     uint32_t type = 0;
     bool rot_active = false;
     uint32_t n_springs = 0, n_joints = 0;
+    uint32_t world = 0;               // batched-world id
 };
 
 struct HCollider {
@@ -250,6 +251,9 @@ class World {
     Mirrored<float> inertia;
     Mirrored<uint2> binfo;    // (BF_* flags, body_col)
     Mirrored<float2> bmg;     // (calculated_mass, gravity_mod)
+    Mirrored<uint32_t> bworld; // batched-world id per body
+    uint32_t cur_world = 0, n_worlds = 1;
+    size_t table_entries() const { return (size_t)grid.n_worlds * grid.ncells + 1; }
     Mirrored<float2> coff;
     Mirrored<uint4> cconst;   // (radius bits, CF_* flags, memberships, filter)
     Mirrored<uint32_t> cparent;
@@ -277,7 +281,7 @@ class World {
     bool topo_dirty = true, bp_dirty = true;
     int topo_error = 0;
     std::string topo_error_msg;
-    uint32_t first_dynamic = NO_SLOT;
+    bool any_dynamic = false;
     float r_max = 0.f;
     uint32_t n_simple = 0, n_multi = 0, n_sb = 0, n_islands = 0, n_springs_live = 0, n_joints_live = 0, n_active_cols = 0;
     DevBuf<uint32_t> mb_body, mb_off, mb_cols, sb_body, sb_off, sb_edge, isl_off, isl_joint;
@@ -285,7 +289,7 @@ class World {
     DevBuf<JointParams> d_joints;
 
     // broadphase
-    GridDesc grid{1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};
+    GridDesc grid{1, 1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};
     DevBuf<float4> hot_a, hot_b;
     DevBuf<uint32_t> tile_a, tile_b;   // per-scan-tile totals, paired with tab_a / tab_b
     DevBuf<uint32_t> tab_a, tab_b;

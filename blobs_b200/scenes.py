@@ -134,6 +134,32 @@ def cfg2_dense(seed=1, side=256):
                          constraint_r=0.9 * side * 0.75, name=f"cfg2_dense_{side * side}", cell_size=1.0)
 
 
+def cfg3(n_worlds=4096, side=16, seed=1):
+    """Batched independent worlds: n_worlds x (side*side) bodies, each world = cfg1 at that size
+    (constraint radius 4 as in demo/src/main.rs:51-54), per-world seed = seed + world id. Returns one Scene per world."""
+    return [cfg1(seed + w, n_side=side) for w in range(n_worlds)]
+
+
+def build_batch(world, scene_list):
+    """Insert a list of per-world Scenes into ONE GPU world as batched independent worlds (BLOBS_PARAM_BATCH_WORLD).
+    Gravity/constraints are shared (taken from the first scene). Returns the per-world handle dicts."""
+    first = scene_list[0]
+    for (x, y, r) in first.constraints:
+        world.constraint_push((x, y), r)
+    if first.cell_size is not None:
+        world.set_param(A.PARAM_CELL_SIZE, first.cell_size)
+    out = []
+    for w, sc in enumerate(scene_list):
+        world.set_param(A.PARAM_BATCH_WORLD, w)
+        bh = world.insert_bodies(sc.bodies)
+        ch = world.insert_colliders(sc.colliders, bh[sc.col_parent]) if sc.n_colliders else np.zeros(0, np.uint64)
+        sh = [world.spring_insert(bh[a], bh[b], rest, k, c) for (a, b, rest, k, c) in sc.springs]
+        jh = [world.joint_insert(bh[a], bh[b]) for (a, b) in sc.joints]
+        out.append({"bodies": bh, "colliders": ch, "springs": sh, "joints": jh})
+    world.set_param(A.PARAM_BATCH_WORLD, 0)
+    return out
+
+
 def cfg4(n_blobs=100_000, k=16, seed=1):
     """Soft blobs: rings of k single-collider bodies r=0.1 on a circle of radius 0.5; adjacent bodies
     joined by fixed joints, second neighbours and opposite bodies by springs k=1000 c=50; lattice pitch 1.6."""

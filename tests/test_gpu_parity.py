@@ -339,3 +339,38 @@ def test_full_size_cfg2_one_step_vs_grid_oracle():
     p1, p2 = g.read_positions(), g2.read_positions()
     assert p1.tobytes() == p2.tobytes(), "ordered mode must be run-to-run deterministic despite atomic binning"
     assert np.isfinite(p1).all()
+
+
+def test_batched_independent_worlds():
+    """BASELINE config #3 in small: 24 independent worlds x 256 bodies inside ONE GPU world (world id folded into the cell
+    index) vs 24 separate oracle worlds. Every world must behave exactly like its own Physics, including the per-world
+    old_dt quirk (Q2) and pair sets (slot offsets are monotone, so the summation order is preserved)."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    worlds = S.cfg3(n_worlds=24, side=16, seed=11)
+    g = blobs_b200.World(gravity=worlds[0].gravity)
+    hs = S.build_batch(g, worlds)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 20)
+    os_ = []
+    for sc in worlds:
+        o = oracle_py.OracleWorld(gravity=sc.gravity, maintain_spatial_hash=False, record_events=False)
+        S.build(o, sc)
+        os_.append(o)
+    nb = worlds[0].n_bodies
+    for step in range(12):
+        g.step(1 / 60)
+        pg = g.pairs_drain()
+        for w, o in enumerate(os_):
+            o.step(1 / 60)
+            po = o.pairs_drain()
+            lo, hi = w * nb, (w + 1) * nb
+            for sub in range(8):
+                mine = pg[sub][(pg[sub][:, 0] >= lo) & (pg[sub][:, 0] < hi)]
+                assert ((mine[:, 1] >= lo) & (mine[:, 1] < hi)).all(), "contact across worlds"
+                assert np.array_equal(mine - lo, po[sub]), f"world {w} step {step} substep {sub}"
+    sg, _ = g.download_bodies()
+    for w, o in enumerate(os_):
+        so, _ = o.download_bodies()
+        assert_bodies_bit_equal(sg[w * nb:(w + 1) * nb], so)
+    assert sum(len(p) for p in pg) > 0

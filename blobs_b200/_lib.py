@@ -57,6 +57,9 @@ SIGNATURES = {
     "blobs_kernel_info": (C.c_int32, [_vp, C.POINTER(A.KernelInfo)]),
     "blobs_profile_enable": (C.c_int32, [_vp, C.c_int32]),
     "blobs_profile_read": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
+    "blobs_strip_unique_id": (C.c_int32, [_vp]),
+    "blobs_strip_configure": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, C.c_uint32, C.c_uint32]),
+    "blobs_strip_owned": (C.c_int32, [_vp, _vp, C.c_size_t]),
 }
 
 _lib = None

@@ -105,4 +105,18 @@ int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out) { W_OR_INVA
 int32_t blobs_profile_enable(BlobsWorld* w, int32_t on) { W_OR_INVALID(w); return w->w.profile_enable(on); }
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n) { W_OR_INVALID(w); return w->w.profile_read(ms, launches, n); }
 
+int32_t blobs_strip_unique_id(uint8_t* out128) {
+    if (!out128) return BLOBS_ERR_INVALID;
+    std::string e;
+    const int rc = World::strip_unique_id(out128, &e);
+    if (rc) snprintf(g_create_error, sizeof(g_create_error), "%s", e.c_str());
+    return rc;
+}
+int32_t blobs_strip_configure(BlobsWorld* w, int32_t rank, int32_t nranks, float x_lo, float x_hi, const uint8_t* id128, uint32_t gcap, uint32_t mcap) {
+    W_OR_INVALID(w);
+    if (nranks > 1 && !id128) return BLOBS_ERR_INVALID;
+    return w->w.strip_configure(rank, nranks, x_lo, x_hi, id128, gcap, mcap);
+}
+int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* out, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.strip_owned(out, cap); }
+
 }  // extern "C"

@@ -454,13 +454,14 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
 // ------------------------------------------------------------------------------------------------
 template <bool FUSED, bool ORDERED, int BATCH, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                              Broadphase bp, Recording rec, DeviceStats* stats) {
+                                              Broadphase bp, Recording rec, DeviceStats* stats, const uint8_t* __restrict__ owned) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;
     out.n_pairs = out.n_coinc = 0;
     unsigned int n_over = 0;
-    const bool inb = b < P.n_bodies;
+    bool inb = b < P.n_bodies;
+    if (owned != nullptr && inb) inb = owned[b] != 0;  // strip mode: only the owner rank updates a body
     const uint32_t bl = inb ? b : 0u;
     // round 1: everything that only needs b (tail threads read slot 0 and discard)
     const uint2 info = B.binfo[bl];
@@ -665,9 +666,10 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
 // K-count: bins every active collider from its current snapshot (used when the broadphase is (re)built outside a step).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, uint32_t* tab_next,
-                                               uint32_t* tile_next, uint32_t n_colliders) {
+                                               uint32_t* tile_next, uint32_t n_colliders, const uint8_t* __restrict__ cowned) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
+    if (cowned != nullptr && !cowned[c]) return;
     if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
     const float2 a = Cc.cabs[c];
     const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
@@ -753,9 +755,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 // K-scatter: writes the 16-byte hot half of every active collider at cell_start[cell] + rank (the cold half is static).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const uint32_t* __restrict__ tab, float4* __restrict__ hot,
-                                                 uint32_t n_colliders) {
+                                                 uint32_t n_colliders, const uint8_t* __restrict__ cowned) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders) return;
+    if (cowned != nullptr && !cowned[c]) return;
     const uint4 cc = Cc.cconst[c];
     const uint2 cr = Cc.ccell[c];
     const float2 a = Cc.cabs[c];
@@ -864,10 +867,12 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
 // small utility kernels
 // ------------------------------------------------------------------------------------------------
 // bbox of the collider snapshot in broadphase cells (drives the table dimensions; host reads it with the stats)
-__global__ void __launch_bounds__(256) k_bbox(ColliderArrays Cc, float cell, uint32_t n_colliders, DeviceStats* stats) {
+__global__ void __launch_bounds__(256) k_bbox(ColliderArrays Cc, float cell, uint32_t n_colliders, DeviceStats* stats,
+                                              const uint8_t* __restrict__ cowned) {
     __shared__ int s_min_x[8], s_min_y[8], s_max_x[8], s_max_y[8];
     int mnx = INT32_MAX, mny = INT32_MAX, mxx = INT32_MIN, mxy = INT32_MIN;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
+        if (cowned != nullptr && !cowned[c]) continue;
         if (!(Cc.cconst[c].y & CF_ACTIVE)) continue;
         const float2 a = Cc.cabs[c];
         if (!(fabsf(a.x) < 1e30f) || !(fabsf(a.y) < 1e30f)) continue;   // ignore runaway / NaN points
@@ -935,6 +940,126 @@ __global__ void __launch_bounds__(256) k_apply_forces(BodyArrays B, const float2
     a.x = fadd(a.x, fdiv(F.x, m));
     a.y = fadd(a.y, fdiv(F.y, m));
     B.acc[b] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Strip decomposition (BASELINE config #5): one world split into vertical strips, one per rank. Contacts are Jacobi on
+// the snapshot, so ONE exchange per substep suffices: each rank sends the hot record of every owned collider within
+// reach of a strip edge (ghosts) and the full state of every body whose new snapshot crossed the edge (migration).
+// A cross-strip contact is seen from both sides; each side applies only its own body's half, so no reduction is needed,
+// and because records carry GLOBAL slots the ordered accumulation stays bit-identical to the single-GPU run.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_strip_init_owned(BodyArrays B, ColliderArrays Cc, StripDesc S, uint8_t* owned, uint8_t* cowned,
+                                                          uint32_t n_bodies) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bodies) return;
+    const uint2 info = B.binfo[b];
+    uint8_t o = 0;
+    const int32_t col = (int32_t)info.y;
+    if (info.x & BF_ALIVE) {
+        const float x = col >= 0 ? Cc.cabs[col].x : B.pos[b].x;
+        const bool left_ok = !S.has_left || x >= S.x_lo;
+        const bool right_ok = !S.has_right || x < S.x_hi;
+        o = (left_ok && right_ok) ? 1 : 0;
+        if (x != x) o = S.has_left ? 0 : 1;  // NaN: rank 0 keeps it
+    }
+    owned[b] = o;
+    if (col >= 0) cowned[col] = o;
+}
+
+__device__ __forceinline__ void strip_append_ghost(void* msg, const StripDesc& S, float4 hot) {
+    StripHeader* h = reinterpret_cast<StripHeader*>(msg);
+    const uint32_t i = atomicAdd(&h->n_ghost, 1u);
+    if (i < S.gcap) strip_ghosts(msg)[i] = hot;
+    else h->overflow = 1u;
+}
+
+// after the owned bodies were advanced: select ghosts and leavers from the NEW snapshots
+__global__ void __launch_bounds__(256) k_strip_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, const uint8_t* __restrict__ cowned,
+                                                    void* send_l, void* send_r, uint32_t n_colliders) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_colliders || !cowned[c]) return;
+    const uint4 cc = Cc.cconst[c];
+    if (!(cc.y & CF_ACTIVE)) return;
+    const float2 a = Cc.cabs[c];
+    const float r = __uint_as_float(cc.x);
+    const float reach = __fadd_ru(r, S.rmax);
+    const float4 hot = make_float4(a.x, a.y, r, __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
+    // a neighbour-owned partner at x' >= x_hi needs me iff x' - x < r + r' <= reach (directed rounding keeps it conservative)
+    if (S.has_right && a.x >= __fsub_rd(S.x_hi, reach)) strip_append_ghost(send_r, S, hot);
+    if (S.has_left && a.x < __fadd_ru(S.x_lo, reach)) strip_append_ghost(send_l, S, hot);
+    void* dst = nullptr;
+    if (S.has_right && a.x >= S.x_hi) dst = send_r;
+    else if (S.has_left && a.x < S.x_lo) dst = send_l;
+    if (dst != nullptr) {
+        StripHeader* h = reinterpret_cast<StripHeader*>(dst);
+        const uint32_t i = atomicAdd(&h->n_mig, 1u);
+        if (i < S.mcap) {
+            const uint32_t b = Cc.cparent[c];
+            MigRec m;
+            m.slot = b; m.col = c;
+            m.pos = B.pos[b]; m.pos_old = B.pos_old[b]; m.acc = B.acc[b]; m.vel = B.vel[b]; m.vreq = B.vreq[b]; m.cabs = a;
+            m.rot = B.rot[b]; m.angvel = B.angvel[b]; m.torque = B.torque[b]; m.has_vreq = B.has_vreq[b];
+            m.pad[0] = m.pad[1] = 0u;
+            strip_migs(dst, S.gcap)[i] = m;
+        } else {
+            h->overflow = 1u;
+        }
+    }
+}
+
+// bins the received ghosts into the table under construction (before k_scan)
+__global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc S, const void* recv_l, const void* recv_r, uint32_t* tab_next,
+                                                          uint32_t* tile_next, uint2* gcell, DeviceStats* stats) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * S.gcap) return;
+    const uint32_t side = i / S.gcap, j = i - side * S.gcap;
+    const void* msg = side ? recv_r : recv_l;
+    if ((side ? S.has_right : S.has_left) == 0) return;
+    const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
+    if (j == 0 && h->overflow) atomicOr(&stats->nan_flag, 4u);
+    if (j >= min(h->n_ghost, S.gcap)) return;
+    const float4 hot = strip_ghosts(const_cast<void*>(msg))[j];
+    const uint32_t cell = cell_index(g, bin_coord(hot.x, g.inv_cell), bin_coord(hot.y, g.inv_cell));
+    gcell[i] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
+}
+
+__global__ void __launch_bounds__(256) k_strip_scatter_ghosts(StripDesc S, const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
+                                                              const uint2* __restrict__ gcell, float4* __restrict__ hot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * S.gcap) return;
+    const uint32_t side = i / S.gcap, j = i - side * S.gcap;
+    const void* msg = side ? recv_r : recv_l;
+    if ((side ? S.has_right : S.has_left) == 0) return;
+    const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
+    if (j >= min(h->n_ghost, S.gcap)) return;
+    const uint2 cr = gcell[i];
+    hot[__ldg(tab + cr.x) + cr.y] = strip_ghosts(const_cast<void*>(msg))[j];
+}
+
+// ownership hand-over, after the broadphase of this substep was built: leavers (my send buffers) are released,
+// arrivals (my receive buffers) are adopted together with their full state
+__global__ void __launch_bounds__(256) k_strip_migrate(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r,
+                                                       const void* recv_l, const void* recv_r, uint8_t* owned, uint8_t* cowned) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4u * S.mcap) return;
+    const uint32_t which = i / S.mcap, j = i - which * S.mcap;
+    const void* msg = which == 0 ? send_l : (which == 1 ? send_r : (which == 2 ? recv_l : recv_r));
+    const bool has = (which & 1u) ? S.has_right != 0 : S.has_left != 0;
+    if (!has) return;
+    const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
+    if (j >= min(h->n_mig, S.mcap)) return;
+    const MigRec m = strip_migs(const_cast<void*>(msg), S.gcap)[j];
+    if (which < 2u) {
+        owned[m.slot] = 0;
+        cowned[m.col] = 0;
+    } else {
+        B.pos[m.slot] = m.pos; B.pos_old[m.slot] = m.pos_old; B.acc[m.slot] = m.acc; B.vel[m.slot] = m.vel; B.vreq[m.slot] = m.vreq;
+        B.rot[m.slot] = m.rot; B.angvel[m.slot] = m.angvel; B.torque[m.slot] = m.torque; B.has_vreq[m.slot] = (uint8_t)m.has_vreq;
+        Cc.cabs[m.col] = m.cabs;
+        owned[m.slot] = 1;
+        cowned[m.col] = 1;
+    }
 }
 
 }  // namespace blobs

@@ -106,6 +106,29 @@ struct Broadphase {
     uint32_t* tile_next;     // per-scan-tile totals of tab_next (zeroed), so k_scan needs no inter-block dependency
 };
 
+// ---- strip decomposition of one large world across ranks (BASELINE config #5) -------------------------------------
+struct StripDesc {
+    float x_lo, x_hi;          // this rank owns bodies whose collider snapshot x lies in [x_lo, x_hi)
+    int has_left, has_right;
+    float rmax;
+    uint32_t gcap, mcap;       // capacities of the ghost / migration sections of a message
+};
+// full body state of a sphere that crossed a strip edge (the arrays are indexed by GLOBAL slot on every rank, so a
+// migration is a plain write at [slot] on the receiving side — no device-side allocation)
+struct MigRec {
+    uint32_t slot, col;
+    float2 pos, pos_old, acc, vel, vreq, cabs;
+    float rot, angvel, torque;
+    uint32_t has_vreq;
+    uint32_t pad[2];
+};
+static_assert(sizeof(MigRec) == 80, "MigRec layout");
+// message = header | float4 ghost[gcap] | MigRec mig[mcap]; fixed size so that no count has to reach the host
+struct StripHeader { uint32_t n_ghost, n_mig, overflow, pad; };
+__host__ __device__ inline size_t strip_msg_bytes(uint32_t gcap, uint32_t mcap) { return sizeof(StripHeader) + (size_t)gcap * 16 + (size_t)mcap * sizeof(MigRec); }
+__host__ __device__ inline float4* strip_ghosts(void* msg) { return reinterpret_cast<float4*>(reinterpret_cast<char*>(msg) + sizeof(StripHeader)); }
+__host__ __device__ inline MigRec* strip_migs(void* msg, uint32_t gcap) { return reinterpret_cast<MigRec*>(reinterpret_cast<char*>(msg) + sizeof(StripHeader) + (size_t)gcap * 16); }
+
 struct Recording {           // optional pair/event output
     uint32_t mode;           // 0 off, 1 pairs, 2 events
     uint32_t cap;

@@ -7,7 +7,12 @@
 #include <cstdio>
 #include <numeric>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 namespace blobs {
+
+static void (*g_nccl_destroy)(void*) = nullptr;  // set once NCCL is loaded
 
 #define CU(call)                                         \
     do {                                                 \
@@ -75,6 +80,9 @@ World::~World() {
     isl_off.release(); isl_joint.release(); d_springs.release(); d_joints.release();
     hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
+    for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
+    d_owned.release(); d_cowned.release(); gcell.release();
+    if (nccl_comm && g_nccl_destroy) g_nccl_destroy(nccl_comm);
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
     if (d_rec_count) cudaFree(d_rec_count);
@@ -721,7 +729,7 @@ int World::choose_grid(bool) {
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
     if (nc) {
-        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), cs, (uint32_t)nc, d_stats);
+        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), cs, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
         launches++;
         CU(cudaGetLastError());
     }
@@ -733,7 +741,7 @@ int World::choose_grid(bool) {
         ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;
     }
     // a little slack so slow drift does not alias immediately; aliasing is harmless for correctness (toroidal table)
-    double W = (double)ex + std::max(4.0, ex / 16.0), H = (double)ey + std::max(4.0, ey / 16.0);
+    double W = (double)ex + std::max(4.0, ex / 16.0) + (strip_on ? 6.0 : 0.0), H = (double)ey + std::max(4.0, ey / 16.0);
     // table budget: ~4 cells per collider (per batched world), at most 2^30 entries overall
     double cap = std::max<double>(n_worlds > 1 ? 64.0 : 4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1) / (double)n_worlds);
     cap = std::min(cap, 1073741824.0 / (double)n_worlds);
@@ -761,7 +769,8 @@ int World::rebuild_broadphase() {
     const size_t nc = cols.slots();
     const size_t tn = table_entries();
     CU(tab_a.ensure(tn + SCAN_ITEMS, stream)); CU(tab_b.ensure(tn + SCAN_ITEMS, stream));
-    CU(hot_a.ensure(nc + 1, stream)); CU(hot_b.ensure(nc + 1, stream));   // +1: the scan may re-read index == #records
+    const size_t nrec = nc + 1 + (strip_on ? 2 * (size_t)strip.gcap : 0);  // +1: the scan may re-read index == #records
+    CU(hot_a.ensure(nrec, stream)); CU(hot_b.ensure(nrec, stream));
     const unsigned ntiles = cdiv(tn, SCAN_TILE);
     CU(tile_a.ensure(ntiles, stream)); CU(tile_b.ensure(ntiles, stream));
     CU(cudaMemsetAsync(tab_a.d, 0, tn * sizeof(uint32_t), stream));
@@ -774,14 +783,12 @@ int World::rebuild_broadphase() {
     uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
     if (nc) {
-        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc);
+        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc, strip_on ? d_cowned.d : nullptr);
         launches++;
     }
-    k_scan<<<ntiles, SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur);
-    launches++;
-    if (nc) {
-        k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(col_arrays(), tab_next, hot_next, (uint32_t)nc);
-        launches++;
+    {
+        int rc2 = strip_build_tail(tab_next, tab_cur, tile_next, tile_cur, hot_next, false);
+        if (rc2) return rc2;
     }
     CU(cudaGetLastError());
     cur_is_a = !cur_is_a;
@@ -840,7 +847,7 @@ int World::launch_substep(const SubstepParams& P) {
     R.count = d_rec_count;
     R.pairs = rec_pairs.d;
     R.vels = rec_vels.d;
-    const bool fused = allow_fused && n_joints_live == 0 && rec_mode != BLOBS_RECORD_EVENTS;
+    const bool fused = (allow_fused && n_joints_live == 0 && rec_mode != BLOBS_RECORD_EVENTS) || strip_on;
     const bool ordered = contact_mode == 0;
     last_fused = fused;
     const uint32_t nb = P.n_bodies, nc = P.n_colliders;
@@ -852,7 +859,7 @@ int World::launch_substep(const SubstepParams& P) {
     if (nb) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(nb, 256);
-#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats)
+#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, strip_on ? d_owned.d : nullptr)
 #define BLOBS_MAIN_VARIANT(BT, MB)                                   \
     do {                                                             \
         if (fused) {                                                 \
@@ -898,13 +905,8 @@ int World::launch_substep(const SubstepParams& P) {
             if (rc) return rc;
         }
     }
-    const size_t tn = table_entries();
-    rc = timed(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(bp.tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, bp.tile_next, tile_cur); });
+    rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
     if (rc) return rc;
-    if (nc) {
-        rc = timed(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, bp.tab_next, hot_next, nc); });
-        if (rc) return rc;
-    }
     cur_is_a = !cur_is_a;
     if (rec_mode && sub_recorded < d_sub_end.cap) {
         CU(cudaMemcpyAsync(d_sub_end.d + sub_recorded, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
@@ -937,7 +939,7 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
 int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run) {
     const size_t nc = cols.slots();
     if (nc) {
-        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), grid.cell, (uint32_t)nc, d_stats);
+        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), grid.cell, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
         launches++;
     }
     CU(cudaEventRecord(ev_step1, stream));
@@ -963,7 +965,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
         const double cap = std::max<double>(n_worlds > 1 ? 64.0 : 4096.0, 4.0 * (double)std::max<uint32_t>(n_active_cols, 1) / (double)n_worlds);
         const bool aliased = (ex > grid.W || ey > grid.H) && (double)grid.ncells < 0.5 * cap;
         const bool oversized = (double)grid.W * grid.H > (n_worlds > 1 ? 64.0 : 4096.0) && ((double)ex * 3 < grid.W && (double)ey * 3 < grid.H);
-        if (aliased || oversized) bp_dirty = true;
+        if ((aliased || oversized) && !strip_on) bp_dirty = true;  // strip mode: a rebuild is a collective, keep the table
     }
     if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");
     return BLOBS_OK;
@@ -1189,6 +1191,166 @@ int World::events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n) {
     if (n) *n = have;
     CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
     sub_recorded = 0;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- strip decomposition
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool load(std::string* err) {
+        if (lib) return true;
+        // resolved at run time so that single-GPU use has no NCCL dependency; inside a torch process this finds torch's copy
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { if (err) *err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define BLOBS_NCCL_SYM(f) f = reinterpret_cast<decltype(f)>(dlsym(lib, "nccl" #f)); if (!f) { if (err) *err = "libnccl lacks nccl" #f; return false; }
+        BLOBS_NCCL_SYM(GetUniqueId) BLOBS_NCCL_SYM(CommInitRank) BLOBS_NCCL_SYM(CommDestroy) BLOBS_NCCL_SYM(Send) BLOBS_NCCL_SYM(Recv)
+        BLOBS_NCCL_SYM(GroupStart) BLOBS_NCCL_SYM(GroupEnd) BLOBS_NCCL_SYM(GetErrorString)
+#undef BLOBS_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
+
+#define NC(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r__ = (call);                                                                    \
+        if (r__ != ncclSuccess) return fail(BLOBS_ERR_CUDA, std::string("NCCL error: ") + g_nccl.GetErrorString(r__) + " in " #call); \
+    } while (0)
+
+int World::strip_unique_id(uint8_t* out128, std::string* err) {
+    if (!g_nccl.load(err)) return BLOBS_ERR_CUDA;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { if (err) *err = "ncclGetUniqueId failed"; return BLOBS_ERR_CUDA; }
+    std::memcpy(out128, &id, 128);
+    return BLOBS_OK;
+}
+
+int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const uint8_t* id128, uint32_t gcap, uint32_t mcap) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !(x_lo < x_hi)) return fail(BLOBS_ERR_INVALID, "bad strip arguments");
+    int rc = flush();
+    if (rc) return rc;
+    if (topo_error) return fail(topo_error, topo_error_msg);
+    if (n_multi || n_springs_live || n_joints_live || n_worlds > 1 || rec_mode == BLOBS_RECORD_EVENTS)
+        return fail(BLOBS_ERR_INVALID, "strip decomposition supports single-collider bodies without springs/joints/events (DESIGN.md 8.1)");
+    if (nranks > 1) {
+        std::string e;
+        if (!g_nccl.load(&e)) return fail(BLOBS_ERR_CUDA, e);
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ncclComm_t comm = nullptr;
+        NC(g_nccl.CommInitRank(&comm, nranks, id, rank));
+        nccl_comm = comm;
+        g_nccl_destroy = [](void* c) { g_nccl.CommDestroy(static_cast<ncclComm_t>(c)); };
+    }
+    s_rank = rank;
+    s_nranks = nranks;
+    strip.x_lo = x_lo;
+    strip.x_hi = x_hi;
+    strip.has_left = rank > 0;
+    strip.has_right = rank + 1 < nranks;
+    strip.rmax = r_max;
+    strip.gcap = std::max<uint32_t>(gcap, 256);
+    strip.mcap = std::max<uint32_t>(mcap, 64);
+    msg_bytes = strip_msg_bytes(strip.gcap, strip.mcap);
+    for (int i = 0; i < 4; ++i) {
+        CU(cudaMalloc(&msg[i], msg_bytes));
+        CU(cudaMemsetAsync(msg[i], 0, msg_bytes, stream));
+    }
+    CU(gcell.ensure(2 * (size_t)strip.gcap, stream));
+    const size_t nb = bodies.slots(), nc = cols.slots();
+    CU(d_owned.ensure(std::max<size_t>(nb, 1), stream));
+    CU(d_cowned.ensure(std::max<size_t>(nc, 1), stream));
+    CU(cudaMemsetAsync(d_cowned.d, 0, d_cowned.cap, stream));
+    if (nb) {
+        k_strip_init_owned<<<cdiv(nb, 256), 256, 0, stream>>>(body_arrays(), col_arrays(), strip, d_owned.d, d_cowned.d, (uint32_t)nb);
+        launches++;
+        CU(cudaGetLastError());
+    }
+    strip_on = true;
+    bp_dirty = true;
+    return rebuild_broadphase();
+}
+
+int World::strip_exchange() {
+    if (s_nranks <= 1) return BLOBS_OK;
+    ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+    NC(g_nccl.GroupStart());
+    if (strip.has_right) {
+        NC(g_nccl.Send(msg[1], msg_bytes, ncclInt8, s_rank + 1, comm, stream));
+        NC(g_nccl.Recv(msg[3], msg_bytes, ncclInt8, s_rank + 1, comm, stream));
+    }
+    if (strip.has_left) {
+        NC(g_nccl.Send(msg[0], msg_bytes, ncclInt8, s_rank - 1, comm, stream));
+        NC(g_nccl.Recv(msg[2], msg_bytes, ncclInt8, s_rank - 1, comm, stream));
+    }
+    NC(g_nccl.GroupEnd());
+    nccl_exchanges++;
+    return BLOBS_OK;
+}
+
+// Everything after the owned colliders were binned into tab_next: [ghost exchange + ghost binning] -> scan -> scatter
+// [-> ghost scatter -> ownership hand-over]. Shared by the per-substep path and the out-of-step rebuild.
+int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch) {
+    const size_t tn = table_entries();
+    const uint32_t nc = (uint32_t)cols.slots();
+    const BodyArrays B = body_arrays();
+    const ColliderArrays C = col_arrays();
+    int rc;
+    auto run = [&](KClass k, auto&& f) -> int {
+        if (timed_launch) return timed(k, f);
+        f();
+        launches++;
+        CU(cudaGetLastError());
+        return BLOBS_OK;
+    };
+    if (strip_on) {
+        CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
+        CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
+        if (nc) {
+            rc = run(KC_OTHER, [&] { k_strip_pack<<<cdiv(nc, 256), 256, 0, stream>>>(B, C, strip, d_cowned.d, msg[0], msg[1], nc); });
+            if (rc) return rc;
+        }
+        rc = strip_exchange();
+        if (rc) return rc;
+        rc = run(KC_OTHER, [&] { k_strip_bin_ghosts<<<cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream>>>(grid, strip, msg[2], msg[3], tab_next, tile_next, gcell.d, d_stats); });
+        if (rc) return rc;
+    }
+    rc = run(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur); });
+    if (rc) return rc;
+    if (nc) {
+        rc = run(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, tab_next, hot_next, nc, strip_on ? d_cowned.d : nullptr); });
+        if (rc) return rc;
+    }
+    if (strip_on) {
+        rc = run(KC_OTHER, [&] { k_strip_scatter_ghosts<<<cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream>>>(strip, msg[2], msg[3], tab_next, gcell.d, hot_next); });
+        if (rc) return rc;
+        rc = run(KC_OTHER, [&] { k_strip_migrate<<<cdiv(4 * (size_t)strip.mcap, 256), 256, 0, stream>>>(B, C, strip, msg[0], msg[1], msg[2], msg[3], d_owned.d, d_cowned.d); });
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
+
+int World::strip_owned(uint8_t* out, size_t cap) {
+    const size_t n = std::min(cap, bodies.slots());
+    if (!strip_on) { std::memset(out, 1, n); return BLOBS_OK; }
+    if (n) {
+        CU(cudaMemcpyAsync(out, d_owned.d, n, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
     return BLOBS_OK;
 }
 

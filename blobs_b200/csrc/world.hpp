@@ -187,6 +187,9 @@ class World {
     int kernel_info(BlobsKernelInfo* out) const;
     int profile_enable(int on);
     int profile_read(float* ms, uint64_t* launches, size_t n);
+    static int strip_unique_id(uint8_t* out128, std::string* err);
+    int strip_configure(int rank, int nranks, float x_lo, float x_hi, const uint8_t* id128, uint32_t gcap, uint32_t mcap);
+    int strip_owned(uint8_t* out, size_t cap);
 
     size_t body_slots() const { return bodies.slots(); }
     size_t collider_slots() const { return cols.slots(); }
@@ -309,6 +312,19 @@ class World {
     std::vector<uint64_t> sub_end_host;  // running pair counts per substep since last drain
     uint32_t sub_recorded = 0;
     bool last_fused = false;
+
+    // strip decomposition (config #5)
+    bool strip_on = false;
+    int s_rank = 0, s_nranks = 1;
+    StripDesc strip{};
+    DevBuf<uint8_t> d_owned, d_cowned;
+    DevBuf<uint2> gcell;
+    void* msg[4] = {nullptr, nullptr, nullptr, nullptr};  // send_l, send_r, recv_l, recv_r
+    size_t msg_bytes = 0;
+    void* nccl_comm = nullptr;
+    uint64_t nccl_exchanges = 0;
+    int strip_exchange();
+    int strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch);
 
     // profiling
     uint64_t launches = 0;

@@ -232,6 +232,26 @@ class World:
         self._ck(self._lib.blobs_events_drain(self._h, A.ptr(ev), cap, C.byref(n)))
         return ev[: n.value]
 
+    # ---- multi-GPU strips (config #5)
+    @staticmethod
+    def strip_unique_id():
+        lib = load()
+        out = np.zeros(128, dtype=np.uint8)
+        rc = lib.blobs_strip_unique_id(A.ptr(out))
+        if rc:
+            raise BlobsError(rc, (lib.blobs_last_error(None) or b"").decode())
+        return out
+
+    def strip_configure(self, rank, nranks, x_lo, x_hi, unique_id=None, ghost_capacity=1 << 16, migrate_capacity=1 << 12):
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, dtype=np.uint8)
+        self._ck(self._lib.blobs_strip_configure(self._h, rank, nranks, x_lo, x_hi, None if uid is None else A.ptr(uid), ghost_capacity, migrate_capacity))
+
+    def strip_owned(self):
+        n = self.body_slots()
+        out = np.zeros(n, dtype=np.uint8)
+        self._ck(self._lib.blobs_strip_owned(self._h, A.ptr(out), n))
+        return out.astype(bool)
+
     # ---- introspection
     def kernel_info(self):
         k = A.KernelInfo()

@@ -249,6 +249,16 @@ int32_t blobs_profile_enable(BlobsWorld* w, int32_t on);
 /* ms accumulated per kernel class since enable: [0]=main/contacts, [1]=scan, [2]=scatter, [3]=springs, [4]=joints, [5]=integrate, [6]=other */
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n);
 
+/* ---- multi-GPU: one large world split into vertical strips, one rank (process + GPU) per strip (BASELINE config #5).
+ * No reference counterpart (the reference is single-threaded). Every rank builds the SAME full scene (identical handles),
+ * then calls blobs_strip_configure; from then on blobs_step* is collective: each rank advances the bodies whose collider
+ * snapshot x lies in [x_lo, x_hi) and exchanges ghost records / migrating bodies with its two neighbours once per
+ * substep (grouped ncclSend/ncclRecv over NVLink). Results are bit-identical to the single-GPU world. */
+int32_t blobs_strip_unique_id(uint8_t out128[128]);   /* ncclGetUniqueId on one rank; broadcast it (e.g. torch.distributed) */
+int32_t blobs_strip_configure(BlobsWorld* w, int32_t rank, int32_t nranks, float x_lo, float x_hi, const uint8_t id128[128],
+                              uint32_t ghost_capacity, uint32_t migrate_capacity);
+int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* owned_by_body_slot, size_t cap);   /* 1 = this rank currently owns the body */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,88 @@
+"""Worker for the multi-GPU parity test (run under torchrun, one rank per GPU):
+a strip-decomposed world across all ranks must be bit-identical to the same world on one GPU."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    import blobs_b200
+    from blobs_b200 import _abi as A
+    from blobs_b200 import scenes as S
+    from blobs_b200 import strips
+
+    side = int(os.environ.get("STRIP_TEST_SIDE", "192"))
+    steps = int(os.environ.get("STRIP_TEST_STEPS", "40"))
+    # gas of spheres with lateral velocities (so bodies really migrate across strip edges) inside a roomy circle
+    sc = S.lattice_scene(side, side, 1.05, (0.0, 0.0), 5, 0.3, 0.5, jitter=0.04, vel_disc=6.0, constraint_r=0.8 * side, name="strip", cell_size=1.0)
+    w = blobs_b200.World(gravity=sc.gravity, device=local)
+    S.build(w, sc)
+    edges = strips.agree_edges(dist, sc.bodies["position"]["x"], world)
+    assert strips.check_strip_width(edges, 0.5)
+    uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8))
+    dist.broadcast(uid, 0)
+    w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.numpy(), ghost_capacity=1 << 14, migrate_capacity=1 << 10)
+    own0 = w.strip_owned()
+    collisions = 0
+    for _ in range(steps):
+        st = w.step(1 / 60)
+        assert st["nan_detected"] == 0, st
+        collisions += st["collisions"]
+    own = w.strip_owned()
+    bodies, _ = w.download_bodies()
+    cols, _ = w.download_colliders()
+    pack = np.concatenate([bodies["position"]["x"], bodies["position"]["y"], bodies["position_old"]["x"], bodies["position_old"]["y"],
+                           bodies["calculated_velocity"]["x"], bodies["calculated_velocity"]["y"],
+                           cols["desc"]["absolute_transform"]["translation"]["x"], cols["desc"]["absolute_transform"]["translation"]["y"]]).astype(np.float32)
+    t_pack, t_own, t_own0 = torch.from_numpy(pack), torch.from_numpy(own.astype(np.uint8)), torch.from_numpy(own0.astype(np.uint8))
+    t_col = torch.tensor([collisions], dtype=torch.int64)
+    gp = [torch.zeros_like(t_pack) for _ in range(world)] if rank == 0 else None
+    go = [torch.zeros_like(t_own) for _ in range(world)] if rank == 0 else None
+    go0 = [torch.zeros_like(t_own0) for _ in range(world)] if rank == 0 else None
+    dist.gather(t_pack, gp, 0)
+    dist.gather(t_own, go, 0)
+    dist.gather(t_own0, go0, 0)
+    dist.all_reduce(t_col)
+    ok = True
+    if rank == 0:
+        n = sc.n_bodies
+        owners = np.stack([o.numpy() for o in go]).astype(np.int32)
+        owners0 = np.stack([o.numpy() for o in go0]).astype(np.int32)
+        assert (owners.sum(0) == 1).all() and (owners0.sum(0) == 1).all(), "every body must have exactly one owner"
+        migrated = int((owners.argmax(0) != owners0.argmax(0)).sum())
+        merged = np.zeros(8 * n, dtype=np.float32)
+        for r in range(world):
+            sel = np.tile(owners[r].astype(bool), 8)
+            merged[sel] = gp[r].numpy()[sel]
+        ref = blobs_b200.World(gravity=sc.gravity, device=local)
+        S.build(ref, sc)
+        ref_col = 0
+        for _ in range(steps):
+            ref_col += ref.step(1 / 60)["collisions"]
+        rb, _ = ref.download_bodies()
+        rc, _ = ref.download_colliders()
+        want = np.concatenate([rb["position"]["x"], rb["position"]["y"], rb["position_old"]["x"], rb["position_old"]["y"],
+                               rb["calculated_velocity"]["x"], rb["calculated_velocity"]["y"],
+                               rc["desc"]["absolute_transform"]["translation"]["x"], rc["desc"]["absolute_transform"]["translation"]["y"]]).astype(np.float32)
+        bad = np.nonzero(merged.view(np.uint32) != want.view(np.uint32))[0]
+        print(f"[strip test] ranks={world} spheres={n} steps={steps} migrated={migrated} collisions strips={int(t_col)} single={ref_col} mismatches={len(bad)}")
+        ok = len(bad) == 0 and int(t_col) == ref_col and (world == 1 or migrated > 0)
+        if len(bad):
+            print("first mismatches (field*n + slot):", bad[:10], merged[bad[:10]], want[bad[:10]])
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()

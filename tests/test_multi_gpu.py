@@ -1,0 +1,75 @@
+"""Multi-GPU path. GPU part: strip-decomposed world == single-GPU world, bit for bit (needs >= 2 GPUs, run
+with `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`). CPU part: the host-side partition logic under
+world_size-2 gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_strip_world_matches_single_gpu():
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29617",
+           os.path.join(REPO, "tests", "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, REPO)
+    from blobs_b200 import scenes as S
+    from blobs_b200 import strips
+
+    sc = S.cfg2(seed=3, side=64)
+    x = sc.bodies["position"]["x"]
+    half = len(x) // 2
+    local = x[:half] if rank == 0 else x[half:]      # each rank only looks at part of the scene
+    edges = strips.agree_edges(dist, local, world)
+    owner = strips.owner_of(x, edges)
+    q.put((rank, edges.tobytes(), owner.tobytes()))
+    dist.destroy_process_group()
+
+
+def test_strip_partition_agrees_across_ranks_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, 29641, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1], "ranks disagree on the strip edges"
+    assert got[0][2] == got[1][2], "ranks disagree on ownership"
+    owner = np.frombuffer(got[0][2], dtype=np.int32)
+    assert set(np.unique(owner)) == {0, 1} and abs(int((owner == 0).sum()) - int((owner == 1).sum())) < len(owner) * 0.1
+
+
+def test_strip_edges_properties():
+    sys.path.insert(0, REPO)
+    from blobs_b200 import strips
+
+    e = strips.strip_edges(-537.6, 537.6, 8)
+    assert e.dtype == np.float32 and len(e) == 9 and np.isneginf(e[0]) and np.isposinf(e[-1])
+    x = np.array([-1e9, -537.6, e[1], np.nextafter(e[1], np.float32(-np.inf)), 0.0, 537.6, 1e9, np.nan], dtype=np.float32)
+    o = strips.owner_of(x, e)
+    assert o.tolist() == [0, 0, 1, 0, 4, 7, 7, 0]
+    assert strips.check_strip_width(e, 0.5) and not strips.check_strip_width(strips.strip_edges(0, 10, 8), 0.5)

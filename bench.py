@@ -214,9 +214,29 @@ def run_ours(args):
         n = nb = 256 * (hi - lo)
         desc = f"cfg3: {n_worlds_total} batched independent worlds x 256 bodies (cfg1 at 16x16, circle R=4), worlds {lo}..{hi - 1} on this rank"
         scaling = "strong"
+    elif world > 1 and args.workload == "cfg2":
+        # BASELINE config #5 family: ONE world of 512*N x 4096 spheres (N=8: 16 777 216), cut into N vertical strips of 512 lattice
+        # columns (2 097 152 spheres per GPU, weak scaling); per-substep ghost + migration exchange with both neighbours over NCCL.
+        from blobs_b200 import strips
+
+        nx, ny = 512 * world, 4096
+        sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * max(nx, ny), name="cfg5", cell_size=1.0)
+        desc = (f"cfg5 family: one world of {nx}x{ny} = {nx * ny} spheres r=0.5 (pitch 1.05, circle R={0.8 * max(nx, ny):.0f}), strip-decomposed over {world} GPUs "
+                f"({nx * ny // world} spheres per GPU), ghost/migration exchange every substep via grouped ncclSend/ncclRecv")
+        w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
+        S.build(w, sc)
+        edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
+        uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=1 << 16, migrate_capacity=1 << 12)
+        n = int(w.strip_owned().sum())
+        nb = sc.n_bodies
+        del sc
     else:
-        # N > 1: one independent world per rank (no data-path collective; "replicas", weak scaling).
+        # other workloads at N > 1: one independent world per rank (no data-path collective; "replicas", weak scaling).
         sc, desc = make_scene(args.workload, seed=1 + rank)
+        if world > 1:
+            desc += f"; one independent world per GPU ({world} replicas, no collective)"
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
         n = sc.n_colliders
@@ -232,9 +252,12 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
     w.step(DT, n=W)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    forces = torch.zeros((nb, 2), dtype=torch.float32).pin_memory()
+    strips_on = world > 1 and args.workload == "cfg2"
+    io_cap = (n + n // 8 + 4096) if strips_on else nb     # strips: a rank only exchanges the bodies it owns with its host
+    forces = torch.zeros((io_cap, 2), dtype=torch.float32).pin_memory()
     forces[:, 0] = 0.05
-    pos_out = torch.zeros((nb, 2), dtype=torch.float32).pin_memory()
+    pos_out = torch.zeros((io_cap, 2), dtype=torch.float32).pin_memory()
+    slots_io = torch.zeros(io_cap, dtype=torch.int32).pin_memory()
 
     # ---- device-timed region -----------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -259,18 +282,28 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- end-to-end region (public C ABI, host buffers, copies inside) ------------------------------
+    io_bytes = 0
+    n_io = w.read_owned_positions_ptr(slots_io.data_ptr(), pos_out.data_ptr(), io_cap) if strips_on else nb
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        w.apply_forces_ptr(forces.data_ptr(), nb)      # pinned host -> device
-        w.step(DT)
-        w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
+        if strips_on:
+            w.apply_forces_indexed_ptr(slots_io.data_ptr(), forces.data_ptr(), min(n_io, io_cap))        # pinned host -> device (owned bodies)
+            io_bytes += min(n_io, io_cap) * 12
+            w.step(DT)
+            n_io = w.read_owned_positions_ptr(slots_io.data_ptr(), pos_out.data_ptr(), io_cap)            # device -> pinned host (synchronous)
+            io_bytes += min(n_io, io_cap) * 12
+        else:
+            w.apply_forces_ptr(forces.data_ptr(), nb)      # pinned host -> device
+            w.step(DT)
+            w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
+            io_bytes += nb * 16
     barrier()
     t_e2e = time.perf_counter() - t0
-    checksum = float(pos_out[:, 1].double().mean())
+    checksum = float(pos_out[: max(1, min(n_io, io_cap)), 1].double().mean())
 
     t = torch.tensor([t_dev_ms, t_e2e], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n), float(collisions), float(launches)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n), float(collisions), float(launches), float(io_bytes)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -286,13 +319,13 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev_ms / K,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc + ("" if world == 1 else f"; one independent world per GPU ({world} replicas, no collective)"),
+            "config": {"workload": desc,
                        "spheres_per_gpu": n, "substeps": substeps, "contact_mode": "ordered (bit-exact summation order)",
                        "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
                        "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
                        "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow},
             "clocks": clocks,
-            "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nb * 8, "d2h_bytes_per_step": nb * 8, "ms_per_step": t_e2e / K * 1e3,
+            "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,
                     "checksum_mean_y": checksum},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": "k_main<fused,ordered> (contacts + verlet + snapshot + clamp + cell binning)",

@@ -117,6 +117,8 @@ int32_t blobs_strip_configure(BlobsWorld* w, int32_t rank, int32_t nranks, float
     if (nranks > 1 && !id128) return BLOBS_ERR_INVALID;
     return w->w.strip_configure(rank, nranks, x_lo, x_hi, id128, gcap, mcap);
 }
+int32_t blobs_read_owned_positions(BlobsWorld* w, uint32_t* slots, float* xy, size_t cap, size_t* n) { W_OR_INVALID(w); W_OR_INVALID(slots); W_OR_INVALID(xy); return w->w.read_owned_positions(slots, xy, cap, n); }
+int32_t blobs_apply_forces_indexed(BlobsWorld* w, const uint32_t* slots, const float* fxy, size_t n) { W_OR_INVALID(w); if (n && (!slots || !fxy)) return BLOBS_ERR_INVALID; return w->w.apply_forces_indexed(slots, fxy, n); }
 int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* out, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.strip_owned(out, cap); }
 
 }  // extern "C"

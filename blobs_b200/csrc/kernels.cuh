@@ -1062,4 +1062,38 @@ __global__ void __launch_bounds__(256) k_strip_migrate(BodyArrays B, ColliderArr
     }
 }
 
+// distributed host I/O: every rank reads / drives only the bodies it currently owns
+__global__ void __launch_bounds__(256) k_compact_owned(BodyArrays B, const uint8_t* __restrict__ owned, uint32_t n_bodies, uint32_t cap,
+                                                       unsigned int* count, uint32_t* __restrict__ slots, float2* __restrict__ xy) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = b < n_bodies && (B.binfo[b].x & BF_ALIVE) && (owned == nullptr || owned[b]);
+    const unsigned int m = __ballot_sync(0xffffffffu, mine);
+    if (!m) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) {
+        const uint32_t i = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (i < cap) { slots[i] = b; xy[i] = B.pos[b]; }
+    }
+}
+
+// indexed RigidBody::apply_force (rigid_body.rs:155-160); entries for bodies this rank does not own are ignored
+__global__ void __launch_bounds__(256) k_apply_forces_indexed(BodyArrays B, const uint8_t* __restrict__ owned, const uint32_t* __restrict__ slots,
+                                                              const float2* __restrict__ force, uint32_t n, uint32_t n_bodies) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = slots[i];
+    if (b >= n_bodies || (owned != nullptr && !owned[b])) return;
+    const uint32_t f = B.binfo[b].x;
+    if (!(f & BF_ALIVE) || (f & BF_STATIC)) return;
+    const float2 F = force[i];
+    const float m = B.bmg[b].x;
+    float2 a = B.acc[b];
+    a.x = fadd(a.x, fdiv(F.x, m));
+    a.y = fadd(a.y, fdiv(F.y, m));
+    B.acc[b] = a;
+}
+
 }  // namespace blobs

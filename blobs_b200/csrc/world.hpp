@@ -146,7 +146,7 @@ struct HCollider {
 struct HSpring { uint64_t a, b; float rest, k, c; };
 struct HJoint { uint64_t a, b; BlobsVec2 aa, ab; float distance, target; };
 
-enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_COUNT };
+enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_PACK, KC_GHOST, KC_NCCL, KC_COUNT };
 
 class World {
    public:
@@ -190,6 +190,8 @@ class World {
     static int strip_unique_id(uint8_t* out128, std::string* err);
     int strip_configure(int rank, int nranks, float x_lo, float x_hi, const uint8_t* id128, uint32_t gcap, uint32_t mcap);
     int strip_owned(uint8_t* out, size_t cap);
+    int read_owned_positions(uint32_t* slots, float* xy, size_t cap, size_t* n);
+    int apply_forces_indexed(const uint32_t* slots, const float* fxy, size_t n);
 
     size_t body_slots() const { return bodies.slots(); }
     size_t collider_slots() const { return cols.slots(); }
@@ -319,6 +321,9 @@ class World {
     StripDesc strip{};
     DevBuf<uint8_t> d_owned, d_cowned;
     DevBuf<uint2> gcell;
+    DevBuf<uint32_t> io_slots;
+    DevBuf<float2> io_xy;
+    unsigned int* d_io_count = nullptr;
     void* msg[4] = {nullptr, nullptr, nullptr, nullptr};  // send_l, send_r, recv_l, recv_r
     size_t msg_bytes = 0;
     void* nccl_comm = nullptr;

@@ -252,6 +252,14 @@ class World:
         self._ck(self._lib.blobs_strip_owned(self._h, A.ptr(out), n))
         return out.astype(bool)
 
+    def read_owned_positions_ptr(self, slots_ptr, xy_ptr, cap):
+        n = C.c_size_t()
+        self._ck(self._lib.blobs_read_owned_positions(self._h, C.c_void_p(slots_ptr), C.c_void_p(xy_ptr), cap, C.byref(n)))
+        return n.value
+
+    def apply_forces_indexed_ptr(self, slots_ptr, fxy_ptr, n):
+        self._ck(self._lib.blobs_apply_forces_indexed(self._h, C.c_void_p(slots_ptr), C.c_void_p(fxy_ptr), n))
+
     # ---- introspection
     def kernel_info(self):
         k = A.KernelInfo()
@@ -262,8 +270,8 @@ class World:
         self._ck(self._lib.blobs_profile_enable(self._h, int(on)))
 
     def profile_read(self):
-        ms = np.zeros(7, dtype=np.float32)
-        nl = np.zeros(7, dtype=np.uint64)
-        self._ck(self._lib.blobs_profile_read(self._h, A.ptr(ms), A.ptr(nl), 7))
-        names = ["main", "scan", "scatter", "springs", "joints", "integrate", "other"]
+        names = ["main", "scan", "scatter", "springs", "joints", "integrate", "other", "strip_pack", "strip_ghost", "nccl_exchange"]
+        ms = np.zeros(len(names), dtype=np.float32)
+        nl = np.zeros(len(names), dtype=np.uint64)
+        self._ck(self._lib.blobs_profile_read(self._h, A.ptr(ms), A.ptr(nl), len(names)))
         return {k: (float(m), int(n)) for k, m, n in zip(names, ms, nl)}

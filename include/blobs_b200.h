@@ -246,7 +246,8 @@ typedef struct BlobsKernelInfo {
 int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out);
 /* CUDA-event timing of individual kernel classes during the next steps (0 = off). Used for the roofline. */
 int32_t blobs_profile_enable(BlobsWorld* w, int32_t on);
-/* ms accumulated per kernel class since enable: [0]=main/contacts, [1]=scan, [2]=scatter, [3]=springs, [4]=joints, [5]=integrate, [6]=other */
+/* ms accumulated per kernel class since enable: [0]=main/contacts, [1]=scan, [2]=scatter, [3]=springs, [4]=joints, [5]=integrate, [6]=other,
+ * [7]=strip pack, [8]=strip ghost binning/scatter/hand-over, [9]=NCCL ghost exchange */
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n);
 
 /* ---- multi-GPU: one large world split into vertical strips, one rank (process + GPU) per strip (BASELINE config #5).
@@ -258,6 +259,10 @@ int32_t blobs_strip_unique_id(uint8_t out128[128]);   /* ncclGetUniqueId on one 
 int32_t blobs_strip_configure(BlobsWorld* w, int32_t rank, int32_t nranks, float x_lo, float x_hi, const uint8_t id128[128],
                               uint32_t ghost_capacity, uint32_t migrate_capacity);
 int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* owned_by_body_slot, size_t cap);   /* 1 = this rank currently owns the body */
+/* distributed host I/O: compact (slot, position) list of the bodies this rank owns (all live bodies without strips), and the
+ * matching indexed RigidBody::apply_force (rigid_body.rs:155-160; entries for bodies owned elsewhere are ignored) */
+int32_t blobs_read_owned_positions(BlobsWorld* w, uint32_t* slots, float* xy, size_t cap, size_t* n);
+int32_t blobs_apply_forces_indexed(BlobsWorld* w, const uint32_t* slots, const float* force_xy, size_t n);
 
 #ifdef __cplusplus
 }

@@ -431,8 +431,8 @@ __device__ __forceinline__ uint32_t bin_collider(uint32_t* tab_next, uint32_t* t
     return rank;
 }
 
-__device__ __forceinline__ void publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t* tile_next,
-                                                 uint32_t c, uint32_t cflags, uint32_t wbase, float sx, float sy, float rot) {
+__device__ __forceinline__ float2 publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t* tile_next,
+                                                   uint32_t c, uint32_t cflags, uint32_t wbase, float sx, float sy, float rot) {
     float2 off = make_float2(0.f, 0.f);
     if (cflags & CF_OFFSET) off = Cc.coff[c];
     float sn = 0.0f, cs = 1.0f;
@@ -442,6 +442,44 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
     Cc.cabs[c] = make_float2(ax, ay);
     const uint32_t cell = wbase + cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
     Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
+    return make_float2(ax, ay);
+}
+
+// ---- strip decomposition: message packing (see the strip section at the end of this file) --------------------------
+__device__ __forceinline__ void strip_append_ghost(void* msg, const StripDesc& S, float4 hot) {
+    StripHeader* h = reinterpret_cast<StripHeader*>(msg);
+    const uint32_t i = atomicAdd(&h->n_ghost, 1u);
+    if (i < S.gcap) strip_ghosts(msg)[i] = hot;
+    else h->overflow = 1u;
+}
+
+// One owned collider with its NEW snapshot a: ghost record for whichever neighbour can reach it, full body state if it left
+// the strip. A neighbour-owned partner at x' >= x_hi needs me iff x' - x < r + r' <= reach (directed rounding keeps the
+// selection conservative).
+__device__ __forceinline__ void strip_pack_one(const BodyArrays& B, const ColliderArrays& Cc, const StripDesc& S, uint32_t c, uint32_t cflags,
+                                               float2 a, float r, void* send_l, void* send_r) {
+    const float reach = __fadd_ru(r, S.rmax);
+    const float4 hot = make_float4(a.x, a.y, r, __uint_as_float(c | ((cflags & CF_SENSOR) ? 0x80000000u : 0u)));
+    if (S.has_right && a.x >= __fsub_rd(S.x_hi, reach)) strip_append_ghost(send_r, S, hot);
+    if (S.has_left && a.x < __fadd_ru(S.x_lo, reach)) strip_append_ghost(send_l, S, hot);
+    void* dst = nullptr;
+    if (S.has_right && a.x >= S.x_hi) dst = send_r;
+    else if (S.has_left && a.x < S.x_lo) dst = send_l;
+    if (dst != nullptr) {
+        StripHeader* h = reinterpret_cast<StripHeader*>(dst);
+        const uint32_t i = atomicAdd(&h->n_mig, 1u);
+        if (i < S.mcap) {
+            const uint32_t b = Cc.cparent[c];
+            MigRec m;
+            m.slot = b; m.col = c;
+            m.pos = B.pos[b]; m.pos_old = B.pos_old[b]; m.acc = B.acc[b]; m.vel = B.vel[b]; m.vreq = B.vreq[b]; m.cabs = a;
+            m.rot = B.rot[b]; m.angvel = B.angvel[b]; m.torque = B.torque[b]; m.has_vreq = B.has_vreq[b];
+            m.pad[0] = m.pad[1] = 0u;
+            strip_migs(dst, S.gcap)[i] = m;
+        } else {
+            h->overflow = 1u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -454,14 +492,20 @@ __device__ __forceinline__ void publish_collider(const GridDesc& g, const Collid
 // ------------------------------------------------------------------------------------------------
 template <bool FUSED, bool ORDERED, int BATCH, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                              Broadphase bp, Recording rec, DeviceStats* stats, const uint8_t* __restrict__ owned) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+                                              Broadphase bp, Recording rec, DeviceStats* stats, StripView sv) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;
     out.n_pairs = out.n_coinc = 0;
     unsigned int n_over = 0;
-    bool inb = b < P.n_bodies;
-    if (owned != nullptr && inb) inb = owned[b] != 0;  // strip mode: only the owner rank updates a body
+    bool inb;
+    if (sv.olist != nullptr) {  // strip mode: threads enumerate the compact list of bodies this rank owns
+        inb = b < __ldg(sv.ocount);
+        b = inb ? sv.olist[b] : NO_SLOT;
+        inb = b != NO_SLOT;
+    } else {
+        inb = b < P.n_bodies;
+    }
     const uint32_t bl = inb ? b : 0u;
     // round 1: everything that only needs b (tail threads read slot 0 and discard)
     const uint2 info = B.binfo[bl];
@@ -514,7 +558,10 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
         if (FUSED) {
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
-            if (active_col) publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+            if (active_col) {
+                const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+                if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
+            }
         } else {
             B.pos[b] = p;
         }
@@ -767,6 +814,24 @@ __global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const uint32
     hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
 }
 
+// strip mode: same, enumerating the owned-body list (single-collider bodies only, see strip_configure)
+__global__ void __launch_bounds__(256) k_scatter_owned(BodyArrays B, ColliderArrays Cc, const uint32_t* __restrict__ tab, float4* __restrict__ hot,
+                                                       const uint32_t* __restrict__ olist, const uint32_t* __restrict__ ocount) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= __ldg(ocount)) return;
+    const uint32_t b = olist[t];
+    if (b == NO_SLOT) return;
+    const int32_t col = (int32_t)B.binfo[b].y;
+    if (col < 0) return;
+    const uint32_t c = (uint32_t)col;
+    const uint4 cc = Cc.cconst[c];
+    if (!(cc.y & CF_ACTIVE)) return;
+    const uint2 cr = Cc.ccell[c];
+    const float2 a = Cc.cabs[c];
+    const uint32_t dst = __ldg(tab + cr.x) + cr.y;
+    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K-springs: gravity + Spring::apply_force (springs.rs:25-47) for bodies with incident springs. One thread per such
 // body; its springs are visited in spring-slot order (the order the reference accumulates into `acceleration`).
@@ -967,45 +1032,14 @@ __global__ void __launch_bounds__(256) k_strip_init_owned(BodyArrays B, Collider
     if (col >= 0) cowned[col] = o;
 }
 
-__device__ __forceinline__ void strip_append_ghost(void* msg, const StripDesc& S, float4 hot) {
-    StripHeader* h = reinterpret_cast<StripHeader*>(msg);
-    const uint32_t i = atomicAdd(&h->n_ghost, 1u);
-    if (i < S.gcap) strip_ghosts(msg)[i] = hot;
-    else h->overflow = 1u;
-}
-
-// after the owned bodies were advanced: select ghosts and leavers from the NEW snapshots
+// out-of-step (re)build: select ghosts (and, defensively, leavers) from the current snapshots of all owned colliders
 __global__ void __launch_bounds__(256) k_strip_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, const uint8_t* __restrict__ cowned,
                                                     void* send_l, void* send_r, uint32_t n_colliders) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_colliders || !cowned[c]) return;
     const uint4 cc = Cc.cconst[c];
     if (!(cc.y & CF_ACTIVE)) return;
-    const float2 a = Cc.cabs[c];
-    const float r = __uint_as_float(cc.x);
-    const float reach = __fadd_ru(r, S.rmax);
-    const float4 hot = make_float4(a.x, a.y, r, __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
-    // a neighbour-owned partner at x' >= x_hi needs me iff x' - x < r + r' <= reach (directed rounding keeps it conservative)
-    if (S.has_right && a.x >= __fsub_rd(S.x_hi, reach)) strip_append_ghost(send_r, S, hot);
-    if (S.has_left && a.x < __fadd_ru(S.x_lo, reach)) strip_append_ghost(send_l, S, hot);
-    void* dst = nullptr;
-    if (S.has_right && a.x >= S.x_hi) dst = send_r;
-    else if (S.has_left && a.x < S.x_lo) dst = send_l;
-    if (dst != nullptr) {
-        StripHeader* h = reinterpret_cast<StripHeader*>(dst);
-        const uint32_t i = atomicAdd(&h->n_mig, 1u);
-        if (i < S.mcap) {
-            const uint32_t b = Cc.cparent[c];
-            MigRec m;
-            m.slot = b; m.col = c;
-            m.pos = B.pos[b]; m.pos_old = B.pos_old[b]; m.acc = B.acc[b]; m.vel = B.vel[b]; m.vreq = B.vreq[b]; m.cabs = a;
-            m.rot = B.rot[b]; m.angvel = B.angvel[b]; m.torque = B.torque[b]; m.has_vreq = B.has_vreq[b];
-            m.pad[0] = m.pad[1] = 0u;
-            strip_migs(dst, S.gcap)[i] = m;
-        } else {
-            h->overflow = 1u;
-        }
-    }
+    strip_pack_one(B, Cc, S, c, cc.y, Cc.cabs[c], __uint_as_float(cc.x), send_l, send_r);
 }
 
 // bins the received ghosts into the table under construction (before k_scan)
@@ -1024,24 +1058,25 @@ __global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc 
     gcell[i] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
 
-__global__ void __launch_bounds__(256) k_strip_scatter_ghosts(StripDesc S, const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
-                                                              const uint2* __restrict__ gcell, float4* __restrict__ hot) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2u * S.gcap) return;
-    const uint32_t side = i / S.gcap, j = i - side * S.gcap;
-    const void* msg = side ? recv_r : recv_l;
-    if ((side ? S.has_right : S.has_left) == 0) return;
-    const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
-    if (j >= min(h->n_ghost, S.gcap)) return;
-    const uint2 cr = gcell[i];
-    hot[__ldg(tab + cr.x) + cr.y] = strip_ghosts(const_cast<void*>(msg))[j];
-}
-
-// ownership hand-over, after the broadphase of this substep was built: leavers (my send buffers) are released,
-// arrivals (my receive buffers) are adopted together with their full state
-__global__ void __launch_bounds__(256) k_strip_migrate(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r,
-                                                       const void* recv_l, const void* recv_r, uint8_t* owned, uint8_t* cowned) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// After the owned records were scattered: (1) ghost records go to their slots in the new sorted array; (2) ownership
+// hand-over — leavers (my send buffers) are released, arrivals (my receive buffers) are adopted with their full state and
+// appended to the owned list. One launch: threads [0, 2*gcap) do (1), threads [2*gcap, 2*gcap + 4*mcap) do (2).
+__global__ void __launch_bounds__(256) k_strip_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r,
+                                                      const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
+                                                      const uint2* __restrict__ gcell, float4* __restrict__ hot, uint8_t* owned, uint8_t* cowned,
+                                                      uint32_t* olist, uint32_t* ocount, uint32_t* opos, uint32_t olist_cap, DeviceStats* stats) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2u * S.gcap) {
+        const uint32_t side = i / S.gcap, j = i - side * S.gcap;
+        const void* msg = side ? recv_r : recv_l;
+        if ((side ? S.has_right : S.has_left) == 0) return;
+        const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
+        if (j >= min(h->n_ghost, S.gcap)) return;
+        const uint2 cr = gcell[i];
+        hot[__ldg(tab + cr.x) + cr.y] = strip_ghosts(const_cast<void*>(msg))[j];
+        return;
+    }
+    i -= 2u * S.gcap;
     if (i >= 4u * S.mcap) return;
     const uint32_t which = i / S.mcap, j = i - which * S.mcap;
     const void* msg = which == 0 ? send_l : (which == 1 ? send_r : (which == 2 ? recv_l : recv_r));
@@ -1053,12 +1088,34 @@ __global__ void __launch_bounds__(256) k_strip_migrate(BodyArrays B, ColliderArr
     if (which < 2u) {
         owned[m.slot] = 0;
         cowned[m.col] = 0;
+        olist[opos[m.slot]] = NO_SLOT;
     } else {
         B.pos[m.slot] = m.pos; B.pos_old[m.slot] = m.pos_old; B.acc[m.slot] = m.acc; B.vel[m.slot] = m.vel; B.vreq[m.slot] = m.vreq;
         B.rot[m.slot] = m.rot; B.angvel[m.slot] = m.angvel; B.torque[m.slot] = m.torque; B.has_vreq[m.slot] = (uint8_t)m.has_vreq;
         Cc.cabs[m.col] = m.cabs;
         owned[m.slot] = 1;
         cowned[m.col] = 1;
+        const uint32_t k = atomicAdd(ocount, 1u);
+        if (k < olist_cap) { olist[k] = m.slot; opos[m.slot] = k; }
+        else atomicOr(&stats->nan_flag, 4u);
+    }
+}
+
+// (re)builds the compact owned list from the ownership bytes (once per blobs_step* call: drops released entries)
+__global__ void __launch_bounds__(256) k_strip_build_olist(const uint8_t* __restrict__ owned, uint32_t n_bodies, uint32_t* olist, uint32_t* ocount,
+                                                           uint32_t* opos) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = b < n_bodies && owned[b];
+    const unsigned int m = __ballot_sync(0xffffffffu, mine);
+    if (!m) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(ocount, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) {
+        const uint32_t i = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        olist[i] = b;
+        opos[b] = i;
     }
 }
 

@@ -129,6 +129,15 @@ __host__ __device__ inline size_t strip_msg_bytes(uint32_t gcap, uint32_t mcap) 
 __host__ __device__ inline float4* strip_ghosts(void* msg) { return reinterpret_cast<float4*>(reinterpret_cast<char*>(msg) + sizeof(StripHeader)); }
 __host__ __device__ inline MigRec* strip_migs(void* msg, uint32_t gcap) { return reinterpret_cast<MigRec*>(reinterpret_cast<char*>(msg) + sizeof(StripHeader) + (size_t)gcap * 16); }
 
+// per-launch view of the strip state handed to k_main / k_scatter (all null / zero when strips are off)
+struct StripView {
+    const uint32_t* olist;     // compact list of owned body slots (NO_SLOT = released entry); nullptr = strips off
+    const uint32_t* ocount;    // number of entries in olist (device-resident: arrivals are appended on the device)
+    void* send_l;
+    void* send_r;
+    StripDesc S;
+};
+
 struct Recording {           // optional pair/event output
     uint32_t mode;           // 0 off, 1 pairs, 2 events
     uint32_t cap;

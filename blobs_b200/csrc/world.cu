@@ -81,7 +81,8 @@ World::~World() {
     hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
-    d_owned.release(); d_cowned.release(); gcell.release(); io_slots.release(); io_xy.release();
+    d_owned.release(); d_cowned.release(); gcell.release(); io_slots.release(); io_xy.release(); olist.release(); opos.release();
+    if (d_ocount) cudaFree(d_ocount);
     if (d_io_count) cudaFree(d_io_count);
     if (nccl_comm && g_nccl_destroy) g_nccl_destroy(nccl_comm);
     if (d_stats) cudaFree(d_stats);
@@ -857,10 +858,15 @@ int World::launch_substep(const SubstepParams& P) {
         rc = timed(KC_SPRINGS, [&] { k_springs<<<cdiv(n_sb, 128), 128, 0, stream>>>(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
         if (rc) return rc;
     }
+    if (strip_on) {
+        CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
+        CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
+    }
     if (nb) {
         rc = timed(KC_MAIN, [&] {
-            const unsigned gdim = cdiv(nb, 256);
-#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, strip_on ? d_owned.d : nullptr)
+            const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch, 1) : nb, 256);
+            const StripView sv = strip_view();
+#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv)
 #define BLOBS_MAIN_VARIANT(BT, MB)                                   \
     do {                                                             \
         if (fused) {                                                 \
@@ -909,6 +915,7 @@ int World::launch_substep(const SubstepParams& P) {
     rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
     if (rc) return rc;
     cur_is_a = !cur_is_a;
+    if (strip_on) olaunch = (uint32_t)std::min<size_t>((size_t)olaunch + 2 * (size_t)strip.mcap, olist.cap);  // arrivals are appended on the device
     if (rec_mode && sub_recorded < d_sub_end.cap) {
         CU(cudaMemcpyAsync(d_sub_end.d + sub_recorded, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
         sub_recorded++;
@@ -982,6 +989,7 @@ int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
     init.bb_max_x = init.bb_max_y = INT32_MIN;
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
+    if (strip_on) { rc = strip_rebuild_olist(); if (rc) return rc; }
     CU(cudaEventRecord(ev_step0, stream));
     shadow_valid = false;
     for (uint32_t i = 0; i < n; ++i) {
@@ -1003,6 +1011,7 @@ int World::fixed_step(double frame_time, BlobsStepStats* stats) {
     init.bb_max_x = init.bb_max_y = INT32_MIN;
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
+    if (strip_on) { rc = strip_rebuild_olist(); if (rc) return rc; }
     CU(cudaEventRecord(ev_step0, stream));
     shadow_valid = false;
     accumulator += frame_time;
@@ -1282,8 +1291,41 @@ int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const u
         CU(cudaGetLastError());
     }
     strip_on = true;
+    CU(olist.ensure(std::max<size_t>(nb, 1), stream));
+    CU(opos.ensure(std::max<size_t>(nb, 1), stream));
+    if (!d_ocount) CU(cudaMalloc(&d_ocount, sizeof(uint32_t)));
+    rc = strip_rebuild_olist();
+    if (rc) return rc;
     bp_dirty = true;
     return rebuild_broadphase();
+}
+
+StripView World::strip_view() {
+    StripView v{};
+    if (strip_on) {
+        v.olist = olist.d;
+        v.ocount = d_ocount;
+        v.send_l = msg[0];
+        v.send_r = msg[1];
+        v.S = strip;
+    }
+    return v;
+}
+
+// compact list of owned bodies in (warp-granular) slot order; once per blobs_step* call, so released entries never pile up
+int World::strip_rebuild_olist() {
+    const size_t nb = bodies.slots();
+    CU(cudaMemsetAsync(d_ocount, 0, sizeof(uint32_t), stream));
+    if (nb) {
+        k_strip_build_olist<<<cdiv(nb, 256), 256, 0, stream>>>(d_owned.d, (uint32_t)nb, olist.d, d_ocount, opos.d);
+        launches++;
+        CU(cudaGetLastError());
+    }
+    uint32_t cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, d_ocount, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    olaunch = cnt;
+    return BLOBS_OK;
 }
 
 int World::strip_exchange() {
@@ -1319,9 +1361,11 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
         return BLOBS_OK;
     };
     if (strip_on) {
-        CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
-        CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
-        if (nc) {
+        if (!timed_launch) {  // in-step: the headers are cleared before k_main (launch_substep)
+            CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
+            CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
+        }
+        if (nc && !timed_launch) {  // inside a step the pack is fused into k_main's tail
             rc = run(KC_PACK, [&] { k_strip_pack<<<cdiv(nc, 256), 256, 0, stream>>>(B, C, strip, d_cowned.d, msg[0], msg[1], nc); });
             if (rc) return rc;
         }
@@ -1340,14 +1384,17 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
     }
     rc = run(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur); });
     if (rc) return rc;
-    if (nc) {
-        rc = run(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, tab_next, hot_next, nc, strip_on ? d_cowned.d : nullptr); });
+    if (nc && !strip_on) {
+        rc = run(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, tab_next, hot_next, nc, nullptr); });
         if (rc) return rc;
     }
     if (strip_on) {
-        rc = run(KC_GHOST, [&] { k_strip_scatter_ghosts<<<cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream>>>(strip, msg[2], msg[3], tab_next, gcell.d, hot_next); });
+        rc = run(KC_SCATTER, [&] { k_scatter_owned<<<cdiv(std::max<uint32_t>(olaunch, 1), 256), 256, 0, stream>>>(B, C, tab_next, hot_next, olist.d, d_ocount); });
         if (rc) return rc;
-        rc = run(KC_GHOST, [&] { k_strip_migrate<<<cdiv(4 * (size_t)strip.mcap, 256), 256, 0, stream>>>(B, C, strip, msg[0], msg[1], msg[2], msg[3], d_owned.d, d_cowned.d); });
+        rc = run(KC_GHOST, [&] {
+            k_strip_finish<<<cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream>>>(B, C, strip, msg[0], msg[1], msg[2], msg[3], tab_next, gcell.d, hot_next,
+                                                                                                           d_owned.d, d_cowned.d, olist.d, d_ocount, opos.d, (uint32_t)olist.cap, d_stats);
+        });
         if (rc) return rc;
     }
     return BLOBS_OK;

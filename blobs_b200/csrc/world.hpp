@@ -321,6 +321,11 @@ class World {
     StripDesc strip{};
     DevBuf<uint8_t> d_owned, d_cowned;
     DevBuf<uint2> gcell;
+    DevBuf<uint32_t> olist, opos;      // compact list of owned body slots + position of each body in it
+    uint32_t* d_ocount = nullptr;
+    uint32_t olaunch = 0;              // host upper bound of *d_ocount for launch sizing
+    StripView strip_view();
+    int strip_rebuild_olist();
     DevBuf<uint32_t> io_slots;
     DevBuf<float2> io_xy;
     unsigned int* d_io_count = nullptr;

@@ -76,10 +76,18 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+
+    def mark(self):
+        """the timed region starts here: remember how many samples belong to the warm-up tail"""
+        self.f.flush()
+        try:
+            self.n_before = sum(1 for _ in open(self.f.name))
+        except OSError:
+            self.n_before = 0
 
     def stop(self):
         if self.p is None:
@@ -105,7 +113,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_before_timed_region": getattr(self, "n_before", 0), "interval_ms": 20, "power_w_max": max(power)}
 
 
 def measured_peak():
@@ -228,7 +237,7 @@ def run_ours(args):
         edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
         uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
         dist.broadcast(uid, 0)
-        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=1 << 16, migrate_capacity=1 << 12)
+        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=8 * ny, migrate_capacity=ny // 2)
         n = int(w.strip_owned().sum())
         nb = sc.n_bodies
         del sc
@@ -250,7 +259,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     K, W = args.steps, max(args.warmup, 3)
-    w.step(DT, n=W)
+    sampler = ClockSampler(local)
+    w.step(DT, n=max(W - 3, 0))
+    sampler.start()          # nvidia-smi needs ~100 ms to produce its first line: start it under the last warm-up steps (same load)
+    w.step(DT, n=min(W, 3))
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     strips_on = world > 1 and args.workload == "cfg2"
     io_cap = (n + n // 8 + 4096) if strips_on else nb     # strips: a rank only exchanges the bodies it owns with its host
@@ -260,9 +272,8 @@ def run_ours(args):
     slots_io = torch.zeros(io_cap, dtype=torch.int32).pin_memory()
 
     # ---- device-timed region -----------------------------------------------------------------
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     w.profile_enable(True)
     l0 = w.kernel_info()["launches"]
     t_dev_ms, collisions, overflow = 0.0, 0, 0
@@ -271,6 +282,7 @@ def run_ours(args):
             flush.zero_()
             torch.cuda.synchronize()
         st = w.step(DT)
+        assert not (st["nan_detected"] & 4), "strip message buffers overflowed"
         t_dev_ms += st["gpu_ms"]
         collisions += st["collisions"]
         overflow += st["list_overflow"]

@@ -50,7 +50,11 @@ __device__ __forceinline__ Rec make_rec(const float4 h, const uint4 c) {
 }
 __device__ __forceinline__ Rec load_rec(const Broadphase& bp, const uint4* __restrict__ ccold, uint32_t k) {
     const float4 h = __ldg(bp.hot + k);
-    return make_rec(h, __ldg(ccold + (__float_as_uint(h.w) & 0x7fffffffu)));
+    const uint32_t w = __float_as_uint(h.w);
+    if (w & HOT_COLD_BIT) return make_rec(h, __ldg(ccold + (w & HOT_SLOT_MASK)));
+    // default sphere: calculated_mass = 2 * (2r) exactly, groups ALL; its parent has no other collider, so it can never equal
+    // the querying body (NO_SLOT is a safe stand-in; event recording, the only consumer of the real parent, forces the flag)
+    return make_rec(h, make_uint4(__float_as_uint(fmul(4.0f, h.z)), 0xffffffffu, 0xffffffffu, NO_SLOT));
 }
 
 // Cell range that can hold a partner of a sphere at (x, y) with radius r, on the toroidal table.
@@ -119,10 +123,11 @@ struct Contact {
 };
 
 __device__ __forceinline__ bool narrowphase(const SelfCol& s, const Rec& o, Contact& c) {
-    if (o.parent == s.body) return false;                                           // physics.rs:260 (also skips self)
+    if ((o.slot_sensor & HOT_SLOT_MASK) == s.slot) return false;                    // a collider never pairs with itself (j < i)
+    if (o.parent == s.body) return false;                                           // physics.rs:260 (same parent)
     if (!((s.memb & o.filt) != 0u && (o.memb & s.filt) != 0u)) return false;        // groups.rs:52-57
-    const uint32_t oslot = o.slot_sensor & 0x7fffffffu;
-    const bool osens = (o.slot_sensor >> 31) != 0u;
+    const uint32_t oslot = o.slot_sensor & HOT_SLOT_MASK;
+    const bool osens = (o.slot_sensor & HOT_SENSOR_BIT) != 0u;
     const bool i_am_a = s.slot > oslot;                                             // physics.rs:248-249 (a = later slot)
     // axis = abs_a - abs_b (physics.rs:264); x - y == -(y - x) exactly, so compute from self and flip
     float ax = i_am_a ? fsub(s.x, o.x) : fsub(o.x, s.x);
@@ -229,7 +234,7 @@ __device__ __forceinline__ void take_candidate(const SelfCol& s, const Rec& o, C
                 if (rec.mode == 2u) {
                     // calculated_velocity before this substep's update (physics.rs:288-289); event mode always runs the
                     // split pipeline, so vel[] is not being rewritten concurrently
-                    const float2 va = vel[s.body], vb = vel[o.parent];
+                    const float2 va = vel[s.body], vb = vel[o.parent];  // event mode flags every record needs_cold, so parent is real
                     rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
                 }
             } else {
@@ -303,7 +308,7 @@ __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphas
             }
 #pragma unroll
             for (int i = 0; i < BATCH; ++i) {
-                const uint32_t oslot = __float_as_uint(h[i].w) & 0x7fffffffu;
+                const uint32_t oslot = __float_as_uint(h[i].w) & HOT_SLOT_MASK;
                 const float dx = s.x - h[i].x, dy = s.y - h[i].y;
                 const float d2 = __fmaf_rn(dx, dx, dy * dy);
                 const float mdk = __fmaf_rn(h[i].z, 1.00005f, srk);  // (ra + rb) * 1.00005
@@ -459,7 +464,7 @@ __device__ __forceinline__ void strip_append_ghost(void* msg, const StripDesc& S
 __device__ __forceinline__ void strip_pack_one(const BodyArrays& B, const ColliderArrays& Cc, const StripDesc& S, uint32_t c, uint32_t cflags,
                                                float2 a, float r, void* send_l, void* send_r) {
     const float reach = __fadd_ru(r, S.rmax);
-    const float4 hot = make_float4(a.x, a.y, r, __uint_as_float(c | ((cflags & CF_SENSOR) ? 0x80000000u : 0u)));
+    const float4 hot = make_float4(a.x, a.y, r, __uint_as_float(hot_word(c, cflags)));
     if (S.has_right && a.x >= __fsub_rd(S.x_hi, reach)) strip_append_ghost(send_r, S, hot);
     if (S.has_left && a.x < __fadd_ru(S.x_lo, reach)) strip_append_ghost(send_l, S, hot);
     void* dst = nullptr;
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(256) k_scatter(ColliderArrays Cc, const uint32
     const float2 a = Cc.cabs[c];
     if (!(cc.y & CF_ACTIVE)) return;
     const uint32_t dst = __ldg(tab + cr.x) + cr.y;
-    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
+    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(hot_word(c, cc.y)));
 }
 
 // strip mode: same, enumerating the owned-body list (single-collider bodies only, see strip_configure)
@@ -829,7 +834,7 @@ __global__ void __launch_bounds__(256) k_scatter_owned(BodyArrays B, ColliderArr
     const uint2 cr = Cc.ccell[c];
     const float2 a = Cc.cabs[c];
     const uint32_t dst = __ldg(tab + cr.x) + cr.y;
-    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(c | ((cc.y & CF_SENSOR) ? 0x80000000u : 0u)));
+    hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(hot_word(c, cc.y)));
 }
 
 // ------------------------------------------------------------------------------------------------

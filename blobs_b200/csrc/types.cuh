@@ -20,20 +20,28 @@ enum : uint32_t {
     CF_ACTIVE = 1u << 0,  // alive AND parent handle resolves to a live body (physics.rs:252-253,270)
     CF_SENSOR = 1u << 1,
     CF_OFFSET = 1u << 2,  // offset.translation != 0 (snapshot needs coff)
+    CF_COLD = 1u << 3,    // the record's cold half is NOT the default (m = 4r, groups = ALL, sole collider of its parent)
 };
 constexpr uint32_t NO_SLOT = 0xffffffffu;
+// hot.w packing: collider slot | needs-cold << 30 | is_sensor << 31
+constexpr uint32_t HOT_SLOT_MASK = 0x3fffffffu, HOT_COLD_BIT = 0x40000000u, HOT_SENSOR_BIT = 0x80000000u;
+__host__ __device__ inline uint32_t hot_word(uint32_t slot, uint32_t cflags) {
+    return slot | ((cflags & CF_SENSOR) ? HOT_SENSOR_BIT : 0u) | ((cflags & CF_COLD) ? HOT_COLD_BIT : 0u);
+}
 constexpr int32_t BODY_NO_COLLIDER = -1;  // body_col[] encoding; <= -2 : multi-collider body (handled by k_multi)
 
 // Broadphase record of an active collider, as seen by the narrowphase. It is stored as two 16-byte halves:
-//   hot  = (x, y, r, slot | is_sensor << 31)   — cell-sorted array rebuilt every substep; enough for the self test and the
-//                                                 distance prefilter
-//   cold = (m, memberships, filter, parent)    — static per-collider array (ccold[slot]), only fetched for candidates that
-//                                                 survive the prefilter
+//   hot  = (x, y, r, slot | needs_cold << 30 | is_sensor << 31) — cell-sorted array rebuilt every substep; enough for the
+//                                                 self test and the distance prefilter
+//   cold = (m, memberships, filter, parent)    — static per-collider array (ccold[slot]); fetched only for prefilter survivors
+//                                                 whose record is flagged needs_cold. The default sphere (sole collider of its
+//                                                 body, no mass override, not a sensor, groups ALL) has m = 2*(2r) = 4r exactly
+//                                                 (collider.rs:40-42 + the doubled handle), so its cold half is synthesised.
 struct Rec {
     float x, y, r, m;          // snapshot translation (physics.rs:360-366), radius, parent body's calculated_mass
     uint32_t memb, filt;       // InteractionGroups (groups.rs:7-12)
     uint32_t parent;           // parent body slot
-    uint32_t slot_sensor;      // collider slot | is_sensor << 31
+    uint32_t slot_sensor;      // hot.w (see hot_word)
 };
 
 struct GridDesc {

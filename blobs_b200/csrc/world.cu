@@ -632,6 +632,18 @@ int World::rebuild_topology() {
             }
             if (x.desc.is_sensor) f |= CF_SENSOR;
             if (x.desc.offset.translation.x != 0.0f || x.desc.offset.translation.y != 0.0f) f |= CF_OFFSET;
+            // default cold half? (sole collider of its body, mass exactly 4r, groups ALL, not a sensor) — otherwise the narrowphase
+            // must fetch ccold[]. Event recording needs the partner's real parent slot, so it flags everything.
+            bool dflt = p != NO_SLOT && !x.desc.is_sensor && x.desc.memberships == 0xffffffffu && x.desc.filter == 0xffffffffu &&
+                        rec_mode != BLOBS_RECORD_EVENTS;
+            if (dflt) {
+                const HBody& pb = hb[p];
+                size_t live = 0;
+                for (uint32_t cc2 : pb.cols) live += (cols.alive[cc2] && hc[cc2].parent == x.parent) ? 1 : 0;
+                const float m4 = 4.0f * x.desc.radius, mb = bmg.h[p].x;
+                dflt = live == 1 && std::memcmp(&m4, &mb, 4) == 0;
+            }
+            if (!dflt) f |= CF_COLD;
         }
         {
             uint4 e = cconst.h[c];
@@ -688,6 +700,7 @@ int World::rebuild_topology() {
     CU(upload(d_springs, sp, stream)); CU(upload(d_joints, jp, stream));
     CU(cudaStreamSynchronize(stream));  // the staging vectors above are locals
     topo_dirty = false;
+    bp_dirty = true;  // record words (flags, parents, masses) may have changed
     return BLOBS_OK;
 }
 
@@ -882,6 +895,8 @@ int World::launch_substep(const SubstepParams& P) {
                 case 3: BLOBS_MAIN_VARIANT(4, 5); break;
                 case 4: BLOBS_MAIN_VARIANT(4, 3); break;
                 case 5: BLOBS_MAIN_VARIANT(8, 3); break;
+                case 6: BLOBS_MAIN_VARIANT(6, 4); break;
+                case 7: BLOBS_MAIN_VARIANT(2, 5); break;
                 default: BLOBS_MAIN_VARIANT(4, 4); break;
             }
 #undef BLOBS_MAIN_VARIANT
@@ -1137,6 +1152,7 @@ int World::download_cell_coords(int32_t* cx, int32_t* cy, size_t cap) {
 int World::record_contacts(int mode, size_t cap) {
     if (mode < 0 || mode > 2) return fail(BLOBS_ERR_INVALID, "bad record mode");
     CU(cudaStreamSynchronize(stream));
+    if ((mode == BLOBS_RECORD_EVENTS) != (rec_mode == BLOBS_RECORD_EVENTS)) topo_dirty = bp_dirty = true;  // CF_COLD depends on it
     rec_mode = mode;
     rec_cap = mode ? std::max<size_t>(cap, 1) : 0;
     if (mode) {

@@ -38,6 +38,8 @@ SIGNATURES = {
     "blobs_spring_remove": (C.c_int32, [_vp, C.c_uint64]),
     "blobs_joint_insert": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, A.Vec2, A.Vec2, C.c_float, _u64p]),
     "blobs_joint_remove": (C.c_int32, [_vp, C.c_uint64]),
+    "blobs_spring_insert_many": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "blobs_joint_insert_many": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
     "blobs_constraint_push": (C.c_int32, [_vp, A.Vec2, C.c_float]),
     "blobs_constraint_clear": (C.c_int32, [_vp]),
     "blobs_step": (C.c_int32, [_vp, C.c_double, C.POINTER(A.StepStats)]),

@@ -1,4 +1,5 @@
 // extern "C" surface of libblobs_b200.so (include/blobs_b200.h). Thin forwarding only.
+#include <cmath>
 #include <new>
 
 #include "world.hpp"
@@ -77,6 +78,26 @@ int32_t blobs_collider_count(const BlobsWorld* w, uint64_t* out) { W_OR_INVALID(
 int32_t blobs_spring_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, float rest, float k, float c, BlobsHandle* out) { W_OR_INVALID(w); return w->w.spring_insert(a, b, rest, k, c, out); }
 int32_t blobs_spring_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.spring_remove(h); }
 int32_t blobs_joint_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, BlobsVec2 aa, BlobsVec2 ab, float dist, BlobsHandle* out) { W_OR_INVALID(w); return w->w.joint_insert(a, b, aa, ab, dist, out); }
+int32_t blobs_spring_insert_many(BlobsWorld* w, size_t n, const BlobsHandle* a, const BlobsHandle* b, const float* p3, BlobsHandle* out) {
+    W_OR_INVALID(w);
+    if (n && (!a || !b || !p3)) return BLOBS_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const int rc = w->w.spring_insert(a[i], b[i], p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], out ? out + i : nullptr);
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
+int32_t blobs_joint_insert_many(BlobsWorld* w, size_t n, const BlobsHandle* a, const BlobsHandle* b, const float* anc, const float* dist, BlobsHandle* out) {
+    W_OR_INVALID(w);
+    if (n && (!a || !b)) return BLOBS_ERR_INVALID;
+    for (size_t i = 0; i < n; ++i) {
+        const BlobsVec2 aa = anc ? BlobsVec2{anc[4 * i], anc[4 * i + 1]} : BlobsVec2{0.f, 0.f};
+        const BlobsVec2 ab = anc ? BlobsVec2{anc[4 * i + 2], anc[4 * i + 3]} : BlobsVec2{0.f, 0.f};
+        const int rc = w->w.joint_insert(a[i], b[i], aa, ab, dist ? dist[i] : NAN, out ? out + i : nullptr);
+        if (rc) return rc;
+    }
+    return BLOBS_OK;
+}
 int32_t blobs_joint_remove(BlobsWorld* w, BlobsHandle h) { W_OR_INVALID(w); return w->w.joint_remove(h); }
 int32_t blobs_constraint_push(BlobsWorld* w, BlobsVec2 p, float r) { W_OR_INVALID(w); return w->w.constraint_push(p, r); }
 int32_t blobs_constraint_clear(BlobsWorld* w) { W_OR_INVALID(w); return w->w.constraint_clear(); }

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
                 }
             }
         }
-        if (FUSED) {
+        if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
             if (active_col) {
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                 p.y = fadd(p.y, out.fy);
             }
         }
-        if (FUSED) {
+        if (FUSED && !(flags & BF_JOINTED)) {
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
             for (uint32_t k = c0; k < c1; ++k) {
@@ -690,12 +690,13 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                                    uint32_t* tab_next, uint32_t* tile_next, DeviceStats* stats,
-                                                   const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols) {
+                                                   const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols, uint32_t only_flag) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.n_bodies) return;
     const uint2 info = B.binfo[b];
     const uint32_t flags = info.x;
     if (!(flags & BF_ALIVE)) return;
+    if (only_flag && !(flags & only_flag)) return;   // fused pipeline: free bodies were already advanced by k_main
     const int32_t col = (int32_t)info.y;
     const float2 p = B.pos[b];
     const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
@@ -931,6 +932,104 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
         }
     }
     if (bad) atomicOr(&stats->nan_flag, 2u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-joints-fused: the fast path of solve_fixed_joints (physics.rs:424-477) for islands of up to JOINT_SMEM_MAX bodies,
+// fused with update_objects + snapshot + constraints + binning for the island's bodies (physics.rs:323-395).
+// One thread per island, exactly the reference's operation order inside the island; the island's bodies live in shared
+// memory laid out [local body][thread] (conflict-free), so the 4 x J sequential solves never touch global memory:
+// every body is read once and written once. Joints carry LOCAL body indices.
+// ------------------------------------------------------------------------------------------------
+constexpr int JOINT_SMEM_MAX = 96;
+constexpr int JOINT_THREADS = 64;
+
+template <bool INTEGRATE>
+__global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                                                uint32_t* tab_next, uint32_t* tile_next, const uint32_t* __restrict__ isl_off,
+                                                                const float4* __restrict__ jli, uint32_t max_j, const uint32_t* __restrict__ isl_boff,
+                                                                const uint32_t* __restrict__ isl_body, const uint32_t* __restrict__ mb_off,
+                                                                const uint32_t* __restrict__ mb_cols, uint32_t n_islands, uint32_t iterations,
+                                                                DeviceStats* stats) {
+    extern __shared__ float4 sm[];  // (pos.x, pos.y, rot, +-1/mass): a negative inverse mass marks a static body
+    const uint32_t t = threadIdx.x, T = JOINT_THREADS;
+    const uint32_t i = blockIdx.x * T + t;
+    if (i >= n_islands) return;
+    const uint32_t b0 = isl_boff[i], nbod = isl_boff[i + 1] - b0;
+    for (uint32_t k = 0; k < nbod; ++k) {
+        const uint32_t slot = isl_body[b0 + k];
+        const float2 p = B.pos[slot];
+        const float m = B.bmg[slot].x;
+        const float im = fdiv(1.0f, m);   // calculated_mass.recip() (physics.rs:450), hoisted: masses do not change inside the solve
+        sm[k * T + t] = make_float4(p.x, p.y, B.rot[slot], (B.binfo[slot].x & BF_STATIC) ? -im : im);
+    }
+    const uint32_t nj = isl_off[i + 1] - isl_off[i];
+    // joints are stored interleaved per CTA: record e of the island handled by thread t sits at ((block * max_j + e) * T + t),
+    // two float4 each, so a warp reads consecutive records (coalesced) and the 4 sweeps re-hit L1
+    const float4* jrow = jli + 2 * ((size_t)blockIdx.x * max_j * T + t);
+    bool bad = false;
+    for (uint32_t it = 0; it < iterations; ++it) {
+        for (uint32_t e = 0; e < nj; ++e) {
+            const float4 q0 = __ldg(jrow + 2 * (size_t)e * T), q1 = __ldg(jrow + 2 * (size_t)e * T + 1);
+            JointParams jp;
+            jp.a = __float_as_uint(q0.x); jp.b = __float_as_uint(q0.y); jp.aax = q0.z; jp.aay = q0.w;
+            jp.abx = q1.x; jp.aby = q1.y; jp.distance = q1.z; jp.target = q1.w;
+            float4 A = sm[jp.a * T + t], Bv = sm[jp.b * T + t];
+            const float wax = fadd(A.x, jp.aax), way = fadd(A.y, jp.aay);            // physics.rs:434-435
+            const float wbx = fadd(Bv.x, jp.abx), wby = fadd(Bv.y, jp.aby);
+            const float dx = fsub(wbx, wax), dy = fsub(wby, way);                    // physics.rs:437
+            const float dist = vlen(dx, dy);
+            if (dist < 1e-6f) continue;                                              // physics.rs:440-442
+            const float off_by = fsub(dist, jp.distance);
+            const float cx = fdiv(fmul(off_by, dx), dist), cy = fdiv(fmul(off_by, dy), dist);   // physics.rs:445
+            const float ima = fabsf(A.w), imb = fabsf(Bv.w);
+            const float ims = fadd(ima, imb);                                        // physics.rs:450
+            if (A.w < 0.f) {                                                         // physics.rs:452-453
+                Bv.x = fsub(Bv.x, fmul(ims, cx)); Bv.y = fsub(Bv.y, fmul(ims, cy));
+            } else if (Bv.w < 0.f) {                                                 // physics.rs:454-455
+                A.x = fadd(A.x, fmul(ims, cx)); A.y = fadd(A.y, fmul(ims, cy));
+            } else {                                                                 // physics.rs:456-461
+                const float ratio = fdiv(ima, ims);
+                A.x = fadd(A.x, fmul(ratio, cx)); A.y = fadd(A.y, fmul(ratio, cy));
+                const float r1 = fsub(1.0f, ratio);
+                Bv.x = fsub(Bv.x, fmul(r1, cx)); Bv.y = fsub(Bv.y, fmul(r1, cy));
+            }
+            const float angle_a = atan2f(dy, dx);                                    // physics.rs:463
+            const float angle_b = -atan2f(dy, -dx);                                  // physics.rs:464
+            const float rc = fmul(fsub(fsub(angle_b, angle_a), jp.target), 0.5f);    // physics.rs:465-466
+            A.z = fadd(A.z, fmul(rc, P.dt));                                         // physics.rs:468-469
+            Bv.z = fsub(Bv.z, fmul(rc, P.dt));
+            if (!(fabsf(A.z) <= 3.4028235e38f) || !(fabsf(Bv.z) <= 3.4028235e38f)) bad = true;   // physics.rs:471-474
+            sm[jp.a * T + t] = A;
+            sm[jp.b * T + t] = Bv;
+        }
+    }
+    if (bad) atomicOr(&stats->nan_flag, 2u);
+    for (uint32_t k = 0; k < nbod; ++k) {
+        const uint32_t slot = isl_body[b0 + k];
+        const float4 v = sm[k * T + t];
+        B.rot[slot] = v.z;
+        if (!INTEGRATE) {
+            B.pos[slot] = make_float2(v.x, v.y);
+            continue;
+        }
+        const uint2 info = B.binfo[slot];
+        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[slot] * g.ncells : 0u;
+        float sx, sy, rot;
+        integrate_body(P, K, B, slot, info.x, B.bmg[slot].y, v.x, v.y, B.pos_old[slot], B.acc[slot], B.has_vreq[slot] != 0, sx, sy, rot, stats);
+        const int32_t col = (int32_t)info.y;
+        if (col >= 0) {
+            const uint32_t cf = Cc.cconst[col].y;
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, wbase, sx, sy, rot);
+        } else if (col <= -2) {
+            const uint32_t mi = (uint32_t)(-(col + 2));
+            for (uint32_t q = mb_off[mi]; q < mb_off[mi + 1]; ++q) {
+                const uint32_t c = mb_cols[q];
+                const uint32_t cf = Cc.cconst[c].y;
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, wbase, sx, sy, rot);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -53,6 +53,8 @@ int World::init() {
     CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
     CU(cudaEventCreate(&ev_step0));
     CU(cudaEventCreate(&ev_step1));
+    CU(cudaFuncSetAttribute(k_joints_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
+    CU(cudaFuncSetAttribute(k_joints_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
     if (params.body_capacity_hint) {
         const size_t n = params.body_capacity_hint;
         CU(pos.ensure(n, stream)); CU(pos_old.ensure(n, stream)); CU(acc.ensure(n, stream)); CU(vel.ensure(n, stream));
@@ -77,7 +79,7 @@ World::~World() {
     has_vreq.release(); rot.release(); angvel.release(); torque.release(); ccell.release();
     d_pending.release(); d_pending_col.release();
     mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
-    isl_off.release(); isl_joint.release(); d_springs.release(); d_joints.release();
+    isl_off.release(); isl_joint.release(); d_joints_inter.release(); isl_boff.release(); isl_body.release(); d_springs.release(); d_joints.release();
     hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
@@ -294,19 +296,20 @@ int World::body_remove(uint64_t h) {
 }
 
 int World::ensure_shadow() {
-    int rc = flush();
+    if (shadow_valid) return BLOBS_OK;  // staged writes keep a valid shadow up to date (body_insert / body_set)
+    int rc = flush_writes();            // only the device-authoritative state matters here: no topology rebuild
     if (rc) return rc;
-    if (!shadow_valid) {
-        const size_t n = bodies.slots();
-        sh_pos.resize(n);
-        sh_rot.resize(n);
-        if (n) {
-            CU(cudaMemcpyAsync(sh_pos.data(), pos.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
-            CU(cudaMemcpyAsync(sh_rot.data(), rot.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-        }
-        shadow_valid = true;
+    const size_t n = bodies.slots();
+    sh_pos.resize(n);
+    sh_rot.resize(n);
+    if (n) {
+        rc = ensure_capacity();
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(sh_pos.data(), pos.d, n * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(sh_rot.data(), rot.d, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
     }
+    shadow_valid = true;
     return BLOBS_OK;
 }
 
@@ -616,6 +619,41 @@ int World::rebuild_topology() {
         n_islands = (uint32_t)cnt.size();
     }
     n_joints_live = (uint32_t)jp.size();
+    // joint records with island-local body indices (bodies numbered in order of first appearance), interleaved per CTA of
+    // JOINT_THREADS islands: record e of island i at ((i / T) * max_j + e) * T + (i % T), two float4 each
+    std::vector<uint32_t> v_isl_boff{0}, v_isl_body;
+    std::vector<float4> jinter;
+    isl_max_bodies = 0;
+    isl_max_joints = 0;
+    for (uint32_t i = 0; i < n_islands; ++i) isl_max_joints = std::max(isl_max_joints, v_isl_off[i + 1] - v_isl_off[i]);
+    const size_t n_jblocks = (n_islands + JOINT_THREADS - 1) / JOINT_THREADS;
+    const bool inter_ok = n_islands > 0 && (double)n_jblocks * isl_max_joints * JOINT_THREADS <= 4.0 * (double)jp.size() + 65536.0;
+    if (inter_ok) jinter.assign(2 * n_jblocks * isl_max_joints * JOINT_THREADS, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        std::vector<int32_t> local(nb, -1);
+        for (uint32_t i = 0; i < n_islands; ++i) {
+            const size_t first = v_isl_body.size();
+            for (uint32_t e = v_isl_off[i]; e < v_isl_off[i + 1]; ++e) {
+                JointParams j = jp[v_isl_joint[e]];
+                for (uint32_t* s2 : {&j.a, &j.b}) {
+                    if (local[*s2] < 0) { local[*s2] = (int32_t)(v_isl_body.size() - first); v_isl_body.push_back(*s2); }
+                    *s2 = (uint32_t)local[*s2];
+                }
+                if (inter_ok) {
+                    const size_t idx = 2 * (((size_t)(i / JOINT_THREADS) * isl_max_joints + (e - v_isl_off[i])) * JOINT_THREADS + (i % JOINT_THREADS));
+                    float fa, fb;
+                    std::memcpy(&fa, &j.a, 4);
+                    std::memcpy(&fb, &j.b, 4);
+                    jinter[idx] = make_float4(fa, fb, j.aax, j.aay);
+                    jinter[idx + 1] = make_float4(j.abx, j.aby, j.distance, j.target);
+                }
+            }
+            for (size_t q = first; q < v_isl_body.size(); ++q) local[v_isl_body[q]] = -1;
+            isl_max_bodies = std::max<uint32_t>(isl_max_bodies, (uint32_t)(v_isl_body.size() - first));
+            v_isl_boff.push_back((uint32_t)v_isl_body.size());
+        }
+    }
+    joints_smem_ok = inter_ok && isl_max_bodies <= (uint32_t)JOINT_SMEM_MAX;
 
     // colliders: parent resolution
     r_max = 0.f;
@@ -698,6 +736,7 @@ int World::rebuild_topology() {
     CU(upload(sb_body, v_sb_body, stream)); CU(upload(sb_off, v_sb_off, stream)); CU(upload(sb_edge, v_sb_edge, stream));
     CU(upload(isl_off, v_isl_off, stream)); CU(upload(isl_joint, v_isl_joint, stream));
     CU(upload(d_springs, sp, stream)); CU(upload(d_joints, jp, stream));
+    CU(upload(d_joints_inter, jinter, stream)); CU(upload(isl_boff, v_isl_boff, stream)); CU(upload(isl_body, v_isl_body, stream));
     CU(cudaStreamSynchronize(stream));  // the staging vectors above are locals
     topo_dirty = false;
     bp_dirty = true;  // record words (flags, parents, masses) may have changed
@@ -862,7 +901,10 @@ int World::launch_substep(const SubstepParams& P) {
     R.count = d_rec_count;
     R.pairs = rec_pairs.d;
     R.vels = rec_vels.d;
-    const bool fused = (allow_fused && n_joints_live == 0 && rec_mode != BLOBS_RECORD_EVENTS) || strip_on;
+    // fused = bodies are advanced (verlet + snapshot + clamp + binning) by the kernel that last touches their position:
+    // k_main for free bodies, k_joints_fused for jointed ones. Needs event recording off (events read pre-update velocities of
+    // OTHER bodies) and, with joints, islands small enough for the shared-memory solver.
+    const bool fused = (allow_fused && rec_mode != BLOBS_RECORD_EVENTS && (n_joints_live == 0 || joints_smem_ok) && joint_iterations_ok()) || strip_on;
     const bool ordered = contact_mode == 0;
     last_fused = fused;
     const uint32_t nb = P.n_bodies, nc = P.n_colliders;
@@ -917,13 +959,31 @@ int World::launch_substep(const SubstepParams& P) {
         });
         if (rc) return rc;
     }
-    if (!fused) {
+    const size_t jsmem = (size_t)JOINT_THREADS * std::max<uint32_t>(isl_max_bodies, 1) * sizeof(float4);
+    if (fused) {
+        if (n_islands) {  // joint projection from shared memory, then a body-parallel (coalesced) verlet pass over the jointed bodies
+            rc = timed(KC_JOINTS, [&] {
+                k_joints_fused<false><<<cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
+                                                                                                         isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
+            });
+            if (rc) return rc;
+            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
+            if (rc) return rc;
+        }
+    } else {
         if (n_islands && joint_iterations) {
-            rc = timed(KC_JOINTS, [&] { k_joints<<<cdiv(n_islands, 128), 128, 0, stream>>>(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
+            if (joints_smem_ok) {
+                rc = timed(KC_JOINTS, [&] {
+                    k_joints_fused<false><<<cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
+                                                                                                             isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
+                });
+            } else {
+                rc = timed(KC_JOINTS, [&] { k_joints<<<cdiv(n_islands, 128), 128, 0, stream>>>(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
+            }
             if (rc) return rc;
         }
         if (nb) {
-            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d); });
+            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, 0u); });
             if (rc) return rc;
         }
     }

@@ -292,6 +292,12 @@ class World {
     DevBuf<uint32_t> mb_body, mb_off, mb_cols, sb_body, sb_off, sb_edge, isl_off, isl_joint;
     DevBuf<SpringParams> d_springs;
     DevBuf<JointParams> d_joints;
+    DevBuf<float4> d_joints_inter;        // per-CTA interleaved joint records with island-local body indices (k_joints_fused)
+    uint32_t isl_max_joints = 0;
+    DevBuf<uint32_t> isl_boff, isl_body;
+    uint32_t isl_max_bodies = 0;
+    bool joints_smem_ok = false;
+    bool joint_iterations_ok() const { return true; }
 
     // broadphase
     GridDesc grid{1, 1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};

@@ -60,9 +60,31 @@ def build(world, scene):
         world.set_param(A.PARAM_CELL_SIZE, scene.cell_size)
     bh = world.insert_bodies(scene.bodies)
     ch = world.insert_colliders(scene.colliders, bh[scene.col_parent]) if scene.n_colliders else np.zeros(0, np.uint64)
-    sh = [world.spring_insert(bh[a], bh[b], rest, k, c) for (a, b, rest, k, c) in scene.springs]
-    jh = [world.joint_insert(bh[a], bh[b]) for (a, b) in scene.joints]
+    sh, jh = _insert_links(world, scene, bh)
     return {"bodies": bh, "colliders": ch, "springs": sh, "joints": jh}
+
+
+def _insert_links(world, scene, bh):
+    """springs and joints of a Scene; uses the bulk entry points when the world has them (the CUDA world does)"""
+    springs, joints = scene.springs, scene.joints
+    if isinstance(springs, np.ndarray):   # structured: a, b, rest, k, c
+        if hasattr(world, "insert_springs") and len(springs):
+            sh = world.insert_springs(bh[springs["a"]], bh[springs["b"]], np.stack([springs["rest"], springs["k"], springs["c"]], axis=1))
+        else:
+            sh = [world.spring_insert(bh[s["a"]], bh[s["b"]], float(s["rest"]), float(s["k"]), float(s["c"])) for s in springs]
+    else:
+        sh = [world.spring_insert(bh[a], bh[b], rest, k, c) for (a, b, rest, k, c) in springs]
+    if isinstance(joints, np.ndarray):    # (n, 2) body indices
+        if hasattr(world, "insert_joints") and len(joints):
+            jh = world.insert_joints(bh[joints[:, 0]], bh[joints[:, 1]])
+        else:
+            jh = [world.joint_insert(bh[a], bh[b]) for a, b in joints]
+    else:
+        jh = [world.joint_insert(bh[a], bh[b]) for (a, b) in joints]
+    return sh, jh
+
+
+SPRING_DTYPE = np.dtype([("a", "<i8"), ("b", "<i8"), ("rest", "<f4"), ("k", "<f4"), ("c", "<f4")])
 
 
 def _spheres(name, pos, radius, vel_req=None, gravity=(0.0, -30.0)):
@@ -153,8 +175,7 @@ def build_batch(world, scene_list):
         world.set_param(A.PARAM_BATCH_WORLD, w)
         bh = world.insert_bodies(sc.bodies)
         ch = world.insert_colliders(sc.colliders, bh[sc.col_parent]) if sc.n_colliders else np.zeros(0, np.uint64)
-        sh = [world.spring_insert(bh[a], bh[b], rest, k, c) for (a, b, rest, k, c) in sc.springs]
-        jh = [world.joint_insert(bh[a], bh[b]) for (a, b) in sc.joints]
+        sh, jh = _insert_links(world, sc, bh)
         out.append({"bodies": bh, "colliders": ch, "springs": sh, "joints": jh})
     world.set_param(A.PARAM_BATCH_WORLD, 0)
     return out
@@ -173,17 +194,20 @@ def cfg4(n_blobs=100_000, k=16, seed=1):
     jit = (uniform(seed, 7, n) - np.float32(0.5)) * np.float32(0.01)
     pos = np.stack([bx + np.float32(0.5) * np.cos(ang) + jit, by + np.float32(0.5) * np.sin(ang)], axis=1).astype(np.float32)
     s = _spheres(f"cfg4_{n_blobs}x{k}", pos, np.full(n, 0.1, dtype=np.float32))
-    s.constraints.append((0.0, 0.0, float(0.8 * side + 2.0)))
+    # roomy circle: contains the lattice corners (half-diagonal 1.13 * side), R = 400 at the full 317 x 316 lattice (SURVEY cfg4)
+    s.constraints.append((0.0, 0.0, float(1.26 * side + 2.0)))
     base = (blob * k).astype(np.int64)
     nxt = base + (j + 1) % k
-    s.joints = list(zip(np.arange(n, dtype=np.int64).tolist(), nxt.tolist()))
-    springs = []
+    s.joints = np.stack([np.arange(n, dtype=np.int64), nxt], axis=1)
+    parts = []
     for step in (2, k // 2):
         other = base + (j + step) % k
         a = np.arange(n, dtype=np.int64)
         keep = a < other if step == k // 2 else np.ones(n, dtype=bool)
         d = pos[other] - pos
         rest = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32)
-        springs += [(int(x), int(y), float(r), 1000.0, 50.0) for x, y, r in zip(a[keep], other[keep], rest[keep])]
-    s.springs = springs
+        sp = np.zeros(int(keep.sum()), dtype=SPRING_DTYPE)
+        sp["a"], sp["b"], sp["rest"], sp["k"], sp["c"] = a[keep], other[keep], rest[keep], 1000.0, 50.0
+        parts.append(sp)
+    s.springs = np.concatenate(parts)
     return s

@@ -124,6 +124,25 @@ class World:
         self._ck(self._lib.blobs_joint_insert(self._h, int(a), int(b), A.Vec2(*anchor_a), A.Vec2(*anchor_b), distance, C.byref(out)))
         return out.value
 
+    def insert_springs(self, a, b, params):
+        """bulk springs.insert: a, b handle arrays; params (n,3) = rest_length, stiffness, damping"""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        params = np.ascontiguousarray(params, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(len(a), dtype=np.uint64)
+        self._ck(self._lib.blobs_spring_insert_many(self._h, len(a), A.ptr(a), A.ptr(b), A.ptr(params), A.ptr(out)))
+        return out
+
+    def insert_joints(self, a, b, anchors=None, distance=None):
+        """bulk create_fixed_joint: anchors (n,4) or None; distance (n,) or None (= measured from current positions)"""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        anc = None if anchors is None else np.ascontiguousarray(anchors, dtype=np.float32).reshape(-1, 4)
+        dst = None if distance is None else np.ascontiguousarray(distance, dtype=np.float32)
+        out = np.zeros(len(a), dtype=np.uint64)
+        self._ck(self._lib.blobs_joint_insert_many(self._h, len(a), A.ptr(a), A.ptr(b), None if anc is None else A.ptr(anc), None if dst is None else A.ptr(dst), A.ptr(out)))
+        return out
+
     def joint_remove(self, h):
         self._ck(self._lib.blobs_joint_remove(self._h, int(h)))
 

@@ -203,6 +203,10 @@ int32_t blobs_spring_remove(BlobsWorld* w, BlobsHandle h);
 /* create_fixed_joint (physics.rs:184-207) when distance is NaN, else create_fixed_joint_with_distance (physics.rs:209-239) */
 int32_t blobs_joint_insert(BlobsWorld* w, BlobsHandle a, BlobsHandle b, BlobsVec2 anchor_a, BlobsVec2 anchor_b, float distance_or_nan, BlobsHandle* out);
 int32_t blobs_joint_remove(BlobsWorld* w, BlobsHandle h);
+/* bulk forms: n x springs.insert / n x create_fixed_joint(_with_distance); params = (rest_length, stiffness, damping) per spring,
+ * anchors = (anchor_a.xy, anchor_b.xy) per joint or NULL for zeros, distance_or_nan NULL = all NaN (distance from positions) */
+int32_t blobs_spring_insert_many(BlobsWorld* w, size_t n, const BlobsHandle* a, const BlobsHandle* b, const float* params3, BlobsHandle* out);
+int32_t blobs_joint_insert_many(BlobsWorld* w, size_t n, const BlobsHandle* a, const BlobsHandle* b, const float* anchors4, const float* distance_or_nan, BlobsHandle* out);
 int32_t blobs_constraint_push(BlobsWorld* w, BlobsVec2 position, float radius);                 /* physics.constraints.push(Constraint{..}) lib.rs:189-193 */
 int32_t blobs_constraint_clear(BlobsWorld* w);
 

@@ -197,12 +197,14 @@ def test_rotating_multi_collider_within_tolerance():
         np.testing.assert_allclose(cg["desc"]["absolute_transform"]["translation"][c_], co["desc"]["absolute_transform"]["translation"][c_], rtol=1e-5, atol=1e-6)
 
 
-def test_soft_blobs_springs_and_joints():
-    """cfg4 at 64 blobs x 16 bodies: springs (Jacobi) + fixed joints (per-island Gauss-Seidel in slot order) + contacts.
-    Positions stay bit-exact (anchors are not rotated, so rotation never feeds back into positions); rotation is
-    tolerance-checked because of atan2f."""
+@pytest.mark.parametrize("fused", [1, 0])
+def test_soft_blobs_springs_and_joints(fused):
+    """cfg4 at 64 blobs x 16 bodies: springs (Jacobi) + fixed joints (per-island Gauss-Seidel in slot order, island state in
+    shared memory) + contacts. Positions stay bit-exact (anchors are not rotated, so rotation never feeds back into positions);
+    rotation is tolerance-checked because of atan2f. fused=1: jointed bodies are advanced inside the joint kernel."""
     sc = S.cfg4(n_blobs=64, k=16, seed=3)
     g, o = _pair(sc.gravity, sc)
+    g.set_param(A.PARAM_FUSED, fused)
     g.record_contacts(A.RECORD_PAIRS, 1 << 20)
     for step in range(20):
         g.step(1 / 60)
@@ -211,10 +213,40 @@ def test_soft_blobs_springs_and_joints():
             assert np.array_equal(x, y)
         _compare_step(g, o)
     info = g.kernel_info()
-    assert info["n_islands"] == 64 and info["n_spring_bodies"] == 64 * 16 and info["fused_path"] == 0
+    assert info["n_islands"] == 64 and info["n_spring_bodies"] == 64 * 16 and info["fused_path"] == fused
     sg, _ = g.download_bodies()
     so, _ = o.download_bodies()
     np.testing.assert_allclose(sg["rotation"], so["rotation"], rtol=1e-5, atol=1e-6)
+
+
+def test_large_island_and_mixed_bodies():
+    """A 130-body chain (island too large for the shared-memory solver -> global-memory fallback, split pipeline), a 12-body
+    chain with a static anchor, free spheres and joint_iterations changed at run time, all in one world."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    ws = [blobs_b200.World(gravity=(0.0, -30.0)), oracle_py.OracleWorld(gravity=(0.0, -30.0), maintain_spatial_hash=False, record_events=False)]
+    for w in ws:
+        w.constraint_push((0.0, 0.0), 60.0)
+        long_chain = [sphere(w, (0.45 * i - 29.0, 5.0 + 0.05 * (i % 3)), r=0.2)[0] for i in range(130)]
+        for a, b in zip(long_chain[:-1], long_chain[1:]):
+            w.joint_insert(a, b)
+        anchor = sphere(w, (0.0, 12.0), r=0.3, body_type=A.BODY_STATIC)[0]
+        short = [sphere(w, (0.5 * (i + 1), 12.0), r=0.2)[0] for i in range(12)]
+        w.joint_insert(anchor, short[0], (0.1, 0.0), (0.0, 0.0))
+        for a, b in zip(short[:-1], short[1:]):
+            w.joint_insert(a, b, (0.0, 0.0), (0.0, 0.0), 0.55)
+        for i in range(60):
+            sphere(w, (-10.0 + 0.35 * i, 8.0 + 0.3 * (i % 4)), r=0.15, velocity_request=(0.5, -3.0))
+        w.step(1 / 60, n=4)
+        w.set_param(A.PARAM_JOINT_ITERATIONS, 2)
+        w.step(1 / 60, n=4)
+    _compare_step(ws[0], ws[1])
+    sg, _ = ws[0].download_bodies()
+    so, _ = ws[1].download_bodies()
+    np.testing.assert_allclose(sg["rotation"], so["rotation"], rtol=1e-5, atol=1e-6)
+    info = ws[0].kernel_info()
+    assert info["n_islands"] == 2 and info["fused_path"] == 0
 
 
 def test_removal_and_reinsert_mid_simulation():

@@ -71,6 +71,8 @@ int World::init() {
 World::~World() {
     if (stream) cudaStreamSynchronize(stream);
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    destroy_graph(gslot[0]);
+    destroy_graph(gslot[1]);
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     inertia.d.release(); binfo.d.release(); bmg.d.release(); bworld.d.release();
@@ -110,6 +112,7 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_CONTACT_MODE: contact_mode = (int)v; break;
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
         case BLOBS_PARAM_TUNE: tune = (int)v; break;
+        case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
         case BLOBS_PARAM_BATCH_WORLD:
             if (v < 0 || v >= 1048576.0) return fail(BLOBS_ERR_INVALID, "batch world id out of range");
             cur_world = (uint32_t)v;
@@ -136,6 +139,8 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_FUSED: *out = allow_fused; break;
         case BLOBS_PARAM_TUNE: *out = tune; break;
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
+        case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
+        case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
         default: return BLOBS_ERR_INVALID;
     }
     return BLOBS_OK;
@@ -854,7 +859,14 @@ int World::rebuild_broadphase() {
 template <class F>
 int World::timed(KClass k, F&& f) {
     EvPair* ep = nullptr;
-    if (profiling) {
+    EvPair cap{};
+    if (profiling && capturing) {
+        // inside a graph capture: timing events become external event-record nodes, re-recorded by every replay
+        CU(cudaEventCreate(&cap.a));
+        CU(cudaEventCreate(&cap.b));
+        cap.k = k;
+        CU(cudaEventRecordWithFlags(cap.a, stream, cudaEventRecordExternal));
+    } else if (profiling) {
         if (ev_used == ev_pool.size()) {
             EvPair p{};
             CU(cudaEventCreate(&p.a));
@@ -868,6 +880,10 @@ int World::timed(KClass k, F&& f) {
     f();
     launches++;
     if (ep) CU(cudaEventRecord(ep->b, stream));
+    if (profiling && capturing) {
+        CU(cudaEventRecordWithFlags(cap.b, stream, cudaEventRecordExternal));
+        cap_evs->push_back(cap);
+    }
     CU(cudaGetLastError());
     return BLOBS_OK;
 }
@@ -880,6 +896,88 @@ int World::collect_profile() {
         prof_launches[ev_pool[i].k]++;
     }
     ev_used = 0;
+    for (GraphSlot* g : graphs_launched) {
+        if (!g->profiled) continue;
+        for (const EvPair& e : g->evs) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e.a, e.b));
+            prof_ms[e.k] += ms;
+            prof_launches[e.k]++;
+        }
+    }
+    graphs_launched.clear();
+    return BLOBS_OK;
+}
+
+void World::destroy_graph(GraphSlot& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& e : g.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g.evs.clear();
+    g.exec = nullptr;
+    g.key = 0;
+}
+
+// Everything that is baked into the kernel arguments of one Physics::integrate call. If any of it changes the graph is
+// re-captured; body/collider DATA changes (staged writes, forces) do not invalidate it.
+uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+    };
+#define MIXV(v) { auto t__ = (v); mix(&t__, sizeof(t__)); }
+    MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
+    MIXV(allow_fused) MIXV(tune) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
+    MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
+    MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim)
+    const BodyArrays B = body_arrays();
+    const ColliderArrays C = col_arrays();
+    mix(&B, sizeof(B));
+    mix(&C, sizeof(C));
+    MIXV(hot_a.d) MIXV(hot_b.d) MIXV(tab_a.d) MIXV(tab_b.d) MIXV(tile_a.d) MIXV(tile_b.d) MIXV(d_constraints.d) MIXV(mb_body.d) MIXV(mb_off.d) MIXV(mb_cols.d)
+    MIXV(sb_body.d) MIXV(sb_off.d) MIXV(sb_edge.d) MIXV(d_springs.d) MIXV(isl_off.d) MIXV(isl_joint.d) MIXV(d_joints.d) MIXV(d_joints_inter.d)
+    MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3])
+#undef MIXV
+    return h ? h : 1;
+}
+
+// One Physics::integrate call: replay the captured graph when nothing structural changed, else (re)capture it.
+int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
+    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF) return integrate(nsub, delta, last);
+    const uint64_t key = step_key(nsub, delta, last);
+    GraphSlot& gs = gslot[last ? 1 : 0];
+    const float step_delta = delta / (float)nsub;
+    if (gs.exec && gs.key == key) {
+        CU(cudaGraphLaunch(gs.exec, stream));
+        // host-side effects of integrate()
+        if (any_dynamic) old_dt = step_delta;
+        if (nsub & 1u) cur_is_a = !cur_is_a;
+        launches += gs.launches;
+        graph_replays++;
+        graphs_launched.push_back(&gs);
+        return BLOBS_OK;
+    }
+    destroy_graph(gs);
+    const uint64_t l0 = launches;
+    capturing = true;
+    cap_evs = &gs.evs;
+    cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { capturing = false; return cuda_fail(e, "cudaStreamBeginCapture"); }
+    const int rc = integrate(nsub, delta, last);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(stream, &graph);
+    capturing = false;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&gs.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { gs.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+    gs.key = key;
+    gs.launches = launches - l0;
+    gs.profiled = profiling;
+    graph_captures++;
+    CU(cudaGraphLaunch(gs.exec, stream));
+    graphs_launched.push_back(&gs);
     return BLOBS_OK;
 }
 
@@ -919,7 +1017,7 @@ int World::launch_substep(const SubstepParams& P) {
     }
     if (nb) {
         rc = timed(KC_MAIN, [&] {
-            const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch, 1) : nb, 256);
+            const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
 #define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv)
 #define BLOBS_MAIN_VARIANT(BT, MB)                                   \
@@ -990,7 +1088,6 @@ int World::launch_substep(const SubstepParams& P) {
     rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
     if (rc) return rc;
     cur_is_a = !cur_is_a;
-    if (strip_on) olaunch = (uint32_t)std::min<size_t>((size_t)olaunch + 2 * (size_t)strip.mcap, olist.cap);  // arrivals are appended on the device
     if (rec_mode && sub_recorded < d_sub_end.cap) {
         CU(cudaMemcpyAsync(d_sub_end.d + sub_recorded, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
         sub_recorded++;
@@ -1032,6 +1129,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev_step0, ev_step1);
     if (profiling) { int rc = collect_profile(); if (rc) return rc; }
+    graphs_launched.clear();
     if (out) {
         out->collisions = h_stats->collisions;
         out->coincident_pairs = h_stats->coincident;
@@ -1064,11 +1162,17 @@ int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
     init.bb_max_x = init.bb_max_y = INT32_MIN;
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
-    if (strip_on) { rc = strip_rebuild_olist(); if (rc) return rc; }
+    if (strip_on) {
+        rc = strip_rebuild_olist();
+        if (rc) return rc;
+        // arrivals are appended on the device: bound the launch for the whole call, rounded so the captured graph stays valid
+        const size_t bound = (size_t)olaunch + 2 * (size_t)strip.mcap * substeps * n;
+        olaunch_dim = (uint32_t)std::min<size_t>((bound + 32767) / 32768 * 32768, olist.cap);
+    }
     CU(cudaEventRecord(ev_step0, stream));
     shadow_valid = false;
     for (uint32_t i = 0; i < n; ++i) {
-        rc = integrate(substeps, (float)delta, i + 1 == n);  // physics.rs:80
+        rc = run_step(substeps, (float)delta, i + 1 == n, !profiling || n == 1);  // physics.rs:80
         if (rc) return rc;
         time += delta;                           // physics.rs:81
     }
@@ -1086,7 +1190,12 @@ int World::fixed_step(double frame_time, BlobsStepStats* stats) {
     init.bb_max_x = init.bb_max_y = INT32_MIN;
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
-    if (strip_on) { rc = strip_rebuild_olist(); if (rc) return rc; }
+    if (strip_on) {
+        rc = strip_rebuild_olist();
+        if (rc) return rc;
+        const size_t bound = (size_t)olaunch + 2 * (size_t)strip.mcap * substeps * 3;
+        olaunch_dim = (uint32_t)std::min<size_t>((bound + 32767) / 32768 * 32768, olist.cap);
+    }
     CU(cudaEventRecord(ev_step0, stream));
     shadow_valid = false;
     accumulator += frame_time;
@@ -1094,7 +1203,7 @@ int World::fixed_step(double frame_time, BlobsStepStats* stats) {
     int max_steps = 3;
     uint32_t n = 0;
     while (accumulator >= delta && max_steps > 0) {
-        rc = integrate(substeps, (float)delta, max_steps == 1 || !(accumulator - delta >= delta));
+        rc = run_step(substeps, (float)delta, max_steps == 1 || !(accumulator - delta >= delta), !profiling);
         if (rc) return rc;
         accumulator -= delta;
         time += delta;
@@ -1401,6 +1510,7 @@ int World::strip_rebuild_olist() {
     CU(cudaMemcpyAsync(&cnt, d_ocount, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     olaunch = cnt;
+    olaunch_dim = olaunch;
     return BLOBS_OK;
 }
 
@@ -1465,7 +1575,7 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
         if (rc) return rc;
     }
     if (strip_on) {
-        rc = run(KC_SCATTER, [&] { k_scatter_owned<<<cdiv(std::max<uint32_t>(olaunch, 1), 256), 256, 0, stream>>>(B, C, tab_next, hot_next, olist.d, d_ocount); });
+        rc = run(KC_SCATTER, [&] { k_scatter_owned<<<cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream>>>(B, C, tab_next, hot_next, olist.d, d_ocount); });
         if (rc) return rc;
         rc = run(KC_GHOST, [&] {
             k_strip_finish<<<cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream>>>(B, C, strip, msg[0], msg[1], msg[2], msg[3], tab_next, gcell.d, hot_next,

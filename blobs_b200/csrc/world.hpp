@@ -210,6 +210,8 @@ class World {
     int rebuild_broadphase();
     int choose_grid(bool force);
     int integrate(uint32_t substeps, float delta, bool last_of_call);
+    int run_step(uint32_t substeps, float delta, bool last_of_call, bool allow_graph);
+    uint64_t step_key(uint32_t substeps, float delta, bool last_of_call);
     int launch_substep(const SubstepParams& P);
     int finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run);
     int ensure_shadow();
@@ -346,6 +348,15 @@ class World {
     uint64_t launches = 0;
     bool profiling = false;
     struct EvPair { cudaEvent_t a, b; int k; };
+    // one captured CUDA graph per (last-step-of-call?) flavour of Physics::integrate; replayed while its key matches
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t key = 0, launches = 0; std::vector<EvPair> evs; bool profiled = false; };
+    GraphSlot gslot[2];
+    bool graphs_on = true, capturing = false;
+    std::vector<EvPair>* cap_evs = nullptr;
+    std::vector<GraphSlot*> graphs_launched;
+    uint64_t graph_replays = 0, graph_captures = 0;
+    uint32_t olaunch_dim = 0;          // strip mode: launch bound, constant within a blobs_step* call
+    void destroy_graph(GraphSlot& g);
     std::vector<EvPair> ev_pool;
     size_t ev_used = 0;
     float prof_ms[KC_COUNT] = {0};

@@ -78,6 +78,9 @@ typedef enum BlobsParamId {
     BLOBS_PARAM_BATCH_WORLD = 14         /* batched independent worlds (BASELINE config #3): bodies inserted from now on belong to this
                                             world id; worlds never interact, each one behaves like its own Physics (gravity, constraints,
                                             substeps are shared). Default 0 = the single world. */
+    ,BLOBS_PARAM_GRAPH = 15              /* 1 (default): a whole Physics::integrate call is captured once as a CUDA graph and replayed while
+                                            nothing structural changes; 0: plain launches. Never changes results. */
+    ,BLOBS_PARAM_GRAPH_REPLAYS = 16      /* read-only: number of graph replays so far */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

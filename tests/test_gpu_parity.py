@@ -406,3 +406,36 @@ def test_batched_independent_worlds():
         so, _ = o.download_bodies()
         assert_bodies_bit_equal(sg[w * nb:(w + 1) * nb], so)
     assert sum(len(p) for p in pg) > 0
+
+
+def test_cuda_graph_replay_is_transparent():
+    """A whole Physics::integrate call is captured as a CUDA graph and replayed while nothing structural changes. Replays,
+    re-captures (dt change, insertion mid-run, profiling on/off) and plain launches must all give the same bits as the oracle."""
+    sc = S.cfg1(2)
+    g, o = _pair(sc.gravity, sc)
+    import blobs_b200
+
+    plain = blobs_b200.World(gravity=sc.gravity)
+    S.build(plain, sc)
+    plain.set_param(A.PARAM_GRAPH, 0)
+    for w in (g, o, plain):
+        w.step(1 / 60, n=6)          # graph: captured on the first step, replayed afterwards (two flavours: last / not last)
+        for _ in range(10):          # (the table may be re-dimensioned while the pile collapses: that re-captures too)
+            w.step(1 / 60)
+    assert g.get_param(A.PARAM_GRAPH_REPLAYS) >= 6 and plain.get_param(A.PARAM_GRAPH_REPLAYS) == 0
+    _compare_step(g, o)
+    g.profile_enable(True)
+    for w in (g, o, plain):
+        w.step(1 / 50)               # dt change -> re-capture (and Q2 ratio on the first dynamic body)
+        w.step(1 / 50)
+        sphere(w, (0.0, 7.0), r=0.1, velocity_request=(0.0, -5.0))   # topology change -> re-capture
+        w.step(1 / 50, n=3)
+        w.apply_forces(np.tile(np.array([[0.3, 0.1]], dtype=np.float32), (1025, 1)))   # data change only -> replay stays valid
+        w.step(1 / 50)
+    prof = g.profile_read()
+    assert prof["main"][1] >= 8 * 3 and prof["main"][0] > 0.0
+    g.profile_enable(False)
+    _compare_step(g, o)
+    sp, _ = plain.download_bodies()
+    so, _ = o.download_bodies()
+    assert_bodies_bit_equal(sp, so)

@@ -237,7 +237,7 @@ def run_ours(args):
         edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
         uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
         dist.broadcast(uid, 0)
-        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=8 * ny, migrate_capacity=ny // 2)
+        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=4 * ny, migrate_capacity=ny // 4)
         n = int(w.strip_owned().sum())
         nb = sc.n_bodies
         del sc
@@ -252,6 +252,8 @@ def run_ours(args):
         nb = sc.n_bodies
     if args.tune:
         w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
+    if os.environ.get("BLOBS_BENCH_GRAPH", "1") == "0":
+        w.set_param(blobs_b200.abi.PARAM_GRAPH, 0)
 
     def barrier():
         if dist is not None:

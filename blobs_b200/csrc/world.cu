@@ -943,7 +943,9 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
 
 // One Physics::integrate call: replay the captured graph when nothing structural changed, else (re)capture it.
 int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
-    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF) return integrate(nsub, delta, last);
+    // measured on 2x B200: replaying a graph that contains the grouped ncclSend/ncclRecv is ~25 % SLOWER than plain launches,
+    // so strip mode keeps plain launches
+    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || strip_on) return integrate(nsub, delta, last);
     const uint64_t key = step_key(nsub, delta, last);
     GraphSlot& gs = gslot[last ? 1 : 0];
     const float step_delta = delta / (float)nsub;

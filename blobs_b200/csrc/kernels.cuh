@@ -1155,7 +1155,11 @@ __global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc 
     const void* msg = side ? recv_r : recv_l;
     if ((side ? S.has_right : S.has_left) == 0) return;
     const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
-    if (j == 0 && h->overflow) atomicOr(&stats->nan_flag, 4u);
+    if (j == 0) {
+        if (h->overflow) atomicOr(&stats->nan_flag, 4u);
+        atomicMax(&stats->max_ghosts, h->n_ghost);
+        atomicMax(&stats->max_migrants, h->n_mig);
+    }
     if (j >= min(h->n_ghost, S.gcap)) return;
     const float4 hot = strip_ghosts(const_cast<void*>(msg))[j];
     const uint32_t cell = cell_index(g, bin_coord(hot.x, g.inv_cell), bin_coord(hot.y, g.inv_cell));

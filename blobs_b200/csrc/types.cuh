@@ -66,7 +66,7 @@ struct DeviceStats {       // accumulated per blobs_step* call, read back once
     unsigned int nan_flag;
     unsigned int list_overflow;
     int bb_min_x, bb_min_y, bb_max_x, bb_max_y;   // bbox of collider snapshot cells (k_bbox)
-    unsigned int pad[2];
+    unsigned int max_ghosts, max_migrants;        // strip mode: largest message sections received in this call
 };
 
 struct SubstepParams {

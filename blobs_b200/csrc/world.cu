@@ -69,7 +69,8 @@ int World::init() {
 }
 
 World::~World() {
-    if (stream) cudaStreamSynchronize(stream);
+    // strip mode: the stream may be parked inside a collective whose peer is gone — never block process exit on it
+    if (stream && !strip_on) cudaStreamSynchronize(stream);
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     destroy_graph(gslot[0]);
     destroy_graph(gslot[1]);
@@ -141,6 +142,8 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
         case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
+        case BLOBS_PARAM_STRIP_MAX_GHOSTS: *out = last_max_ghosts; break;
+        case BLOBS_PARAM_STRIP_MAX_MIGRANTS: *out = last_max_migrants; break;
         default: return BLOBS_ERR_INVALID;
     }
     return BLOBS_OK;
@@ -1132,6 +1135,8 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     cudaEventElapsedTime(&ms, ev_step0, ev_step1);
     if (profiling) { int rc = collect_profile(); if (rc) return rc; }
     graphs_launched.clear();
+    last_max_ghosts = std::max(last_max_ghosts, h_stats->max_ghosts);
+    last_max_migrants = std::max(last_max_migrants, h_stats->max_migrants);
     if (out) {
         out->collisions = h_stats->collisions;
         out->coincident_pairs = h_stats->coincident;

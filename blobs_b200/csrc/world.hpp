@@ -341,6 +341,7 @@ class World {
     size_t msg_bytes = 0;
     void* nccl_comm = nullptr;
     uint64_t nccl_exchanges = 0;
+    uint32_t last_max_ghosts = 0, last_max_migrants = 0;
     int strip_exchange();
     int strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch);
 

@@ -81,6 +81,8 @@ typedef enum BlobsParamId {
     ,BLOBS_PARAM_GRAPH = 15              /* 1 (default): a whole Physics::integrate call is captured once as a CUDA graph and replayed while
                                             nothing structural changes; 0: plain launches. Never changes results. */
     ,BLOBS_PARAM_GRAPH_REPLAYS = 16      /* read-only: number of graph replays so far */
+    ,BLOBS_PARAM_STRIP_MAX_GHOSTS = 17   /* read-only: largest ghost / migrant section received from a neighbour so far (strip mode); */
+    ,BLOBS_PARAM_STRIP_MAX_MIGRANTS = 18 /*            size the capacities of blobs_strip_configure from these */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

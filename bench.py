@@ -19,6 +19,8 @@ import sys
 import tempfile
 import time
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version banner to stdout otherwise)
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
@@ -237,7 +239,7 @@ def run_ours(args):
         edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
         uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
         dist.broadcast(uid, 0)
-        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=8 * ny, migrate_capacity=ny // 2)
+        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=4 * ny, migrate_capacity=2 * ny)   # bounds: the band next to an edge holds ~1-2 lattice columns (ny rows each)
         n = int(w.strip_owned().sum())
         nb = sc.n_bodies
         del sc

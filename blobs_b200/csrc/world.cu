@@ -114,6 +114,8 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
         case BLOBS_PARAM_TUNE: tune = (int)v; break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
+        case BLOBS_PARAM_STRIP_MAX_GHOSTS: last_max_ghosts = (uint32_t)v; break;      // reset
+        case BLOBS_PARAM_STRIP_MAX_MIGRANTS: last_max_migrants = (uint32_t)v; break;  // reset
         case BLOBS_PARAM_BATCH_WORLD:
             if (v < 0 || v >= 1048576.0) return fail(BLOBS_ERR_INVALID, "batch world id out of range");
             cur_world = (uint32_t)v;

@@ -1009,7 +1009,7 @@ int World::launch_substep(const SubstepParams& P) {
     // fused = bodies are advanced (verlet + snapshot + clamp + binning) by the kernel that last touches their position:
     // k_main for free bodies, k_joints_fused for jointed ones. Needs event recording off (events read pre-update velocities of
     // OTHER bodies) and, with joints, islands small enough for the shared-memory solver.
-    const bool fused = (allow_fused && rec_mode != BLOBS_RECORD_EVENTS && (n_joints_live == 0 || joints_smem_ok) && joint_iterations_ok()) || strip_on;
+    const bool fused = (allow_fused && rec_mode != BLOBS_RECORD_EVENTS && (n_joints_live == 0 || joints_smem_ok)) || strip_on;
     const bool ordered = contact_mode == 0;
     last_fused = fused;
     const uint32_t nb = P.n_bodies, nc = P.n_colliders;

@@ -299,7 +299,6 @@ class World {
     DevBuf<uint32_t> isl_boff, isl_body;
     uint32_t isl_max_bodies = 0;
     bool joints_smem_ok = false;
-    bool joint_iterations_ok() const { return true; }
 
     // broadphase
     GridDesc grid{1, 1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};

@@ -256,6 +256,8 @@ def run_ours(args):
         w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
     if os.environ.get("BLOBS_BENCH_GRAPH", "1") == "0":
         w.set_param(blobs_b200.abi.PARAM_GRAPH, 0)
+    if "BLOBS_BENCH_CROWDED" in os.environ:   # A/B aid: 0 inline, 1 always k_crowded, 2 auto (library default)
+        w.set_param(blobs_b200.abi.PARAM_CROWDED, int(os.environ["BLOBS_BENCH_CROWDED"]))
 
     def barrier():
         if dist is not None:
@@ -343,6 +345,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         main_ms, main_n = prof["main"]
+        main_ms += prof["crowded"][0]   # k_crowded finishes the bodies k_main deferred: same algorithmic bytes, so same bucket
         substeps = int(w.get_param(blobs_b200.abi.PARAM_SUBSTEPS))
         achieved = (B_MAIN * n / 1e9) / (main_ms / max(main_n, 1) / 1e3) if main_n else None
         value = n_total * K / (t_dev_ms / 1e3)
@@ -354,6 +357,8 @@ def run_ours(args):
                        "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
                        "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
                        "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow,
+                       "crowded_mode": int(w.get_param(blobs_b200.abi.PARAM_CROWDED)),
+                       "sim_time_s": [W * DT, (W + K) * DT],
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1])},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,

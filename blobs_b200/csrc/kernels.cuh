@@ -324,36 +324,41 @@ __device__ __forceinline__ void gather_single(const GridDesc& g, const Broadphas
     }
 }
 
-// Rare path when a body has more than LIST_CAP contributions: repeated selection of the next key in order
-// (k+1 neighbourhood scans, no storage). Everything by value so the callers keep their state in registers.
+// Rare path when a body has more than LIST_CAP contributions: windowed selection. Every pass re-scans the neighbourhood and
+// keeps the LIST_CAP smallest keys greater than the last one applied (bounded insertion), applies them in order and moves
+// the window on: ceil(k / LIST_CAP) scans for k contributions, same summation order as the reference. (The first version
+// selected ONE key per scan; in the dense shell that forms where the circle constraint projects bodies onto its boundary a
+// few bodies with hundreds of contacts then stalled the whole launch.) Everything by value so callers keep their state in
+// registers.
 __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase bp, const uint4* __restrict__ ccold, const SelfCol* cols, int ncols,
                                                         float px, float py) {
     bool have_last = false;
     unsigned long long last = 0;
     for (;;) {
-        bool found = false;
-        unsigned long long best = 0;
-        float bx = 0.f, by = 0.f;
+        ContactList<unsigned long long> win;
+        win.clear();
+        auto offer = [&](unsigned long long k, float x, float y) {
+            if (have_last && !(k > last)) return;
+            if (win.n == LIST_CAP) {
+                if (!(k < win.key[LIST_CAP - 1])) return;
+                win.n = LIST_CAP - 1;  // drop the largest to make room
+            }
+            win.insert(k, x, y);
+        };
         for (int ci = 0; ci < ncols; ++ci) {
             const SelfCol s = cols[ci];
             for_each_candidate(g, bp, ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
-                if (c.coincident) {
-                    const unsigned long long k = pair_key<unsigned long long>(s.slot, c.other, true);
-                    if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.i_am_a ? 0.01f : -0.01f; by = 0.f; }
-                }
-                if (c.push) {
-                    const unsigned long long k = pair_key<unsigned long long>(s.slot, c.other, false);
-                    if ((!have_last || k > last) && (!found || k < best)) { found = true; best = k; bx = c.cx; by = c.cy; }
-                }
+                if (c.coincident) offer(pair_key<unsigned long long>(s.slot, c.other, true), c.i_am_a ? 0.01f : -0.01f, 0.f);
+                if (c.push) offer(pair_key<unsigned long long>(s.slot, c.other, false), c.cx, c.cy);
             });
         }
-        if (!found) break;
-        px = fadd(px, bx);
-        py = fadd(py, by);
-        last = best;
+        if (win.n == 0) break;
+        for (int i = 0; i < win.n; ++i) { px = fadd(px, win.cx[i]); py = fadd(py, win.cy[i]); }
+        last = win.key[win.n - 1];
         have_last = true;
+        if (win.n < LIST_CAP) break;
     }
     return make_float2(px, py);
 }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
     const uint32_t flags = info.x;
     const int32_t col = (int32_t)info.y;
     if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
-        bool active_col = false;
+        bool active_col = false, deferred = false;
         if (col >= 0) {
             const uint32_t c = (uint32_t)col;
             if (c != cs) {  // speculation missed: fetch the real collider
@@ -551,8 +556,13 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
                         for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
                     } else {
                         n_over = 1;
-                        SelfCol s2 = s;  // stack copy only on this rare path
-                        p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
+                        if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
+                            P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
+                            deferred = true;
+                        } else {
+                            SelfCol s2 = s;  // stack copy only on this rare path
+                            p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
+                        }
                     }
                 } else {
                     p.x = fadd(p.x, out.fx);
@@ -560,7 +570,9 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
                 }
             }
         }
-        if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
+        if (deferred) {
+            // nothing: every array of this body is left untouched for k_crowded
+        } else if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
             if (active_col) {
@@ -595,6 +607,36 @@ __device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArr
     return true;
 }
 
+// Serial resolution of a multi-collider body with more than LIST_CAP contributions: order-preserving windowed rescan over
+// all colliders of the body; bodies with more than MULTI_MAX_INLINE colliders fall back to the unordered sum (counted in
+// list_overflow).
+__device__ __forceinline__ float2 multi_overflow_serial(const GridDesc& g, const Broadphase& bp, const BodyArrays& B, const ColliderArrays& Cc,
+                                                        uint32_t b, const uint32_t* __restrict__ mb_cols, uint32_t c0, uint32_t c1, float m,
+                                                        uint32_t wbase, float2 p) {
+    SelfCol cols[MULTI_MAX_INLINE];
+    int nc = 0;
+    bool fits = true;
+    for (uint32_t k = c0; k < c1; ++k) {
+        SelfCol s;
+        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
+        if (nc == MULTI_MAX_INLINE) { fits = false; break; }
+        cols[nc++] = s;
+    }
+    if (fits) return apply_contacts_rescan(g, bp, Cc.ccold, cols, nc, p.x, p.y);
+    float fx = 0.f, fy = 0.f;
+    for (uint32_t k = c0; k < c1; ++k) {
+        SelfCol s;
+        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
+        for_each_candidate(g, bp, Cc.ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) {
+            Contact c;
+            if (!narrowphase(s, o, c)) return;
+            if (c.coincident) fx = fadd(fx, c.i_am_a ? 0.01f : -0.01f);
+            if (c.push) { fx = fadd(fx, c.cx); fy = fadd(fy, c.cy); }
+        });
+    }
+    return make_float2(fadd(p.x, fx), fadd(p.y, fy));
+}
+
 template <bool FUSED, bool ORDERED>
 __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                                Broadphase bp, Recording rec, DeviceStats* stats, const uint32_t* __restrict__ mb_body,
@@ -615,6 +657,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
         const float2 acc0 = B.acc[b];
         const bool hv = B.has_vreq[b] != 0;
         const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
+        bool deferred = false;
         if (P.collisions_enabled) {
             ContactList<unsigned long long> list;
             list.clear();
@@ -628,35 +671,12 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                 if (!list.overflow) {
                     for (int j = 0; j < list.n; ++j) { p.x = fadd(p.x, list.cx[j]); p.y = fadd(p.y, list.cy[j]); }
                 } else {
-                    // more than LIST_CAP contributions: order-preserving rescan over all colliders of the body; bodies
-                    // with more than MULTI_MAX_INLINE colliders fall back to the unordered sum (counted in list_overflow)
                     n_over = 1;
-                    SelfCol cols[MULTI_MAX_INLINE];
-                    int nc = 0;
-                    bool fits = true;
-                    for (uint32_t k = c0; k < c1; ++k) {
-                        SelfCol s;
-                        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
-                        if (nc == MULTI_MAX_INLINE) { fits = false; break; }
-                        cols[nc++] = s;
-                    }
-                    if (fits) {
-                        p = apply_contacts_rescan(g, bp, Cc.ccold, cols, nc, p.x, p.y);
+                    if (P.crowded) {
+                        P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_MULTI_BIT | i;
+                        deferred = true;
                     } else {
-                        ContactList<unsigned long long> dummy;
-                        dummy.clear();
-                        GatherOut o2;
-                        o2.fx = o2.fy = 0.f;
-                        o2.n_pairs = o2.n_coinc = 0;
-                        Recording off = rec;
-                        off.mode = 0;
-                        for (uint32_t k = c0; k < c1; ++k) {
-                            SelfCol s;
-                            if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
-                            gather_generic<false, unsigned long long>(g, bp, Cc.ccold, s, dummy, o2, off, B.vel, stats);
-                        }
-                        p.x = fadd(p.x, o2.fx);
-                        p.y = fadd(p.y, o2.fy);
+                        p = multi_overflow_serial(g, bp, B, Cc, b, mb_cols, c0, c1, m, wbase, p);
                     }
                 }
             } else {
@@ -664,7 +684,9 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
                 p.y = fadd(p.y, out.fy);
             }
         }
-        if (FUSED && !(flags & BF_JOINTED)) {
+        if (deferred) {
+            // k_crowded finishes this body
+        } else if (FUSED && !(flags & BF_JOINTED)) {
             float sx, sy, rot;
             integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
             for (uint32_t k = c0; k < c1; ++k) {
@@ -681,6 +703,139 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
         warp_add_u64(&stats->coincident, out.n_coinc);
         unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
         if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-crowded: bodies whose ordered contact list overflowed in k_main / k_multi (more than LIST_CAP contributions), one WARP
+// per body. Such bodies appear where the circle constraint projects many bodies onto its boundary: a few hundred threads
+// with hundreds of contacts each would otherwise serialise the tail of k_main. The lanes walk the neighbourhood together
+// (lane-strided over each row span), drop their contributions into a shared-memory buffer, the warp sorts it by pair key
+// (bitonic) and every lane replays the sum in reference order; lane 0 then runs the same tail as k_main / k_multi
+// (verlet + snapshot + clamp + binning [+ strip packing]). Pair counting / recording already happened in the first pass.
+// More than CROWD_CAP contributions: lane 0 falls back to the serial windowed rescan.
+// over_count is double-buffered by substep parity: this launch consumes [parity] and clears [parity ^ 1] for the next substep.
+// ------------------------------------------------------------------------------------------------
+constexpr int CROWD_CAP = 1024;
+constexpr int CROWD_WARPS = 2;
+
+template <class F>
+__device__ __forceinline__ void warp_for_each_candidate(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, uint32_t wbase,
+                                                        float x, float y, float r, uint32_t lane, F&& f) {
+    const CellRange R = cell_range(g, x, y, r);
+    const uint32_t n1 = min(R.nx, g.W - R.c0);
+    for (uint32_t j = 0; j < R.ny; ++j) {
+        uint32_t row = R.r0 + j;
+        if (row >= g.H) row -= g.H;
+        const uint32_t base = wbase + row * g.W;
+        uint32_t lo = __ldg(bp.tab + base + R.c0), hi = __ldg(bp.tab + base + R.c0 + n1);
+        for (uint32_t k = lo + lane; k < hi; k += 32u) f(load_rec(bp, ccold, k));
+        if (n1 < R.nx) {
+            lo = __ldg(bp.tab + base);
+            hi = __ldg(bp.tab + base + (R.nx - n1));
+            for (uint32_t k = lo + lane; k < hi; k += 32u) f(load_rec(bp, ccold, k));
+        }
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                                              Broadphase bp, DeviceStats* stats, StripView sv,
+                                                              const uint32_t* __restrict__ mb_body, const uint32_t* __restrict__ mb_off,
+                                                              const uint32_t* __restrict__ mb_cols) {
+    __shared__ unsigned long long skey[CROWD_WARPS][CROWD_CAP];
+    __shared__ float scx[CROWD_WARPS][CROWD_CAP];
+    __shared__ float scy[CROWD_WARPS][CROWD_CAP];
+    __shared__ uint32_t scount[CROWD_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long* const key = skey[warp];
+    float* const cx = scx[warp];
+    float* const cy = scy[warp];
+    uint32_t* const cnt = &scount[warp];
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats->over_count[P.over_parity ^ 1u] = 0u;
+    const uint32_t n_over = min(*reinterpret_cast<volatile unsigned int*>(&stats->over_count[P.over_parity]), P.n_bodies);
+    for (uint32_t w = blockIdx.x * CROWD_WARPS + warp; w < n_over; w += gridDim.x * CROWD_WARPS) {
+        const uint32_t entry = P.over_list[w];
+        const bool multi = (entry & OVER_MULTI_BIT) != 0u;
+        const uint32_t idx = entry & ~OVER_MULTI_BIT;
+        const uint32_t b = multi ? mb_body[idx] : idx;
+        const uint2 info = B.binfo[b];
+        const uint32_t flags = info.x;
+        const float2 mg = B.bmg[b];
+        float2 p = B.pos[b];
+        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
+        const uint32_t c0 = multi ? mb_off[idx] : 0u, c1 = multi ? mb_off[idx + 1] : 1u;
+        if (lane == 0) *cnt = 0u;
+        __syncwarp();
+        for (uint32_t k = c0; k < c1; ++k) {
+            SelfCol s;
+            if (!load_self(B, Cc, b, multi ? mb_cols[k] : info.y, mg.x, wbase, s)) continue;
+            warp_for_each_candidate(g, bp, Cc.ccold, s.wbase, s.x, s.y, s.r, lane, [&](const Rec& o) {
+                Contact c;
+                if (!narrowphase(s, o, c)) return;
+                if (c.coincident) {
+                    const uint32_t i = atomicAdd(cnt, 1u);
+                    if (i < (uint32_t)CROWD_CAP) { key[i] = pair_key<unsigned long long>(s.slot, c.other, true); cx[i] = c.i_am_a ? 0.01f : -0.01f; cy[i] = 0.f; }
+                }
+                if (c.push) {
+                    const uint32_t i = atomicAdd(cnt, 1u);
+                    if (i < (uint32_t)CROWD_CAP) { key[i] = pair_key<unsigned long long>(s.slot, c.other, false); cx[i] = c.cx; cy[i] = c.cy; }
+                }
+            });
+        }
+        __syncwarp();
+        const uint32_t n = *cnt;
+        if (n <= (uint32_t)CROWD_CAP) {
+            uint32_t m = 2u;
+            while (m < n) m <<= 1;
+            for (uint32_t i = n + lane; i < m; i += 32u) key[i] = ~0ull;  // pads sort to the end (real keys are < 2^63)
+            __syncwarp();
+            for (uint32_t kk = 2u; kk <= m; kk <<= 1) {
+                for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
+                    for (uint32_t i = lane; i < m; i += 32u) {
+                        const uint32_t l = i ^ j;
+                        if (l > i) {
+                            const unsigned long long ka = key[i], kb = key[l];
+                            const bool up = (i & kk) == 0u;
+                            if ((ka > kb) == up) {
+                                key[i] = kb; key[l] = ka;
+                                const float xa = cx[i], ya = cy[i];
+                                cx[i] = cx[l]; cy[i] = cy[l];
+                                cx[l] = xa; cy[l] = ya;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (uint32_t i = 0; i < n; ++i) { p.x = fadd(p.x, cx[i]); p.y = fadd(p.y, cy[i]); }  // every lane, same order
+        } else if (lane == 0) {
+            if (multi) {
+                p = multi_overflow_serial(g, bp, B, Cc, b, mb_cols, c0, c1, mg.x, wbase, p);
+            } else {
+                SelfCol s;
+                if (load_self(B, Cc, b, info.y, mg.x, wbase, s)) p = apply_contacts_rescan(g, bp, Cc.ccold, &s, 1, p.x, p.y);
+            }
+        }
+        if (lane == 0) {
+            if (FUSED && !(flags & BF_JOINTED)) {
+                const float2 po = B.pos_old[b];
+                const float2 acc0 = B.acc[b];
+                const bool hv = B.has_vreq[b] != 0;
+                float sx, sy, rot;
+                integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+                for (uint32_t k = c0; k < c1; ++k) {
+                    const uint32_t c = multi ? mb_cols[k] : info.y;
+                    const uint4 cc = Cc.cconst[c];
+                    if (!(cc.y & CF_ACTIVE)) continue;
+                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cc.y, wbase, sx, sy, rot);
+                    if (!multi && sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, c, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
+                }
+            } else {
+                B.pos[b] = p;
+            }
+        }
+        __syncwarp();
     }
 }
 

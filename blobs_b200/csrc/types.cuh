@@ -23,6 +23,7 @@ enum : uint32_t {
     CF_COLD = 1u << 3,    // the record's cold half is NOT the default (m = 4r, groups = ALL, sole collider of its parent)
 };
 constexpr uint32_t NO_SLOT = 0xffffffffu;
+constexpr uint32_t OVER_MULTI_BIT = 0x80000000u;   // k_crowded list entry: index into the multi-collider body list
 // hot.w packing: collider slot | needs-cold << 30 | is_sensor << 31
 constexpr uint32_t HOT_SLOT_MASK = 0x3fffffffu, HOT_COLD_BIT = 0x40000000u, HOT_SENSOR_BIT = 0x80000000u;
 __host__ __device__ inline uint32_t hot_word(uint32_t slot, uint32_t cflags) {
@@ -67,6 +68,7 @@ struct DeviceStats {       // accumulated per blobs_step* call, read back once
     unsigned int list_overflow;
     int bb_min_x, bb_min_y, bb_max_x, bb_max_y;   // bbox of collider snapshot cells (k_bbox)
     unsigned int max_ghosts, max_migrants;        // strip mode: largest message sections received in this call
+    unsigned int over_count[2];                   // crowded-body list lengths, double-buffered by substep parity (k_crowded)
 };
 
 struct SubstepParams {
@@ -77,6 +79,9 @@ struct SubstepParams {
     uint32_t n_bodies;              // body slots
     uint32_t n_colliders;           // collider slots
     uint32_t write_vel;             // materialise calculated_velocity this substep
+    uint32_t crowded;               // bodies whose contact list overflows are deferred to k_crowded (else resolved inline)
+    uint32_t over_parity;           // which DeviceStats::over_count entry this substep appends to
+    uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list
 };
 
 struct BodyArrays {

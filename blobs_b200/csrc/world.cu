@@ -83,7 +83,7 @@ World::~World() {
     d_pending.release(); d_pending_col.release();
     mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
     isl_off.release(); isl_joint.release(); d_joints_inter.release(); isl_boff.release(); isl_body.release(); d_springs.release(); d_joints.release();
-    hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release();
+    hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release(); over_list.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
     d_owned.release(); d_cowned.release(); gcell.release(); io_slots.release(); io_xy.release(); olist.release(); opos.release();
@@ -113,6 +113,7 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_CONTACT_MODE: contact_mode = (int)v; break;
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
         case BLOBS_PARAM_TUNE: tune = (int)v; break;
+        case BLOBS_PARAM_CROWDED: crowded_mode = (int)v; break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
         case BLOBS_PARAM_STRIP_MAX_GHOSTS: last_max_ghosts = (uint32_t)v; break;      // reset
         case BLOBS_PARAM_STRIP_MAX_MIGRANTS: last_max_migrants = (uint32_t)v; break;  // reset
@@ -141,6 +142,7 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_CONTACT_MODE: *out = contact_mode; break;
         case BLOBS_PARAM_FUSED: *out = allow_fused; break;
         case BLOBS_PARAM_TUNE: *out = tune; break;
+        case BLOBS_PARAM_CROWDED: *out = crowded_mode; break;
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
         case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
@@ -182,6 +184,7 @@ int World::ensure_capacity() {
     CU(pos.ensure(nb, stream)); CU(pos_old.ensure(nb, stream)); CU(acc.ensure(nb, stream)); CU(vel.ensure(nb, stream));
     CU(vreq.ensure(nb, stream)); CU(has_vreq.ensure(nb, stream)); CU(rot.ensure(nb, stream)); CU(angvel.ensure(nb, stream));
     CU(torque.ensure(nb, stream)); CU(cabs.ensure(nc, stream)); CU(ccell.ensure(nc, stream));
+    CU(over_list.ensure(nb, stream));
     return BLOBS_OK;
 }
 
@@ -932,7 +935,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     };
 #define MIXV(v) { auto t__ = (v); mix(&t__, sizeof(t__)); }
     MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
-    MIXV(allow_fused) MIXV(tune) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
+    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
     MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
     MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim)
     const BodyArrays B = body_arrays();
@@ -988,7 +991,13 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
     return BLOBS_OK;
 }
 
-int World::launch_substep(const SubstepParams& P) {
+int World::launch_substep(const SubstepParams& P_in) {
+    SubstepParams P = P_in;
+    // contact-list overflows: deferred to k_crowded (one warp per body) when such bodies are expected, else resolved inline
+    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && crowded_seen));
+    P.crowded = crowded ? 1u : 0u;
+    P.over_parity = cur_is_a ? 0u : 1u;
+    P.over_list = over_list.d;
     const BodyArrays B = body_arrays();
     const ColliderArrays C = col_arrays();
     const Constraints K = constraints_pod();
@@ -1061,6 +1070,14 @@ int World::launch_substep(const SubstepParams& P) {
                 if (ordered) k_multi<false, true><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
                 else k_multi<false, false><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
             }
+        });
+        if (rc) return rc;
+    }
+    if (crowded && nb) {
+        rc = timed(KC_CROWDED, [&] {
+            const StripView sv = strip_view();
+            if (fused) k_crowded<true><<<148 * 7, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
+            else k_crowded<false><<<148 * 7, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
         });
         if (rc) return rc;
     }
@@ -1149,6 +1166,10 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
         out->list_overflow = h_stats->list_overflow;
         out->gpu_ms = ms;
     }
+    // auto mode: keep k_crowded in the pipeline for a while after the last overflow (a flip re-captures the CUDA graph)
+    if (h_stats->list_overflow != 0) crowded_hold = 64;
+    else if (crowded_hold > 0) crowded_hold--;
+    crowded_seen = crowded_hold > 0;
     // table re-dimensioning: only when the snapshot outgrew (aliasing) or vastly undershoots the table
     if (h_stats->bb_min_x <= h_stats->bb_max_x) {
         const long long ex = (long long)h_stats->bb_max_x - h_stats->bb_min_x + 1, ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;

@@ -146,7 +146,7 @@ struct HCollider {
 struct HSpring { uint64_t a, b; float rest, k, c; };
 struct HJoint { uint64_t a, b; BlobsVec2 aa, ab; float distance, target; };
 
-enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_PACK, KC_GHOST, KC_NCCL, KC_COUNT };
+enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_PACK, KC_GHOST, KC_NCCL, KC_CROWDED, KC_COUNT };
 
 class World {
    public:
@@ -212,7 +212,7 @@ class World {
     int integrate(uint32_t substeps, float delta, bool last_of_call);
     int run_step(uint32_t substeps, float delta, bool last_of_call, bool allow_graph);
     uint64_t step_key(uint32_t substeps, float delta, bool last_of_call);
-    int launch_substep(const SubstepParams& P);
+    int launch_substep(const SubstepParams& P_in);
     int finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run);
     int ensure_shadow();
     void update_mass_and_inertia(uint32_t bslot);
@@ -242,6 +242,9 @@ class World {
     int contact_mode = 0;           // 0 ordered, 1 fast
     bool allow_fused = true;
     int tune = 0;                   // kernel-variant selector (benchmarking aid)
+    int crowded_mode = 2;           // BLOBS_PARAM_CROWDED: 0 inline, 1 always defer to k_crowded, 2 auto
+    bool crowded_seen = false;      // auto mode: a recent step call reported contact-list overflows
+    int crowded_hold = 0;           //            step calls left before auto mode drops k_crowded again
     std::vector<BlobsVec2> con_pos;
     std::vector<float> con_r;
     bool con_dirty = true;
@@ -303,6 +306,7 @@ class World {
     // broadphase
     GridDesc grid{1, 1, 1, 1, 1.0f, 1.0f, 0.f, 0ull, 0ull};
     DevBuf<float4> hot_a, hot_b;
+    DevBuf<uint32_t> over_list;        // bodies deferred to k_crowded this substep (capacity = body slots)
     DevBuf<uint32_t> tile_a, tile_b;   // per-scan-tile totals, paired with tab_a / tab_b
     DevBuf<uint32_t> tab_a, tab_b;
     bool cur_is_a = true;

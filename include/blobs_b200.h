@@ -83,6 +83,9 @@ typedef enum BlobsParamId {
     ,BLOBS_PARAM_GRAPH_REPLAYS = 16      /* read-only: number of graph replays so far */
     ,BLOBS_PARAM_STRIP_MAX_GHOSTS = 17   /* read-only: largest ghost / migrant section received from a neighbour so far (strip mode); */
     ,BLOBS_PARAM_STRIP_MAX_MIGRANTS = 18 /*            size the capacities of blobs_strip_configure from these */
+    ,BLOBS_PARAM_CROWDED = 19            /* bodies with more contacts than the in-register ordered list holds (24): 0 = resolved inline by
+                                            their own thread, 1 = deferred to a warp-per-body kernel, 2 (default) = automatic (deferred
+                                            once a step has seen such bodies). Never changes results. */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

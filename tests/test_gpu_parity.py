@@ -439,3 +439,63 @@ def test_cuda_graph_replay_is_transparent():
     sp, _ = plain.download_bodies()
     so, _ = o.download_bodies()
     assert_bodies_bit_equal(sp, so)
+
+
+@pytest.mark.parametrize("crowded", [0, 1, 2])
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("n_small", [30, 200, 1200])
+def test_contact_list_overflow_keeps_reference_order(n_small, fused, crowded):
+    """More contributions on one body than the 24-entry in-register list: the overflow paths (inline windowed rescan = 0,
+    warp-per-body k_crowded = 1, automatic = 2; n_small = 1200 also exceeds k_crowded's 1024-entry sort buffer) must still
+    apply them in the reference's pair-loop order (bit-exact), for the big sphere (slot in the middle of the range) and
+    for a multi-collider body."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    ws = [blobs_b200.World(gravity=(0.0, -10.0)), oracle_py.OracleWorld(gravity=(0.0, -10.0), maintain_spatial_hash=False, record_events=False)]
+    ws[0].set_param(A.PARAM_CROWDED, crowded)
+    ws[0].set_param(A.PARAM_FUSED, fused)
+    rng = np.random.default_rng(n_small)
+    ang = rng.uniform(0, 2 * np.pi, n_small)
+    rad = rng.uniform(0.2, 1.9, n_small)
+    for w in ws:
+        half = n_small // 2
+        for i in range(half):
+            sphere(w, (float(rad[i] * np.cos(ang[i])), float(rad[i] * np.sin(ang[i]))), r=0.1)
+        sphere(w, (0.0, 0.0), r=2.0)                               # overlaps every small sphere
+        for i in range(half, n_small):
+            sphere(w, (float(rad[i] * np.cos(ang[i])), float(rad[i] * np.sin(ang[i]))), r=0.1)
+        # a two-collider body sitting in the crowd as well
+        b = A.body_descs(1)
+        b["position"]["x"], b["position"]["y"] = 0.3, 0.2
+        b["position_old"] = b["position"]
+        bh = w.insert_bodies(b)
+        c = A.collider_descs(2)
+        c["radius"] = 1.5
+        c["offset"]["translation"]["x"] = [0.4, -0.4]
+        c["absolute_transform"]["translation"]["x"] = [0.7, -0.1]
+        c["absolute_transform"]["translation"]["y"] = [0.2, 0.2]
+        w.insert_colliders(c, bh[[0, 0]])
+    tot_over = 0
+    for _ in range(3):
+        st = ws[0].step(1 / 60)
+        ws[1].step(1 / 60)
+        tot_over += st["list_overflow"]
+        _compare_step(ws[0], ws[1])
+    assert tot_over > 0, "the scene must overflow the in-register list"
+
+
+@pytest.mark.parametrize("crowded", [0, 1, 2])
+def test_boundary_shell_vs_grid_oracle(crowded):
+    """A lattice block larger than its circle constraint: the clamp projects the corners onto the boundary, which gives a
+    dense shell where ~1000 bodies have more than 24 contacts (the regime cfg2 reaches once the block hits the wall)."""
+    sc = S.lattice_scene(96, 96, 1.05, (0.0, 0.0), 3, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=40.0, name="shell", cell_size=1.0)
+    g, o = _pair(sc.gravity, sc, grid_oracle=True)
+    g.set_param(A.PARAM_CROWDED, crowded)
+    tot_over = 0
+    for _ in range(6):
+        st = g.step(1 / 60)
+        o.step(1 / 60)
+        tot_over += st["list_overflow"]
+        _compare_step(g, o)
+    assert tot_over > 500

@@ -1,0 +1,48 @@
+"""Throughput of BASELINE config #2 as a function of SIMULATED time (one line per block of steps): the block falls
+freely (few contacts), reaches the circle constraint at ~1.9 s, gets compressed against it (dense contacts, bodies with
+more than 24 contributions) and settles. Usage: python profiles/trace_cfg2.py [total_steps] [block] [crowded_mode]
+Also used as the workload for the dense-regime ncu capture (env CAPTURE_STEPS=N: run N plain steps without CUDA graphs
+and exit)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import blobs_b200  # noqa: E402
+from blobs_b200 import _abi as A, scenes  # noqa: E402
+
+DT = 1.0 / 60.0
+
+
+def main():
+    total = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+    block = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    crowded = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    sc = scenes.cfg2(seed=1)
+    w = blobs_b200.World(gravity=sc.gravity)
+    scenes.build(w, sc)
+    w.set_param(A.PARAM_CROWDED, crowded)
+    cap = int(os.environ.get("CAPTURE_STEPS", "0"))
+    if cap:
+        w.set_param(A.PARAM_GRAPH, 0)
+        for _ in range(cap):
+            w.step(DT)
+        return
+    n = sc.n_bodies
+    done = 0
+    while done < total:
+        ms = 0.0
+        coll = over = 0
+        for _ in range(block):
+            st = w.step(DT)
+            ms += st["gpu_ms"]
+            coll += st["collisions"]
+            over += st["list_overflow"]
+        done += block
+        print(json.dumps({"steps": [done - block, done], "sim_time_s": round(done * DT, 3), "ms_per_step": ms / block,
+                          "sphere_steps_per_s": n * block / (ms / 1e3), "contacts_per_step": coll / block,
+                          "list_overflow_per_step": over / block, "grid": [w.kernel_info()["grid_w"], w.kernel_info()["grid_h"]]}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

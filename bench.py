@@ -256,6 +256,10 @@ def run_ours(args):
         w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
     if os.environ.get("BLOBS_BENCH_GRAPH", "1") == "0":
         w.set_param(blobs_b200.abi.PARAM_GRAPH, 0)
+    if "BLOBS_BENCH_POOL" in os.environ:      # A/B aid: 0 per-lane contact resolution, 1 warp-pooled, 2 auto (library default)
+        w.set_param(blobs_b200.abi.PARAM_POOL, int(os.environ["BLOBS_BENCH_POOL"]))
+    if "BLOBS_BENCH_POOL_MIN" in os.environ:
+        w.set_param(blobs_b200.abi.PARAM_POOL_MIN, int(os.environ["BLOBS_BENCH_POOL_MIN"]))
     if "BLOBS_BENCH_CROWDED" in os.environ:   # A/B aid: 0 inline, 1 always k_crowded, 2 auto (library default)
         w.set_param(blobs_b200.abi.PARAM_CROWDED, int(os.environ["BLOBS_BENCH_CROWDED"]))
 
@@ -357,7 +361,7 @@ def run_ours(args):
                        "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
                        "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
                        "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow,
-                       "crowded_mode": int(w.get_param(blobs_b200.abi.PARAM_CROWDED)),
+                       "crowded_mode": int(w.get_param(blobs_b200.abi.PARAM_CROWDED)), "pool_mode": int(w.get_param(blobs_b200.abi.PARAM_POOL)),
                        "sim_time_s": [W * DT, (W + K) * DT],
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1])},
             "clocks": clocks,

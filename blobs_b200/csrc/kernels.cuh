@@ -218,30 +218,35 @@ struct GatherOut {
     unsigned int n_pairs, n_coinc;
 };
 
+// Bookkeeping for one contact: the later slot reports the pair, once, as (a, b) (physics.rs:302-311).
+__device__ __forceinline__ void note_pair(const SelfCol& s, const Rec& o, const Contact& c, GatherOut& out, const Recording& rec,
+                                          const float2* __restrict__ vel, DeviceStats* stats) {
+    if (!c.i_am_a) return;
+    out.n_pairs++;
+    if (c.coincident) out.n_coinc++;
+    if (rec.mode) {
+        const unsigned long long idx = atomicAdd(rec.count, 1ull);
+        if (idx < rec.cap) {
+            rec.pairs[idx] = make_uint2(s.slot, c.other);
+            if (rec.mode == 2u) {
+                // calculated_velocity before this substep's update (physics.rs:288-289); event mode always runs the
+                // split pipeline, so vel[] is not being rewritten concurrently
+                const float2 va = vel[s.body], vb = vel[o.parent];  // event mode flags every record needs_cold, so parent is real
+                rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
+            }
+        } else {
+            atomicAdd(&stats->rec_dropped, 1ull);
+        }
+    }
+}
+
 // One confirmed candidate: narrowphase, bookkeeping, ordered insert (or fast-mode sum).
 template <bool ORDERED, class KEY>
 __device__ __forceinline__ void take_candidate(const SelfCol& s, const Rec& o, ContactList<KEY>& list, GatherOut& out,
                                                const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats) {
     Contact c;
     if (!narrowphase(s, o, c)) return;
-    if (c.i_am_a) {  // the later slot reports the pair, once, as (a, b) (physics.rs:302-311)
-        out.n_pairs++;
-        if (c.coincident) out.n_coinc++;
-        if (rec.mode) {
-            const unsigned long long idx = atomicAdd(rec.count, 1ull);
-            if (idx < rec.cap) {
-                rec.pairs[idx] = make_uint2(s.slot, c.other);
-                if (rec.mode == 2u) {
-                    // calculated_velocity before this substep's update (physics.rs:288-289); event mode always runs the
-                    // split pipeline, so vel[] is not being rewritten concurrently
-                    const float2 va = vel[s.body], vb = vel[o.parent];  // event mode flags every record needs_cold, so parent is real
-                    rec.vels[idx] = make_float4(va.x, va.y, vb.x, vb.y);
-                }
-            } else {
-                atomicAdd(&stats->rec_dropped, 1ull);
-            }
-        }
-    }
+    note_pair(s, o, c, out, rec, vel, stats);
     if (c.coincident) {
         const float px = c.i_am_a ? 0.01f : -0.01f;
         if (ORDERED) list.insert(pair_key<KEY>(s.slot, c.other, true), px, 0.0f);
@@ -361,6 +366,212 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
         if (win.n < LIST_CAP) break;
     }
     return make_float2(px, py);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-pooled contact resolution (k_main<POOLED>), for contact-rich states. The per-lane resolve loop of gather_single runs
+// at the pace of the lane with the most contacts (measured in the compressed cfg2 pile: 7 of 32 lanes active on average,
+// and the sorted-insert loop - local memory - is the top hotspot). Here the warp pools the prefilter survivors of all its
+// bodies in shared memory, the exact narrowphase runs one (body, candidate) PAIR per lane (full lanes, the owner's collider
+// is fetched by shuffle), and the ordering is a rank computation inside each owner's segment instead of a sorted insert:
+//   scan (per lane, as before, <= 64 candidates -> two 32-bit survivor masks) -> warp prefix sum -> survivor queue ->
+//   pooled narrowphase -> rank of every contribution among its owner's -> owner adds its contributions in rank order.
+// Same arithmetic, same summation order (ascending partner slot) as the list path. Bodies with more than 64 candidates or
+// a non-trivial cell range keep the per-lane path; an owner that meets a coincident pair (distance < 1e-6: two contributions
+// per pair) redoes its sum with the serial windowed rescan. Batches of at most POOL_Q survivors: a warp with more is
+// processed as several lane ranges.
+// ------------------------------------------------------------------------------------------------
+constexpr int POOL_Q = 256;
+constexpr uint32_t POOL_NONE = 0xffffffffu;
+
+struct PoolSmem {                 // per warp
+    uint32_t key[POOL_Q];         // record index, then the contribution key (POOL_NONE = contributes nothing)
+    float cx[POOL_Q], cy[POOL_Q];
+    uint16_t perm[POOL_Q];        // perm[segment start + rank] = entry
+    uint8_t owner[POOL_Q];        // lane that owns the entry
+    uint32_t nvalid[32];          // contributions per owner lane
+    uint32_t fb;                  // owner lanes that must fall back to the serial rescan
+};
+
+template <int BATCH>
+__device__ __forceinline__ uint32_t scan_chunk(const Broadphase& bp, const SelfCol& s, float srk, uint32_t base, uint32_t total, uint32_t n0,
+                                               uint32_t n01, uint32_t off0, uint32_t off1, uint32_t off2, uint32_t lo0) {
+    const uint32_t lim = min(32u, total - base);
+    uint32_t mask = 0;
+    for (uint32_t t0 = 0; t0 < lim; t0 += BATCH) {
+        float4 h[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const uint32_t t = base + t0 + i;
+            const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
+            h[i] = __ldg(bp.hot + (t0 + i < lim ? k : lo0));
+        }
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+            const uint32_t oslot = __float_as_uint(h[i].w) & HOT_SLOT_MASK;
+            const float dx = s.x - h[i].x, dy = s.y - h[i].y;
+            const float d2 = __fmaf_rn(dx, dx, dy * dy);
+            const float mdk = __fmaf_rn(h[i].z, 1.00005f, srk);
+            if (t0 + i < lim && oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << (t0 + i);
+        }
+    }
+    return mask;
+}
+
+// Must be called by all 32 lanes of the warp (valid = this lane has a collider to resolve). Returns true when the lane's
+// contributions were added to (px, py) here; false when they are in `list` (per-lane path), to be applied by the caller.
+template <int BATCH>
+__device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, bool valid, const SelfCol& s,
+                                            ContactList<uint32_t>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
+                                            DeviceStats* stats, PoolSmem& ps, uint32_t pool_min, float& px, float& py) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool fits = false;
+    uint32_t lo0 = 0, n0 = 0, n01 = 0, total = 0, off0 = 0, off1 = 0, off2 = 0;
+    if (valid) {
+        const CellRange R = cell_range(g, s.x, s.y, s.r);
+        if (!(R.ny > 3u || R.c0 + R.nx > g.W)) {
+            uint32_t lo[3], cnt[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint32_t row = R.r0 + j;
+                if (row >= g.H) row -= g.H;
+                const bool rv = (uint32_t)j < R.ny;
+                const uint32_t idx = s.wbase + (rv ? row * g.W + R.c0 : 0u);
+                const uint32_t a = __ldg(bp.tab + idx), b = __ldg(bp.tab + idx + (rv ? R.nx : 0u));
+                lo[j] = a;
+                cnt[j] = b - a;
+            }
+            n0 = cnt[0]; n01 = cnt[0] + cnt[1]; total = n01 + cnt[2];
+            off0 = lo[0]; off1 = lo[1] - n0; off2 = lo[2] - n01; lo0 = lo[0];
+            fits = total <= 64u;
+        }
+    }
+    const float srk = s.r * 1.00005f;
+    uint32_t m0 = 0, m1 = 0;
+    if (fits) {
+        if (total) m0 = scan_chunk<BATCH>(bp, s, srk, 0u, total, n0, n01, off0, off1, off2, lo0);
+        if (total > 32u) m1 = scan_chunk<BATCH>(bp, s, srk, 32u, total, n0, n01, off0, off1, off2, lo0);
+    }
+    const uint32_t c = (uint32_t)(__popc(m0) + __popc(m1));
+    const uint32_t T = __reduce_add_sync(FULL, c);
+    bool applied = false;
+    if (T >= pool_min) {   // warp-uniform
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        const uint32_t seg1g = incl, seg0g = incl - c;   // this lane's survivor range in the warp-wide sequence
+        const uint32_t sflag = s.slot | (s.sensor ? HOT_SENSOR_BIT : 0u);
+        ps.nvalid[lane] = 0u;
+        if (lane == 0) ps.fb = 0u;
+        uint32_t start = 0;
+        while (start < 32u) {   // lane ranges [start, end) whose survivors fit the queue
+            const uint32_t base = __shfl_sync(FULL, seg0g, start);
+            const bool in_batch = lane >= start && (seg1g - base) <= (uint32_t)POOL_Q;
+            const uint32_t bal = __ballot_sync(FULL, in_batch);
+            const uint32_t zeros = ~bal & (FULL << start);
+            const uint32_t end = zeros ? (uint32_t)__ffs(zeros) - 1u : 32u;   // > start: one lane never exceeds 64 <= POOL_Q
+            const bool mine = fits && lane >= start && lane < end;
+            const uint32_t Tb = __shfl_sync(FULL, seg1g, end - 1u) - base;
+            const uint32_t seg0 = seg0g - base;
+            __syncwarp();
+            if (mine) {
+                uint32_t w = seg0;
+                for (uint32_t m = m0; m; m &= m - 1u) {
+                    const uint32_t t = (uint32_t)__ffs(m) - 1u;
+                    ps.key[w] = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
+                    ps.owner[w] = (uint8_t)lane;
+                    ++w;
+                }
+                for (uint32_t m = m1; m; m &= m - 1u) {
+                    const uint32_t t = 32u + (uint32_t)__ffs(m) - 1u;
+                    ps.key[w] = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
+                    ps.owner[w] = (uint8_t)lane;
+                    ++w;
+                }
+            }
+            __syncwarp();
+            // exact narrowphase, one (owner, candidate) pair per lane
+            for (uint32_t i0 = 0; i0 < Tb; i0 += 32u) {
+                const uint32_t i = i0 + lane;
+                const bool act = i < Tb;
+                const uint32_t o = act ? (uint32_t)ps.owner[i] : lane;
+                SelfCol so;
+                so.x = __shfl_sync(FULL, s.x, o); so.y = __shfl_sync(FULL, s.y, o); so.r = __shfl_sync(FULL, s.r, o);
+                so.m = __shfl_sync(FULL, s.m, o); so.memb = __shfl_sync(FULL, s.memb, o); so.filt = __shfl_sync(FULL, s.filt, o);
+                so.body = __shfl_sync(FULL, s.body, o);
+                const uint32_t sf = __shfl_sync(FULL, sflag, o);
+                so.slot = sf & HOT_SLOT_MASK; so.sensor = (sf & HOT_SENSOR_BIT) != 0u; so.wbase = 0u;
+                if (act) {
+                    const Rec r = load_rec(bp, ccold, ps.key[i]);
+                    Contact ct;
+                    uint32_t key = POOL_NONE;
+                    if (narrowphase(so, r, ct)) {
+                        note_pair(so, r, ct, out, rec, vel, stats);
+                        if (ct.coincident) {
+                            atomicOr(&ps.fb, 1u << o);
+                        } else if (ct.push) {
+                            key = pair_key<uint32_t>(so.slot, ct.other, false);
+                            ps.cx[i] = ct.cx;
+                            ps.cy[i] = ct.cy;
+                            atomicAdd(&ps.nvalid[o], 1u);
+                        }
+                    }
+                    ps.key[i] = key;
+                }
+            }
+            __syncwarp();
+            // rank of every contribution inside its owner's segment
+            for (uint32_t i0 = 0; i0 < Tb; i0 += 32u) {
+                const uint32_t i = i0 + lane;
+                const bool act = i < Tb;
+                const uint32_t o = act ? (uint32_t)ps.owner[i] : lane;
+                const uint32_t a = __shfl_sync(FULL, seg0, o), b = __shfl_sync(FULL, seg0 + c, o);
+                if (act) {
+                    const uint32_t key = ps.key[i];
+                    if (key != POOL_NONE) {
+                        uint32_t rank = 0;
+                        for (uint32_t j = a; j < b; ++j) rank += ps.key[j] < key ? 1u : 0u;
+                        ps.perm[a + rank] = (uint16_t)i;
+                    }
+                }
+            }
+            __syncwarp();
+            if (mine) {
+                applied = true;
+                if (!((ps.fb >> lane) & 1u)) {
+                    const uint32_t nv = ps.nvalid[lane];
+                    for (uint32_t r = 0; r < nv; ++r) {
+                        const uint32_t e = ps.perm[seg0 + r];
+                        px = fadd(px, ps.cx[e]);
+                        py = fadd(py, ps.cy[e]);
+                    }
+                }
+            }
+            start = end;
+        }
+        __syncwarp();
+        if (applied && ((ps.fb >> lane) & 1u)) {   // coincident pair seen: exact serial path (pairs were already counted)
+            SelfCol s2 = s;
+            const float2 q = apply_contacts_rescan(g, bp, ccold, &s2, 1, px, py);
+            px = q.x;
+            py = q.y;
+        }
+    } else if (fits) {   // few survivors in the whole warp: per-lane resolve straight from the masks
+        for (uint32_t m = m0; m; m &= m - 1u) {
+            const uint32_t t = (uint32_t)__ffs(m) - 1u;
+            take_candidate<true, uint32_t>(s, load_rec(bp, ccold, t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), list, out, rec, vel, stats);
+        }
+        for (uint32_t m = m1; m; m &= m - 1u) {
+            const uint32_t t = 32u + (uint32_t)__ffs(m) - 1u;
+            take_candidate<true, uint32_t>(s, load_rec(bp, ccold, t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), list, out, rec, vel, stats);
+        }
+    }
+    if (valid && !fits) gather_single<true, uint32_t, BATCH>(g, bp, ccold, s, list, out, rec, vel, stats);
+    return applied;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,9 +711,10 @@ __device__ __forceinline__ void strip_pack_one(const BodyArrays& B, const Collid
 // round 2 = six cell-table entries; round 3 = hot record halves; round 4 = cold halves of prefilter survivors;
 // round 5 = the binning atomic.
 // ------------------------------------------------------------------------------------------------
-template <bool FUSED, bool ORDERED, int BATCH, int MINB>
+template <bool FUSED, bool ORDERED, int BATCH, int MINB, bool POOLED>
 __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                               Broadphase bp, Recording rec, DeviceStats* stats, StripView sv) {
+    __shared__ PoolSmem pool[POOLED ? 8 : 1];
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;
@@ -535,9 +747,62 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
     }
     const uint32_t flags = info.x;
     const int32_t col = (int32_t)info.y;
-    if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
-        bool active_col = false, deferred = false;
-        if (col >= 0) {
+    if (!POOLED) {   // per-lane contact resolution (the variant tuned for sparse contacts; kept textually as it was)
+        if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
+            bool active_col = false, deferred = false;
+            if (col >= 0) {
+                const uint32_t c = (uint32_t)col;
+                if (c != cs) {  // speculation missed: fetch the real collider
+                    cc = Cc.cconst[c];
+                    ab = Cc.cabs[c];
+                }
+                active_col = (cc.y & CF_ACTIVE) != 0u;
+                if (active_col && P.collisions_enabled) {
+                    SelfCol s;
+                    s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
+                    s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
+                    ContactList<uint32_t> list;
+                    list.clear();
+                    gather_single<ORDERED, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
+                    if (ORDERED) {
+                        if (!list.overflow) {
+                            for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
+                        } else {
+                            n_over = 1;
+                            if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
+                                P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
+                                deferred = true;
+                            } else {
+                                SelfCol s2 = s;  // stack copy only on this rare path
+                                p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
+                            }
+                        }
+                    } else {
+                        p.x = fadd(p.x, out.fx);
+                        p.y = fadd(p.y, out.fy);
+                    }
+                }
+            }
+            if (deferred) {
+                // nothing: every array of this body is left untouched for k_crowded
+            } else if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
+                float sx, sy, rot;
+                integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+                if (active_col) {
+                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+                    if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
+                }
+            } else {
+                B.pos[b] = p;
+            }
+        }
+    } else {
+        const bool do_body = inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER;
+        bool active_col = false, deferred = false, do_gather = false;
+        SelfCol s;
+        s.x = s.y = s.r = s.m = 0.f;
+        s.memb = s.filt = 0u; s.body = b; s.slot = 0u; s.wbase = wbase; s.sensor = false;
+        if (do_body && col >= 0) {
             const uint32_t c = (uint32_t)col;
             if (c != cs) {  // speculation missed: fetch the real collider
                 cc = Cc.cconst[c];
@@ -545,42 +810,54 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
             }
             active_col = (cc.y & CF_ACTIVE) != 0u;
             if (active_col && P.collisions_enabled) {
-                SelfCol s;
                 s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
                 s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
-                ContactList<uint32_t> list;
-                list.clear();
-                gather_single<ORDERED, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
-                if (ORDERED) {
-                    if (!list.overflow) {
-                        for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
-                    } else {
-                        n_over = 1;
-                        if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
-                            P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
-                            deferred = true;
-                        } else {
-                            SelfCol s2 = s;  // stack copy only on this rare path
-                            p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
-                        }
-                    }
-                } else {
-                    p.x = fadd(p.x, out.fx);
-                    p.y = fadd(p.y, out.fy);
-                }
+                do_gather = true;
             }
         }
-        if (deferred) {
-            // nothing: every array of this body is left untouched for k_crowded
-        } else if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
-            float sx, sy, rot;
-            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
-            if (active_col) {
-                const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
-                if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
+        if (ORDERED) {
+            ContactList<uint32_t> list;
+            list.clear();
+            bool applied = false;
+            if (POOLED) {   // warp-collective: every lane calls
+                applied = gather_warp<BATCH>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.pool_min, p.x, p.y);
+            } else if (do_gather) {
+                gather_single<true, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
-        } else {
-            B.pos[b] = p;
+            if (do_gather && !applied) {
+                if (!list.overflow) {
+                    for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
+                } else {
+                    n_over = 1;
+                    if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
+                        P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
+                        deferred = true;
+                    } else {
+                        SelfCol s2 = s;  // stack copy only on this rare path
+                        p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
+                    }
+                }
+            }
+        } else if (do_gather) {
+            ContactList<uint32_t> list;
+            list.clear();
+            gather_single<false, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
+            p.x = fadd(p.x, out.fx);
+            p.y = fadd(p.y, out.fy);
+        }
+        if (do_body) {
+            if (deferred) {
+                // nothing: every array of this body is left untouched for k_crowded
+            } else if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_joints_fused after the joint projection
+                float sx, sy, rot;
+                integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+                if (active_col) {
+                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+                    if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
+                }
+            } else {
+                B.pos[b] = p;
+            }
         }
     }
     warp_add_u64(&stats->collisions, out.n_pairs);

@@ -81,6 +81,7 @@ struct SubstepParams {
     uint32_t write_vel;             // materialise calculated_velocity this substep
     uint32_t crowded;               // bodies whose contact list overflows are deferred to k_crowded (else resolved inline)
     uint32_t over_parity;           // which DeviceStats::over_count entry this substep appends to
+    uint32_t pool_min;              // k_main<POOLED>: pool a warp's contact resolution when it has at least this many survivors
     uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list
 };
 

@@ -1,4 +1,5 @@
 // Host orchestration of the GPU-resident world. See world.hpp / kernels.cuh.
+#include <cstdlib>
 #include "world.hpp"
 #include "kernels.cuh"
 
@@ -32,6 +33,12 @@ World::World(const BlobsParams& p) : params(p) {
     gx = p.gravity.x;
     gy = p.gravity.y;
     use_spatial_hash = p.use_spatial_hash != 0;
+    // test aids: initial values of the execution knobs (none of them changes results), so that a whole test-suite run can be
+    // pushed through a non-default kernel path. Same meaning as the BLOBS_PARAM_* of the same name.
+    if (const char* e = std::getenv("BLOBS_B200_POOL")) pool_mode = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_POOL_MIN")) pool_min = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
 }
 
 int World::init() {
@@ -114,6 +121,8 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_FUSED: allow_fused = v != 0; break;
         case BLOBS_PARAM_TUNE: tune = (int)v; break;
         case BLOBS_PARAM_CROWDED: crowded_mode = (int)v; break;
+        case BLOBS_PARAM_POOL: pool_mode = (int)v; break;
+        case BLOBS_PARAM_POOL_MIN: pool_min = (uint32_t)v; break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
         case BLOBS_PARAM_STRIP_MAX_GHOSTS: last_max_ghosts = (uint32_t)v; break;      // reset
         case BLOBS_PARAM_STRIP_MAX_MIGRANTS: last_max_migrants = (uint32_t)v; break;  // reset
@@ -143,6 +152,8 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_FUSED: *out = allow_fused; break;
         case BLOBS_PARAM_TUNE: *out = tune; break;
         case BLOBS_PARAM_CROWDED: *out = crowded_mode; break;
+        case BLOBS_PARAM_POOL: *out = pool_mode; break;
+        case BLOBS_PARAM_POOL_MIN: *out = pool_min; break;
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
         case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
@@ -935,7 +946,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     };
 #define MIXV(v) { auto t__ = (v); mix(&t__, sizeof(t__)); }
     MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
-    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
+    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
     MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
     MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim)
     const BodyArrays B = body_arrays();
@@ -998,6 +1009,8 @@ int World::launch_substep(const SubstepParams& P_in) {
     P.crowded = crowded ? 1u : 0u;
     P.over_parity = cur_is_a ? 0u : 1u;
     P.over_list = over_list.d;
+    const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen));
+    P.pool_min = pool_min;
     const BodyArrays B = body_arrays();
     const ColliderArrays C = col_arrays();
     const Constraints K = constraints_pod();
@@ -1035,17 +1048,24 @@ int World::launch_substep(const SubstepParams& P_in) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
-#define BLOBS_LAUNCH_MAIN(F, O, BT, MB) k_main<F, O, BT, MB><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv)
-#define BLOBS_MAIN_VARIANT(BT, MB)                                   \
-    do {                                                             \
-        if (fused) {                                                 \
-            if (ordered) BLOBS_LAUNCH_MAIN(true, true, BT, MB);      \
-            else BLOBS_LAUNCH_MAIN(true, false, BT, MB);             \
-        } else {                                                     \
-            if (ordered) BLOBS_LAUNCH_MAIN(false, true, BT, MB);     \
-            else BLOBS_LAUNCH_MAIN(false, false, BT, MB);            \
-        }                                                            \
+#define BLOBS_LAUNCH_MAIN(F, O, BT, MB, PL) k_main<F, O, BT, MB, PL><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv)
+#define BLOBS_MAIN_VARIANT(BT, MB)                                          \
+    do {                                                                    \
+        if (fused) {                                                        \
+            if (ordered) BLOBS_LAUNCH_MAIN(true, true, BT, MB, false);      \
+            else BLOBS_LAUNCH_MAIN(true, false, BT, MB, false);             \
+        } else {                                                            \
+            if (ordered) BLOBS_LAUNCH_MAIN(false, true, BT, MB, false);     \
+            else BLOBS_LAUNCH_MAIN(false, false, BT, MB, false);            \
+        }                                                                   \
     } while (0)
+            if (pooled && tune == 0) {  // contact-rich state: warp-pooled resolution
+                if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 4, true);
+                else BLOBS_LAUNCH_MAIN(false, true, 4, 4, true);
+            } else if (pooled && tune == 8) {  // same with 85 registers per thread (3 CTAs per SM)
+                if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 3, true);
+                else BLOBS_LAUNCH_MAIN(false, true, 4, 3, true);
+            } else
             switch (tune) {
                 case 2: BLOBS_MAIN_VARIANT(8, 4); break;
                 case 3: BLOBS_MAIN_VARIANT(4, 5); break;
@@ -1170,6 +1190,10 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     if (h_stats->list_overflow != 0) crowded_hold = 64;
     else if (crowded_hold > 0) crowded_hold--;
     crowded_seen = crowded_hold > 0;
+    // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep
+    if (substeps_run && (double)h_stats->collisions >= 0.25 * (double)substeps_run * (double)std::max<size_t>(bodies.slots(), 1)) pool_hold = 64;
+    else if (pool_hold > 0) pool_hold--;
+    pool_seen = pool_hold > 0;
     // table re-dimensioning: only when the snapshot outgrew (aliasing) or vastly undershoots the table
     if (h_stats->bb_min_x <= h_stats->bb_max_x) {
         const long long ex = (long long)h_stats->bb_max_x - h_stats->bb_min_x + 1, ey = (long long)h_stats->bb_max_y - h_stats->bb_min_y + 1;

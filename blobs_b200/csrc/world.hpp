@@ -244,6 +244,10 @@ class World {
     int tune = 0;                   // kernel-variant selector (benchmarking aid)
     int crowded_mode = 2;           // BLOBS_PARAM_CROWDED: 0 inline, 1 always defer to k_crowded, 2 auto
     bool crowded_seen = false;      // auto mode: a recent step call reported contact-list overflows
+    int pool_mode = 2;              // BLOBS_PARAM_POOL: 0 per-lane contact resolution, 1 warp-pooled k_main, 2 auto (by contact density)
+    uint32_t pool_min = 16;         // BLOBS_PARAM_POOL_MIN: survivors per warp from which the pooled path is taken
+    bool pool_seen = false;
+    int pool_hold = 0;
     int crowded_hold = 0;           //            step calls left before auto mode drops k_crowded again
     std::vector<BlobsVec2> con_pos;
     std::vector<float> con_r;

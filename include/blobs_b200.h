@@ -86,6 +86,10 @@ typedef enum BlobsParamId {
     ,BLOBS_PARAM_CROWDED = 19            /* bodies with more contacts than the in-register ordered list holds (24): 0 = resolved inline by
                                             their own thread, 1 = deferred to a warp-per-body kernel, 2 (default) = automatic (deferred
                                             once a step has seen such bodies). Never changes results. */
+    ,BLOBS_PARAM_POOL = 20               /* contact resolution inside k_main: 0 = per lane, 1 = pooled across the warp (one body-candidate
+                                            pair per lane, rank-ordered sums; for contact-rich states), 2 (default) = automatic, by the
+                                            contact density of the previous step call. Never changes results. */
+    ,BLOBS_PARAM_POOL_MIN = 21           /* pooled path: minimum prefilter survivors in a warp (default 16) */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

@@ -419,12 +419,15 @@ __device__ __forceinline__ uint32_t scan_chunk(const Broadphase& bp, const SelfC
 }
 
 // Must be called by all 32 lanes of the warp (valid = this lane has a collider to resolve). Returns true when the lane's
-// contributions were added to (px, py) here; false when they are in `list` (per-lane path), to be applied by the caller.
+// contributions were added to (px, py) here; false when they are in `list` (per-lane path), to be applied by the caller -
+// unless `big` comes back set (only with defer_big): then nothing was done for this lane, not even pair counting.
 template <int BATCH>
 __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, bool valid, const SelfCol& s,
                                             ContactList<uint32_t>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
-                                            DeviceStats* stats, PoolSmem& ps, uint32_t pool_min, float& px, float& py) {
+                                            DeviceStats* stats, PoolSmem& ps, uint32_t pool_min, bool defer_big, bool& big, float& px,
+                                            float& py) {
     constexpr uint32_t FULL = 0xffffffffu;
+    big = false;
     const uint32_t lane = threadIdx.x & 31u;
     bool fits = false;
     uint32_t lo0 = 0, n0 = 0, n01 = 0, total = 0, off0 = 0, off1 = 0, off2 = 0;
@@ -570,7 +573,10 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
             take_candidate<true, uint32_t>(s, load_rec(bp, ccold, t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), list, out, rec, vel, stats);
         }
     }
-    if (valid && !fits) gather_single<true, uint32_t, BATCH>(g, bp, ccold, s, list, out, rec, vel, stats);
+    if (valid && !fits) {   // more than 64 candidates (or a wrapped / tall cell range)
+        if (defer_big) big = true;   // the caller hands the body to k_crowded: a warp-wide scan beats a per-lane one
+        else gather_single<true, uint32_t, BATCH>(g, bp, ccold, s, list, out, rec, vel, stats);
+    }
     return applied;
 }
 
@@ -818,13 +824,18 @@ __global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g,
         if (ORDERED) {
             ContactList<uint32_t> list;
             list.clear();
-            bool applied = false;
+            bool applied = false, big = false;
             if (POOLED) {   // warp-collective: every lane calls
-                applied = gather_warp<BATCH>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.pool_min, p.x, p.y);
+                applied = gather_warp<BATCH>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.pool_min,
+                                             P.crowded != 0u, big, p.x, p.y);
             } else if (do_gather) {
                 gather_single<true, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
-            if (do_gather && !applied) {
+            if (big) {   // k_crowded does the whole body, pair counting included
+                n_over = 1;
+                P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
+                deferred = true;
+            } else if (do_gather && !applied) {
                 if (!list.overflow) {
                     for (int i = 0; i < list.n; ++i) { p.x = fadd(p.x, list.cx[i]); p.y = fadd(p.y, list.cy[i]); }
                 } else {
@@ -990,10 +1001,11 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
 // (lane-strided over each row span), drop their contributions into a shared-memory buffer, the warp sorts it by pair key
 // (bitonic) and every lane replays the sum in reference order; lane 0 then runs the same tail as k_main / k_multi
 // (verlet + snapshot + clamp + binning [+ strip packing]). Pair counting / recording already happened in the first pass.
-// More than CROWD_CAP contributions: lane 0 falls back to the serial windowed rescan.
+// More than CROWD_CAP contributions: lane 0 falls back to the serial windowed rescan. The pooled k_main also sends bodies with
+// more than 64 candidates straight here (OVER_COUNT_BIT: their pairs are counted / recorded by this kernel).
 // over_count is double-buffered by substep parity: this launch consumes [parity] and clears [parity ^ 1] for the next substep.
 // ------------------------------------------------------------------------------------------------
-constexpr int CROWD_CAP = 1024;
+constexpr int CROWD_CAP = 512;
 constexpr int CROWD_WARPS = 2;
 
 template <class F>
@@ -1017,9 +1029,12 @@ __device__ __forceinline__ void warp_for_each_candidate(const GridDesc& g, const
 
 template <bool FUSED>
 __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                              Broadphase bp, DeviceStats* stats, StripView sv,
+                                                              Broadphase bp, Recording rec, DeviceStats* stats, StripView sv,
                                                               const uint32_t* __restrict__ mb_body, const uint32_t* __restrict__ mb_off,
                                                               const uint32_t* __restrict__ mb_cols) {
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
     __shared__ unsigned long long skey[CROWD_WARPS][CROWD_CAP];
     __shared__ float scx[CROWD_WARPS][CROWD_CAP];
     __shared__ float scy[CROWD_WARPS][CROWD_CAP];
@@ -1034,7 +1049,8 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
     for (uint32_t w = blockIdx.x * CROWD_WARPS + warp; w < n_over; w += gridDim.x * CROWD_WARPS) {
         const uint32_t entry = P.over_list[w];
         const bool multi = (entry & OVER_MULTI_BIT) != 0u;
-        const uint32_t idx = entry & ~OVER_MULTI_BIT;
+        const bool count = (entry & OVER_COUNT_BIT) != 0u;   // k_main skipped this body altogether: count / record its pairs here
+        const uint32_t idx = entry & ~(OVER_MULTI_BIT | OVER_COUNT_BIT);
         const uint32_t b = multi ? mb_body[idx] : idx;
         const uint2 info = B.binfo[b];
         const uint32_t flags = info.x;
@@ -1050,6 +1066,7 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
             warp_for_each_candidate(g, bp, Cc.ccold, s.wbase, s.x, s.y, s.r, lane, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
+                if (count) note_pair(s, o, c, out, rec, B.vel, stats);
                 if (c.coincident) {
                     const uint32_t i = atomicAdd(cnt, 1u);
                     if (i < (uint32_t)CROWD_CAP) { key[i] = pair_key<unsigned long long>(s.slot, c.other, true); cx[i] = c.i_am_a ? 0.01f : -0.01f; cy[i] = 0.f; }
@@ -1114,6 +1131,8 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
         }
         __syncwarp();
     }
+    warp_add_u64(&stats->collisions, out.n_pairs);
+    if (__any_sync(0xffffffffu, out.n_coinc)) warp_add_u64(&stats->coincident, out.n_coinc);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ enum : uint32_t {
 };
 constexpr uint32_t NO_SLOT = 0xffffffffu;
 constexpr uint32_t OVER_MULTI_BIT = 0x80000000u;   // k_crowded list entry: index into the multi-collider body list
+constexpr uint32_t OVER_COUNT_BIT = 0x40000000u;   // k_crowded list entry: pairs of this body were not counted / recorded yet
 // hot.w packing: collider slot | needs-cold << 30 | is_sensor << 31
 constexpr uint32_t HOT_SLOT_MASK = 0x3fffffffu, HOT_COLD_BIT = 0x40000000u, HOT_SENSOR_BIT = 0x80000000u;
 __host__ __device__ inline uint32_t hot_word(uint32_t slot, uint32_t cflags) {

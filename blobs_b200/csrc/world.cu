@@ -1005,11 +1005,12 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
 int World::launch_substep(const SubstepParams& P_in) {
     SubstepParams P = P_in;
     // contact-list overflows: deferred to k_crowded (one warp per body) when such bodies are expected, else resolved inline
-    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && crowded_seen));
+    const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen));
+    // (automatic mode: the pooled k_main hands its big-neighbourhood bodies to k_crowded, so the two come together)
+    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && (crowded_seen || pooled)));
     P.crowded = crowded ? 1u : 0u;
     P.over_parity = cur_is_a ? 0u : 1u;
     P.over_list = over_list.d;
-    const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen));
     P.pool_min = pool_min;
     const BodyArrays B = body_arrays();
     const ColliderArrays C = col_arrays();
@@ -1096,8 +1097,8 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (crowded && nb) {
         rc = timed(KC_CROWDED, [&] {
             const StripView sv = strip_view();
-            if (fused) k_crowded<true><<<148 * 7, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
-            else k_crowded<false><<<148 * 7, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
+            if (fused) k_crowded<true><<<148 * 12, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
+            else k_crowded<false><<<148 * 12, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
         });
         if (rc) return rc;
     }

@@ -476,13 +476,15 @@ def test_contact_list_overflow_keeps_reference_order(n_small, fused, crowded):
         c["absolute_transform"]["translation"]["x"] = [0.7, -0.1]
         c["absolute_transform"]["translation"]["y"] = [0.2, 0.2]
         w.insert_colliders(c, bh[[0, 0]])
-    tot_over = 0
+    tot_over = tot_col = 0
     for _ in range(3):
         st = ws[0].step(1 / 60)
         ws[1].step(1 / 60)
         tot_over += st["list_overflow"]
+        tot_col += st["collisions"]
         _compare_step(ws[0], ws[1])
     assert tot_over > 0, "the scene must overflow the in-register list"
+    assert tot_col == ws[1].step(1 / 60, n=0)["collisions"]   # every pair counted exactly once, whichever kernel resolved it
 
 
 @pytest.mark.parametrize("crowded", [0, 1, 2])
@@ -492,10 +494,16 @@ def test_boundary_shell_vs_grid_oracle(crowded):
     sc = S.lattice_scene(96, 96, 1.05, (0.0, 0.0), 3, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=40.0, name="shell", cell_size=1.0)
     g, o = _pair(sc.gravity, sc, grid_oracle=True)
     g.set_param(A.PARAM_CROWDED, crowded)
-    tot_over = 0
-    for _ in range(6):
+    g.record_contacts(A.RECORD_PAIRS, 1 << 22)
+    tot_over = tot_col = 0
+    for step in range(6):
         st = g.step(1 / 60)
         o.step(1 / 60)
         tot_over += st["list_overflow"]
+        tot_col += st["collisions"]
         _compare_step(g, o)
+        pg, po = g.pairs_drain(), o.pairs_drain()
+        for sub, (x, y) in enumerate(zip(pg, po)):
+            assert np.array_equal(x, y), f"pair set differs at step {step} substep {sub}: gpu {len(x)} oracle {len(y)}"
     assert tot_over > 500
+    assert tot_col == o.step(1 / 60, n=0)["collisions"]

@@ -1005,9 +1005,12 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
 int World::launch_substep(const SubstepParams& P_in) {
     SubstepParams P = P_in;
     // contact-list overflows: deferred to k_crowded (one warp per body) when such bodies are expected, else resolved inline
-    const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen));
+    // Automatic mode stays off in strip mode for now: the pooled / crowded kernels were validated on one GPU only (the 2-GPU
+    // parity test needs a 2-GPU box); forcing them (mode 1) works there too.
+    const bool auto_ok = !strip_on;
+    const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen && auto_ok));
     // (automatic mode: the pooled k_main hands its big-neighbourhood bodies to k_crowded, so the two come together)
-    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && (crowded_seen || pooled)));
+    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && (crowded_seen || pooled) && auto_ok));
     P.crowded = crowded ? 1u : 0u;
     P.over_parity = cur_is_a ? 0u : 1u;
     P.over_list = over_list.d;

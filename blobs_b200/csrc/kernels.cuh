@@ -383,6 +383,7 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
 // ------------------------------------------------------------------------------------------------
 constexpr int POOL_Q = 256;
 constexpr uint32_t POOL_NONE = 0xffffffffu;
+constexpr uint32_t POOL_BIG_MIN = 128u;   // candidates above which a body is handed to k_crowded without a per-lane scan
 
 struct PoolSmem {                 // per warp
     uint32_t key[POOL_Q];         // record index, then the contribution key (POOL_NONE = contributes nothing)
@@ -429,7 +430,7 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
     constexpr uint32_t FULL = 0xffffffffu;
     big = false;
     const uint32_t lane = threadIdx.x & 31u;
-    bool fits = false;
+    bool fits = false, ranged = false;   // ranged: plain 3-row range, `total` is known
     uint32_t lo0 = 0, n0 = 0, n01 = 0, total = 0, off0 = 0, off1 = 0, off2 = 0;
     if (valid) {
         const CellRange R = cell_range(g, s.x, s.y, s.r);
@@ -447,6 +448,7 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
             }
             n0 = cnt[0]; n01 = cnt[0] + cnt[1]; total = n01 + cnt[2];
             off0 = lo[0]; off1 = lo[1] - n0; off2 = lo[2] - n01; lo0 = lo[0];
+            ranged = true;
             fits = total <= 64u;
         }
     }
@@ -574,7 +576,10 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
         }
     }
     if (valid && !fits) {   // more than 64 candidates (or a wrapped / tall cell range)
-        if (defer_big) big = true;   // the caller hands the body to k_crowded: a warp-wide scan beats a per-lane one
+        // really big neighbourhoods (the boundary shell of cfg2: hundreds of candidates) go to k_crowded unscanned - a
+        // warp-wide scan beats a per-lane one; moderately big ones (cfg3's compressed piles: 65-128 candidates, few contacts)
+        // stay per-lane, where they measured faster
+        if (defer_big && !(ranged && total <= POOL_BIG_MIN)) big = true;
         else gather_single<true, uint32_t, BATCH>(g, bp, ccold, s, list, out, rec, vel, stats);
     }
     return applied;

@@ -1407,7 +1407,11 @@ __global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P,
                                                                 const uint32_t* __restrict__ isl_body, const uint32_t* __restrict__ mb_off,
                                                                 const uint32_t* __restrict__ mb_cols, uint32_t n_islands, uint32_t iterations,
                                                                 DeviceStats* stats) {
+#ifdef BLOBS_EMU   // host-compiled test build (tests/emu): dynamic shared memory comes from the fiber engine
+    float4* const sm = static_cast<float4*>(::emu::dynamic_smem());
+#else
     extern __shared__ float4 sm[];  // (pos.x, pos.y, rot, +-1/mass): a negative inverse mass marks a static body
+#endif
     const uint32_t t = threadIdx.x, T = JOINT_THREADS;
     const uint32_t i = blockIdx.x * T + t;
     if (i >= n_islands) return;

@@ -21,6 +21,21 @@ static void (*g_nccl_destroy)(void*) = nullptr;  // set once NCCL is loaded
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// Kernel launch. The indirection exists for the host-compiled test build of this file (tests/emu, -DBLOBS_EMU), where
+// `<<< >>>` is not C++; in the CUDA build it expands to the plain launch statement.
+#ifdef BLOBS_EMU
+#define BLOBS_LAUNCH(g, b, s, st, ...) ::emu::make_launch((g), (b), (s), __VA_ARGS__)
+#else
+#define BLOBS_LAUNCH(g, b, s, st, ...) __VA_ARGS__<<<(g), (b), (s), (st)>>>
+#endif
+
+// k_crowded runs a fixed grid whose warps stride over the list of deferred bodies (12 CTAs of 2 warps per SM)
+#ifdef BLOBS_EMU
+constexpr unsigned CROWD_GRID = 6;   // a fiber per thread: keep the empty CTAs few
+#else
+constexpr unsigned CROWD_GRID = 148 * 12;
+#endif
+
 static inline uint32_t h_slot(uint64_t h) { return (uint32_t)h; }
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 
@@ -39,6 +54,9 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_POOL_MIN")) pool_min = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
+#ifdef BLOBS_EMU
+    graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
+#endif
 }
 
 int World::init() {
@@ -207,7 +225,7 @@ int World::flush_writes() {
     if (!pending.empty()) {
         CU(d_pending.ensure(pending.size(), stream));
         CU(cudaMemcpyAsync(d_pending.d, pending.data(), pending.size() * sizeof(BodyWrite), cudaMemcpyHostToDevice, stream));
-        k_apply_body_writes<<<cdiv(pending.size(), 256), 256, 0, stream>>>(body_arrays(), d_pending.d, (uint32_t)pending.size());
+        BLOBS_LAUNCH(cdiv(pending.size(), 256), 256, 0, stream, k_apply_body_writes)(body_arrays(), d_pending.d, (uint32_t)pending.size());
         launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(stream));  // pending is pageable host memory
@@ -217,7 +235,7 @@ int World::flush_writes() {
     if (!pending_col.empty()) {
         CU(d_pending_col.ensure(pending_col.size(), stream));
         CU(cudaMemcpyAsync(d_pending_col.d, pending_col.data(), pending_col.size() * sizeof(ColWrite), cudaMemcpyHostToDevice, stream));
-        k_apply_col_writes<<<cdiv(pending_col.size(), 256), 256, 0, stream>>>(cabs.d, d_pending_col.d, (uint32_t)pending_col.size());
+        BLOBS_LAUNCH(cdiv(pending_col.size(), 256), 256, 0, stream, k_apply_col_writes)(cabs.d, d_pending_col.d, (uint32_t)pending_col.size());
         launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(stream));
@@ -807,7 +825,7 @@ int World::choose_grid(bool) {
     *h_stats = init;
     CU(cudaMemcpyAsync(d_stats, h_stats, sizeof(DeviceStats), cudaMemcpyHostToDevice, stream));
     if (nc) {
-        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), cs, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
+        BLOBS_LAUNCH(std::min(cdiv(nc, 256), 1184u), 256, 0, stream, k_bbox)(col_arrays(), cs, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
         launches++;
         CU(cudaGetLastError());
     }
@@ -861,7 +879,7 @@ int World::rebuild_broadphase() {
     uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
     if (nc) {
-        k_count<<<cdiv(nc, 256), 256, 0, stream>>>(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc, strip_on ? d_cowned.d : nullptr);
+        BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_count)(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc, strip_on ? d_cowned.d : nullptr);
         launches++;
     }
     {
@@ -1041,7 +1059,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     const uint32_t nb = P.n_bodies, nc = P.n_colliders;
     int rc;
     if (n_sb) {
-        rc = timed(KC_SPRINGS, [&] { k_springs<<<cdiv(n_sb, 128), 128, 0, stream>>>(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
+        rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
         if (rc) return rc;
     }
     if (strip_on) {
@@ -1052,7 +1070,7 @@ int World::launch_substep(const SubstepParams& P_in) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
-#define BLOBS_LAUNCH_MAIN(F, O, BT, MB, PL) k_main<F, O, BT, MB, PL><<<gdim, 256, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv)
+#define BLOBS_LAUNCH_MAIN(F, O, BT, MB, PL) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<F, O, BT, MB, PL>)(P, grid, K, B, C, bp, R, d_stats, sv)
 #define BLOBS_MAIN_VARIANT(BT, MB)                                          \
     do {                                                                    \
         if (fused) {                                                        \
@@ -1088,11 +1106,11 @@ int World::launch_substep(const SubstepParams& P_in) {
         rc = timed(KC_MAIN, [&] {
             const unsigned g = cdiv(n_multi, 128);
             if (fused) {
-                if (ordered) k_multi<true, true><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
-                else k_multi<true, false><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                if (ordered) BLOBS_LAUNCH(g, 128, 0, stream, k_multi<true, true>)(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                else BLOBS_LAUNCH(g, 128, 0, stream, k_multi<true, false>)(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
             } else {
-                if (ordered) k_multi<false, true><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
-                else k_multi<false, false><<<g, 128, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                if (ordered) BLOBS_LAUNCH(g, 128, 0, stream, k_multi<false, true>)(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
+                else BLOBS_LAUNCH(g, 128, 0, stream, k_multi<false, false>)(P, grid, K, B, C, bp, R, d_stats, mb_body.d, mb_off.d, mb_cols.d, n_multi);
             }
         });
         if (rc) return rc;
@@ -1100,8 +1118,8 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (crowded && nb) {
         rc = timed(KC_CROWDED, [&] {
             const StripView sv = strip_view();
-            if (fused) k_crowded<true><<<148 * 12, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
-            else k_crowded<false><<<148 * 12, 32 * CROWD_WARPS, 0, stream>>>(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
+            if (fused) BLOBS_LAUNCH(CROWD_GRID, 32 * CROWD_WARPS, 0, stream, k_crowded<true>)(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
+            else BLOBS_LAUNCH(CROWD_GRID, 32 * CROWD_WARPS, 0, stream, k_crowded<false>)(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
         });
         if (rc) return rc;
     }
@@ -1109,27 +1127,27 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (fused) {
         if (n_islands) {  // joint projection from shared memory, then a body-parallel (coalesced) verlet pass over the jointed bodies
             rc = timed(KC_JOINTS, [&] {
-                k_joints_fused<false><<<cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
+                BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused<false>)(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
                                                                                                          isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
             });
             if (rc) return rc;
-            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
+            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
             if (rc) return rc;
         }
     } else {
         if (n_islands && joint_iterations) {
             if (joints_smem_ok) {
                 rc = timed(KC_JOINTS, [&] {
-                    k_joints_fused<false><<<cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
+                    BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused<false>)(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
                                                                                                              isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
                 });
             } else {
-                rc = timed(KC_JOINTS, [&] { k_joints<<<cdiv(n_islands, 128), 128, 0, stream>>>(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
+                rc = timed(KC_JOINTS, [&] { BLOBS_LAUNCH(cdiv(n_islands, 128), 128, 0, stream, k_joints)(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
             }
             if (rc) return rc;
         }
         if (nb) {
-            rc = timed(KC_INTEGRATE, [&] { k_integrate<<<cdiv(nb, 256), 256, 0, stream>>>(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, 0u); });
+            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, 0u); });
             if (rc) return rc;
         }
     }
@@ -1167,7 +1185,7 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
 int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run) {
     const size_t nc = cols.slots();
     if (nc) {
-        k_bbox<<<std::min(cdiv(nc, 256), 1184u), 256, 0, stream>>>(col_arrays(), grid.cell, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
+        BLOBS_LAUNCH(std::min(cdiv(nc, 256), 1184u), 256, 0, stream, k_bbox)(col_arrays(), grid.cell, (uint32_t)nc, d_stats, strip_on ? d_cowned.d : nullptr);
         launches++;
     }
     CU(cudaEventRecord(ev_step1, stream));
@@ -1351,7 +1369,7 @@ int World::apply_forces(const float* f, size_t cap) {
     if (!n) return BLOBS_OK;
     CU(d_forces.ensure(n, stream));
     CU(cudaMemcpyAsync(d_forces.d, f, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
-    k_apply_forces<<<cdiv(n, 256), 256, 0, stream>>>(body_arrays(), d_forces.d, (uint32_t)n);
+    BLOBS_LAUNCH(cdiv(n, 256), 256, 0, stream, k_apply_forces)(body_arrays(), d_forces.d, (uint32_t)n);
     launches++;
     CU(cudaGetLastError());
     return BLOBS_OK;
@@ -1364,7 +1382,7 @@ int World::download_cell_coords(int32_t* cx, int32_t* cy, size_t cap) {
     if (!n) return BLOBS_OK;
     CU(d_cellx.ensure(n, stream));
     CU(d_celly.ensure(n, stream));
-    k_cell_coords<<<cdiv(n, 256), 256, 0, stream>>>(cabs.d, cell_size, (uint32_t)n, d_cellx.d, d_celly.d);
+    BLOBS_LAUNCH(cdiv(n, 256), 256, 0, stream, k_cell_coords)(cabs.d, cell_size, (uint32_t)n, d_cellx.d, d_celly.d);
     launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(cx, d_cellx.d, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1529,7 +1547,7 @@ int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const u
     CU(d_cowned.ensure(std::max<size_t>(nc, 1), stream));
     CU(cudaMemsetAsync(d_cowned.d, 0, d_cowned.cap, stream));
     if (nb) {
-        k_strip_init_owned<<<cdiv(nb, 256), 256, 0, stream>>>(body_arrays(), col_arrays(), strip, d_owned.d, d_cowned.d, (uint32_t)nb);
+        BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_strip_init_owned)(body_arrays(), col_arrays(), strip, d_owned.d, d_cowned.d, (uint32_t)nb);
         launches++;
         CU(cudaGetLastError());
     }
@@ -1560,7 +1578,7 @@ int World::strip_rebuild_olist() {
     const size_t nb = bodies.slots();
     CU(cudaMemsetAsync(d_ocount, 0, sizeof(uint32_t), stream));
     if (nb) {
-        k_strip_build_olist<<<cdiv(nb, 256), 256, 0, stream>>>(d_owned.d, (uint32_t)nb, olist.d, d_ocount, opos.d);
+        BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_strip_build_olist)(d_owned.d, (uint32_t)nb, olist.d, d_ocount, opos.d);
         launches++;
         CU(cudaGetLastError());
     }
@@ -1610,7 +1628,7 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
             CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
         }
         if (nc && !timed_launch) {  // inside a step the pack is fused into k_main's tail
-            rc = run(KC_PACK, [&] { k_strip_pack<<<cdiv(nc, 256), 256, 0, stream>>>(B, C, strip, d_cowned.d, msg[0], msg[1], nc); });
+            rc = run(KC_PACK, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_strip_pack)(B, C, strip, d_cowned.d, msg[0], msg[1], nc); });
             if (rc) return rc;
         }
         if (timed_launch && profiling) {
@@ -1623,20 +1641,20 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
             rc = strip_exchange();
             if (rc) return rc;
         }
-        rc = run(KC_GHOST, [&] { k_strip_bin_ghosts<<<cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream>>>(grid, strip, msg[2], msg[3], tab_next, tile_next, gcell.d, d_stats); });
+        rc = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_strip_bin_ghosts)(grid, strip, msg[2], msg[3], tab_next, tile_next, gcell.d, d_stats); });
         if (rc) return rc;
     }
-    rc = run(KC_SCAN, [&] { k_scan<<<cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream>>>(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur); });
+    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_scan)(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur); });
     if (rc) return rc;
     if (nc && !strip_on) {
-        rc = run(KC_SCATTER, [&] { k_scatter<<<cdiv(nc, 256), 256, 0, stream>>>(C, tab_next, hot_next, nc, nullptr); });
+        rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_scatter)(C, tab_next, hot_next, nc, nullptr); });
         if (rc) return rc;
     }
     if (strip_on) {
-        rc = run(KC_SCATTER, [&] { k_scatter_owned<<<cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream>>>(B, C, tab_next, hot_next, olist.d, d_ocount); });
+        rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_scatter_owned)(B, C, tab_next, hot_next, olist.d, d_ocount); });
         if (rc) return rc;
         rc = run(KC_GHOST, [&] {
-            k_strip_finish<<<cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream>>>(B, C, strip, msg[0], msg[1], msg[2], msg[3], tab_next, gcell.d, hot_next,
+            BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_strip_finish)(B, C, strip, msg[0], msg[1], msg[2], msg[3], tab_next, gcell.d, hot_next,
                                                                                                            d_owned.d, d_cowned.d, olist.d, d_ocount, opos.d, (uint32_t)olist.cap, d_stats);
         });
         if (rc) return rc;
@@ -1663,7 +1681,7 @@ int World::read_owned_positions(uint32_t* slots, float* xy, size_t cap, size_t* 
     CU(io_xy.ensure(std::max<size_t>(cap, 1), stream));
     CU(cudaMemsetAsync(d_io_count, 0, sizeof(unsigned int), stream));
     if (nb) {
-        k_compact_owned<<<cdiv(nb, 256), 256, 0, stream>>>(body_arrays(), strip_on ? d_owned.d : nullptr, (uint32_t)nb, (uint32_t)std::min<size_t>(cap, 0xffffffffu),
+        BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_compact_owned)(body_arrays(), strip_on ? d_owned.d : nullptr, (uint32_t)nb, (uint32_t)std::min<size_t>(cap, 0xffffffffu),
                                                            d_io_count, io_slots.d, io_xy.d);
         launches++;
         CU(cudaGetLastError());
@@ -1689,7 +1707,7 @@ int World::apply_forces_indexed(const uint32_t* slots, const float* fxy, size_t 
     CU(d_forces.ensure(n, stream));
     CU(cudaMemcpyAsync(io_slots.d, slots, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(d_forces.d, fxy, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
-    k_apply_forces_indexed<<<cdiv(n, 256), 256, 0, stream>>>(body_arrays(), strip_on ? d_owned.d : nullptr, io_slots.d, d_forces.d, (uint32_t)n, (uint32_t)bodies.slots());
+    BLOBS_LAUNCH(cdiv(n, 256), 256, 0, stream, k_apply_forces_indexed)(body_arrays(), strip_on ? d_owned.d : nullptr, io_slots.d, d_forces.d, (uint32_t)n, (uint32_t)bodies.slots());
     launches++;
     CU(cudaGetLastError());
     return BLOBS_OK;

@@ -1,0 +1,205 @@
+// TEST INFRASTRUCTURE (see include/cuda_runtime.h): cooperative-fiber execution of one CUDA grid on the calling thread.
+#include <cuda_runtime.h>
+#include <ucontext.h>
+
+#include <unordered_map>
+#include <vector>
+
+#undef threadIdx
+#undef blockIdx
+#undef blockDim
+#undef gridDim
+
+namespace emu {
+
+uint3 g_threadIdx{0, 0, 0}, g_blockIdx{0, 0, 0};
+dim3 g_blockDim(1, 1, 1), g_gridDim(1, 1, 1);
+
+namespace {
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+struct Barrier {
+    unsigned arrived = 0, gen = 0;
+};
+
+struct Warp {
+    unsigned present = 0;   // lanes that exist in this warp
+    unsigned exited = 0;
+    unsigned long long slots[32];
+    std::unordered_map<unsigned, Barrier> bars;   // one barrier per participation mask
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    bool done = false;
+    bool wait_cta = false;
+    unsigned wait_cta_gen = 0;
+};
+
+struct Cta {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    unsigned n = 0, n_exited = 0;
+    unsigned cta_arrived = 0, cta_gen = 0;
+    unsigned cur = 0;
+    unsigned long long progress = 0;
+    ucontext_t sched;
+    std::vector<unsigned char> smem;
+    const std::function<void()>* body = nullptr;
+};
+
+Cta C;
+unsigned long long g_launches = 0;
+
+void yield() { swapcontext(&C.fibers[C.cur].ctx, &C.sched); }
+
+void trampoline() {
+    (*C.body)();
+    Fiber& f = C.fibers[C.cur];
+    Warp& w = C.warps[C.cur >> 5];
+    f.done = true;
+    w.exited |= 1u << (C.cur & 31u);
+    w.slots[C.cur & 31u] = 0;
+    C.n_exited++;
+    C.progress++;
+    // returning resumes uc_link == the scheduler
+}
+
+[[noreturn]] void deadlock(const char* what) {
+    fprintf(stderr, "[emu] DEADLOCK in block %u: %s\n", g_blockIdx.x, what);
+    for (unsigned t = 0; t < C.n; ++t) {
+        const Fiber& f = C.fibers[t];
+        if (!f.done) fprintf(stderr, "[emu]   thread %u: %s\n", t, f.wait_cta ? "at __syncthreads" : "at a warp collective");
+    }
+    abort();
+}
+
+void run_cta() {
+    for (unsigned t = 0; t < C.n; ++t) {
+        Fiber& f = C.fibers[t];
+        f.done = false;
+        f.wait_cta = false;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = STACK_BYTES;
+        f.ctx.uc_link = &C.sched;
+        makecontext(&f.ctx, trampoline, 0);
+    }
+    const unsigned nw = (C.n + 31) / 32;
+    for (unsigned w = 0; w < nw; ++w) {
+        Warp& W = C.warps[w];
+        const unsigned lanes = C.n - w * 32 >= 32 ? 32 : C.n - w * 32;
+        W.present = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1u);
+        W.exited = 0;
+        W.bars.clear();
+        memset(W.slots, 0, sizeof(W.slots));
+    }
+    C.n_exited = 0;
+    C.cta_arrived = 0;
+    C.cta_gen = 0;
+    while (C.n_exited < C.n) {
+        const unsigned long long pass_progress = C.progress;
+        for (unsigned w = 0; w < nw; ++w) {
+            for (;;) {   // rounds over the lanes of this warp until none of them can run
+                const unsigned long long before = C.progress;
+                bool any = false;
+                for (unsigned l = 0; l < 32 && w * 32 + l < C.n; ++l) {
+                    const unsigned t = w * 32 + l;
+                    Fiber& f = C.fibers[t];
+                    if (f.done) continue;
+                    if (f.wait_cta && f.wait_cta_gen == C.cta_gen) continue;   // parked until the CTA barrier opens
+                    any = true;
+                    C.cur = t;
+                    g_threadIdx = uint3{t, 0, 0};
+                    swapcontext(&C.sched, &f.ctx);
+                }
+                if (!any) break;
+                if (C.progress == before) deadlock("a warp made no progress in a full round (divergent collective?)");
+            }
+        }
+        // threads that exited after others arrived can complete a CTA barrier
+        if (C.cta_arrived && C.cta_arrived >= C.n - C.n_exited) {
+            C.cta_arrived = 0;
+            C.cta_gen++;
+            C.progress++;
+        }
+        if (C.progress == pass_progress && C.n_exited < C.n) deadlock("no thread can run");
+    }
+}
+
+}  // namespace
+
+unsigned lane_id() { return C.cur & 31u; }
+unsigned long long* warp_slots() { return C.warps[C.cur >> 5].slots; }
+unsigned participants(unsigned mask) {
+    const Warp& w = C.warps[C.cur >> 5];
+    return mask & w.present & ~w.exited;
+}
+void* dynamic_smem() { return C.smem.data(); }
+unsigned long long launches() { return g_launches; }
+
+void warp_barrier(unsigned mask) {
+    const unsigned me = C.cur;   // C.cur changes while this fiber is switched out
+    Warp& w = C.warps[me >> 5];
+    const unsigned bit = 1u << (me & 31u);
+    mask |= bit;
+    Barrier& b = w.bars[mask];   // references into unordered_map stay valid across inserts
+    b.arrived |= bit;
+    C.progress++;
+    const unsigned my_gen = b.gen;
+    for (;;) {
+        if (b.gen != my_gen) return;
+        const unsigned need = mask & w.present & ~w.exited;
+        if ((b.arrived & need) == need) {
+            b.arrived = 0;
+            b.gen++;
+            C.progress++;
+            return;
+        }
+        yield();
+    }
+}
+
+void cta_barrier() {
+    const unsigned me = C.cur;
+    Fiber& f = C.fibers[me];
+    C.cta_arrived++;
+    C.progress++;
+    const unsigned my_gen = C.cta_gen;
+    while (C.cta_gen == my_gen) {
+        if (C.cta_arrived >= C.n - C.n_exited) {
+            C.cta_arrived = 0;
+            C.cta_gen++;
+            C.progress++;
+            break;
+        }
+        f.wait_cta = true;
+        f.wait_cta_gen = my_gen;
+        yield();
+    }
+    f.wait_cta = false;
+}
+
+void run_grid(unsigned grid, unsigned block, size_t dyn_smem, const std::function<void()>& body) {
+    if (grid == 0 || block == 0) return;
+    g_launches++;
+    if (C.fibers.size() < block) {
+        const size_t old = C.fibers.size();
+        C.fibers.resize(block);
+        for (size_t i = old; i < block; ++i) C.fibers[i].stack = static_cast<char*>(malloc(STACK_BYTES));
+    }
+    if (C.warps.size() < (block + 31) / 32) C.warps.resize((block + 31) / 32);
+    C.n = block;
+    C.body = &body;
+    C.smem.assign(dyn_smem ? dyn_smem : 1, 0xCD);
+    g_blockDim = dim3(block, 1, 1);
+    g_gridDim = dim3(grid, 1, 1);
+    for (unsigned bx = 0; bx < grid; ++bx) {
+        g_blockIdx = uint3{bx, 0, 0};
+        run_cta();
+    }
+}
+
+}  // namespace emu

@@ -16,7 +16,8 @@ class Backend:
 
 
 def backend_params():
-    return ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
+    # "emu" = the CUDA sources compiled for the host (tests/emu): kernel logic on the CPU, part of the CPU suite
+    return ["oracle", pytest.param("cuda", marks=pytest.mark.gpu), pytest.param("emu", marks=pytest.mark.emu)]
 
 
 def make_backend(name):
@@ -26,6 +27,14 @@ def make_backend(name):
         return Backend("oracle", lambda gravity=(0.0, 0.0), **kw: oracle_py.OracleWorld(gravity=gravity, **kw))
     import blobs_b200
 
+    if name == "emu":
+        from .emu_loader import emulated
+
+        def make(gravity=(0.0, 0.0), **kw):
+            with emulated():   # a World keeps the library handle it was created with
+                return blobs_b200.World(gravity=gravity, **kw)
+
+        return Backend("emu", make)
     return Backend("cuda", lambda gravity=(0.0, 0.0), **kw: blobs_b200.World(gravity=gravity, **kw))
 
 

@@ -1,0 +1,51 @@
+"""Kernel LOGIC on the CPU: the parity tests of test_gpu_parity.py / test_physics_api.py, run against the host-compiled
+build of the very same CUDA sources (tests/emu: one fiber per CUDA thread, warp collectives and shared memory emulated)
+and compared bit-for-bit with the oracle. This is what lets a kernel change be checked in a container without a GPU; it
+says nothing about speed and is not a product path (blobs_b200 never loads the emulation library - see emu_loader.py).
+The `-m gpu` runs of the same tests on the B200 remain the parity gate proper.
+
+Only cases that finish in a few seconds are listed; `BLOBS_TEST_EMU=1 python -m pytest tests -m gpu -k ...` runs any GPU
+test this way (the whole parity suite takes ~8 minutes)."""
+import pytest
+
+from . import test_gpu_parity as T
+from . import test_physics_api as P
+from .emu_loader import emulated
+
+pytestmark = pytest.mark.emu
+
+# knob sets: library defaults (automatic kernel selection) / every optional kernel path forced on for every warp
+DEFAULT = {}
+FORCED = {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}
+
+CASES = [
+    ("overflow30-fused-inline", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=30, fused=1, crowded=0)),
+    ("overflow30-split-crowded", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=30, fused=0, crowded=1)),
+    ("overflow200-fused-crowded", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=200, fused=1, crowded=1)),
+    ("overflow200-split-auto", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=200, fused=0, crowded=2)),
+    ("overflow1200-fused-crowded", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=1200, fused=1, crowded=1)),
+    ("overflow1200-fused-inline", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=1200, fused=1, crowded=0)),
+    ("multi-collider", T.test_multi_collider_bodies_and_filters, {}),
+    ("rotating-multi-collider", T.test_rotating_multi_collider_within_tolerance, {}),
+    ("removal-reinsert", T.test_removal_and_reinsert_mid_simulation, {}),
+    ("body-set-translate", T.test_body_set_and_translate_between_steps, {}),
+    ("far-outlier", T.test_far_outlier_aliases_harmlessly, {}),
+    ("collisions-disabled-variable-delta", T.test_collisions_disabled_and_variable_delta, {}),
+    ("events", T.test_events_match_reference_channel, {}),
+    ("large-island", T.test_large_island_and_mixed_bodies, {}),
+    ("fast-mode", T.test_fast_mode_within_tolerance, {}),
+    ("batched-worlds", T.test_batched_independent_worlds, {}),
+    ("soft-blobs-fused", T.test_soft_blobs_springs_and_joints, dict(fused=1)),
+    ("physics-api-balls", P.test_balls_demo_flow, {}),
+    ("physics-api-joints-springs-panics", P.test_joints_springs_and_panics, {}),
+]
+
+
+@pytest.mark.parametrize("knobs", [DEFAULT, FORCED], ids=["default", "forced-pool-crowded"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
+    _, fn, kw = case
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)   # read by World's constructor (same meaning as the BLOBS_PARAM_* knobs)
+    with emulated():
+        fn(**kw)

@@ -26,6 +26,28 @@ def test_strip_world_matches_single_gpu():
     assert r.returncode == 0
 
 
+@pytest.mark.emu
+@pytest.mark.parametrize("knobs", [{}, {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
+                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
+                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"}],
+                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default"])
+def test_strip_world_matches_single_world_emulated_ranks(knobs):
+    """The same worker without GPUs: 2 CPU processes, each running the host-compiled build of the CUDA sources (tests/emu),
+    exchanging ghosts and migrants every substep through a socket stand-in for NCCL; merged result == single world, bit for
+    bit, with bodies migrating between the strips."""
+    from .emu_loader import build
+
+    build()
+    env = dict(os.environ, BLOBS_TEST_EMU="1", STRIP_TEST_SIDE="48", STRIP_TEST_STEPS="24")
+    env.update(knobs)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29653",
+           os.path.join(REPO, "tests", "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert "mismatches=0" in r.stdout
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
 

@@ -23,7 +23,8 @@ def load_emu():
     global _emu
     if _emu is None:
         build()
-        lib = C.CDLL(EMU_PATH)
+        # BLOBS_TEST_EMU_LIB: an alternative build of the same thing, e.g. one compiled with -fsanitize=address
+        lib = C.CDLL(os.environ.get("BLOBS_TEST_EMU_LIB", EMU_PATH))
         for name, (res, args) in L.SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

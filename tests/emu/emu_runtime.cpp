@@ -2,6 +2,9 @@
 #include <cuda_runtime.h>
 #include <ucontext.h>
 
+#include <algorithm>
+#include <numeric>
+#include <random>
 #include <unordered_map>
 #include <vector>
 
@@ -53,6 +56,23 @@ struct Cta {
 Cta C;
 unsigned long long g_launches = 0;
 
+// BLOBS_EMU_SEED=<n>: CTAs of a launch, warps of a CTA and lanes of a warp are visited in a seeded random order instead of
+// ascending order. Results must not depend on it (atomics hand out different ranks, cells hold their records in a different
+// order): a cheap check for accidental order dependence.
+struct Shuffle {
+    bool on = false;
+    std::mt19937 rng;
+    Shuffle() {
+        if (const char* e = getenv("BLOBS_EMU_SEED")) { on = true; rng.seed((unsigned)atoi(e)); }
+    }
+    void order(std::vector<unsigned>& v, unsigned n) {
+        v.resize(n);
+        std::iota(v.begin(), v.end(), 0u);
+        if (on) std::shuffle(v.begin(), v.end(), rng);
+    }
+};
+Shuffle g_shuffle;
+
 void yield() { swapcontext(&C.fibers[C.cur].ctx, &C.sched); }
 
 void trampoline() {
@@ -99,13 +119,17 @@ void run_cta() {
     C.n_exited = 0;
     C.cta_arrived = 0;
     C.cta_gen = 0;
+    std::vector<unsigned> worder, lorder;
     while (C.n_exited < C.n) {
         const unsigned long long pass_progress = C.progress;
-        for (unsigned w = 0; w < nw; ++w) {
+        g_shuffle.order(worder, nw);
+        for (unsigned w : worder) {
             for (;;) {   // rounds over the lanes of this warp until none of them can run
                 const unsigned long long before = C.progress;
                 bool any = false;
-                for (unsigned l = 0; l < 32 && w * 32 + l < C.n; ++l) {
+                g_shuffle.order(lorder, 32);
+                for (unsigned l : lorder) {
+                    if (w * 32 + l >= C.n) continue;
                     const unsigned t = w * 32 + l;
                     Fiber& f = C.fibers[t];
                     if (f.done) continue;
@@ -196,7 +220,9 @@ void run_grid(unsigned grid, unsigned block, size_t dyn_smem, const std::functio
     C.smem.assign(dyn_smem ? dyn_smem : 1, 0xCD);
     g_blockDim = dim3(block, 1, 1);
     g_gridDim = dim3(grid, 1, 1);
-    for (unsigned bx = 0; bx < grid; ++bx) {
+    std::vector<unsigned> border;
+    g_shuffle.order(border, grid);
+    for (unsigned bx : border) {
         g_blockIdx = uint3{bx, 0, 0};
         run_cta();
     }

@@ -49,3 +49,20 @@ def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
         monkeypatch.setenv(k, v)   # read by World's constructor (same meaning as the BLOBS_PARAM_* knobs)
     with emulated():
         fn(**kw)
+
+
+def test_results_do_not_depend_on_the_schedule():
+    """Same cases with the emulator visiting CTAs, warps and lanes in a seeded RANDOM order (BLOBS_EMU_SEED, read when the
+    library is loaded, hence the subprocess): atomics then hand out different ranks and cells hold their records in another
+    order, yet every result must stay bit-identical to the oracle's."""
+    import os
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BLOBS_EMU_SEED="20261017")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_emu_parity.py"), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "test_kernel_logic_on_cpu and (overflow200 or overflow1200-fused-crowded or multi-collider or large-island or events or removal)"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=repo)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and " passed" in r.stdout

@@ -103,6 +103,10 @@ class KernelInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class DebugCounts(C.Structure):
+    _fields_ = [("bodies", C.c_uint64), ("joints", C.c_uint64), ("colliders", C.c_uint64), ("springs", C.c_uint64)]
+
+
 def body_descs(n):
     """n default RigidBodyBuilder::new() descriptors (rigid_body.rs:303-318)."""
     d = np.zeros(n, dtype=BODY_DESC)

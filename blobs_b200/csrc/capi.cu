@@ -115,6 +115,12 @@ int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap) { W_OR_
 int32_t blobs_apply_forces(BlobsWorld* w, const float* f, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(f); return w->w.apply_forces(f, cap); }
 int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(cx); W_OR_INVALID(cy); return w->w.download_cell_coords(cx, cy, cap); }
 
+int32_t blobs_debug_counts(const BlobsWorld* w, BlobsDebugCounts* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.debug_counts(out); }
+int32_t blobs_debug_data(BlobsWorld* w, float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps) {
+    W_OR_INVALID(w); W_OR_INVALID(caps);
+    return w->w.debug_data(body_xform, joint_ab, col_xform, col_radius, spring_ab, caps);
+}
+
 int32_t blobs_record_contacts(BlobsWorld* w, int32_t mode, size_t cap) { W_OR_INVALID(w); return w->w.record_contacts(mode, cap); }
 int32_t blobs_events_drain(BlobsWorld* w, BlobsCollisionEvent* buf, size_t cap, size_t* n) { W_OR_INVALID(w); return w->w.events_drain(buf, cap, n); }
 int32_t blobs_pairs_drain(BlobsWorld* w, uint32_t* a, uint32_t* b, size_t cap, size_t* n, uint64_t* se, size_t se_cap, size_t* n_sub) {

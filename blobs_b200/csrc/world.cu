@@ -470,6 +470,7 @@ int World::collider_insert(const BlobsColliderDesc& d, uint64_t parent, uint64_t
     if (hc.size() < cols.slots()) hc.resize(cols.slots());
     hc[s].desc = d;
     hc[s].parent = parent;
+    hc[s].born_epoch = snap_epoch;
     const size_t n = cols.slots();
     coff.resize(n, make_float2(0.f, 0.f)); cconst.resize(n, make_uint4(0u, 0u, 0u, 0u)); cparent.resize(n, NO_SLOT);
     ccold.resize(n, make_uint4(0u, 0u, 0u, NO_SLOT));
@@ -517,10 +518,12 @@ int World::collider_get(uint64_t h, BlobsColliderState* out) {
     if (rc) return rc;
     const uint32_t s = h_slot(h);
     float2 a;
+    std::vector<float> r(bodies.slots());
     CU(cudaMemcpyAsync(&a, cabs.d + s, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    if (!r.empty()) CU(cudaMemcpyAsync(r.data(), rot.d, r.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     out->desc = hc[s].desc;
-    out->desc.absolute_transform.translation = {a.x, a.y};
+    out->desc.absolute_transform = live_snapshot(s, a, r);
     out->parent = hc[s].parent;
     return BLOBS_OK;
 }
@@ -1213,6 +1216,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     if (h_stats->list_overflow != 0) crowded_hold = 64;
     else if (crowded_hold > 0) crowded_hold--;
     crowded_seen = crowded_hold > 0;
+    if (substeps_run) snap_epoch++;
     // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep
     if (substeps_run && (double)h_stats->collisions >= 0.25 * (double)substeps_run * (double)std::max<size_t>(bodies.slots(), 1)) pool_hold = 64;
     else if (pool_hold > 0) pool_hold--;
@@ -1346,8 +1350,87 @@ int World::download_colliders(BlobsColliderState* st, uint64_t* handles, size_t 
         std::memset(&st[s], 0, sizeof(BlobsColliderState));
         if (!alive) continue;
         st[s].desc = hc[s].desc;
-        st[s].desc.absolute_transform.translation = {a[s].x, a[s].y};
+        st[s].desc.absolute_transform = live_snapshot((uint32_t)s, a[s], r);
         st[s].parent = hc[s].parent;
+    }
+    return BLOBS_OK;
+}
+
+// collider.absolute_transform as the reference holds it: the caller's value until a substep has run, then
+// rbd.transform() * offset (physics.rs:360-366): the translation is what the device keeps (bit-exact), the matrix part is
+// only ever read by debug output, so it is recomposed here: M(rot) * offset.matrix2 (glam column convention).
+BlobsAffine2 World::live_snapshot(uint32_t s, float2 t, const std::vector<float>& rot_host) const {
+    BlobsAffine2 out = hc[s].desc.absolute_transform;
+    out.translation = {t.x, t.y};
+    if (hc[s].born_epoch < snap_epoch && bodies.valid(hc[s].parent)) {
+        const uint32_t b = h_slot(hc[s].parent);
+        const float th = b < rot_host.size() ? rot_host[b] : 0.f;
+        const float sn = std::sin(th), cs = std::cos(th);
+        const BlobsAffine2& o = hc[s].desc.offset;
+        // M * v = x_axis * v.x + y_axis * v.y with x_axis = (cos, sin), y_axis = (-sin, cos)
+        out.x_axis = {cs * o.x_axis.x + (-sn) * o.x_axis.y, sn * o.x_axis.x + cs * o.x_axis.y};
+        out.y_axis = {cs * o.y_axis.x + (-sn) * o.y_axis.y, sn * o.y_axis.x + cs * o.y_axis.y};
+    }
+    return out;
+}
+
+// Physics::debug_data (physics.rs:479-481, debug.rs:34-91): arena iteration order = ascending slot, free slots skipped.
+int World::debug_counts(BlobsDebugCounts* out) const {
+    out->bodies = bodies.len;
+    out->joints = joints.len;
+    out->colliders = cols.len;
+    out->springs = springs.len;
+    return BLOBS_OK;
+}
+
+int World::debug_data(float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps) {
+    int rc = flush();
+    if (rc) return rc;
+    const size_t nb = bodies.slots(), nc = cols.slots();
+    std::vector<float2> p(nb), a(nc);
+    std::vector<float> r(nb);
+    if (nb) {
+        CU(cudaMemcpyAsync(p.data(), pos.d, nb * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(r.data(), rot.d, nb * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
+    if (nc) CU(cudaMemcpyAsync(a.data(), cabs.d, nc * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const float nanv = std::nanf("");
+    if (body_xform) {   // DebugRigidBody { transform: Affine2::from_angle_translation(rotation, position) }
+        size_t k = 0;
+        for (size_t s = 0; s < nb && k < caps->bodies; ++s) {
+            if (!bodies.alive[s]) continue;
+            const float sn = std::sin(r[s]), cs = std::cos(r[s]);
+            float* o = body_xform + 6 * k++;
+            o[0] = cs; o[1] = sn; o[2] = -sn; o[3] = cs; o[4] = p[s].x; o[5] = p[s].y;
+        }
+    }
+    auto endpoints = [&](float* out, size_t cap, const HostArena& arena, auto&& ab_of) {
+        size_t k = 0;
+        for (size_t s = 0; s < arena.slots() && k < cap; ++s) {
+            if (!arena.alive[s]) continue;
+            const auto ab = ab_of(s);
+            float* o = out + 4 * k++;
+            // the reference indexes the arena directly and panics on a removed body; here the endpoint reads as NaN
+            const bool va = bodies.valid(ab.first), vb = bodies.valid(ab.second);
+            o[0] = va ? p[h_slot(ab.first)].x : nanv; o[1] = va ? p[h_slot(ab.first)].y : nanv;
+            o[2] = vb ? p[h_slot(ab.second)].x : nanv; o[3] = vb ? p[h_slot(ab.second)].y : nanv;
+        }
+    };
+    if (joint_ab) endpoints(joint_ab, caps->joints, joints, [&](size_t s) { return std::make_pair(hj[s].a, hj[s].b); });
+    if (spring_ab) endpoints(spring_ab, caps->springs, springs, [&](size_t s) { return std::make_pair(hs[s].a, hs[s].b); });
+    if (col_xform || col_radius) {   // DebugCollider { transform: collider.absolute_transform, radius: ball.radius }
+        size_t k = 0;
+        for (size_t s = 0; s < nc && k < caps->colliders; ++s) {
+            if (!cols.alive[s]) continue;
+            if (col_xform) {
+                const BlobsAffine2 t = live_snapshot((uint32_t)s, a[s], r);
+                float* o = col_xform + 6 * k;
+                o[0] = t.x_axis.x; o[1] = t.x_axis.y; o[2] = t.y_axis.x; o[3] = t.y_axis.y; o[4] = t.translation.x; o[5] = t.translation.y;
+            }
+            if (col_radius) col_radius[k] = hc[s].desc.shape_radius;
+            ++k;
+        }
     }
     return BLOBS_OK;
 }

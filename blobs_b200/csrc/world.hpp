@@ -141,6 +141,7 @@ struct HBody {
 struct HCollider {
     BlobsColliderDesc desc;
     uint64_t parent = 0;
+    uint64_t born_epoch = 0;   // World::snap_epoch at insertion: the snapshot matrix is the caller's until a substep has run
 };
 
 struct HSpring { uint64_t a, b; float rest, k, c; };
@@ -178,6 +179,8 @@ class World {
     int fixed_step(double frame_time, BlobsStepStats* stats);
     int download_bodies(BlobsBodyState* st, uint64_t* handles, size_t cap);
     int download_colliders(BlobsColliderState* st, uint64_t* handles, size_t cap);
+    int debug_counts(BlobsDebugCounts* out) const;
+    int debug_data(float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps);
     int read_body_vec(int which, float* xy, size_t cap);
     int apply_forces(const float* f, size_t cap);
     int download_cell_coords(int32_t* cx, int32_t* cy, size_t cap);
@@ -256,6 +259,8 @@ class World {
 
     // arenas + host records
     HostArena bodies, cols, springs, joints;
+    uint64_t snap_epoch = 0;   // number of step calls that ran at least one substep (every live collider snapshot is rewritten by each)
+    BlobsAffine2 live_snapshot(uint32_t col_slot, float2 translation, const std::vector<float>& rot_host) const;
     std::vector<HBody> hb;
     std::vector<HCollider> hc;
     std::vector<HSpring> hs;

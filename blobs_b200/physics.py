@@ -350,13 +350,15 @@ class Physics:
         return self._w.spring_insert(spring.rigid_body_a, spring.rigid_body_b, spring.rest_length, spring.stiffness, spring.damping)
 
     def debug_data(self):  # physics.rs:479-481 / debug.rs:34-91
-        bodies, bh = self._w.download_bodies()
-        cols, ch = self._w.download_colliders()
-        live_b, live_c = bh != 0, ch != 0
+        """DebugData { bodies, joints, colliders, springs } from one library call (blobs_debug_data)."""
+        d = self._w.debug_data()
+
+        def affine(row):
+            return Affine2((float(row[0]), float(row[1])), (float(row[2]), float(row[3])), (float(row[4]), float(row[5])))
+
         return {
-            "bodies": [Affine2.from_angle_translation(float(r), (float(x), float(y)))
-                       for r, x, y in zip(bodies["rotation"][live_b], bodies["position"]["x"][live_b], bodies["position"]["y"][live_b])],
-            "colliders": [((float(x), float(y)), float(r)) for x, y, r in zip(cols["desc"]["absolute_transform"]["translation"]["x"][live_c],
-                                                                             cols["desc"]["absolute_transform"]["translation"]["y"][live_c],
-                                                                             cols["desc"]["shape_radius"][live_c])],
+            "bodies": [affine(r) for r in d["bodies"]],                                                        # DebugRigidBody.transform
+            "joints": [((float(r[0]), float(r[1])), (float(r[2]), float(r[3]))) for r in d["joints"]],         # DebugJoint {body_a, body_b}
+            "colliders": [(affine(r), float(rad)) for r, rad in zip(d["colliders"], d["collider_radius"])],    # DebugCollider {transform, radius}
+            "springs": [((float(r[0]), float(r[1])), (float(r[2]), float(r[3]))) for r in d["springs"]],       # DebugSpring {body_a, body_b}
         }

@@ -285,6 +285,19 @@ class World:
         self._ck(self._lib.blobs_kernel_info(self._h, C.byref(k)))
         return k.as_dict()
 
+    def debug_data(self):
+        """Physics::debug_data (physics.rs:479-481, debug.rs:34-91) in one call: dict of float32 arrays in arena order -
+        bodies (n, 6) and colliders (n, 6) as glam Affine2 (x_axis, y_axis, translation), collider_radius (n,),
+        joints (n, 4) and springs (n, 4) as (body_a.xy, body_b.xy)."""
+        cnt = A.DebugCounts()
+        self._ck(self._lib.blobs_debug_counts(self._h, C.byref(cnt)))
+        out = {"bodies": np.zeros((cnt.bodies, 6), np.float32), "joints": np.zeros((cnt.joints, 4), np.float32),
+               "colliders": np.zeros((cnt.colliders, 6), np.float32), "collider_radius": np.zeros(cnt.colliders, np.float32),
+               "springs": np.zeros((cnt.springs, 4), np.float32)}
+        self._ck(self._lib.blobs_debug_data(self._h, A.ptr(out["bodies"]), A.ptr(out["joints"]), A.ptr(out["colliders"]),
+                                            A.ptr(out["collider_radius"]), A.ptr(out["springs"]), C.byref(cnt)))
+        return out
+
     def profile_enable(self, on=True):
         self._ck(self._lib.blobs_profile_enable(self._h, int(on)))
 

@@ -241,6 +241,16 @@ int32_t blobs_apply_forces(BlobsWorld* w, const float* force_xy, size_t cap);  /
 /* SpatialHash::get_cell_coords (spatial.rs:57-62) of every collider snapshot, with BLOBS_PARAM_CELL_SIZE */
 int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap);
 
+/* Physics::debug_data (physics.rs:479-481) / make_debug_data (debug.rs:34-91): one call, arena iteration order (ascending
+ * slot, free slots skipped). body_xform / col_xform: 6 floats per entry = glam::Affine2 (x_axis.xy, y_axis.xy, translation.xy),
+ * bodies as from_angle_translation(rotation, position), colliders as collider.absolute_transform; col_radius: Ball radius;
+ * joint_ab / spring_ab: 4 floats per entry = position of rigid_body_a, position of rigid_body_b (NaN where the reference would
+ * panic on a removed body). Any pointer may be NULL; `caps` holds the capacities in entries. */
+typedef struct BlobsDebugCounts { uint64_t bodies, joints, colliders, springs; } BlobsDebugCounts;
+int32_t blobs_debug_counts(const BlobsWorld* w, BlobsDebugCounts* out);
+int32_t blobs_debug_data(BlobsWorld* w, float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab,
+                         const BlobsDebugCounts* caps);
+
 /* ---- contact output ------------------------------------------------------------------------------ */
 enum { BLOBS_RECORD_OFF = 0, BLOBS_RECORD_PAIRS = 1, BLOBS_RECORD_EVENTS = 2 };
 /* collision_send / collision_recv, physics.rs:22-23,304-311. PAIRS records slots only. */

@@ -40,6 +40,10 @@ pub const BLOBS_PARAM_ACCUMULATOR: i32 = 6; pub const BLOBS_PARAM_TIME: i32 = 7;
 pub const BLOBS_RECORD_EVENTS: i32 = 2;
 
 #[link(name = "blobs_b200")]
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct BlobsDebugCounts { pub bodies: u64, pub joints: u64, pub colliders: u64, pub springs: u64 }
+
 extern "C" {
     pub fn blobs_world_create(params: *const BlobsParams, out: *mut *mut BlobsWorld) -> i32;
     pub fn blobs_world_destroy(w: *mut BlobsWorld) -> i32;
@@ -66,6 +70,9 @@ extern "C" {
     pub fn blobs_events_drain(w: *mut BlobsWorld, buf: *mut BlobsCollisionEvent, cap: usize, n: *mut usize) -> i32;
     pub fn blobs_download_bodies(w: *mut BlobsWorld, states: *mut BlobsBodyState, handles: *mut BlobsHandle, cap: usize) -> i32;
     pub fn blobs_download_colliders(w: *mut BlobsWorld, states: *mut BlobsColliderState, handles: *mut BlobsHandle, cap: usize) -> i32;
+    pub fn blobs_debug_counts(w: *const BlobsWorld, out: *mut BlobsDebugCounts) -> i32;
+    pub fn blobs_debug_data(w: *mut BlobsWorld, body_xform: *mut c_float, joint_ab: *mut c_float, col_xform: *mut c_float, col_radius: *mut c_float,
+                            spring_ab: *mut c_float, caps: *const BlobsDebugCounts) -> i32;
     pub fn blobs_body_slots(w: *const BlobsWorld, out: *mut u64) -> i32;
     pub fn blobs_collider_slots(w: *const BlobsWorld, out: *mut u64) -> i32;
 }

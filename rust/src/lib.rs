@@ -93,6 +93,21 @@ impl Physics {
     }
     pub fn remove_rbd(&mut self, h: RigidBodyHandle) { unsafe { blobs_body_remove(self.w, h.0.to_bits()) }; }     // physics.rs:163-172 (missing body: event only)
     pub fn remove_col(&mut self, h: ColliderHandle) { unsafe { blobs_collider_remove(self.w, h.0.to_bits()) }; } // physics.rs:159-161
+    /// Physics::debug_data (physics.rs:479-481): one library call, lists in arena order (debug.rs:34-91)
+    pub fn debug_data(&mut self) -> DebugData {
+        let mut c = BlobsDebugCounts::default();
+        self.ck(unsafe { blobs_debug_counts(self.w, &mut c) });
+        let (mut bx, mut jx) = (vec![0f32; 6 * c.bodies as usize], vec![0f32; 4 * c.joints as usize]);
+        let (mut cx, mut cr, mut sx) = (vec![0f32; 6 * c.colliders as usize], vec![0f32; c.colliders as usize], vec![0f32; 4 * c.springs as usize]);
+        self.ck(unsafe { blobs_debug_data(self.w, bx.as_mut_ptr(), jx.as_mut_ptr(), cx.as_mut_ptr(), cr.as_mut_ptr(), sx.as_mut_ptr(), &c) });
+        let aff = |r: &[f32]| Affine2::from_mat2_translation(Mat2::from_cols(Vec2::new(r[0], r[1]), Vec2::new(r[2], r[3])), Vec2::new(r[4], r[5]));
+        DebugData {
+            bodies: bx.chunks(6).map(|r| DebugRigidBody { transform: aff(r) }).collect(),
+            joints: jx.chunks(4).map(|r| DebugJoint { body_a: Vec2::new(r[0], r[1]), body_b: Vec2::new(r[2], r[3]) }).collect(),
+            colliders: cx.chunks(6).zip(cr.iter()).map(|(r, &radius)| DebugCollider { transform: aff(r), radius }).collect(),
+            springs: sx.chunks(4).map(|r| DebugSpring { body_a: Vec2::new(r[0], r[1]), body_b: Vec2::new(r[2], r[3]) }).collect(),
+        }
+    }
     pub fn rbd_count(&self) -> usize { let mut n = 0u64; unsafe { blobs_body_count(self.w, &mut n) }; n as usize }
     pub fn get_rbd_state(&mut self, h: RigidBodyHandle) -> Option<BlobsBodyState> { let mut s = BlobsBodyState::default(); (unsafe { blobs_body_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then_some(s) }
     pub fn rbd_position(&mut self, h: RigidBodyHandle) -> Option<Vec2> { self.get_rbd_state(h).map(|s| g(s.position)) }              // physics.rs:151-153
@@ -150,3 +165,10 @@ impl ColliderBuilder {
     pub fn build(self) -> Collider { self.0 }
 }
 #[allow(dead_code)] fn _unused(_: Mat2) {}
+
+/// debug.rs:6-32
+pub struct DebugRigidBody { pub transform: Affine2 }
+pub struct DebugCollider { pub transform: Affine2, pub radius: f32 }
+pub struct DebugJoint { pub body_a: Vec2, pub body_b: Vec2 }
+pub struct DebugSpring { pub body_a: Vec2, pub body_b: Vec2 }
+pub struct DebugData { pub bodies: Vec<DebugRigidBody>, pub joints: Vec<DebugJoint>, pub colliders: Vec<DebugCollider>, pub springs: Vec<DebugSpring> }

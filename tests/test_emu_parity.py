@@ -36,6 +36,7 @@ CASES = [
     ("fast-mode", T.test_fast_mode_within_tolerance, {}),
     ("batched-worlds", T.test_batched_independent_worlds, {}),
     ("soft-blobs-fused", T.test_soft_blobs_springs_and_joints, dict(fused=1)),
+    ("debug-data", T.test_debug_data_one_call_snapshot, {}),
     ("physics-api-balls", P.test_balls_demo_flow, {}),
     ("physics-api-joints-springs-panics", P.test_joints_springs_and_panics, {}),
 ]

@@ -511,3 +511,68 @@ def test_boundary_shell_vs_grid_oracle(crowded):
             assert np.array_equal(x, y), f"pair set differs at step {step} substep {sub}: gpu {len(x)} oracle {len(y)}"
     assert tot_over > 500
     assert tot_col == o.step(1 / 60, n=0)["collisions"]
+
+
+def test_debug_data_one_call_snapshot():
+    """Physics::debug_data (debug.rs:34-91) through blobs_debug_data: arena order for all four lists (a removed and re-inserted
+    spring re-uses its slot), joint / spring endpoints = live body positions, collider transforms = the live snapshot
+    (translation bit-exact vs the oracle, matrix = M(rotation) * offset.matrix2 once a substep has run)."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    g = blobs_b200.World(gravity=(0.0, -5.0))
+    o = oracle_py.OracleWorld(gravity=(0.0, -5.0), maintain_spatial_hash=False, record_events=False)
+    hs = []
+    for w in (g, o):
+        b = [sphere(w, (0.0, 0.0), r=0.3)[0], sphere(w, (1.0, 0.2), r=0.3)[0], sphere(w, (2.1, 0.0), r=0.25)[0], sphere(w, (0.5, 1.4), r=0.2)[0]]
+        # a body with two colliders, one of them with a rotated offset
+        bd = A.body_descs(1)
+        bd["position"]["x"], bd["position"]["y"] = 4.0, 1.0
+        bd["position_old"] = bd["position"]
+        mb = w.insert_bodies(bd)
+        cd = A.collider_descs(2)
+        cd["radius"] = 0.2
+        cd["shape_radius"] = [0.2, 0.35]
+        cd["offset"]["translation"]["x"] = [0.3, -0.3]
+        cd["offset"]["x_axis"]["x"], cd["offset"]["x_axis"]["y"] = [1.0, 0.0], [0.0, 1.0]      # second offset rotated by 90 degrees
+        cd["offset"]["y_axis"]["x"], cd["offset"]["y_axis"]["y"] = [0.0, -1.0], [1.0, 0.0]
+        cd["absolute_transform"]["translation"]["x"] = [4.3, 3.7]
+        cd["absolute_transform"]["translation"]["y"] = [1.0, 1.0]
+        w.insert_colliders(cd, mb[[0, 0]])
+        j0 = w.joint_insert(b[0], b[1])                 # the joint makes both bodies rotate (physics.rs:455-469)
+        s0 = w.spring_insert(b[1], b[2], 1.0, 50.0, 1.0)
+        s1 = w.spring_insert(b[2], b[3], 1.5, 20.0, 0.5)
+        w.spring_remove(s0)
+        s2 = w.spring_insert(b[3], b[0], 1.2, 30.0, 0.5)   # LIFO: lands in s0's slot, so it iterates BEFORE s1
+        hs.append((b, int(mb[0]), j0, s1, s2))
+    assert hs[0] == hs[1]
+    b, mb, _, _, _ = hs[0]
+    before = g.debug_data()
+    assert np.allclose(before["colliders"][4:, :4], [[1, 0, 0, 1], [1, 0, 0, 1]])    # caller's absolute_transform until a substep runs
+    for _ in range(5):
+        g.step(1 / 60)
+        o.step(1 / 60)
+    d = g.debug_data()
+    sb, hb = g.download_bodies()
+    ob, _ = o.download_bodies()
+    oc, och = o.download_colliders()
+    slot = lambda h: int(h) & 0xFFFFFFFF
+    live = hb != 0
+    assert d["bodies"].shape == (5, 6) and d["joints"].shape == (1, 4) and d["colliders"].shape == (6, 6) and d["springs"].shape == (2, 4)
+    px, py, rot = sb["position"]["x"][live], sb["position"]["y"][live], sb["rotation"][live]
+    assert np.array_equal(bits(d["bodies"][:, 4]), bits(px)) and np.array_equal(bits(d["bodies"][:, 5]), bits(py))
+    assert np.array_equal(bits(px), bits(ob["position"]["x"][live]))
+    assert np.allclose(d["bodies"][:, 0], np.cos(rot), atol=1e-6) and np.allclose(d["bodies"][:, 1], np.sin(rot), atol=1e-6)
+    assert np.allclose(d["bodies"][:, 2], -np.sin(rot), atol=1e-6) and np.allclose(d["bodies"][:, 3], np.cos(rot), atol=1e-6)
+    assert np.abs(rot[:2]).max() > 0, "the jointed bodies must have rotated"
+    pos = lambda h: (sb["position"]["x"][slot(h)], sb["position"]["y"][slot(h)])
+    assert np.array_equal(bits(d["joints"][0]), bits(np.array([*pos(b[0]), *pos(b[1])], dtype=np.float32)))
+    assert np.array_equal(bits(d["springs"][0]), bits(np.array([*pos(b[3]), *pos(b[0])], dtype=np.float32)))   # re-used slot first
+    assert np.array_equal(bits(d["springs"][1]), bits(np.array([*pos(b[2]), *pos(b[3])], dtype=np.float32)))
+    olive = och != 0
+    ot = oc["desc"]["absolute_transform"][olive]
+    assert np.array_equal(bits(d["colliders"][:, 4]), bits(ot["translation"]["x"])) and np.array_equal(bits(d["colliders"][:, 5]), bits(ot["translation"]["y"]))
+    want_m = np.stack([ot["x_axis"]["x"], ot["x_axis"]["y"], ot["y_axis"]["x"], ot["y_axis"]["y"]], axis=1)
+    assert np.allclose(d["colliders"][:, :4], want_m, atol=1e-6)
+    assert np.allclose(d["colliders"][5, :4], [0, 1, -1, 0], atol=1e-6)          # M(0) * the 90-degree offset
+    assert np.allclose(d["collider_radius"], [0.3, 0.3, 0.25, 0.2, 0.2, 0.35])

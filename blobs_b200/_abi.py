@@ -103,6 +103,14 @@ class KernelInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class QueryFilter(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("has_groups", C.c_int32), ("memberships", C.c_uint32), ("filter", C.c_uint32),
+                ("exclude_collider", C.c_uint64), ("exclude_rigid_body", C.c_uint64), ("batch_world", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+QUERY_EXCLUDE_FIXED, QUERY_EXCLUDE_KINEMATIC, QUERY_EXCLUDE_DYNAMIC, QUERY_EXCLUDE_SENSORS, QUERY_EXCLUDE_SOLIDS = 2, 4, 8, 16, 32
+
+
 class DebugCounts(C.Structure):
     _fields_ = [("bodies", C.c_uint64), ("joints", C.c_uint64), ("colliders", C.c_uint64), ("springs", C.c_uint64)]
 

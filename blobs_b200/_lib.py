@@ -53,6 +53,7 @@ SIGNATURES = {
     "blobs_read_body_velocities": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "blobs_apply_forces": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "blobs_download_cell_coords": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
+    "blobs_query_circles": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, C.POINTER(A.QueryFilter), _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "blobs_debug_counts": (C.c_int32, [_vp, C.POINTER(A.DebugCounts)]),
     "blobs_debug_data": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(A.DebugCounts)]),
     "blobs_record_contacts": (C.c_int32, [_vp, C.c_int32, C.c_size_t]),

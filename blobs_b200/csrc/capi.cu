@@ -115,6 +115,12 @@ int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap) { W_OR_
 int32_t blobs_apply_forces(BlobsWorld* w, const float* f, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(f); return w->w.apply_forces(f, cap); }
 int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(cx); W_OR_INVALID(cy); return w->w.download_cell_coords(cx, cy, cap); }
 
+int32_t blobs_query_circles(BlobsWorld* w, size_t n, const float* c, const float* r, const BlobsQueryFilter* f, uint64_t* off, BlobsHandle* hits, size_t cap, size_t* nh) {
+    W_OR_INVALID(w); W_OR_INVALID(off);
+    if (n) { W_OR_INVALID(c); W_OR_INVALID(r); }
+    if (cap) W_OR_INVALID(hits);
+    return w->w.query_circles(n, c, r, f, off, hits, cap, nh);
+}
 int32_t blobs_debug_counts(const BlobsWorld* w, BlobsDebugCounts* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.debug_counts(out); }
 int32_t blobs_debug_data(BlobsWorld* w, float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps) {
     W_OR_INVALID(w); W_OR_INVALID(caps);

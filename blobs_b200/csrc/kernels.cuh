@@ -1524,6 +1524,54 @@ __global__ void __launch_bounds__(256) k_bbox(ColliderArrays Cc, float cell, uin
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K-query: circle queries against the live collider snapshots, served from the broadphase table (the
+// reference's SpatialHash::query, spatial.rs:155-195, and the stubbed QueryPipeline / QueryFilter, lib.rs:167-187,
+// query_filter.rs:27-108). One thread per query. Hit test as in SpatialHash::query: (p - q).length_squared() <= (qr + pr)^2,
+// inclusive, in the reference's f32 evaluation order; unlike the reference's fixed 3x3 cell window the walk covers every cell
+// the circle can reach, so no hit is missed when qr exceeds the cell size. Two passes over the same (unchanged) table:
+// offsets == nullptr counts, otherwise hits are written at offsets[q] in walk order (the host sorts each segment).
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { QF_EXCLUDE_FIXED = 1u << 1, QF_EXCLUDE_KINEMATIC = 1u << 2, QF_EXCLUDE_DYNAMIC = 1u << 3, QF_EXCLUDE_SENSORS = 1u << 4, QF_EXCLUDE_SOLIDS = 1u << 5 };
+
+__global__ void __launch_bounds__(128) k_query(GridDesc g, Broadphase bp, ColliderArrays Cc, BodyArrays B, const float2* __restrict__ centers,
+                                               const float* __restrict__ radii, uint32_t nq, QueryFilterDev F, const uint32_t* __restrict__ offsets,
+                                               uint32_t* __restrict__ counts, uint32_t* __restrict__ hits) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float2 c = centers[q];
+    const float qr = radii[q];
+    uint32_t n = 0;
+    if (qr >= 0.f && c.x == c.x && c.y == c.y) {   // negative / NaN radius or centre: no hits
+        const uint32_t base = offsets != nullptr ? offsets[q] : 0u;
+        // candidate cells: reach = qr (slightly inflated: the hit test is inclusive and rounds) + largest collider radius
+        for_each_candidate(g, bp, Cc.ccold, F.wbase, c.x, c.y, qr * 1.000001f + 1e-30f, [&](const Rec& o) {
+            const float dist = fadd(qr, o.r);
+            const float dx = fsub(o.x, c.x), dy = fsub(o.y, c.y);
+            const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+            if (!(d2 <= fmul(dist, dist))) return;
+            const uint32_t slot = o.slot_sensor & HOT_SLOT_MASK;
+            const bool sensor = (o.slot_sensor & HOT_SENSOR_BIT) != 0u;
+            if (slot == F.exclude_col) return;
+            if ((F.flags & QF_EXCLUDE_SENSORS) && sensor) return;
+            if ((F.flags & QF_EXCLUDE_SOLIDS) && !sensor) return;
+            if (F.has_groups && !((o.memb & F.filt) != 0u && (F.memb & o.filt) != 0u)) return;   // collision_groups.test(groups)
+            if (F.exclude_body != NO_SLOT || (F.flags & (QF_EXCLUDE_FIXED | QF_EXCLUDE_KINEMATIC | QF_EXCLUDE_DYNAMIC))) {
+                const uint32_t parent = Cc.cparent[slot];   // the record's own parent word is a stand-in for default spheres
+                if (parent == F.exclude_body) return;
+                const uint32_t bf = B.binfo[parent].x;
+                const bool fixed = (bf & BF_STATIC) != 0u, kin = (bf & BF_KINEMATIC) != 0u;
+                if ((F.flags & QF_EXCLUDE_FIXED) && fixed) return;
+                if ((F.flags & QF_EXCLUDE_KINEMATIC) && kin) return;
+                if ((F.flags & QF_EXCLUDE_DYNAMIC) && !fixed && !kin) return;
+            }
+            if (offsets != nullptr) hits[base + n] = slot;
+            ++n;
+        });
+    }
+    if (offsets == nullptr) counts[q] = n;
+}
+
 // SpatialHash::get_cell_coords of every collider snapshot with the reference's cell size (spatial.rs:57-62)
 __global__ void __launch_bounds__(256) k_cell_coords(const float2* __restrict__ cabs, float cell_size, uint32_t n, int* __restrict__ cx,
                                                      int* __restrict__ cy) {

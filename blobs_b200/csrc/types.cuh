@@ -13,7 +13,8 @@ enum : uint32_t {
     BF_SPRINGS = 1u << 2,      // has incident springs: gravity + spring forces are summed by k_springs
     BF_ROT = 1u << 3,          // angular state may be non-zero / rotation matters (torque, joints, rotated)
     BF_JOINTED = 1u << 4,
-    BF_FIRST_DYN = 1u << 5,    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
+    BF_FIRST_DYN = 1u << 5,
+    BF_KINEMATIC = 1u << 6,    // RigidBodyType::KinematicPositionBased / KinematicVelocityBased (only scene queries look at it)    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
 };
 // collider flags (host-authoritative, cflags[])
 enum : uint32_t {
@@ -70,6 +71,15 @@ struct DeviceStats {       // accumulated per blobs_step* call, read back once
     int bb_min_x, bb_min_y, bb_max_x, bb_max_y;   // bbox of collider snapshot cells (k_bbox)
     unsigned int max_ghosts, max_migrants;        // strip mode: largest message sections received in this call
     unsigned int over_count[2];                   // crowded-body list lengths, double-buffered by substep parity (k_crowded)
+};
+
+// Scene-query filter on the device (QueryFilter, query_filter.rs:74-108; flag values query_filter.rs:6-25)
+struct QueryFilterDev {
+    uint32_t flags;          // QueryFilterFlags bits
+    uint32_t has_groups, memb, filt;
+    uint32_t exclude_col;    // collider slot or NO_SLOT
+    uint32_t exclude_body;   // body slot or NO_SLOT
+    uint32_t wbase;          // first table entry of the batched world the query runs in
 };
 
 struct SubstepParams {

@@ -109,6 +109,7 @@ World::~World() {
     mb_body.release(); mb_off.release(); mb_cols.release(); sb_body.release(); sb_off.release(); sb_edge.release();
     isl_off.release(); isl_joint.release(); d_joints_inter.release(); isl_boff.release(); isl_body.release(); d_springs.release(); d_joints.release();
     hot_a.release(); hot_b.release(); tab_a.release(); tab_b.release(); tile_a.release(); tile_b.release(); over_list.release();
+    d_qcentre.release(); d_qradius.release(); d_qcount.release(); d_qoff.release(); d_qhits.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
     d_owned.release(); d_cowned.release(); gcell.release(); io_slots.release(); io_xy.release(); olist.release(); opos.release();
@@ -754,6 +755,7 @@ int World::rebuild_topology() {
             HBody& x = hb[b];
             f |= BF_ALIVE;
             if (x.type == BLOBS_BODY_STATIC) f |= BF_STATIC;
+            if (x.type == BLOBS_BODY_KINEMATIC_POSITION || x.type == BLOBS_BODY_KINEMATIC_VELOCITY) f |= BF_KINEMATIC;
             else {
                 any_dynamic = true;
                 if (!world_has_first[x.world]) { world_has_first[x.world] = 1; f |= BF_FIRST_DYN; }
@@ -1474,6 +1476,66 @@ int World::download_cell_coords(int32_t* cx, int32_t* cy, size_t cap) {
     CU(cudaStreamSynchronize(stream));
     for (size_t s = 0; s < n; ++s)
         if (!cols.alive[s]) cx[s] = cy[s] = 0;
+    return BLOBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- scene queries
+int World::query_circles(size_t n, const float* centre_xy, const float* radius, const BlobsQueryFilter* filter, uint64_t* offsets, uint64_t* hits,
+                         size_t hit_cap, size_t* n_hits) {
+    if (strip_on) return fail(BLOBS_ERR_INVALID, "scene queries are not available on a strip-decomposed world (each rank holds one strip)");
+    if (n > 0xffffffffull) return fail(BLOBS_ERR_INVALID, "too many queries in one call");
+    int rc = flush();   // also (re)builds the table if colliders were inserted or moved since the last step
+    if (rc) return rc;
+    if (n_hits) *n_hits = 0;
+    for (size_t q = 0; q <= n; ++q) offsets[q] = 0;
+    if (!n || !cols.slots() || !n_active_cols) return BLOBS_OK;
+    QueryFilterDev F{};
+    F.exclude_col = F.exclude_body = NO_SLOT;
+    if (filter) {
+        F.flags = filter->flags;
+        F.has_groups = filter->has_groups ? 1u : 0u;
+        F.memb = filter->memberships;
+        F.filt = filter->filter;
+        if (filter->exclude_collider && cols.valid(filter->exclude_collider)) F.exclude_col = h_slot(filter->exclude_collider);
+        if (filter->exclude_rigid_body && bodies.valid(filter->exclude_rigid_body)) F.exclude_body = h_slot(filter->exclude_rigid_body);
+        if (filter->batch_world >= n_worlds) return fail(BLOBS_ERR_INVALID, "query: batch world id out of range");
+        F.wbase = filter->batch_world * grid.ncells;
+    }
+    Broadphase bp;
+    bp.hot = cur_is_a ? hot_a.d : hot_b.d;
+    bp.tab = cur_is_a ? tab_a.d : tab_b.d;
+    bp.tab_next = nullptr;
+    bp.tile_next = nullptr;
+    CU(d_qcentre.ensure(n, stream)); CU(d_qradius.ensure(n, stream)); CU(d_qcount.ensure(n, stream)); CU(d_qoff.ensure(n, stream));
+    CU(cudaMemcpyAsync(d_qcentre.d, centre_xy, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(d_qradius.d, radius, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    const BodyArrays B = body_arrays();
+    const ColliderArrays C = col_arrays();
+    BLOBS_LAUNCH(cdiv(n, 128), 128, 0, stream, k_query)(grid, bp, C, B, d_qcentre.d, d_qradius.d, (uint32_t)n, F, nullptr, d_qcount.d, nullptr);
+    launches++;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> cnt(n), off(n);
+    CU(cudaMemcpyAsync(cnt.data(), d_qcount.d, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    uint64_t total = 0;
+    for (size_t q = 0; q < n; ++q) { offsets[q] = total; off[q] = (uint32_t)total; total += cnt[q]; }
+    offsets[n] = total;
+    if (n_hits) *n_hits = (size_t)total;
+    if (total > 0xffffffffull) return fail(BLOBS_ERR_CAPACITY, "query: more than 2^32 hits in one call");
+    if (total > hit_cap) return fail(BLOBS_ERR_CAPACITY, "query: hit buffer too small (n_hits holds the required capacity)");
+    if (!total) return BLOBS_OK;
+    CU(d_qhits.ensure((size_t)total, stream));
+    CU(cudaMemcpyAsync(d_qoff.d, off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    BLOBS_LAUNCH(cdiv(n, 128), 128, 0, stream, k_query)(grid, bp, C, B, d_qcentre.d, d_qradius.d, (uint32_t)n, F, d_qoff.d, d_qcount.d, d_qhits.d);
+    launches++;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> slots((size_t)total);
+    CU(cudaMemcpyAsync(slots.data(), d_qhits.d, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (size_t q = 0; q < n; ++q) {
+        std::sort(slots.begin() + (ptrdiff_t)offsets[q], slots.begin() + (ptrdiff_t)offsets[q + 1]);
+        for (uint64_t i = offsets[q]; i < offsets[q + 1]; ++i) hits[i] = cols.handle_at(slots[i]);
+    }
     return BLOBS_OK;
 }
 

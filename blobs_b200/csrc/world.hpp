@@ -179,6 +179,8 @@ class World {
     int fixed_step(double frame_time, BlobsStepStats* stats);
     int download_bodies(BlobsBodyState* st, uint64_t* handles, size_t cap);
     int download_colliders(BlobsColliderState* st, uint64_t* handles, size_t cap);
+    int query_circles(size_t n, const float* centre_xy, const float* radius, const BlobsQueryFilter* filter, uint64_t* offsets, uint64_t* hits,
+                      size_t hit_cap, size_t* n_hits);
     int debug_counts(BlobsDebugCounts* out) const;
     int debug_data(float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps);
     int read_body_vec(int which, float* xy, size_t cap);
@@ -377,6 +379,9 @@ class World {
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
     DevBuf<float2> d_forces;
     DevBuf<int> d_cellx, d_celly;
+    DevBuf<float2> d_qcentre;
+    DevBuf<float> d_qradius;
+    DevBuf<uint32_t> d_qcount, d_qoff, d_qhits;
 };
 
 }  // namespace blobs

@@ -285,6 +285,28 @@ class World:
         self._ck(self._lib.blobs_kernel_info(self._h, C.byref(k)))
         return k.as_dict()
 
+    def query_circles(self, centres, radii, flags=0, groups=None, exclude_collider=0, exclude_rigid_body=0, batch_world=0):
+        """n circle queries against the live collider snapshots (SpatialHash::query semantics, spatial.rs:155-195, plus the
+        QueryFilter the reference left as a stub). Returns (offsets[n+1], hits): hits[offsets[q]:offsets[q+1]] are the collider
+        handles of query q in ascending slot order. groups = (memberships, filter) or None."""
+        centres = np.ascontiguousarray(centres, dtype=np.float32).reshape(-1, 2)
+        n = len(centres)
+        radii = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float32), (n,)))
+        f = A.QueryFilter(flags=int(flags), has_groups=int(groups is not None), memberships=int(groups[0]) if groups else 0,
+                          filter=int(groups[1]) if groups else 0, exclude_collider=int(exclude_collider),
+                          exclude_rigid_body=int(exclude_rigid_body), batch_world=int(batch_world))
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        nh = C.c_size_t(0)
+        cap = max(16 * n, 64)
+        while True:
+            hits = np.zeros(cap, dtype=np.uint64)
+            rc = self._lib.blobs_query_circles(self._h, n, A.ptr(centres), A.ptr(radii), C.byref(f), A.ptr(offsets), A.ptr(hits), cap, C.byref(nh))
+            if rc == A.ERR_CAPACITY and nh.value > cap:
+                cap = nh.value
+                continue
+            self._ck(rc)
+            return offsets, hits[: nh.value]
+
     def debug_data(self):
         """Physics::debug_data (physics.rs:479-481, debug.rs:34-91) in one call: dict of float32 arrays in arena order -
         bodies (n, 6) and colliders (n, 6) as glam Affine2 (x_axis, y_axis, translation), collider_radius (n,),

@@ -251,6 +251,26 @@ int32_t blobs_debug_counts(const BlobsWorld* w, BlobsDebugCounts* out);
 int32_t blobs_debug_data(BlobsWorld* w, float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab,
                          const BlobsDebugCounts* caps);
 
+/* ---- scene queries: the reference's SpatialHash::query (spatial.rs:155-195) and the QueryPipeline / QueryFilter it
+ * left as stubs (lib.rs:167-187, query_filter.rs:27-108), served from the GPU broadphase table. n circle queries are answered
+ * in one call against the live collider snapshots: collider c is a hit iff |c.position - centre|^2 <= (radius + c.radius)^2
+ * (inclusive, as SpatialHash::query) and it passes the filter. Colliders whose parent body is gone are never reported.
+ * hits of query q = hits[offsets[q] .. offsets[q+1]), ascending slot order. If hit_cap is too small nothing is written,
+ * *n_hits holds the required capacity and BLOBS_ERR_CAPACITY is returned. Not available in strip mode. */
+enum { BLOBS_QUERY_EXCLUDE_FIXED = 1u << 1, BLOBS_QUERY_EXCLUDE_KINEMATIC = 1u << 2, BLOBS_QUERY_EXCLUDE_DYNAMIC = 1u << 3,
+       BLOBS_QUERY_EXCLUDE_SENSORS = 1u << 4, BLOBS_QUERY_EXCLUDE_SOLIDS = 1u << 5 };   /* QueryFilterFlags, query_filter.rs:6-25 */
+typedef struct BlobsQueryFilter {
+    uint32_t flags;                      /* BLOBS_QUERY_* */
+    int32_t has_groups;                  /* QueryFilter::groups is Some */
+    uint32_t memberships, filter;        /* ... tested with InteractionGroups::test against the collider's groups */
+    BlobsHandle exclude_collider;        /* 0 = None */
+    BlobsHandle exclude_rigid_body;      /* 0 = None */
+    uint32_t batch_world;                /* which batched world to query (BLOBS_PARAM_BATCH_WORLD), 0 = the single world */
+    uint32_t reserved;
+} BlobsQueryFilter;
+int32_t blobs_query_circles(BlobsWorld* w, size_t n, const float* centre_xy, const float* radius, const BlobsQueryFilter* filter_or_null,
+                            uint64_t* offsets /* n + 1 */, BlobsHandle* hits, size_t hit_cap, size_t* n_hits);
+
 /* ---- contact output ------------------------------------------------------------------------------ */
 enum { BLOBS_RECORD_OFF = 0, BLOBS_RECORD_PAIRS = 1, BLOBS_RECORD_EVENTS = 2 };
 /* collision_send / collision_recv, physics.rs:22-23,304-311. PAIRS records slots only. */

@@ -42,6 +42,12 @@ pub const BLOBS_RECORD_EVENTS: i32 = 2;
 #[link(name = "blobs_b200")]
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
+pub struct BlobsQueryFilter { pub flags: u32, pub has_groups: i32, pub memberships: u32, pub filter: u32, pub exclude_collider: BlobsHandle,
+                              pub exclude_rigid_body: BlobsHandle, pub batch_world: u32, pub reserved: u32 }
+pub const BLOBS_ERR_CAPACITY: i32 = 9;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
 pub struct BlobsDebugCounts { pub bodies: u64, pub joints: u64, pub colliders: u64, pub springs: u64 }
 
 extern "C" {
@@ -70,6 +76,8 @@ extern "C" {
     pub fn blobs_events_drain(w: *mut BlobsWorld, buf: *mut BlobsCollisionEvent, cap: usize, n: *mut usize) -> i32;
     pub fn blobs_download_bodies(w: *mut BlobsWorld, states: *mut BlobsBodyState, handles: *mut BlobsHandle, cap: usize) -> i32;
     pub fn blobs_download_colliders(w: *mut BlobsWorld, states: *mut BlobsColliderState, handles: *mut BlobsHandle, cap: usize) -> i32;
+    pub fn blobs_query_circles(w: *mut BlobsWorld, n: usize, centre_xy: *const c_float, radius: *const c_float, filter: *const BlobsQueryFilter,
+                               offsets: *mut u64, hits: *mut BlobsHandle, hit_cap: usize, n_hits: *mut usize) -> i32;
     pub fn blobs_debug_counts(w: *const BlobsWorld, out: *mut BlobsDebugCounts) -> i32;
     pub fn blobs_debug_data(w: *mut BlobsWorld, body_xform: *mut c_float, joint_ab: *mut c_float, col_xform: *mut c_float, col_radius: *mut c_float,
                             spring_ab: *mut c_float, caps: *const BlobsDebugCounts) -> i32;

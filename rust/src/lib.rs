@@ -93,6 +93,25 @@ impl Physics {
     }
     pub fn remove_rbd(&mut self, h: RigidBodyHandle) { unsafe { blobs_body_remove(self.w, h.0.to_bits()) }; }     // physics.rs:163-172 (missing body: event only)
     pub fn remove_col(&mut self, h: ColliderHandle) { unsafe { blobs_collider_remove(self.w, h.0.to_bits()) }; } // physics.rs:159-161
+    /// What SpatialHash::query (spatial.rs:155-195) and QueryPipeline::intersection_with_shape (lib.rs:177-187, a stub in the
+    /// reference) are for: every collider whose snapshot circle touches the query circle and passes `filter`, ascending slot order.
+    pub fn query_circle(&mut self, position: Vec2, radius: f32, filter: QueryFilter) -> Vec<ColliderHandle> {
+        let f = BlobsQueryFilter { flags: filter.flags, has_groups: filter.groups.is_some() as i32,
+            memberships: filter.groups.map(|g| g.memberships).unwrap_or(0), filter: filter.groups.map(|g| g.filter).unwrap_or(0),
+            exclude_collider: filter.exclude_collider.map(|h| h.0.to_bits()).unwrap_or(0),
+            exclude_rigid_body: filter.exclude_rigid_body.map(|h| h.0.to_bits()).unwrap_or(0), batch_world: 0, reserved: 0 };
+        let (c, r) = ([position.x, position.y], [radius]);
+        let mut off = [0u64; 2];
+        let mut n = 0usize;
+        let mut hits = vec![0u64; 64];
+        loop {
+            let rc = unsafe { blobs_query_circles(self.w, 1, c.as_ptr(), r.as_ptr(), &f, off.as_mut_ptr(), hits.as_mut_ptr(), hits.len(), &mut n) };
+            if rc == BLOBS_ERR_CAPACITY && n > hits.len() { hits.resize(n, 0); continue; }
+            self.ck(rc);
+            break;
+        }
+        hits[..n].iter().map(|&h| ColliderHandle(idx(h))).collect()
+    }
     /// Physics::debug_data (physics.rs:479-481): one library call, lists in arena order (debug.rs:34-91)
     pub fn debug_data(&mut self) -> DebugData {
         let mut c = BlobsDebugCounts::default();
@@ -172,3 +191,8 @@ pub struct DebugCollider { pub transform: Affine2, pub radius: f32 }
 pub struct DebugJoint { pub body_a: Vec2, pub body_b: Vec2 }
 pub struct DebugSpring { pub body_a: Vec2, pub body_b: Vec2 }
 pub struct DebugData { pub bodies: Vec<DebugRigidBody>, pub joints: Vec<DebugJoint>, pub colliders: Vec<DebugCollider>, pub springs: Vec<DebugSpring> }
+
+/// query_filter.rs:74-87 (the closure predicate of the reference is applied by the caller on the returned handles);
+/// flags: QueryFilterFlags bits (query_filter.rs:6-25), e.g. EXCLUDE_SENSORS = 1 << 4
+#[derive(Copy, Clone, Default)]
+pub struct QueryFilter { pub flags: u32, pub groups: Option<InteractionGroups>, pub exclude_collider: Option<ColliderHandle>, pub exclude_rigid_body: Option<RigidBodyHandle> }

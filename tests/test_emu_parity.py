@@ -37,6 +37,7 @@ CASES = [
     ("batched-worlds", T.test_batched_independent_worlds, {}),
     ("soft-blobs-fused", T.test_soft_blobs_springs_and_joints, dict(fused=1)),
     ("debug-data", T.test_debug_data_one_call_snapshot, {}),
+    ("scene-queries", T.test_scene_queries_served_from_the_grid, {}),
     ("physics-api-balls", P.test_balls_demo_flow, {}),
     ("physics-api-joints-springs-panics", P.test_joints_springs_and_panics, {}),
 ]

@@ -576,3 +576,83 @@ def test_debug_data_one_call_snapshot():
     assert np.allclose(d["colliders"][:, :4], want_m, atol=1e-6)
     assert np.allclose(d["colliders"][5, :4], [0, 1, -1, 0], atol=1e-6)          # M(0) * the 90-degree offset
     assert np.allclose(d["collider_radius"], [0.3, 0.3, 0.25, 0.2, 0.2, 0.35])
+
+
+def _brute_force_query(cx, cy, qr, px, py, pr):
+    """SpatialHash::query's hit test (spatial.rs:171-177) over ALL points, in f32 op by op."""
+    f = np.float32
+    dx, dy = (px - f(cx)).astype(f), (py - f(cy)).astype(f)
+    d2 = ((dx * dx).astype(f) + (dy * dy).astype(f)).astype(f)
+    dist = (f(qr) + pr).astype(f)
+    return d2 <= (dist * dist).astype(f)
+
+
+def test_scene_queries_served_from_the_grid():
+    """blobs_query_circles (SURVEY 8f: SpatialHash::query, spatial.rs:155-195 + the stubbed QueryFilter): hits from the GPU
+    broadphase table == brute force over every live collider snapshot with the reference's inclusive f32 hit test, for radii
+    from 0 to several cells; == the oracle's SpatialHash::query where that one's 3x3 window is complete; every filter."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    sc = S.cfg1(seed=4)
+    g, o = _pair(sc.gravity, sc)
+    extra = []
+    for w in (g, o):
+        hs = [sphere(w, (0.5, 0.5), r=0.15, body_type=A.BODY_STATIC), sphere(w, (-1.0, 2.0), r=0.12, body_type=A.BODY_KINEMATIC_POSITION),
+              sphere(w, (1.5, 3.0), r=0.18, col={"is_sensor": 1}), sphere(w, (-2.0, 4.0), r=0.1, col={"memberships": 0b0100, "filter": 0b0010})]
+        extra.append(hs)
+    assert extra[0] == extra[1]
+    (static_b, static_c), (kin_b, kin_c), (sens_b, sens_c), (grp_b, grp_c) = extra[0]
+    for _ in range(12):
+        g.step(1 / 60)
+        o.step(1 / 60)
+    oc, och = o.download_colliders()
+    live = och != 0
+    px, py = oc["desc"]["absolute_transform"]["translation"]["x"][live], oc["desc"]["absolute_transform"]["translation"]["y"][live]
+    pr, handles = oc["desc"]["radius"][live], och[live]
+    rng = np.random.default_rng(11)
+    nq = 300
+    centres = np.stack([rng.uniform(-7, 7, nq), rng.uniform(-8, 8, nq)], axis=1).astype(np.float32)
+    centres[:20] = np.stack([px[:20], py[:20]], axis=1)          # some queries exactly on a collider
+    radii = rng.choice([0.0, 0.05, 0.3, 1.0, 3.0], nq).astype(np.float32)
+    radii[5], radii[6] = -1.0, np.nan                            # no hits, no crash
+    off, hits = g.query_circles(centres, radii)
+    assert off[0] == 0 and off[-1] == len(hits)
+    total = 0
+    for q in range(nq):
+        want = handles[_brute_force_query(centres[q, 0], centres[q, 1], radii[q], px, py, pr)] if radii[q] >= 0 else handles[:0]
+        got = hits[off[q]:off[q + 1]]
+        assert np.array_equal(got, np.sort(want)), f"query {q}: centre {centres[q]} r {radii[q]}: {len(got)} hits, brute force {len(want)}"
+        total += len(got)
+    assert total > 2000
+    # the reference's own query: identical where its 3x3 window cannot miss anything (query radius + point radius <= cell size)
+    sh = oracle_py.OracleSpatialHash(2.0)
+    for i in range(len(px)):
+        sh.insert_with_id(int(handles[i]), (float(px[i]), float(py[i])), float(pr[i]))
+    for q in range(0, nq, 7):
+        if not (0 <= radii[q] <= 1.0):
+            continue
+        ref_ids = sorted(pid for pid, _ in sh.query((float(centres[q, 0]), float(centres[q, 1])), float(radii[q])))
+        assert ref_ids == [int(h) for h in hits[off[q]:off[q + 1]]]
+    # filters (query_filter.rs:27-108), on one big query that sees everything
+    everything = lambda **kw: set(int(h) for h in g.query_circles([[0.0, 0.0]], [100.0], **kw)[1])
+    full = everything()
+    assert full == set(int(h) for h in handles)
+    assert everything(flags=A.QUERY_EXCLUDE_SENSORS) == full - {sens_c}
+    assert everything(flags=A.QUERY_EXCLUDE_SOLIDS) == {sens_c}
+    assert everything(flags=A.QUERY_EXCLUDE_FIXED) == full - {static_c}
+    assert everything(flags=A.QUERY_EXCLUDE_KINEMATIC) == full - {kin_c}
+    assert everything(flags=A.QUERY_EXCLUDE_DYNAMIC) == {static_c, kin_c}
+    assert everything(flags=A.QUERY_EXCLUDE_DYNAMIC | A.QUERY_EXCLUDE_KINEMATIC) == {static_c}            # ONLY_FIXED
+    assert everything(exclude_collider=grp_c) == full - {grp_c}
+    assert everything(exclude_rigid_body=kin_b) == full - {kin_c}
+    assert everything(groups=(0b0010, 0b0100)) == full                                                     # compatible with the special collider too
+    assert everything(groups=(0b0001, 0b0001)) == full - {grp_c}                                           # groups.rs:52-57 fails for it
+    # capacity protocol of the C ABI
+    import ctypes as C
+    offs = np.zeros(2, dtype=np.uint64)
+    nh = C.c_size_t(0)
+    c1, r1 = np.array([[0.0, 0.0]], dtype=np.float32), np.array([100.0], dtype=np.float32)
+    small = np.zeros(4, dtype=np.uint64)
+    rc = g._lib.blobs_query_circles(g._h, 1, A.ptr(c1), A.ptr(r1), None, A.ptr(offs), A.ptr(small), 4, C.byref(nh))
+    assert rc == A.ERR_CAPACITY and nh.value == len(full) and not small.any()

@@ -115,6 +115,14 @@ class DebugCounts(C.Structure):
     _fields_ = [("bodies", C.c_uint64), ("joints", C.c_uint64), ("colliders", C.c_uint64), ("springs", C.c_uint64)]
 
 
+class PhysicsEvent(C.Structure):  # events.rs:42-50
+    _fields_ = [("real_time", C.c_double), ("unpaused_time", C.c_double), ("position", Vec2), ("has_position", C.c_int32),
+                ("severity", C.c_int32), ("col_handle", C.c_uint64), ("rbd_handle", C.c_uint64), ("message", C.c_char * 64)]
+
+
+SEVERITY_TRACE, SEVERITY_DEBUG, SEVERITY_INFO, SEVERITY_WARN, SEVERITY_ERROR, SEVERITY_CRITICAL = range(6)
+
+
 def body_descs(n):
     """n default RigidBodyBuilder::new() descriptors (rigid_body.rs:303-318)."""
     d = np.zeros(n, dtype=BODY_DESC)

@@ -62,6 +62,16 @@ SIGNATURES = {
     "blobs_kernel_info": (C.c_int32, [_vp, C.POINTER(A.KernelInfo)]),
     "blobs_profile_enable": (C.c_int32, [_vp, C.c_int32]),
     "blobs_profile_read": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
+    "blobs_perf_counter": (None, [C.c_char_p, C.c_uint64]),
+    "blobs_perf_counter_inc": (None, [C.c_char_p, C.c_uint64]),
+    "blobs_perf_counters_new_frame": (None, [C.c_double]),
+    "blobs_perf_counters_reset": (None, []),
+    "blobs_perf_counter_get": (C.c_int32, [C.c_char_p, _u64p, C.POINTER(C.c_double)]),
+    "blobs_perf_counter_count": (C.c_uint64, []),
+    "blobs_perf_counter_at": (C.c_int32, [C.c_uint64, C.c_char_p, C.c_size_t, _u64p, C.POINTER(C.c_double)]),
+    "blobs_event_history_len": (C.c_uint64, []),
+    "blobs_event_history_get": (C.c_int32, [C.c_uint64, C.POINTER(A.PhysicsEvent)]),
+    "blobs_event_history_clear": (None, []),
     "blobs_strip_unique_id": (C.c_int32, [_vp]),
     "blobs_strip_configure": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, C.c_uint32, C.c_uint32]),
     "blobs_strip_owned": (C.c_int32, [_vp, _vp, C.c_size_t]),

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <new>
 
+#include "perf.hpp"
 #include "world.hpp"
 
 using blobs::World;
@@ -137,6 +138,49 @@ int32_t blobs_pairs_drain(BlobsWorld* w, uint32_t* a, uint32_t* b, size_t cap, s
 int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.kernel_info(out); }
 int32_t blobs_profile_enable(BlobsWorld* w, int32_t on) { W_OR_INVALID(w); return w->w.profile_enable(on); }
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n) { W_OR_INVALID(w); return w->w.profile_read(ms, launches, n); }
+
+void blobs_perf_counter(const char* name, uint64_t count) { if (name) blobs::PerfCounters::global().update(name, count); }
+void blobs_perf_counter_inc(const char* name, uint64_t inc) { if (name) blobs::PerfCounters::global().inc(name, inc); }
+void blobs_perf_counters_new_frame(double delta) { blobs::PerfCounters::global().new_frame(delta); }
+void blobs_perf_counters_reset(void) { blobs::PerfCounters::global().reset(); }
+int32_t blobs_perf_counter_get(const char* name, uint64_t* count, double* avg) {
+    if (!name) return BLOBS_ERR_INVALID;
+    const blobs::PerfCounter c = blobs::PerfCounters::global().get(name);
+    if (count) *count = c.count;
+    if (avg) *avg = c.decayed_average;
+    return BLOBS_OK;
+}
+uint64_t blobs_perf_counter_count(void) { return blobs::PerfCounters::global().size(); }
+int32_t blobs_perf_counter_at(uint64_t i, char* name, size_t name_cap, uint64_t* count, double* avg) {
+    std::string n;
+    blobs::PerfCounter c;
+    if (!blobs::PerfCounters::global().at((size_t)i, &n, &c)) return BLOBS_ERR_INVALID;
+    if (name) {
+        if (n.size() + 1 > name_cap) return BLOBS_ERR_CAPACITY;
+        std::memcpy(name, n.c_str(), n.size() + 1);
+    }
+    if (count) *count = c.count;
+    if (avg) *avg = c.decayed_average;
+    return BLOBS_OK;
+}
+
+uint64_t blobs_event_history_len(void) { return blobs::EventHistory::global().size(); }
+int32_t blobs_event_history_get(uint64_t i, BlobsPhysicsEvent* out) {
+    if (!out) return BLOBS_ERR_INVALID;
+    blobs::PhysicsEventRec e;
+    if (!blobs::EventHistory::global().at((size_t)i, &e)) return BLOBS_ERR_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    out->real_time = e.real_time;
+    out->unpaused_time = e.unpaused_time;
+    out->position = BlobsVec2{e.px, e.py};
+    out->has_position = e.has_position ? 1 : 0;
+    out->severity = e.severity;
+    out->col_handle = e.col_handle;
+    out->rbd_handle = e.rbd_handle;
+    snprintf(out->message, sizeof(out->message), "%s", e.message.c_str());
+    return BLOBS_OK;
+}
+void blobs_event_history_clear(void) { blobs::EventHistory::global().clear(); }
 
 int32_t blobs_strip_unique_id(uint8_t* out128) {
     if (!out128) return BLOBS_ERR_INVALID;

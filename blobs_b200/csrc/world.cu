@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include "world.hpp"
 #include "kernels.cuh"
+#include "perf.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -328,13 +329,31 @@ void World::update_mass_and_inertia(uint32_t bs) {
 }
 
 int World::body_remove(uint64_t h) {
-    if (!bodies.valid(h)) return fail(BLOBS_ERR_STALE_HANDLE, "removing a non-existent rigid body");  // rigid_body.rs:266-275
+    if (!bodies.valid(h)) {   // rigid_body.rs:266-275: not a panic, an Error entry in the event history
+        PhysicsEventRec ev;
+        ev.message = "removing a non-existent rigid body";
+        ev.severity = 4;
+        ev.rbd_handle = h;
+        EventHistory::global().push(std::move(ev));
+        return fail(BLOBS_ERR_STALE_HANDLE, "removing a non-existent rigid body");
+    }
     const uint32_t s = h_slot(h);
     for (uint64_t ch : hb[s].colliders)
         if (cols.valid(ch)) cols.remove_slot(h_slot(ch));  // remove_ignoring_parent (physics.rs:165-167)
     hb[s] = HBody{};
     bodies.remove_slot(s);
     topo_dirty = bp_dirty = true;
+    return BLOBS_OK;
+}
+
+// position of one body as the host would see it now (staged writes applied); no topology work
+int World::peek_position(uint32_t slot, float2* out) {
+    if (shadow_valid && slot < sh_pos.size()) { *out = sh_pos[slot]; return BLOBS_OK; }
+    int rc = flush_writes();
+    if (rc) return rc;
+    if (slot >= pos.cap) return BLOBS_ERR_INVALID;
+    CU(cudaMemcpyAsync(out, pos.d + slot, sizeof(float2), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
     return BLOBS_OK;
 }
 
@@ -504,6 +523,14 @@ int World::collider_remove(uint64_t h) {
         b.cols.erase(std::remove(b.cols.begin(), b.cols.end(), s), b.cols.end());
         update_mass_and_inertia(bs);
         if (b.colliders.empty()) {  // "rbd removed because colliders.len() == 0" (collider.rs:143-158)
+            PhysicsEventRec ev;
+            ev.message = "rbd removed because colliders.len() == 0";
+            ev.severity = 2;
+            ev.col_handle = h;
+            ev.rbd_handle = parent;
+            float2 p;
+            if (peek_position(bs, &p) == BLOBS_OK) { ev.has_position = true; ev.px = p.x; ev.py = p.y; }
+            EventHistory::global().push(std::move(ev));
             hb[bs] = HBody{};
             bodies.remove_slot(bs);
         }
@@ -898,8 +925,14 @@ int World::rebuild_broadphase() {
 }
 
 // ---------------------------------------------------------------------------------------------- stepping
+// profiler range per kernel class: the reference's tracy span names where the kernel replaces a spanned function
+// (physics.rs:242 "brute_force_collisions", physics.rs:324 "update positions"), descriptive names otherwise
+static const char* const kclass_span[KC_COUNT] = {"brute_force_collisions", "broadphase scan", "broadphase scatter", "springs", "solve_fixed_joints",
+                                                  "update positions", "other", "strip pack", "strip ghosts", "strip exchange", "crowded contacts"};
+
 template <class F>
 int World::timed(KClass k, F&& f) {
+    Span span(kclass_span[k]);
     EvPair* ep = nullptr;
     EvPair cap{};
     if (profiling && capturing) {
@@ -985,6 +1018,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
 
 // One Physics::integrate call: replay the captured graph when nothing structural changed, else (re)capture it.
 int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
+    Span span("integrate");   // physics.rs:92,398
     // measured on 2x B200: replaying a graph that contains the grouped ncclSend/ncclRecv is ~25 % SLOWER than plain launches,
     // so strip mode keeps plain launches
     if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || strip_on) return integrate(nsub, delta, last);
@@ -1026,6 +1060,7 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
 }
 
 int World::launch_substep(const SubstepParams& P_in) {
+    Span span("substep");     // physics.rs:402
     SubstepParams P = P_in;
     // contact-list overflows: deferred to k_crowded (one warp per body) when such bodies are expected, else resolved inline
     // Automatic mode stays off in strip mode for now: on real GPUs the pooled / crowded kernels were validated on one device
@@ -1202,6 +1237,9 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     cudaEventElapsedTime(&ms, ev_step0, ev_step1);
     if (profiling) { int rc = collect_profile(); if (rc) return rc; }
     graphs_launched.clear();
+    // perf_counter_inc("collisions", count) once per brute_force_collisions call (physics.rs:316); the per-substep counts of this
+    // API call arrive here as one sum. In strip mode every rank adds the pairs it counted (its share of the world's).
+    if (substeps_run && collisions_enabled) PerfCounters::global().inc("collisions", h_stats->collisions);
     last_max_ghosts = std::max(last_max_ghosts, h_stats->max_ghosts);
     last_max_migrants = std::max(last_max_migrants, h_stats->max_migrants);
     if (out) {
@@ -1236,6 +1274,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
 }
 
 int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
+    Span span("step");        // physics.rs:79
     if (collisions_enabled && use_spatial_hash && substeps > 0) return fail(BLOBS_ERR_SPATIAL_HASH, "spatial collisions not supported right now");
     int rc = flush();
     if (rc) return rc;
@@ -1264,6 +1303,7 @@ int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
 
 // Physics::fixed_step (physics.rs:84-99)
 int World::fixed_step(double frame_time, BlobsStepStats* stats) {
+    Span span("step");        // physics.rs:85
     if (collisions_enabled && use_spatial_hash && substeps > 0) return fail(BLOBS_ERR_SPATIAL_HASH, "spatial collisions not supported right now");
     int rc = flush();
     if (rc) return rc;

@@ -220,6 +220,7 @@ class World {
     int launch_substep(const SubstepParams& P_in);
     int finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_run);
     int ensure_shadow();
+    int peek_position(uint32_t slot, float2* out);
     void update_mass_and_inertia(uint32_t bslot);
     BodyWrite& stage(uint32_t slot);
     int flush_writes();

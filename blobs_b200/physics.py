@@ -184,6 +184,126 @@ class CollisionEvent:  # lib.rs:146-153
     impact_vel_b: tuple
 
 
+_f32 = np.float32
+
+
+class RigidBodyMut:
+    """What `physics.get_mut_rbd(handle)` hands out (physics.rs:109-111): a host mirror of ONE RigidBody (rigid_body.rs:41-74)
+    whose `pub` fields can be assigned and whose methods are the reference's (rigid_body.rs:130-214), evaluated on the host
+    in f32 exactly as written there. The body itself lives in HBM: `commit()` (or leaving the `with` block) compares the
+    mirror with what was downloaded and writes back only the fields that changed (one blobs_body_set with a field mask) -
+    the dirty tracking a `&mut RigidBody` borrow needs when the storage is on the GPU."""
+
+    _VEC = {"position": A.BODY_POSITION, "position_old": A.BODY_POSITION_OLD, "acceleration": A.BODY_ACCELERATION,
+            "calculated_velocity": A.BODY_CALC_VELOCITY, "scale": A.BODY_SCALE, "center_of_mass": A.BODY_CENTER_OF_MASS}
+    _SCALAR = {"rotation": A.BODY_ROTATION, "angular_velocity": A.BODY_ANGULAR_VELOCITY, "torque": A.BODY_TORQUE,
+               "calculated_mass": A.BODY_MASS, "inertia": A.BODY_INERTIA, "gravity_mod": A.BODY_GRAVITY_MOD}
+
+    def __init__(self, world, handle, state):
+        self._w, self._handle = world, handle
+        self._st0 = state.copy()
+        for k in self._VEC:
+            setattr(self, k, (_f32(state[k]["x"]), _f32(state[k]["y"])))
+        for k in self._SCALAR:
+            setattr(self, k, _f32(state[k]))
+        self.velocity_request = (_f32(state["velocity_request"]["x"]), _f32(state["velocity_request"]["y"])) if state["has_velocity_request"] else None
+        self.body_type = int(state["body_type"])
+        self.user_data = int(state["user_data_lo"]) | (int(state["user_data_hi"]) << 64)
+
+    # ---- rigid_body.rs:130-214, f32 arithmetic in the reference's order (glam Vec2 ops are per-component scalar ops)
+    def is_static(self):
+        return self.body_type == RigidBodyType.Static
+
+    def is_dynamic(self):
+        return self.body_type == RigidBodyType.Dynamic
+
+    def is_kinematic(self):
+        return self.body_type in (RigidBodyType.KinematicPositionBased, RigidBodyType.KinematicVelocityBased)
+
+    def get_velocity(self):  # :186-188
+        return self.calculated_velocity
+
+    def set_velocity(self, velocity):  # :182-184
+        self.velocity_request = (_f32(velocity[0]), _f32(velocity[1]))
+
+    def add_velocity(self, velocity):  # :151-153
+        v = self.get_velocity()
+        self.set_velocity((v[0] + _f32(velocity[0]), v[1] + _f32(velocity[1])))
+
+    def apply_impulse(self, impulse):  # :130-135
+        if not self.is_static():
+            self.add_velocity((_f32(impulse[0]) / self.calculated_mass, _f32(impulse[1]) / self.calculated_mass))
+
+    def _lever_arm(self, world_point):
+        cx, cy = self.position[0] + self.center_of_mass[0], self.position[1] + self.center_of_mass[1]
+        return _f32(world_point[0]) - cx, _f32(world_point[1]) - cy
+
+    @staticmethod
+    def _perp_dot(a, b):  # glam Vec2::perp_dot: a.x * b.y - a.y * b.x
+        return a[0] * _f32(b[1]) - a[1] * _f32(b[0])
+
+    def apply_impulse_at_point(self, impulse, world_point):  # :137-149
+        if not self.is_static():
+            self.apply_impulse(impulse)
+            self.angular_velocity = self.angular_velocity + self._perp_dot(self._lever_arm(world_point), impulse) / self.inertia
+
+    def apply_force(self, force):  # :155-160
+        if not self.is_static():
+            self.acceleration = (self.acceleration[0] + _f32(force[0]) / self.calculated_mass,
+                                 self.acceleration[1] + _f32(force[1]) / self.calculated_mass)
+
+    def apply_force_at_point(self, force, world_point):  # :162-172
+        if not self.is_static():
+            self.apply_force(force)
+            self.torque = self.torque + self._perp_dot(self._lever_arm(world_point), force)
+
+    def apply_torque_at_point(self, force, world_point):  # :174-180
+        if not self.is_static():
+            self.torque = self.torque + self._perp_dot(self._lever_arm(world_point), force)
+
+    def accelerate(self, a):  # :207-209
+        self.acceleration = (self.acceleration[0] + _f32(a[0]), self.acceleration[1] + _f32(a[1]))
+
+    # ---- write-back
+    def commit(self):
+        st, mask = self._st0.copy(), 0
+        for k, bit in self._VEC.items():
+            v = getattr(self, k)
+            if _f32(v[0]).tobytes() != _f32(self._st0[k]["x"]).tobytes() or _f32(v[1]).tobytes() != _f32(self._st0[k]["y"]).tobytes():
+                st[k]["x"], st[k]["y"] = v
+                mask |= bit
+        for k, bit in self._SCALAR.items():
+            if _f32(getattr(self, k)).tobytes() != _f32(self._st0[k]).tobytes():
+                st[k] = getattr(self, k)
+                mask |= bit
+        had = bool(self._st0["has_velocity_request"])
+        old = (_f32(self._st0["velocity_request"]["x"]), _f32(self._st0["velocity_request"]["y"])) if had else None
+        new = None if self.velocity_request is None else (_f32(self.velocity_request[0]), _f32(self.velocity_request[1]))
+        if new != old:
+            st["has_velocity_request"] = 0 if new is None else 1
+            if new is not None:
+                st["velocity_request"]["x"], st["velocity_request"]["y"] = new
+            mask |= A.BODY_VELOCITY_REQUEST
+        if self.body_type != int(self._st0["body_type"]):
+            st["body_type"] = self.body_type
+            mask |= A.BODY_TYPE
+        if self.user_data != (int(self._st0["user_data_lo"]) | (int(self._st0["user_data_hi"]) << 64)):
+            st["user_data_lo"], st["user_data_hi"] = self.user_data & 0xFFFFFFFFFFFFFFFF, self.user_data >> 64
+            mask |= A.BODY_USER_DATA
+        if mask:
+            self._w.body_set(self._handle, st, mask)
+            self._st0 = st
+        return mask
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, *_):
+        if exc_type is None:
+            self.commit()
+        return False
+
+
 def _body_desc(rbd):
     d = A.body_descs(1)
     d["position"]["x"], d["position"]["y"] = rbd.position
@@ -316,6 +436,10 @@ class Physics:
                 "velocity": (float(s["calculated_velocity"]["x"]), float(s["calculated_velocity"]["y"])),
                 "angular_velocity": float(s["angular_velocity"]), "rotation": float(s["rotation"]),
                 "center_of_mass": (float(s["center_of_mass"]["x"]), float(s["center_of_mass"]["y"])), "mass": float(s["calculated_mass"])}
+
+    def get_mut_rbd(self, handle):  # physics.rs:109-111 -> Option<&mut RigidBody>: a host mirror with dirty tracking
+        s = self.get_rbd(handle)
+        return None if s is None else RigidBodyMut(self._w, handle, s)
 
     def set_rbd(self, handle, state, mask):  # get_mut_rbd physics.rs:109-111: write back the fields in `mask`
         self._w.body_set(handle, state, mask)

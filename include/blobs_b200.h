@@ -296,6 +296,39 @@ int32_t blobs_profile_enable(BlobsWorld* w, int32_t on);
  * [7]=strip pack, [8]=strip ghost binning/scatter/hand-over, [9]=NCCL ghost exchange */
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n);
 
+/* ---- perf counters: the reference's process-global registry (perf_counters.rs:3-87). blobs_step* feeds "collisions"
+ * (physics.rs:316); the host application calls new_frame(delta) once per frame (demo/src/main.rs:223) and reads
+ * (count, decayed_average) pairs for its perf panel (main.rs:291-300). Not per world: one registry per process, like the
+ * reference's static. Kernels are also bracketed by profiler (NVTX) ranges named after the reference's tracy spans
+ * ("step", "integrate", "substep", "brute_force_collisions", "update positions"; physics.rs:79,92,242,324,398,402). */
+void blobs_perf_counter(const char* name, uint64_t count);                      /* perf_counter, perf_counters.rs:66-69 */
+void blobs_perf_counter_inc(const char* name, uint64_t inc);                    /* perf_counter_inc, perf_counters.rs:71-76 */
+void blobs_perf_counters_new_frame(double delta);                               /* perf_counters_new_frame, perf_counters.rs:56-59 */
+void blobs_perf_counters_reset(void);                                           /* reset_perf_counters, perf_counters.rs:61-64 */
+int32_t blobs_perf_counter_get(const char* name, uint64_t* count, double* decayed_average); /* get_perf_counter, perf_counters.rs:78-81: (0, 0.0) if absent */
+uint64_t blobs_perf_counter_count(void);                                        /* PerfCounters::global().counters.len() */
+/* i-th counter in name order (the reference iterates a HashMap: unordered); BLOBS_ERR_INVALID past the end, BLOBS_ERR_CAPACITY if the
+ * name (with its terminating NUL) does not fit name_cap */
+int32_t blobs_perf_counter_at(uint64_t i, char* name, size_t name_cap, uint64_t* count, double* decayed_average);
+
+/* ---- soft-error history: the reference's process-global event ring (events.rs:20-64; at most 1000 entries, oldest dropped).
+ * Two messages exist: "removing a non-existent rigid body" (Error; remove_rbd on a stale handle, rigid_body.rs:266-275 - the call
+ * itself returns BLOBS_ERR_STALE_HANDLE, which the shim ignores like the reference) and "rbd removed because colliders.len() == 0"
+ * (Info; removing a body's last collider removes the body, collider.rs:143-158). The reference never reads the ring back; the
+ * accessors below are what a debug panel would need. */
+enum { BLOBS_SEVERITY_TRACE = 0, BLOBS_SEVERITY_DEBUG, BLOBS_SEVERITY_INFO, BLOBS_SEVERITY_WARN, BLOBS_SEVERITY_ERROR, BLOBS_SEVERITY_CRITICAL }; /* events.rs:52-60 */
+typedef struct BlobsPhysicsEvent {       /* PhysicsEvent, events.rs:42-50 */
+    double real_time, unpaused_time;     /* TimeData (never advanced by the reference: always 0) */
+    BlobsVec2 position;
+    int32_t has_position;
+    int32_t severity;
+    BlobsHandle col_handle, rbd_handle;  /* 0 = None */
+    char message[64];
+} BlobsPhysicsEvent;
+uint64_t blobs_event_history_len(void);
+int32_t blobs_event_history_get(uint64_t i, BlobsPhysicsEvent* out);   /* i = 0 is the oldest entry still held */
+void blobs_event_history_clear(void);
+
 /* ---- multi-GPU: one large world split into vertical strips, one rank (process + GPU) per strip (BASELINE config #5).
  * No reference counterpart (the reference is single-threaded). Every rank builds the SAME full scene (identical handles),
  * then calls blobs_strip_configure; from then on blobs_step* is collective: each rank advances the bodies whose collider

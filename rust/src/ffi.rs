@@ -39,7 +39,6 @@ pub const BLOBS_PARAM_JOINT_ITERATIONS: i32 = 3; pub const BLOBS_PARAM_USE_SPATI
 pub const BLOBS_PARAM_ACCUMULATOR: i32 = 6; pub const BLOBS_PARAM_TIME: i32 = 7; pub const BLOBS_PARAM_OLD_DT: i32 = 8; pub const BLOBS_PARAM_CELL_SIZE: i32 = 9;
 pub const BLOBS_RECORD_EVENTS: i32 = 2;
 
-#[link(name = "blobs_b200")]
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct BlobsQueryFilter { pub flags: u32, pub has_groups: i32, pub memberships: u32, pub filter: u32, pub exclude_collider: BlobsHandle,
@@ -50,6 +49,20 @@ pub const BLOBS_ERR_CAPACITY: i32 = 9;
 #[derive(Clone, Copy, Default)]
 pub struct BlobsDebugCounts { pub bodies: u64, pub joints: u64, pub colliders: u64, pub springs: u64 }
 
+/// PhysicsEvent (events.rs:42-50) as the library stores it
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct BlobsPhysicsEvent { pub real_time: c_double, pub unpaused_time: c_double, pub position: BlobsVec2, pub has_position: i32, pub severity: i32,
+                               pub col_handle: BlobsHandle, pub rbd_handle: BlobsHandle, pub message: [c_char; 64] }
+
+// field mask of blobs_body_set (include/blobs_b200.h)
+pub const BLOBS_BODY_POSITION: u32 = 1 << 0; pub const BLOBS_BODY_POSITION_OLD: u32 = 1 << 1; pub const BLOBS_BODY_ACCELERATION: u32 = 1 << 2;
+pub const BLOBS_BODY_VELOCITY_REQUEST: u32 = 1 << 3; pub const BLOBS_BODY_CALC_VELOCITY: u32 = 1 << 4; pub const BLOBS_BODY_ROTATION: u32 = 1 << 5;
+pub const BLOBS_BODY_ANGULAR_VELOCITY: u32 = 1 << 6; pub const BLOBS_BODY_TORQUE: u32 = 1 << 7; pub const BLOBS_BODY_MASS: u32 = 1 << 8;
+pub const BLOBS_BODY_INERTIA: u32 = 1 << 9; pub const BLOBS_BODY_GRAVITY_MOD: u32 = 1 << 10; pub const BLOBS_BODY_TYPE: u32 = 1 << 11;
+pub const BLOBS_BODY_USER_DATA: u32 = 1 << 12; pub const BLOBS_BODY_SCALE: u32 = 1 << 13; pub const BLOBS_BODY_CENTER_OF_MASS: u32 = 1 << 14;
+
+#[link(name = "blobs_b200")]
 extern "C" {
     pub fn blobs_world_create(params: *const BlobsParams, out: *mut *mut BlobsWorld) -> i32;
     pub fn blobs_world_destroy(w: *mut BlobsWorld) -> i32;
@@ -83,4 +96,16 @@ extern "C" {
                             spring_ab: *mut c_float, caps: *const BlobsDebugCounts) -> i32;
     pub fn blobs_body_slots(w: *const BlobsWorld, out: *mut u64) -> i32;
     pub fn blobs_collider_slots(w: *const BlobsWorld, out: *mut u64) -> i32;
+    // perf_counters.rs:52-87 (process-global registry; blobs_step* feeds "collisions")
+    pub fn blobs_perf_counter(name: *const c_char, count: u64);
+    pub fn blobs_perf_counter_inc(name: *const c_char, inc: u64);
+    pub fn blobs_perf_counters_new_frame(delta: c_double);
+    pub fn blobs_perf_counters_reset();
+    pub fn blobs_perf_counter_get(name: *const c_char, count: *mut u64, decayed_average: *mut c_double) -> i32;
+    pub fn blobs_perf_counter_count() -> u64;
+    pub fn blobs_perf_counter_at(i: u64, name: *mut c_char, name_cap: usize, count: *mut u64, decayed_average: *mut c_double) -> i32;
+    // events.rs:20-64 (process-global soft-error ring)
+    pub fn blobs_event_history_len() -> u64;
+    pub fn blobs_event_history_get(i: u64, out: *mut BlobsPhysicsEvent) -> i32;
+    pub fn blobs_event_history_clear();
 }

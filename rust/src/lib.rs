@@ -132,7 +132,15 @@ impl Physics {
     pub fn rbd_position(&mut self, h: RigidBodyHandle) -> Option<Vec2> { self.get_rbd_state(h).map(|s| g(s.position)) }              // physics.rs:151-153
     pub fn col_position(&mut self, h: ColliderHandle) -> Option<Vec2> { let mut s = BlobsColliderState::default(); (unsafe { blobs_collider_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then(|| g(s.desc.absolute_transform.translation)) }
     pub fn update_rigid_body_position(&mut self, id: u64, offset: Vec2) { unsafe { blobs_body_translate(self.w, id, v(offset)) }; }   // physics.rs:174-182
-    /// get_mut_rbd (physics.rs:109-111): mutate a copy, write back the fields named in `mask`
+    /// get_mut_rbd (physics.rs:109-111). The body lives in HBM, so the `&mut RigidBody` of the reference becomes a guard that
+    /// derefs to a host mirror of the body; when the guard is dropped the fields that changed are written back with one
+    /// blobs_body_set (field mask = dirty set). Every RigidBody method of the reference (rigid_body.rs:130-214) then runs
+    /// unchanged on the mirror - same glam arithmetic, hence the same bits.
+    pub fn get_mut_rbd(&mut self, h: RigidBodyHandle) -> Option<RigidBodyMut<'_>> {
+        let before = self.get_rbd_state(h)?;
+        Some(RigidBodyMut { physics: self, handle: h, before, body: RigidBodyMirror::from_state(&before) })
+    }
+    /// lower-level form of the same: write back the fields named in `mask`
     pub fn set_rbd_state(&mut self, h: RigidBodyHandle, s: &BlobsBodyState, mask: u32) { self.ck(unsafe { blobs_body_set(self.w, h.0.to_bits(), s, mask) }); }
     /// create_fixed_joint (physics.rs:184-207)
     pub fn create_fixed_joint(&mut self, a: RigidBodyHandle, b: RigidBodyHandle, anchor_a: Vec2, anchor_b: Vec2) -> JointHandle { self.create_fixed_joint_with_distance(a, b, anchor_a, anchor_b, f32::NAN) }
@@ -184,6 +192,110 @@ impl ColliderBuilder {
     pub fn build(self) -> Collider { self.0 }
 }
 #[allow(dead_code)] fn _unused(_: Mat2) {}
+
+/// Host mirror of one RigidBody (rigid_body.rs:41-74): the `pub` fields plus the reference's methods, verbatim semantics.
+#[derive(Copy, Clone, Debug)]
+pub struct RigidBodyMirror {
+    pub position: Vec2, pub position_old: Vec2, pub center_of_mass: Vec2, pub scale: Vec2, pub acceleration: Vec2,
+    pub velocity_request: Option<Vec2>, pub calculated_velocity: Vec2, pub calculated_mass: f32, pub gravity_mod: f32,
+    pub rotation: f32, pub angular_velocity: f32, pub torque: f32, pub inertia: f32, pub user_data: u128, pub body_type: RigidBodyType,
+}
+impl RigidBodyMirror {
+    fn from_state(s: &BlobsBodyState) -> Self {
+        let body_type = match s.body_type { 1 => RigidBodyType::Static, 2 => RigidBodyType::KinematicPositionBased, 3 => RigidBodyType::KinematicVelocityBased, _ => RigidBodyType::Dynamic };
+        Self { position: g(s.position), position_old: g(s.position_old), center_of_mass: g(s.center_of_mass), scale: g(s.scale), acceleration: g(s.acceleration),
+               velocity_request: (s.has_velocity_request != 0).then(|| g(s.velocity_request)), calculated_velocity: g(s.calculated_velocity),
+               calculated_mass: s.calculated_mass, gravity_mod: s.gravity_mod, rotation: s.rotation, angular_velocity: s.angular_velocity, torque: s.torque,
+               inertia: s.inertia, user_data: (s.user_data_lo as u128) | ((s.user_data_hi as u128) << 64), body_type }
+    }
+    pub fn is_static(&self) -> bool { self.body_type == RigidBodyType::Static }                                  // rigid_body.rs:211-213
+    pub fn is_dynamic(&self) -> bool { self.body_type == RigidBodyType::Dynamic }                                // :198-200
+    pub fn is_kinematic(&self) -> bool { matches!(self.body_type, RigidBodyType::KinematicPositionBased | RigidBodyType::KinematicVelocityBased) } // :202-205
+    pub fn get_velocity(&self) -> Vec2 { self.calculated_velocity }                                              // :186-188
+    pub fn set_velocity(&mut self, velocity: Vec2) { self.velocity_request = Some(velocity); }                   // :182-184
+    pub fn add_velocity(&mut self, velocity: Vec2) { self.set_velocity(self.get_velocity() + velocity); }        // :151-153
+    pub fn apply_impulse(&mut self, impulse: Vec2) { if !self.is_static() { self.add_velocity(impulse / self.calculated_mass); } }   // :130-135
+    pub fn apply_impulse_at_point(&mut self, impulse: Vec2, world_point: Vec2) {                                 // :137-149
+        if !self.is_static() {
+            self.apply_impulse(impulse);
+            let lever_arm = world_point - (self.position + self.center_of_mass);
+            self.angular_velocity += lever_arm.perp_dot(impulse) / self.inertia;
+        }
+    }
+    pub fn apply_force(&mut self, force: Vec2) { if !self.is_static() { self.acceleration += force / self.calculated_mass; } }       // :155-160
+    pub fn apply_force_at_point(&mut self, force: Vec2, world_point: Vec2) {                                     // :162-172
+        if !self.is_static() {
+            self.apply_force(force);
+            let lever_arm = world_point - (self.position + self.center_of_mass);
+            self.torque += lever_arm.perp_dot(force);
+        }
+    }
+    pub fn apply_torque_at_point(&mut self, force: Vec2, world_point: Vec2) {                                    // :174-180
+        if !self.is_static() { let lever_arm = world_point - (self.position + self.center_of_mass); self.torque += lever_arm.perp_dot(force); }
+    }
+    pub fn accelerate(&mut self, a: Vec2) { self.acceleration += a; }                                            // :207-209
+}
+
+/// The guard `get_mut_rbd` returns: `Deref`/`DerefMut` to the mirror, write-back of the dirty fields on drop.
+pub struct RigidBodyMut<'a> { physics: &'a mut Physics, handle: RigidBodyHandle, before: BlobsBodyState, body: RigidBodyMirror }
+impl std::ops::Deref for RigidBodyMut<'_> { type Target = RigidBodyMirror; fn deref(&self) -> &RigidBodyMirror { &self.body } }
+impl std::ops::DerefMut for RigidBodyMut<'_> { fn deref_mut(&mut self) -> &mut RigidBodyMirror { &mut self.body } }
+impl Drop for RigidBodyMut<'_> {
+    fn drop(&mut self) {
+        let (b, o) = (&self.body, RigidBodyMirror::from_state(&self.before));
+        let bits = |a: Vec2, c: Vec2| a.x.to_bits() != c.x.to_bits() || a.y.to_bits() != c.y.to_bits();
+        let mut s = self.before;
+        let mut mask = 0u32;
+        if bits(b.position, o.position) { s.position = v(b.position); mask |= BLOBS_BODY_POSITION; }
+        if bits(b.position_old, o.position_old) { s.position_old = v(b.position_old); mask |= BLOBS_BODY_POSITION_OLD; }
+        if bits(b.acceleration, o.acceleration) { s.acceleration = v(b.acceleration); mask |= BLOBS_BODY_ACCELERATION; }
+        if bits(b.calculated_velocity, o.calculated_velocity) { s.calculated_velocity = v(b.calculated_velocity); mask |= BLOBS_BODY_CALC_VELOCITY; }
+        if bits(b.scale, o.scale) { s.scale = v(b.scale); mask |= BLOBS_BODY_SCALE; }
+        if bits(b.center_of_mass, o.center_of_mass) { s.center_of_mass = v(b.center_of_mass); mask |= BLOBS_BODY_CENTER_OF_MASS; }
+        if b.velocity_request.map(|q| (q.x.to_bits(), q.y.to_bits())) != o.velocity_request.map(|q| (q.x.to_bits(), q.y.to_bits())) {
+            s.has_velocity_request = b.velocity_request.is_some() as i32;
+            s.velocity_request = v(b.velocity_request.unwrap_or(Vec2::ZERO));
+            mask |= BLOBS_BODY_VELOCITY_REQUEST;
+        }
+        if b.rotation.to_bits() != o.rotation.to_bits() { s.rotation = b.rotation; mask |= BLOBS_BODY_ROTATION; }
+        if b.angular_velocity.to_bits() != o.angular_velocity.to_bits() { s.angular_velocity = b.angular_velocity; mask |= BLOBS_BODY_ANGULAR_VELOCITY; }
+        if b.torque.to_bits() != o.torque.to_bits() { s.torque = b.torque; mask |= BLOBS_BODY_TORQUE; }
+        if b.calculated_mass.to_bits() != o.calculated_mass.to_bits() { s.calculated_mass = b.calculated_mass; mask |= BLOBS_BODY_MASS; }
+        if b.inertia.to_bits() != o.inertia.to_bits() { s.inertia = b.inertia; mask |= BLOBS_BODY_INERTIA; }
+        if b.gravity_mod.to_bits() != o.gravity_mod.to_bits() { s.gravity_mod = b.gravity_mod; mask |= BLOBS_BODY_GRAVITY_MOD; }
+        if b.body_type != o.body_type { s.body_type = b.body_type as u32; mask |= BLOBS_BODY_TYPE; }
+        if b.user_data != o.user_data { s.user_data_lo = b.user_data as u64; s.user_data_hi = (b.user_data >> 64) as u64; mask |= BLOBS_BODY_USER_DATA; }
+        if mask != 0 { self.physics.set_rbd_state(self.handle, &s, mask); }
+    }
+}
+
+/// perf_counters.rs:52-87 - same free functions, backed by the library's process-global registry (blobs_step feeds "collisions")
+pub mod perf_counters {
+    use super::ffi::*;
+    use std::ffi::CString;
+    pub fn perf_counter(counter_name: &str, count: u64) { let n = CString::new(counter_name).unwrap(); unsafe { blobs_perf_counter(n.as_ptr(), count) } }
+    pub fn perf_counter_inc(counter_name: &str, inc: u64) { let n = CString::new(counter_name).unwrap(); unsafe { blobs_perf_counter_inc(n.as_ptr(), inc) } }
+    pub fn perf_counters_new_frame(delta: f64) { unsafe { blobs_perf_counters_new_frame(delta) } }
+    pub fn reset_perf_counters() { unsafe { blobs_perf_counters_reset() } }
+    pub fn get_perf_counter(counter_name: &str) -> (u64, f64) {
+        let n = CString::new(counter_name).unwrap();
+        let (mut c, mut a) = (0u64, 0f64);
+        unsafe { blobs_perf_counter_get(n.as_ptr(), &mut c, &mut a) };
+        (c, a)
+    }
+    /// what the demo's perf panel iterates (demo/src/main.rs:291-300): (name, count, decayed_average)
+    pub fn counters() -> Vec<(String, u64, f64)> {
+        let mut out = Vec::new();
+        for i in 0..unsafe { blobs_perf_counter_count() } {
+            let mut name = [0 as std::os::raw::c_char; 256];
+            let (mut c, mut a) = (0u64, 0f64);
+            if unsafe { blobs_perf_counter_at(i, name.as_mut_ptr(), name.len(), &mut c, &mut a) } == BLOBS_OK {
+                out.push((unsafe { std::ffi::CStr::from_ptr(name.as_ptr()) }.to_string_lossy().into_owned(), c, a));
+            }
+        }
+        out
+    }
+}
 
 /// debug.rs:6-32
 pub struct DebugRigidBody { pub transform: Affine2 }

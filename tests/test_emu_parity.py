@@ -9,7 +9,9 @@ test this way (the whole parity suite takes ~8 minutes)."""
 import pytest
 
 from . import test_gpu_parity as T
+from . import test_perf_counters as PC
 from . import test_physics_api as P
+from . import test_rigid_body_api as RB
 from .emu_loader import emulated
 
 pytestmark = pytest.mark.emu
@@ -40,6 +42,8 @@ CASES = [
     ("scene-queries", T.test_scene_queries_served_from_the_grid, {}),
     ("physics-api-balls", P.test_balls_demo_flow, {}),
     ("physics-api-joints-springs-panics", P.test_joints_springs_and_panics, {}),
+    ("perf-counter-collisions", PC.check_step_feeds_collisions, {}),
+    ("removal-semantics-event-ring", RB.check_removal_semantics_and_event_ring, {}),
 ]
 
 

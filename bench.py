@@ -9,7 +9,8 @@ config #2 (1 048 576 single-collider spheres in one world). Prints ONE JSON line
 Timing: `value` is device time (CUDA events recorded by the library on its own stream around each step's
 kernels), inputs resident in HBM, max over ranks; between timed steps a 256 MiB buffer is rewritten to flush L2
 (outside the per-step events). `e2e` is wall-clock through the public C ABI with per-step pinned-host -> device forces
-and device -> pinned-host positions inside the timed region.
+and device -> pinned-host positions inside the timed region (N = 1: the ABI's pipelined host I/O, copies on their own
+streams; `e2e.sync_value` = the blocking calls on a short sample).
 """
 import argparse
 import json
@@ -316,24 +317,66 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- end-to-end region (public C ABI, host buffers, copies inside) ------------------------------
+    # N = 1: the pipelined host I/O of the C ABI (blobs_forces_upload_async / blobs_apply_forces_uploaded /
+    # blobs_read_body_positions_async / blobs_io_sync): every step's forces are copied from pinned host memory and every step's
+    # positions are copied back to pinned host memory inside the timed region, on their own streams, overlapping the kernels of
+    # the neighbouring steps. BLOBS_BENCH_E2E=sync times the blocking calls instead (copy, step, copy back to back); a short
+    # sample of that loop is always reported beside it as e2e.sync_value.
     io_bytes = 0
+    e2e_mode = "sync"
+    sync_sample = None
     n_io = w.read_owned_positions_ptr(slots_io.data_ptr(), pos_out.data_ptr(), io_cap) if strips_on else nb
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        if strips_on:
+
+    def sync_loop(k):
+        for _ in range(k):
+            w.apply_forces_ptr(forces.data_ptr(), nb)      # pinned host -> device
+            w.step(DT)
+            w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
+
+    if strips_on:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
             w.apply_forces_indexed_ptr(slots_io.data_ptr(), forces.data_ptr(), min(n_io, io_cap))        # pinned host -> device (owned bodies)
             io_bytes += min(n_io, io_cap) * 12
             w.step(DT)
             n_io = w.read_owned_positions_ptr(slots_io.data_ptr(), pos_out.data_ptr(), io_cap)            # device -> pinned host (synchronous)
             io_bytes += min(n_io, io_cap) * 12
-        else:
-            w.apply_forces_ptr(forces.data_ptr(), nb)      # pinned host -> device
+        barrier()
+        t_e2e = time.perf_counter() - t0
+    elif os.environ.get("BLOBS_BENCH_E2E", "pipelined") == "sync":
+        barrier()
+        t0 = time.perf_counter()
+        sync_loop(K)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        io_bytes = K * nb * 16
+    else:
+        ks = max(1, K // 5)
+        barrier()
+        t0 = time.perf_counter()
+        sync_loop(ks)
+        barrier()
+        sync_sample = (ks, time.perf_counter() - t0)
+        forces2 = forces.clone().pin_memory()
+        pos_out2 = torch.zeros_like(pos_out).pin_memory()
+        fbuf, obuf = (forces, forces2), (pos_out, pos_out2)
+        e2e_mode = "pipelined"
+        barrier()
+        t0 = time.perf_counter()
+        w.forces_upload_async_ptr(fbuf[0].data_ptr(), nb)              # pinned host -> device, step 0
+        for i in range(K):
+            w.apply_forces_uploaded()
+            if i + 1 < K:
+                w.forces_upload_async_ptr(fbuf[(i + 1) & 1].data_ptr(), nb)   # step i+1's forces travel under step i's kernels
             w.step(DT)
-            w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
-            io_bytes += nb * 16
-    barrier()
-    t_e2e = time.perf_counter() - t0
+            w.io_sync()                                                # positions of step i-1 have landed in obuf[(i-1)&1]
+            w.read_positions_async_ptr(obuf[i & 1].data_ptr(), nb)     # device -> pinned host, under step i+1's kernels
+        w.io_sync()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        io_bytes = K * nb * 16
+        pos_out = obuf[(K - 1) & 1]
     checksum = float(pos_out[: max(1, min(n_io, io_cap)), 1].double().mean())
 
     t = torch.tensor([t_dev_ms, t_e2e], dtype=torch.float64, device="cuda")
@@ -366,7 +409,8 @@ def run_ours(args):
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1])},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,
-                    "checksum_mean_y": checksum},
+                    "checksum_mean_y": checksum, "host_io": e2e_mode,
+                    "sync_value": (n_total * sync_sample[0] / sync_sample[1]) if sync_sample else None},
             "gpu_launches": launches_total,
             "roofline": {"bound": "hbm", "kernel": "k_main<fused,ordered> (contacts + verlet + snapshot + clamp + cell binning)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

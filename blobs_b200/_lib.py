@@ -52,6 +52,10 @@ SIGNATURES = {
     "blobs_read_body_positions": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "blobs_read_body_velocities": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "blobs_apply_forces": (C.c_int32, [_vp, _vp, C.c_size_t]),
+    "blobs_forces_upload_async": (C.c_int32, [_vp, _vp, C.c_size_t]),
+    "blobs_apply_forces_uploaded": (C.c_int32, [_vp]),
+    "blobs_read_body_positions_async": (C.c_int32, [_vp, _vp, C.c_size_t]),
+    "blobs_io_sync": (C.c_int32, [_vp]),
     "blobs_download_cell_coords": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
     "blobs_query_circles": (C.c_int32, [_vp, C.c_size_t, _vp, _vp, C.POINTER(A.QueryFilter), _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "blobs_debug_counts": (C.c_int32, [_vp, C.POINTER(A.DebugCounts)]),

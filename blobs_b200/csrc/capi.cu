@@ -114,6 +114,10 @@ int32_t blobs_download_colliders(BlobsWorld* w, BlobsColliderState* st, BlobsHan
 int32_t blobs_read_body_positions(BlobsWorld* w, float* xy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(xy); return w->w.read_body_vec(0, xy, cap); }
 int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(xy); return w->w.read_body_vec(1, xy, cap); }
 int32_t blobs_apply_forces(BlobsWorld* w, const float* f, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(f); return w->w.apply_forces(f, cap); }
+int32_t blobs_forces_upload_async(BlobsWorld* w, const float* f, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(f); return w->w.forces_upload_async(f, cap); }
+int32_t blobs_apply_forces_uploaded(BlobsWorld* w) { W_OR_INVALID(w); return w->w.apply_forces_uploaded(); }
+int32_t blobs_read_body_positions_async(BlobsWorld* w, float* xy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(xy); return w->w.read_positions_async(xy, cap); }
+int32_t blobs_io_sync(BlobsWorld* w) { W_OR_INVALID(w); return w->w.io_sync(); }
 int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(cx); W_OR_INVALID(cy); return w->w.download_cell_coords(cx, cy, cap); }
 
 int32_t blobs_query_circles(BlobsWorld* w, size_t n, const float* c, const float* r, const BlobsQueryFilter* f, uint64_t* off, BlobsHandle* hits, size_t cap, size_t* nh) {

@@ -97,6 +97,9 @@ int World::init() {
 World::~World() {
     // strip mode: the stream may be parked inside a collective whose peer is gone — never block process exit on it
     if (stream && !strip_on) cudaStreamSynchronize(stream);
+    if (io_ready) { cudaStreamSynchronize(s_h2d); cudaStreamDestroy(s_h2d); cudaStreamSynchronize(s_d2h); cudaStreamDestroy(s_d2h); }
+    for (cudaEvent_t e : {ev_up_done[0], ev_up_done[1], ev_up_free[0], ev_up_free[1], ev_snap_ready, ev_snap_free}) if (e) cudaEventDestroy(e);
+    d_forces_up[0].release(); d_forces_up[1].release(); d_pos_snap.release();
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     destroy_graph(gslot[0]);
     destroy_graph(gslot[1]);
@@ -1498,6 +1501,90 @@ int World::apply_forces(const float* f, size_t cap) {
     BLOBS_LAUNCH(cdiv(n, 256), 256, 0, stream, k_apply_forces)(body_arrays(), d_forces.d, (uint32_t)n);
     launches++;
     CU(cudaGetLastError());
+    return BLOBS_OK;
+}
+
+// ---- pipelined host I/O -------------------------------------------------------------------------------------------------
+// blobs_apply_forces / blobs_read_body_positions put their PCIe copy on the compute stream, so a frame costs
+// H2D + step + D2H back to back. The calls below move the copies to one stream per direction: the forces of step i+1 travel
+// while step i computes, and the positions of step i (snapshotted device-to-device first, so step i+1 may overwrite them)
+// travel while step i+1 computes. Ordering is by events only; results are identical to the synchronous calls.
+int World::io_init() {
+    if (io_ready) return BLOBS_OK;
+    CU(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&ev_up_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_up_free[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&ev_snap_ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_snap_free, cudaEventDisableTiming));
+    io_ready = true;
+    return BLOBS_OK;
+}
+
+// starts the host->device copy of one batch of per-slot forces (double-buffered on the device); returns at once
+int World::forces_upload_async(const float* f, size_t cap) {
+    int rc = io_init();
+    if (rc) return rc;
+    if (up_pending >= 0) return fail(BLOBS_ERR_INVALID, "blobs_forces_upload_async: the previous batch has not been applied yet");
+    const size_t n = std::min(cap, bodies.slots());
+    const int k = up_next;
+    up_next ^= 1;
+    if (n) {
+        if (up_used[k]) CU(cudaStreamWaitEvent(s_h2d, ev_up_free[k], 0));   // the kernel that read this buffer two batches ago
+        CU(d_forces_up[k].ensure(n, s_h2d));
+        CU(cudaMemcpyAsync(d_forces_up[k].d, f, n * sizeof(float2), cudaMemcpyHostToDevice, s_h2d));
+    }
+    CU(cudaEventRecord(ev_up_done[k], s_h2d));
+    up_pending = k;
+    up_n = n;
+    return BLOBS_OK;
+}
+
+// RigidBody::apply_force (rigid_body.rs:155-160) for every slot of the uploaded batch; the compute stream waits for the copy
+int World::apply_forces_uploaded() {
+    if (up_pending < 0) return fail(BLOBS_ERR_INVALID, "blobs_apply_forces_uploaded: no uploaded batch");
+    int rc = flush();
+    if (rc) return rc;
+    const int k = up_pending;
+    up_pending = -1;
+    const size_t n = std::min(up_n, bodies.slots());
+    CU(cudaStreamWaitEvent(stream, ev_up_done[k], 0));
+    if (n) {
+        BLOBS_LAUNCH(cdiv(n, 256), 256, 0, stream, k_apply_forces)(body_arrays(), d_forces_up[k].d, (uint32_t)n);
+        launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev_up_free[k], stream));
+    up_used[k] = true;
+    return BLOBS_OK;
+}
+
+// positions of all body slots -> host, without blocking: device-to-device snapshot on the compute stream, PCIe copy on its own
+// stream. `xy` must stay untouched until blobs_io_sync returns.
+int World::read_positions_async(float* xy, size_t cap) {
+    int rc = io_init();
+    if (rc) return rc;
+    rc = flush();
+    if (rc) return rc;
+    const size_t n = std::min(cap, bodies.slots());
+    if (!n) return BLOBS_OK;
+    if (snap_used) CU(cudaStreamWaitEvent(stream, ev_snap_free, 0));   // the previous snapshot is still on its way to the host
+    CU(d_pos_snap.ensure(n, stream));
+    CU(cudaMemcpyAsync(d_pos_snap.d, pos.d, n * sizeof(float2), cudaMemcpyDeviceToDevice, stream));
+    CU(cudaEventRecord(ev_snap_ready, stream));
+    CU(cudaStreamWaitEvent(s_d2h, ev_snap_ready, 0));
+    CU(cudaMemcpyAsync(xy, d_pos_snap.d, n * sizeof(float2), cudaMemcpyDeviceToHost, s_d2h));
+    CU(cudaEventRecord(ev_snap_free, s_d2h));
+    snap_used = true;
+    return BLOBS_OK;
+}
+
+int World::io_sync() {
+    if (!io_ready) return BLOBS_OK;
+    CU(cudaStreamSynchronize(s_h2d));
+    CU(cudaStreamSynchronize(s_d2h));
     return BLOBS_OK;
 }
 

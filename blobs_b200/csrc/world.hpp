@@ -185,6 +185,10 @@ class World {
     int debug_data(float* body_xform, float* joint_ab, float* col_xform, float* col_radius, float* spring_ab, const BlobsDebugCounts* caps);
     int read_body_vec(int which, float* xy, size_t cap);
     int apply_forces(const float* f, size_t cap);
+    int forces_upload_async(const float* f, size_t cap);
+    int apply_forces_uploaded();
+    int read_positions_async(float* xy, size_t cap);
+    int io_sync();
     int download_cell_coords(int32_t* cx, int32_t* cy, size_t cap);
     int record_contacts(int mode, size_t cap);
     int events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n);
@@ -379,6 +383,15 @@ class World {
     uint64_t prof_launches[KC_COUNT] = {0};
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
     DevBuf<float2> d_forces;
+    // pipelined host I/O (blobs_forces_upload_async / blobs_read_body_positions_async): one copy stream per direction so the
+    // PCIe transfers of neighbouring steps overlap the kernels of this one
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up_done[2] = {nullptr, nullptr}, ev_up_free[2] = {nullptr, nullptr}, ev_snap_ready = nullptr, ev_snap_free = nullptr;
+    DevBuf<float2> d_forces_up[2], d_pos_snap;
+    int up_next = 0, up_pending = -1;
+    size_t up_n = 0;
+    bool up_used[2] = {false, false}, snap_used = false, io_ready = false;
+    int io_init();
     DevBuf<int> d_cellx, d_celly;
     DevBuf<float2> d_qcentre;
     DevBuf<float> d_qradius;

@@ -221,6 +221,19 @@ class World:
     def apply_forces_ptr(self, ptr, n):
         self._ck(self._lib.blobs_apply_forces(self._h, C.c_void_p(ptr), n))
 
+    # pipelined host I/O (include/blobs_b200.h): copies on their own streams, overlapping the neighbouring steps
+    def forces_upload_async_ptr(self, ptr, n):
+        self._ck(self._lib.blobs_forces_upload_async(self._h, C.c_void_p(ptr), n))
+
+    def apply_forces_uploaded(self):
+        self._ck(self._lib.blobs_apply_forces_uploaded(self._h))
+
+    def read_positions_async_ptr(self, ptr, n):
+        self._ck(self._lib.blobs_read_body_positions_async(self._h, C.c_void_p(ptr), n))
+
+    def io_sync(self):
+        self._ck(self._lib.blobs_io_sync(self._h))
+
     def cell_coords(self):
         n = self.collider_slots()
         cx = np.zeros(n, dtype=np.int32)

@@ -238,6 +238,21 @@ int32_t blobs_download_colliders(BlobsWorld* w, BlobsColliderState* states, Blob
 int32_t blobs_read_body_positions(BlobsWorld* w, float* xy, size_t cap);
 int32_t blobs_read_body_velocities(BlobsWorld* w, float* xy, size_t cap);
 int32_t blobs_apply_forces(BlobsWorld* w, const float* force_xy, size_t cap);  /* per-slot RigidBody::apply_force rigid_body.rs:155-160 */
+/* Pipelined forms of the two calls above for a per-frame loop (no reference counterpart: the reference's state is host memory).
+ * The PCIe copies run on their own streams, one per direction, so they overlap the kernels of the neighbouring steps:
+ *     blobs_forces_upload_async(w, f[0]);
+ *     for each frame i:  blobs_apply_forces_uploaded(w);             // forces i (already on the device)
+ *                        blobs_forces_upload_async(w, f[i+1]);        // travels while step i computes
+ *                        blobs_step(w, delta, &stats);
+ *                        blobs_io_sync(w);                            // positions i-1 have arrived, f[i+1] may be reused
+ *                        blobs_read_body_positions_async(w, out[i&1]); // travels while step i+1 computes
+ *     blobs_io_sync(w);
+ * Host buffers should be pinned (cudaHostAlloc / torch pin_memory) and must not be touched between the call and the next
+ * blobs_io_sync. Results are identical to the synchronous calls. */
+int32_t blobs_forces_upload_async(BlobsWorld* w, const float* force_xy, size_t cap);  /* at most one batch may be pending */
+int32_t blobs_apply_forces_uploaded(BlobsWorld* w);                                   /* per-slot RigidBody::apply_force rigid_body.rs:155-160 */
+int32_t blobs_read_body_positions_async(BlobsWorld* w, float* xy, size_t cap);
+int32_t blobs_io_sync(BlobsWorld* w);
 /* SpatialHash::get_cell_coords (spatial.rs:57-62) of every collider snapshot, with BLOBS_PARAM_CELL_SIZE */
 int32_t blobs_download_cell_coords(BlobsWorld* w, int32_t* cx, int32_t* cy, size_t cap);
 

@@ -231,7 +231,7 @@ typedef struct emuEvent { std::chrono::steady_clock::time_point t; }* cudaEvent_
 typedef struct emuGraph* cudaGraph_t;
 typedef struct emuGraphExec* cudaGraphExec_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-enum { cudaStreamNonBlocking = 1, cudaStreamCaptureModeThreadLocal = 1, cudaEventRecordExternal = 1 };
+enum { cudaStreamNonBlocking = 1, cudaStreamCaptureModeThreadLocal = 1, cudaEventRecordExternal = 1, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorNotSupported ? "not supported by the CPU test build" : "error"); }
@@ -255,6 +255,8 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent(); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emuEvent(); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }   // every stream runs synchronously here
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 static inline cudaError_t cudaEventRecordWithFlags(cudaEvent_t e, cudaStream_t, unsigned) { return cudaEventRecord(e); }

@@ -298,6 +298,51 @@ def test_body_set_and_translate_between_steps():
     _compare_step(g, o)
 
 
+def test_pipelined_host_io_matches_synchronous_calls():
+    """blobs_forces_upload_async / blobs_apply_forces_uploaded / blobs_read_body_positions_async / blobs_io_sync (copies on their
+    own streams, overlapping the neighbouring steps) against the oracle driven with the synchronous apply_forces + read: the
+    positions read back every frame and the final state must be bit-identical."""
+    import torch
+
+    sc = S.cfg1(2)
+    g, o = _pair(sc.gravity, sc)
+    nb, frames = 1024, 12
+    pin = torch.cuda.is_available()
+    forces = [torch.from_numpy(np.ascontiguousarray(S.uniform(77 + i, 0, 2 * nb).reshape(nb, 2) * np.float32(8.0) - np.float32(4.0))) for i in range(frames + 1)]
+    outs = [torch.zeros((nb, 2), dtype=torch.float32) for _ in range(2)]
+    if pin:
+        forces = [f.pin_memory() for f in forces]
+        outs = [x.pin_memory() for x in outs]
+    want = []
+    for i in range(frames):
+        o.apply_forces(forces[i].numpy())
+        o.step(1 / 60)
+        want.append(o.read_positions().copy())
+    got = []
+    g.forces_upload_async_ptr(forces[0].data_ptr(), nb)
+    with pytest.raises(RuntimeError, match="has not been applied"):
+        g.forces_upload_async_ptr(forces[1].data_ptr(), nb)       # at most one pending batch
+    for i in range(frames):
+        g.apply_forces_uploaded()
+        g.forces_upload_async_ptr(forces[i + 1].data_ptr(), nb)   # next frame's input travels under this frame's kernels
+        g.step(1 / 60)
+        g.io_sync()
+        if i:
+            got.append(outs[(i - 1) & 1].numpy().copy())          # frame i-1 has arrived
+        g.read_positions_async_ptr(outs[i & 1].data_ptr(), nb)    # travels under the next frame's kernels
+    g.io_sync()
+    got.append(outs[(frames - 1) & 1].numpy().copy())
+    for i in range(frames):
+        assert np.array_equal(bits(got[i]), bits(want[i])), f"frame {i}"
+    g.apply_forces_uploaded()                                     # the last uploaded batch is still applicable
+    o.apply_forces(forces[frames].numpy())
+    with pytest.raises(RuntimeError, match="no uploaded batch"):
+        g.apply_forces_uploaded()
+    for w in (g, o):
+        w.step(1 / 60)
+    _compare_step(g, o)
+
+
 def test_far_outlier_aliases_harmlessly():
     """A body far outside the table's extent wraps around the toroidal grid: still exact."""
     sc = S.cfg1(1)

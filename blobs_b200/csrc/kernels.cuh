@@ -722,10 +722,10 @@ __device__ __forceinline__ void strip_pack_one(const BodyArrays& B, const Collid
 // round 2 = six cell-table entries; round 3 = hot record halves; round 4 = cold halves of prefilter survivors;
 // round 5 = the binning atomic.
 // ------------------------------------------------------------------------------------------------
-template <bool FUSED, bool ORDERED, int BATCH, int MINB, bool POOLED>
-__global__ void __launch_bounds__(256, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+template <bool FUSED, bool ORDERED, int BATCH, int MINB, bool POOLED, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                               Broadphase bp, Recording rec, DeviceStats* stats, StripView sv) {
-    __shared__ PoolSmem pool[POOLED ? 8 : 1];
+    __shared__ PoolSmem pool[POOLED ? THREADS / 32 : 1];
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;

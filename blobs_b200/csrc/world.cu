@@ -1131,6 +1131,16 @@ int World::launch_substep(const SubstepParams& P_in) {
             } else if (pooled && tune == 8) {  // same with 85 registers per thread (3 CTAs per SM)
                 if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 3, true);
                 else BLOBS_LAUNCH_MAIN(false, true, 4, 3, true);
+            } else if (tune == 9 || tune == 10) {
+                // 128-thread CTAs (8 per SM, same registers per thread): the warps of a CTA finish at very different times in
+                // contact-rich states (35 % achieved vs 50 % theoretical occupancy with 256 threads), smaller CTAs free their slots
+                // sooner. 9 = with the automatic pooled/per-lane choice, 10 = per-lane only. Unmeasured so far (round-2 sweep).
+                const unsigned g128 = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 128);
+#define BLOBS_LAUNCH_MAIN128(F, PL) BLOBS_LAUNCH(g128, 128, 0, stream, k_main<F, true, 4, 8, PL, 128>)(P, grid, K, B, C, bp, R, d_stats, sv)
+                if (!ordered) BLOBS_MAIN_VARIANT(4, 4);
+                else if (pooled && tune == 9) { if (fused) BLOBS_LAUNCH_MAIN128(true, true); else BLOBS_LAUNCH_MAIN128(false, true); }
+                else { if (fused) BLOBS_LAUNCH_MAIN128(true, false); else BLOBS_LAUNCH_MAIN128(false, false); }
+#undef BLOBS_LAUNCH_MAIN128
             } else
             switch (tune) {
                 case 2: BLOBS_MAIN_VARIANT(8, 4); break;

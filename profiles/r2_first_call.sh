@@ -1,0 +1,29 @@
+#!/bin/bash
+# Round-2 opener: everything the round-1 notes say must be measured first, in ONE gpurun call (one box, ~12 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash profiles/r2_first_call.sh'
+# Outputs land in gpurun_out/r2/ (copy what is to be judged into profiles/).
+#  1. the GPU parity suite (new since the last GPU run: perf counters, RigidBodyMut, removal/event ring, pipelined host I/O,
+#     debug_data, scene queries, 128-thread k_main variants)
+#  2. default bench line (pipelined e2e gets its first measurement here) + the blocking e2e loop for comparison
+#  3. k_main variant sweep in the two regimes of config #2: TUNE 0 (256-thread CTAs), 9 (128-thread, auto pooled), 10 (128-thread,
+#     per-lane), 8 (pooled, 3 CTAs/SM); sparse window = --warmup 60 --steps 30, dense window = the default
+#  4. ncu: launch list of the default command, and ONE --set full capture of the pooled k_main + k_crowded at step 275
+#     (the profile round 1 could not take: expect the scan phase and the per-pair shuffles on top)
+set -u
+O=gpurun_out/r2
+mkdir -p $O
+export PYTHONUNBUFFERED=1
+timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
+timeout 300 python bench.py > $O/bench_default.json 2> $O/bench_default.err
+BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
+for t in 0 9 10 8; do
+  timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
+  timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
+done
+timeout 200 python bench.py --workload cfg3 --no-cpu-baseline > $O/cfg3.json 2>> $O/sweep.err
+timeout 200 python bench.py --workload cfg4 --no-cpu-baseline > $O/cfg4.json 2>> $O/sweep.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 100 --csv --log-file $O/ncu_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
+CAPTURE_STEPS=277 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_main|k_crowded" --launch-skip 4400 --launch-count 2 \
+    -o $O/dense_pooled python profiles/trace_cfg2.py 0 0 2 > $O/ncu_dense.log 2>&1
+ls -la $O

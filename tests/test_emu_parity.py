@@ -58,6 +58,21 @@ def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
         fn(**kw)
 
 
+SMALL_CTA_CASES = [c for c in CASES if c[0] in ("overflow200-fused-crowded", "multi-collider", "batched-worlds", "removal-reinsert")]
+
+
+@pytest.mark.parametrize("tune", ["9", "10"], ids=["tune9-128thr-pooled", "tune10-128thr-per-lane"])
+@pytest.mark.parametrize("case", SMALL_CTA_CASES, ids=[c[0] for c in SMALL_CTA_CASES])
+def test_128_thread_cta_variants(case, tune, monkeypatch):
+    """BLOBS_PARAM_TUNE 9 / 10: k_main with 128-thread CTAs (a round-2 experiment, never the default): same results."""
+    _, fn, kw = case
+    monkeypatch.setenv("BLOBS_B200_TUNE", tune)
+    for k, v in FORCED.items():
+        monkeypatch.setenv(k, v)
+    with emulated():
+        fn(**kw)
+
+
 def test_results_do_not_depend_on_the_schedule():
     """Same cases with the emulator visiting CTAs, warps and lanes in a seeded RANDOM order (BLOBS_EMU_SEED, read when the
     library is loaded, hence the subprocess): atomics then hand out different ranks and cells hold their records in another

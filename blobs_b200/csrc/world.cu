@@ -1100,7 +1100,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     const bool fused = (allow_fused && rec_mode != BLOBS_RECORD_EVENTS && (n_joints_live == 0 || joints_smem_ok)) || strip_on;
     const bool ordered = contact_mode == 0;
     last_fused = fused;
-    const uint32_t nb = P.n_bodies, nc = P.n_colliders;
+    const uint32_t nb = P.n_bodies;
     int rc;
     if (n_sb) {
         rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });

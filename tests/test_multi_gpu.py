@@ -8,6 +8,15 @@ import sys
 import numpy as np
 import pytest
 
+
+def _free_port():
+    """a TCP port nobody listens on right now (fixed ports collide when two test runs share a machine)"""
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -19,7 +28,7 @@ def test_strip_world_matches_single_gpu():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     n = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", "29617",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-3000:])
@@ -40,7 +49,7 @@ def test_strip_world_matches_single_world_emulated_ranks(knobs):
     build()
     env = dict(os.environ, BLOBS_TEST_EMU="1", STRIP_TEST_SIDE="48", STRIP_TEST_STEPS="24")
     env.update(knobs)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29653",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
@@ -72,7 +81,8 @@ def test_strip_partition_agrees_across_ranks_gloo():
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, 29641, q)) for r in range(2)]
+    port = _free_port()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
     got = sorted(q.get(timeout=120) for _ in ps)

@@ -394,8 +394,24 @@ struct PoolSmem {                 // per warp
     uint32_t fb;                  // owner lanes that must fall back to the serial rescan
 };
 
-template <int BATCH>
-__device__ __forceinline__ uint32_t scan_chunk(const Broadphase& bp, const SelfCol& s, float srk, uint32_t base, uint32_t total, uint32_t n0,
+// Where the pooled path reads hot record halves from: the cell-sorted array in global memory (k_main), or the windows a
+// k_tile CTA staged in shared memory (indices are then window offsets).
+struct GlobalHot {
+    const float4* hot;
+    __device__ __forceinline__ float4 operator()(uint32_t k) const { return __ldg(hot + k); }
+};
+struct StagedHot {
+    const float4* win;
+    __device__ __forceinline__ float4 operator()(uint32_t k) const { return win[k]; }
+};
+__device__ __forceinline__ Rec rec_of(const float4 h, const uint4* __restrict__ ccold) {
+    const uint32_t w = __float_as_uint(h.w);
+    if (w & HOT_COLD_BIT) return make_rec(h, __ldg(ccold + (w & HOT_SLOT_MASK)));
+    return make_rec(h, make_uint4(__float_as_uint(fmul(4.0f, h.z)), 0xffffffffu, 0xffffffffu, NO_SLOT));   // default sphere, see load_rec
+}
+
+template <int BATCH, class SRC>
+__device__ __forceinline__ uint32_t scan_chunk(const SRC& src, const SelfCol& s, float srk, uint32_t base, uint32_t total, uint32_t n0,
                                                uint32_t n01, uint32_t off0, uint32_t off1, uint32_t off2, uint32_t lo0) {
     const uint32_t lim = min(32u, total - base);
     uint32_t mask = 0;
@@ -405,7 +421,7 @@ __device__ __forceinline__ uint32_t scan_chunk(const Broadphase& bp, const SelfC
         for (int i = 0; i < BATCH; ++i) {
             const uint32_t t = base + t0 + i;
             const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-            h[i] = __ldg(bp.hot + (t0 + i < lim ? k : lo0));
+            h[i] = src(t0 + i < lim ? k : lo0);
         }
 #pragma unroll
         for (int i = 0; i < BATCH; ++i) {
@@ -422,16 +438,28 @@ __device__ __forceinline__ uint32_t scan_chunk(const Broadphase& bp, const SelfC
 // Must be called by all 32 lanes of the warp (valid = this lane has a collider to resolve). Returns true when the lane's
 // contributions were added to (px, py) here; false when they are in `list` (per-lane path), to be applied by the caller -
 // unless `big` comes back set (only with defer_big): then nothing was done for this lane, not even pair counting.
+// The candidate span of one lane as the pooled path sees it: three row spans flattened into t = 0 .. total-1, record index
+// (in whatever SRC addresses) = t + (t < n0 ? off0 : t < n01 ? off1 : off2).
+struct LaneSpan {
+    bool fits;     // <= 64 candidates in a plain 3-row range: this lane takes part in the pooled resolution
+    bool ranged;   // plain 3-row range, `total` is known
+    uint32_t lo0, n0, n01, total, off0, off1, off2;
+};
+
+template <int BATCH, class SRC>
+__device__ __forceinline__ bool gather_warp_core(const GridDesc& g, const Broadphase& bp, const SRC& src, const uint4* __restrict__ ccold, bool valid,
+                                                 const SelfCol& s, const LaneSpan& L, ContactList<uint32_t>& list, GatherOut& out,
+                                                 const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats, PoolSmem& ps,
+                                                 uint32_t pool_min, bool defer_big, bool& big, float& px, float& py);
+
 template <int BATCH>
 __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, bool valid, const SelfCol& s,
                                             ContactList<uint32_t>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
                                             DeviceStats* stats, PoolSmem& ps, uint32_t pool_min, bool defer_big, bool& big, float& px,
                                             float& py) {
-    constexpr uint32_t FULL = 0xffffffffu;
-    big = false;
-    const uint32_t lane = threadIdx.x & 31u;
-    bool fits = false, ranged = false;   // ranged: plain 3-row range, `total` is known
-    uint32_t lo0 = 0, n0 = 0, n01 = 0, total = 0, off0 = 0, off1 = 0, off2 = 0;
+    LaneSpan L;
+    L.fits = L.ranged = false;
+    L.lo0 = L.n0 = L.n01 = L.total = L.off0 = L.off1 = L.off2 = 0u;
     if (valid) {
         const CellRange R = cell_range(g, s.x, s.y, s.r);
         if (!(R.ny > 3u || R.c0 + R.nx > g.W)) {
@@ -446,17 +474,31 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
                 lo[j] = a;
                 cnt[j] = b - a;
             }
-            n0 = cnt[0]; n01 = cnt[0] + cnt[1]; total = n01 + cnt[2];
-            off0 = lo[0]; off1 = lo[1] - n0; off2 = lo[2] - n01; lo0 = lo[0];
-            ranged = true;
-            fits = total <= 64u;
+            L.n0 = cnt[0]; L.n01 = cnt[0] + cnt[1]; L.total = L.n01 + cnt[2];
+            L.off0 = lo[0]; L.off1 = lo[1] - L.n0; L.off2 = lo[2] - L.n01; L.lo0 = lo[0];
+            L.ranged = true;
+            L.fits = L.total <= 64u;
         }
     }
+    const GlobalHot src{bp.hot};
+    return gather_warp_core<BATCH>(g, bp, src, ccold, valid, s, L, list, out, rec, vel, stats, ps, pool_min, defer_big, big, px, py);
+}
+
+template <int BATCH, class SRC>
+__device__ __forceinline__ bool gather_warp_core(const GridDesc& g, const Broadphase& bp, const SRC& src, const uint4* __restrict__ ccold, bool valid,
+                                                 const SelfCol& s, const LaneSpan& L, ContactList<uint32_t>& list, GatherOut& out,
+                                                 const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats, PoolSmem& ps,
+                                                 uint32_t pool_min, bool defer_big, bool& big, float& px, float& py) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    big = false;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool fits = L.fits, ranged = L.ranged;
+    const uint32_t lo0 = L.lo0, n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
     const float srk = s.r * 1.00005f;
     uint32_t m0 = 0, m1 = 0;
     if (fits) {
-        if (total) m0 = scan_chunk<BATCH>(bp, s, srk, 0u, total, n0, n01, off0, off1, off2, lo0);
-        if (total > 32u) m1 = scan_chunk<BATCH>(bp, s, srk, 32u, total, n0, n01, off0, off1, off2, lo0);
+        if (total) m0 = scan_chunk<BATCH>(src, s, srk, 0u, total, n0, n01, off0, off1, off2, lo0);
+        if (total > 32u) m1 = scan_chunk<BATCH>(src, s, srk, 32u, total, n0, n01, off0, off1, off2, lo0);
     }
     const uint32_t c = (uint32_t)(__popc(m0) + __popc(m1));
     const uint32_t T = __reduce_add_sync(FULL, c);
@@ -511,7 +553,7 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
                 const uint32_t sf = __shfl_sync(FULL, sflag, o);
                 so.slot = sf & HOT_SLOT_MASK; so.sensor = (sf & HOT_SENSOR_BIT) != 0u; so.wbase = 0u;
                 if (act) {
-                    const Rec r = load_rec(bp, ccold, ps.key[i]);
+                    const Rec r = rec_of(src(ps.key[i]), ccold);
                     Contact ct;
                     uint32_t key = POOL_NONE;
                     if (narrowphase(so, r, ct)) {
@@ -568,11 +610,11 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
     } else if (fits) {   // few survivors in the whole warp: per-lane resolve straight from the masks
         for (uint32_t m = m0; m; m &= m - 1u) {
             const uint32_t t = (uint32_t)__ffs(m) - 1u;
-            take_candidate<true, uint32_t>(s, load_rec(bp, ccold, t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), list, out, rec, vel, stats);
+            take_candidate<true, uint32_t>(s, rec_of(src(t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), ccold), list, out, rec, vel, stats);
         }
         for (uint32_t m = m1; m; m &= m - 1u) {
             const uint32_t t = 32u + (uint32_t)__ffs(m) - 1u;
-            take_candidate<true, uint32_t>(s, load_rec(bp, ccold, t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), list, out, rec, vel, stats);
+            take_candidate<true, uint32_t>(s, rec_of(src(t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), ccold), list, out, rec, vel, stats);
         }
     }
     if (valid && !fits) {   // more than 64 candidates (or a wrapped / tall cell range)
@@ -874,6 +916,240 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
             } else {
                 B.pos[b] = p;
             }
+        }
+    }
+    warp_add_u64(&stats->collisions, out.n_pairs);
+    if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, out.n_coinc);
+        unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
+        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-tile (BLOBS_PARAM_TUNE 11): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
+// the cell-sorted array instead of one per body slot, 256 consecutive records per CTA. The records a CTA's bodies can
+// touch then form three contiguous windows of the same array (the linear cell range [cA-1, cB+1] of the tile's own cells,
+// and that range shifted one table row up and down), which the CTA stages in shared memory with coalesced 16-byte loads:
+// the candidate scan and the narrowphase read shared memory, where k_main issues 9-12 dependent L2 loads per thread.
+// Dependent memory rounds per CTA: own record -> window bounds (6 table entries) -> windows; the per-body state (gathered
+// by slot; slot order ~ cell order in every lattice scene, so the gather stays sector-coherent) and the six table entries of
+// the thread's own range travel under those. x, y, r and the flag bits of the own collider come from the record itself, so
+// cabs[] / cconst[] are not read for default spheres.
+// Anything that does not fit the picture takes the global-memory path of k_main for that thread only: a range that wraps
+// the torus or is not covered by a staged window (window larger than TILE_WCAP records, table edge). Same arithmetic, same
+// summation order as k_main => bit-identical results. Requires: every alive body has at least one collider (host checks
+// n_loose == 0); colliders of multi-collider bodies are skipped here and done by k_multi as before.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_THREADS = 256;
+// records per staged window (own 256 + two halo cells, with slack); the pooled variant also holds the per-warp queues and
+// must stay under the 48 KB of static shared memory
+template <bool POOLED> struct TileCfg { static constexpr int WCAP = POOLED ? 320 : 384; };
+#ifdef BLOBS_EMU
+inline unsigned long long tile_path_count[2] = {0, 0};   // [0] shared-memory windows, [1] global-memory fallback
+#endif
+
+template <bool POOLED>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+                                                          Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries) {
+    constexpr uint32_t WCAP = (uint32_t)TileCfg<POOLED>::WCAP;
+    __shared__ float4 win[3 * WCAP];
+    __shared__ PoolSmem pool[POOLED ? TILE_THREADS / 32 : 1];
+    __shared__ uint32_t wlo[3], whi[3];
+    __shared__ uint32_t cab[2];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t i0 = blockIdx.x * TILE_THREADS;
+    const uint32_t nrec = __ldg(bp.tab + n_entries);      // total number of records (last table entry)
+    if (i0 >= nrec) return;                               // CTA-uniform
+    const bool valid = i0 + tid < nrec;
+    // round 1: the own record
+    const float4 h = __ldg(bp.hot + (valid ? i0 + tid : i0));
+    const uint32_t hw = __float_as_uint(h.w);
+    const uint32_t c = hw & HOT_SLOT_MASK;
+    const bool cold = (hw & HOT_COLD_BIT) != 0u;
+    const uint32_t lastv = min((uint32_t)TILE_THREADS - 1u, nrec - 1u - i0);
+    uint32_t mycell = cell_index(g, bin_coord(h.x, g.inv_cell), bin_coord(h.y, g.inv_cell));   // what publish_collider / k_count binned it to
+    const CellRange R = cell_range(g, h.x, h.y, h.z);
+    const bool plain = !(R.ny > 3u || R.c0 + R.nx > g.W);
+    // round 2: body state at the SPECULATED body slot b == c (lock-step insertion), cold half for non-default records,
+    // and (single world: the table index does not depend on the body) the six table entries of the own range
+    uint32_t b = min(c, P.n_bodies - 1u);
+    uint2 info = B.binfo[b];
+    float2 mg = B.bmg[b];
+    float2 p = B.pos[b];
+    float2 po = B.pos_old[b];
+    float2 acc0 = B.acc[b];
+    bool hv = B.has_vreq[b] != 0;
+    uint4 ce = make_uint4(0u, 0xffffffffu, 0xffffffffu, 0u);
+    uint32_t cf = CF_ACTIVE;                              // default record: active, no offset, not a sensor
+    if (cold) {
+        ce = __ldg(Cc.ccold + c);
+        cf = Cc.cconst[c].y;
+    }
+    uint32_t tlo[3], tcnt[3];
+    uint32_t wbase = 0u;
+    if (g.n_worlds == 1u) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            uint32_t row = R.r0 + j;
+            if (row >= g.H) row -= g.H;
+            const bool rv = plain && (uint32_t)j < R.ny;
+            const uint32_t idx = rv ? row * g.W + R.c0 : 0u;
+            const uint32_t a = __ldg(bp.tab + idx), e = __ldg(bp.tab + idx + (rv ? R.nx : 0u));
+            tlo[j] = a;
+            tcnt[j] = e - a;
+        }
+    }
+    bool mine = valid;
+    if (sv.olist != nullptr) mine = mine && sv.cowned[c] != 0;   // strip mode: ghost records belong to the neighbour rank
+    if (mine && (b != c || info.y != c)) {                // speculation missed: fetch the real parent
+        b = Cc.cparent[c];
+        info = B.binfo[b];
+        mg = B.bmg[b];
+        p = B.pos[b];
+        po = B.pos_old[b];
+        acc0 = B.acc[b];
+        hv = B.has_vreq[b] != 0;
+        if (info.y != c) mine = false;                    // collider of a multi-collider body: k_multi does that body
+    }
+    if (g.n_worlds > 1u) {
+        wbase = B.bworld[b] * g.ncells;
+        mycell += wbase;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            uint32_t row = R.r0 + j;
+            if (row >= g.H) row -= g.H;
+            const bool rv = plain && (uint32_t)j < R.ny;
+            const uint32_t idx = wbase + (rv ? row * g.W + R.c0 : 0u);
+            const uint32_t a = __ldg(bp.tab + idx), e = __ldg(bp.tab + idx + (rv ? R.nx : 0u));
+            tlo[j] = a;
+            tcnt[j] = e - a;
+        }
+    }
+    // the tile's own linear cell range [cA, cB] (records are sorted by cell)
+    if (tid == 0u) cab[0] = mycell;
+    if (tid == lastv) cab[1] = mycell;
+    __syncthreads();
+    if (tid < 3u) {   // window k: cells [cA - 1, cB + 1] shifted by (k - 1) table rows, as a record range
+        const long long shift = ((long long)tid - 1) * (long long)g.W;
+        long long lo = (long long)cab[0] + shift - 1, hi = (long long)cab[1] + shift + 2;
+        lo = lo < 0 ? 0 : (lo > (long long)n_entries ? (long long)n_entries : lo);
+        hi = hi < 0 ? 0 : (hi > (long long)n_entries ? (long long)n_entries : hi);
+        uint32_t a = 0u, e = 0u;
+        if (hi > lo) {
+            a = __ldg(bp.tab + (uint32_t)lo);
+            e = __ldg(bp.tab + (uint32_t)hi);
+            if (e - a > WCAP) e = a;                      // too crowded to stage: its users take the global path
+        }
+        wlo[tid] = a;
+        whi[tid] = e;
+    }
+    __syncthreads();
+    // round 3: stage the windows (coalesced)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t a = wlo[k], n = whi[k] - a;
+        for (uint32_t j = tid; j < n; j += TILE_THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
+    }
+    __syncthreads();
+
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
+    unsigned int n_over = 0;
+    const uint32_t flags = info.x;
+    const bool do_gather = mine && P.collisions_enabled != 0u;
+    bool deferred = false;
+    SelfCol s;
+    s.x = h.x; s.y = h.y; s.r = h.z; s.m = mg.x;
+    s.memb = ce.y; s.filt = ce.z; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (hw & HOT_SENSOR_BIT) != 0u;
+    // where the three row spans of this thread sit in shared memory
+    LaneSpan L;
+    bool staged = do_gather && plain;
+    {
+        uint32_t so[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            so[j] = 0u;
+            if (staged && tcnt[j]) {
+                const uint32_t a = tlo[j], e = a + tcnt[j];
+                if (a >= wlo[1] && e <= whi[1]) so[j] = WCAP + (a - wlo[1]);
+                else if (a >= wlo[0] && e <= whi[0]) so[j] = a - wlo[0];
+                else if (a >= wlo[2] && e <= whi[2]) so[j] = 2u * WCAP + (a - wlo[2]);
+                else staged = false;
+            }
+        }
+        L.n0 = tcnt[0]; L.n01 = tcnt[0] + tcnt[1]; L.total = L.n01 + tcnt[2];
+        L.off0 = so[0]; L.off1 = so[1] - L.n0; L.off2 = so[2] - L.n01;
+        L.lo0 = WCAP;                                     // a staged record (the middle window holds the tile's own)
+        L.ranged = do_gather && plain;
+        L.fits = staged && L.total <= 64u;
+    }
+#ifdef BLOBS_EMU   // host-compiled test build only: lets a test assert which path its bodies took
+    if (do_gather) tile_path_count[staged ? 0 : 1]++;
+#endif
+    ContactList<uint32_t> list;
+    list.clear();
+    bool applied = false, big = false;
+    const StagedHot src{win};
+    if (POOLED) {   // warp-collective: every lane calls. Lanes whose range is not staged take gather_single inside (global memory).
+        applied = gather_warp_core<4>(g, bp, src, Cc.ccold, do_gather, s, L, list, out, rec, B.vel, stats, pool[tid >> 5], P.pool_min,
+                                      P.crowded != 0u, big, p.x, p.y);
+    } else if (do_gather) {
+        if (staged) {
+            const uint32_t n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
+            const float srk = s.r * 1.00005f;              // prefilter: see gather_single
+            for (uint32_t base = 0; base < total; base += 32u) {
+                const uint32_t lim = min(32u, total - base);
+                uint32_t mask = 0;
+                for (uint32_t q = 0; q < lim; ++q) {
+                    const uint32_t t = base + q;
+                    const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
+                    const uint32_t oslot = __float_as_uint(o.w) & HOT_SLOT_MASK;
+                    const float dx = s.x - o.x, dy = s.y - o.y;
+                    const float d2 = __fmaf_rn(dx, dx, dy * dy);
+                    const float mdk = __fmaf_rn(o.z, 1.00005f, srk);
+                    if (oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << q;
+                }
+                while (mask) {
+                    const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
+                    mask &= mask - 1u;
+                    const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
+                    take_candidate<true, uint32_t>(s, rec_of(o, Cc.ccold), list, out, rec, B.vel, stats);
+                }
+            }
+        } else {
+            gather_single<true, uint32_t, 4>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
+        }
+    }
+    if (big) {   // k_crowded does the whole body, pair counting included
+        n_over = 1;
+        P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
+        deferred = true;
+    } else if (do_gather && !applied) {
+        if (!list.overflow) {
+            for (int q = 0; q < list.n; ++q) { p.x = fadd(p.x, list.cx[q]); p.y = fadd(p.y, list.cy[q]); }
+        } else {
+            n_over = 1;
+            if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
+                P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
+                deferred = true;
+            } else {
+                SelfCol s2 = s;
+                p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
+            }
+        }
+    }
+    if (mine) {
+        if (deferred) {
+            // nothing: every array of this body is left untouched for k_crowded
+        } else if (!(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_integrate after the joint projection
+            float sx, sy, rot;
+            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+            const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, wbase, sx, sy, rot);
+            if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, c, cf, a, h.z, sv.send_l, sv.send_r);
+        } else {
+            B.pos[b] = p;
         }
     }
     warp_add_u64(&stats->collisions, out.n_pairs);

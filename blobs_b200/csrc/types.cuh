@@ -161,6 +161,7 @@ struct StripView {
     void* send_l;
     void* send_r;
     StripDesc S;
+    const uint8_t* cowned;     // per collider slot: owned by this rank (k_tile enumerates records, ghosts included)
 };
 
 struct Recording {           // optional pair/event output

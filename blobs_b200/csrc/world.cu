@@ -81,6 +81,8 @@ int World::init() {
     CU(cudaEventCreate(&ev_step1));
     CU(cudaFuncSetAttribute(k_joints_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
     CU(cudaFuncSetAttribute(k_joints_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
+    // k_tile<POOLED> holds 46 KB of windows + queues per CTA: ask for the large shared-memory carve-out so that 4 CTAs fit an SM
+    CU(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (params.body_capacity_hint) {
         const size_t n = params.body_capacity_hint;
         CU(pos.ensure(n, stream)); CU(pos_old.ensure(n, stream)); CU(acc.ensure(n, stream)); CU(vel.ensure(n, stream));
@@ -748,8 +750,9 @@ int World::rebuild_topology() {
             if (x.desc.offset.translation.x != 0.0f || x.desc.offset.translation.y != 0.0f) f |= CF_OFFSET;
             // default cold half? (sole collider of its body, mass exactly 4r, groups ALL, not a sensor) — otherwise the narrowphase
             // must fetch ccold[]. Event recording needs the partner's real parent slot, so it flags everything.
+            // (a collider with an offset is flagged too: k_tile takes "not flagged" to mean "snapshot == body position")
             bool dflt = p != NO_SLOT && !x.desc.is_sensor && x.desc.memberships == 0xffffffffu && x.desc.filter == 0xffffffffu &&
-                        rec_mode != BLOBS_RECORD_EVENTS;
+                        rec_mode != BLOBS_RECORD_EVENTS && !(f & CF_OFFSET);
             if (dflt) {
                 const HBody& pb = hb[p];
                 size_t live = 0;
@@ -778,6 +781,7 @@ int World::rebuild_topology() {
     any_dynamic = false;
     std::vector<uint8_t> world_has_first(n_worlds, 0);
     n_simple = 0;
+    n_loose = 0;
     for (uint32_t b = 0; b < nb; ++b) {
         uint32_t f = 0;
         int32_t bc = BODY_NO_COLLIDER;
@@ -803,7 +807,7 @@ int World::rebuild_topology() {
                 v_mb_body.push_back(b);
                 v_mb_cols.insert(v_mb_cols.end(), cs.begin(), cs.end());
                 v_mb_off.push_back((uint32_t)v_mb_cols.size());
-            } else n_simple++;
+            } else { n_simple++; n_loose++; }   // no collider: only k_main / k_integrate (one thread per body slot) reach it
         }
         binfo.set(b, make_uint2(f, (uint32_t)bc));
     }
@@ -1007,7 +1011,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
     MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
     MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
-    MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim)
+    MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim) MIXV(n_loose) MIXV(n_active_cols)
     const BodyArrays B = body_arrays();
     const ColliderArrays C = col_arrays();
     mix(&B, sizeof(B));
@@ -1125,7 +1129,15 @@ int World::launch_substep(const SubstepParams& P_in) {
             else BLOBS_LAUNCH_MAIN(false, false, BT, MB, false);            \
         }                                                                   \
     } while (0)
-            if (pooled && tune == 0) {  // contact-rich state: warp-pooled resolution
+            if (tune == 11 && fused && ordered && n_loose == 0 && n_active_cols) {
+                // one thread per cell-sorted record, candidate windows staged in shared memory (kernels.cuh: k_tile).
+                // Strip mode: the records are the owned colliders plus the ghosts received for this table (skipped by their threads).
+                const size_t nrec_bound = strip_on ? (size_t)std::max<uint32_t>(olaunch_dim, 1) + 2 * (size_t)strip.gcap : (size_t)n_active_cols;
+                const unsigned gt = cdiv(nrec_bound, TILE_THREADS);
+                const uint32_t n_ent = (uint32_t)(table_entries() - 1);
+                if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent);
+                else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent);
+            } else if (pooled && tune == 0) {  // contact-rich state: warp-pooled resolution
                 if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 4, true);
                 else BLOBS_LAUNCH_MAIN(false, true, 4, 4, true);
             } else if (pooled && tune == 8) {  // same with 85 registers per thread (3 CTAs per SM)
@@ -1856,6 +1868,7 @@ StripView World::strip_view() {
         v.send_l = msg[0];
         v.send_r = msg[1];
         v.S = strip;
+        v.cowned = d_cowned.d;
     }
     return v;
 }
@@ -2035,3 +2048,13 @@ int World::profile_read(float* ms, uint64_t* nl, size_t n) {
 }
 
 }  // namespace blobs
+
+#ifdef BLOBS_EMU
+// host-compiled test build only (tests/emu): how many bodies k_tile served from its shared-memory windows / from the
+// global-memory fallback since the last call. Not part of the C ABI, absent from libblobs_b200.so.
+extern "C" void blobs_emu_tile_paths(unsigned long long* out2) {
+    out2[0] = blobs::tile_path_count[0];
+    out2[1] = blobs::tile_path_count[1];
+    blobs::tile_path_count[0] = blobs::tile_path_count[1] = 0;
+}
+#endif

@@ -309,7 +309,7 @@ class World {
     std::string topo_error_msg;
     bool any_dynamic = false;
     float r_max = 0.f;
-    uint32_t n_simple = 0, n_multi = 0, n_sb = 0, n_islands = 0, n_springs_live = 0, n_joints_live = 0, n_active_cols = 0;
+    uint32_t n_simple = 0, n_multi = 0, n_sb = 0, n_islands = 0, n_springs_live = 0, n_joints_live = 0, n_active_cols = 0, n_loose = 0;
     DevBuf<uint32_t> mb_body, mb_off, mb_cols, sb_body, sb_off, sb_edge, isl_off, isl_joint;
     DevBuf<SpringParams> d_springs;
     DevBuf<JointParams> d_joints;

@@ -232,7 +232,8 @@ typedef struct emuGraph* cudaGraph_t;
 typedef struct emuGraphExec* cudaGraphExec_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1, cudaStreamCaptureModeThreadLocal = 1, cudaEventRecordExternal = 1, cudaEventDisableTiming = 2 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorNotSupported ? "not supported by the CPU test build" : "error"); }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }

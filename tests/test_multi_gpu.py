@@ -38,8 +38,10 @@ def test_strip_world_matches_single_gpu():
 @pytest.mark.emu
 @pytest.mark.parametrize("knobs", [{}, {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
-                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"}],
-                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default"])
+                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"},
+                                   {"BLOBS_B200_TUNE": "11"},
+                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}],
+                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-tile", "shell-tile-forced-pool-crowded"])
 def test_strip_world_matches_single_world_emulated_ranks(knobs):
     """The same worker without GPUs: 2 CPU processes, each running the host-compiled build of the CUDA sources (tests/emu),
     exchanging ghosts and migrants every substep through a socket stand-in for NCCL; merged result == single world, bit for

@@ -234,7 +234,7 @@ def run_ours(args):
         nx, ny = 512 * world, 4096
         sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * max(nx, ny), name="cfg5", cell_size=1.0)
         desc = (f"cfg5 family: one world of {nx}x{ny} = {nx * ny} spheres r=0.5 (pitch 1.05, circle R={0.8 * max(nx, ny):.0f}), strip-decomposed over {world} GPUs "
-                f"({nx * ny // world} spheres per GPU), ghost/migration exchange every substep via grouped ncclSend/ncclRecv")
+                f"({nx * ny // world} spheres per GPU), ghost/migration exchange with both neighbours every substep")
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
         edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
@@ -406,13 +406,16 @@ def run_ours(args):
                        "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow,
                        "crowded_mode": int(w.get_param(blobs_b200.abi.PARAM_CROWDED)), "pool_mode": int(w.get_param(blobs_b200.abi.PARAM_POOL)),
                        "sim_time_s": [W * DT, (W + K) * DT],
-                       "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1])},
+                       "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1]),
+                       "strip_exchange": (("peer-memory stores over NVLink (k_strip_push, CUDA IPC)" if int(w.get_param(blobs_b200.abi.PARAM_STRIP_P2P)) else "grouped ncclSend/ncclRecv")
+                                          if strips_on else None),
+                       "main_kernel": "k_tile" if args.tune == 11 else "k_main"},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,
                     "checksum_mean_y": checksum, "host_io": e2e_mode,
                     "sync_value": (n_total * sync_sample[0] / sync_sample[1]) if sync_sample else None},
             "gpu_launches": launches_total,
-            "roofline": {"bound": "hbm", "kernel": "k_main<fused,ordered> (contacts + verlet + snapshot + clamp + cell binning)",
+            "roofline": {"bound": "hbm", "kernel": ("k_tile" if args.tune == 11 else "k_main<fused,ordered>") + " (contacts + verlet + snapshot + clamp + cell binning)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": B_MAIN * n, "avg_launch_ms": main_ms / max(main_n, 1),
                          "timing": "CUDA events around every k_main launch, second timed pass of the same K steps",

@@ -1930,6 +1930,73 @@ __global__ void __launch_bounds__(256) k_strip_pack(BodyArrays B, ColliderArrays
     strip_pack_one(B, Cc, S, c, cc.y, Cc.cabs[c], __uint_as_float(cc.x), send_l, send_r);
 }
 
+// Peer-memory exchange (BLOBS_PARAM_STRIP_P2P): the fused "pack -> send -> receive" step of a substep as ONE small kernel.
+// k_main has packed the outgoing messages into send_l / send_r (local memory). Every CTA copies a slice of their USED part
+// (header counts, not the fixed capacity NCCL has to move) into the neighbours' receive buffers peer_l / peer_r - device
+// memory of the neighbouring GPUs mapped through CUDA IPC, so these are plain stores that travel over NVLink. Each CTA fences
+// its stores at system scope and bumps `done`; the last one publishes the two headers with the exchange sequence number in
+// StripHeader::pad (after another system fence), then spins (volatile loads, served by L2 where the peer's stores land)
+// until both incoming headers carry this sequence number; the kernels that follow in the stream read the received messages.
+// A wait that exceeds ~4 s (a peer died or the ranks fell out of step) raises bit 3 of stats.nan_flag instead of hanging.
+constexpr int STRIP_PUSH_CTAS = 8;
+#ifdef BLOBS_EMU
+constexpr long long STRIP_WAIT_TICKS = 120ll * 1000000000ll;   // host-compiled build: clock64() counts nanoseconds, ranks are slow
+#else
+constexpr long long STRIP_WAIT_TICKS = 1ll << 33;
+#endif
+
+__global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* send_l, const void* send_r, void* peer_l, void* peer_r,
+                                                    const void* recv_l, const void* recv_r, uint32_t seq, unsigned int* done, DeviceStats* stats) {
+    __shared__ bool last;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const void* src = side ? send_r : send_l;
+        void* dst = side ? peer_r : peer_l;
+        if (dst == nullptr) continue;
+        const StripHeader* h = reinterpret_cast<const StripHeader*>(src);
+        const uint32_t ng = min(h->n_ghost, S.gcap), nm4 = min(h->n_mig, S.mcap) * (uint32_t)(sizeof(MigRec) / 16);
+        const float4* sg = strip_ghosts(const_cast<void*>(src));
+        float4* dg = strip_ghosts(dst);
+        for (uint32_t i = gtid; i < ng; i += gsz) dg[i] = sg[i];
+        const float4* sm = reinterpret_cast<const float4*>(strip_migs(const_cast<void*>(src), S.gcap));
+        float4* dm = reinterpret_cast<float4*>(strip_migs(dst, S.gcap));
+        for (uint32_t i = gtid; i < nm4; i += gsz) dm[i] = sm[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!last) return;   // CTA-uniform
+    const int side = (int)(threadIdx.x & 1u);
+    if (threadIdx.x < 2u) {
+        const void* src = side ? send_r : send_l;
+        void* dst = side ? peer_r : peer_l;
+        if (threadIdx.x == 0) *done = 0u;
+        if (dst != nullptr) {
+            __threadfence_system();   // every CTA's slice is visible before the header says so
+            const StripHeader* h = reinterpret_cast<const StripHeader*>(src);
+            volatile StripHeader* d = reinterpret_cast<volatile StripHeader*>(dst);
+            d->n_ghost = h->n_ghost;
+            d->n_mig = h->n_mig;
+            d->overflow = h->overflow;
+            __threadfence_system();
+            d->pad = seq;
+        }
+    }
+    __syncthreads();
+    // ... and the same CTA waits for the neighbours' messages of this exchange: both of mine are out by now, so the wait can
+    // never sit in front of the publication it mirrors, whatever order CTAs (or, in the host-compiled build, fibers) run in
+    if (threadIdx.x < 2u && (side ? S.has_right : S.has_left)) {
+        const volatile StripHeader* h = reinterpret_cast<const volatile StripHeader*>(side ? recv_r : recv_l);
+        const long long t0 = clock64();
+        while (h->pad != seq) {
+            if (clock64() - t0 > STRIP_WAIT_TICKS) { atomicOr(&stats->nan_flag, 8u); break; }
+        }
+        __threadfence_system();
+    }
+}
+
 // bins the received ghosts into the table under construction (before k_scan)
 __global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc S, const void* recv_l, const void* recv_r, uint32_t* tab_next,
                                                           uint32_t* tile_next, uint2* gcell, DeviceStats* stats) {

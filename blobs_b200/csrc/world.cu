@@ -40,6 +40,23 @@ constexpr unsigned CROWD_GRID = 148 * 12;
 static inline uint32_t h_slot(uint64_t h) { return (uint32_t)h; }
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 
+// device allocation that another process can map. Real CUDA: any cudaMalloc block has an IPC handle; the host-compiled test
+// build needs memory shared between its rank processes.
+static cudaError_t blobs_ipc_alloc(char** p, size_t bytes) {
+#ifdef BLOBS_EMU
+    return ::emu::ipc_alloc(reinterpret_cast<void**>(p), bytes);
+#else
+    return cudaMalloc(p, bytes);
+#endif
+}
+static void blobs_ipc_free(char* p) {
+#ifdef BLOBS_EMU
+    ::emu::ipc_free(p);
+#else
+    cudaFree(p);
+#endif
+}
+
 int World::cuda_fail(cudaError_t e, const char* what) {
     err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
     return BLOBS_ERR_CUDA;
@@ -55,6 +72,7 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_POOL_MIN")) pool_min = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
     graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
 #endif
@@ -118,6 +136,9 @@ World::~World() {
     d_qcentre.release(); d_qradius.release(); d_qcount.release(); d_qoff.release(); d_qhits.release();
     rec_pairs.release(); rec_vels.release(); d_sub_end.release(); d_forces.release(); d_constraints.release(); d_cellx.release(); d_celly.release();
     for (int i = 0; i < 4; ++i) if (msg[i]) cudaFree(msg[i]);
+    for (int i = 0; i < 2; ++i) if (p2p_peer[i]) cudaIpcCloseMemHandle(p2p_peer[i]);
+    if (p2p_block) blobs_ipc_free(p2p_block);
+    if (d_push_done) cudaFree(d_push_done);
     d_owned.release(); d_cowned.release(); gcell.release(); io_slots.release(); io_xy.release(); olist.release(); opos.release();
     if (d_ocount) cudaFree(d_ocount);
     if (d_io_count) cudaFree(d_io_count);
@@ -148,6 +169,10 @@ int World::set_param(int id, double v) {
         case BLOBS_PARAM_CROWDED: crowded_mode = (int)v; break;
         case BLOBS_PARAM_POOL: pool_mode = (int)v; break;
         case BLOBS_PARAM_POOL_MIN: pool_min = (uint32_t)v; break;
+        case BLOBS_PARAM_STRIP_P2P:
+            if (strip_on) return fail(BLOBS_ERR_INVALID, "BLOBS_PARAM_STRIP_P2P must be set before blobs_strip_configure");
+            p2p_request = v != 0;
+            break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
         case BLOBS_PARAM_STRIP_MAX_GHOSTS: last_max_ghosts = (uint32_t)v; break;      // reset
         case BLOBS_PARAM_STRIP_MAX_MIGRANTS: last_max_migrants = (uint32_t)v; break;  // reset
@@ -179,6 +204,7 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_CROWDED: *out = crowded_mode; break;
         case BLOBS_PARAM_POOL: *out = pool_mode; break;
         case BLOBS_PARAM_POOL_MIN: *out = pool_min; break;
+        case BLOBS_PARAM_STRIP_P2P: *out = strip_on ? (p2p_on ? 1.0 : 0.0) : (p2p_request ? 1.0 : 0.0); break;
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
         case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
@@ -1018,7 +1044,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     mix(&C, sizeof(C));
     MIXV(hot_a.d) MIXV(hot_b.d) MIXV(tab_a.d) MIXV(tab_b.d) MIXV(tile_a.d) MIXV(tile_b.d) MIXV(d_constraints.d) MIXV(mb_body.d) MIXV(mb_off.d) MIXV(mb_cols.d)
     MIXV(sb_body.d) MIXV(sb_off.d) MIXV(sb_edge.d) MIXV(d_springs.d) MIXV(isl_off.d) MIXV(isl_joint.d) MIXV(d_joints.d) MIXV(d_joints_inter.d)
-    MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3])
+    MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3]) MIXV(p2p_on)
 #undef MIXV
     return h ? h : 1;
 }
@@ -1840,6 +1866,13 @@ int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const u
         CU(cudaMalloc(&msg[i], msg_bytes));
         CU(cudaMemsetAsync(msg[i], 0, msg_bytes, stream));
     }
+    cur_recv[0] = msg[2];
+    cur_recv[1] = msg[3];
+    p2p_on = false;
+    if (nranks > 1 && p2p_request) {
+        rc = strip_p2p_setup();
+        if (rc) return rc;
+    }
     CU(gcell.ensure(2 * (size_t)strip.gcap, stream));
     const size_t nb = bodies.slots(), nc = cols.slots();
     CU(d_owned.ensure(std::max<size_t>(nb, 1), stream));
@@ -1890,8 +1923,74 @@ int World::strip_rebuild_olist() {
     return BLOBS_OK;
 }
 
+// Peer-memory exchange set-up: allocate my receive block, swap IPC handles with both neighbours (one grouped ncclSend/ncclRecv
+// of 64 bytes - NCCL is only the rendezvous here), map their blocks, then agree across ALL ranks (nranks - 1 rounds of
+// neighbour min) whether everybody succeeded: the exchange is either peer stores on every rank or NCCL on every rank.
+int World::strip_p2p_setup() {
+    ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    p2p_stride = (msg_bytes + 255) / 256 * 256;
+    int ok = 1;
+    if (blobs_ipc_alloc(&p2p_block, 4 * p2p_stride) != cudaSuccess) { cudaGetLastError(); p2p_block = nullptr; ok = 0; }
+    cudaIpcMemHandle_t hmine{}, hpeer[2]{};
+    if (ok) {
+        CU(cudaMemsetAsync(p2p_block, 0, 4 * p2p_stride, stream));
+        if (cudaIpcGetMemHandle(&hmine, p2p_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    if (!d_push_done) { CU(cudaMalloc(&d_push_done, sizeof(unsigned int))); CU(cudaMemsetAsync(d_push_done, 0, sizeof(unsigned int), stream)); }
+    char* d_h = nullptr;   // [mine | from left | from right] handles, then [mine | left | right] ok words
+    CU(cudaMalloc(&d_h, 3 * 64 + 3 * sizeof(int)));
+    int* d_ok = reinterpret_cast<int*>(d_h + 3 * 64);
+    CU(cudaMemcpyAsync(d_h, &hmine, 64, cudaMemcpyHostToDevice, stream));
+    auto swap = [&](const void* send, void* from_l, void* from_r, size_t n) -> int {
+        NC(g_nccl.GroupStart());
+        if (strip.has_right) { NC(g_nccl.Send(send, n, ncclInt8, s_rank + 1, comm, stream)); NC(g_nccl.Recv(from_r, n, ncclInt8, s_rank + 1, comm, stream)); }
+        if (strip.has_left) { NC(g_nccl.Send(send, n, ncclInt8, s_rank - 1, comm, stream)); NC(g_nccl.Recv(from_l, n, ncclInt8, s_rank - 1, comm, stream)); }
+        NC(g_nccl.GroupEnd());
+        CU(cudaStreamSynchronize(stream));
+        return BLOBS_OK;
+    };
+    int rc = swap(d_h, d_h + 64, d_h + 128, 64);
+    if (rc) return rc;
+    CU(cudaMemcpy(hpeer, d_h + 64, 128, cudaMemcpyDeviceToHost));
+    for (int side = 0; side < 2 && ok; ++side) {
+        if (!(side ? strip.has_right : strip.has_left)) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, hpeer[side], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        p2p_peer[side] = static_cast<char*>(q);
+    }
+    for (int round = 0; round + 1 < s_nranks; ++round) {   // global AND of `ok` along the chain of strips
+        int h3[3] = {ok, 1, 1};
+        CU(cudaMemcpy(d_ok, h3, sizeof(h3), cudaMemcpyHostToDevice));
+        rc = swap(d_ok, d_ok + 1, d_ok + 2, sizeof(int));
+        if (rc) return rc;
+        CU(cudaMemcpy(h3, d_ok, sizeof(h3), cudaMemcpyDeviceToHost));
+        ok = std::min(h3[0], std::min(h3[1], h3[2]));
+    }
+    cudaFree(d_h);
+    p2p_on = ok != 0;
+    return BLOBS_OK;
+}
+
 int World::strip_exchange() {
     if (s_nranks <= 1) return BLOBS_OK;
+    if (p2p_on) {
+        // One kernel instead of the NCCL group: copies the USED part of both outgoing messages straight into the neighbours'
+        // receive buffers (peer stores over NVLink), publishes header + sequence number once every CTA's stores are fenced,
+        // and waits for the two incoming sequence numbers. Buffers alternate with the exchange parity: a neighbour cannot be
+        // two exchanges ahead of me (it waits for my message of the exchange in between), so parity p is free again.
+        const uint32_t seq = (uint32_t)(nccl_exchanges + 1);
+        const size_t par = seq & 1u;
+        cur_recv[0] = p2p_block + (0 * 2 + par) * p2p_stride;
+        cur_recv[1] = p2p_block + (1 * 2 + par) * p2p_stride;
+        void* peer_l = strip.has_left ? p2p_peer[0] + (1 * 2 + par) * p2p_stride : nullptr;    // I am my left neighbour's RIGHT
+        void* peer_r = strip.has_right ? p2p_peer[1] + (0 * 2 + par) * p2p_stride : nullptr;   // and my right neighbour's LEFT
+        BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_strip_push)(strip, msg[0], msg[1], peer_l, peer_r, cur_recv[0], cur_recv[1], seq, d_push_done, d_stats);
+        launches++;
+        CU(cudaGetLastError());
+        nccl_exchanges++;
+        return BLOBS_OK;
+    }
     ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
     NC(g_nccl.GroupStart());
     if (strip.has_right) {
@@ -1941,7 +2040,7 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
             rc = strip_exchange();
             if (rc) return rc;
         }
-        rc = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_strip_bin_ghosts)(grid, strip, msg[2], msg[3], tab_next, tile_next, gcell.d, d_stats); });
+        rc = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_strip_bin_ghosts)(grid, strip, cur_recv[0], cur_recv[1], tab_next, tile_next, gcell.d, d_stats); });
         if (rc) return rc;
     }
     rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_scan)(tab_next, (uint32_t)tn, tab_cur, (uint32_t)tn, tile_next, tile_cur); });
@@ -1954,7 +2053,7 @@ int World::strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* til
         rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_scatter_owned)(B, C, tab_next, hot_next, olist.d, d_ocount); });
         if (rc) return rc;
         rc = run(KC_GHOST, [&] {
-            BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_strip_finish)(B, C, strip, msg[0], msg[1], msg[2], msg[3], tab_next, gcell.d, hot_next,
+            BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_strip_finish)(B, C, strip, msg[0], msg[1], cur_recv[0], cur_recv[1], tab_next, gcell.d, hot_next,
                                                                                                            d_owned.d, d_cowned.d, olist.d, d_ocount, opos.d, (uint32_t)olist.cap, d_stats);
         });
         if (rc) return rc;

@@ -362,6 +362,15 @@ class World {
     uint64_t nccl_exchanges = 0;
     uint32_t last_max_ghosts = 0, last_max_migrants = 0;
     int strip_exchange();
+    // peer-memory exchange (BLOBS_PARAM_STRIP_P2P): my receive block = 4 messages [from left / from right][exchange parity];
+    // the neighbours' blocks are mapped through CUDA IPC and written by k_strip_push over NVLink
+    bool p2p_request = false, p2p_on = false;
+    char* p2p_block = nullptr;          // mine
+    char* p2p_peer[2] = {nullptr, nullptr};   // left / right neighbour's block (IPC mapping)
+    size_t p2p_stride = 0;
+    unsigned int* d_push_done = nullptr;
+    void* cur_recv[2] = {nullptr, nullptr};   // receive buffers of the exchange in flight (== msg[2], msg[3] on the NCCL path)
+    int strip_p2p_setup();
     int strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch);
 
     // profiling

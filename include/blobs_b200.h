@@ -90,6 +90,10 @@ typedef enum BlobsParamId {
                                             pair per lane, rank-ordered sums; for contact-rich states), 2 (default) = automatic, by the
                                             contact density of the previous step call. Never changes results. */
     ,BLOBS_PARAM_POOL_MIN = 21           /* pooled path: minimum prefilter survivors in a warp (default 16) */
+    ,BLOBS_PARAM_STRIP_P2P = 22          /* strip mode, set BEFORE blobs_strip_configure: 1 = exchange ghosts / migrants by direct peer-memory
+                                            stores over NVLink (neighbours' receive buffers mapped through CUDA IPC, one push kernel per
+                                            substep) instead of grouped ncclSend/ncclRecv; falls back to NCCL on every rank if any rank
+                                            cannot map its neighbours. Reads back 1 only while the peer path is active. Never changes results. */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

@@ -5,8 +5,9 @@
 #  1. the GPU parity suite (new since the last GPU run: perf counters, RigidBodyMut, removal/event ring, pipelined host I/O,
 #     debug_data, scene queries, 128-thread k_main variants)
 #  2. default bench line (pipelined e2e gets its first measurement here) + the blocking e2e loop for comparison
-#  3. k_main variant sweep in the two regimes of config #2: TUNE 0 (256-thread CTAs), 9 (128-thread, auto pooled), 10 (128-thread,
-#     per-lane), 8 (pooled, 3 CTAs/SM); sparse window = --warmup 60 --steps 30, dense window = the default
+#  3. k_main variant sweep in the two regimes of config #2: TUNE 0 (256-thread CTAs), 11 (k_tile: thread per cell-sorted record, candidate
+#     windows in shared memory - the round-2 candidate for the default), 9 (128-thread, auto pooled), 10 (128-thread, per-lane),
+#     8 (pooled, 3 CTAs/SM); sparse window = --warmup 60 --steps 30, dense window = the default
 #  4. ncu: launch list of the default command, and ONE --set full capture of the pooled k_main + k_crowded at step 275
 #     (the profile round 1 could not take: expect the scan phase and the per-pair shuffles on top)
 set -u
@@ -16,14 +17,18 @@ export PYTHONUNBUFFERED=1
 timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
 timeout 300 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
-for t in 0 9 10 8; do
+for t in 0 11 9 10 8; do
   timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
   timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
 done
-timeout 200 python bench.py --workload cfg3 --no-cpu-baseline > $O/cfg3.json 2>> $O/sweep.err
-timeout 200 python bench.py --workload cfg4 --no-cpu-baseline > $O/cfg4.json 2>> $O/sweep.err
+for t in 0 11; do
+  timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
+  timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
+done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 100 --csv --log-file $O/ncu_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_tile" -s 8 -c 1 -o $O/tile_sparse \
+    python bench.py --tune 11 --steps 2 --warmup 3 --no-cpu-baseline --no-flush > $O/ncu_tile.log 2>&1
 CAPTURE_STEPS=277 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_main|k_crowded" --launch-skip 4400 --launch-count 2 \
     -o $O/dense_pooled python profiles/trace_cfg2.py 0 0 2 > $O/ncu_dense.log 2>&1
 ls -la $O

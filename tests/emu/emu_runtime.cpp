@@ -229,3 +229,78 @@ void run_grid(unsigned grid, unsigned block, size_t dyn_smem, const std::functio
 }
 
 }  // namespace emu
+
+// ---------------------------------------------------------------------------------------------- CUDA IPC stand-in
+// A block allocated with emu::ipc_alloc lives in a POSIX shared-memory segment named after the allocating process, so that
+// the rank processes of the emulated strip test can map each other's receive buffers like GPUs map peer memory.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+namespace emu {
+namespace {
+struct IpcSeg { std::string name; size_t bytes; bool owner; };
+std::map<void*, IpcSeg> g_ipc;
+std::mutex g_ipc_mu;
+int g_ipc_counter = 0;
+}  // namespace
+
+cudaError_t ipc_alloc(void** p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    char name[64];
+    snprintf(name, sizeof(name), "/blobs_emu_%d_%d", (int)getpid(), g_ipc_counter++);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return cudaErrorMemoryAllocation;
+    if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); shm_unlink(name); return cudaErrorMemoryAllocation; }
+    void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) { shm_unlink(name); return cudaErrorMemoryAllocation; }
+    memset(q, 0xCD, bytes);
+    g_ipc[q] = IpcSeg{name, bytes, true};
+    *p = q;
+    return cudaSuccess;
+}
+
+void ipc_free(void* p) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    auto it = g_ipc.find(p);
+    if (it == g_ipc.end()) return;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    g_ipc.erase(it);
+}
+
+cudaError_t ipc_get_handle(cudaIpcMemHandle_t* h, void* p) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    auto it = g_ipc.find(p);
+    if (it == g_ipc.end()) return cudaErrorNotSupported;
+    memset(h, 0, sizeof(*h));
+    snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+    const unsigned long long n = it->second.bytes;
+    memcpy(h->reserved + 48, &n, sizeof(n));
+    return cudaSuccess;
+}
+
+cudaError_t ipc_open(void** p, const cudaIpcMemHandle_t& h) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    unsigned long long n = 0;
+    memcpy(&n, h.reserved + 48, sizeof(n));
+    char name[49];
+    memcpy(name, h.reserved, 48);
+    name[48] = 0;
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorNotSupported;
+    void* q = mmap(nullptr, (size_t)n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (q == MAP_FAILED) return cudaErrorNotSupported;
+    g_ipc[q] = IpcSeg{name, (size_t)n, false};
+    *p = q;
+    return cudaSuccess;
+}
+
+cudaError_t ipc_close(void* p) { ipc_free(p); return cudaSuccess; }
+}  // namespace emu

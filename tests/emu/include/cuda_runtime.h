@@ -246,6 +246,21 @@ template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) {
     memset(*p, 0xCD, n);
     return cudaSuccess;
 }
+// ---- CUDA IPC stand-in: "device memory" another rank PROCESS can map = a POSIX shared-memory segment (emu_runtime.cpp)
+typedef struct cudaIpcMemHandle_st { char reserved[64]; } cudaIpcMemHandle_t;
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+namespace emu {
+cudaError_t ipc_alloc(void** p, size_t bytes);
+void ipc_free(void* p);
+cudaError_t ipc_get_handle(cudaIpcMemHandle_t* h, void* p);
+cudaError_t ipc_open(void** p, const cudaIpcMemHandle_t& h);
+cudaError_t ipc_close(void* p);
+}  // namespace emu
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { return emu::ipc_get_handle(h, p); }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { return emu::ipc_open(p, h); }
+static inline cudaError_t cudaIpcCloseMemHandle(void* p) { return emu::ipc_close(p); }
+static inline long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline void __threadfence_system() { __sync_synchronize(); }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = static_cast<T*>(calloc(1, n ? n : 1)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }

@@ -54,6 +54,9 @@ def run(rank, world, local):
     dist.broadcast(uid, 0)
     w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.numpy(), ghost_capacity=1 << 14, migrate_capacity=1 << 10)
     own0 = w.strip_owned()
+    p2p = int(w.get_param(A.PARAM_STRIP_P2P))   # 1 = ghosts / migrants travel by peer-memory stores (k_strip_push), 0 = ncclSend/ncclRecv
+    if os.environ.get("STRIP_TEST_EXPECT_P2P"):
+        assert p2p == int(os.environ["STRIP_TEST_EXPECT_P2P"]), f"rank {rank}: peer-memory exchange active={p2p}"
     collisions = overflow = 0
     for _ in range(steps):
         st = w.step(1 / 60)
@@ -98,7 +101,7 @@ def run(rank, world, local):
                                rc["desc"]["absolute_transform"]["translation"]["x"], rc["desc"]["absolute_transform"]["translation"]["y"]]).astype(np.float32)
         bad = np.nonzero(merged.view(np.uint32) != want.view(np.uint32))[0]
         print(f"[strip test] ranks={world} spheres={n} steps={steps} migrated={migrated} collisions strips={int(t_col)} single={ref_col} "
-              f"list_overflow rank0={overflow} mismatches={len(bad)}")
+              f"list_overflow rank0={overflow} p2p={p2p} mismatches={len(bad)}")
         ok = len(bad) == 0 and int(t_col) == ref_col and (world == 1 or migrated > 0)
         if len(bad):
             print("first mismatches (field*n + slot):", bad[:10], merged[bad[:10]], want[bad[:10]])

@@ -35,13 +35,35 @@ def test_strip_world_matches_single_gpu():
     assert r.returncode == 0
 
 
+@pytest.mark.gpu
+def test_strip_world_peer_memory_exchange_matches_single_gpu():
+    """Same, with the per-substep exchange done by k_strip_push (peer-memory stores through CUDA IPC mappings, BLOBS_PARAM_STRIP_P2P)
+    instead of ncclSend/ncclRecv. The worker asserts that the peer path is really active on every rank."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(REPO, "tests", "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+
+
 @pytest.mark.emu
 @pytest.mark.parametrize("knobs", [{}, {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"},
+                                   {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"},
+                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1", "STRIP_TEST_RANKS": "3",
+                                    "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
                                    {"BLOBS_B200_TUNE": "11"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}],
-                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-tile", "shell-tile-forced-pool-crowded"])
+                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-p2p", "shell-p2p-3ranks-tile-forced", "gas-tile",
+                              "shell-tile-forced-pool-crowded"])
 def test_strip_world_matches_single_world_emulated_ranks(knobs):
     """The same worker without GPUs: 2 CPU processes, each running the host-compiled build of the CUDA sources (tests/emu),
     exchanging ghosts and migrants every substep through a socket stand-in for NCCL; merged result == single world, bit for
@@ -51,8 +73,8 @@ def test_strip_world_matches_single_world_emulated_ranks(knobs):
     build()
     env = dict(os.environ, BLOBS_TEST_EMU="1", STRIP_TEST_SIDE="48", STRIP_TEST_STEPS="24")
     env.update(knobs)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(REPO, "tests", "multi_gpu_worker.py")]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={env.get('STRIP_TEST_RANKS', '2')}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0

@@ -196,6 +196,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap, on_step=None):
+    """K frames of a strip-decomposed world with the pipelined distributed host I/O of the C ABI. `sl`, `xy`, `cnt` are pairs of
+    pinned host tensors (slot list, positions, count); both slot lists / counts hold the current owned list on entry. The newest
+    list that has landed is in pair (K - 1) & 1 on return. Returns the bytes moved. (tests/multi_gpu_worker.py runs this very loop.)"""
+    io_bytes = 0
+    newest = 1                                                    # pair holding the newest list that has landed (frame 0 writes pair 0)
+    m = min(int(cnt[newest][0]), io_cap)
+    w.forces_indexed_upload_async_ptr(sl[newest].data_ptr(), forces.data_ptr(), m)
+    io_bytes += m * 12
+    for i in range(K):
+        w.apply_forces_indexed_uploaded()
+        if i + 1 < K:
+            m = min(int(cnt[newest][0]), io_cap)
+            w.forces_indexed_upload_async_ptr(sl[newest].data_ptr(), forces.data_ptr(), m)   # frame i+1's forces travel under frame i's kernels
+            io_bytes += m * 12
+        st = w.step(DT)
+        if on_step is not None:
+            on_step(st)
+        w.io_sync()                                               # frame i-1's list has landed in pair (i-1)&1; the upload has left pair `newest`
+        if i:
+            newest = (i - 1) & 1
+        w.read_owned_positions_async_ptr(sl[i & 1].data_ptr(), xy[i & 1].data_ptr(), cnt[i & 1].data_ptr(), io_cap)   # under frame i+1's kernels
+        io_bytes += min(int(cnt[newest][0]), io_cap) * 12         # (the copy moves the owned-list bound; counted as the valid part)
+    w.io_sync()
+    return io_bytes
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -333,17 +360,48 @@ def run_ours(args):
             w.step(DT)
             w.read_positions_ptr(pos_out.data_ptr(), nb)   # device -> pinned host (synchronous)
 
-    if strips_on:
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
+    def strip_sync_loop(k):
+        nonlocal n_io
+        moved = 0
+        for _ in range(k):
             w.apply_forces_indexed_ptr(slots_io.data_ptr(), forces.data_ptr(), min(n_io, io_cap))        # pinned host -> device (owned bodies)
-            io_bytes += min(n_io, io_cap) * 12
+            moved += min(n_io, io_cap) * 12
             w.step(DT)
             n_io = w.read_owned_positions_ptr(slots_io.data_ptr(), pos_out.data_ptr(), io_cap)            # device -> pinned host (synchronous)
-            io_bytes += min(n_io, io_cap) * 12
+            moved += min(n_io, io_cap) * 12
+        return moved
+
+    if strips_on and os.environ.get("BLOBS_BENCH_E2E", "pipelined") == "sync":
+        barrier()
+        t0 = time.perf_counter()
+        io_bytes = strip_sync_loop(K)
         barrier()
         t_e2e = time.perf_counter() - t0
+    elif strips_on:
+        # N > 1: the same pipeline on the distributed host I/O (blobs_forces_indexed_upload_async / blobs_apply_forces_indexed_uploaded /
+        # blobs_read_owned_positions_async): every rank moves the (slot, force) list in and the (slot, position) list out for the
+        # bodies it owns, on its own copy streams. The slot list a frame's forces are addressed to is the newest one that has
+        # landed on the host (two frames old); a body that migrated in between is skipped by its old owner for that frame.
+        ks = max(1, K // 5)
+        barrier()
+        t0 = time.perf_counter()
+        strip_sync_loop(ks)
+        barrier()
+        sync_sample = (ks, time.perf_counter() - t0)
+        e2e_mode = "pipelined"
+        sl = (slots_io, slots_io.clone().pin_memory())
+        xy = (pos_out, torch.zeros_like(pos_out).pin_memory())
+        cnt = (torch.zeros(1, dtype=torch.int32).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory())
+        cnt[0][0] = cnt[1][0] = min(n_io, io_cap)
+        sl[1].copy_(sl[0])
+        barrier()
+        t0 = time.perf_counter()
+        io_bytes = strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        newest = (K - 1) & 1
+        pos_out = xy[newest]
+        n_io = int(cnt[newest][0])
     elif os.environ.get("BLOBS_BENCH_E2E", "pipelined") == "sync":
         barrier()
         t0 = time.perf_counter()

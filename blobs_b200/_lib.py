@@ -80,6 +80,9 @@ SIGNATURES = {
     "blobs_strip_configure": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, C.c_uint32, C.c_uint32]),
     "blobs_strip_owned": (C.c_int32, [_vp, _vp, C.c_size_t]),
     "blobs_read_owned_positions": (C.c_int32, [_vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "blobs_forces_indexed_upload_async": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
+    "blobs_apply_forces_indexed_uploaded": (C.c_int32, [_vp]),
+    "blobs_read_owned_positions_async": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_size_t]),
     "blobs_apply_forces_indexed": (C.c_int32, [_vp, _vp, _vp, C.c_size_t]),
 }
 

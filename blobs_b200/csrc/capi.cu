@@ -200,6 +200,9 @@ int32_t blobs_strip_configure(BlobsWorld* w, int32_t rank, int32_t nranks, float
 }
 int32_t blobs_read_owned_positions(BlobsWorld* w, uint32_t* slots, float* xy, size_t cap, size_t* n) { W_OR_INVALID(w); W_OR_INVALID(slots); W_OR_INVALID(xy); return w->w.read_owned_positions(slots, xy, cap, n); }
 int32_t blobs_apply_forces_indexed(BlobsWorld* w, const uint32_t* slots, const float* fxy, size_t n) { W_OR_INVALID(w); if (n && (!slots || !fxy)) return BLOBS_ERR_INVALID; return w->w.apply_forces_indexed(slots, fxy, n); }
+int32_t blobs_forces_indexed_upload_async(BlobsWorld* w, const uint32_t* slots, const float* fxy, size_t n) { W_OR_INVALID(w); if (n && (!slots || !fxy)) return BLOBS_ERR_INVALID; return w->w.forces_indexed_upload_async(slots, fxy, n); }
+int32_t blobs_apply_forces_indexed_uploaded(BlobsWorld* w) { W_OR_INVALID(w); return w->w.apply_forces_indexed_uploaded(); }
+int32_t blobs_read_owned_positions_async(BlobsWorld* w, uint32_t* slots, float* xy, uint32_t* n_out, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(slots); W_OR_INVALID(xy); W_OR_INVALID(n_out); return w->w.read_owned_positions_async(slots, xy, n_out, cap); }
 int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* out, size_t cap) { W_OR_INVALID(w); W_OR_INVALID(out); return w->w.strip_owned(out, cap); }
 
 }  // extern "C"

@@ -120,6 +120,8 @@ World::~World() {
     if (io_ready) { cudaStreamSynchronize(s_h2d); cudaStreamDestroy(s_h2d); cudaStreamSynchronize(s_d2h); cudaStreamDestroy(s_d2h); }
     for (cudaEvent_t e : {ev_up_done[0], ev_up_done[1], ev_up_free[0], ev_up_free[1], ev_snap_ready, ev_snap_free}) if (e) cudaEventDestroy(e);
     d_forces_up[0].release(); d_forces_up[1].release(); d_pos_snap.release();
+    d_fslots_up[0].release(); d_fslots_up[1].release(); d_oslots_snap.release(); d_oxy_snap.release();
+    if (d_ocount_snap) cudaFree(d_ocount_snap);
     for (auto& e : ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     destroy_graph(gslot[0]);
     destroy_graph(gslot[1]);
@@ -1592,7 +1594,7 @@ int World::forces_upload_async(const float* f, size_t cap) {
 
 // RigidBody::apply_force (rigid_body.rs:155-160) for every slot of the uploaded batch; the compute stream waits for the copy
 int World::apply_forces_uploaded() {
-    if (up_pending < 0) return fail(BLOBS_ERR_INVALID, "blobs_apply_forces_uploaded: no uploaded batch");
+    if (up_pending < 0 || up_indexed) return fail(BLOBS_ERR_INVALID, "blobs_apply_forces_uploaded: no uploaded batch");
     int rc = flush();
     if (rc) return rc;
     const int k = up_pending;
@@ -1624,6 +1626,78 @@ int World::read_positions_async(float* xy, size_t cap) {
     CU(cudaEventRecord(ev_snap_ready, stream));
     CU(cudaStreamWaitEvent(s_d2h, ev_snap_ready, 0));
     CU(cudaMemcpyAsync(xy, d_pos_snap.d, n * sizeof(float2), cudaMemcpyDeviceToHost, s_d2h));
+    CU(cudaEventRecord(ev_snap_free, s_d2h));
+    snap_used = true;
+    return BLOBS_OK;
+}
+
+// ---- the same pipeline for the distributed (strip) host I/O: indexed forces in, compact (slot, position) list of the owned bodies out
+int World::forces_indexed_upload_async(const uint32_t* slots, const float* f, size_t n) {
+    int rc = io_init();
+    if (rc) return rc;
+    if (up_pending >= 0) return fail(BLOBS_ERR_INVALID, "blobs_forces_indexed_upload_async: the previous batch has not been applied yet");
+    const int k = up_next;
+    up_next ^= 1;
+    if (n) {
+        if (up_used[k]) CU(cudaStreamWaitEvent(s_h2d, ev_up_free[k], 0));   // the kernel that read this buffer two batches ago
+        CU(d_fslots_up[k].ensure(n, s_h2d));
+        CU(d_forces_up[k].ensure(n, s_h2d));
+        CU(cudaMemcpyAsync(d_fslots_up[k].d, slots, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s_h2d));
+        CU(cudaMemcpyAsync(d_forces_up[k].d, f, n * sizeof(float2), cudaMemcpyHostToDevice, s_h2d));
+    }
+    CU(cudaEventRecord(ev_up_done[k], s_h2d));
+    up_pending = k;
+    up_n = n;
+    up_indexed = true;
+    return BLOBS_OK;
+}
+
+int World::apply_forces_indexed_uploaded() {
+    if (up_pending < 0 || !up_indexed) return fail(BLOBS_ERR_INVALID, "blobs_apply_forces_indexed_uploaded: no uploaded indexed batch");
+    int rc = flush();
+    if (rc) return rc;
+    const int k = up_pending;
+    up_pending = -1;
+    up_indexed = false;
+    CU(cudaStreamWaitEvent(stream, ev_up_done[k], 0));
+    if (up_n) {
+        BLOBS_LAUNCH(cdiv(up_n, 256), 256, 0, stream, k_apply_forces_indexed)(body_arrays(), strip_on ? d_owned.d : nullptr, d_fslots_up[k].d, d_forces_up[k].d, (uint32_t)up_n,
+                                                                            (uint32_t)bodies.slots());
+        launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev_up_free[k], stream));
+    up_used[k] = true;
+    return BLOBS_OK;
+}
+
+// compaction on the compute stream into a snapshot pair, PCIe copies (count, slots, positions) on the device-to-host stream
+int World::read_owned_positions_async(uint32_t* slots, float* xy, uint32_t* n_out, size_t cap) {
+    int rc = io_init();
+    if (rc) return rc;
+    rc = flush();
+    if (rc) return rc;
+    const size_t nb = bodies.slots();
+    if (!d_ocount_snap) CU(cudaMalloc(&d_ocount_snap, sizeof(unsigned int)));
+    // entries that can be valid: the owned-list bound of the step just run (strips), every body slot otherwise
+    const size_t m = std::min<size_t>(cap, strip_on ? std::max<size_t>(olaunch_dim, 1) : std::max<size_t>(nb, 1));
+    if (snap_used) CU(cudaStreamWaitEvent(stream, ev_snap_free, 0));   // the previous snapshot is still on its way to the host
+    CU(d_oslots_snap.ensure(std::max<size_t>(m, 1), stream));
+    CU(d_oxy_snap.ensure(std::max<size_t>(m, 1), stream));
+    CU(cudaMemsetAsync(d_ocount_snap, 0, sizeof(unsigned int), stream));
+    if (nb && m) {
+        BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_compact_owned)(body_arrays(), strip_on ? d_owned.d : nullptr, (uint32_t)nb, (uint32_t)std::min<size_t>(m, 0xffffffffu),
+                                                           d_ocount_snap, d_oslots_snap.d, d_oxy_snap.d);
+        launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev_snap_ready, stream));
+    CU(cudaStreamWaitEvent(s_d2h, ev_snap_ready, 0));
+    CU(cudaMemcpyAsync(n_out, d_ocount_snap, sizeof(unsigned int), cudaMemcpyDeviceToHost, s_d2h));
+    if (m) {
+        CU(cudaMemcpyAsync(slots, d_oslots_snap.d, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_d2h));
+        CU(cudaMemcpyAsync(xy, d_oxy_snap.d, m * sizeof(float2), cudaMemcpyDeviceToHost, s_d2h));
+    }
     CU(cudaEventRecord(ev_snap_free, s_d2h));
     snap_used = true;
     return BLOBS_OK;

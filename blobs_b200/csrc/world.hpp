@@ -189,6 +189,9 @@ class World {
     int apply_forces_uploaded();
     int read_positions_async(float* xy, size_t cap);
     int io_sync();
+    int forces_indexed_upload_async(const uint32_t* slots, const float* fxy, size_t n);
+    int apply_forces_indexed_uploaded();
+    int read_owned_positions_async(uint32_t* slots, float* xy, uint32_t* n_out, size_t cap);
     int download_cell_coords(int32_t* cx, int32_t* cy, size_t cap);
     int record_contacts(int mode, size_t cap);
     int events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n);
@@ -397,6 +400,10 @@ class World {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up_done[2] = {nullptr, nullptr}, ev_up_free[2] = {nullptr, nullptr}, ev_snap_ready = nullptr, ev_snap_free = nullptr;
     DevBuf<float2> d_forces_up[2], d_pos_snap;
+    DevBuf<uint32_t> d_fslots_up[2], d_oslots_snap;   // indexed (strip) forms: slot lists beside the force / position payloads
+    DevBuf<float2> d_oxy_snap;
+    unsigned int* d_ocount_snap = nullptr;
+    bool up_indexed = false;
     int up_next = 0, up_pending = -1;
     size_t up_n = 0;
     bool up_used[2] = {false, false}, snap_used = false, io_ready = false;

@@ -292,6 +292,16 @@ class World:
     def apply_forces_indexed_ptr(self, slots_ptr, fxy_ptr, n):
         self._ck(self._lib.blobs_apply_forces_indexed(self._h, C.c_void_p(slots_ptr), C.c_void_p(fxy_ptr), n))
 
+    # pipelined forms (copies on their own streams; io_sync() completes them)
+    def forces_indexed_upload_async_ptr(self, slots_ptr, fxy_ptr, n):
+        self._ck(self._lib.blobs_forces_indexed_upload_async(self._h, C.c_void_p(slots_ptr), C.c_void_p(fxy_ptr), n))
+
+    def apply_forces_indexed_uploaded(self):
+        self._ck(self._lib.blobs_apply_forces_indexed_uploaded(self._h))
+
+    def read_owned_positions_async_ptr(self, slots_ptr, xy_ptr, n_out_ptr, cap):
+        self._ck(self._lib.blobs_read_owned_positions_async(self._h, C.c_void_p(slots_ptr), C.c_void_p(xy_ptr), C.c_void_p(n_out_ptr), cap))
+
     # ---- introspection
     def kernel_info(self):
         k = A.KernelInfo()

@@ -361,6 +361,20 @@ int32_t blobs_strip_owned(BlobsWorld* w, uint8_t* owned_by_body_slot, size_t cap
  * matching indexed RigidBody::apply_force (rigid_body.rs:155-160; entries for bodies owned elsewhere are ignored) */
 int32_t blobs_read_owned_positions(BlobsWorld* w, uint32_t* slots, float* xy, size_t cap, size_t* n);
 int32_t blobs_apply_forces_indexed(BlobsWorld* w, const uint32_t* slots, const float* force_xy, size_t n);
+/* Pipelined forms of the two calls above, for the per-frame loop of a strip-decomposed world (same copy streams and rules as
+ * blobs_forces_upload_async / blobs_read_body_positions_async; blobs_io_sync completes them):
+ *     blobs_forces_indexed_upload_async(w, slots, f, n);
+ *     for each frame i:  blobs_apply_forces_indexed_uploaded(w);
+ *                        blobs_forces_indexed_upload_async(w, slots', f', n');      // travels while step i computes
+ *                        blobs_step(w, delta, &stats);
+ *                        blobs_io_sync(w);                                          // (slots, xy, n) of frame i-1 have arrived
+ *                        blobs_read_owned_positions_async(w, slots_out[i&1], xy_out[i&1], &n_out[i&1], cap);
+ *     blobs_io_sync(w);
+ * `n_out` is written by the device-to-host copy (keep it in pinned memory); the number of entries copied is min(cap, this rank's
+ * current owned-list bound), of which the first *n_out are valid. */
+int32_t blobs_forces_indexed_upload_async(BlobsWorld* w, const uint32_t* slots, const float* force_xy, size_t n);  /* at most one batch may be pending */
+int32_t blobs_apply_forces_indexed_uploaded(BlobsWorld* w);
+int32_t blobs_read_owned_positions_async(BlobsWorld* w, uint32_t* slots, float* xy, uint32_t* n_out, size_t cap);
 
 #ifdef __cplusplus
 }

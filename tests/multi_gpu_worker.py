@@ -58,11 +58,43 @@ def run(rank, world, local):
     if os.environ.get("STRIP_TEST_EXPECT_P2P"):
         assert p2p == int(os.environ["STRIP_TEST_EXPECT_P2P"]), f"rank {rank}: peer-memory exchange active={p2p}"
     collisions = overflow = 0
-    for _ in range(steps):
-        st = w.step(1 / 60)
-        assert st["nan_detected"] == 0, st
-        collisions += st["collisions"]
-        overflow += st["list_overflow"]
+    if os.environ.get("STRIP_TEST_IO") == "pipelined":
+        # the frame loop of bench.py at N > 1 (pipelined distributed host I/O), with zero forces so that the world still has to
+        # equal the undisturbed single world; the (slot, position) list that lands last must be this rank's owned bodies
+        import bench
+
+        tot = {"collisions": 0, "list_overflow": 0}
+
+        def on_step(st):
+            assert st["nan_detected"] == 0, st
+            tot["collisions"] += st["collisions"]
+            tot["list_overflow"] += st["list_overflow"]
+
+        cap = sc.n_bodies
+        pin = (lambda t: t) if os.environ.get("BLOBS_TEST_EMU") == "1" else (lambda t: t.pin_memory())
+        sl = (pin(torch.zeros(cap, dtype=torch.int32)), pin(torch.zeros(cap, dtype=torch.int32)))
+        xy = (pin(torch.zeros((cap, 2), dtype=torch.float32)), pin(torch.zeros((cap, 2), dtype=torch.float32)))
+        cnt = (pin(torch.zeros(1, dtype=torch.int32)), pin(torch.zeros(1, dtype=torch.int32)))
+        forces = pin(torch.zeros((cap, 2), dtype=torch.float32))
+        n0 = w.read_owned_positions_ptr(sl[0].data_ptr(), xy[0].data_ptr(), cap)
+        sl[1].copy_(sl[0])
+        cnt[0][0] = cnt[1][0] = n0
+        moved = bench.strip_pipelined_loop(w, steps, forces, sl, xy, cnt, cap, on_step=on_step)
+        collisions, overflow = tot["collisions"], tot["list_overflow"]
+        k = (steps - 1) & 1
+        n_last = int(cnt[k][0])
+        own_now = w.strip_owned().astype(bool)
+        got_slots = sl[k].numpy()[:n_last].astype(np.int64)
+        assert n_last == int(own_now.sum()) and len(np.unique(got_slots)) == n_last and own_now[got_slots].all(), "pipelined owned list != ownership"
+        pos_now = w.read_positions()
+        assert np.array_equal(xy[k].numpy()[:n_last].view(np.uint32), pos_now[got_slots].view(np.uint32)), "pipelined positions != device state"
+        assert moved > 0
+    else:
+        for _ in range(steps):
+            st = w.step(1 / 60)
+            assert st["nan_detected"] == 0, st
+            collisions += st["collisions"]
+            overflow += st["list_overflow"]
     own = w.strip_owned()
     bodies, _ = w.download_bodies()
     cols, _ = w.download_colliders()

@@ -33,6 +33,7 @@ CASES = [
     ("body-set-translate", T.test_body_set_and_translate_between_steps, {}),
     ("far-outlier", T.test_far_outlier_aliases_harmlessly, {}),
     ("pipelined-host-io", T.test_pipelined_host_io_matches_synchronous_calls, {}),
+    ("pipelined-indexed-host-io", T.test_pipelined_indexed_host_io_matches_synchronous_calls, {}),
     ("collisions-disabled-variable-delta", T.test_collisions_disabled_and_variable_delta, {}),
     ("events", T.test_events_match_reference_channel, {}),
     ("large-island", T.test_large_island_and_mixed_bodies, {}),

@@ -45,7 +45,7 @@ def test_strip_world_peer_memory_exchange_matches_single_gpu():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     n = 2 if n < 4 else 4
-    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1")
+    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", STRIP_TEST_IO="pipelined")   # + bench.py's pipelined frame loop
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -60,9 +60,10 @@ def test_strip_world_peer_memory_exchange_matches_single_gpu():
                                    {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1", "STRIP_TEST_RANKS": "3",
                                     "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
+                                   {"STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"},
                                    {"BLOBS_B200_TUNE": "11"},
                                    {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}],
-                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-p2p", "shell-p2p-3ranks-tile-forced", "gas-tile",
+                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-p2p", "shell-p2p-3ranks-tile-forced", "gas-pipelined-host-io", "gas-tile",
                               "shell-tile-forced-pool-crowded"])
 def test_strip_world_matches_single_world_emulated_ranks(knobs):
     """The same worker without GPUs: 2 CPU processes, each running the host-compiled build of the CUDA sources (tests/emu),

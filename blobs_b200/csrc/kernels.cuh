@@ -951,7 +951,8 @@ inline unsigned long long tile_path_count[2] = {0, 0};   // [0] shared-memory wi
 
 template <bool POOLED>
 __global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                          Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries) {
+                                                          Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries,
+                                                          uint32_t hot_len) {
     constexpr uint32_t WCAP = (uint32_t)TileCfg<POOLED>::WCAP;
     __shared__ float4 win[3 * WCAP];
     __shared__ PoolSmem pool[POOLED ? TILE_THREADS / 32 : 1];
@@ -959,11 +960,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridD
     __shared__ uint32_t cab[2];
     const uint32_t tid = threadIdx.x;
     const uint32_t i0 = blockIdx.x * TILE_THREADS;
-    const uint32_t nrec = __ldg(bp.tab + n_entries);      // total number of records (last table entry)
+    // round 1: the own record, together with the total number of records (last table entry); the address is clamped to the
+    // ALLOCATED length so that it does not wait for the count
+    const float4 h0 = __ldg(bp.hot + min(i0 + tid, hot_len - 1u));
+    const uint32_t nrec = __ldg(bp.tab + n_entries);
     if (i0 >= nrec) return;                               // CTA-uniform
     const bool valid = i0 + tid < nrec;
-    // round 1: the own record
-    const float4 h = __ldg(bp.hot + (valid ? i0 + tid : i0));
+    const float4 h = valid ? h0 : __ldg(bp.hot + i0);     // tail threads of the last tile mirror its first record and discard
     const uint32_t hw = __float_as_uint(h.w);
     const uint32_t c = hw & HOT_SLOT_MASK;
     const bool cold = (hw & HOT_COLD_BIT) != 0u;
@@ -1946,8 +1949,11 @@ constexpr long long STRIP_WAIT_TICKS = 1ll << 33;
 #endif
 
 __global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* send_l, const void* send_r, void* peer_l, void* peer_r,
-                                                    const void* recv_l, const void* recv_r, uint32_t seq, unsigned int* done, DeviceStats* stats) {
+                                                    const void* recv_l, const void* recv_r, unsigned int* xseq, unsigned int* done, DeviceStats* stats) {
     __shared__ bool last;
+    // exchange sequence number: device-resident (so that a captured CUDA graph can be replayed), bumped by the publishing CTA -
+    // which is the last one to arrive at `done`, i.e. after every CTA has read it here
+    const uint32_t seq = *reinterpret_cast<volatile unsigned int*>(xseq) + 1u;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
@@ -1972,7 +1978,7 @@ __global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* sen
     if (threadIdx.x < 2u) {
         const void* src = side ? send_r : send_l;
         void* dst = side ? peer_r : peer_l;
-        if (threadIdx.x == 0) *done = 0u;
+        if (threadIdx.x == 0) { *done = 0u; *xseq = seq; }
         if (dst != nullptr) {
             __threadfence_system();   // every CTA's slice is visible before the header says so
             const StripHeader* h = reinterpret_cast<const StripHeader*>(src);

@@ -73,6 +73,7 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
     graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
 #endif
@@ -1046,7 +1047,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     mix(&C, sizeof(C));
     MIXV(hot_a.d) MIXV(hot_b.d) MIXV(tab_a.d) MIXV(tab_b.d) MIXV(tile_a.d) MIXV(tile_b.d) MIXV(d_constraints.d) MIXV(mb_body.d) MIXV(mb_off.d) MIXV(mb_cols.d)
     MIXV(sb_body.d) MIXV(sb_off.d) MIXV(sb_edge.d) MIXV(d_springs.d) MIXV(isl_off.d) MIXV(isl_joint.d) MIXV(d_joints.d) MIXV(d_joints_inter.d)
-    MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3]) MIXV(p2p_on)
+    MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3]) MIXV(p2p_on) MIXV(p2p_block) MIXV(p2p_peer[0]) MIXV(p2p_peer[1]) MIXV(nccl_exchanges & 1u)
 #undef MIXV
     return h ? h : 1;
 }
@@ -1056,7 +1057,8 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
     Span span("integrate");   // physics.rs:92,398
     // measured on 2x B200: replaying a graph that contains the grouped ncclSend/ncclRecv is ~25 % SLOWER than plain launches,
     // so strip mode keeps plain launches
-    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || strip_on) return integrate(nsub, delta, last);
+    // (with the peer-memory exchange the substep holds no NCCL call; replaying it is opt-in until measured: BLOBS_B200_STRIP_GRAPH=1)
+    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || (strip_on && !(p2p_on && strip_graph))) return integrate(nsub, delta, last);
     const uint64_t key = step_key(nsub, delta, last);
     GraphSlot& gs = gslot[last ? 1 : 0];
     const float step_delta = delta / (float)nsub;
@@ -1065,6 +1067,7 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
         // host-side effects of integrate()
         if (any_dynamic) old_dt = step_delta;
         if (nsub & 1u) cur_is_a = !cur_is_a;
+        if (strip_on) nccl_exchanges += nsub;   // one exchange per substep; its parity picks the receive buffers baked into the graph
         launches += gs.launches;
         graph_replays++;
         graphs_launched.push_back(&gs);
@@ -1163,8 +1166,9 @@ int World::launch_substep(const SubstepParams& P_in) {
                 const size_t nrec_bound = strip_on ? (size_t)std::max<uint32_t>(olaunch_dim, 1) + 2 * (size_t)strip.gcap : (size_t)n_active_cols;
                 const unsigned gt = cdiv(nrec_bound, TILE_THREADS);
                 const uint32_t n_ent = (uint32_t)(table_entries() - 1);
-                if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent);
-                else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent);
+                const uint32_t hot_len = (uint32_t)std::min<size_t>(cur_is_a ? hot_a.cap : hot_b.cap, 0xffffffffu);
+                if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
+                else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
             } else if (pooled && tune == 0) {  // contact-rich state: warp-pooled resolution
                 if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 4, true);
                 else BLOBS_LAUNCH_MAIN(false, true, 4, 4, true);
@@ -2011,7 +2015,7 @@ int World::strip_p2p_setup() {
         CU(cudaMemsetAsync(p2p_block, 0, 4 * p2p_stride, stream));
         if (cudaIpcGetMemHandle(&hmine, p2p_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     }
-    if (!d_push_done) { CU(cudaMalloc(&d_push_done, sizeof(unsigned int))); CU(cudaMemsetAsync(d_push_done, 0, sizeof(unsigned int), stream)); }
+    if (!d_push_done) { CU(cudaMalloc(&d_push_done, 2 * sizeof(unsigned int))); CU(cudaMemsetAsync(d_push_done, 0, 2 * sizeof(unsigned int), stream)); }
     char* d_h = nullptr;   // [mine | from left | from right] handles, then [mine | left | right] ok words
     CU(cudaMalloc(&d_h, 3 * 64 + 3 * sizeof(int)));
     int* d_ok = reinterpret_cast<int*>(d_h + 3 * 64);
@@ -2053,13 +2057,12 @@ int World::strip_exchange() {
         // receive buffers (peer stores over NVLink), publishes header + sequence number once every CTA's stores are fenced,
         // and waits for the two incoming sequence numbers. Buffers alternate with the exchange parity: a neighbour cannot be
         // two exchanges ahead of me (it waits for my message of the exchange in between), so parity p is free again.
-        const uint32_t seq = (uint32_t)(nccl_exchanges + 1);
-        const size_t par = seq & 1u;
+        const size_t par = (size_t)((nccl_exchanges + 1) & 1u);   // the device-side sequence number (d_push_done[1]) counts in step with nccl_exchanges
         cur_recv[0] = p2p_block + (0 * 2 + par) * p2p_stride;
         cur_recv[1] = p2p_block + (1 * 2 + par) * p2p_stride;
         void* peer_l = strip.has_left ? p2p_peer[0] + (1 * 2 + par) * p2p_stride : nullptr;    // I am my left neighbour's RIGHT
         void* peer_r = strip.has_right ? p2p_peer[1] + (0 * 2 + par) * p2p_stride : nullptr;   // and my right neighbour's LEFT
-        BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_strip_push)(strip, msg[0], msg[1], peer_l, peer_r, cur_recv[0], cur_recv[1], seq, d_push_done, d_stats);
+        BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_strip_push)(strip, msg[0], msg[1], peer_l, peer_r, cur_recv[0], cur_recv[1], d_push_done + 1, d_push_done, d_stats);
         launches++;
         CU(cudaGetLastError());
         nccl_exchanges++;

@@ -371,7 +371,8 @@ class World {
     char* p2p_block = nullptr;          // mine
     char* p2p_peer[2] = {nullptr, nullptr};   // left / right neighbour's block (IPC mapping)
     size_t p2p_stride = 0;
-    unsigned int* d_push_done = nullptr;
+    unsigned int* d_push_done = nullptr;   // [0] CTA arrival counter, [1] exchange sequence number (device-resident: graph replay)
+    bool strip_graph = false;               // BLOBS_B200_STRIP_GRAPH=1: with the peer-memory exchange, replay whole steps as CUDA graphs
     void* cur_recv[2] = {nullptr, nullptr};   // receive buffers of the exchange in flight (== msg[2], msg[3] on the NCCL path)
     int strip_p2p_setup();
     int strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch);

@@ -53,18 +53,26 @@ def test_strip_world_peer_memory_exchange_matches_single_gpu():
     assert r.returncode == 0
 
 
+_FORCED = {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}
+_SHELL = {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"}
+_P2P = {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"}
+# the combinations that add nothing new to the ones below only run with BLOBS_TEST_SLOW=1 (each costs ~40 s of emulation)
+_slow = pytest.mark.skipif(os.environ.get("BLOBS_TEST_SLOW") != "1", reason="redundant combination; set BLOBS_TEST_SLOW=1")
+_STRIP_CASES = [
+    pytest.param({}, id="gas-default"),
+    pytest.param(dict(_FORCED), id="gas-forced-pool-crowded", marks=_slow),
+    pytest.param({**_SHELL, **_FORCED}, id="shell-forced-pool-crowded"),
+    pytest.param(dict(_SHELL), id="shell-default", marks=_slow),
+    pytest.param(dict(_P2P), id="gas-p2p"),
+    pytest.param({**_SHELL, **_P2P, **_FORCED, "STRIP_TEST_RANKS": "3", "BLOBS_B200_TUNE": "11"}, id="shell-p2p-3ranks-tile-forced"),
+    pytest.param({"STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-pipelined-host-io"),
+    pytest.param({"BLOBS_B200_TUNE": "11", "STRIP_TEST_STEPS": "16"}, id="gas-tile"),
+    pytest.param({**_SHELL, **_FORCED, "BLOBS_B200_TUNE": "11"}, id="shell-tile-forced-pool-crowded", marks=_slow),
+]
+
+
 @pytest.mark.emu
-@pytest.mark.parametrize("knobs", [{}, {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
-                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
-                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"},
-                                   {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"},
-                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1", "STRIP_TEST_RANKS": "3",
-                                    "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"},
-                                   {"STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"},
-                                   {"BLOBS_B200_TUNE": "11"},
-                                   {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8", "BLOBS_B200_TUNE": "11", "BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}],
-                         ids=["gas-default", "gas-forced-pool-crowded", "shell-forced-pool-crowded", "shell-default", "gas-p2p", "shell-p2p-3ranks-tile-forced", "gas-pipelined-host-io", "gas-tile",
-                              "shell-tile-forced-pool-crowded"])
+@pytest.mark.parametrize("knobs", _STRIP_CASES)
 def test_strip_world_matches_single_world_emulated_ranks(knobs):
     """The same worker without GPUs: 2 CPU processes, each running the host-compiled build of the CUDA sources (tests/emu),
     exchanging ghosts and migrants every substep through a socket stand-in for NCCL; merged result == single world, bit for

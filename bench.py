@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--tune", type=int, default=0, help="kernel variant selector (BLOBS_PARAM_TUNE)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--probe", action="store_true", help="(internal) kernel-variant probe run by the autotuner in a child process")
+    ap.add_argument("--device", type=int, default=None, help="(internal) CUDA device of the probe")
     return ap.parse_args()
 
 
@@ -196,6 +198,86 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def build_single_world(workload, device):
+    """one world of `workload` on `device` (the N = 1 form of every workload)"""
+    import blobs_b200
+    from blobs_b200 import scenes as S
+
+    if workload == "cfg3":
+        worlds = [S.cfg1(1 + wid, n_side=16) for wid in range(4096)]
+        w = blobs_b200.World(gravity=worlds[0].gravity, device=device, body_capacity=256 * 4096, collider_capacity=256 * 4096)
+        S.build_batch(w, worlds)
+        return w, 256 * 4096
+    sc, _ = make_scene(workload, seed=1)
+    w = blobs_b200.World(gravity=sc.gravity, device=device, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
+    S.build(w, sc)
+    return w, sc.n_bodies
+
+
+def run_probe(args):
+    """Child process of the autotuner: the same scene twice, once through k_main (BLOBS_PARAM_TUNE 0) and once through k_tile (11),
+    W warm-up steps each, then K steps timed in alternating blocks of 5. Prints {"ms": {"0": .., "11": ..}, "parity": bool}: parity =
+    positions, previous positions and velocities of the two worlds are bit-identical after all W + K steps (they must be: the
+    variants only differ in how threads are mapped onto the same arithmetic). Runs in its own process so that a fault in the
+    not-yet-measured variant cannot take the benchmark down with it."""
+    import numpy as np
+    import torch
+
+    import blobs_b200
+
+    dev = args.device if args.device is not None else 0
+    torch.cuda.set_device(dev)
+    worlds = {}
+    for tune in (0, 11):
+        w, _ = build_single_world(args.workload, dev)
+        w.set_param(blobs_b200.abi.PARAM_TUNE, tune)
+        w.step(DT, n=max(args.warmup, 1))
+        worlds[tune] = w
+    ms = {0: 0.0, 11: 0.0}
+    done = 0
+    while done < args.steps:
+        blk = min(5, args.steps - done)
+        for tune in (0, 11):
+            for _ in range(blk):
+                ms[tune] += worlds[tune].step(DT)["gpu_ms"]
+        done += blk
+    a, _ = worlds[0].download_bodies()
+    b, _ = worlds[11].download_bodies()
+    same = all(np.array_equal(a[f][c].view(np.uint32), b[f][c].view(np.uint32)) for f in ("position", "position_old", "calculated_velocity") for c in ("x", "y"))
+    print(json.dumps({"probe": True, "ms": {str(k): v / max(args.steps, 1) for k, v in ms.items()}, "parity": bool(same), "steps": args.steps, "warmup": args.warmup}), flush=True)
+
+
+def autotune_main_kernel(args, device):
+    """Picks the dominant kernel's variant for this run by MEASUREMENT, like a library autotuner: a child process (run_probe) times
+    k_main against k_tile on this GPU, in the regime the timed window sits in, and checks that they agree bit for bit. k_tile is
+    used only if the child finished cleanly, parity held and it was at least 3 % faster. Returns (tune, report)."""
+    if args.tune or os.environ.get("BLOBS_BENCH_AUTOTUNE", "1") == "0":
+        return args.tune, {"mode": "off (variant forced)" if args.tune else "off"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--probe", "--workload", args.workload, "--warmup", str(max(args.warmup, 3)), "--steps", str(min(max(args.steps, 10), 30)),
+           "--device", str(device)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    rep = {"mode": "probe in a child process: k_main (tune 0) vs k_tile (tune 11), same scene and window, bit-exact parity required"}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "300")), env=env)
+        line = next((l for l in r.stdout.splitlines() if l.startswith("{") and '"probe"' in l), None)
+        if r.returncode != 0 or line is None:
+            rep["result"] = f"probe failed (rc={r.returncode}): {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else 'no output'}"[:300]
+            return 0, rep
+        p = json.loads(line)
+        rep.update({"k_main_ms_per_step": p["ms"]["0"], "k_tile_ms_per_step": p["ms"]["11"], "parity_bit_exact": p["parity"], "probe_steps": p["steps"]})
+        if p["parity"] and p["ms"]["11"] < 0.97 * p["ms"]["0"]:
+            rep["chosen"] = "k_tile"
+            return 11, rep
+        rep["chosen"] = "k_main"
+        return 0, rep
+    except subprocess.TimeoutExpired:
+        rep["result"] = "probe timed out"
+        return 0, rep
+    except Exception as e:  # noqa: BLE001 - the probe is optional
+        rep["result"] = f"probe error: {e}"[:300]
+        return 0, rep
+
+
 def strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap, on_step=None):
     """K frames of a strip-decomposed world with the pipelined distributed host I/O of the C ABI. `sl`, `xy`, `cnt` are pairs of
     pinned host tensors (slot list, positions, count); both slot lists / counts hold the current owned list on entry. The newest
@@ -241,6 +323,12 @@ def run_ours(args):
 
     import blobs_b200
     from blobs_b200 import scenes as S
+
+    # which variant of the dominant kernel runs: measured on this GPU first (N = 1; the strip path keeps k_main until k_tile has
+    # been run in strip mode on real GPUs)
+    tune_report = {"mode": "off (N > 1)"}
+    if world == 1:
+        args.tune, tune_report = autotune_main_kernel(args, local)
 
     scaling = "weak"
     if args.workload == "cfg3":
@@ -476,7 +564,7 @@ def run_ours(args):
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1]),
                        "strip_exchange": (("peer-memory stores over NVLink (k_strip_push, CUDA IPC)" if int(w.get_param(blobs_b200.abi.PARAM_STRIP_P2P)) else "grouped ncclSend/ncclRecv")
                                           if strips_on else None),
-                       "main_kernel": "k_tile" if args.tune == 11 else "k_main"},
+                       "main_kernel": "k_tile" if args.tune == 11 else "k_main", "autotune": tune_report},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,
                     "checksum_mean_y": checksum, "host_io": e2e_mode,
@@ -506,7 +594,9 @@ def run_ours(args):
 def main():
     args = parse()
     try:
-        if args.impl == "reference":
+        if args.probe:
+            run_probe(args)
+        elif args.impl == "reference":
             run_reference(args)
         else:
             run_ours(args)

@@ -14,19 +14,20 @@ set -u
 O=gpurun_out/r2
 mkdir -p $O
 export PYTHONUNBUFFERED=1
+# the sweep lines force their variant: the default bench line (step 2) is the only one that autotunes (bench.py: child-process probe)
 timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
-timeout 300 python bench.py > $O/bench_default.json 2> $O/bench_default.err
-BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
+timeout 500 python bench.py > $O/bench_default.json 2> $O/bench_default.err
+BLOBS_BENCH_AUTOTUNE=0 BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
 for t in 0 11 9 10 8; do
-  timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
-  timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
+  BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
+  BLOBS_BENCH_AUTOTUNE=0 timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
 done
 for t in 0 11; do
-  timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
-  timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
+  BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
+  BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 100 --csv --log-file $O/ncu_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
+    env BLOBS_BENCH_AUTOTUNE=0 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_tile" -s 8 -c 1 -o $O/tile_sparse \
     python bench.py --tune 11 --steps 2 --warmup 3 --no-cpu-baseline --no-flush > $O/ncu_tile.log 2>&1
 CAPTURE_STEPS=277 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_main|k_crowded" --launch-skip 4400 --launch-count 2 \

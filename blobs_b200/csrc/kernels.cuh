@@ -938,8 +938,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
 // cabs[] / cconst[] are not read for default spheres.
 // Anything that does not fit the picture takes the global-memory path of k_main for that thread only: a range that wraps
 // the torus or is not covered by a staged window (window larger than TILE_WCAP records, table edge). Same arithmetic, same
-// summation order as k_main => bit-identical results. Requires: every alive body has at least one collider (host checks
-// n_loose == 0); colliders of multi-collider bodies are skipped here and done by k_multi as before.
+// summation order as k_main => bit-identical results. Colliders of multi-collider bodies are skipped here and done by k_multi
+// as before; bodies without any collider have no record, the host adds a k_integrate(BF_LOOSE) pass for them.
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_THREADS = 256;
 // records per staged window (own 256 + two halo cells, with slack); the pooled variant also holds the per-warp queues and

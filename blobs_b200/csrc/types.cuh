@@ -14,6 +14,7 @@ enum : uint32_t {
     BF_ROT = 1u << 3,          // angular state may be non-zero / rotation matters (torque, joints, rotated)
     BF_JOINTED = 1u << 4,
     BF_FIRST_DYN = 1u << 5,
+    BF_LOOSE = 1u << 7,        // no collider and no joint: no record stands for it in the cell-sorted array (k_tile advances these with a k_integrate pass)
     BF_KINEMATIC = 1u << 6,    // RigidBodyType::KinematicPositionBased / KinematicVelocityBased (only scene queries look at it)    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
 };
 // collider flags (host-authoritative, cflags[])

@@ -836,7 +836,10 @@ int World::rebuild_topology() {
                 v_mb_body.push_back(b);
                 v_mb_cols.insert(v_mb_cols.end(), cs.begin(), cs.end());
                 v_mb_off.push_back((uint32_t)v_mb_cols.size());
-            } else { n_simple++; n_loose++; }   // no collider: only k_main / k_integrate (one thread per body slot) reach it
+            } else {   // no collider: only kernels with one thread per body SLOT reach it (k_main, k_integrate)
+                n_simple++;
+                if (!x.n_joints) { f |= BF_LOOSE; n_loose++; }   // (a jointed one is advanced by k_integrate(BF_JOINTED) anyway)
+            }
         }
         binfo.set(b, make_uint2(f, (uint32_t)bc));
     }
@@ -1145,6 +1148,7 @@ int World::launch_substep(const SubstepParams& P_in) {
         CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
         CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
     }
+    const bool tile_used = nb && tune == 11 && fused && ordered && !(strip_on && n_loose) && n_active_cols;
     if (nb) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
@@ -1160,7 +1164,7 @@ int World::launch_substep(const SubstepParams& P_in) {
             else BLOBS_LAUNCH_MAIN(false, false, BT, MB, false);            \
         }                                                                   \
     } while (0)
-            if (tune == 11 && fused && ordered && n_loose == 0 && n_active_cols) {
+            if (tile_used) {
                 // one thread per cell-sorted record, candidate windows staged in shared memory (kernels.cuh: k_tile).
                 // Strip mode: the records are the owned colliders plus the ghosts received for this table (skipped by their threads).
                 const size_t nrec_bound = strip_on ? (size_t)std::max<uint32_t>(olaunch_dim, 1) + 2 * (size_t)strip.gcap : (size_t)n_active_cols;
@@ -1198,6 +1202,10 @@ int World::launch_substep(const SubstepParams& P_in) {
 #undef BLOBS_MAIN_VARIANT
 #undef BLOBS_LAUNCH_MAIN
         });
+        if (rc) return rc;
+    }
+    if (tile_used && n_loose) {   // bodies without a collider have no record for k_tile to start from: a body-parallel pass advances them
+        rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_LOOSE); });
         if (rc) return rc;
     }
     if (n_multi) {

@@ -74,7 +74,7 @@ def test_128_thread_cta_variants(case, tune, monkeypatch):
         fn(**kw)
 
 
-TILE_CASES = [c for c in CASES if c[0] in ("overflow200-fused-crowded", "overflow1200-fused-inline", "removal-reinsert", "far-outlier", "batched-worlds",
+TILE_CASES = [c for c in CASES if c[0] in ("multi-collider", "overflow200-fused-crowded", "overflow1200-fused-inline", "removal-reinsert", "far-outlier", "batched-worlds",
                                            "soft-blobs-fused", "collisions-disabled-variable-delta")]
 
 

@@ -258,7 +258,7 @@ def autotune_main_kernel(args, device):
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
     rep = {"mode": "probe in a child process: k_main (tune 0) vs k_tile (tune 11), same scene and window, bit-exact parity required"}
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "300")), env=env)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "180")), env=env)
         line = next((l for l in r.stdout.splitlines() if l.startswith("{") and '"probe"' in l), None)
         if r.returncode != 0 or line is None:
             rep["result"] = f"probe failed (rc={r.returncode}): {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else 'no output'}"[:300]

@@ -214,10 +214,14 @@ def build_single_world(workload, device):
     return w, sc.n_bodies
 
 
+PROBE_VARIANTS = (0, 11, 12)   # BLOBS_PARAM_TUNE: k_main, k_tile (256-record tiles), k_tile (128-record tiles)
+VARIANT_NAME = {0: "k_main", 11: "k_tile", 12: "k_tile<128>"}
+
+
 def run_probe(args):
-    """Child process of the autotuner: the same scene twice, once through k_main (BLOBS_PARAM_TUNE 0) and once through k_tile (11),
-    W warm-up steps each, then K steps timed in alternating blocks of 5. Prints {"ms": {"0": .., "11": ..}, "parity": bool}: parity =
-    positions, previous positions and velocities of the two worlds are bit-identical after all W + K steps (they must be: the
+    """Child process of the autotuner: the same scene once per variant (k_main = BLOBS_PARAM_TUNE 0, k_tile = 11, k_tile with 128-record
+    tiles = 12), W warm-up steps each, then K steps timed in alternating blocks of 5. Prints {"ms": {tune: ..}, "parity": {tune: bool}}:
+    parity = positions, previous positions and velocities are bit-identical to k_main's after all W + K steps (they must be: the
     variants only differ in how threads are mapped onto the same arithmetic). Runs in its own process so that a fault in the
     not-yet-measured variant cannot take the benchmark down with it."""
     import numpy as np
@@ -228,23 +232,26 @@ def run_probe(args):
     dev = args.device if args.device is not None else 0
     torch.cuda.set_device(dev)
     worlds = {}
-    for tune in (0, 11):
+    for tune in PROBE_VARIANTS:
         w, _ = build_single_world(args.workload, dev)
         w.set_param(blobs_b200.abi.PARAM_TUNE, tune)
         w.step(DT, n=max(args.warmup, 1))
         worlds[tune] = w
-    ms = {0: 0.0, 11: 0.0}
+    ms = {t: 0.0 for t in PROBE_VARIANTS}
     done = 0
     while done < args.steps:
         blk = min(5, args.steps - done)
-        for tune in (0, 11):
+        for tune in PROBE_VARIANTS:
             for _ in range(blk):
                 ms[tune] += worlds[tune].step(DT)["gpu_ms"]
         done += blk
     a, _ = worlds[0].download_bodies()
-    b, _ = worlds[11].download_bodies()
-    same = all(np.array_equal(a[f][c].view(np.uint32), b[f][c].view(np.uint32)) for f in ("position", "position_old", "calculated_velocity") for c in ("x", "y"))
-    print(json.dumps({"probe": True, "ms": {str(k): v / max(args.steps, 1) for k, v in ms.items()}, "parity": bool(same), "steps": args.steps, "warmup": args.warmup}), flush=True)
+    parity = {}
+    for tune in PROBE_VARIANTS[1:]:
+        b, _ = worlds[tune].download_bodies()
+        parity[str(tune)] = bool(all(np.array_equal(a[f][c].view(np.uint32), b[f][c].view(np.uint32))
+                                     for f in ("position", "position_old", "calculated_velocity") for c in ("x", "y")))
+    print(json.dumps({"probe": True, "ms": {str(k): v / max(args.steps, 1) for k, v in ms.items()}, "parity": parity, "steps": args.steps, "warmup": args.warmup}), flush=True)
 
 
 def autotune_main_kernel(args, device):
@@ -256,7 +263,7 @@ def autotune_main_kernel(args, device):
     cmd = [sys.executable, os.path.abspath(__file__), "--probe", "--workload", args.workload, "--warmup", str(max(args.warmup, 3)), "--steps", str(min(max(args.steps, 10), 30)),
            "--device", str(device)]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
-    rep = {"mode": "probe in a child process: k_main (tune 0) vs k_tile (tune 11), same scene and window, bit-exact parity required"}
+    rep = {"mode": "probe in a child process: k_main (tune 0) vs k_tile (tune 11 / 12), same scene and window, bit-exact parity required"}
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "180")), env=env)
         line = next((l for l in r.stdout.splitlines() if l.startswith("{") and '"probe"' in l), None)
@@ -264,12 +271,14 @@ def autotune_main_kernel(args, device):
             rep["result"] = f"probe failed (rc={r.returncode}): {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else 'no output'}"[:300]
             return 0, rep
         p = json.loads(line)
-        rep.update({"k_main_ms_per_step": p["ms"]["0"], "k_tile_ms_per_step": p["ms"]["11"], "parity_bit_exact": p["parity"], "probe_steps": p["steps"]})
-        if p["parity"] and p["ms"]["11"] < 0.97 * p["ms"]["0"]:
-            rep["chosen"] = "k_tile"
-            return 11, rep
-        rep["chosen"] = "k_main"
-        return 0, rep
+        rep.update({"ms_per_step": {VARIANT_NAME[int(k)]: v for k, v in p["ms"].items()},
+                    "parity_bit_exact": {VARIANT_NAME[int(k)]: v for k, v in p["parity"].items()}, "probe_steps": p["steps"]})
+        best, best_ms = 0, 0.97 * p["ms"]["0"]
+        for k, v in p["ms"].items():
+            if int(k) and p["parity"].get(k) is True and v < best_ms:
+                best, best_ms = int(k), v
+        rep["chosen"] = VARIANT_NAME[best]
+        return best, rep
     except subprocess.TimeoutExpired:
         rep["result"] = "probe timed out"
         return 0, rep
@@ -564,13 +573,13 @@ def run_ours(args):
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1]),
                        "strip_exchange": (("peer-memory stores over NVLink (k_strip_push, CUDA IPC)" if int(w.get_param(blobs_b200.abi.PARAM_STRIP_P2P)) else "grouped ncclSend/ncclRecv")
                                           if strips_on else None),
-                       "main_kernel": "k_tile" if args.tune == 11 else "k_main", "autotune": tune_report},
+                       "main_kernel": VARIANT_NAME.get(args.tune, f"k_main (tune {args.tune})"), "autotune": tune_report},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2, "ms_per_step": t_e2e / K * 1e3,
                     "checksum_mean_y": checksum, "host_io": e2e_mode,
                     "sync_value": (n_total * sync_sample[0] / sync_sample[1]) if sync_sample else None},
             "gpu_launches": launches_total,
-            "roofline": {"bound": "hbm", "kernel": ("k_tile" if args.tune == 11 else "k_main<fused,ordered>") + " (contacts + verlet + snapshot + clamp + cell binning)",
+            "roofline": {"bound": "hbm", "kernel": ("k_tile" if args.tune in (11, 12) else "k_main<fused,ordered>") + " (contacts + verlet + snapshot + clamp + cell binning)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": B_MAIN * n, "avg_launch_ms": main_ms / max(main_n, 1),
                          "timing": "CUDA events around every k_main launch, second timed pass of the same K steps",

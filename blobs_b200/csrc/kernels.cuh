@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-tile (BLOBS_PARAM_TUNE 11): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
+// K-tile (BLOBS_PARAM_TUNE 11; 12 = the same with 128-record tiles / 128-thread CTAs, 8 per SM): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
 // the cell-sorted array instead of one per body slot, 256 consecutive records per CTA. The records a CTA's bodies can
 // touch then form three contiguous windows of the same array (the linear cell range [cA-1, cB+1] of the tile's own cells,
 // and that range shifted one table row up and down), which the CTA stages in shared memory with coalesced 16-byte loads:
@@ -944,22 +944,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
 constexpr int TILE_THREADS = 256;
 // records per staged window (own 256 + two halo cells, with slack); the pooled variant also holds the per-warp queues and
 // must stay under the 48 KB of static shared memory
-template <bool POOLED> struct TileCfg { static constexpr int WCAP = POOLED ? 320 : 384; };
+template <bool POOLED, int THREADS> struct TileCfg { static constexpr int WCAP = THREADS >= 256 ? (POOLED ? 320 : 384) : (POOLED ? 224 : 256); };
 #ifdef BLOBS_EMU
 inline unsigned long long tile_path_count[2] = {0, 0};   // [0] shared-memory windows, [1] global-memory fallback
 #endif
 
-template <bool POOLED>
-__global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
+template <bool POOLED, int THREADS = TILE_THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                                           Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries,
                                                           uint32_t hot_len) {
-    constexpr uint32_t WCAP = (uint32_t)TileCfg<POOLED>::WCAP;
+    constexpr uint32_t WCAP = (uint32_t)TileCfg<POOLED, THREADS>::WCAP;
     __shared__ float4 win[3 * WCAP];
-    __shared__ PoolSmem pool[POOLED ? TILE_THREADS / 32 : 1];
+    __shared__ PoolSmem pool[POOLED ? THREADS / 32 : 1];
     __shared__ uint32_t wlo[3], whi[3];
     __shared__ uint32_t cab[2];
     const uint32_t tid = threadIdx.x;
-    const uint32_t i0 = blockIdx.x * TILE_THREADS;
+    const uint32_t i0 = blockIdx.x * (uint32_t)THREADS;
     // round 1: the own record, together with the total number of records (last table entry); the address is clamped to the
     // ALLOCATED length so that it does not wait for the count
     const float4 h0 = __ldg(bp.hot + min(i0 + tid, hot_len - 1u));
@@ -970,7 +970,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridD
     const uint32_t hw = __float_as_uint(h.w);
     const uint32_t c = hw & HOT_SLOT_MASK;
     const bool cold = (hw & HOT_COLD_BIT) != 0u;
-    const uint32_t lastv = min((uint32_t)TILE_THREADS - 1u, nrec - 1u - i0);
+    const uint32_t lastv = min((uint32_t)THREADS - 1u, nrec - 1u - i0);
     uint32_t mycell = cell_index(g, bin_coord(h.x, g.inv_cell), bin_coord(h.y, g.inv_cell));   // what publish_collider / k_count binned it to
     const CellRange R = cell_range(g, h.x, h.y, h.z);
     const bool plain = !(R.ny > 3u || R.c0 + R.nx > g.W);
@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_tile(SubstepParams P, GridD
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint32_t a = wlo[k], n = whi[k] - a;
-        for (uint32_t j = tid; j < n; j += TILE_THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
+        for (uint32_t j = tid; j < n; j += (uint32_t)THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
     }
     __syncthreads();
 

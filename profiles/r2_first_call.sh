@@ -18,11 +18,11 @@ export PYTHONUNBUFFERED=1
 timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
 timeout 500 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 BLOBS_BENCH_AUTOTUNE=0 BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
-for t in 0 11 9 10 8; do
+for t in 0 11 12 9 10 8; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
 done
-for t in 0 11; do
+for t in 0 11 12; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
 done

@@ -32,14 +32,16 @@ def test_probe_compares_the_two_variants_bit_for_bit(monkeypatch, capsys):
         bench.run_probe(_args())
     line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1]
     p = json.loads(line)
-    assert p["probe"] is True and p["parity"] is True and p["steps"] == 6
-    assert p["ms"]["0"] > 0 and p["ms"]["11"] > 0
+    assert p["probe"] is True and p["parity"] == {"11": True, "12": True} and p["steps"] == 6
+    assert all(p["ms"][k] > 0 for k in ("0", "11", "12"))
 
 
 @pytest.mark.parametrize("stdout,rc,want_tune,want_key", [
-    ('{"probe": true, "ms": {"0": 2.0, "11": 1.5}, "parity": true, "steps": 30, "warmup": 200}\n', 0, 11, "k_tile"),
-    ('{"probe": true, "ms": {"0": 2.0, "11": 1.99}, "parity": true, "steps": 30, "warmup": 200}\n', 0, 0, "k_main"),     # not 3 % faster
-    ('{"probe": true, "ms": {"0": 2.0, "11": 1.0}, "parity": false, "steps": 30, "warmup": 200}\n', 0, 0, "k_main"),     # faster but wrong: never
+    ('{"probe": true, "ms": {"0": 2.0, "11": 1.5, "12": 1.7}, "parity": {"11": true, "12": true}, "steps": 30, "warmup": 200}\n', 0, 11, "k_tile"),
+    ('{"probe": true, "ms": {"0": 2.0, "11": 1.5, "12": 1.2}, "parity": {"11": true, "12": true}, "steps": 30, "warmup": 200}\n', 0, 12, "k_tile<128>"),
+    ('{"probe": true, "ms": {"0": 2.0, "11": 1.99, "12": 2.4}, "parity": {"11": true, "12": true}, "steps": 30, "warmup": 200}\n', 0, 0, "k_main"),    # not 3 % faster
+    ('{"probe": true, "ms": {"0": 2.0, "11": 1.0, "12": 1.8}, "parity": {"11": false, "12": true}, "steps": 30, "warmup": 200}\n', 0, 12, "k_tile<128>"),  # faster but wrong: never
+    ('{"probe": true, "ms": {"0": 2.0, "11": 1.0, "12": 1.0}, "parity": {"11": false, "12": false}, "steps": 30, "warmup": 200}\n', 0, 0, "k_main"),
     ("", 1, 0, None),                                                                                                      # the child died
     ("garbage\n", 0, 0, None),
 ])

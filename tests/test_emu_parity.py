@@ -100,6 +100,17 @@ def test_tile_kernel(case, knobs, monkeypatch):
     assert paths[0] > paths[1], f"k_tile: {paths[0]} bodies via shared-memory windows, {paths[1]} via the global fallback"
 
 
+@pytest.mark.parametrize("case", [c for c in TILE_CASES if c[0] in ("overflow200-fused-crowded", "removal-reinsert", "multi-collider")], ids=lambda c: c[0])
+def test_tile_kernel_128_record_tiles(case, monkeypatch):
+    """BLOBS_PARAM_TUNE 12: k_tile with 128-record tiles (128-thread CTAs), pooled + crowded forced."""
+    _, fn, kw = case
+    monkeypatch.setenv("BLOBS_B200_TUNE", "12")
+    for k, v in FORCED.items():
+        monkeypatch.setenv(k, v)
+    with emulated():
+        fn(**kw)
+
+
 def test_results_do_not_depend_on_the_schedule():
     """Same cases with the emulator visiting CTAs, warps and lanes in a seeded RANDOM order (BLOBS_EMU_SEED, read when the
     library is loaded, hence the subprocess): atomics then hand out different ranks and cells hold their records in another

@@ -35,3 +35,17 @@ def test_tile_kernel_on_gpu(case, knobs, monkeypatch):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     fn(**kw)
+
+
+SMALL_TILE_CASES = [c for c in CASES if c[0] in ("cfg1-every-substep", "dense-pile-fused", "multi-collider", "batched-worlds", "boundary-shell-auto", "full-size-cfg2")]
+
+
+@pytest.mark.parametrize("knobs", [{}, FORCED], ids=["default", "forced-pool-crowded"])
+@pytest.mark.parametrize("case", SMALL_TILE_CASES, ids=[c[0] for c in SMALL_TILE_CASES])
+def test_tile_kernel_128_record_tiles_on_gpu(case, knobs, monkeypatch):
+    """BLOBS_PARAM_TUNE 12: the same kernel with 128-record tiles (128-thread CTAs)."""
+    name, fn, kw = case
+    monkeypatch.setenv("BLOBS_B200_TUNE", "12")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    fn(**kw)

@@ -59,7 +59,7 @@ def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
         fn(**kw)
 
 
-SMALL_CTA_CASES = [c for c in CASES if c[0] in ("overflow200-fused-crowded", "multi-collider", "batched-worlds", "removal-reinsert")]
+SMALL_CTA_CASES = [c for c in CASES if c[0] in ("overflow200-fused-crowded", "multi-collider", "removal-reinsert")]
 
 
 @pytest.mark.parametrize("tune", ["9", "10"], ids=["tune9-128thr-pooled", "tune10-128thr-per-lane"])

@@ -421,7 +421,7 @@ def run_ours(args):
                 flush.zero_()
                 torch.cuda.synchronize()
             st = w.step(DT)
-            bad[0] |= st["nan_detected"] & 4   # strip message overflow: reported in the JSON line, never raised (a rank that dies would hang its peers)
+            bad[0] |= st["nan_detected"] & 12  # strip message overflow (4) / peer-exchange wait timed out (8): reported in the JSON line, never raised (a rank that dies would hang its peers)
             t_ms += st["gpu_ms"]
             coll += st["collisions"]
             over += st["list_overflow"]
@@ -591,7 +591,7 @@ def run_ours(args):
                          "ms_per_step_with_kernel_events": t_prof_ms / K, "cuda_graph_replays": int(w.get_param(blobs_b200.abi.PARAM_GRAPH_REPLAYS))},
         }
         if float(tot[4]) != 0:
-            line["invalid"] = "strip message buffers overflowed: results are not valid, raise ghost_capacity / migrate_capacity"
+            line["invalid"] = "strip message buffers overflowed (raise ghost_capacity / migrate_capacity) or a peer-memory exchange timed out: results are not valid"
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(args.cpu_budget)[0]
         print(json.dumps(line), flush=True)

@@ -179,7 +179,9 @@ typedef struct BlobsStepStats {
     uint64_t collisions;        /* perf_counter_inc("collisions", count), physics.rs:316 — summed over substeps */
     uint64_t coincident_pairs;  /* pairs that took the distance < 1e-6 branch, physics.rs:272-286 */
     uint64_t events_dropped;    /* events/pairs that did not fit the recording buffer */
-    uint32_t nan_detected;      /* non-zero: a position/normal became NaN (reference would have panicked) */
+    uint32_t nan_detected;      /* bit 0: a position became NaN; bit 1: a rotation became non-finite (the reference would have panicked,
+                                   physics.rs:471-474); strip mode - bit 2: a ghost / migration message or the owned list overflowed its
+                                   capacity, bit 3: a peer-memory exchange waited > ~4 s for a neighbour (results are not valid) */
     uint32_t steps_run;         /* integrate() calls performed (fixed_step: 0..3, physics.rs:88-98) */
     uint32_t substeps_run;
     uint32_t list_overflow;     /* contact lists that exceeded the in-register capacity and took the rescan path */

@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-tile (BLOBS_PARAM_TUNE 11; 12 = the same with 128-record tiles / 128-thread CTAs, 8 per SM): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
+// K-tile (BLOBS_PARAM_TUNE 11; 12 = the same with 128-record tiles / 128-thread CTAs, 8 per SM; 13 = windows fetched by TMA bulk copies): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
 // the cell-sorted array instead of one per body slot, 256 consecutive records per CTA. The records a CTA's bodies can
 // touch then form three contiguous windows of the same array (the linear cell range [cA-1, cB+1] of the tile's own cells,
 // and that range shifted one table row up and down), which the CTA stages in shared memory with coalesced 16-byte loads:
@@ -949,7 +949,40 @@ template <bool POOLED, int THREADS> struct TileCfg { static constexpr int WCAP =
 inline unsigned long long tile_path_count[2] = {0, 0};   // [0] shared-memory windows, [1] global-memory fallback
 #endif
 
-template <bool POOLED, int THREADS = TILE_THREADS>
+// BLOBS_PARAM_TUNE 13: the three windows are fetched by the TMA engine instead of by the CTA's threads - one elected thread
+// arms an mbarrier with the byte count and issues up to three 1-D bulk copies (cp.async.bulk global -> shared, SASS UBLKCP),
+// everybody waits on the barrier's phase. Frees the load/store slots of 256 threads and their registers for the body-state
+// gather that is in flight at the same time. (The host-compiled test build keeps the plain loop.)
+#ifndef BLOBS_EMU
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+#endif
+
+template <bool POOLED, int THREADS = TILE_THREADS, bool BULK = false>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                                           Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries,
                                                           uint32_t hot_len) {
@@ -958,8 +991,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams 
     __shared__ PoolSmem pool[POOLED ? THREADS / 32 : 1];
     __shared__ uint32_t wlo[3], whi[3];
     __shared__ uint32_t cab[2];
+    __shared__ __align__(8) unsigned long long bulk_bar;
     const uint32_t tid = threadIdx.x;
     const uint32_t i0 = blockIdx.x * (uint32_t)THREADS;
+#ifndef BLOBS_EMU
+    if (BULK && tid == 0u) mbar_init(&bulk_bar, 1u);   // visible to the CTA after the first __syncthreads below
+#endif
     // round 1: the own record, together with the total number of records (last table entry); the address is clamped to the
     // ALLOCATED length so that it does not wait for the count
     const float4 h0 = __ldg(bp.hot + min(i0 + tid, hot_len - 1u));
@@ -1048,13 +1085,34 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams 
         whi[tid] = e;
     }
     __syncthreads();
-    // round 3: stage the windows (coalesced)
+    // round 3: stage the windows
+#ifndef BLOBS_EMU
+    if (BULK) {
+        const uint32_t bytes = ((whi[0] - wlo[0]) + (whi[1] - wlo[1]) + (whi[2] - wlo[2])) * 16u;
+        if (bytes) {   // CTA-uniform
+            if (tid == 0u) {
+                mbar_expect_tx(&bulk_bar, bytes);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint32_t a = wlo[k], n = whi[k] - a;
-        for (uint32_t j = tid; j < n; j += (uint32_t)THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t a = wlo[k], n = whi[k] - a;
+                    if (n) bulk_load(&win[k * WCAP], bp.hot + a, n * 16u, &bulk_bar);
+                }
+            }
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&bulk_bar, 0u)) {
+                if (++spins > (1u << 16)) { atomicOr(&stats->nan_flag, 16u); break; }   // never hang the GPU on a lost copy (each try_wait suspends for a while)
+            }
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {   // coalesced 16-byte loads by the whole CTA
+            const uint32_t a = wlo[k], n = whi[k] - a;
+            for (uint32_t j = tid; j < n; j += (uint32_t)THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     GatherOut out;
     out.fx = out.fy = 0.f;

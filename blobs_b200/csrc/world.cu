@@ -103,6 +103,7 @@ int World::init() {
     // k_tile<POOLED> holds 46 KB of windows + queues per CTA: ask for the large shared-memory carve-out so that 4 CTAs fit an SM
     CU(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_tile<true, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_tile<true, TILE_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     if (params.body_capacity_hint) {
         const size_t n = params.body_capacity_hint;
         CU(pos.ensure(n, stream)); CU(pos_old.ensure(n, stream)); CU(acc.ensure(n, stream)); CU(vel.ensure(n, stream));
@@ -1149,7 +1150,7 @@ int World::launch_substep(const SubstepParams& P_in) {
         CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
         CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
     }
-    const bool tile_used = nb && (tune == 11 || tune == 12) && fused && ordered && !(strip_on && n_loose) && n_active_cols;
+    const bool tile_used = nb && tune >= 11 && tune <= 13 && fused && ordered && !(strip_on && n_loose) && n_active_cols;
     if (nb) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
@@ -1171,7 +1172,11 @@ int World::launch_substep(const SubstepParams& P_in) {
                 const size_t nrec_bound = strip_on ? (size_t)std::max<uint32_t>(olaunch_dim, 1) + 2 * (size_t)strip.gcap : (size_t)n_active_cols;
                 const uint32_t n_ent = (uint32_t)(table_entries() - 1);
                 const uint32_t hot_len = (uint32_t)std::min<size_t>(cur_is_a ? hot_a.cap : hot_b.cap, 0xffffffffu);
-                if (tune == 12) {   // 128-record tiles: twice the CTAs, half the barrier-coupled work each
+                if (tune == 13) {   // windows fetched by TMA bulk copies (cp.async.bulk + mbarrier) instead of by the CTA's threads
+                    const unsigned gt = cdiv(nrec_bound, TILE_THREADS);
+                    if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true, TILE_THREADS, true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
+                    else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false, TILE_THREADS, true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
+                } else if (tune == 12) {   // 128-record tiles: twice the CTAs, half the barrier-coupled work each
                     const unsigned gt = cdiv(nrec_bound, 128);
                     if (pooled) BLOBS_LAUNCH(gt, 128, 0, stream, k_tile<true, 128>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
                     else BLOBS_LAUNCH(gt, 128, 0, stream, k_tile<false, 128>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);

@@ -16,9 +16,11 @@ mkdir -p $O
 export PYTHONUNBUFFERED=1
 # the sweep lines force their variant: the default bench line (step 2) is the only one that autotunes (bench.py: child-process probe)
 timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests rc=$?" >> $O/tests.log
+# the TMA-bulk variant of k_tile (tune 13) has never executed anywhere: its parity tests run on purpose, under their own timeout
+BLOBS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_tile_gpu.py -x -q -m gpu -k tune13 > $O/tests_tune13.log 2>&1; echo "tune13 rc=$?" >> $O/tests_tune13.log
 timeout 500 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 BLOBS_BENCH_AUTOTUNE=0 BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
-for t in 0 11 12 9 10 8; do
+for t in 0 11 12 13 9 10 8; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
 done

@@ -40,12 +40,19 @@ def test_tile_kernel_on_gpu(case, knobs, monkeypatch):
 SMALL_TILE_CASES = [c for c in CASES if c[0] in ("cfg1-every-substep", "dense-pile-fused", "multi-collider", "batched-worlds", "boundary-shell-auto", "full-size-cfg2")]
 
 
+@pytest.mark.parametrize("tune", ["12", "13"], ids=["tune12-128-record-tiles", "tune13-tma-bulk-windows"])
 @pytest.mark.parametrize("knobs", [{}, FORCED], ids=["default", "forced-pool-crowded"])
 @pytest.mark.parametrize("case", SMALL_TILE_CASES, ids=[c[0] for c in SMALL_TILE_CASES])
-def test_tile_kernel_128_record_tiles_on_gpu(case, knobs, monkeypatch):
-    """BLOBS_PARAM_TUNE 12: the same kernel with 128-record tiles (128-thread CTAs)."""
+def test_tile_kernel_variants_on_gpu(case, knobs, tune, monkeypatch):
+    """BLOBS_PARAM_TUNE 12: the same kernel with 128-record tiles (128-thread CTAs); 13: windows fetched by TMA bulk copies
+    (cp.async.bulk + mbarrier; this one cannot run on the host-compiled build at all - the GPU run is its first). The very last
+    tests of the suite for that reason."""
+    import os
+
+    if tune == "13" and os.environ.get("BLOBS_TEST_EXPERIMENTAL") != "1":
+        pytest.skip("inline-PTX path that has never executed anywhere: run it on purpose (BLOBS_TEST_EXPERIMENTAL=1, under a timeout)")
     name, fn, kw = case
-    monkeypatch.setenv("BLOBS_B200_TUNE", "12")
+    monkeypatch.setenv("BLOBS_B200_TUNE", tune)
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     fn(**kw)

@@ -946,7 +946,7 @@ constexpr int TILE_THREADS = 256;
 // must stay under the 48 KB of static shared memory
 template <bool POOLED, int THREADS> struct TileCfg { static constexpr int WCAP = THREADS >= 256 ? (POOLED ? 320 : 384) : (POOLED ? 224 : 256); };
 #ifdef BLOBS_EMU
-inline unsigned long long tile_path_count[2] = {0, 0};   // [0] shared-memory windows, [1] global-memory fallback
+inline unsigned long long tile_path_count[3] = {0, 0, 0};   // [0] shared-memory windows, [1] global-memory fallback, [2] pooled variant: per-lane staged scan
 #endif
 
 // BLOBS_PARAM_TUNE 13: the three windows are fetched by the TMA engine instead of by the CTA's threads - one elected thread
@@ -1153,35 +1153,43 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams 
     list.clear();
     bool applied = false, big = false;
     const StagedHot src{win};
-    if (POOLED) {   // warp-collective: every lane calls. Lanes whose range is not staged take gather_single inside (global memory).
-        applied = gather_warp_core<4>(g, bp, src, Cc.ccold, do_gather, s, L, list, out, rec, B.vel, stats, pool[tid >> 5], P.pool_min,
-                                      P.crowded != 0u, big, p.x, p.y);
-    } else if (do_gather) {
-        if (staged) {
-            const uint32_t n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
-            const float srk = s.r * 1.00005f;              // prefilter: see gather_single
-            for (uint32_t base = 0; base < total; base += 32u) {
-                const uint32_t lim = min(32u, total - base);
-                uint32_t mask = 0;
-                for (uint32_t q = 0; q < lim; ++q) {
-                    const uint32_t t = base + q;
-                    const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
-                    const uint32_t oslot = __float_as_uint(o.w) & HOT_SLOT_MASK;
-                    const float dx = s.x - o.x, dy = s.y - o.y;
-                    const float d2 = __fmaf_rn(dx, dx, dy * dy);
-                    const float mdk = __fmaf_rn(o.z, 1.00005f, srk);
-                    if (oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << q;
-                }
-                while (mask) {
-                    const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
-                    mask &= mask - 1u;
-                    const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
-                    take_candidate<true, uint32_t>(s, rec_of(o, Cc.ccold), list, out, rec, B.vel, stats);
-                }
+    // per-lane scan of a staged span: prefilter, then the exact narrowphase into the ordered list (gather_single on shared memory)
+    auto scan_staged = [&]() {
+        const uint32_t n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
+        const float srk = s.r * 1.00005f;              // prefilter: see gather_single
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t lim = min(32u, total - base);
+            uint32_t mask = 0;
+            for (uint32_t q = 0; q < lim; ++q) {
+                const uint32_t t = base + q;
+                const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
+                const uint32_t oslot = __float_as_uint(o.w) & HOT_SLOT_MASK;
+                const float dx = s.x - o.x, dy = s.y - o.y;
+                const float d2 = __fmaf_rn(dx, dx, dy * dy);
+                const float mdk = __fmaf_rn(o.z, 1.00005f, srk);
+                if (oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << q;
             }
-        } else {
-            gather_single<true, uint32_t, 4>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
+            while (mask) {
+                const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
+                take_candidate<true, uint32_t>(s, rec_of(o, Cc.ccold), list, out, rec, B.vel, stats);
+            }
         }
+    };
+    if (POOLED) {   // warp-collective: every lane calls. Lanes whose range is not staged take gather_single inside (global memory).
+        // Lanes with 65 .. POOL_BIG_MIN staged candidates keep the per-lane path, as in k_main (config #3's compressed piles), but
+        // scan shared memory: they sit the pooled resolution out and are done right after it.
+        const bool lane_scan = staged && L.total > 64u && L.total <= POOL_BIG_MIN;
+        applied = gather_warp_core<4>(g, bp, src, Cc.ccold, do_gather && !lane_scan, s, L, list, out, rec, B.vel, stats, pool[tid >> 5], P.pool_min,
+                                      P.crowded != 0u, big, p.x, p.y);
+#ifdef BLOBS_EMU
+        if (lane_scan) tile_path_count[2]++;
+#endif
+        if (lane_scan) scan_staged();
+    } else if (do_gather) {
+        if (staged) scan_staged();
+        else gather_single<true, uint32_t, 4>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
     }
     if (big) {   // k_crowded does the whole body, pair counting included
         n_over = 1;

@@ -2248,9 +2248,7 @@ int World::profile_read(float* ms, uint64_t* nl, size_t n) {
 #ifdef BLOBS_EMU
 // host-compiled test build only (tests/emu): how many bodies k_tile served from its shared-memory windows / from the
 // global-memory fallback since the last call. Not part of the C ABI, absent from libblobs_b200.so.
-extern "C" void blobs_emu_tile_paths(unsigned long long* out2) {
-    out2[0] = blobs::tile_path_count[0];
-    out2[1] = blobs::tile_path_count[1];
-    blobs::tile_path_count[0] = blobs::tile_path_count[1] = 0;
+extern "C" void blobs_emu_tile_paths(unsigned long long* out3) {
+    for (int i = 0; i < 3; ++i) { out3[i] = blobs::tile_path_count[i]; blobs::tile_path_count[i] = 0; }
 }
 #endif

@@ -92,7 +92,7 @@ def test_tile_kernel(case, knobs, monkeypatch):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     lib = load_emu()
-    paths = (C.c_ulonglong * 2)()
+    paths = (C.c_ulonglong * 3)()
     lib.blobs_emu_tile_paths(paths)   # reset
     with emulated():
         fn(**kw)

@@ -583,7 +583,7 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": B_MAIN * n, "avg_launch_ms": main_ms / max(main_n, 1),
                          "timing": "CUDA events around every k_main launch, second timed pass of the same K steps",
-                         "traffic": ncu_traffic()},
+                         "traffic": ncu_traffic() if args.tune in (0, 2, 3, 4, 5, 6, 7) else None},   # the committed ncu capture is k_main's (per-lane variant)
             "pipeline": {"algorithmic_gbps": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9,
                          "frac_of_peak": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9 / (peak * world),
                          "sphere_substeps_per_sec": value * substeps,

@@ -28,6 +28,9 @@ for t in 0 11 12; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
 done
+# throughput vs simulated time (free fall -> compression -> settled pile), k_main and k_tile
+timeout 300 python profiles/trace_cfg2.py 700 50 > $O/trace_kmain.jsonl 2>> $O/sweep.err
+BLOBS_B200_TUNE=11 timeout 300 python profiles/trace_cfg2.py 700 50 > $O/trace_ktile.jsonl 2>> $O/sweep.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 100 --csv --log-file $O/ncu_launches.csv \
     env BLOBS_BENCH_AUTOTUNE=0 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_tile" -s 8 -c 1 -o $O/tile_sparse \

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--probe", action="store_true", help="(internal) kernel-variant probe run by the autotuner in a child process")
     ap.add_argument("--device", type=int, default=None, help="(internal) CUDA device of the probe")
+    ap.add_argument("--probe-strips", action="store_true", help="(internal) strip-mode kernel-variant probe: one child per rank, own process group")
     return ap.parse_args()
 
 
@@ -214,6 +215,7 @@ def build_single_world(workload, device):
     return w, sc.n_bodies
 
 
+_EMU_CTX = None
 PROBE_VARIANTS = (0, 11, 12)   # BLOBS_PARAM_TUNE: k_main, k_tile (256-record tiles), k_tile (128-record tiles)
 VARIANT_NAME = {0: "k_main", 11: "k_tile", 12: "k_tile<128>"}
 
@@ -287,6 +289,106 @@ def autotune_main_kernel(args, device):
         return 0, rep
 
 
+def run_probe_strips(args):
+    """Child processes of the N > 1 autotuner (one per rank, their own process group on another port): a small strip-decomposed
+    world (128 lattice columns per rank) once through k_main and once through k_tile, W warm-up + K timed steps each. Prints
+    {"ms": {tune: max over ranks}, "parity": {tune: bool over all ranks}}: parity = every rank ends up owning the same bodies with
+    bit-identical positions in both runs. BLOBS_TEST_EMU=1 runs the same thing on the host-compiled build over gloo (tests)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    emu = os.environ.get("BLOBS_TEST_EMU") == "1"
+    if emu:   # test infrastructure: CPU rank processes on the host-compiled kernels, socket stand-in for NCCL (tests/emu)
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import emu_loader
+
+        os.environ["BLOBS_EMU_NCCL_LIB"] = os.path.join(emu_loader.EMU_DIR, "libnccl_fake.so")
+        global _EMU_CTX
+        _EMU_CTX = emu_loader.emulated()   # kept alive for the life of the process
+        _EMU_CTX.__enter__()
+        dist.init_process_group("gloo")
+        dev = "cpu"
+        nx, ny = 24 * world, 48
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dev = "cuda"
+        nx, ny = 128 * world, 2048
+    import blobs_b200
+    from blobs_b200 import scenes as S
+    from blobs_b200 import strips
+
+    sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * max(nx, ny), name="cfg5-probe", cell_size=1.0)
+    edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
+    variants = (0, 11)
+    ms, owned, pos, flags = {}, {}, {}, 0
+    for tune in variants:
+        w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
+        S.build(w, sc)
+        w.set_param(blobs_b200.abi.PARAM_TUNE, tune)
+        uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
+        dist.broadcast(uid, 0)
+        w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=4 * ny, migrate_capacity=2 * ny)
+        flags |= w.step(DT, n=max(args.warmup, 1))["nan_detected"]
+        t = 0.0
+        for _ in range(args.steps):
+            st = w.step(DT)
+            t += st["gpu_ms"]
+            flags |= st["nan_detected"]
+        ms[tune] = t / max(args.steps, 1)
+        owned[tune] = w.strip_owned().astype(bool)
+        pos[tune] = w.read_positions()
+        del w
+    same = {}
+    for tune in variants[1:]:
+        same[tune] = bool(np.array_equal(owned[0], owned[tune]) and np.array_equal(pos[0][owned[0]].view(np.uint32), pos[tune][owned[tune]].view(np.uint32)) and flags == 0)
+    t_ms = torch.tensor([ms[v] for v in variants], dtype=torch.float64, device=dev)
+    t_ok = torch.tensor([1.0 if same[v] else 0.0 for v in variants[1:]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+    print(json.dumps({"probe": True, "ms": {str(v): float(t_ms[i]) for i, v in enumerate(variants)},
+                      "parity": {str(v): bool(float(t_ok[i]) > 0.5) for i, v in enumerate(variants[1:])}, "steps": args.steps, "warmup": args.warmup,
+                      "spheres_per_rank": nx * ny // world}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def autotune_strips(args):
+    """N > 1 (strip-decomposed world): every rank starts ONE child (run_probe_strips); the children form their own process group
+    on MASTER_PORT + 23 and time k_main against k_tile on a small strip world, with bit-exact parity required on every rank. All
+    ranks read the same all-reduced verdict. Any failure (a child dies, the group hangs until the timeout) means k_main."""
+    if args.tune or os.environ.get("BLOBS_BENCH_AUTOTUNE", "1") == "0":
+        return args.tune, {"mode": "off (variant forced)" if args.tune else "off"}
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}   # the children rendezvous among themselves (rank 0 hosts the store)
+    env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 23)
+    env.setdefault("MASTER_ADDR", "127.0.0.1")
+    cmd = [sys.executable, os.path.abspath(__file__), "--probe-strips", "--warmup", "30", "--steps", "20"]
+    rep = {"mode": "strip probe, one child process per rank in their own process group: k_main (tune 0) vs k_tile (tune 11), bit-exact parity required on every rank"}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "180")), env=env)
+        line = next((l for l in r.stdout.splitlines() if l.startswith("{") and '"probe"' in l), None)
+        if r.returncode != 0 or line is None:
+            rep["result"] = f"probe failed (rc={r.returncode}): {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else 'no output'}"[:300]
+            return 0, rep
+        p = json.loads(line)
+        rep.update({"ms_per_step": {VARIANT_NAME[int(k)]: v for k, v in p["ms"].items()},
+                    "parity_bit_exact": {VARIANT_NAME[int(k)]: v for k, v in p["parity"].items()}, "probe_steps": p["steps"], "probe_spheres_per_rank": p.get("spheres_per_rank")})
+        best, best_ms = 0, 0.97 * p["ms"]["0"]
+        for k, v in p["ms"].items():
+            if int(k) and p["parity"].get(k) is True and v < best_ms:
+                best, best_ms = int(k), v
+        rep["chosen"] = VARIANT_NAME[best]
+        return best, rep
+    except subprocess.TimeoutExpired:
+        rep["result"] = "probe timed out"
+        return 0, rep
+    except Exception as e:  # noqa: BLE001 - the probe is optional
+        rep["result"] = f"probe error: {e}"[:300]
+        return 0, rep
+
+
 def strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap, on_step=None):
     """K frames of a strip-decomposed world with the pipelined distributed host I/O of the C ABI. `sl`, `xy`, `cnt` are pairs of
     pinned host tensors (slot list, positions, count); both slot lists / counts hold the current owned list on entry. The newest
@@ -333,11 +435,13 @@ def run_ours(args):
     import blobs_b200
     from blobs_b200 import scenes as S
 
-    # which variant of the dominant kernel runs: measured on this GPU first (N = 1; the strip path keeps k_main until k_tile has
-    # been run in strip mode on real GPUs)
-    tune_report = {"mode": "off (N > 1)"}
+    # which variant of the dominant kernel runs: measured first, in child processes (a fault in a variant that had never run on a
+    # GPU when it was committed costs the probe, not the benchmark)
+    tune_report = {"mode": "off (N > 1, independent worlds)"}
     if world == 1:
         args.tune, tune_report = autotune_main_kernel(args, local)
+    elif args.workload == "cfg2":   # strip-decomposed world: probed by a group of child processes, one per rank
+        args.tune, tune_report = autotune_strips(args)
 
     scaling = "weak"
     if args.workload == "cfg3":
@@ -603,7 +707,9 @@ def run_ours(args):
 def main():
     args = parse()
     try:
-        if args.probe:
+        if args.probe_strips:
+            run_probe_strips(args)
+        elif args.probe:
             run_probe(args)
         elif args.impl == "reference":
             run_reference(args)

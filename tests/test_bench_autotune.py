@@ -64,3 +64,31 @@ def test_autotune_off_when_a_variant_is_forced_or_the_child_hangs(monkeypatch):
     monkeypatch.setattr(subprocess, "run", hang)
     tune, rep = bench.autotune_main_kernel(_args(probe=False), 0)
     assert tune == 0 and rep["result"] == "probe timed out"
+
+
+@pytest.mark.emu
+def test_strip_probe_children_form_their_own_group():
+    """N > 1: two parent ranks under torchrun each start one child; the children (host-compiled kernels, gloo, socket stand-in for
+    NCCL) rendezvous on MASTER_PORT + 23, run the small strip world through k_main and k_tile and agree on one verdict."""
+    import socket
+
+    from .emu_loader import build
+
+    build()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, BLOBS_TEST_EMU="1", BLOBS_BENCH_PROBE_TIMEOUT="400")
+    env.pop("BLOBS_BENCH_AUTOTUNE", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(REPO, "tests", "strip_autotune_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    verdicts = [json.loads(l[len("VERDICT "):]) for l in r.stdout.splitlines() if l.startswith("VERDICT ")]
+    assert sorted(v["rank"] for v in verdicts) == [0, 1]
+    for v in verdicts:
+        rep = v["report"]
+        assert rep.get("parity_bit_exact") == {"k_tile": True}, rep
+        assert rep["chosen"] in ("k_main", "k_tile") and v["tune"] in (0, 11)
+    assert verdicts[0]["report"]["ms_per_step"] == verdicts[1]["report"]["ms_per_step"]   # all-reduced: every rank decides alike

@@ -216,6 +216,8 @@ def build_single_world(workload, device):
 
 
 _EMU_CTX = None
+STRIP_VARIANTS = ((0, 0), (11, 0), (0, 1), (11, 1))   # (BLOBS_PARAM_TUNE, BLOBS_PARAM_STRIP_P2P) probed at N > 1; the first is the baseline
+STRIP_VARIANT_NAME = {"0": "k_main + ncclSend/ncclRecv", "11": "k_tile + ncclSend/ncclRecv", "0+p2p": "k_main + peer-memory exchange", "11+p2p": "k_tile + peer-memory exchange"}
 PROBE_VARIANTS = (0, 11, 12)   # BLOBS_PARAM_TUNE: k_main, k_tile (256-record tiles), k_tile (128-record tiles)
 VARIANT_NAME = {0: "k_main", 11: "k_tile", 12: "k_tile<128>"}
 
@@ -322,34 +324,42 @@ def run_probe_strips(args):
 
     sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * max(nx, ny), name="cfg5-probe", cell_size=1.0)
     edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
-    variants = (0, 11)
-    ms, owned, pos, flags = {}, {}, {}, 0
-    for tune in variants:
+    # (BLOBS_PARAM_TUNE, peer-memory exchange): the baseline first. A peer exchange that delivered stale ghosts, or waited out its
+    # timeout (bit 3 of nan_detected), fails the parity check like any other wrong variant.
+    variants = STRIP_VARIANTS
+    ms, owned, pos, flags, active = {}, {}, {}, {}, {}
+    for v in variants:
+        tune, p2p = v
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
         w.set_param(blobs_b200.abi.PARAM_TUNE, tune)
+        w.set_param(blobs_b200.abi.PARAM_STRIP_P2P, p2p)
         uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
         dist.broadcast(uid, 0)
         w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=4 * ny, migrate_capacity=2 * ny)
-        flags |= w.step(DT, n=max(args.warmup, 1))["nan_detected"]
+        active[v] = int(w.get_param(blobs_b200.abi.PARAM_STRIP_P2P)) == p2p   # a requested peer exchange may have fallen back to NCCL
+        flags[v] = w.step(DT, n=max(args.warmup, 1))["nan_detected"]
         t = 0.0
         for _ in range(args.steps):
             st = w.step(DT)
             t += st["gpu_ms"]
-            flags |= st["nan_detected"]
-        ms[tune] = t / max(args.steps, 1)
-        owned[tune] = w.strip_owned().astype(bool)
-        pos[tune] = w.read_positions()
+            flags[v] |= st["nan_detected"]
+        ms[v] = t / max(args.steps, 1)
+        owned[v] = w.strip_owned().astype(bool)
+        pos[v] = w.read_positions()
         del w
+    base = variants[0]
     same = {}
-    for tune in variants[1:]:
-        same[tune] = bool(np.array_equal(owned[0], owned[tune]) and np.array_equal(pos[0][owned[0]].view(np.uint32), pos[tune][owned[tune]].view(np.uint32)) and flags == 0)
+    for v in variants[1:]:
+        same[v] = bool(active[v] and flags[v] == 0 and flags[base] == 0 and np.array_equal(owned[base], owned[v])
+                       and np.array_equal(pos[base][owned[base]].view(np.uint32), pos[v][owned[v]].view(np.uint32)))
     t_ms = torch.tensor([ms[v] for v in variants], dtype=torch.float64, device=dev)
     t_ok = torch.tensor([1.0 if same[v] else 0.0 for v in variants[1:]], dtype=torch.float64, device=dev)
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-    print(json.dumps({"probe": True, "ms": {str(v): float(t_ms[i]) for i, v in enumerate(variants)},
-                      "parity": {str(v): bool(float(t_ok[i]) > 0.5) for i, v in enumerate(variants[1:])}, "steps": args.steps, "warmup": args.warmup,
+    key = lambda v: f"{v[0]}+p2p" if v[1] else str(v[0])
+    print(json.dumps({"probe": True, "ms": {key(v): float(t_ms[i]) for i, v in enumerate(variants)},
+                      "parity": {key(v): bool(float(t_ok[i]) > 0.5) for i, v in enumerate(variants[1:])}, "steps": args.steps, "warmup": args.warmup,
                       "spheres_per_rank": nx * ny // world}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
@@ -359,34 +369,37 @@ def autotune_strips(args):
     """N > 1 (strip-decomposed world): every rank starts ONE child (run_probe_strips); the children form their own process group
     on MASTER_PORT + 23 and time k_main against k_tile on a small strip world, with bit-exact parity required on every rank. All
     ranks read the same all-reduced verdict. Any failure (a child dies, the group hangs until the timeout) means k_main."""
-    if args.tune or os.environ.get("BLOBS_BENCH_AUTOTUNE", "1") == "0":
-        return args.tune, {"mode": "off (variant forced)" if args.tune else "off"}
+    forced_p2p = 1 if os.environ.get("BLOBS_B200_STRIP_P2P", "0") not in ("", "0") else 0
+    if args.tune or forced_p2p or os.environ.get("BLOBS_BENCH_AUTOTUNE", "1") == "0":
+        return args.tune, forced_p2p, {"mode": "off (variant forced)" if (args.tune or forced_p2p) else "off"}
     env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}   # the children rendezvous among themselves (rank 0 hosts the store)
     env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 23)
     env.setdefault("MASTER_ADDR", "127.0.0.1")
     cmd = [sys.executable, os.path.abspath(__file__), "--probe-strips", "--warmup", "30", "--steps", "20"]
-    rep = {"mode": "strip probe, one child process per rank in their own process group: k_main (tune 0) vs k_tile (tune 11), bit-exact parity required on every rank"}
+    rep = {"mode": "strip probe, one child process per rank in their own process group: {k_main, k_tile} x {ncclSend/ncclRecv, peer-memory exchange}, "
+                   "bit-exact parity with the baseline required on every rank"}
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("BLOBS_BENCH_PROBE_TIMEOUT", "180")), env=env)
         line = next((l for l in r.stdout.splitlines() if l.startswith("{") and '"probe"' in l), None)
         if r.returncode != 0 or line is None:
             rep["result"] = f"probe failed (rc={r.returncode}): {r.stderr.strip().splitlines()[-1] if r.stderr.strip() else 'no output'}"[:300]
-            return 0, rep
+            return 0, 0, rep
         p = json.loads(line)
-        rep.update({"ms_per_step": {VARIANT_NAME[int(k)]: v for k, v in p["ms"].items()},
-                    "parity_bit_exact": {VARIANT_NAME[int(k)]: v for k, v in p["parity"].items()}, "probe_steps": p["steps"], "probe_spheres_per_rank": p.get("spheres_per_rank")})
-        best, best_ms = 0, 0.97 * p["ms"]["0"]
+        rep.update({"ms_per_step": {STRIP_VARIANT_NAME.get(k, k): v for k, v in p["ms"].items()},
+                    "parity_bit_exact": {STRIP_VARIANT_NAME.get(k, k): v for k, v in p["parity"].items()}, "probe_steps": p["steps"],
+                    "probe_spheres_per_rank": p.get("spheres_per_rank")})
+        best, best_ms = "0", 0.97 * p["ms"]["0"]
         for k, v in p["ms"].items():
-            if int(k) and p["parity"].get(k) is True and v < best_ms:
-                best, best_ms = int(k), v
-        rep["chosen"] = VARIANT_NAME[best]
-        return best, rep
+            if k != "0" and p["parity"].get(k) is True and v < best_ms:
+                best, best_ms = k, v
+        rep["chosen"] = STRIP_VARIANT_NAME.get(best, best)
+        return int(best.split("+")[0]), (1 if best.endswith("+p2p") else 0), rep
     except subprocess.TimeoutExpired:
         rep["result"] = "probe timed out"
-        return 0, rep
+        return 0, 0, rep
     except Exception as e:  # noqa: BLE001 - the probe is optional
         rep["result"] = f"probe error: {e}"[:300]
-        return 0, rep
+        return 0, 0, rep
 
 
 def strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap, on_step=None):
@@ -440,8 +453,9 @@ def run_ours(args):
     tune_report = {"mode": "off (N > 1, independent worlds)"}
     if world == 1:
         args.tune, tune_report = autotune_main_kernel(args, local)
-    elif args.workload == "cfg2":   # strip-decomposed world: probed by a group of child processes, one per rank
-        args.tune, tune_report = autotune_strips(args)
+    strip_p2p = 0
+    if world > 1 and args.workload == "cfg2":   # strip-decomposed world: probed by a group of child processes, one per rank
+        args.tune, strip_p2p, tune_report = autotune_strips(args)
 
     scaling = "weak"
     if args.workload == "cfg3":
@@ -465,6 +479,8 @@ def run_ours(args):
                 f"({nx * ny // world} spheres per GPU), ghost/migration exchange with both neighbours every substep")
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
+        if strip_p2p:
+            w.set_param(blobs_b200.abi.PARAM_STRIP_P2P, 1)   # chosen by the probe (BLOBS_B200_STRIP_P2P=1 in the environment forces it)
         edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
         uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).cuda()
         dist.broadcast(uid, 0)

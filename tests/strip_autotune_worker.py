@@ -13,5 +13,5 @@ import bench  # noqa: E402
 
 if __name__ == "__main__":
     args = argparse.Namespace(tune=0, workload="cfg2", warmup=200, steps=100)
-    tune, rep = bench.autotune_strips(args)
-    print("VERDICT " + json.dumps({"rank": int(os.environ["RANK"]), "tune": tune, "report": rep}), flush=True)
+    tune, p2p, rep = bench.autotune_strips(args)
+    print("VERDICT " + json.dumps({"rank": int(os.environ["RANK"]), "tune": tune, "p2p": p2p, "report": rep}), flush=True)

@@ -80,6 +80,7 @@ def test_strip_probe_children_form_their_own_group():
         port = sk.getsockname()[1]
     env = dict(os.environ, BLOBS_TEST_EMU="1", BLOBS_BENCH_PROBE_TIMEOUT="400")
     env.pop("BLOBS_BENCH_AUTOTUNE", None)
+    env.pop("BLOBS_B200_STRIP_P2P", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(REPO, "tests", "strip_autotune_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -89,6 +90,7 @@ def test_strip_probe_children_form_their_own_group():
     assert sorted(v["rank"] for v in verdicts) == [0, 1]
     for v in verdicts:
         rep = v["report"]
-        assert rep.get("parity_bit_exact") == {"k_tile": True}, rep
-        assert rep["chosen"] in ("k_main", "k_tile") and v["tune"] in (0, 11)
+        assert rep.get("parity_bit_exact") == {"k_tile + ncclSend/ncclRecv": True, "k_main + peer-memory exchange": True, "k_tile + peer-memory exchange": True}, rep
+        assert rep["chosen"] in bench.STRIP_VARIANT_NAME.values() and v["tune"] in (0, 11) and v["p2p"] in (0, 1)
+        assert (v["p2p"] == 1) == rep["chosen"].endswith("peer-memory exchange") and (v["tune"] == 11) == rep["chosen"].startswith("k_tile")
     assert verdicts[0]["report"]["ms_per_step"] == verdicts[1]["report"]["ms_per_step"]   # all-reduced: every rank decides alike

@@ -16,6 +16,8 @@ run() {  # name, extra env...
       bench.py --gpus 2 --steps 60 --warmup 60 ${TUNE:+--tune $TUNE} > $O/$name.json 2> $O/$name.err
   echo "$name rc=$?" >> $O/runs.log
 }
+run auto            BLOBS_BENCH_AUTOTUNE=1          # the default line: the child-group probe picks kernel variant and exchange kind
+export BLOBS_BENCH_AUTOTUNE=0                        # everything below forces its combination
 run nccl            BLOBS_B200_STRIP_P2P=0
 run p2p             BLOBS_B200_STRIP_P2P=1
 run p2p_graph       BLOBS_B200_STRIP_P2P=1 BLOBS_B200_STRIP_GRAPH=1

@@ -14,4 +14,6 @@ import bench  # noqa: E402
 if __name__ == "__main__":
     args = argparse.Namespace(tune=0, workload="cfg2", warmup=200, steps=100)
     tune, p2p, rep = bench.autotune_strips(args)
-    print("VERDICT " + json.dumps({"rank": int(os.environ["RANK"]), "tune": tune, "p2p": p2p, "report": rep}), flush=True)
+    # one write() call including the newline, so that the two ranks' lines cannot interleave on the shared pipe
+    sys.stdout.write("VERDICT " + json.dumps({"rank": int(os.environ["RANK"]), "tune": tune, "p2p": p2p, "report": rep}) + "\n")
+    sys.stdout.flush()

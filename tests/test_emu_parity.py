@@ -20,6 +20,15 @@ pytestmark = pytest.mark.emu
 DEFAULT = {}
 FORCED = {"BLOBS_B200_POOL": "1", "BLOBS_B200_POOL_MIN": "1", "BLOBS_B200_CROWDED": "1"}
 
+
+def _skip_if_redundant(case, knobs):
+    """The 30 s combinations whose paths the other cases already walk run only with BLOBS_TEST_SLOW=1 (the CPU suite is meant
+    to finish in a few minutes); the default-knob twin of each still runs."""
+    import os
+
+    if case[0] == "batched-worlds" and knobs is FORCED and os.environ.get("BLOBS_TEST_SLOW") != "1":
+        pytest.skip("redundant combination; set BLOBS_TEST_SLOW=1")
+
 CASES = [
     ("overflow30-fused-inline", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=30, fused=1, crowded=0)),
     ("overflow30-split-crowded", T.test_contact_list_overflow_keeps_reference_order, dict(n_small=30, fused=0, crowded=1)),
@@ -53,6 +62,7 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
     _, fn, kw = case
+    _skip_if_redundant(case, knobs)
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)   # read by World's constructor (same meaning as the BLOBS_PARAM_* knobs)
     with emulated():
@@ -88,6 +98,7 @@ def test_tile_kernel(case, knobs, monkeypatch):
     from .emu_loader import load_emu
 
     _, fn, kw = case
+    _skip_if_redundant(case, knobs)
     monkeypatch.setenv("BLOBS_B200_TUNE", "11")
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)

@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--tune", type=int, default=0, help="kernel variant selector (BLOBS_PARAM_TUNE)")
+    ap.add_argument("--list", type=int, default=None, help="BLOBS_PARAM_LIST: 0 = cell grid every substep, 1 = neighbour lists")
+    ap.add_argument("--skin", type=float, default=None, help="BLOBS_PARAM_SKIN (fraction of the largest radius)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--probe", action="store_true", help="(internal) kernel-variant probe run by the autotuner in a child process")
     ap.add_argument("--device", type=int, default=None, help="(internal) CUDA device of the probe")
@@ -499,6 +501,10 @@ def run_ours(args):
         nb = sc.n_bodies
     if args.tune:
         w.set_param(blobs_b200.abi.PARAM_TUNE, args.tune)
+    if args.list is not None:
+        w.set_param(blobs_b200.abi.PARAM_LIST, args.list)
+    if args.skin is not None:
+        w.set_param(blobs_b200.abi.PARAM_SKIN, args.skin)
     if os.environ.get("BLOBS_BENCH_GRAPH", "1") == "0":
         w.set_param(blobs_b200.abi.PARAM_GRAPH, 0)
     if "BLOBS_BENCH_POOL" in os.environ:      # A/B aid: 0 per-lane contact resolution, 1 warp-pooled, 2 auto (library default)
@@ -549,11 +555,13 @@ def run_ours(args):
 
     barrier()
     sampler.mark()
+    nl0 = (w.get_param(blobs_b200.abi.PARAM_LIST_REBUILDS), w.get_param(blobs_b200.abi.PARAM_LIST_SUBSTEPS))
     l0 = w.kernel_info()["launches"]
     t_dev_ms, collisions, overflow = timed_pass(False)
     barrier()
     info = w.kernel_info()
     launches = info["launches"] - l0
+    nl1 = (w.get_param(blobs_b200.abi.PARAM_LIST_REBUILDS), w.get_param(blobs_b200.abi.PARAM_LIST_SUBSTEPS))
     t_prof_ms, _, _ = timed_pass(True)
     barrier()
     prof = w.profile_read()
@@ -690,6 +698,8 @@ def run_ours(args):
                        "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": overflow,
                        "crowded_mode": int(w.get_param(blobs_b200.abi.PARAM_CROWDED)), "pool_mode": int(w.get_param(blobs_b200.abi.PARAM_POOL)),
                        "sim_time_s": [W * DT, (W + K) * DT],
+                       "list_mode": int(w.get_param(blobs_b200.abi.PARAM_LIST)), "skin": w.get_param(blobs_b200.abi.PARAM_SKIN),
+                       "list_rebuilds_per_substep": (nl1[0] - nl0[0]) / max(nl1[1] - nl0[1], 1.0),
                        "strip_max_ghosts_per_message": int(mx[0]), "strip_max_migrants_per_message": int(mx[1]),
                        "strip_exchange": (("peer-memory stores over NVLink (k_strip_push, CUDA IPC)" if int(w.get_param(blobs_b200.abi.PARAM_STRIP_P2P)) else "grouped ncclSend/ncclRecv")
                                           if strips_on else None),

@@ -49,7 +49,10 @@ __device__ __forceinline__ Rec make_rec(const float4 h, const uint4 c) {
     return r;
 }
 __device__ __forceinline__ Rec load_rec(const Broadphase& bp, const uint4* __restrict__ ccold, uint32_t k) {
-    const float4 h = __ldg(bp.hot + k);
+    float4 h = __ldg(bp.hot + k);
+    // list pipeline: the cell-sorted array dates from the last list rebuild - it still says WHO is near (within the skin), the
+    // record itself is re-read from the slot-indexed snapshot array of the previous substep
+    if (bp.snap != nullptr) h = __ldg(bp.snap + (__float_as_uint(h.w) & HOT_SLOT_MASK));
     const uint32_t w = __float_as_uint(h.w);
     if (w & HOT_COLD_BIT) return make_rec(h, __ldg(ccold + (w & HOT_SLOT_MASK)));
     // default sphere: calculated_mass = 2 * (2r) exactly, groups ALL; its parent has no other collider, so it can never equal
@@ -107,6 +110,7 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc& g, const Broa
 // ------------------------------------------------------------------------------------------------
 struct SelfCol {
     float x, y, r, m;
+    float qx, qy;    // centre of the cell-range query: (x, y), or - list pipeline - where the collider was when the grid was built
     uint32_t memb, filt;
     uint32_t body;   // parent body slot
     uint32_t slot;   // collider slot
@@ -263,7 +267,7 @@ template <bool ORDERED, class KEY>
 __device__ __forceinline__ void gather_generic(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, const SelfCol& s,
                                                ContactList<KEY>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
                                                DeviceStats* stats) {
-    for_each_candidate(g, bp, ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
+    for_each_candidate(g, bp, ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) { take_candidate<ORDERED, KEY>(s, o, list, out, rec, vel, stats); });
 }
 
 // Latency- and divergence-oriented gather for the common case (<= 3 rows, no column wrap):
@@ -352,7 +356,7 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
         };
         for (int ci = 0; ci < ncols; ++ci) {
             const SelfCol s = cols[ci];
-            for_each_candidate(g, bp, ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) {
+            for_each_candidate(g, bp, ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
                 if (c.coincident) offer(pair_key<unsigned long long>(s.slot, c.other, true), c.i_am_a ? 0.01f : -0.01f, 0.f);
@@ -394,15 +398,10 @@ struct PoolSmem {                 // per warp
     uint32_t fb;                  // owner lanes that must fall back to the serial rescan
 };
 
-// Where the pooled path reads hot record halves from: the cell-sorted array in global memory (k_main), or the windows a
-// k_tile CTA staged in shared memory (indices are then window offsets).
+// Where the pooled path reads hot record halves from: the cell-sorted array in global memory.
 struct GlobalHot {
     const float4* hot;
     __device__ __forceinline__ float4 operator()(uint32_t k) const { return __ldg(hot + k); }
-};
-struct StagedHot {
-    const float4* win;
-    __device__ __forceinline__ float4 operator()(uint32_t k) const { return win[k]; }
 };
 __device__ __forceinline__ Rec rec_of(const float4 h, const uint4* __restrict__ ccold) {
     const uint32_t w = __float_as_uint(h.w);
@@ -551,7 +550,7 @@ __device__ __forceinline__ bool gather_warp_core(const GridDesc& g, const Broadp
                 so.m = __shfl_sync(FULL, s.m, o); so.memb = __shfl_sync(FULL, s.memb, o); so.filt = __shfl_sync(FULL, s.filt, o);
                 so.body = __shfl_sync(FULL, s.body, o);
                 const uint32_t sf = __shfl_sync(FULL, sflag, o);
-                so.slot = sf & HOT_SLOT_MASK; so.sensor = (sf & HOT_SENSOR_BIT) != 0u; so.wbase = 0u;
+                so.slot = sf & HOT_SLOT_MASK; so.sensor = (sf & HOT_SENSOR_BIT) != 0u; so.wbase = 0u; so.qx = so.x; so.qy = so.y;
                 if (act) {
                     const Rec r = rec_of(src(ps.key[i]), ccold);
                     Contact ct;
@@ -692,9 +691,64 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
     B.pos[b] = make_float2(px, py);
 }
 
+// ---- list pipeline: displacement tracking -------------------------------------------------------------------------
+// Every publisher (a kernel that writes new collider snapshots) measures how far each snapshot has moved from where it was
+// when the neighbour lists were built, relative to a common displacement c (bodies falling together have not moved RELATIVE
+// to each other): m = |snapshot - ref - c|. A pair that is NOT in a list was further apart than r_a + r_b + skin at build time,
+// and |(d_a - c) - (d_b - c)| <= m_a + m_b, so while max m <= 0.45 * skin no such pair can touch: the lists remain supersets
+// of the contact set. The slack term (a few ulps of the coordinates) covers the rounding of this estimate and of the exact
+// narrowphase. c is only an estimate (sampled mean, extrapolated by k_nl_decide): it decides WHEN lists are rebuilt, never
+// WHAT the contacts are.
+struct NlAcc { float m, dx, dy; uint32_t n; };
+__device__ __forceinline__ void nl_track(float ax, float ay, float refx, float refy, float cx, float cy, NlAcc& na) {
+    const float ddx = ax - refx, ddy = ay - refy;
+    const float ex = ddx - cx, ey = ddy - cy;
+    float m = sqrtf(ex * ex + ey * ey) * 1.000001f + 4e-6f * (fabsf(ax) + fabsf(ay));
+    if (!(m == m)) m = 3.4e38f;   // NaN position: forces a rebuild every substep (lists then always date from this very snapshot)
+    na.m = fmaxf(na.m, m);
+    if (ddx == ddx && ddy == ddy && fabsf(ddx) < 1e30f && fabsf(ddy) < 1e30f) { na.dx += ddx; na.dy += ddy; na.n++; }
+}
+// CTA-wide commit of the tracking (and of a pair count): one atomicMax per CTA and only if it raises the maximum; every 64th
+// CTA contributes its displacement sum (a sample is enough for an estimate). Must be reached by every thread of the CTA.
+__device__ __forceinline__ void nl_commit(NlCtl* ctl, const NlAcc& na, unsigned long long* pair_counter, unsigned int n_pairs) {
+    __shared__ uint32_t s_m[32], s_n[32], s_p[32];
+    __shared__ float s_x[32], s_y[32];
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nw = (blockDim.x + 31u) >> 5;
+    const bool sample = (blockIdx.x & 63u) == 0u;
+    const uint32_t mb = __reduce_max_sync(FULL, __float_as_uint(na.m));
+    const uint32_t np = __reduce_add_sync(FULL, n_pairs);
+    float sx = na.dx, sy = na.dy;
+    uint32_t sn = na.n;
+    if (sample) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { sx += __shfl_xor_sync(FULL, sx, d); sy += __shfl_xor_sync(FULL, sy, d); }
+        sn = __reduce_add_sync(FULL, sn);
+    }
+    if (lane == 0) { s_m[warp] = mb; s_p[warp] = np; s_x[warp] = sx; s_y[warp] = sy; s_n[warp] = sn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t M = 0, N = 0, Pn = 0;
+        float X = 0.f, Y = 0.f;
+        for (uint32_t w = 0; w < nw; ++w) { M = max(M, s_m[w]); Pn += s_p[w]; X += s_x[w]; Y += s_y[w]; N += s_n[w]; }
+        if (Pn) atomicAdd(pair_counter, (unsigned long long)Pn);
+        if (ctl != nullptr) {
+            if (M > *reinterpret_cast<volatile unsigned int*>(&ctl->max_m)) atomicMax(&ctl->max_m, M);
+            if (sample && N) { atomicAdd(&ctl->sum_x, X); atomicAdd(&ctl->sum_y, Y); atomicAdd(&ctl->n_sum, N); }
+        }
+    }
+}
+
 // Collider snapshot (physics.rs:360-366): abs.translation = M(rot) * offset.translation + pos, with
 // glam's Mat2::from_angle columns (cos, sin), (-sin, cos) and M*v = x_axis*v.x + y_axis*v.y.
-// Then bins the collider into the next broadphase table.
+__device__ __forceinline__ float2 snapshot_of(const ColliderArrays& Cc, uint32_t c, uint32_t cflags, float sx, float sy, float rot) {
+    float2 off = make_float2(0.f, 0.f);
+    if (cflags & CF_OFFSET) off = Cc.coff[c];
+    float sn = 0.0f, cs = 1.0f;
+    if (rot != 0.0f) sincosf(rot, &sn, &cs);
+    return make_float2(fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx), fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy));
+}
+
 // Bins one collider: rank within its cell (atomic on the cell counter) + warp-aggregated add to the counter of the
 // scan tile that owns the cell (lanes of a warp mostly share a tile, so this is ~1 extra atomic per warp).
 __device__ __forceinline__ uint32_t bin_collider(uint32_t* tab_next, uint32_t* tile_next, uint32_t cell) {
@@ -705,18 +759,31 @@ __device__ __forceinline__ uint32_t bin_collider(uint32_t* tab_next, uint32_t* t
     return rank;
 }
 
-__device__ __forceinline__ float2 publish_collider(const GridDesc& g, const ColliderArrays& Cc, uint32_t* tab_next, uint32_t* tile_next,
-                                                   uint32_t c, uint32_t cflags, uint32_t wbase, float sx, float sy, float rot) {
-    float2 off = make_float2(0.f, 0.f);
-    if (cflags & CF_OFFSET) off = Cc.coff[c];
-    float sn = 0.0f, cs = 1.0f;
-    if (rot != 0.0f) sincosf(rot, &sn, &cs);
-    const float ax = fadd(fadd(fmul(cs, off.x), fmul(-sn, off.y)), sx);
-    const float ay = fadd(fadd(fmul(sn, off.x), fmul(cs, off.y)), sy);
-    Cc.cabs[c] = make_float2(ax, ay);
-    const uint32_t cell = wbase + cell_index(g, bin_coord(ax, g.inv_cell), bin_coord(ay, g.inv_cell));
-    Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
-    return make_float2(ax, ay);
+// Publishes the new snapshot of one collider. Grid pipeline: bins it into the table under construction. List pipeline: writes
+// the slot-indexed record for the next substep's contact pass and tracks its displacement (see nl_track).
+__device__ __forceinline__ float2 publish_collider(const GridDesc& g, const ColliderArrays& Cc, const Broadphase& bp, uint32_t c, uint32_t cflags,
+                                                   uint32_t wbase, float sx, float sy, float rot, NlAcc& na) {
+    const float2 a = snapshot_of(Cc, c, cflags, sx, sy, rot);
+    Cc.cabs[c] = a;
+    if (bp.nl.snap_next != nullptr) {
+        const float4 me = __ldg(bp.nl.snap_cur + c);
+        const uint4 hd = bp.nl.hdr[c];
+        bp.nl.snap_next[c] = make_float4(a.x, a.y, me.z, me.w);
+        nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), bp.nl.ctl->cx, bp.nl.ctl->cy, na);
+    } else {
+        const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
+        Cc.ccell[c] = make_uint2(cell, bin_collider(bp.tab_next, bp.tile_next, cell));
+    }
+    return a;
+}
+// list pipeline: kernels that walk the cell grid (k_multi, k_crowded) use the tables of the last rebuild
+__device__ __forceinline__ Broadphase resolve_grid(Broadphase bp) {
+    if (bp.nl.snap_next != nullptr) {
+        bp.tab = bp.nl.tab[bp.nl.ctl->parity & 1u];
+        bp.hot = bp.nl.hot;
+        bp.snap = bp.nl.snap_cur;
+    }
+    return bp;
 }
 
 // ---- strip decomposition: message packing (see the strip section at the end of this file) --------------------------
@@ -812,7 +879,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
                 active_col = (cc.y & CF_ACTIVE) != 0u;
                 if (active_col && P.collisions_enabled) {
                     SelfCol s;
-                    s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
+                    s.x = s.qx = ab.x; s.y = s.qy = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
                     s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
                     ContactList<uint32_t> list;
                     list.clear();
@@ -842,7 +909,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
                 float sx, sy, rot;
                 integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
                 if (active_col) {
-                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+                    NlAcc na_unused{0.f, 0.f, 0.f, 0u};
+                    const float2 a = publish_collider(g, Cc, bp, (uint32_t)col, cc.y, wbase, sx, sy, rot, na_unused);
                     if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
                 }
             } else {
@@ -853,7 +921,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
         const bool do_body = inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER;
         bool active_col = false, deferred = false, do_gather = false;
         SelfCol s;
-        s.x = s.y = s.r = s.m = 0.f;
+        s.x = s.y = s.r = s.m = s.qx = s.qy = 0.f;
         s.memb = s.filt = 0u; s.body = b; s.slot = 0u; s.wbase = wbase; s.sensor = false;
         if (do_body && col >= 0) {
             const uint32_t c = (uint32_t)col;
@@ -863,7 +931,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
             }
             active_col = (cc.y & CF_ACTIVE) != 0u;
             if (active_col && P.collisions_enabled) {
-                s.x = ab.x; s.y = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
+                s.x = s.qx = ab.x; s.y = s.qy = ab.y; s.r = __uint_as_float(cc.x); s.m = mg.x;
                 s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
                 do_gather = true;
             }
@@ -910,7 +978,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
                 float sx, sy, rot;
                 integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
                 if (active_col) {
-                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, (uint32_t)col, cc.y, wbase, sx, sy, rot);
+                    NlAcc na_unused{0.f, 0.f, 0.f, 0u};
+                    const float2 a = publish_collider(g, Cc, bp, (uint32_t)col, cc.y, wbase, sx, sy, rot, na_unused);
                     if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, (uint32_t)col, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
                 }
             } else {
@@ -927,32 +996,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-tile (BLOBS_PARAM_TUNE 11; 12 = the same with 128-record tiles / 128-thread CTAs, 8 per SM; 13 = windows fetched by TMA bulk copies): the work of k_main<FUSED, ORDERED>, mapped the other way round — one thread per RECORD of
-// the cell-sorted array instead of one per body slot, 256 consecutive records per CTA. The records a CTA's bodies can
-// touch then form three contiguous windows of the same array (the linear cell range [cA-1, cB+1] of the tile's own cells,
-// and that range shifted one table row up and down), which the CTA stages in shared memory with coalesced 16-byte loads:
-// the candidate scan and the narrowphase read shared memory, where k_main issues 9-12 dependent L2 loads per thread.
-// Dependent memory rounds per CTA: own record -> window bounds (6 table entries) -> windows; the per-body state (gathered
-// by slot; slot order ~ cell order in every lattice scene, so the gather stays sector-coherent) and the six table entries of
-// the thread's own range travel under those. x, y, r and the flag bits of the own collider come from the record itself, so
-// cabs[] / cconst[] are not read for default spheres.
-// Anything that does not fit the picture takes the global-memory path of k_main for that thread only: a range that wraps
-// the torus or is not covered by a staged window (window larger than TILE_WCAP records, table edge). Same arithmetic, same
-// summation order as k_main => bit-identical results. Colliders of multi-collider bodies are skipped here and done by k_multi
-// as before; bodies without any collider have no record, the host adds a k_integrate(BF_LOOSE) pass for them.
+// TMA bulk-copy helpers (cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS). Round 2 measured a tile kernel that staged its
+// candidate windows this way (profiles/r2_ktile_tma_verdict.md): bit-exact, but no faster than plain loads for this gather-bound
+// access pattern, so that kernel was removed; the helpers stay for contiguous per-CTA state tiles.
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE_THREADS = 256;
-// records per staged window (own 256 + two halo cells, with slack); the pooled variant also holds the per-warp queues and
-// must stay under the 48 KB of static shared memory
-template <bool POOLED, int THREADS> struct TileCfg { static constexpr int WCAP = THREADS >= 256 ? (POOLED ? 320 : 384) : (POOLED ? 224 : 256); };
-#ifdef BLOBS_EMU
-inline unsigned long long tile_path_count[3] = {0, 0, 0};   // [0] shared-memory windows, [1] global-memory fallback, [2] pooled variant: per-lane staged scan
-#endif
-
-// BLOBS_PARAM_TUNE 13: the three windows are fetched by the TMA engine instead of by the CTA's threads - one elected thread
-// arms an mbarrier with the byte count and issues up to three 1-D bulk copies (cp.async.bulk global -> shared, SASS UBLKCP),
-// everybody waits on the barrier's phase. Frees the load/store slots of 256 threads and their registers for the body-state
-// gather that is in flight at the same time. (The host-compiled test build keeps the plain loop.)
 #ifndef BLOBS_EMU
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -982,265 +1029,23 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 }
 #endif
 
-template <bool POOLED, int THREADS = TILE_THREADS, bool BULK = false>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_tile(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                          Broadphase bp, Recording rec, DeviceStats* stats, StripView sv, uint32_t n_entries,
-                                                          uint32_t hot_len) {
-    constexpr uint32_t WCAP = (uint32_t)TileCfg<POOLED, THREADS>::WCAP;
-    __shared__ float4 win[3 * WCAP];
-    __shared__ PoolSmem pool[POOLED ? THREADS / 32 : 1];
-    __shared__ uint32_t wlo[3], whi[3];
-    __shared__ uint32_t cab[2];
-    __shared__ __align__(8) unsigned long long bulk_bar;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t i0 = blockIdx.x * (uint32_t)THREADS;
-#ifndef BLOBS_EMU
-    if (BULK && tid == 0u) mbar_init(&bulk_bar, 1u);   // visible to the CTA after the first __syncthreads below
-#endif
-    // round 1: the own record, together with the total number of records (last table entry); the address is clamped to the
-    // ALLOCATED length so that it does not wait for the count
-    const float4 h0 = __ldg(bp.hot + min(i0 + tid, hot_len - 1u));
-    const uint32_t nrec = __ldg(bp.tab + n_entries);
-    if (i0 >= nrec) return;                               // CTA-uniform
-    const bool valid = i0 + tid < nrec;
-    const float4 h = valid ? h0 : __ldg(bp.hot + i0);     // tail threads of the last tile mirror its first record and discard
-    const uint32_t hw = __float_as_uint(h.w);
-    const uint32_t c = hw & HOT_SLOT_MASK;
-    const bool cold = (hw & HOT_COLD_BIT) != 0u;
-    const uint32_t lastv = min((uint32_t)THREADS - 1u, nrec - 1u - i0);
-    uint32_t mycell = cell_index(g, bin_coord(h.x, g.inv_cell), bin_coord(h.y, g.inv_cell));   // what publish_collider / k_count binned it to
-    const CellRange R = cell_range(g, h.x, h.y, h.z);
-    const bool plain = !(R.ny > 3u || R.c0 + R.nx > g.W);
-    // round 2: body state at the SPECULATED body slot b == c (lock-step insertion), cold half for non-default records,
-    // and (single world: the table index does not depend on the body) the six table entries of the own range
-    uint32_t b = min(c, P.n_bodies - 1u);
-    uint2 info = B.binfo[b];
-    float2 mg = B.bmg[b];
-    float2 p = B.pos[b];
-    float2 po = B.pos_old[b];
-    float2 acc0 = B.acc[b];
-    bool hv = B.has_vreq[b] != 0;
-    uint4 ce = make_uint4(0u, 0xffffffffu, 0xffffffffu, 0u);
-    uint32_t cf = CF_ACTIVE;                              // default record: active, no offset, not a sensor
-    if (cold) {
-        ce = __ldg(Cc.ccold + c);
-        cf = Cc.cconst[c].y;
-    }
-    uint32_t tlo[3], tcnt[3];
-    uint32_t wbase = 0u;
-    if (g.n_worlds == 1u) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            uint32_t row = R.r0 + j;
-            if (row >= g.H) row -= g.H;
-            const bool rv = plain && (uint32_t)j < R.ny;
-            const uint32_t idx = rv ? row * g.W + R.c0 : 0u;
-            const uint32_t a = __ldg(bp.tab + idx), e = __ldg(bp.tab + idx + (rv ? R.nx : 0u));
-            tlo[j] = a;
-            tcnt[j] = e - a;
-        }
-    }
-    bool mine = valid;
-    if (sv.olist != nullptr) mine = mine && sv.cowned[c] != 0;   // strip mode: ghost records belong to the neighbour rank
-    if (mine && (b != c || info.y != c)) {                // speculation missed: fetch the real parent
-        b = Cc.cparent[c];
-        info = B.binfo[b];
-        mg = B.bmg[b];
-        p = B.pos[b];
-        po = B.pos_old[b];
-        acc0 = B.acc[b];
-        hv = B.has_vreq[b] != 0;
-        if (info.y != c) mine = false;                    // collider of a multi-collider body: k_multi does that body
-    }
-    if (g.n_worlds > 1u) {
-        wbase = B.bworld[b] * g.ncells;
-        mycell += wbase;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            uint32_t row = R.r0 + j;
-            if (row >= g.H) row -= g.H;
-            const bool rv = plain && (uint32_t)j < R.ny;
-            const uint32_t idx = wbase + (rv ? row * g.W + R.c0 : 0u);
-            const uint32_t a = __ldg(bp.tab + idx), e = __ldg(bp.tab + idx + (rv ? R.nx : 0u));
-            tlo[j] = a;
-            tcnt[j] = e - a;
-        }
-    }
-    // the tile's own linear cell range [cA, cB] (records are sorted by cell)
-    if (tid == 0u) cab[0] = mycell;
-    if (tid == lastv) cab[1] = mycell;
-    __syncthreads();
-    if (tid < 3u) {   // window k: cells [cA - 1, cB + 1] shifted by (k - 1) table rows, as a record range
-        const long long shift = ((long long)tid - 1) * (long long)g.W;
-        long long lo = (long long)cab[0] + shift - 1, hi = (long long)cab[1] + shift + 2;
-        lo = lo < 0 ? 0 : (lo > (long long)n_entries ? (long long)n_entries : lo);
-        hi = hi < 0 ? 0 : (hi > (long long)n_entries ? (long long)n_entries : hi);
-        uint32_t a = 0u, e = 0u;
-        if (hi > lo) {
-            a = __ldg(bp.tab + (uint32_t)lo);
-            e = __ldg(bp.tab + (uint32_t)hi);
-            if (e - a > WCAP) e = a;                      // too crowded to stage: its users take the global path
-        }
-        wlo[tid] = a;
-        whi[tid] = e;
-    }
-    __syncthreads();
-    // round 3: stage the windows
-#ifndef BLOBS_EMU
-    if (BULK) {
-        const uint32_t bytes = ((whi[0] - wlo[0]) + (whi[1] - wlo[1]) + (whi[2] - wlo[2])) * 16u;
-        if (bytes) {   // CTA-uniform
-            if (tid == 0u) {
-                mbar_expect_tx(&bulk_bar, bytes);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const uint32_t a = wlo[k], n = whi[k] - a;
-                    if (n) bulk_load(&win[k * WCAP], bp.hot + a, n * 16u, &bulk_bar);
-                }
-            }
-            uint32_t spins = 0;
-            while (!mbar_try_wait(&bulk_bar, 0u)) {
-                if (++spins > (1u << 16)) { atomicOr(&stats->nan_flag, 16u); break; }   // never hang the GPU on a lost copy (each try_wait suspends for a while)
-            }
-        }
-    } else
-#endif
-    {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {   // coalesced 16-byte loads by the whole CTA
-            const uint32_t a = wlo[k], n = whi[k] - a;
-            for (uint32_t j = tid; j < n; j += (uint32_t)THREADS) win[k * WCAP + j] = __ldg(bp.hot + a + j);
-        }
-        __syncthreads();
-    }
-
-    GatherOut out;
-    out.fx = out.fy = 0.f;
-    out.n_pairs = out.n_coinc = 0;
-    unsigned int n_over = 0;
-    const uint32_t flags = info.x;
-    const bool do_gather = mine && P.collisions_enabled != 0u;
-    bool deferred = false;
-    SelfCol s;
-    s.x = h.x; s.y = h.y; s.r = h.z; s.m = mg.x;
-    s.memb = ce.y; s.filt = ce.z; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (hw & HOT_SENSOR_BIT) != 0u;
-    // where the three row spans of this thread sit in shared memory
-    LaneSpan L;
-    bool staged = do_gather && plain;
-    {
-        uint32_t so[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            so[j] = 0u;
-            if (staged && tcnt[j]) {
-                const uint32_t a = tlo[j], e = a + tcnt[j];
-                if (a >= wlo[1] && e <= whi[1]) so[j] = WCAP + (a - wlo[1]);
-                else if (a >= wlo[0] && e <= whi[0]) so[j] = a - wlo[0];
-                else if (a >= wlo[2] && e <= whi[2]) so[j] = 2u * WCAP + (a - wlo[2]);
-                else staged = false;
-            }
-        }
-        L.n0 = tcnt[0]; L.n01 = tcnt[0] + tcnt[1]; L.total = L.n01 + tcnt[2];
-        L.off0 = so[0]; L.off1 = so[1] - L.n0; L.off2 = so[2] - L.n01;
-        L.lo0 = WCAP;                                     // a staged record (the middle window holds the tile's own)
-        L.ranged = do_gather && plain;
-        L.fits = staged && L.total <= 64u;
-    }
-#ifdef BLOBS_EMU   // host-compiled test build only: lets a test assert which path its bodies took
-    if (do_gather) tile_path_count[staged ? 0 : 1]++;
-#endif
-    ContactList<uint32_t> list;
-    list.clear();
-    bool applied = false, big = false;
-    const StagedHot src{win};
-    // per-lane scan of a staged span: prefilter, then the exact narrowphase into the ordered list (gather_single on shared memory)
-    auto scan_staged = [&]() {
-        const uint32_t n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
-        const float srk = s.r * 1.00005f;              // prefilter: see gather_single
-        for (uint32_t base = 0; base < total; base += 32u) {
-            const uint32_t lim = min(32u, total - base);
-            uint32_t mask = 0;
-            for (uint32_t q = 0; q < lim; ++q) {
-                const uint32_t t = base + q;
-                const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
-                const uint32_t oslot = __float_as_uint(o.w) & HOT_SLOT_MASK;
-                const float dx = s.x - o.x, dy = s.y - o.y;
-                const float d2 = __fmaf_rn(dx, dx, dy * dy);
-                const float mdk = __fmaf_rn(o.z, 1.00005f, srk);
-                if (oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << q;
-            }
-            while (mask) {
-                const uint32_t t = base + (uint32_t)__ffs(mask) - 1u;
-                mask &= mask - 1u;
-                const float4 o = win[t + (t < n0 ? off0 : (t < n01 ? off1 : off2))];
-                take_candidate<true, uint32_t>(s, rec_of(o, Cc.ccold), list, out, rec, B.vel, stats);
-            }
-        }
-    };
-    if (POOLED) {   // warp-collective: every lane calls. Lanes whose range is not staged take gather_single inside (global memory).
-        // Lanes with 65 .. POOL_BIG_MIN staged candidates keep the per-lane path, as in k_main (config #3's compressed piles), but
-        // scan shared memory: they sit the pooled resolution out and are done right after it.
-        const bool lane_scan = staged && L.total > 64u && L.total <= POOL_BIG_MIN;
-        applied = gather_warp_core<4>(g, bp, src, Cc.ccold, do_gather && !lane_scan, s, L, list, out, rec, B.vel, stats, pool[tid >> 5], P.pool_min,
-                                      P.crowded != 0u, big, p.x, p.y);
-#ifdef BLOBS_EMU
-        if (lane_scan) tile_path_count[2]++;
-#endif
-        if (lane_scan) scan_staged();
-    } else if (do_gather) {
-        if (staged) scan_staged();
-        else gather_single<true, uint32_t, 4>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
-    }
-    if (big) {   // k_crowded does the whole body, pair counting included
-        n_over = 1;
-        P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
-        deferred = true;
-    } else if (do_gather && !applied) {
-        if (!list.overflow) {
-            for (int q = 0; q < list.n; ++q) { p.x = fadd(p.x, list.cx[q]); p.y = fadd(p.y, list.cy[q]); }
-        } else {
-            n_over = 1;
-            if (P.crowded) {  // a whole warp of k_crowded redoes this body, including the fused tail below
-                P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = b;
-                deferred = true;
-            } else {
-                SelfCol s2 = s;
-                p = apply_contacts_rescan(g, bp, Cc.ccold, &s2, 1, p.x, p.y);
-            }
-        }
-    }
-    if (mine) {
-        if (deferred) {
-            // nothing: every array of this body is left untouched for k_crowded
-        } else if (!(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_integrate after the joint projection
-            float sx, sy, rot;
-            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
-            const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, wbase, sx, sy, rot);
-            if (sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, c, cf, a, h.z, sv.send_l, sv.send_r);
-        } else {
-            B.pos[b] = p;
-        }
-    }
-    warp_add_u64(&stats->collisions, out.n_pairs);
-    if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
-        warp_add_u64(&stats->coincident, out.n_coinc);
-        unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
-        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K-multi: bodies with more than one distinct collider. One thread per such body; the contributions of all its
 // colliders are merged into one ordered list (order = (later slot, earlier slot) over the union).
 // ------------------------------------------------------------------------------------------------
 constexpr int MULTI_MAX_INLINE = 8;  // colliders staged for the rescan path
 
-__device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, uint32_t b, uint32_t c, float m, uint32_t wbase,
-                                          SelfCol& s) {
+__device__ __forceinline__ bool load_self(const BodyArrays& B, const ColliderArrays& Cc, const Broadphase& bp, uint32_t b, uint32_t c, float m,
+                                          uint32_t wbase, SelfCol& s) {
     const uint4 cc = Cc.cconst[c];
     if (!(cc.y & CF_ACTIVE)) return false;
     const float2 a = Cc.cabs[c];
-    s.x = a.x; s.y = a.y; s.r = __uint_as_float(cc.x); s.m = m;
+    s.x = s.qx = a.x; s.y = s.qy = a.y; s.r = __uint_as_float(cc.x); s.m = m;
+    if (bp.snap != nullptr) {   // list pipeline: the grid was built around the reference position
+        const uint4 hd = bp.nl.hdr[c];
+        s.qx = __uint_as_float(hd.x);
+        s.qy = __uint_as_float(hd.y);
+    }
     s.memb = cc.z; s.filt = cc.w; s.body = b; s.slot = c; s.wbase = wbase; s.sensor = (cc.y & CF_SENSOR) != 0u;
     return true;
 }
@@ -1256,7 +1061,7 @@ __device__ __forceinline__ float2 multi_overflow_serial(const GridDesc& g, const
     bool fits = true;
     for (uint32_t k = c0; k < c1; ++k) {
         SelfCol s;
-        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
+        if (!load_self(B, Cc, bp, b, mb_cols[k], m, wbase, s)) continue;
         if (nc == MULTI_MAX_INLINE) { fits = false; break; }
         cols[nc++] = s;
     }
@@ -1264,8 +1069,8 @@ __device__ __forceinline__ float2 multi_overflow_serial(const GridDesc& g, const
     float fx = 0.f, fy = 0.f;
     for (uint32_t k = c0; k < c1; ++k) {
         SelfCol s;
-        if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
-        for_each_candidate(g, bp, Cc.ccold, s.wbase, s.x, s.y, s.r, [&](const Rec& o) {
+        if (!load_self(B, Cc, bp, b, mb_cols[k], m, wbase, s)) continue;
+        for_each_candidate(g, bp, Cc.ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
             Contact c;
             if (!narrowphase(s, o, c)) return;
             if (c.coincident) fx = fadd(fx, c.i_am_a ? 0.01f : -0.01f);
@@ -1277,9 +1082,11 @@ __device__ __forceinline__ float2 multi_overflow_serial(const GridDesc& g, const
 
 template <bool FUSED, bool ORDERED>
 __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                               Broadphase bp, Recording rec, DeviceStats* stats, const uint32_t* __restrict__ mb_body,
+                                               Broadphase bp_in, Recording rec, DeviceStats* stats, const uint32_t* __restrict__ mb_body,
                                                const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols,
                                                uint32_t n_multi) {
+    const Broadphase bp = resolve_grid(bp_in);
+    NlAcc na{0.f, 0.f, 0.f, 0u};
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;
@@ -1302,7 +1109,7 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             const float m = mg.x;
             for (uint32_t k = c0; k < c1; ++k) {
                 SelfCol s;
-                if (!load_self(B, Cc, b, mb_cols[k], m, wbase, s)) continue;
+                if (!load_self(B, Cc, bp, b, mb_cols[k], m, wbase, s)) continue;
                 gather_generic<ORDERED, unsigned long long>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
             if (ORDERED) {
@@ -1330,12 +1137,13 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
             for (uint32_t k = c0; k < c1; ++k) {
                 const uint32_t c = mb_cols[k];
                 const uint32_t cf = Cc.cconst[c].y;
-                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cf, wbase, sx, sy, rot);
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, c, cf, wbase, sx, sy, rot, na);
             }
         } else {
             B.pos[b] = p;
         }
     }
+    if (bp.nl.snap_next != nullptr) nl_commit(bp.nl.ctl, na, &stats->collisions, 0u);
     warp_add_u64(&stats->collisions, out.n_pairs);
     if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
         warp_add_u64(&stats->coincident, out.n_coinc);
@@ -1379,9 +1187,11 @@ __device__ __forceinline__ void warp_for_each_candidate(const GridDesc& g, const
 
 template <bool FUSED>
 __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                              Broadphase bp, Recording rec, DeviceStats* stats, StripView sv,
+                                                              Broadphase bp_in, Recording rec, DeviceStats* stats, StripView sv,
                                                               const uint32_t* __restrict__ mb_body, const uint32_t* __restrict__ mb_off,
                                                               const uint32_t* __restrict__ mb_cols) {
+    const Broadphase bp = resolve_grid(bp_in);
+    NlAcc na{0.f, 0.f, 0.f, 0u};
     GatherOut out;
     out.fx = out.fy = 0.f;
     out.n_pairs = out.n_coinc = 0;
@@ -1412,8 +1222,8 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
         __syncwarp();
         for (uint32_t k = c0; k < c1; ++k) {
             SelfCol s;
-            if (!load_self(B, Cc, b, multi ? mb_cols[k] : info.y, mg.x, wbase, s)) continue;
-            warp_for_each_candidate(g, bp, Cc.ccold, s.wbase, s.x, s.y, s.r, lane, [&](const Rec& o) {
+            if (!load_self(B, Cc, bp, b, multi ? mb_cols[k] : info.y, mg.x, wbase, s)) continue;
+            warp_for_each_candidate(g, bp, Cc.ccold, s.wbase, s.qx, s.qy, s.r, lane, [&](const Rec& o) {
                 Contact c;
                 if (!narrowphase(s, o, c)) return;
                 if (count) note_pair(s, o, c, out, rec, B.vel, stats);
@@ -1458,7 +1268,7 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
                 p = multi_overflow_serial(g, bp, B, Cc, b, mb_cols, c0, c1, mg.x, wbase, p);
             } else {
                 SelfCol s;
-                if (load_self(B, Cc, b, info.y, mg.x, wbase, s)) p = apply_contacts_rescan(g, bp, Cc.ccold, &s, 1, p.x, p.y);
+                if (load_self(B, Cc, bp, b, info.y, mg.x, wbase, s)) p = apply_contacts_rescan(g, bp, Cc.ccold, &s, 1, p.x, p.y);
             }
         }
         if (lane == 0) {
@@ -1472,7 +1282,7 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
                     const uint32_t c = multi ? mb_cols[k] : info.y;
                     const uint4 cc = Cc.cconst[c];
                     if (!(cc.y & CF_ACTIVE)) continue;
-                    const float2 a = publish_collider(g, Cc, bp.tab_next, bp.tile_next, c, cc.y, wbase, sx, sy, rot);
+                    const float2 a = publish_collider(g, Cc, bp, c, cc.y, wbase, sx, sy, rot, na);
                     if (!multi && sv.olist != nullptr) strip_pack_one(B, Cc, sv.S, c, cc.y, a, __uint_as_float(cc.x), sv.send_l, sv.send_r);
                 }
             } else {
@@ -1481,6 +1291,7 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
         }
         __syncwarp();
     }
+    if (bp.nl.snap_next != nullptr) nl_commit(bp.nl.ctl, na, &stats->collisions, 0u);
     warp_add_u64(&stats->collisions, out.n_pairs);
     if (__any_sync(0xffffffffu, out.n_coinc)) warp_add_u64(&stats->coincident, out.n_coinc);
 }
@@ -1489,31 +1300,34 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
 // K-integrate (split pipeline, used when joints or event recording forbid fusion): update_objects + snapshot +
 // constraints + binning for every body.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                   uint32_t* tab_next, uint32_t* tile_next, DeviceStats* stats,
-                                                   const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols, uint32_t only_flag) {
+__global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
+                                                   DeviceStats* stats, const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols,
+                                                   uint32_t only_flag) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.n_bodies) return;
-    const uint2 info = B.binfo[b];
+    NlAcc na{0.f, 0.f, 0.f, 0u};
+    uint2 info = make_uint2(0u, 0u);
+    if (b < P.n_bodies) info = B.binfo[b];
     const uint32_t flags = info.x;
-    if (!(flags & BF_ALIVE)) return;
-    if (only_flag && !(flags & only_flag)) return;   // fused pipeline: free bodies were already advanced by k_main
-    const int32_t col = (int32_t)info.y;
-    const float2 p = B.pos[b];
-    const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
-    float sx, sy, rot;
-    integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
-    if (col >= 0) {
-        const uint32_t cf = Cc.cconst[col].y;
-        if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, wbase, sx, sy, rot);
-    } else if (col <= -2) {
-        const uint32_t i = (uint32_t)(-(col + 2));
-        for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
-            const uint32_t c = mb_cols[k];
-            const uint32_t cf = Cc.cconst[c].y;
-            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, wbase, sx, sy, rot);
+    // fused pipeline (only_flag set): free bodies were already advanced by the contact kernel
+    if (b < P.n_bodies && (flags & BF_ALIVE) && (!only_flag || (flags & only_flag))) {
+        const int32_t col = (int32_t)info.y;
+        const float2 p = B.pos[b];
+        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
+        float sx, sy, rot;
+        integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
+        if (col >= 0) {
+            const uint32_t cf = Cc.cconst[col].y;
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, (uint32_t)col, cf, wbase, sx, sy, rot, na);
+        } else if (col <= -2) {
+            const uint32_t i = (uint32_t)(-(col + 2));
+            for (uint32_t k = mb_off[i]; k < mb_off[i + 1]; ++k) {
+                const uint32_t c = mb_cols[k];
+                const uint32_t cf = Cc.cconst[c].y;
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, c, cf, wbase, sx, sy, rot, na);
+            }
         }
     }
+    if (bp.nl.snap_next != nullptr) nl_commit(bp.nl.ctl, na, &stats->collisions, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1537,9 +1351,8 @@ __global__ void __launch_bounds__(256) k_count(GridDesc g, ColliderArrays Cc, co
 // block derives its own starting offset by summing the totals of the tiles before it — no inter-block dependency, no
 // look-back spinning. Also zeroes `zero_me` and `tile_zero` (the table / tile totals that become "next" after the swap).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ zero_me,
-                                                       uint32_t n_zero, const uint32_t* __restrict__ tile_cur,
-                                                       uint32_t* __restrict__ tile_zero) {
+__device__ __forceinline__ void scan_tile(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ zero_me, uint32_t n_zero,
+                                          const uint32_t* __restrict__ tile_cur, uint32_t* __restrict__ tile_zero) {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
     __shared__ uint32_t warp_pre[SCAN_THREADS / 32];
     const uint32_t tile = blockIdx.x;
@@ -1603,6 +1416,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
         for (int i = 0; i < SCAN_ITEMS; ++i)
             if (base + i < n) data[base + i] = o[i];
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ zero_me,
+                                                       uint32_t n_zero, const uint32_t* __restrict__ tile_cur,
+                                                       uint32_t* __restrict__ tile_zero) {
+    scan_tile(data, n, zero_me, n_zero, tile_cur, tile_zero);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1736,8 +1555,7 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-joints-fused: the fast path of solve_fixed_joints (physics.rs:424-477) for islands of up to JOINT_SMEM_MAX bodies,
-// fused with update_objects + snapshot + constraints + binning for the island's bodies (physics.rs:323-395).
+// K-joints-fused: the fast path of solve_fixed_joints (physics.rs:424-477) for islands of up to JOINT_SMEM_MAX bodies.
 // One thread per island, exactly the reference's operation order inside the island; the island's bodies live in shared
 // memory laid out [local body][thread] (conflict-free), so the 4 x J sequential solves never touch global memory:
 // every body is read once and written once. Joints carry LOCAL body indices.
@@ -1745,12 +1563,9 @@ __global__ void __launch_bounds__(128) k_joints(SubstepParams P, BodyArrays B, c
 constexpr int JOINT_SMEM_MAX = 96;
 constexpr int JOINT_THREADS = 64;
 
-template <bool INTEGRATE>
-__global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
-                                                                uint32_t* tab_next, uint32_t* tile_next, const uint32_t* __restrict__ isl_off,
+__global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P, BodyArrays B, const uint32_t* __restrict__ isl_off,
                                                                 const float4* __restrict__ jli, uint32_t max_j, const uint32_t* __restrict__ isl_boff,
-                                                                const uint32_t* __restrict__ isl_body, const uint32_t* __restrict__ mb_off,
-                                                                const uint32_t* __restrict__ mb_cols, uint32_t n_islands, uint32_t iterations,
+                                                                const uint32_t* __restrict__ isl_body, uint32_t n_islands, uint32_t iterations,
                                                                 DeviceStats* stats) {
 #ifdef BLOBS_EMU   // host-compiled test build (tests/emu): dynamic shared memory comes from the fiber engine
     float4* const sm = static_cast<float4*>(::emu::dynamic_smem());
@@ -1814,26 +1629,7 @@ __global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P,
         const uint32_t slot = isl_body[b0 + k];
         const float4 v = sm[k * T + t];
         B.rot[slot] = v.z;
-        if (!INTEGRATE) {
-            B.pos[slot] = make_float2(v.x, v.y);
-            continue;
-        }
-        const uint2 info = B.binfo[slot];
-        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[slot] * g.ncells : 0u;
-        float sx, sy, rot;
-        integrate_body(P, K, B, slot, info.x, B.bmg[slot].y, v.x, v.y, B.pos_old[slot], B.acc[slot], B.has_vreq[slot] != 0, sx, sy, rot, stats);
-        const int32_t col = (int32_t)info.y;
-        if (col >= 0) {
-            const uint32_t cf = Cc.cconst[col].y;
-            if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, (uint32_t)col, cf, wbase, sx, sy, rot);
-        } else if (col <= -2) {
-            const uint32_t mi = (uint32_t)(-(col + 2));
-            for (uint32_t q = mb_off[mi]; q < mb_off[mi + 1]; ++q) {
-                const uint32_t c = mb_cols[q];
-                const uint32_t cf = Cc.cconst[c].y;
-                if (cf & CF_ACTIVE) publish_collider(g, Cc, tab_next, tile_next, c, cf, wbase, sx, sy, rot);
-            }
-        }
+        B.pos[slot] = make_float2(v.x, v.y);
     }
 }
 
@@ -2183,5 +1979,7 @@ __global__ void __launch_bounds__(256) k_apply_forces_indexed(BodyArrays B, cons
     a.y = fadd(a.y, fdiv(F.y, m));
     B.acc[b] = a;
 }
+
+#include "nlist.cuh"
 
 }  // namespace blobs

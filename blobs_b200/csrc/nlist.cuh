@@ -1,0 +1,313 @@
+// Neighbour-list pipeline (included at the end of kernels.cuh, inside namespace blobs).
+//
+// brute_force_collisions (physics.rs:241-317) tests every pair every substep; the grid pipeline (k_main + k_scan + k_scatter)
+// re-sorts every collider into cells every substep to find the same pairs. But between two substeps a sphere moves by a small
+// fraction of its radius, so WHO can touch whom changes slowly. Here every collider keeps a list of all colliders within
+// r_a + r_b + skin of it, sorted by slot, and the per-substep kernel (k_step) only walks that list:
+//   * the exact narrowphase (narrowphase(), the reference's arithmetic) runs on the CURRENT snapshots of the listed colliders,
+//     so the contact set of every substep is exactly the reference's — the list only has to be a superset of it;
+//   * the list is sorted by partner slot, which is the reference's pair-loop order for a single-collider body, so
+//     contributions are simply added as they are found: no ordered insert, no contact list in local memory;
+//   * every publisher tracks how far snapshots have moved since the lists were built (nl_track); k_nl_decide turns that into a
+//     device-side "rebuild" flag, and the four rebuild kernels below (cell counting sort of the current snapshots + list
+//     construction) return at once when it is not set. No host round trip, so whole steps stay CUDA-graph replayable.
+// Bodies with more than NL_CAP neighbours (the shell the circle constraint builds, physics.rs:377-395) are handed to k_crowded,
+// which walks the cell grid of the last rebuild instead of a list.
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_nl_decide: one thread, first launch of every substep. Decides whether the lists are rebuilt before this substep's contact
+// pass, predicts the common displacement c the publishers will subtract, and resets the accumulators.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step) {
+    if (threadIdx.x != 0u || blockIdx.x != 0u) return;
+    const float m = __uint_as_float(ctl->max_m);
+    const unsigned int need = (ctl->force != 0u || !(m <= lim)) ? 1u : 0u;
+    const unsigned int n = ctl->n_sum;
+    float mx = ctl->mean_x, my = ctl->mean_y;   // no sample this substep: assume nothing moved
+    if (n) { mx = ctl->sum_x / (float)n; my = ctl->sum_y / (float)n; }
+    if (!(fabsf(mx) < 1e30f)) mx = 0.f;
+    if (!(fabsf(my) < 1e30f)) my = 0.f;
+    // displacement per substep (the references were reset by the last rebuild, hence mean_* == 0 right after one)
+    const float ux = mx - ctl->mean_x, uy = my - ctl->mean_y;
+    if (need) {   // references move to the current snapshots: the next publishers see one substep's worth of motion
+        ctl->cx = ux; ctl->cy = uy;
+        ctl->mean_x = 0.f; ctl->mean_y = 0.f;
+        ctl->rebuilds += in_step;
+    } else {      // linear extrapolation: under gravity alone the error is g * dt^2
+        ctl->cx = mx + ux; ctl->cy = my + uy;
+        ctl->mean_x = mx; ctl->mean_y = my;
+    }
+    ctl->need = need;
+    ctl->force = 0u;
+    ctl->max_m = 0u;
+    ctl->sum_x = 0.f; ctl->sum_y = 0.f;
+    ctl->n_sum = 0u;
+    ctl->substeps += in_step;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rebuild, step 1-3: counting sort of the current snapshots into cells (the grid pipeline's k_count / k_scan / k_scatter, gated
+// by the device flag and addressing the table pair by the device parity).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nl_count(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L, uint32_t n_colliders,
+                                                  const uint8_t* __restrict__ cowned) {
+    if (L.ctl->need == 0u) return;
+    const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_colliders) return;
+    if (cowned != nullptr && !cowned[c]) return;
+    if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
+    const float2 a = Cc.cabs[c];
+    const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
+    const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
+    Cc.ccell[c] = make_uint2(cell, bin_collider(L.tab[nx], L.tile[nx], cell));
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_nl_scan(NlView L, uint32_t n) {
+    if (L.ctl->need == 0u) return;
+    const uint32_t cur = L.ctl->parity & 1u, nx = cur ^ 1u;
+    // the table of the previous rebuild is zeroed on the way: it takes the counts of the NEXT rebuild
+    scan_tile(L.tab[nx], n, L.tab[cur], n, L.tile[nx], L.tile[cur]);
+}
+
+__global__ void __launch_bounds__(256) k_nl_scatter(ColliderArrays Cc, NlView L, uint32_t n_colliders, const uint8_t* __restrict__ cowned) {
+    if (L.ctl->need == 0u) return;
+    const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_colliders) return;
+    if (cowned != nullptr && !cowned[c]) return;
+    const uint4 cc = Cc.cconst[c];
+    const uint2 cr = Cc.ccell[c];
+    const float2 a = Cc.cabs[c];
+    if (!(cc.y & CF_ACTIVE)) return;
+    const uint32_t dst = __ldg(L.tab[nx] + cr.x) + cr.y;
+    L.hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(hot_word(c, cc.y)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rebuild, step 4: one thread per collider slot walks the cells within r + r_max + skin of its snapshot (g.rmax is inflated by
+// the skin on the host) and keeps every collider closer than r_a + r_b + skin, sorted by slot (rank by counting: slots are
+// unique), in the transposed list array. Also (re)writes the slot-indexed snapshot record the next contact pass reads, and the
+// reference position the displacement tracking measures from. The last CTA to finish flips the table parity.
+// The keep test is deliberately loose (1e-4 relative): it only has to err on the side of keeping.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NL_BUILD_THREADS = 128;
+
+__global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L,
+                                                               float4* __restrict__ snap_cur, uint32_t n_colliders,
+                                                               const uint8_t* __restrict__ cowned) {
+    __shared__ uint32_t keep[NL_CAP * NL_BUILD_THREADS];
+    NlCtl* const ctl = L.ctl;
+    if (ctl->need == 0u) return;   // grid-uniform
+    const uint32_t nx = (ctl->parity & 1u) ^ 1u;
+    const uint32_t* __restrict__ tab = L.tab[nx];
+    const float4* __restrict__ hot = L.hot;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t c = blockIdx.x * (uint32_t)NL_BUILD_THREADS + tid;
+    if (c < n_colliders) {
+        const uint4 cc = Cc.cconst[c];
+        uint4 hd = make_uint4(0u, 0u, NL_INACTIVE, cc.y);
+        if ((cc.y & CF_ACTIVE) && (cowned == nullptr || cowned[c])) {
+            const float2 a = Cc.cabs[c];
+            const float r = __uint_as_float(cc.x);
+            snap_cur[c] = make_float4(a.x, a.y, r, __uint_as_float(hot_word(c, cc.y)));
+            const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
+            const float rs = r + L.skin;
+            uint32_t n = 0;
+            auto offer = [&](const float4 h) {
+                const uint32_t oslot = __float_as_uint(h.w) & HOT_SLOT_MASK;
+                const float dx = a.x - h.x, dy = a.y - h.y;
+                const float d2 = dx * dx + dy * dy;
+                const float cut = (rs + h.z) * 1.0001f;
+                if (oslot != c && !(d2 > cut * cut)) {   // NaNs are kept
+                    if (n < (uint32_t)NL_CAP) keep[n * NL_BUILD_THREADS + tid] = oslot;
+                    ++n;
+                }
+            };
+            const CellRange R = cell_range(g, a.x, a.y, r);
+            const uint32_t n1 = min(R.nx, g.W - R.c0);   // cells before the row wraps
+            for (uint32_t j = 0; j < R.ny; ++j) {
+                uint32_t row = R.r0 + j;
+                if (row >= g.H) row -= g.H;
+                const uint32_t base = wbase + row * g.W;
+                uint32_t lo = __ldg(tab + base + R.c0), hi = __ldg(tab + base + R.c0 + n1);
+#pragma unroll 4
+                for (uint32_t k = lo; k < hi; ++k) offer(__ldg(hot + k));
+                if (n1 < R.nx) {   // wrapped part of the row
+                    lo = __ldg(tab + base);
+                    hi = __ldg(tab + base + (R.nx - n1));
+                    for (uint32_t k = lo; k < hi; ++k) offer(__ldg(hot + k));
+                }
+            }
+            uint32_t cnt = NL_OVER;
+            if (n <= (uint32_t)NL_CAP) {
+                cnt = n;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t v = keep[i * NL_BUILD_THREADS + tid];
+                    uint32_t rank = 0;
+                    for (uint32_t q = 0; q < n; ++q) rank += keep[q * NL_BUILD_THREADS + tid] < v ? 1u : 0u;
+                    L.idx[(size_t)rank * L.stride + c] = v;
+                }
+            }
+            hd = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), cnt, cc.y);
+        }
+        L.hdr[c] = hd;
+    }
+    __syncthreads();
+    if (tid == 0u) {
+        __threadfence();
+        if (atomicAdd(&ctl->done, 1u) == gridDim.x - 1u) {   // last CTA: every CTA has read the parity by now
+            ctl->done = 0u;
+            ctl->parity = nx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_step: one thread per body slot (bodies with zero or one collider; multi-collider bodies go to k_multi).
+// brute_force_collisions restricted to the body's neighbour list + apply_gravity + update_objects + apply_constraints
+// (physics.rs:241-395), then the new snapshot record and its displacement tracking.
+// Memory rounds: (1) the body arrays, the own snapshot record, the list header and the first NL_SPEC list rows, all at the
+// speculated collider slot c == b (lock-step insertion); (2) the listed snapshot records, NL_SPEC in flight, squared-distance
+// prefilter into a bit mask; (3) survivors re-read (L1) one by one for the exact narrowphase, in list order = ascending slot =
+// the reference's summation order.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nl_prefilter(const SelfCol& s, float srk, const float4 h) {
+    const float dx = s.x - h.x, dy = s.y - h.y;
+    const float d2 = __fmaf_rn(dx, dx, dy * dy);
+    const float mdk = __fmaf_rn(h.z, 1.00005f, srk);   // (ra + rb) * 1.00005, see gather_single
+    return !(d2 > mdk * mdk);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 3) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
+                                                 Recording rec, DeviceStats* stats) {
+    const NlView& L = bp.nl;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inb = b < P.n_bodies;
+    const uint32_t bl = inb ? b : 0u;
+    const float ccx = L.ctl->cx, ccy = L.ctl->cy;
+    // round 1 (tail threads read slot 0 and discard)
+    const uint2 info = B.binfo[bl];
+    const float2 mg = B.bmg[bl];
+    float2 p = B.pos[bl];
+    const float2 po = B.pos_old[bl];
+    const float2 acc0 = B.acc[bl];
+    const bool hv = B.has_vreq[bl] != 0;
+    uint32_t cs = 0;
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 hd = make_uint4(0u, 0u, NL_INACTIVE, 0u);
+    uint32_t e[NL_SPEC];
+#pragma unroll
+    for (int k = 0; k < NL_SPEC; ++k) e[k] = 0u;
+    if (P.n_colliders) {
+        cs = min(bl, P.n_colliders - 1u);
+        me = __ldg(L.snap_cur + cs);
+        hd = __ldg(reinterpret_cast<const uint4*>(L.hdr) + cs);
+#pragma unroll
+        for (int k = 0; k < NL_SPEC; ++k) e[k] = __ldg(L.idx + (size_t)k * L.stride + cs);
+    }
+    const uint32_t flags = info.x;
+    const int32_t col = (int32_t)info.y;
+    NlAcc na{0.f, 0.f, 0.f, 0u};
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
+    unsigned int n_over = 0;
+    if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
+        bool active_col = false, deferred = false;
+        uint32_t c = 0;
+        if (col >= 0) {
+            c = (uint32_t)col;
+            if (c != cs) {   // speculation missed: fetch the real collider
+                me = __ldg(L.snap_cur + c);
+                hd = __ldg(reinterpret_cast<const uint4*>(L.hdr) + c);
+#pragma unroll
+                for (int k = 0; k < NL_SPEC; ++k) e[k] = __ldg(L.idx + (size_t)k * L.stride + c);
+            }
+            active_col = hd.z != NL_INACTIVE;
+            if (active_col && P.collisions_enabled) {
+                const uint32_t word = __float_as_uint(me.w);
+                SelfCol s;
+                s.x = me.x; s.y = me.y; s.r = me.z; s.m = mg.x;
+                s.qx = __uint_as_float(hd.x); s.qy = __uint_as_float(hd.y);   // where the grid of the last rebuild has this collider
+                s.memb = s.filt = 0xffffffffu;
+                if (word & HOT_COLD_BIT) {
+                    const uint4 cc = Cc.cconst[c];
+                    s.memb = cc.z; s.filt = cc.w;
+                }
+                s.body = b; s.slot = c; s.wbase = 0u; s.sensor = (word & HOT_SENSOR_BIT) != 0u;
+                if (hd.z == NL_OVER) {   // more neighbours than a list holds (the shell the circle constraint builds)
+                    n_over = 1;
+                    if (P.crowded) {     // a whole warp of k_crowded does this body, pair counting included
+                        P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
+                        deferred = true;
+                    } else {             // first sighting (the host adds k_crowded to the pipeline from the next call on): serial, exact
+                        const Broadphase gb = resolve_grid(bp);
+                        if (g.n_worlds > 1u) s.wbase = B.bworld[b] * g.ncells;
+                        for_each_candidate(g, gb, Cc.ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
+                            Contact ct;
+                            if (narrowphase(s, o, ct)) note_pair(s, o, ct, out, rec, B.vel, stats);
+                        });
+                        SelfCol s2 = s;
+                        p = apply_contacts_rescan(g, gb, Cc.ccold, &s2, 1, p.x, p.y);
+                    }
+                } else {
+                    const uint32_t cnt = hd.z;
+                    const float srk = s.r * 1.00005f;
+                    uint32_t mask = 0;
+                    {
+                        float4 h[NL_SPEC];
+#pragma unroll
+                        for (int k = 0; k < NL_SPEC; ++k) h[k] = __ldg(L.snap_cur + ((uint32_t)k < cnt ? e[k] : c));
+#pragma unroll
+                        for (int k = 0; k < NL_SPEC; ++k)
+                            if ((uint32_t)k < cnt && nl_prefilter(s, srk, h[k])) mask |= 1u << k;
+                    }
+                    for (uint32_t k0 = NL_SPEC; k0 < cnt; k0 += 4u) {
+                        uint32_t j[4];
+                        float4 h[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) j[i] = k0 + i < cnt ? __ldg(L.idx + (size_t)(k0 + i) * L.stride + c) : c;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __ldg(L.snap_cur + j[i]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (k0 + i < cnt && nl_prefilter(s, srk, h[i])) mask |= 1u << (k0 + i);
+                    }
+                    while (mask) {   // the whole warp runs this loop together: trip count = most survivors of any lane
+                        const uint32_t k = (uint32_t)__ffs(mask) - 1u;
+                        mask &= mask - 1u;
+                        const uint32_t j = __ldg(L.idx + (size_t)k * L.stride + c);
+                        const Rec o = rec_of(__ldg(L.snap_cur + j), Cc.ccold);
+                        Contact ct;
+                        if (!narrowphase(s, o, ct)) continue;
+                        note_pair(s, o, ct, out, rec, B.vel, stats);
+                        if (ct.coincident) p.x = fadd(p.x, ct.i_am_a ? 0.01f : -0.01f);   // physics.rs:275-276, ordered just before the push
+                        if (ct.push) { p.x = fadd(p.x, ct.cx); p.y = fadd(p.y, ct.cy); }
+                    }
+                }
+            }
+        }
+        if (deferred) {
+            // nothing: every array of this body is left untouched for k_crowded
+        } else if (FUSED && !(flags & BF_JOINTED)) {   // jointed bodies are advanced by k_integrate after the joint projection
+            float sx, sy, rot;
+            integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+            if (active_col) {
+                const float2 a = snapshot_of(Cc, c, hd.w, sx, sy, rot);
+                Cc.cabs[c] = a;
+                L.snap_next[c] = make_float4(a.x, a.y, me.z, me.w);
+                nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), ccx, ccy, na);
+            }
+        } else {
+            B.pos[b] = p;
+        }
+    }
+    nl_commit(L.ctl, na, &stats->collisions, out.n_pairs);
+    if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
+        warp_add_u64(&stats->coincident, out.n_coinc);
+        unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
+        if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
+    }
+}

@@ -13,9 +13,9 @@ enum : uint32_t {
     BF_SPRINGS = 1u << 2,      // has incident springs: gravity + spring forces are summed by k_springs
     BF_ROT = 1u << 3,          // angular state may be non-zero / rotation matters (torque, joints, rotated)
     BF_JOINTED = 1u << 4,
-    BF_FIRST_DYN = 1u << 5,
+    BF_FIRST_DYN = 1u << 5,    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
+    BF_KINEMATIC = 1u << 6,    // RigidBodyType::KinematicPositionBased / KinematicVelocityBased (only scene queries look at it)
     BF_LOOSE = 1u << 7,        // no collider and no joint: no record stands for it in the cell-sorted array (k_tile advances these with a k_integrate pass)
-    BF_KINEMATIC = 1u << 6,    // RigidBodyType::KinematicPositionBased / KinematicVelocityBased (only scene queries look at it)    // first non-static body of its world in arena order: sees dt/old_dt (physics.rs:338-339, Q2)
 };
 // collider flags (host-authoritative, cflags[])
 enum : uint32_t {
@@ -125,11 +125,45 @@ struct ColliderArrays {
     const uint4* ccold;      // (parent's calculated_mass bits, memberships, filter, parent slot) — Rec cold half
 };
 
+// ---- neighbour-list pipeline: contacts are found from per-collider lists of every collider within
+// r_a + r_b + skin, rebuilt from the cell grid only when the snapshots have moved by more than ~skin/2 since the last build --
+constexpr int NL_CAP = 32;                       // list rows; entry k of collider c sits at idx[k * stride + c] (transposed: coalesced)
+constexpr int NL_SPEC = 8;                       // rows fetched together with the body state (before the count is known)
+constexpr uint32_t NL_OVER = 0xffffffffu;        // NlView::hdr[c].z: more than NL_CAP neighbours -> the body goes to k_crowded
+constexpr uint32_t NL_INACTIVE = 0xfffffffeu;    // NlView::hdr[c].z: collider slot is free / parentless / not owned by this rank
+struct NlCtl {                 // device-resident control block
+    unsigned int need;         // the lists are rebuilt before this substep's contact pass (decided by k_nl_decide)
+    unsigned int force;        // host request: topology / table / staged collider writes changed
+    unsigned int parity;       // which of the two tables holds the grid of the last rebuild
+    unsigned int max_m;        // float bits: max over colliders of |snapshot - ref - c| (+ rounding slack), accumulated by the publishers
+    float sum_x, sum_y;        // sampled sum of (snapshot - ref), and how many colliders were sampled
+    unsigned int n_sum;
+    float cx, cy;              // common-mode displacement the publishers of this substep subtract (any value is valid: it only decides WHEN lists are rebuilt)
+    float mean_x, mean_y;      // sampled mean displacement at the previous decision (0 right after a rebuild)
+    unsigned int done;         // CTA arrival counter of k_nl_build
+    unsigned long long rebuilds, substeps;   // statistics
+};
+struct NlView {
+    const float4* snap_cur;    // slot-indexed snapshot records (x, y, r, hot word) of the previous substep: what the contact pass reads
+    float4* snap_next;         // ... written by the publishers of this substep; nullptr = grid pipeline (no lists)
+    uint4* hdr;                // per collider slot: (ref.x, ref.y, list length | NL_OVER | NL_INACTIVE, CF_* flags)
+    uint32_t* idx;             // neighbour collider slots, ascending (= the reference's pair-loop order for a single-collider body)
+    uint32_t stride;
+    float lim;                 // rebuild when max_m exceeds this (0.45 * skin; +inf while collisions are disabled)
+    float skin;
+    NlCtl* ctl;
+    uint32_t* tab[2];          // the two cell-start tables / scan-tile totals; [ctl->parity] is current
+    uint32_t* tile[2];
+    float4* hot;               // cell-sorted records of the last rebuild (their POSITIONS are stale: only the slot word is used)
+};
+
 struct Broadphase {
     const float4* hot;       // current cell-sorted hot halves (see Rec), read-only during the contact pass
     const uint32_t* tab;     // current cell starts, ncells + 1 entries
     uint32_t* tab_next;      // counts for the next table (zeroed)
     uint32_t* tile_next;     // per-scan-tile totals of tab_next (zeroed), so k_scan needs no inter-block dependency
+    const float4* snap;      // list pipeline: records found through `hot` are re-read from this slot-indexed array (nullptr otherwise)
+    NlView nl;
 };
 
 // ---- strip decomposition of one large world across ranks (BASELINE config #5) -------------------------------------

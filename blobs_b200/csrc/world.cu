@@ -72,6 +72,8 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_POOL_MIN")) pool_min = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_LIST")) list_mode = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_SKIN")) skin_frac = (float)std::atof(e);
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
@@ -94,16 +96,15 @@ int World::init() {
     CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&d_stats, sizeof(DeviceStats)));
     CU(cudaMallocHost(&h_stats, sizeof(DeviceStats)));
+    CU(cudaMalloc(&d_nlctl, sizeof(NlCtl)));
+    CU(cudaMemsetAsync(d_nlctl, 0, sizeof(NlCtl), stream));
+    CU(cudaMallocHost(&h_nlctl, sizeof(NlCtl)));
+    std::memset(h_nlctl, 0, sizeof(NlCtl));
     CU(cudaMalloc(&d_rec_count, sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
     CU(cudaEventCreate(&ev_step0));
     CU(cudaEventCreate(&ev_step1));
-    CU(cudaFuncSetAttribute(k_joints_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
-    CU(cudaFuncSetAttribute(k_joints_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
-    // k_tile<POOLED> holds 46 KB of windows + queues per CTA: ask for the large shared-memory carve-out so that 4 CTAs fit an SM
-    CU(cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_tile<true, 128>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_tile<true, TILE_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_joints_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, JOINT_THREADS * JOINT_SMEM_MAX * (int)sizeof(float4)));
     if (params.body_capacity_hint) {
         const size_t n = params.body_capacity_hint;
         CU(pos.ensure(n, stream)); CU(pos_old.ensure(n, stream)); CU(acc.ensure(n, stream)); CU(vel.ensure(n, stream));
@@ -148,6 +149,9 @@ World::~World() {
     if (d_ocount) cudaFree(d_ocount);
     if (d_io_count) cudaFree(d_io_count);
     if (nccl_comm && g_nccl_destroy) g_nccl_destroy(nccl_comm);
+    snap_a.release(); snap_b.release(); nl_hdr.release(); nl_idx.release();
+    if (d_nlctl) cudaFree(d_nlctl);
+    if (h_nlctl) cudaFreeHost(h_nlctl);
     if (d_stats) cudaFree(d_stats);
     if (h_stats) cudaFreeHost(h_stats);
     if (d_rec_count) cudaFree(d_rec_count);
@@ -179,6 +183,11 @@ int World::set_param(int id, double v) {
             p2p_request = v != 0;
             break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
+        case BLOBS_PARAM_LIST: list_mode = (int)v; bp_dirty = true; break;
+        case BLOBS_PARAM_SKIN:
+            if (!(v > 0.0) || !(v <= 16.0)) return fail(BLOBS_ERR_INVALID, "BLOBS_PARAM_SKIN must be in (0, 16] (fraction of the largest collider radius)");
+            skin_frac = (float)v; bp_dirty = true;
+            break;
         case BLOBS_PARAM_STRIP_MAX_GHOSTS: last_max_ghosts = (uint32_t)v; break;      // reset
         case BLOBS_PARAM_STRIP_MAX_MIGRANTS: last_max_migrants = (uint32_t)v; break;  // reset
         case BLOBS_PARAM_BATCH_WORLD:
@@ -212,6 +221,10 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_STRIP_P2P: *out = strip_on ? (p2p_on ? 1.0 : 0.0) : (p2p_request ? 1.0 : 0.0); break;
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
+        case BLOBS_PARAM_LIST: *out = list_mode; break;
+        case BLOBS_PARAM_SKIN: *out = skin_frac; break;
+        case BLOBS_PARAM_LIST_REBUILDS: *out = (double)h_nlctl->rebuilds; break;
+        case BLOBS_PARAM_LIST_SUBSTEPS: *out = (double)h_nlctl->substeps; break;
         case BLOBS_PARAM_GRAPH_REPLAYS: *out = (double)graph_replays; break;
         case BLOBS_PARAM_STRIP_MAX_GHOSTS: *out = last_max_ghosts; break;
         case BLOBS_PARAM_STRIP_MAX_MIGRANTS: *out = last_max_migrants; break;
@@ -271,6 +284,7 @@ int World::flush_writes() {
         pending.clear();
     }
     if (!pending_col.empty()) {
+        nl_force_pending = true;   // caller-supplied snapshots: the lists (and the slot-indexed records) must be rebuilt from them
         CU(d_pending_col.ensure(pending_col.size(), stream));
         CU(cudaMemcpyAsync(d_pending_col.d, pending_col.data(), pending_col.size() * sizeof(ColWrite), cudaMemcpyHostToDevice, stream));
         BLOBS_LAUNCH(cdiv(pending_col.size(), 256), 256, 0, stream, k_apply_col_writes)(cabs.d, d_pending_col.d, (uint32_t)pending_col.size());
@@ -819,12 +833,15 @@ int World::rebuild_topology() {
         if (bodies.alive[b]) {
             HBody& x = hb[b];
             f |= BF_ALIVE;
-            if (x.type == BLOBS_BODY_STATIC) f |= BF_STATIC;
-            if (x.type == BLOBS_BODY_KINEMATIC_POSITION || x.type == BLOBS_BODY_KINEMATIC_VELOCITY) f |= BF_KINEMATIC;
-            else {
+            // physics.rs:327-339: the dt/old_dt ratio goes to the first NON-STATIC body in arena order (kinematic bodies count as
+            // non-static), and old_dt is only overwritten when such a body exists
+            if (x.type == BLOBS_BODY_STATIC) {
+                f |= BF_STATIC;
+            } else {
                 any_dynamic = true;
                 if (!world_has_first[x.world]) { world_has_first[x.world] = 1; f |= BF_FIRST_DYN; }
             }
+            if (x.type == BLOBS_BODY_KINEMATIC_POSITION || x.type == BLOBS_BODY_KINEMATIC_VELOCITY) f |= BF_KINEMATIC;
             if (x.n_springs) f |= BF_SPRINGS;
             if (x.n_joints) f |= BF_JOINTED | BF_ROT;
             if (x.rot_active) f |= BF_ROT;
@@ -890,7 +907,11 @@ int World::flush() {
 // ---------------------------------------------------------------------------------------------- broadphase
 int World::choose_grid(bool) {
     const size_t nc = cols.slots();
-    float cs = bp_cell_override > 0.f ? bp_cell_override : (r_max > 0.f ? 2.0f * r_max : 1.0f);
+    // list pipeline: the rebuild collects every collider within r_a + r_b + skin, so the search reach (and the cell that keeps it
+    // inside a 3x3 neighbourhood) grows by the skin
+    nl_on = list_mode != 0 && !strip_on;
+    nl_skin = nl_on ? skin_frac * r_max : 0.f;
+    float cs = bp_cell_override > 0.f ? bp_cell_override : (r_max > 0.f ? 2.0f * r_max + nl_skin : 1.0f);
     if (!(cs > 0.f) || !std::isfinite(cs)) cs = 1.0f;
     DeviceStats init{};
     init.bb_min_x = init.bb_min_y = INT32_MAX;
@@ -925,7 +946,7 @@ int World::choose_grid(bool) {
     grid.n_worlds = n_worlds;
     grid.cell = cs;
     grid.inv_cell = 1.0f / cs;
-    grid.rmax = r_max;
+    grid.rmax = nl_on ? (r_max + nl_skin) * 1.000001f : r_max;
     grid.MW = ~0ull / grid.W + 1ull;
     grid.MH = ~0ull / grid.H + 1ull;
     bb[0] = h_stats->bb_min_x; bb[1] = h_stats->bb_min_y; bb[2] = h_stats->bb_max_x; bb[3] = h_stats->bb_max_y;
@@ -951,6 +972,23 @@ int World::rebuild_broadphase() {
     uint32_t* tile_next = cur_is_a ? tile_b.d : tile_a.d;
     uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
+    if (nl_on) {
+        // list pipeline: the tables stay empty here; the first substep finds `force` set and runs the rebuild chain on the device
+        const size_t ncap = std::max<size_t>(cabs.cap, 1);
+        CU(snap_a.ensure(ncap, stream)); CU(snap_b.ensure(ncap, stream)); CU(nl_hdr.ensure(ncap, stream));
+        nl_stride = (uint32_t)nl_hdr.cap;
+        CU(nl_idx.ensure((size_t)NL_CAP * nl_stride, stream));
+        NlCtl init{};
+        init.force = 1u;
+        init.rebuilds = h_nlctl->rebuilds;
+        init.substeps = h_nlctl->substeps;
+        *h_nlctl = init;
+        CU(cudaMemcpyAsync(d_nlctl, h_nlctl, sizeof(NlCtl), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        nl_force_pending = false;
+        bp_dirty = false;
+        return BLOBS_OK;
+    }
     if (nc) {
         BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_count)(grid, col_arrays(), bworld.d.d, tab_next, tile_next, (uint32_t)nc, strip_on ? d_cowned.d : nullptr);
         launches++;
@@ -965,11 +1003,69 @@ int World::rebuild_broadphase() {
     return BLOBS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- neighbour lists
+NlView World::nl_view() {
+    NlView L{};
+    L.snap_cur = cur_is_a ? snap_a.d : snap_b.d;
+    L.snap_next = cur_is_a ? snap_b.d : snap_a.d;
+    L.hdr = nl_hdr.d;
+    L.idx = nl_idx.d;
+    L.stride = nl_stride;
+    L.skin = nl_skin;
+    // while collisions are disabled nothing reads the lists: no rebuilds (re-enabling forces one, see step())
+    L.lim = collisions_enabled ? 0.45f * nl_skin : INFINITY;
+    L.ctl = d_nlctl;
+    L.tab[0] = tab_a.d; L.tab[1] = tab_b.d;
+    L.tile[0] = tile_a.d; L.tile[1] = tile_b.d;
+    L.hot = hot_a.d;
+    return L;
+}
+
+// First launches of every substep in list mode: the decision kernel, then the four rebuild kernels, which return at once unless
+// the decision was "rebuild" (the decision lives on the device, so that captured steps can be replayed).
+int World::nl_rebuild_chain(bool timed_launch) {
+    const NlView L = nl_view();
+    const ColliderArrays C = col_arrays();
+    const uint32_t nc = (uint32_t)cols.slots();
+    const size_t tn = table_entries();
+    auto run = [&](KClass k, auto&& f) -> int {
+        if (timed_launch) return timed(k, f);
+        f();
+        launches++;
+        CU(cudaGetLastError());
+        return BLOBS_OK;
+    };
+    int rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u); });
+    if (rc) return rc;
+    if (!nc) return BLOBS_OK;
+    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, nullptr); });
+    if (rc) return rc;
+    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
+    if (rc) return rc;
+    rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_nl_scatter)(C, L, nc, nullptr); });
+    if (rc) return rc;
+    rc = run(KC_NLBUILD, [&] {
+        BLOBS_LAUNCH(cdiv(nc, NL_BUILD_THREADS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr);
+    });
+    return rc;
+}
+
+// Outside a step (scene queries): bring the cell grid up to date with the current snapshots, and learn which table holds it.
+int World::nl_rebuild_now() {
+    const unsigned int one = 1u;
+    CU(cudaMemcpyAsync(&d_nlctl->force, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+    int rc = nl_rebuild_chain(false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_nlctl, d_nlctl, sizeof(NlCtl), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return BLOBS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- stepping
 // profiler range per kernel class: the reference's tracy span names where the kernel replaces a spanned function
 // (physics.rs:242 "brute_force_collisions", physics.rs:324 "update positions"), descriptive names otherwise
 static const char* const kclass_span[KC_COUNT] = {"brute_force_collisions", "broadphase scan", "broadphase scatter", "springs", "solve_fixed_joints",
-                                                  "update positions", "other", "strip pack", "strip ghosts", "strip exchange", "crowded contacts"};
+                                                  "update positions", "other", "strip pack", "strip ghosts", "strip exchange", "crowded contacts", "neighbour lists", "list decision"};
 
 template <class F>
 int World::timed(KClass k, F&& f) {
@@ -1052,6 +1148,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     mix(&C, sizeof(C));
     MIXV(hot_a.d) MIXV(hot_b.d) MIXV(tab_a.d) MIXV(tab_b.d) MIXV(tile_a.d) MIXV(tile_b.d) MIXV(d_constraints.d) MIXV(mb_body.d) MIXV(mb_off.d) MIXV(mb_cols.d)
     MIXV(sb_body.d) MIXV(sb_off.d) MIXV(sb_edge.d) MIXV(d_springs.d) MIXV(isl_off.d) MIXV(isl_joint.d) MIXV(d_joints.d) MIXV(d_joints_inter.d)
+    MIXV(nl_on) MIXV(nl_skin) MIXV(snap_a.d) MIXV(snap_b.d) MIXV(nl_hdr.d) MIXV(nl_idx.d) MIXV(nl_stride) MIXV(d_nlctl)
     MIXV(isl_boff.d) MIXV(isl_body.d) MIXV(olist.d) MIXV(opos.d) MIXV(d_owned.d) MIXV(d_cowned.d) MIXV(gcell.d) MIXV(msg[0]) MIXV(msg[1]) MIXV(msg[2]) MIXV(msg[3]) MIXV(p2p_on) MIXV(p2p_block) MIXV(p2p_peer[0]) MIXV(p2p_peer[1]) MIXV(nccl_exchanges & 1u)
 #undef MIXV
     return h ? h : 1;
@@ -1112,7 +1209,9 @@ int World::launch_substep(const SubstepParams& P_in) {
     const bool auto_ok = !strip_on;
     const bool pooled = contact_mode == 0 && collisions_enabled && (pool_mode == 1 || (pool_mode == 2 && pool_seen && auto_ok));
     // (automatic mode: the pooled k_main hands its big-neighbourhood bodies to k_crowded, so the two come together)
-    const bool crowded = contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && (crowded_seen || pooled) && auto_ok));
+    const bool lists = nl_on;
+    const bool crowded = lists ? (collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && crowded_seen)))
+                               : (contact_mode == 0 && collisions_enabled && (crowded_mode == 1 || (crowded_mode == 2 && (crowded_seen || pooled) && auto_ok)));
     P.crowded = crowded ? 1u : 0u;
     P.over_parity = cur_is_a ? 0u : 1u;
     P.over_list = over_list.d;
@@ -1120,11 +1219,17 @@ int World::launch_substep(const SubstepParams& P_in) {
     const BodyArrays B = body_arrays();
     const ColliderArrays C = col_arrays();
     const Constraints K = constraints_pod();
-    Broadphase bp;
+    Broadphase bp{};
     bp.hot = cur_is_a ? hot_a.d : hot_b.d;
     bp.tab = cur_is_a ? tab_a.d : tab_b.d;
     bp.tab_next = cur_is_a ? tab_b.d : tab_a.d;
     bp.tile_next = cur_is_a ? tile_b.d : tile_a.d;
+    if (lists) {   // the kernels that walk the grid pick the table of the last rebuild on the device (resolve_grid)
+        bp.nl = nl_view();
+        bp.hot = bp.nl.hot;
+        bp.tab = nullptr;
+        bp.tab_next = bp.tile_next = nullptr;
+    }
     uint32_t* tile_cur = cur_is_a ? tile_a.d : tile_b.d;
     uint32_t* tab_cur = cur_is_a ? tab_a.d : tab_b.d;
     float4* hot_next = cur_is_a ? hot_b.d : hot_a.d;
@@ -1142,6 +1247,10 @@ int World::launch_substep(const SubstepParams& P_in) {
     last_fused = fused;
     const uint32_t nb = P.n_bodies;
     int rc;
+    if (lists) {   // decide on the device whether the lists are still supersets of the contact set; rebuild them if not
+        rc = nl_rebuild_chain(true);
+        if (rc) return rc;
+    }
     if (n_sb) {
         rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
         if (rc) return rc;
@@ -1150,74 +1259,29 @@ int World::launch_substep(const SubstepParams& P_in) {
         CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
         CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
     }
-    const bool tile_used = nb && tune >= 11 && tune <= 13 && fused && ordered && !(strip_on && n_loose) && n_active_cols;
-    if (nb) {
+    if (nb && lists) {
+        rc = timed(KC_MAIN, [&] {
+            if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true>)(P, grid, K, B, C, bp, R, d_stats);
+            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false>)(P, grid, K, B, C, bp, R, d_stats);
+        });
+        if (rc) return rc;
+    } else if (nb) {
         rc = timed(KC_MAIN, [&] {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
-#define BLOBS_LAUNCH_MAIN(F, O, BT, MB, PL) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<F, O, BT, MB, PL>)(P, grid, K, B, C, bp, R, d_stats, sv)
-#define BLOBS_MAIN_VARIANT(BT, MB)                                          \
-    do {                                                                    \
-        if (fused) {                                                        \
-            if (ordered) BLOBS_LAUNCH_MAIN(true, true, BT, MB, false);      \
-            else BLOBS_LAUNCH_MAIN(true, false, BT, MB, false);             \
-        } else {                                                            \
-            if (ordered) BLOBS_LAUNCH_MAIN(false, true, BT, MB, false);     \
-            else BLOBS_LAUNCH_MAIN(false, false, BT, MB, false);            \
-        }                                                                   \
-    } while (0)
-            if (tile_used) {
-                // one thread per cell-sorted record, candidate windows staged in shared memory (kernels.cuh: k_tile).
-                // Strip mode: the records are the owned colliders plus the ghosts received for this table (skipped by their threads).
-                const size_t nrec_bound = strip_on ? (size_t)std::max<uint32_t>(olaunch_dim, 1) + 2 * (size_t)strip.gcap : (size_t)n_active_cols;
-                const uint32_t n_ent = (uint32_t)(table_entries() - 1);
-                const uint32_t hot_len = (uint32_t)std::min<size_t>(cur_is_a ? hot_a.cap : hot_b.cap, 0xffffffffu);
-                if (tune == 13) {   // windows fetched by TMA bulk copies (cp.async.bulk + mbarrier) instead of by the CTA's threads
-                    const unsigned gt = cdiv(nrec_bound, TILE_THREADS);
-                    if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true, TILE_THREADS, true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                    else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false, TILE_THREADS, true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                } else if (tune == 12) {   // 128-record tiles: twice the CTAs, half the barrier-coupled work each
-                    const unsigned gt = cdiv(nrec_bound, 128);
-                    if (pooled) BLOBS_LAUNCH(gt, 128, 0, stream, k_tile<true, 128>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                    else BLOBS_LAUNCH(gt, 128, 0, stream, k_tile<false, 128>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                } else {
-                    const unsigned gt = cdiv(nrec_bound, TILE_THREADS);
-                    if (pooled) BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<true>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                    else BLOBS_LAUNCH(gt, TILE_THREADS, 0, stream, k_tile<false>)(P, grid, K, B, C, bp, R, d_stats, sv, n_ent, hot_len);
-                }
-            } else if (pooled && tune == 0) {  // contact-rich state: warp-pooled resolution
-                if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 4, true);
-                else BLOBS_LAUNCH_MAIN(false, true, 4, 4, true);
-            } else if (pooled && tune == 8) {  // same with 85 registers per thread (3 CTAs per SM)
-                if (fused) BLOBS_LAUNCH_MAIN(true, true, 4, 3, true);
-                else BLOBS_LAUNCH_MAIN(false, true, 4, 3, true);
-            } else if (tune == 9 || tune == 10) {
-                // 128-thread CTAs (8 per SM, same registers per thread): the warps of a CTA finish at very different times in
-                // contact-rich states (35 % achieved vs 50 % theoretical occupancy with 256 threads), smaller CTAs free their slots
-                // sooner. 9 = with the automatic pooled/per-lane choice, 10 = per-lane only. Unmeasured so far (round-2 sweep).
-                const unsigned g128 = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 128);
-#define BLOBS_LAUNCH_MAIN128(F, PL) BLOBS_LAUNCH(g128, 128, 0, stream, k_main<F, true, 4, 8, PL, 128>)(P, grid, K, B, C, bp, R, d_stats, sv)
-                if (!ordered) BLOBS_MAIN_VARIANT(4, 4);
-                else if (pooled && tune == 9) { if (fused) BLOBS_LAUNCH_MAIN128(true, true); else BLOBS_LAUNCH_MAIN128(false, true); }
-                else { if (fused) BLOBS_LAUNCH_MAIN128(true, false); else BLOBS_LAUNCH_MAIN128(false, false); }
-#undef BLOBS_LAUNCH_MAIN128
-            } else
-            switch (tune) {
-                case 2: BLOBS_MAIN_VARIANT(8, 4); break;
-                case 3: BLOBS_MAIN_VARIANT(4, 5); break;
-                case 4: BLOBS_MAIN_VARIANT(4, 3); break;
-                case 5: BLOBS_MAIN_VARIANT(8, 3); break;
-                case 6: BLOBS_MAIN_VARIANT(6, 4); break;
-                case 7: BLOBS_MAIN_VARIANT(2, 5); break;
-                default: BLOBS_MAIN_VARIANT(4, 4); break;
+#define BLOBS_LAUNCH_MAIN(F, O, PL) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<F, O, 4, 4, PL>)(P, grid, K, B, C, bp, R, d_stats, sv)
+            if (pooled) {   // contact-rich state: warp-pooled resolution
+                if (fused) BLOBS_LAUNCH_MAIN(true, true, true);
+                else BLOBS_LAUNCH_MAIN(false, true, true);
+            } else if (fused) {
+                if (ordered) BLOBS_LAUNCH_MAIN(true, true, false);
+                else BLOBS_LAUNCH_MAIN(true, false, false);
+            } else {
+                if (ordered) BLOBS_LAUNCH_MAIN(false, true, false);
+                else BLOBS_LAUNCH_MAIN(false, false, false);
             }
-#undef BLOBS_MAIN_VARIANT
 #undef BLOBS_LAUNCH_MAIN
         });
-        if (rc) return rc;
-    }
-    if (tile_used && n_loose) {   // bodies without a collider have no record for k_tile to start from: a body-parallel pass advances them
-        rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_LOOSE); });
         if (rc) return rc;
     }
     if (n_multi) {
@@ -1245,19 +1309,19 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (fused) {
         if (n_islands) {  // joint projection from shared memory, then a body-parallel (coalesced) verlet pass over the jointed bodies
             rc = timed(KC_JOINTS, [&] {
-                BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused<false>)(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
-                                                                                                         isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
+                BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused)(P, B, isl_off.d, d_joints_inter.d, isl_max_joints, isl_boff.d, isl_body.d, n_islands,
+                                                                                                  joint_iterations, d_stats);
             });
             if (rc) return rc;
-            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
+            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
             if (rc) return rc;
         }
     } else {
         if (n_islands && joint_iterations) {
             if (joints_smem_ok) {
                 rc = timed(KC_JOINTS, [&] {
-                    BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused<false>)(P, grid, K, B, C, bp.tab_next, bp.tile_next, isl_off.d, d_joints_inter.d, isl_max_joints,
-                                                                                                             isl_boff.d, isl_body.d, mb_off.d, mb_cols.d, n_islands, joint_iterations, d_stats);
+                    BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused)(P, B, isl_off.d, d_joints_inter.d, isl_max_joints, isl_boff.d, isl_body.d, n_islands,
+                                                                                                      joint_iterations, d_stats);
                 });
             } else {
                 rc = timed(KC_JOINTS, [&] { BLOBS_LAUNCH(cdiv(n_islands, 128), 128, 0, stream, k_joints)(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });
@@ -1265,13 +1329,15 @@ int World::launch_substep(const SubstepParams& P_in) {
             if (rc) return rc;
         }
         if (nb) {
-            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp.tab_next, bp.tile_next, d_stats, mb_off.d, mb_cols.d, 0u); });
+            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp, d_stats, mb_off.d, mb_cols.d, 0u); });
             if (rc) return rc;
         }
     }
-    rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
-    if (rc) return rc;
-    cur_is_a = !cur_is_a;
+    if (!lists) {
+        rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
+        if (rc) return rc;
+    }
+    cur_is_a = !cur_is_a;   // list pipeline: swaps the slot-indexed snapshot buffers
     if (rec_mode && sub_recorded < d_sub_end.cap) {
         CU(cudaMemcpyAsync(d_sub_end.d + sub_recorded, d_rec_count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
         sub_recorded++;
@@ -1308,6 +1374,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     }
     CU(cudaEventRecord(ev_step1, stream));
     CU(cudaMemcpyAsync(h_stats, d_stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, stream));
+    if (nl_on) CU(cudaMemcpyAsync(h_nlctl, d_nlctl, sizeof(NlCtl), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     CU(cudaGetLastError());
     float ms = 0.f;
@@ -1356,6 +1423,15 @@ int World::step(double delta, uint32_t n, BlobsStepStats* stats) {
     int rc = flush();
     if (rc) return rc;
     if (topo_error) return fail(topo_error, topo_error_msg);
+    if (nl_on) {
+        if (collisions_enabled && !nl_collisions_were_on) nl_force_pending = true;   // the lists were not maintained meanwhile
+        nl_collisions_were_on = collisions_enabled;
+        if (nl_force_pending) {
+            const unsigned int one = 1u;
+            CU(cudaMemcpyAsync(&d_nlctl->force, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+            nl_force_pending = false;
+        }
+    }
     DeviceStats init{};
     init.bb_min_x = init.bb_min_y = INT32_MAX;
     init.bb_max_x = init.bb_max_y = INT32_MIN;
@@ -1385,6 +1461,15 @@ int World::fixed_step(double frame_time, BlobsStepStats* stats) {
     int rc = flush();
     if (rc) return rc;
     if (topo_error) return fail(topo_error, topo_error_msg);
+    if (nl_on) {
+        if (collisions_enabled && !nl_collisions_were_on) nl_force_pending = true;   // the lists were not maintained meanwhile
+        nl_collisions_were_on = collisions_enabled;
+        if (nl_force_pending) {
+            const unsigned int one = 1u;
+            CU(cudaMemcpyAsync(&d_nlctl->force, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
+            nl_force_pending = false;
+        }
+    }
     DeviceStats init{};
     init.bb_min_x = init.bb_min_y = INT32_MAX;
     init.bb_max_x = init.bb_max_y = INT32_MIN;
@@ -1774,11 +1859,17 @@ int World::query_circles(size_t n, const float* centre_xy, const float* radius, 
         if (filter->batch_world >= n_worlds) return fail(BLOBS_ERR_INVALID, "query: batch world id out of range");
         F.wbase = filter->batch_world * grid.ncells;
     }
-    Broadphase bp;
+    Broadphase bp{};
     bp.hot = cur_is_a ? hot_a.d : hot_b.d;
     bp.tab = cur_is_a ? tab_a.d : tab_b.d;
     bp.tab_next = nullptr;
     bp.tile_next = nullptr;
+    if (nl_on) {   // list pipeline: the grid dates from the last list rebuild - sort the current snapshots into it first
+        rc = nl_rebuild_now();
+        if (rc) return rc;
+        bp.hot = hot_a.d;
+        bp.tab = (h_nlctl->parity & 1u) ? tab_b.d : tab_a.d;
+    }
     CU(d_qcentre.ensure(n, stream)); CU(d_qradius.ensure(n, stream)); CU(d_qcount.ensure(n, stream)); CU(d_qoff.ensure(n, stream));
     CU(cudaMemcpyAsync(d_qcentre.d, centre_xy, n * sizeof(float2), cudaMemcpyHostToDevice, stream));
     CU(cudaMemcpyAsync(d_qradius.d, radius, n * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -2244,11 +2335,3 @@ int World::profile_read(float* ms, uint64_t* nl, size_t n) {
 }
 
 }  // namespace blobs
-
-#ifdef BLOBS_EMU
-// host-compiled test build only (tests/emu): how many bodies k_tile served from its shared-memory windows / from the
-// global-memory fallback since the last call. Not part of the C ABI, absent from libblobs_b200.so.
-extern "C" void blobs_emu_tile_paths(unsigned long long* out3) {
-    for (int i = 0; i < 3; ++i) { out3[i] = blobs::tile_path_count[i]; blobs::tile_path_count[i] = 0; }
-}
-#endif

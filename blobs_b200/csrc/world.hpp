@@ -147,7 +147,7 @@ struct HCollider {
 struct HSpring { uint64_t a, b; float rest, k, c; };
 struct HJoint { uint64_t a, b; BlobsVec2 aa, ab; float distance, target; };
 
-enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_PACK, KC_GHOST, KC_NCCL, KC_CROWDED, KC_COUNT };
+enum KClass { KC_MAIN = 0, KC_SCAN, KC_SCATTER, KC_SPRINGS, KC_JOINTS, KC_INTEGRATE, KC_OTHER, KC_PACK, KC_GHOST, KC_NCCL, KC_CROWDED, KC_NLBUILD, KC_DECIDE, KC_COUNT };
 
 class World {
    public:
@@ -331,6 +331,23 @@ class World {
     bool cur_is_a = true;
     int bb[4] = {0, 0, 0, 0};
     bool bb_valid = false;
+
+    // neighbour-list pipeline (nlist.cuh): lists of every collider within r_a + r_b + skin, rebuilt on the device's own decision
+    int list_mode = 1;                 // BLOBS_PARAM_LIST: 0 = cell grid rebuilt every substep (k_main), 1 = neighbour lists (k_step)
+    float skin_frac = 0.4f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
+    float nl_skin = 0.f;
+    bool nl_on = false;                // the current broadphase is the list pipeline
+    bool nl_force_pending = false;     // host-side changes since the last step that invalidate the lists
+    bool nl_collisions_were_on = true;
+    DevBuf<float4> snap_a, snap_b;     // slot-indexed snapshot records, double-buffered by cur_is_a
+    DevBuf<uint4> nl_hdr;
+    DevBuf<uint32_t> nl_idx;
+    uint32_t nl_stride = 0;
+    NlCtl* d_nlctl = nullptr;
+    NlCtl* h_nlctl = nullptr;          // pinned copy, refreshed with the step statistics
+    NlView nl_view();
+    int nl_rebuild_chain(bool timed_launch);
+    int nl_rebuild_now();
 
     // stats / recording
     DeviceStats* d_stats = nullptr;

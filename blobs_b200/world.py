@@ -347,7 +347,7 @@ class World:
         self._ck(self._lib.blobs_profile_enable(self._h, int(on)))
 
     def profile_read(self):
-        names = ["main", "scan", "scatter", "springs", "joints", "integrate", "other", "strip_pack", "strip_ghost", "nccl_exchange", "crowded"]
+        names = ["main", "scan", "scatter", "springs", "joints", "integrate", "other", "strip_pack", "strip_ghost", "nccl_exchange", "crowded", "list_build", "list_decide"]
         ms = np.zeros(len(names), dtype=np.float32)
         nl = np.zeros(len(names), dtype=np.uint64)
         self._ck(self._lib.blobs_profile_read(self._h, A.ptr(ms), A.ptr(nl), len(names)))

@@ -20,11 +20,11 @@ timeout 900 python -m pytest tests -x -q -m gpu > $O/tests.log 2>&1; echo "tests
 BLOBS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_tile_gpu.py -x -q -m gpu -k tune13 > $O/tests_tune13.log 2>&1; echo "tune13 rc=$?" >> $O/tests_tune13.log
 timeout 500 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 BLOBS_BENCH_AUTOTUNE=0 BLOBS_BENCH_E2E=sync timeout 300 python bench.py --no-cpu-baseline > $O/bench_default_sync_e2e.json 2>> $O/bench_default.err
-for t in 0 11 12 13 9 10 8; do
+for t in 0 11 13; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --warmup 60 --steps 30 --no-cpu-baseline > $O/sparse_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 300 python bench.py --tune $t --no-cpu-baseline > $O/dense_tune$t.json 2>> $O/sweep.err
 done
-for t in 0 11 12; do
+for t in 0 11; do
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg3 --no-cpu-baseline > $O/cfg3_tune$t.json 2>> $O/sweep.err
   BLOBS_BENCH_AUTOTUNE=0 timeout 200 python bench.py --tune $t --workload cfg4 --no-cpu-baseline > $O/cfg4_tune$t.json 2>> $O/sweep.err
 done

@@ -22,6 +22,10 @@ def main():
     w = blobs_b200.World(gravity=sc.gravity)
     scenes.build(w, sc)
     w.set_param(A.PARAM_CROWDED, crowded)
+    if "TRACE_LIST" in os.environ:
+        w.set_param(A.PARAM_LIST, int(os.environ["TRACE_LIST"]))
+    if "TRACE_SKIN" in os.environ:
+        w.set_param(A.PARAM_SKIN, float(os.environ["TRACE_SKIN"]))
     cap = int(os.environ.get("CAPTURE_STEPS", "0"))
     if cap:
         w.set_param(A.PARAM_GRAPH, 0)
@@ -33,6 +37,7 @@ def main():
     while done < total:
         ms = 0.0
         coll = over = 0
+        r0, s0 = w.get_param(A.PARAM_LIST_REBUILDS), w.get_param(A.PARAM_LIST_SUBSTEPS)
         for _ in range(block):
             st = w.step(DT)
             ms += st["gpu_ms"]
@@ -41,7 +46,8 @@ def main():
         done += block
         print(json.dumps({"steps": [done - block, done], "sim_time_s": round(done * DT, 3), "ms_per_step": ms / block,
                           "sphere_steps_per_s": n * block / (ms / 1e3), "contacts_per_step": coll / block,
-                          "list_overflow_per_step": over / block, "grid": [w.kernel_info()["grid_w"], w.kernel_info()["grid_h"]]}), flush=True)
+                          "list_overflow_per_step": over / block,
+                          "rebuilds_per_substep": (w.get_param(A.PARAM_LIST_REBUILDS) - r0) / max(w.get_param(A.PARAM_LIST_SUBSTEPS) - s0, 1.0), "grid": [w.kernel_info()["grid_w"], w.kernel_info()["grid_h"]]}), flush=True)
 
 
 if __name__ == "__main__":

@@ -261,6 +261,7 @@ static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, u
 static inline cudaError_t cudaIpcCloseMemHandle(void* p) { return emu::ipc_close(p); }
 static inline long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static inline void __threadfence_system() { __sync_synchronize(); }
+static inline void __threadfence() { __sync_synchronize(); }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = static_cast<T*>(calloc(1, n ? n : 1)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }

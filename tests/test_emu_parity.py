@@ -69,59 +69,6 @@ def test_kernel_logic_on_cpu(case, knobs, monkeypatch):
         fn(**kw)
 
 
-SMALL_CTA_CASES = [c for c in CASES if c[0] in ("overflow200-fused-crowded", "multi-collider", "removal-reinsert")]
-
-
-@pytest.mark.parametrize("tune", ["9", "10"], ids=["tune9-128thr-pooled", "tune10-128thr-per-lane"])
-@pytest.mark.parametrize("case", SMALL_CTA_CASES, ids=[c[0] for c in SMALL_CTA_CASES])
-def test_128_thread_cta_variants(case, tune, monkeypatch):
-    """BLOBS_PARAM_TUNE 9 / 10: k_main with 128-thread CTAs (a round-2 experiment, never the default): same results."""
-    _, fn, kw = case
-    monkeypatch.setenv("BLOBS_B200_TUNE", tune)
-    for k, v in FORCED.items():
-        monkeypatch.setenv(k, v)
-    with emulated():
-        fn(**kw)
-
-
-TILE_CASES = [c for c in CASES if c[0] in ("multi-collider", "overflow200-fused-crowded", "overflow1200-fused-inline", "removal-reinsert", "far-outlier", "batched-worlds",
-                                           "soft-blobs-fused", "collisions-disabled-variable-delta")]
-
-
-@pytest.mark.parametrize("knobs", [DEFAULT, FORCED], ids=["default", "forced-pool-crowded"])
-@pytest.mark.parametrize("case", TILE_CASES, ids=[c[0] for c in TILE_CASES])
-def test_tile_kernel(case, knobs, monkeypatch):
-    """BLOBS_PARAM_TUNE 11: k_tile (one thread per cell-sorted record, candidate windows staged in shared memory; opt-in until it
-    has been measured on a B200) instead of k_main - same results, and the bodies really went through the staged path."""
-    import ctypes as C
-
-    from .emu_loader import load_emu
-
-    _, fn, kw = case
-    _skip_if_redundant(case, knobs)
-    monkeypatch.setenv("BLOBS_B200_TUNE", "11")
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
-    lib = load_emu()
-    paths = (C.c_ulonglong * 3)()
-    lib.blobs_emu_tile_paths(paths)   # reset
-    with emulated():
-        fn(**kw)
-    lib.blobs_emu_tile_paths(paths)
-    assert paths[0] > paths[1], f"k_tile: {paths[0]} bodies via shared-memory windows, {paths[1]} via the global fallback"
-
-
-@pytest.mark.parametrize("case", [c for c in TILE_CASES if c[0] in ("overflow200-fused-crowded", "removal-reinsert", "multi-collider")], ids=lambda c: c[0])
-def test_tile_kernel_128_record_tiles(case, monkeypatch):
-    """BLOBS_PARAM_TUNE 12: k_tile with 128-record tiles (128-thread CTAs), pooled + crowded forced."""
-    _, fn, kw = case
-    monkeypatch.setenv("BLOBS_B200_TUNE", "12")
-    for k, v in FORCED.items():
-        monkeypatch.setenv(k, v)
-    with emulated():
-        fn(**kw)
-
-
 def test_results_do_not_depend_on_the_schedule():
     """Same cases with the emulator visiting CTAs, warps and lanes in a seeded RANDOM order (BLOBS_EMU_SEED, read when the
     library is loaded, hence the subprocess): atomics then hand out different ranks and cells hold their records in another
@@ -133,7 +80,7 @@ def test_results_do_not_depend_on_the_schedule():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, BLOBS_EMU_SEED="20261017")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(repo, "tests", "test_emu_parity.py"), "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "(test_kernel_logic_on_cpu and (overflow200 or overflow1200-fused-crowded or multi-collider or large-island or events or removal)) or (test_tile_kernel and (overflow200 or removal))"],
+                        "-k", "(test_kernel_logic_on_cpu and (overflow200 or overflow1200-fused-crowded or multi-collider or large-island or events or removal))"],
                        capture_output=True, text=True, timeout=900, env=env, cwd=repo)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and " passed" in r.stdout

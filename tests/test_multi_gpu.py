@@ -64,10 +64,8 @@ _STRIP_CASES = [
     pytest.param({**_SHELL, **_FORCED}, id="shell-forced-pool-crowded"),
     pytest.param(dict(_SHELL), id="shell-default", marks=_slow),
     pytest.param(dict(_P2P), id="gas-p2p", marks=_slow),   # the 3-rank case below goes through the same exchange
-    pytest.param({**_SHELL, **_P2P, **_FORCED, "STRIP_TEST_RANKS": "3", "BLOBS_B200_TUNE": "11"}, id="shell-p2p-3ranks-tile-forced"),
+    pytest.param({**_SHELL, **_P2P, **_FORCED, "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-forced"),
     pytest.param({"STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-pipelined-host-io"),
-    pytest.param({"BLOBS_B200_TUNE": "11", "STRIP_TEST_STEPS": "16"}, id="gas-tile", marks=_slow),   # k_tile in strip mode: the 3-rank case above
-    pytest.param({**_SHELL, **_FORCED, "BLOBS_B200_TUNE": "11"}, id="shell-tile-forced-pool-crowded", marks=_slow),
 ]
 
 

@@ -23,7 +23,7 @@ BODY_DYNAMIC, BODY_STATIC, BODY_KINEMATIC_POSITION, BODY_KINEMATIC_VELOCITY = ra
 (PARAM_GRAVITY_X, PARAM_GRAVITY_Y, PARAM_SUBSTEPS, PARAM_JOINT_ITERATIONS, PARAM_USE_SPATIAL_HASH, PARAM_COLLISIONS_ENABLED,
  PARAM_ACCUMULATOR, PARAM_TIME, PARAM_OLD_DT, PARAM_CELL_SIZE, PARAM_BROADPHASE_CELL, PARAM_CONTACT_MODE, PARAM_FUSED, PARAM_TUNE, PARAM_BATCH_WORLD, PARAM_GRAPH, PARAM_GRAPH_REPLAYS, PARAM_STRIP_MAX_GHOSTS,
  PARAM_STRIP_MAX_MIGRANTS, PARAM_CROWDED, PARAM_POOL, PARAM_POOL_MIN, PARAM_STRIP_P2P, PARAM_LIST, PARAM_SKIN, PARAM_LIST_REBUILDS,
- PARAM_LIST_SUBSTEPS) = range(27)
+ PARAM_LIST_SUBSTEPS, PARAM_LIST_ACTIVE) = range(28)
 
 # body field mask
 BODY_POSITION = 1 << 0

@@ -11,6 +11,12 @@
 
 #include "types.cuh"
 
+#ifdef BLOBS_EMU   // host-compiled test build: libstdc++ spells the attribute __noinline__ itself, so no macro of that name
+#define BLOBS_NOINLINE __attribute__((noinline))
+#else
+#define BLOBS_NOINLINE __noinline__
+#endif
+
 namespace blobs {
 
 // ------------------------------------------------------------------------------------------------
@@ -373,92 +379,62 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-pooled contact resolution (k_main<POOLED>), for contact-rich states. The per-lane resolve loop of gather_single runs
-// at the pace of the lane with the most contacts (measured in the compressed cfg2 pile: 7 of 32 lanes active on average,
-// and the sorted-insert loop - local memory - is the top hotspot). Here the warp pools the prefilter survivors of all its
-// bodies in shared memory, the exact narrowphase runs one (body, candidate) PAIR per lane (full lanes, the owner's collider
-// is fetched by shuffle), and the ordering is a rank computation inside each owner's segment instead of a sorted insert:
-//   scan (per lane, as before, <= 64 candidates -> two 32-bit survivor masks) -> warp prefix sum -> survivor queue ->
-//   pooled narrowphase -> rank of every contribution among its owner's -> owner adds its contributions in rank order.
-// Same arithmetic, same summation order (ascending partner slot) as the list path. Bodies with more than 64 candidates or
-// a non-trivial cell range keep the per-lane path; an owner that meets a coincident pair (distance < 1e-6: two contributions
-// per pair) redoes its sum with the serial windowed rescan. Batches of at most POOL_Q survivors: a warp with more is
-// processed as several lane ranges.
+// Warp-cooperative contact resolution (k_main<POOLED>), for agitated / contact-rich states. Measured on config #2 once the
+// block has hit the circle constraint (profiles/r2_dense_ncu.md): the reference's positional solver turns the pile into a hot
+// gas - bodies move several diameters per substep, so slot order says nothing about position any more - with clusters where a
+// body has 60+ candidates next to bodies with 5. One thread per body then runs at the pace of the busiest lane: 8 of 32 lanes
+// active in the candidate scan, 12 of 32 overall, and the ordered insert into a per-thread list lives in local memory.
+// Here the warp shares ALL the work of its 32 bodies:
+//   1. every lane looks up its three row spans (six table loads) and publishes its collider + spans in shared memory;
+//   2. the candidates of all lanes are flattened into one sequence (prefix sum of the span lengths) and scanned 64 per
+//      iteration, one candidate per lane and step: owner found by binary search in the prefix array, squared-distance prefilter
+//      (no sqrt / divide), survivors appended to a per-warp queue in sequence order (ballot + popc), which keeps every owner's
+//      survivors contiguous;
+//   3. exact narrowphase, one (owner, candidate) PAIR per lane; pair counting / recording happens here;
+//   4. ordering = RANK of each contribution among its owner's (keys are unique), written as a permutation;
+//   5. each owner adds its contributions in rank order = ascending partner slot = the reference's pair-loop order.
+// Same arithmetic, same summation order as the per-lane path => bit-identical. Lanes are batched so that the candidates of a
+// batch fit the queue (COOP_Q); a body with more candidates than that (the shell the circle constraint builds) goes to
+// k_crowded, or - when that kernel is not in the pipeline - through the per-lane path. An owner that meets a coincident pair
+// (distance < 1e-6: two contributions per pair, physics.rs:272-286) redoes its sum with the serial windowed rescan.
 // ------------------------------------------------------------------------------------------------
-constexpr int POOL_Q = 256;
+constexpr int COOP_Q = 256;
 constexpr uint32_t POOL_NONE = 0xffffffffu;
-constexpr uint32_t POOL_BIG_MIN = 128u;   // candidates above which a body is handed to k_crowded without a per-lane scan
 
-struct PoolSmem {                 // per warp
-    uint32_t key[POOL_Q];         // record index, then the contribution key (POOL_NONE = contributes nothing)
-    float cx[POOL_Q], cy[POOL_Q];
-    uint16_t perm[POOL_Q];        // perm[segment start + rank] = entry
-    uint8_t owner[POOL_Q];        // lane that owns the entry
+struct CoopSmem {                 // per warp
+    float4 sa[32];                // the lanes' own colliders: x, y, r, parent mass
+    uint4 sb[32];                 //                           memberships, filter, body slot, collider slot | sensor << 31
+    uint32_t lo[3][32];           // first record of each row span
+    uint32_t c1[32], c2[32];      // candidates in span 0, in spans 0 + 1
+    uint32_t pre[33];             // exclusive prefix of the lanes' candidate totals (lanes outside the batch: their batch-relative bound)
+    uint32_t key[COOP_Q];         // survivor: record index, then the contribution key (POOL_NONE = contributes nothing)
+    float cx[COOP_Q], cy[COOP_Q];
+    uint16_t perm[COOP_Q];        // perm[segment start + rank] = entry
+    uint8_t owner[COOP_Q];        // lane that owns the entry
+    uint32_t seg[33];             // first queue entry of each owner lane
     uint32_t nvalid[32];          // contributions per owner lane
     uint32_t fb;                  // owner lanes that must fall back to the serial rescan
 };
 
-// Where the pooled path reads hot record halves from: the cell-sorted array in global memory.
-struct GlobalHot {
-    const float4* hot;
-    __device__ __forceinline__ float4 operator()(uint32_t k) const { return __ldg(hot + k); }
-};
 __device__ __forceinline__ Rec rec_of(const float4 h, const uint4* __restrict__ ccold) {
     const uint32_t w = __float_as_uint(h.w);
     if (w & HOT_COLD_BIT) return make_rec(h, __ldg(ccold + (w & HOT_SLOT_MASK)));
     return make_rec(h, make_uint4(__float_as_uint(fmul(4.0f, h.z)), 0xffffffffu, 0xffffffffu, NO_SLOT));   // default sphere, see load_rec
 }
 
-template <int BATCH, class SRC>
-__device__ __forceinline__ uint32_t scan_chunk(const SRC& src, const SelfCol& s, float srk, uint32_t base, uint32_t total, uint32_t n0,
-                                               uint32_t n01, uint32_t off0, uint32_t off1, uint32_t off2, uint32_t lo0) {
-    const uint32_t lim = min(32u, total - base);
-    uint32_t mask = 0;
-    for (uint32_t t0 = 0; t0 < lim; t0 += BATCH) {
-        float4 h[BATCH];
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-            const uint32_t t = base + t0 + i;
-            const uint32_t k = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-            h[i] = src(t0 + i < lim ? k : lo0);
-        }
-#pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
-            const uint32_t oslot = __float_as_uint(h[i].w) & HOT_SLOT_MASK;
-            const float dx = s.x - h[i].x, dy = s.y - h[i].y;
-            const float d2 = __fmaf_rn(dx, dx, dy * dy);
-            const float mdk = __fmaf_rn(h[i].z, 1.00005f, srk);
-            if (t0 + i < lim && oslot != s.slot && !(d2 > mdk * mdk)) mask |= 1u << (t0 + i);
-        }
-    }
-    return mask;
-}
-
 // Must be called by all 32 lanes of the warp (valid = this lane has a collider to resolve). Returns true when the lane's
 // contributions were added to (px, py) here; false when they are in `list` (per-lane path), to be applied by the caller -
 // unless `big` comes back set (only with defer_big): then nothing was done for this lane, not even pair counting.
-// The candidate span of one lane as the pooled path sees it: three row spans flattened into t = 0 .. total-1, record index
-// (in whatever SRC addresses) = t + (t < n0 ? off0 : t < n01 ? off1 : off2).
-struct LaneSpan {
-    bool fits;     // <= 64 candidates in a plain 3-row range: this lane takes part in the pooled resolution
-    bool ranged;   // plain 3-row range, `total` is known
-    uint32_t lo0, n0, n01, total, off0, off1, off2;
-};
-
-template <int BATCH, class SRC>
-__device__ __forceinline__ bool gather_warp_core(const GridDesc& g, const Broadphase& bp, const SRC& src, const uint4* __restrict__ ccold, bool valid,
-                                                 const SelfCol& s, const LaneSpan& L, ContactList<uint32_t>& list, GatherOut& out,
-                                                 const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats, PoolSmem& ps,
-                                                 uint32_t pool_min, bool defer_big, bool& big, float& px, float& py);
-
 template <int BATCH>
-__device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, bool valid, const SelfCol& s,
+__device__ __forceinline__ bool gather_coop(const GridDesc& g, const Broadphase& bp, const uint4* __restrict__ ccold, bool valid, const SelfCol& s,
                                             ContactList<uint32_t>& list, GatherOut& out, const Recording& rec, const float2* __restrict__ vel,
-                                            DeviceStats* stats, PoolSmem& ps, uint32_t pool_min, bool defer_big, bool& big, float& px,
-                                            float& py) {
-    LaneSpan L;
-    L.fits = L.ranged = false;
-    L.lo0 = L.n0 = L.n01 = L.total = L.off0 = L.off1 = L.off2 = 0u;
+                                            DeviceStats* stats, CoopSmem& ps, bool defer_big, bool& big, float& px, float& py) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    big = false;
+    const uint32_t lane = threadIdx.x & 31u;
+    // ---- 1. spans -------------------------------------------------------------------------------------------------
+    bool plain = false;
+    uint32_t lo0 = 0, lo1 = 0, lo2 = 0, n0 = 0, n01 = 0, total = 0;
     if (valid) {
         const CellRange R = cell_range(g, s.x, s.y, s.r);
         if (!(R.ny > 3u || R.c0 + R.nx > g.W)) {
@@ -473,155 +449,162 @@ __device__ __forceinline__ bool gather_warp(const GridDesc& g, const Broadphase&
                 lo[j] = a;
                 cnt[j] = b - a;
             }
-            L.n0 = cnt[0]; L.n01 = cnt[0] + cnt[1]; L.total = L.n01 + cnt[2];
-            L.off0 = lo[0]; L.off1 = lo[1] - L.n0; L.off2 = lo[2] - L.n01; L.lo0 = lo[0];
-            L.ranged = true;
-            L.fits = L.total <= 64u;
+            lo0 = lo[0]; lo1 = lo[1]; lo2 = lo[2];
+            n0 = cnt[0]; n01 = cnt[0] + cnt[1]; total = n01 + cnt[2];
+            plain = true;
         }
     }
-    const GlobalHot src{bp.hot};
-    return gather_warp_core<BATCH>(g, bp, src, ccold, valid, s, L, list, out, rec, vel, stats, ps, pool_min, defer_big, big, px, py);
-}
-
-template <int BATCH, class SRC>
-__device__ __forceinline__ bool gather_warp_core(const GridDesc& g, const Broadphase& bp, const SRC& src, const uint4* __restrict__ ccold, bool valid,
-                                                 const SelfCol& s, const LaneSpan& L, ContactList<uint32_t>& list, GatherOut& out,
-                                                 const Recording& rec, const float2* __restrict__ vel, DeviceStats* stats, PoolSmem& ps,
-                                                 uint32_t pool_min, bool defer_big, bool& big, float& px, float& py) {
-    constexpr uint32_t FULL = 0xffffffffu;
-    big = false;
-    const uint32_t lane = threadIdx.x & 31u;
-    const bool fits = L.fits, ranged = L.ranged;
-    const uint32_t lo0 = L.lo0, n0 = L.n0, n01 = L.n01, total = L.total, off0 = L.off0, off1 = L.off1, off2 = L.off2;
-    const float srk = s.r * 1.00005f;
-    uint32_t m0 = 0, m1 = 0;
-    if (fits) {
-        if (total) m0 = scan_chunk<BATCH>(src, s, srk, 0u, total, n0, n01, off0, off1, off2, lo0);
-        if (total > 32u) m1 = scan_chunk<BATCH>(src, s, srk, 32u, total, n0, n01, off0, off1, off2, lo0);
-    }
-    const uint32_t c = (uint32_t)(__popc(m0) + __popc(m1));
-    const uint32_t T = __reduce_add_sync(FULL, c);
-    bool applied = false;
-    if (T >= pool_min) {   // warp-uniform
-        uint32_t incl = c;
+    const bool coop = plain && total <= (uint32_t)COOP_Q;
+    const uint32_t tc = coop ? total : 0u;
+    ps.sa[lane] = make_float4(s.x, s.y, s.r, s.m);
+    ps.sb[lane] = make_uint4(s.memb, s.filt, s.body, s.slot | (s.sensor ? HOT_SENSOR_BIT : 0u));
+    ps.lo[0][lane] = lo0; ps.lo[1][lane] = lo1; ps.lo[2][lane] = lo2;
+    ps.c1[lane] = n0; ps.c2[lane] = n01;
+    ps.nvalid[lane] = 0u;
+    if (lane == 0) ps.fb = 0u;
+    uint32_t incl = tc;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, incl, d);
-            if (lane >= (uint32_t)d) incl += t;
-        }
-        const uint32_t seg1g = incl, seg0g = incl - c;   // this lane's survivor range in the warp-wide sequence
-        const uint32_t sflag = s.slot | (s.sensor ? HOT_SENSOR_BIT : 0u);
-        ps.nvalid[lane] = 0u;
-        if (lane == 0) ps.fb = 0u;
-        uint32_t start = 0;
-        while (start < 32u) {   // lane ranges [start, end) whose survivors fit the queue
-            const uint32_t base = __shfl_sync(FULL, seg0g, start);
-            const bool in_batch = lane >= start && (seg1g - base) <= (uint32_t)POOL_Q;
-            const uint32_t bal = __ballot_sync(FULL, in_batch);
-            const uint32_t zeros = ~bal & (FULL << start);
-            const uint32_t end = zeros ? (uint32_t)__ffs(zeros) - 1u : 32u;   // > start: one lane never exceeds 64 <= POOL_Q
-            const bool mine = fits && lane >= start && lane < end;
-            const uint32_t Tb = __shfl_sync(FULL, seg1g, end - 1u) - base;
-            const uint32_t seg0 = seg0g - base;
-            __syncwarp();
-            if (mine) {
-                uint32_t w = seg0;
-                for (uint32_t m = m0; m; m &= m - 1u) {
-                    const uint32_t t = (uint32_t)__ffs(m) - 1u;
-                    ps.key[w] = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-                    ps.owner[w] = (uint8_t)lane;
-                    ++w;
-                }
-                for (uint32_t m = m1; m; m &= m - 1u) {
-                    const uint32_t t = 32u + (uint32_t)__ffs(m) - 1u;
-                    ps.key[w] = t + (t < n0 ? off0 : (t < n01 ? off1 : off2));
-                    ps.owner[w] = (uint8_t)lane;
-                    ++w;
-                }
-            }
-            __syncwarp();
-            // exact narrowphase, one (owner, candidate) pair per lane
-            for (uint32_t i0 = 0; i0 < Tb; i0 += 32u) {
-                const uint32_t i = i0 + lane;
-                const bool act = i < Tb;
-                const uint32_t o = act ? (uint32_t)ps.owner[i] : lane;
-                SelfCol so;
-                so.x = __shfl_sync(FULL, s.x, o); so.y = __shfl_sync(FULL, s.y, o); so.r = __shfl_sync(FULL, s.r, o);
-                so.m = __shfl_sync(FULL, s.m, o); so.memb = __shfl_sync(FULL, s.memb, o); so.filt = __shfl_sync(FULL, s.filt, o);
-                so.body = __shfl_sync(FULL, s.body, o);
-                const uint32_t sf = __shfl_sync(FULL, sflag, o);
-                so.slot = sf & HOT_SLOT_MASK; so.sensor = (sf & HOT_SENSOR_BIT) != 0u; so.wbase = 0u; so.qx = so.x; so.qy = so.y;
-                if (act) {
-                    const Rec r = rec_of(src(ps.key[i]), ccold);
-                    Contact ct;
-                    uint32_t key = POOL_NONE;
-                    if (narrowphase(so, r, ct)) {
-                        note_pair(so, r, ct, out, rec, vel, stats);
-                        if (ct.coincident) {
-                            atomicOr(&ps.fb, 1u << o);
-                        } else if (ct.push) {
-                            key = pair_key<uint32_t>(so.slot, ct.other, false);
-                            ps.cx[i] = ct.cx;
-                            ps.cy[i] = ct.cy;
-                            atomicAdd(&ps.nvalid[o], 1u);
-                        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t excl = incl - tc;
+    bool applied = false;
+    uint32_t start = 0;
+    while (start < 32u) {   // lane ranges [start, end) whose candidates fit the queue
+        const uint32_t base = __shfl_sync(FULL, excl, start);
+        const bool in_batch = lane >= start && (incl - base) <= (uint32_t)COOP_Q;
+        const uint32_t bal = __ballot_sync(FULL, in_batch);
+        const uint32_t zeros = ~bal & (FULL << start);
+        const uint32_t end = zeros ? (uint32_t)__ffs(zeros) - 1u : 32u;   // > start: one cooperative lane never exceeds COOP_Q
+        const uint32_t C = __shfl_sync(FULL, incl, end - 1u) - base;      // candidates of this batch
+        const bool mine = coop && lane >= start && lane < end;
+        __syncwarp();
+        // batch-relative exclusive prefix; lanes after the batch carry C so that the binary search never selects them
+        ps.pre[lane] = lane < start ? 0u : (lane < end ? excl - base : C);
+        if (lane == 0) ps.pre[32] = C;
+        __syncwarp();
+        // ---- 2. cooperative scan: candidate i of the batch belongs to the lane l with pre[l] <= i < pre[l + 1] -----------
+        uint32_t qn = 0;   // warp-uniform queue length
+        for (uint32_t i0 = 0; i0 < C; i0 += 32u * BATCH) {
+            float4 h[BATCH];
+            uint32_t kk[BATCH], own[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const uint32_t i = i0 + 32u * u + lane;
+                uint32_t l = start;
+                if (i < C) {   // largest l in [start, end) with pre[l] <= i (lanes with no candidates share their successor's prefix)
+                    uint32_t a = start, b = end;   // invariant: pre[a] <= i, answer in [a, b)
+                    while (b - a > 1u) {
+                        const uint32_t m = (a + b) >> 1;
+                        if (ps.pre[m] <= i) a = m; else b = m;
                     }
-                    ps.key[i] = key;
+                    l = a;
                 }
+                const uint32_t t = i < C ? i - ps.pre[l] : 0u;
+                const uint32_t c1 = ps.c1[l], c2 = ps.c2[l];
+                kk[u] = t < c1 ? ps.lo[0][l] + t : (t < c2 ? ps.lo[1][l] + (t - c1) : ps.lo[2][l] + (t - c2));
+                own[u] = l;
+                h[u] = __ldg(bp.hot + (i < C ? kk[u] : 0u));   // (index 0 always exists: the arrays are padded by one record)
             }
-            __syncwarp();
-            // rank of every contribution inside its owner's segment
-            for (uint32_t i0 = 0; i0 < Tb; i0 += 32u) {
-                const uint32_t i = i0 + lane;
-                const bool act = i < Tb;
-                const uint32_t o = act ? (uint32_t)ps.owner[i] : lane;
-                const uint32_t a = __shfl_sync(FULL, seg0, o), b = __shfl_sync(FULL, seg0 + c, o);
-                if (act) {
-                    const uint32_t key = ps.key[i];
-                    if (key != POOL_NONE) {
-                        uint32_t rank = 0;
-                        for (uint32_t j = a; j < b; ++j) rank += ps.key[j] < key ? 1u : 0u;
-                        ps.perm[a + rank] = (uint16_t)i;
-                    }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const uint32_t i = i0 + 32u * u + lane;
+                const float4 a = ps.sa[own[u]];
+                const uint32_t oslot = __float_as_uint(h[u].w) & HOT_SLOT_MASK;
+                const float dx = a.x - h[u].x, dy = a.y - h[u].y;
+                const float d2 = __fmaf_rn(dx, dx, dy * dy);
+                const float mdk = (a.z + h[u].z) * 1.00005f;   // prefilter, see gather_single
+                const bool pass = i < C && oslot != (ps.sb[own[u]].w & HOT_SLOT_MASK) && !(d2 > mdk * mdk);
+                const uint32_t bl = __ballot_sync(FULL, pass);
+                if (pass) {
+                    const uint32_t w = qn + (uint32_t)__popc(bl & ((1u << lane) - 1u));
+                    ps.key[w] = kk[u];
+                    ps.owner[w] = (uint8_t)own[u];
                 }
+                qn += (uint32_t)__popc(bl);
             }
-            __syncwarp();
-            if (mine) {
-                applied = true;
-                if (!((ps.fb >> lane) & 1u)) {
-                    const uint32_t nv = ps.nvalid[lane];
-                    for (uint32_t r = 0; r < nv; ++r) {
-                        const uint32_t e = ps.perm[seg0 + r];
-                        px = fadd(px, ps.cx[e]);
-                        py = fadd(py, ps.cy[e]);
-                    }
-                }
-            }
-            start = end;
         }
         __syncwarp();
-        if (applied && ((ps.fb >> lane) & 1u)) {   // coincident pair seen: exact serial path (pairs were already counted)
-            SelfCol s2 = s;
-            const float2 q = apply_contacts_rescan(g, bp, ccold, &s2, 1, px, py);
-            px = q.x;
-            py = q.y;
+        // first queue entry of every owner (the queue is in candidate order, so an owner's entries are contiguous): every entry
+        // that starts a new owner run records where the run starts
+        for (uint32_t i0 = 0; i0 < qn; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            const uint32_t o = i < qn ? (uint32_t)ps.owner[i] : 0xffu;
+            const uint32_t prev = __shfl_up_sync(FULL, o, 1);
+            const uint32_t before = lane == 0u ? (i0 ? (uint32_t)ps.owner[i0 - 1u] : 0xfeu) : prev;
+            if (i < qn && o != before) ps.seg[o] = i;
         }
-    } else if (fits) {   // few survivors in the whole warp: per-lane resolve straight from the masks
-        for (uint32_t m = m0; m; m &= m - 1u) {
-            const uint32_t t = (uint32_t)__ffs(m) - 1u;
-            take_candidate<true, uint32_t>(s, rec_of(src(t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), ccold), list, out, rec, vel, stats);
+        __syncwarp();
+        // ---- 3. exact narrowphase, one (owner, candidate) pair per lane ---------------------------------------------------
+        for (uint32_t i0 = 0; i0 < qn; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            if (i < qn) {
+                const uint32_t o = (uint32_t)ps.owner[i];
+                const float4 a = ps.sa[o];
+                const uint4 bb = ps.sb[o];
+                SelfCol so;
+                so.x = so.qx = a.x; so.y = so.qy = a.y; so.r = a.z; so.m = a.w;
+                so.memb = bb.x; so.filt = bb.y; so.body = bb.z; so.slot = bb.w & HOT_SLOT_MASK; so.sensor = (bb.w & HOT_SENSOR_BIT) != 0u; so.wbase = 0u;
+                const Rec r = rec_of(__ldg(bp.hot + ps.key[i]), ccold);
+                Contact ct;
+                uint32_t key = POOL_NONE;
+                if (narrowphase(so, r, ct)) {
+                    note_pair(so, r, ct, out, rec, vel, stats);
+                    if (ct.coincident) {
+                        atomicOr(&ps.fb, 1u << o);
+                    } else if (ct.push) {
+                        key = pair_key<uint32_t>(so.slot, ct.other, false);
+                        ps.cx[i] = ct.cx;
+                        ps.cy[i] = ct.cy;
+                        atomicAdd(&ps.nvalid[o], 1u);
+                    }
+                }
+                ps.key[i] = key;
+            }
         }
-        for (uint32_t m = m1; m; m &= m - 1u) {
-            const uint32_t t = 32u + (uint32_t)__ffs(m) - 1u;
-            take_candidate<true, uint32_t>(s, rec_of(src(t + (t < n0 ? off0 : (t < n01 ? off1 : off2))), ccold), list, out, rec, vel, stats);
+        __syncwarp();
+        // ---- 4. rank of every contribution inside its owner's run -----------------------------------------------------------
+        for (uint32_t i0 = 0; i0 < qn; i0 += 32u) {
+            const uint32_t i = i0 + lane;
+            if (i < qn) {
+                const uint32_t key = ps.key[i];
+                if (key != POOL_NONE) {
+                    const uint32_t o = (uint32_t)ps.owner[i];
+                    const uint32_t a = ps.seg[o];
+                    uint32_t rank = 0;
+                    for (uint32_t j = a; j < qn && (uint32_t)ps.owner[j] == o; ++j) rank += ps.key[j] < key ? 1u : 0u;
+                    ps.perm[a + rank] = (uint16_t)i;
+                }
+            }
         }
+        __syncwarp();
+        // ---- 5. every owner adds its contributions in rank order ---------------------------------------------------------
+        if (mine) {
+            applied = true;
+            if (!((ps.fb >> lane) & 1u)) {
+                const uint32_t nv = ps.nvalid[lane], a = ps.seg[lane];
+                for (uint32_t r = 0; r < nv; ++r) {
+                    const uint32_t e = ps.perm[a + r];
+                    px = fadd(px, ps.cx[e]);
+                    py = fadd(py, ps.cy[e]);
+                }
+            }
+        }
+        start = end;
     }
-    if (valid && !fits) {   // more than 64 candidates (or a wrapped / tall cell range)
-        // really big neighbourhoods (the boundary shell of cfg2: hundreds of candidates) go to k_crowded unscanned - a
-        // warp-wide scan beats a per-lane one; moderately big ones (cfg3's compressed piles: 65-128 candidates, few contacts)
-        // stay per-lane, where they measured faster
-        if (defer_big && !(ranged && total <= POOL_BIG_MIN)) big = true;
-        else gather_single<true, uint32_t, BATCH>(g, bp, ccold, s, list, out, rec, vel, stats);
+    __syncwarp();
+    if (applied && ((ps.fb >> lane) & 1u)) {   // coincident pair seen: exact serial path (pairs were already counted)
+        SelfCol s2 = s;
+        const float2 q = apply_contacts_rescan(g, bp, ccold, &s2, 1, px, py);
+        px = q.x;
+        py = q.y;
+    }
+    if (valid && !coop) {   // wrapped / tall cell range, or more candidates than the queue holds
+        // really big neighbourhoods (the boundary shell of cfg2: hundreds of candidates) go to k_crowded unscanned - a whole warp
+        // per body beats one lane
+        if (defer_big && plain) big = true;
+        else gather_single<true, uint32_t, 4>(g, bp, ccold, s, list, out, rec, vel, stats);
     }
     return applied;
 }
@@ -779,7 +762,7 @@ __device__ __forceinline__ float2 publish_collider(const GridDesc& g, const Coll
 // list pipeline: kernels that walk the cell grid (k_multi, k_crowded) use the tables of the last rebuild
 __device__ __forceinline__ Broadphase resolve_grid(Broadphase bp) {
     if (bp.nl.snap_next != nullptr) {
-        bp.tab = bp.nl.tab[bp.nl.ctl->parity & 1u];
+        bp.tab = (bp.nl.ctl->parity & 1u) ? bp.nl.tab[1] : bp.nl.tab[0];
         bp.hot = bp.nl.hot;
         bp.snap = bp.nl.snap_cur;
     }
@@ -834,7 +817,7 @@ __device__ __forceinline__ void strip_pack_one(const BodyArrays& B, const Collid
 template <bool FUSED, bool ORDERED, int BATCH, int MINB, bool POOLED, int THREADS = 256>
 __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc,
                                               Broadphase bp, Recording rec, DeviceStats* stats, StripView sv) {
-    __shared__ PoolSmem pool[POOLED ? THREADS / 32 : 1];
+    __shared__ CoopSmem pool[POOLED ? THREADS / 32 : 1];
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     GatherOut out;
     out.fx = out.fy = 0.f;
@@ -941,8 +924,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
             list.clear();
             bool applied = false, big = false;
             if (POOLED) {   // warp-collective: every lane calls
-                applied = gather_warp<BATCH>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.pool_min,
-                                             P.crowded != 0u, big, p.x, p.y);
+                applied = gather_coop<2>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.crowded != 0u, big, p.x, p.y);
             } else if (do_gather) {
                 gather_single<true, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }

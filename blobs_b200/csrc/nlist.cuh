@@ -15,11 +15,12 @@
 // which walks the cell grid of the last rebuild instead of a list.
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_nl_decide: one thread, first launch of every substep. Decides whether the lists are rebuilt before this substep's contact
-// pass, predicts the common displacement c the publishers will subtract, and resets the accumulators.
+// The decision: are the lists rebuilt before the coming substep's contact pass? Also predicts the common displacement c the
+// publishers will subtract and resets the accumulators. Taken by the last CTA of k_step when that kernel is the substep's only
+// publisher (SubstepParams::nl_tail_decide), else by the one-thread kernel k_nl_decide at the start of the substep; the first
+// substep of every step call always runs k_nl_decide, which is also where a host request (NlCtl::force) is honoured.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step) {
-    if (threadIdx.x != 0u || blockIdx.x != 0u) return;
+__device__ __forceinline__ void nl_decide(volatile NlCtl* ctl, float lim, uint32_t in_step) {
     const float m = __uint_as_float(ctl->max_m);
     const unsigned int need = (ctl->force != 0u || !(m <= lim)) ? 1u : 0u;
     const unsigned int n = ctl->n_sum;
@@ -45,6 +46,29 @@ __global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_
     ctl->substeps += in_step;
 }
 
+__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step) {
+    if (threadIdx.x != 0u || blockIdx.x != 0u) return;
+    if (ctl->decided) {   // k_step's last CTA has decided already; only a host request can still change the verdict
+        ctl->decided = 0u;
+        if (ctl->force) {
+            ctl->force = 0u;
+            if (!ctl->need) {
+                ctl->need = 1u;
+                ctl->cx -= ctl->mean_x; ctl->cy -= ctl->mean_y;   // the references are about to move to the current snapshots
+                ctl->mean_x = 0.f; ctl->mean_y = 0.f;
+                ctl->rebuilds += in_step;
+            }
+        }
+        return;
+    }
+    nl_decide(ctl, lim, in_step);
+}
+
+// the two tables are picked by ternaries (a runtime index into a kernel-parameter array would copy the struct to local memory)
+__device__ __forceinline__ uint32_t* nl_tab(const NlView& L, uint32_t which) { return which ? L.tab[1] : L.tab[0]; }
+__device__ __forceinline__ uint32_t* nl_tile(const NlView& L, uint32_t which) { return which ? L.tile[1] : L.tile[0]; }
+constexpr unsigned NL_GATED_CTAS = 148 * 8;   // the gated kernels run grid-stride loops on a fixed grid: returning at once costs ~2 us
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Rebuild, step 1-3: counting sort of the current snapshots into cells (the grid pipeline's k_count / k_scan / k_scatter, gated
 // by the device flag and addressing the table pair by the device parity).
@@ -53,41 +77,42 @@ __global__ void __launch_bounds__(256) k_nl_count(GridDesc g, ColliderArrays Cc,
                                                   const uint8_t* __restrict__ cowned) {
     if (L.ctl->need == 0u) return;
     const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_colliders) return;
-    if (cowned != nullptr && !cowned[c]) return;
-    if (!(Cc.cconst[c].y & CF_ACTIVE)) return;
-    const float2 a = Cc.cabs[c];
-    const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
-    const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
-    Cc.ccell[c] = make_uint2(cell, bin_collider(L.tab[nx], L.tile[nx], cell));
+    uint32_t* const tab_next = nl_tab(L, nx);
+    uint32_t* const tile_next = nl_tile(L, nx);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
+        if (cowned != nullptr && !cowned[c]) continue;
+        if (!(Cc.cconst[c].y & CF_ACTIVE)) continue;
+        const float2 a = Cc.cabs[c];
+        const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
+        const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
+        Cc.ccell[c] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_nl_scan(NlView L, uint32_t n) {
     if (L.ctl->need == 0u) return;
     const uint32_t cur = L.ctl->parity & 1u, nx = cur ^ 1u;
     // the table of the previous rebuild is zeroed on the way: it takes the counts of the NEXT rebuild
-    scan_tile(L.tab[nx], n, L.tab[cur], n, L.tile[nx], L.tile[cur]);
+    scan_tile(nl_tab(L, nx), n, nl_tab(L, cur), n, nl_tile(L, nx), nl_tile(L, cur));
 }
 
 __global__ void __launch_bounds__(256) k_nl_scatter(ColliderArrays Cc, NlView L, uint32_t n_colliders, const uint8_t* __restrict__ cowned) {
     if (L.ctl->need == 0u) return;
-    const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_colliders) return;
-    if (cowned != nullptr && !cowned[c]) return;
-    const uint4 cc = Cc.cconst[c];
-    const uint2 cr = Cc.ccell[c];
-    const float2 a = Cc.cabs[c];
-    if (!(cc.y & CF_ACTIVE)) return;
-    const uint32_t dst = __ldg(L.tab[nx] + cr.x) + cr.y;
-    L.hot[dst] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(hot_word(c, cc.y)));
+    const uint32_t* __restrict__ tab = nl_tab(L, (L.ctl->parity & 1u) ^ 1u);
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
+        if (cowned != nullptr && !cowned[c]) continue;
+        const uint4 cc = Cc.cconst[c];
+        if (!(cc.y & CF_ACTIVE)) continue;
+        const uint2 cr = Cc.ccell[c];
+        const float2 a = Cc.cabs[c];
+        L.hot[__ldg(tab + cr.x) + cr.y] = make_float4(a.x, a.y, __uint_as_float(cc.x), __uint_as_float(hot_word(c, cc.y)));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Rebuild, step 4: one thread per collider slot walks the cells within r + r_max + skin of its snapshot (g.rmax is inflated by
-// the skin on the host) and keeps every collider closer than r_a + r_b + skin, sorted by slot (rank by counting: slots are
-// unique), in the transposed list array. Also (re)writes the slot-indexed snapshot record the next contact pass reads, and the
+// the skin on the host) and keeps every collider closer than r_a + r_b + skin, sorted by slot (sorted insert into a
+// shared-memory column), in the transposed list array. Also (re)writes the slot-indexed snapshot record the next contact pass reads, and the
 // reference position the displacement tracking measures from. The last CTA to finish flips the table parity.
 // The keep test is deliberately loose (1e-4 relative): it only has to err on the side of keeping.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -100,11 +125,10 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
     NlCtl* const ctl = L.ctl;
     if (ctl->need == 0u) return;   // grid-uniform
     const uint32_t nx = (ctl->parity & 1u) ^ 1u;
-    const uint32_t* __restrict__ tab = L.tab[nx];
+    const uint32_t* __restrict__ tab = nl_tab(L, nx);
     const float4* __restrict__ hot = L.hot;
     const uint32_t tid = threadIdx.x;
-    const uint32_t c = blockIdx.x * (uint32_t)NL_BUILD_THREADS + tid;
-    if (c < n_colliders) {
+    for (uint32_t c = blockIdx.x * (uint32_t)NL_BUILD_THREADS + tid; c < n_colliders; c += gridDim.x * (uint32_t)NL_BUILD_THREADS) {
         const uint4 cc = Cc.cconst[c];
         uint4 hd = make_uint4(0u, 0u, NL_INACTIVE, cc.y);
         if ((cc.y & CF_ACTIVE) && (cowned == nullptr || cowned[c])) {
@@ -120,7 +144,14 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
                 const float d2 = dx * dx + dy * dy;
                 const float cut = (rs + h.z) * 1.0001f;
                 if (oslot != c && !(d2 > cut * cut)) {   // NaNs are kept
-                    if (n < (uint32_t)NL_CAP) keep[n * NL_BUILD_THREADS + tid] = oslot;
+                    if (n < (uint32_t)NL_CAP) {          // sorted insert into this thread's shared-memory column
+                        uint32_t i = n;
+                        while (i > 0u && keep[(i - 1u) * NL_BUILD_THREADS + tid] > oslot) {
+                            keep[i * NL_BUILD_THREADS + tid] = keep[(i - 1u) * NL_BUILD_THREADS + tid];
+                            --i;
+                        }
+                        keep[i * NL_BUILD_THREADS + tid] = oslot;
+                    }
                     ++n;
                 }
             };
@@ -142,12 +173,7 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
             uint32_t cnt = NL_OVER;
             if (n <= (uint32_t)NL_CAP) {
                 cnt = n;
-                for (uint32_t i = 0; i < n; ++i) {
-                    const uint32_t v = keep[i * NL_BUILD_THREADS + tid];
-                    uint32_t rank = 0;
-                    for (uint32_t q = 0; q < n; ++q) rank += keep[q * NL_BUILD_THREADS + tid] < v ? 1u : 0u;
-                    L.idx[(size_t)rank * L.stride + c] = v;
-                }
+                for (uint32_t i = 0; i < n; ++i) L.idx[(size_t)i * L.stride + c] = keep[i * NL_BUILD_THREADS + tid];
             }
             hd = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), cnt, cc.y);
         }
@@ -179,8 +205,19 @@ __device__ __forceinline__ bool nl_prefilter(const SelfCol& s, float srk, const 
     return !(d2 > mdk * mdk);
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(256, 3) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
+// rare path, kept out of line so that its registers and its local-memory window do not weigh on k_step
+__device__ BLOBS_NOINLINE float2 nl_overflow_inline(GridDesc g, Broadphase bp, const uint4* __restrict__ ccold, SelfCol s, GatherOut& out, Recording rec,
+                                                  const float2* __restrict__ vel, DeviceStats* stats, float2 p) {
+    const Broadphase gb = resolve_grid(bp);
+    for_each_candidate(g, gb, ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
+        Contact ct;
+        if (narrowphase(s, o, ct)) note_pair(s, o, ct, out, rec, vel, stats);
+    });
+    return apply_contacts_rescan(g, gb, ccold, &s, 1, p.x, p.y);
+}
+
+template <bool FUSED, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
                                                  Recording rec, DeviceStats* stats) {
     const NlView& L = bp.nl;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,14 +280,8 @@ __global__ void __launch_bounds__(256, 3) k_step(SubstepParams P, GridDesc g, Co
                         P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
                         deferred = true;
                     } else {             // first sighting (the host adds k_crowded to the pipeline from the next call on): serial, exact
-                        const Broadphase gb = resolve_grid(bp);
                         if (g.n_worlds > 1u) s.wbase = B.bworld[b] * g.ncells;
-                        for_each_candidate(g, gb, Cc.ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
-                            Contact ct;
-                            if (narrowphase(s, o, ct)) note_pair(s, o, ct, out, rec, B.vel, stats);
-                        });
-                        SelfCol s2 = s;
-                        p = apply_contacts_rescan(g, gb, Cc.ccold, &s2, 1, p.x, p.y);
+                        p = nl_overflow_inline(g, bp, Cc.ccold, s, out, rec, B.vel, stats, p);
                     }
                 } else {
                     const uint32_t cnt = hd.z;
@@ -305,6 +336,15 @@ __global__ void __launch_bounds__(256, 3) k_step(SubstepParams P, GridDesc g, Co
         }
     }
     nl_commit(L.ctl, na, &stats->collisions, out.n_pairs);
+    if (P.nl_tail_decide && threadIdx.x == 0u) {   // this kernel is the substep's only publisher: the last CTA decides for the next substep
+        __threadfence();
+        if (atomicAdd(&L.ctl->step_done, 1u) == gridDim.x - 1u) {
+            L.ctl->step_done = 0u;
+            __threadfence();
+            nl_decide(L.ctl, L.lim, 1u);
+            L.ctl->decided = 1u;
+        }
+    }
     if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
         warp_add_u64(&stats->coincident, out.n_coinc);
         unsigned int o = __reduce_add_sync(0xffffffffu, n_over);

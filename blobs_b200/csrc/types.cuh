@@ -93,7 +93,8 @@ struct SubstepParams {
     uint32_t write_vel;             // materialise calculated_velocity this substep
     uint32_t crowded;               // bodies whose contact list overflows are deferred to k_crowded (else resolved inline)
     uint32_t over_parity;           // which DeviceStats::over_count entry this substep appends to
-    uint32_t pool_min;              // k_main<POOLED>: pool a warp's contact resolution when it has at least this many survivors
+    uint32_t pool_min;              // (unused since the cooperative gather; kept for the parameter's ABI)
+    uint32_t nl_tail_decide;        // list pipeline: k_step is this substep's only publisher, so its last CTA decides for the next substep
     uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list
 };
 
@@ -128,7 +129,7 @@ struct ColliderArrays {
 // ---- neighbour-list pipeline: contacts are found from per-collider lists of every collider within
 // r_a + r_b + skin, rebuilt from the cell grid only when the snapshots have moved by more than ~skin/2 since the last build --
 constexpr int NL_CAP = 32;                       // list rows; entry k of collider c sits at idx[k * stride + c] (transposed: coalesced)
-constexpr int NL_SPEC = 8;                       // rows fetched together with the body state (before the count is known)
+constexpr int NL_SPEC = 4;                       // rows fetched together with the body state (before the count is known)
 constexpr uint32_t NL_OVER = 0xffffffffu;        // NlView::hdr[c].z: more than NL_CAP neighbours -> the body goes to k_crowded
 constexpr uint32_t NL_INACTIVE = 0xfffffffeu;    // NlView::hdr[c].z: collider slot is free / parentless / not owned by this rank
 struct NlCtl {                 // device-resident control block
@@ -141,6 +142,8 @@ struct NlCtl {                 // device-resident control block
     float cx, cy;              // common-mode displacement the publishers of this substep subtract (any value is valid: it only decides WHEN lists are rebuilt)
     float mean_x, mean_y;      // sampled mean displacement at the previous decision (0 right after a rebuild)
     unsigned int done;         // CTA arrival counter of k_nl_build
+    unsigned int step_done;    // CTA arrival counter of k_step (its last CTA takes the decision for the next substep)
+    unsigned int decided;      // the decision for the coming substep has been taken already (by k_step's last CTA)
     unsigned long long rebuilds, substeps;   // statistics
 };
 struct NlView {

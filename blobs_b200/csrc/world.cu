@@ -183,7 +183,7 @@ int World::set_param(int id, double v) {
             p2p_request = v != 0;
             break;
         case BLOBS_PARAM_GRAPH: graphs_on = v != 0; break;
-        case BLOBS_PARAM_LIST: list_mode = (int)v; bp_dirty = true; break;
+        case BLOBS_PARAM_LIST: list_mode = (int)v; nl_grid_hold = 0; nl_next_hold = 32; bp_dirty = true; break;
         case BLOBS_PARAM_SKIN:
             if (!(v > 0.0) || !(v <= 16.0)) return fail(BLOBS_ERR_INVALID, "BLOBS_PARAM_SKIN must be in (0, 16] (fraction of the largest collider radius)");
             skin_frac = (float)v; bp_dirty = true;
@@ -222,6 +222,7 @@ int World::get_param(int id, double* out) const {
         case BLOBS_PARAM_BATCH_WORLD: *out = cur_world; break;
         case BLOBS_PARAM_GRAPH: *out = graphs_on; break;
         case BLOBS_PARAM_LIST: *out = list_mode; break;
+        case BLOBS_PARAM_LIST_ACTIVE: *out = nl_on ? 1.0 : 0.0; break;
         case BLOBS_PARAM_SKIN: *out = skin_frac; break;
         case BLOBS_PARAM_LIST_REBUILDS: *out = (double)h_nlctl->rebuilds; break;
         case BLOBS_PARAM_LIST_SUBSTEPS: *out = (double)h_nlctl->substeps; break;
@@ -909,7 +910,7 @@ int World::choose_grid(bool) {
     const size_t nc = cols.slots();
     // list pipeline: the rebuild collects every collider within r_a + r_b + skin, so the search reach (and the cell that keeps it
     // inside a 3x3 neighbourhood) grows by the skin
-    nl_on = list_mode != 0 && !strip_on;
+    nl_on = (list_mode == 1 || (list_mode == 2 && nl_grid_hold == 0)) && !strip_on;
     nl_skin = nl_on ? skin_frac * r_max : 0.f;
     float cs = bp_cell_override > 0.f ? bp_cell_override : (r_max > 0.f ? 2.0f * r_max + nl_skin : 1.0f);
     if (!(cs > 0.f) || !std::isfinite(cs)) cs = 1.0f;
@@ -1023,7 +1024,7 @@ NlView World::nl_view() {
 
 // First launches of every substep in list mode: the decision kernel, then the four rebuild kernels, which return at once unless
 // the decision was "rebuild" (the decision lives on the device, so that captured steps can be replayed).
-int World::nl_rebuild_chain(bool timed_launch) {
+int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     const NlView L = nl_view();
     const ColliderArrays C = col_arrays();
     const uint32_t nc = (uint32_t)cols.slots();
@@ -1035,17 +1036,18 @@ int World::nl_rebuild_chain(bool timed_launch) {
         CU(cudaGetLastError());
         return BLOBS_OK;
     };
-    int rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u); });
+    int rc = BLOBS_OK;
+    if (decide) rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u); });
     if (rc) return rc;
     if (!nc) return BLOBS_OK;
-    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, nullptr); });
+    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, nullptr); });
     if (rc) return rc;
     rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
     if (rc) return rc;
-    rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(cdiv(nc, 256), 256, 0, stream, k_nl_scatter)(C, L, nc, nullptr); });
+    rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, nullptr); });
     if (rc) return rc;
     rc = run(KC_NLBUILD, [&] {
-        BLOBS_LAUNCH(cdiv(nc, NL_BUILD_THREADS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr);
+        BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr);
     });
     return rc;
 }
@@ -1054,7 +1056,7 @@ int World::nl_rebuild_chain(bool timed_launch) {
 int World::nl_rebuild_now() {
     const unsigned int one = 1u;
     CU(cudaMemcpyAsync(&d_nlctl->force, &one, sizeof(one), cudaMemcpyHostToDevice, stream));
-    int rc = nl_rebuild_chain(false);
+    int rc = nl_rebuild_chain(false, true);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_nlctl, d_nlctl, sizeof(NlCtl), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
@@ -1248,8 +1250,11 @@ int World::launch_substep(const SubstepParams& P_in) {
     const uint32_t nb = P.n_bodies;
     int rc;
     if (lists) {   // decide on the device whether the lists are still supersets of the contact set; rebuild them if not
-        rc = nl_rebuild_chain(true);
+        // k_step takes the decision for the NEXT substep itself when nothing else publishes snapshots after it
+        P.nl_tail_decide = (fused && nb && !n_islands && !n_multi && !crowded) ? 1u : 0u;
+        rc = nl_rebuild_chain(true, !nl_prev_tail);
         if (rc) return rc;
+        nl_prev_tail = P.nl_tail_decide != 0u;
     }
     if (n_sb) {
         rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
@@ -1261,8 +1266,10 @@ int World::launch_substep(const SubstepParams& P_in) {
     }
     if (nb && lists) {
         rc = timed(KC_MAIN, [&] {
-            if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true>)(P, grid, K, B, C, bp, R, d_stats);
-            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false>)(P, grid, K, B, C, bp, R, d_stats);
+            // BLOBS_PARAM_TUNE 1: 3 CTAs per SM (85 registers, no spills) instead of 4 (64 registers)
+            if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3>)(P, grid, K, B, C, bp, R, d_stats);
+            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4>)(P, grid, K, B, C, bp, R, d_stats);
+            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4>)(P, grid, K, B, C, bp, R, d_stats);
         });
         if (rc) return rc;
     } else if (nb) {
@@ -1348,8 +1355,10 @@ int World::launch_substep(const SubstepParams& P_in) {
 // Physics::integrate (physics.rs:397-422)
 int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
     const float step_delta = delta / (float)nsub;
+    nl_prev_tail = false;   // the first substep of a call always runs k_nl_decide (host requests are honoured there)
     for (uint32_t i = 0; i < nsub; ++i) {
         SubstepParams P;
+        P.nl_tail_decide = 0u;
         P.dt = step_delta;
         P.ratio_first = step_delta / old_dt;        // physics.rs:338
         P.ratio_rest = step_delta / step_delta;     // every later body sees old_dt == dt (Q2)
@@ -1401,6 +1410,25 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     else if (crowded_hold > 0) crowded_hold--;
     crowded_seen = crowded_hold > 0;
     if (substeps_run) snap_epoch++;
+    // automatic broadphase choice (BLOBS_PARAM_LIST 2): neighbour lists pay while they survive several substeps; when the scene is
+    // so agitated that they are rebuilt (almost) every substep, sorting straight into cells every substep is the cheaper way to the
+    // same contact set. Lists are tried again after a hold that doubles each time they turn out to be still too short-lived.
+    if (list_mode == 2 && !strip_on && substeps_run) {
+        if (nl_on) {
+            const double dr = (double)(h_nlctl->rebuilds - nl_seen_rebuilds), ds = (double)(h_nlctl->substeps - nl_seen_substeps);
+            if (ds > 0 && dr > 0.5 * ds + 1.0) {
+                nl_grid_hold = nl_next_hold;
+                nl_next_hold = std::min(nl_next_hold * 2, 1024);
+                bp_dirty = true;
+            } else if (ds > 0 && dr < 0.25 * ds) {
+                nl_next_hold = 32;
+            }
+        } else if (nl_grid_hold > 0 && --nl_grid_hold == 0) {
+            bp_dirty = true;
+        }
+    }
+    nl_seen_rebuilds = h_nlctl->rebuilds;
+    nl_seen_substeps = h_nlctl->substeps;
     // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep
     if (substeps_run && (double)h_stats->collisions >= 0.25 * (double)substeps_run * (double)std::max<size_t>(bodies.slots(), 1)) pool_hold = 64;
     else if (pool_hold > 0) pool_hold--;

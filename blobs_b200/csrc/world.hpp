@@ -333,7 +333,9 @@ class World {
     bool bb_valid = false;
 
     // neighbour-list pipeline (nlist.cuh): lists of every collider within r_a + r_b + skin, rebuilt on the device's own decision
-    int list_mode = 1;                 // BLOBS_PARAM_LIST: 0 = cell grid rebuilt every substep (k_main), 1 = neighbour lists (k_step)
+    int list_mode = 2;                 // BLOBS_PARAM_LIST: 0 = cell grid rebuilt every substep (k_main), 1 = neighbour lists (k_step), 2 = automatic
+    int nl_grid_hold = 0, nl_next_hold = 32;   // automatic mode: step calls left on the grid pipeline before lists are tried again
+    unsigned long long nl_seen_rebuilds = 0, nl_seen_substeps = 0;
     float skin_frac = 0.4f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
     float nl_skin = 0.f;
     bool nl_on = false;                // the current broadphase is the list pipeline
@@ -346,7 +348,8 @@ class World {
     NlCtl* d_nlctl = nullptr;
     NlCtl* h_nlctl = nullptr;          // pinned copy, refreshed with the step statistics
     NlView nl_view();
-    int nl_rebuild_chain(bool timed_launch);
+    int nl_rebuild_chain(bool timed_launch, bool decide);
+    bool nl_prev_tail = false;         // the previous substep's k_step already took the rebuild decision for this one
     int nl_rebuild_now();
 
     // stats / recording

@@ -94,14 +94,16 @@ typedef enum BlobsParamId {
                                             stores over NVLink (neighbours' receive buffers mapped through CUDA IPC, one push kernel per
                                             substep) instead of grouped ncclSend/ncclRecv; falls back to NCCL on every rank if any rank
                                             cannot map its neighbours. Reads back 1 only while the peer path is active. Never changes results. */
-    ,BLOBS_PARAM_LIST = 23               /* broadphase strategy: 1 (default) = per-collider neighbour lists (every collider within r_a + r_b + skin,
-                                            sorted by slot), walked by one fused kernel per substep and rebuilt from the cell grid only when the
-                                            device-side displacement tracking says a pair outside the lists could touch; 0 = the cell grid is rebuilt
-                                            every substep. The contact set of every substep is the reference's either way (physics.rs:241-317):
-                                            never changes results. */
+    ,BLOBS_PARAM_LIST = 23               /* broadphase strategy: 1 = per-collider neighbour lists (every collider within r_a + r_b + skin, sorted by
+                                            slot), walked by one fused kernel per substep and rebuilt from the cell grid only when the device-side
+                                            displacement tracking says a pair outside the lists could touch; 0 = the cell grid is rebuilt every
+                                            substep; 2 (default) = lists, falling back to 0 for a while whenever the scene is so agitated that the
+                                            lists are rebuilt almost every substep. The contact set of every substep is the reference's either way
+                                            (physics.rs:241-317): never changes results. */
     ,BLOBS_PARAM_SKIN = 24               /* neighbour-list skin as a fraction of the largest collider radius (default 0.4) */
     ,BLOBS_PARAM_LIST_REBUILDS = 25      /* read-only: list rebuilds / substeps run so far (as of the last blobs_step* call) */
     ,BLOBS_PARAM_LIST_SUBSTEPS = 26
+    ,BLOBS_PARAM_LIST_ACTIVE = 27        /* read-only: 1 while the neighbour-list pipeline is the one in use */
 } BlobsParamId;
 
 /* RigidBodyBuilder, rigid_body.rs:287-401 */

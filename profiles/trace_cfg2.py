@@ -1,8 +1,8 @@
 """Throughput of BASELINE config #2 as a function of SIMULATED time (one line per block of steps): the block falls
 freely (few contacts), reaches the circle constraint at ~1.9 s, gets compressed against it (dense contacts, bodies with
 more than 24 contributions) and settles. Usage: python profiles/trace_cfg2.py [total_steps] [block] [crowded_mode]
-Also used as the workload for the dense-regime ncu capture (env CAPTURE_STEPS=N: run N plain steps without CUDA graphs
-and exit)."""
+Also used as the workload for the dense-regime ncu captures (env CAPTURE_STEPS=N: run N steps, then one more step inside a
+cudaProfilerStart/Stop window, for `ncu --profile-from-start off`). TRACE_LIST / TRACE_SKIN select the broadphase pipeline."""
 import json
 import os
 import sys
@@ -28,9 +28,18 @@ def main():
         w.set_param(A.PARAM_SKIN, float(os.environ["TRACE_SKIN"]))
     cap = int(os.environ.get("CAPTURE_STEPS", "0"))
     if cap:
+        # ncu --profile-from-start off: run `cap` steps at full speed (CUDA graphs), then open the profiler window around one
+        # more step launched kernel by kernel
+        import torch
+
+        w.step(DT, n=cap)
         w.set_param(A.PARAM_GRAPH, 0)
-        for _ in range(cap):
-            w.step(DT)
+        w.step(DT)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        w.step(DT)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
         return
     n = sc.n_bodies
     done = 0

@@ -398,20 +398,23 @@ __device__ __forceinline__ float2 apply_contacts_rescan(GridDesc g, Broadphase b
 // k_crowded, or - when that kernel is not in the pipeline - through the per-lane path. An owner that meets a coincident pair
 // (distance < 1e-6: two contributions per pair, physics.rs:272-286) redoes its sum with the serial windowed rescan.
 // ------------------------------------------------------------------------------------------------
-constexpr int COOP_Q = 256;
+constexpr int COOP_Q = 256;            // survivor queue entries per warp
+constexpr uint32_t COOP_C = 1024u;     // candidates scanned per batch of lanes (if their survivors overflow the queue the batch is halved)
+constexpr uint32_t COOP_LANE_MAX = 96u;   // a lane with more candidates than this is not pooled (rank ordering is quadratic in the run length)
 constexpr uint32_t POOL_NONE = 0xffffffffu;
 
 struct CoopSmem {                 // per warp
     float4 sa[32];                // the lanes' own colliders: x, y, r, parent mass
     uint4 sb[32];                 //                           memberships, filter, body slot, collider slot | sensor << 31
     uint32_t lo[3][32];           // first record of each row span
-    uint32_t c1[32], c2[32];      // candidates in span 0, in spans 0 + 1
-    uint32_t pre[33];             // exclusive prefix of the lanes' candidate totals (lanes outside the batch: their batch-relative bound)
+    uint16_t c1[32], c2[32];      // candidates in span 0, in spans 0 + 1 (pooled lanes: <= COOP_LANE_MAX)
+    uint32_t pre[32];             // batch-relative exclusive prefix of the lanes' candidate totals
+    uint32_t ol[32];              // the lanes of the batch that have candidates, in lane order
     uint32_t key[COOP_Q];         // survivor: record index, then the contribution key (POOL_NONE = contributes nothing)
     float cx[COOP_Q], cy[COOP_Q];
     uint16_t perm[COOP_Q];        // perm[segment start + rank] = entry
     uint8_t owner[COOP_Q];        // lane that owns the entry
-    uint32_t seg[33];             // first queue entry of each owner lane
+    uint32_t seg[32], send[32];   // first / one-past-last queue entry of each owner lane
     uint32_t nvalid[32];          // contributions per owner lane
     uint32_t fb;                  // owner lanes that must fall back to the serial rescan
 };
@@ -454,12 +457,12 @@ __device__ __forceinline__ bool gather_coop(const GridDesc& g, const Broadphase&
             plain = true;
         }
     }
-    const bool coop = plain && total <= (uint32_t)COOP_Q;
+    const bool coop = plain && total <= COOP_LANE_MAX;
     const uint32_t tc = coop ? total : 0u;
     ps.sa[lane] = make_float4(s.x, s.y, s.r, s.m);
     ps.sb[lane] = make_uint4(s.memb, s.filt, s.body, s.slot | (s.sensor ? HOT_SENSOR_BIT : 0u));
     ps.lo[0][lane] = lo0; ps.lo[1][lane] = lo1; ps.lo[2][lane] = lo2;
-    ps.c1[lane] = n0; ps.c2[lane] = n01;
+    ps.c1[lane] = (uint16_t)min(n0, 0xffffu); ps.c2[lane] = (uint16_t)min(n01, 0xffffu);
     ps.nvalid[lane] = 0u;
     if (lane == 0) ps.fb = 0u;
     uint32_t incl = tc;
@@ -469,71 +472,82 @@ __device__ __forceinline__ bool gather_coop(const GridDesc& g, const Broadphase&
         if (lane >= (uint32_t)d) incl += t;
     }
     const uint32_t excl = incl - tc;
+    const uint32_t le_mask = FULL >> (31u - lane);   // bits 0 .. lane
     bool applied = false;
     uint32_t start = 0;
-    while (start < 32u) {   // lane ranges [start, end) whose candidates fit the queue
+    while (start < 32u) {   // lane ranges [start, end): at most COOP_C candidates, and survivors that fit the queue
         const uint32_t base = __shfl_sync(FULL, excl, start);
-        const bool in_batch = lane >= start && (incl - base) <= (uint32_t)COOP_Q;
-        const uint32_t bal = __ballot_sync(FULL, in_batch);
-        const uint32_t zeros = ~bal & (FULL << start);
-        const uint32_t end = zeros ? (uint32_t)__ffs(zeros) - 1u : 32u;   // > start: one cooperative lane never exceeds COOP_Q
-        const uint32_t C = __shfl_sync(FULL, incl, end - 1u) - base;      // candidates of this batch
+        uint32_t end;
+        {
+            const bool in_batch = lane >= start && (incl - base) <= COOP_C;
+            const uint32_t zeros = ~__ballot_sync(FULL, in_batch) & (FULL << start);
+            end = zeros ? (uint32_t)__ffs(zeros) - 1u : 32u;   // > start: one pooled lane never exceeds COOP_LANE_MAX <= COOP_C
+        }
+        uint32_t qn, C;
+        for (;;) {
+            C = __shfl_sync(FULL, incl, end - 1u) - base;      // candidates of this batch
+            const bool inb = lane >= start && lane < end;
+            const uint32_t have = __ballot_sync(FULL, inb && tc != 0u);
+            __syncwarp();
+            ps.pre[lane] = excl - base;
+            if (inb && tc != 0u) ps.ol[__popc(have & (le_mask >> 1))] = lane;
+            __syncwarp();
+            // ---- 2. cooperative scan. Candidate i of the batch belongs to the lane l with pre[l] <= i < pre[l] + total[l]. The 32
+            // candidates of one group belong to consecutive owners: every owner marks where it starts inside the group (one OR
+            // across the warp), so the owner of candidate t is the (number of marks at or before t)-th one, counted from `carry`.
+            qn = 0;                 // warp-uniform queue length
+            bool ovf = false;       // warp-uniform
+            uint32_t carry = 0;     // owners that start before the current group
+            for (uint32_t i0 = 0; i0 < C; i0 += 32u * BATCH) {
+                float4 h[BATCH];
+                uint32_t kk[BATCH], own[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const uint32_t I = i0 + 32u * u, i = I + lane;
+                    const uint32_t myp = excl - base;   // (meaningful for the owners of this batch only)
+                    const uint32_t M = __reduce_or_sync(FULL, (inb && tc != 0u && myp >= I && myp < I + 32u) ? 1u << (myp - I) : 0u);
+                    const uint32_t ord = carry + (uint32_t)__popc(M & le_mask) - 1u;
+                    carry += (uint32_t)__popc(M);
+                    const uint32_t l = i < C ? ps.ol[ord] : start;
+                    const uint32_t t = i < C ? i - ps.pre[l] : 0u;
+                    const uint32_t c1 = ps.c1[l], c2 = ps.c2[l];
+                    kk[u] = t < c1 ? ps.lo[0][l] + t : (t < c2 ? ps.lo[1][l] + (t - c1) : ps.lo[2][l] + (t - c2));
+                    own[u] = l;
+                    h[u] = __ldg(bp.hot + (i < C ? kk[u] : 0u));   // (index 0 always exists: the arrays are padded by one record)
+                }
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) {
+                    const uint32_t i = i0 + 32u * u + lane;
+                    const float4 a = ps.sa[own[u]];
+                    const uint32_t oslot = __float_as_uint(h[u].w) & HOT_SLOT_MASK;
+                    const float dx = a.x - h[u].x, dy = a.y - h[u].y;
+                    const float d2 = __fmaf_rn(dx, dx, dy * dy);
+                    const float mdk = (a.z + h[u].z) * 1.00005f;   // prefilter, see gather_single
+                    const bool pass = i < C && oslot != (ps.sb[own[u]].w & HOT_SLOT_MASK) && !(d2 > mdk * mdk);
+                    const uint32_t bl = __ballot_sync(FULL, pass);
+                    const uint32_t w = qn + (uint32_t)__popc(bl & (le_mask >> 1));
+                    if (pass && w < (uint32_t)COOP_Q) {
+                        ps.key[w] = kk[u];
+                        ps.owner[w] = (uint8_t)own[u];
+                    }
+                    qn += (uint32_t)__popc(bl);
+                }
+                if (qn > (uint32_t)COOP_Q) { ovf = true; break; }
+            }
+            if (!ovf) break;
+            end = start + max(1u, (end - start) >> 1);   // more survivors than the queue holds: redo with half the lanes
+        }
         const bool mine = coop && lane >= start && lane < end;
         __syncwarp();
-        // batch-relative exclusive prefix; lanes after the batch carry C so that the binary search never selects them
-        ps.pre[lane] = lane < start ? 0u : (lane < end ? excl - base : C);
-        if (lane == 0) ps.pre[32] = C;
-        __syncwarp();
-        // ---- 2. cooperative scan: candidate i of the batch belongs to the lane l with pre[l] <= i < pre[l + 1] -----------
-        uint32_t qn = 0;   // warp-uniform queue length
-        for (uint32_t i0 = 0; i0 < C; i0 += 32u * BATCH) {
-            float4 h[BATCH];
-            uint32_t kk[BATCH], own[BATCH];
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint32_t i = i0 + 32u * u + lane;
-                uint32_t l = start;
-                if (i < C) {   // largest l in [start, end) with pre[l] <= i (lanes with no candidates share their successor's prefix)
-                    uint32_t a = start, b = end;   // invariant: pre[a] <= i, answer in [a, b)
-                    while (b - a > 1u) {
-                        const uint32_t m = (a + b) >> 1;
-                        if (ps.pre[m] <= i) a = m; else b = m;
-                    }
-                    l = a;
-                }
-                const uint32_t t = i < C ? i - ps.pre[l] : 0u;
-                const uint32_t c1 = ps.c1[l], c2 = ps.c2[l];
-                kk[u] = t < c1 ? ps.lo[0][l] + t : (t < c2 ? ps.lo[1][l] + (t - c1) : ps.lo[2][l] + (t - c2));
-                own[u] = l;
-                h[u] = __ldg(bp.hot + (i < C ? kk[u] : 0u));   // (index 0 always exists: the arrays are padded by one record)
-            }
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const uint32_t i = i0 + 32u * u + lane;
-                const float4 a = ps.sa[own[u]];
-                const uint32_t oslot = __float_as_uint(h[u].w) & HOT_SLOT_MASK;
-                const float dx = a.x - h[u].x, dy = a.y - h[u].y;
-                const float d2 = __fmaf_rn(dx, dx, dy * dy);
-                const float mdk = (a.z + h[u].z) * 1.00005f;   // prefilter, see gather_single
-                const bool pass = i < C && oslot != (ps.sb[own[u]].w & HOT_SLOT_MASK) && !(d2 > mdk * mdk);
-                const uint32_t bl = __ballot_sync(FULL, pass);
-                if (pass) {
-                    const uint32_t w = qn + (uint32_t)__popc(bl & ((1u << lane) - 1u));
-                    ps.key[w] = kk[u];
-                    ps.owner[w] = (uint8_t)own[u];
-                }
-                qn += (uint32_t)__popc(bl);
-            }
-        }
-        __syncwarp();
-        // first queue entry of every owner (the queue is in candidate order, so an owner's entries are contiguous): every entry
-        // that starts a new owner run records where the run starts
+        // first / last queue entry of every owner (the queue is in candidate order, so an owner's entries are contiguous)
         for (uint32_t i0 = 0; i0 < qn; i0 += 32u) {
             const uint32_t i = i0 + lane;
             const uint32_t o = i < qn ? (uint32_t)ps.owner[i] : 0xffu;
-            const uint32_t prev = __shfl_up_sync(FULL, o, 1);
+            const uint32_t prev = __shfl_up_sync(FULL, o, 1), next = __shfl_down_sync(FULL, o, 1);
             const uint32_t before = lane == 0u ? (i0 ? (uint32_t)ps.owner[i0 - 1u] : 0xfeu) : prev;
+            const uint32_t after = lane == 31u ? (i + 1u < qn ? (uint32_t)ps.owner[i + 1u] : 0xfeu) : next;
             if (i < qn && o != before) ps.seg[o] = i;
+            if (i < qn && o != after) ps.send[o] = i + 1u;
         }
         __syncwarp();
         // ---- 3. exact narrowphase, one (owner, candidate) pair per lane ---------------------------------------------------
@@ -571,9 +585,10 @@ __device__ __forceinline__ bool gather_coop(const GridDesc& g, const Broadphase&
                 const uint32_t key = ps.key[i];
                 if (key != POOL_NONE) {
                     const uint32_t o = (uint32_t)ps.owner[i];
-                    const uint32_t a = ps.seg[o];
+                    const uint32_t a = ps.seg[o], e = ps.send[o];
                     uint32_t rank = 0;
-                    for (uint32_t j = a; j < qn && (uint32_t)ps.owner[j] == o; ++j) rank += ps.key[j] < key ? 1u : 0u;
+#pragma unroll 4
+                    for (uint32_t j = a; j < e; ++j) rank += ps.key[j] < key ? 1u : 0u;
                     ps.perm[a + rank] = (uint16_t)i;
                 }
             }

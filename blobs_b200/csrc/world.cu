@@ -1945,6 +1945,7 @@ int World::record_contacts(int mode, size_t cap) {
     }
     CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
     sub_recorded = 0;
+    rec_drained = 0;
     return BLOBS_OK;
 }
 
@@ -1977,18 +1978,23 @@ int World::pairs_drain(uint32_t* a, uint32_t* b, size_t cap, size_t* n, uint64_t
     return BLOBS_OK;
 }
 
+// A drain may be partial (cap smaller than what was recorded): *n reports how many events were still pending BEFORE this call,
+// the first min(*n, cap) of them are returned and consumed, the rest stay for the next call (the channel of the reference,
+// physics.rs:22-23, never loses an event either).
 int World::events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n) {
     if (rec_mode != BLOBS_RECORD_EVENTS) return fail(BLOBS_ERR_INVALID, "event recording is not enabled");
     unsigned long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, d_rec_count, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
-    const size_t have = (size_t)std::min<unsigned long long>(cnt, rec_cap);
+    const size_t recorded = (size_t)std::min<unsigned long long>(cnt, rec_cap);
+    if (rec_drained > recorded) rec_drained = recorded;
+    const size_t have = recorded - rec_drained;
     const size_t m = std::min(have, cap);
     std::vector<uint2> pr(m);
     std::vector<float4> vl(m);
     if (m) {
-        CU(cudaMemcpyAsync(pr.data(), rec_pairs.d, m * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
-        CU(cudaMemcpyAsync(vl.data(), rec_vels.d, m * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(pr.data(), rec_pairs.d + rec_drained, m * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(vl.data(), rec_vels.d + rec_drained, m * sizeof(float4), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
     }
     for (size_t i = 0; i < m; ++i) {
@@ -1998,8 +2004,12 @@ int World::events_drain(BlobsCollisionEvent* buf, size_t cap, size_t* n) {
         buf[i].impact_vel_b = {vl[i].z, vl[i].w};
     }
     if (n) *n = have;
-    CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
-    sub_recorded = 0;
+    rec_drained += m;
+    if (rec_drained == recorded) {   // everything consumed: recording restarts at the beginning of the buffer
+        CU(cudaMemsetAsync(d_rec_count, 0, sizeof(unsigned long long), stream));
+        rec_drained = 0;
+        sub_recorded = 0;
+    }
     return BLOBS_OK;
 }
 

@@ -357,6 +357,7 @@ class World {
     DeviceStats* h_stats = nullptr;  // pinned
     int rec_mode = 0;
     size_t rec_cap = 0;
+    size_t rec_drained = 0;            // events of the current recording already handed out by partial blobs_events_drain calls
     DevBuf<uint2> rec_pairs;
     DevBuf<float4> rec_vels;
     unsigned long long* d_rec_count = nullptr;

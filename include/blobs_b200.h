@@ -306,6 +306,8 @@ int32_t blobs_query_circles(BlobsWorld* w, size_t n, const float* centre_xy, con
 enum { BLOBS_RECORD_OFF = 0, BLOBS_RECORD_PAIRS = 1, BLOBS_RECORD_EVENTS = 2 };
 /* collision_send / collision_recv, physics.rs:22-23,304-311. PAIRS records slots only. */
 int32_t blobs_record_contacts(BlobsWorld* w, int32_t mode, size_t capacity);
+/* *n = events pending before the call; the first min(*n, cap) are returned and consumed, the rest stay queued for the next call
+ * (loop while *n > cap). Events beyond the recording capacity are counted in BlobsStepStats::events_dropped, never silently lost. */
 int32_t blobs_events_drain(BlobsWorld* w, BlobsCollisionEvent* buf, size_t cap, size_t* n);
 /* slot pairs (a > b) recorded since the last drain; substep_end[i] = running pair count after substep i */
 int32_t blobs_pairs_drain(BlobsWorld* w, uint32_t* slot_a, uint32_t* slot_b, size_t cap, size_t* n,

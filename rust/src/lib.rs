@@ -65,13 +65,18 @@ impl Physics {
                 let _ = self.collision_send.send(CollisionEvent { col_handle_a: ColliderHandle(idx(e.col_handle_a)), col_handle_b: ColliderHandle(idx(e.col_handle_b)),
                                                                   impact_vel_a: g(e.impact_vel_a), impact_vel_b: g(e.impact_vel_b) });
             }
-            if n <= buf.len() { break; }
+            if n <= buf.len() { break; }   // a partial drain leaves the rest queued (blobs_events_drain): keep pumping
         }
     }
+    fn after_step(&mut self, st: &BlobsStepStats) {
+        // the reference's channel is unbounded (physics.rs:22-23); the device-side recording is not: make an overflow loud
+        assert!(st.events_dropped == 0, "blobs_b200: {} collision events did not fit the recording capacity (blobs_record_contacts)", st.events_dropped);
+        self.pump_events();
+    }
     /// Physics::step (physics.rs:78-82)
-    pub fn step(&mut self, delta: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_step(self.w, delta, &mut st) }); self.pump_events(); }
+    pub fn step(&mut self, delta: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_step(self.w, delta, &mut st) }); self.after_step(&st); }
     /// Physics::fixed_step (physics.rs:84-99)
-    pub fn fixed_step(&mut self, frame_time: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_fixed_step(self.w, frame_time, &mut st) }); self.pump_events(); }
+    pub fn fixed_step(&mut self, frame_time: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_fixed_step(self.w, frame_time, &mut st) }); self.after_step(&st); }
 
     /// insert_rbd (physics.rs:121-128); `RigidBody` is the builder output (rigid_body.rs:376-400)
     pub fn insert_rbd(&mut self, rbd: RigidBody) -> RigidBodyHandle {

@@ -15,6 +15,16 @@ from .helpers import assert_bodies_bit_equal, bits, sphere
 
 pytestmark = pytest.mark.gpu
 
+_PIPELINES = {
+    "grid-per-lane": {A.PARAM_LIST: 0, A.PARAM_POOL: 0},
+    "grid-cooperative-crowded": {A.PARAM_LIST: 0, A.PARAM_POOL: 1, A.PARAM_CROWDED: 1},
+    "lists": {A.PARAM_LIST: 1},
+    "lists-tiny-skin": {A.PARAM_LIST: 1, A.PARAM_SKIN: 0.02},   # rebuilt almost every substep
+    "lists-crowded": {A.PARAM_LIST: 1, A.PARAM_CROWDED: 1},
+}
+
+
+
 
 def _pair(gravity, scene, grid_oracle=False, **gpu_kw):
     import blobs_b200
@@ -466,6 +476,36 @@ def test_events_match_reference_channel():
     assert n > 50
 
 
+def test_events_partial_drains_lose_nothing():
+    """blobs_events_drain with a buffer smaller than what was recorded hands the events out in pieces (the Rust shim drains 65 536
+    at a time): the concatenation equals one big drain."""
+    import ctypes as C
+
+    import blobs_b200
+
+    sc = S.cfg1(1, n_side=16)
+    ws = []
+    for _ in range(2):
+        w = blobs_b200.World(gravity=sc.gravity)
+        S.build(w, sc)
+        w.record_contacts(A.RECORD_EVENTS, 1 << 16)
+        w.step(1 / 60, n=12)
+        ws.append(w)
+    whole = ws[0].events_drain()
+    assert len(whole) > 40
+    parts, n = [], C.c_size_t(1 << 30)
+    while n.value > 7:
+        buf = np.zeros(7, dtype=A.COLLISION_EVENT)
+        ws[1]._ck(ws[1]._lib.blobs_events_drain(ws[1]._h, A.ptr(buf), 7, C.byref(n)))
+        parts.append(buf[: min(n.value, 7)])
+    got = np.concatenate(parts)
+    assert got.tobytes() == whole.tobytes()
+    assert len(ws[1].events_drain()) == 0
+    ws[1].step(1 / 60)   # recording restarts cleanly
+    ws[0].step(1 / 60)
+    assert ws[1].events_drain().tobytes() == ws[0].events_drain().tobytes()
+
+
 def test_full_size_cfg2_one_step_vs_grid_oracle():
     """BASELINE config #2 at full size (1 048 576 spheres): one step (8 substeps) vs the cell-list oracle, bit-exact, then
     size-independent properties over more steps: determinism across two GPU runs and bounded penetration."""
@@ -492,6 +532,47 @@ def test_full_size_cfg2_one_step_vs_grid_oracle():
     p1, p2 = g.read_positions(), g2.read_positions()
     assert p1.tobytes() == p2.tobytes(), "ordered mode must be run-to-run deterministic despite atomic binning"
     assert np.isfinite(p1).all()
+
+
+def _vs_cpu_checker(scene, checkpoints, **params):
+    """GPU world vs the all-cores CPU checker (oracle/grid_omp.cpp, pinned to the sequential oracle by tests/test_grid_omp.py):
+    state bit-equal at every checkpoint, same pair count."""
+    import blobs_b200
+    from oracle import grid_omp
+
+    g = blobs_b200.World(gravity=scene.gravity)
+    S.build(g, scene)
+    for k, v in params.items():
+        g.set_param(k, v)
+    o = grid_omp.GridOmpWorld(scene)
+    done = coll_g = coll_o = 0
+    xy = lambda v: np.stack([v["x"], v["y"]], axis=1)
+    for cp in checkpoints:
+        st = g.step(1 / 60, n=cp - done)
+        assert st["nan_detected"] == 0
+        coll_g += st["collisions"]
+        coll_o += o.step(1 / 60, n=cp - done)["collisions"]
+        done = cp
+        assert o.coincident == 0, "the CPU checker does not restate the sequential coincident branch"
+        sb, _ = g.download_bodies()
+        for f, arr in (("position", o.pos), ("position_old", o.pos_old), ("calculated_velocity", o.vel)):
+            assert np.array_equal(bits(xy(sb[f])), bits(arr)), f"{f} differs from the CPU checker after {cp} steps"
+        assert coll_g == coll_o
+    return g, coll_g
+
+
+def test_full_size_cfg2_twelve_steps_vs_cpu_checker():
+    """BASELINE config #2 at full size (1 048 576 spheres), 12 steps = 96 substeps (SURVEY §8d gate: >= 10 steps), library defaults."""
+    g, coll = _vs_cpu_checker(S.cfg2(seed=1), (1, 4, 12))
+    assert coll > 100_000
+
+
+@pytest.mark.parametrize("pipeline", ["grid-cooperative-crowded", "lists"])
+def test_full_size_contact_rich_start_vs_cpu_checker(pipeline):
+    """1 048 576 spheres on a pitch-0.9 lattice (every sphere overlaps its four neighbours from the first substep on, ~2 M pairs per
+    substep): the contact-rich paths - cooperative gather, k_crowded hand-over, list rebuilds - checked at scale, 6 steps."""
+    g, coll = _vs_cpu_checker(S.cfg2_dense(seed=1, side=1024), (1, 6), **_PIPELINES[pipeline])
+    assert coll > 6 * 8 * 1_000_000
 
 
 def test_batched_independent_worlds():
@@ -628,8 +709,43 @@ def test_boundary_shell_vs_grid_oracle(crowded):
         pg, po = g.pairs_drain(), o.pairs_drain()
         for sub, (x, y) in enumerate(zip(pg, po)):
             assert np.array_equal(x, y), f"pair set differs at step {step} substep {sub}: gpu {len(x)} oracle {len(y)}"
-    assert tot_over > 500
+    if int(g.get_param(A.PARAM_POOL)) != 1 and int(g.get_param(A.PARAM_LIST_ACTIVE)) == 0:
+        assert tot_over > 500   # per-lane path: these bodies overflow the 24-entry list (the cooperative gather has no such list)
     assert tot_col == o.step(1 / 60, n=0)["collisions"]
+
+
+@pytest.mark.parametrize("pipeline", list(_PIPELINES))
+@pytest.mark.parametrize("scene", ["cfg1", "dense", "shell", "falling"])
+def test_every_broadphase_pipeline_gives_the_reference_contact_sets(scene, pipeline):
+    """The broadphase strategy (BLOBS_PARAM_LIST: cell grid rebuilt every substep / neighbour lists rebuilt on demand) and the
+    contact-resolution variant (per lane / warp-cooperative / k_crowded) never change results: pair set of every substep and the
+    state after every step equal the oracle's on a gas (cfg1), an over-full dense pile, a boundary shell and a falling lattice."""
+    sc = {"cfg1": lambda: S.cfg1(2),
+          "dense": lambda: S.lattice_scene(96, 96, 0.9, (0.0, 0.0), 7, 0.25, 0.5, jitter=0.08, vel_disc=2.0, constraint_r=40.0, name="dense", cell_size=1.0),
+          "shell": lambda: S.lattice_scene(96, 96, 1.05, (0.0, 0.0), 3, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=40.0, name="shell", cell_size=1.0),
+          "falling": lambda: S.lattice_scene(96, 96, 1.05, (0.0, 0.0), 5, 0.3, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=90.0, name="falling", cell_size=1.0)}[scene]()
+    g, o = _pair(sc.gravity, sc, grid_oracle=scene != "cfg1")
+    for k, v in _PIPELINES[pipeline].items():
+        g.set_param(k, v)
+    g.record_contacts(A.RECORD_PAIRS, 1 << 22)
+    steps = {"cfg1": 12, "dense": 3, "shell": 4, "falling": 12}[scene]
+    n = 0
+    for step in range(steps):
+        st = g.step(1 / 60)
+        o.step(1 / 60)
+        assert st["nan_detected"] == 0 and st["events_dropped"] == 0
+        pg, po = g.pairs_drain(), o.pairs_drain()
+        assert len(pg) == len(po) == 8
+        for sub, (x, y) in enumerate(zip(pg, po)):
+            assert np.array_equal(x, y), f"pair set differs at step {step} substep {sub}: gpu {len(x)} oracle {len(y)}"
+            n += len(x)
+        _compare_step(g, o)
+    assert n > 100
+    assert int(g.get_param(A.PARAM_LIST_ACTIVE)) == (1 if pipeline.startswith("lists") else 0)
+    if pipeline == "lists" and scene == "falling":   # a lattice falling together keeps its lists for many substeps
+        assert g.get_param(A.PARAM_LIST_REBUILDS) < 0.5 * g.get_param(A.PARAM_LIST_SUBSTEPS)
+    if pipeline == "lists-tiny-skin":
+        assert g.get_param(A.PARAM_LIST_REBUILDS) > 0.5 * g.get_param(A.PARAM_LIST_SUBSTEPS)
 
 
 def test_debug_data_one_call_snapshot():

@@ -766,7 +766,13 @@ __device__ __forceinline__ float2 publish_collider(const GridDesc& g, const Coll
     if (bp.nl.snap_next != nullptr) {
         const float4 me = __ldg(bp.nl.snap_cur + c);
         const uint4 hd = bp.nl.hdr[c];
-        bp.nl.snap_next[c] = make_float4(a.x, a.y, me.z, me.w);
+        const float4 rec_new = make_float4(a.x, a.y, me.z, me.w);
+        bp.nl.snap_next[c] = rec_new;
+        if (hd.w & (NLF_PUSH_L | NLF_PUSH_R)) {   // strips: a neighbour rank keeps this collider as a ghost
+            if (hd.w & NLF_PUSH_L) bp.nl.peer_next[0][c] = rec_new;
+            if (hd.w & NLF_PUSH_R) bp.nl.peer_next[1][c] = rec_new;
+            __threadfence_system();
+        }
         nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), bp.nl.ctl->cx, bp.nl.ctl->cy, na);
     } else {
         const uint32_t cell = wbase + cell_index(g, bin_coord(a.x, g.inv_cell), bin_coord(a.y, g.inv_cell));
@@ -939,7 +945,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
             list.clear();
             bool applied = false, big = false;
             if (POOLED) {   // warp-collective: every lane calls
-                applied = gather_coop<2>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.crowded != 0u, big, p.x, p.y);
+                applied = gather_coop<BATCH>(g, bp, Cc.ccold, do_gather, s, list, out, rec, B.vel, stats, pool[threadIdx.x >> 5], P.crowded != 0u, big, p.x, p.y);
             } else if (do_gather) {
                 gather_single<true, uint32_t, BATCH>(g, bp, Cc.ccold, s, list, out, rec, B.vel, stats);
             }
@@ -1807,12 +1813,10 @@ constexpr long long STRIP_WAIT_TICKS = 120ll * 1000000000ll;   // host-compiled 
 constexpr long long STRIP_WAIT_TICKS = 1ll << 33;
 #endif
 
-__global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* send_l, const void* send_r, void* peer_l, void* peer_r,
-                                                    const void* recv_l, const void* recv_r, unsigned int* xseq, unsigned int* done, DeviceStats* stats) {
+__device__ __forceinline__ void strip_push_body(const StripDesc& S, const void* send_l, const void* send_r, void* peer_l, void* peer_r,
+                                                const void* recv_l, const void* recv_r, uint32_t seq, unsigned int* xseq, unsigned int* done,
+                                                DeviceStats* stats) {
     __shared__ bool last;
-    // exchange sequence number: device-resident (so that a captured CUDA graph can be replayed), bumped by the publishing CTA -
-    // which is the last one to arrive at `done`, i.e. after every CTA has read it here
-    const uint32_t seq = *reinterpret_cast<volatile unsigned int*>(xseq) + 1u;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
@@ -1862,9 +1866,17 @@ __global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* sen
     }
 }
 
+__global__ void __launch_bounds__(256) k_strip_push(StripDesc S, const void* send_l, const void* send_r, void* peer_l, void* peer_r,
+                                                    const void* recv_l, const void* recv_r, unsigned int* xseq, unsigned int* done, DeviceStats* stats) {
+    // exchange sequence number: device-resident (so that a captured CUDA graph can be replayed), bumped by the publishing CTA -
+    // which is the last one to arrive at `done`, i.e. after every CTA has read it here
+    const uint32_t seq = *reinterpret_cast<volatile unsigned int*>(xseq) + 1u;
+    strip_push_body(S, send_l, send_r, peer_l, peer_r, recv_l, recv_r, seq, xseq, done, stats);
+}
+
 // bins the received ghosts into the table under construction (before k_scan)
-__global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc S, const void* recv_l, const void* recv_r, uint32_t* tab_next,
-                                                          uint32_t* tile_next, uint2* gcell, DeviceStats* stats) {
+__device__ __forceinline__ void strip_bin_ghosts_body(const GridDesc& g, const StripDesc& S, const void* recv_l, const void* recv_r, uint32_t* tab_next,
+                                                      uint32_t* tile_next, uint2* gcell, DeviceStats* stats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2u * S.gcap) return;
     const uint32_t side = i / S.gcap, j = i - side * S.gcap;
@@ -1881,14 +1893,19 @@ __global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc 
     const uint32_t cell = cell_index(g, bin_coord(hot.x, g.inv_cell), bin_coord(hot.y, g.inv_cell));
     gcell[i] = make_uint2(cell, bin_collider(tab_next, tile_next, cell));
 }
+__global__ void __launch_bounds__(256) k_strip_bin_ghosts(GridDesc g, StripDesc S, const void* recv_l, const void* recv_r, uint32_t* tab_next,
+                                                          uint32_t* tile_next, uint2* gcell, DeviceStats* stats) {
+    strip_bin_ghosts_body(g, S, recv_l, recv_r, tab_next, tile_next, gcell, stats);
+}
 
 // After the owned records were scattered: (1) ghost records go to their slots in the new sorted array; (2) ownership
 // hand-over — leavers (my send buffers) are released, arrivals (my receive buffers) are adopted with their full state and
 // appended to the owned list. One launch: threads [0, 2*gcap) do (1), threads [2*gcap, 2*gcap + 4*mcap) do (2).
-__global__ void __launch_bounds__(256) k_strip_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r,
-                                                      const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
-                                                      const uint2* __restrict__ gcell, float4* __restrict__ hot, uint8_t* owned, uint8_t* cowned,
-                                                      uint32_t* olist, uint32_t* ocount, uint32_t* opos, uint32_t olist_cap, DeviceStats* stats) {
+__device__ __forceinline__ void strip_finish_body(const BodyArrays& B, const ColliderArrays& Cc, const StripDesc& S, const void* send_l, const void* send_r,
+                                                  const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
+                                                  const uint2* __restrict__ gcell, float4* __restrict__ hot, uint8_t* owned, uint8_t* cowned,
+                                                  uint32_t* olist, uint32_t* ocount, uint32_t* opos, uint32_t olist_cap, DeviceStats* stats,
+                                                  float4* __restrict__ snap) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 2u * S.gcap) {
         const uint32_t side = i / S.gcap, j = i - side * S.gcap;
@@ -1897,7 +1914,9 @@ __global__ void __launch_bounds__(256) k_strip_finish(BodyArrays B, ColliderArra
         const StripHeader* h = reinterpret_cast<const StripHeader*>(msg);
         if (j >= min(h->n_ghost, S.gcap)) return;
         const uint2 cr = gcell[i];
-        hot[__ldg(tab + cr.x) + cr.y] = strip_ghosts(const_cast<void*>(msg))[j];
+        const float4 rec = strip_ghosts(const_cast<void*>(msg))[j];
+        hot[__ldg(tab + cr.x) + cr.y] = rec;
+        if (snap != nullptr) snap[__float_as_uint(rec.w) & HOT_SLOT_MASK] = rec;   // list pipeline: what the contact pass reads until the owner's next push
         return;
     }
     i -= 2u * S.gcap;
@@ -1923,6 +1942,12 @@ __global__ void __launch_bounds__(256) k_strip_finish(BodyArrays B, ColliderArra
         if (k < olist_cap) { olist[k] = m.slot; opos[m.slot] = k; }
         else atomicOr(&stats->nan_flag, 4u);
     }
+}
+__global__ void __launch_bounds__(256) k_strip_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r,
+                                                      const void* recv_l, const void* recv_r, const uint32_t* __restrict__ tab,
+                                                      const uint2* __restrict__ gcell, float4* __restrict__ hot, uint8_t* owned, uint8_t* cowned,
+                                                      uint32_t* olist, uint32_t* ocount, uint32_t* opos, uint32_t olist_cap, DeviceStats* stats) {
+    strip_finish_body(B, Cc, S, send_l, send_r, recv_l, recv_r, tab, gcell, hot, owned, cowned, olist, ocount, opos, olist_cap, stats, nullptr);
 }
 
 // (re)builds the compact owned list from the ownership bytes (once per blobs_step* call: drops released entries)

@@ -20,14 +20,16 @@
 // publisher (SubstepParams::nl_tail_decide), else by the one-thread kernel k_nl_decide at the start of the substep; the first
 // substep of every step call always runs k_nl_decide, which is also where a host request (NlCtl::force) is honoured.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void nl_decide(volatile NlCtl* ctl, float lim, uint32_t in_step) {
-    const float m = __uint_as_float(ctl->max_m);
-    const unsigned int need = (ctl->force != 0u || !(m <= lim)) ? 1u : 0u;
-    const unsigned int n = ctl->n_sum;
+// (max_m_bits, sum_x, sum_y, n): the accumulators of the substep that just ended - this GPU's, or (strips) every rank's combined.
+// xlim: strips only - also rebuild when the common displacement along x exceeds this (ownership is re-assigned at rebuilds only)
+__device__ __forceinline__ void nl_decide_from(volatile NlCtl* ctl, unsigned int max_m_bits, float sum_x, float sum_y, unsigned int n, float lim,
+                                               float xlim, uint32_t in_step) {
+    const float m = __uint_as_float(max_m_bits);
     float mx = ctl->mean_x, my = ctl->mean_y;   // no sample this substep: assume nothing moved
-    if (n) { mx = ctl->sum_x / (float)n; my = ctl->sum_y / (float)n; }
+    if (n) { mx = sum_x / (float)n; my = sum_y / (float)n; }
     if (!(fabsf(mx) < 1e30f)) mx = 0.f;
     if (!(fabsf(my) < 1e30f)) my = 0.f;
+    const unsigned int need = (ctl->force != 0u || !(m <= lim) || !(fabsf(mx) <= xlim)) ? 1u : 0u;
     // displacement per substep (the references were reset by the last rebuild, hence mean_* == 0 right after one)
     const float ux = mx - ctl->mean_x, uy = my - ctl->mean_y;
     if (need) {   // references move to the current snapshots: the next publishers see one substep's worth of motion
@@ -44,6 +46,9 @@ __device__ __forceinline__ void nl_decide(volatile NlCtl* ctl, float lim, uint32
     ctl->sum_x = 0.f; ctl->sum_y = 0.f;
     ctl->n_sum = 0u;
     ctl->substeps += in_step;
+}
+__device__ __forceinline__ void nl_decide(volatile NlCtl* ctl, float lim, uint32_t in_step) {
+    nl_decide_from(ctl, ctl->max_m, ctl->sum_x, ctl->sum_y, ctl->n_sum, lim, 3.4e38f, in_step);
 }
 
 __global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step) {
@@ -120,7 +125,7 @@ constexpr int NL_BUILD_THREADS = 128;
 
 __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L,
                                                                float4* __restrict__ snap_cur, uint32_t n_colliders,
-                                                               const uint8_t* __restrict__ cowned) {
+                                                               const uint8_t* __restrict__ cowned, StripDesc S) {
     __shared__ uint32_t keep[NL_CAP * NL_BUILD_THREADS];
     NlCtl* const ctl = L.ctl;
     if (ctl->need == 0u) return;   // grid-uniform
@@ -175,7 +180,13 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
                 cnt = n;
                 for (uint32_t i = 0; i < n; ++i) L.idx[(size_t)i * L.stride + c] = keep[i * NL_BUILD_THREADS + tid];
             }
-            hd = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), cnt, cc.y);
+            uint32_t fl = cc.y;
+            if (cowned != nullptr) {   // strips: the neighbour that keeps this collider as a ghost (same test as strip_pack_one, which sent it there)
+                const float reach = __fadd_ru(r, S.rmax);
+                if (S.has_right && a.x >= __fsub_rd(S.x_hi, reach)) fl |= NLF_PUSH_R;
+                if (S.has_left && a.x < __fadd_ru(S.x_lo, reach)) fl |= NLF_PUSH_L;
+            }
+            hd = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), cnt, fl);
         }
         L.hdr[c] = hd;
     }
@@ -216,12 +227,19 @@ __device__ BLOBS_NOINLINE float2 nl_overflow_inline(GridDesc g, Broadphase bp, c
     return apply_contacts_rescan(g, gb, ccold, &s, 1, p.x, p.y);
 }
 
-template <bool FUSED, int MINB>
+template <bool FUSED, int MINB, bool STRIP>
 __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
                                                  Recording rec, DeviceStats* stats) {
     const NlView& L = bp.nl;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inb = b < P.n_bodies;
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inb;
+    if (STRIP) {   // strip-decomposed world: threads enumerate the compact list of bodies this rank owns
+        inb = b < __ldg(L.ocount);
+        b = inb ? L.olist[b] : NO_SLOT;
+        inb = b != NO_SLOT;
+    } else {
+        inb = b < P.n_bodies;
+    }
     const uint32_t bl = inb ? b : 0u;
     const float ccx = L.ctl->cx, ccy = L.ctl->cy;
     // round 1 (tail threads read slot 0 and discard)
@@ -328,7 +346,13 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
             if (active_col) {
                 const float2 a = snapshot_of(Cc, c, hd.w, sx, sy, rot);
                 Cc.cabs[c] = a;
-                L.snap_next[c] = make_float4(a.x, a.y, me.z, me.w);
+                const float4 rec_new = make_float4(a.x, a.y, me.z, me.w);
+                L.snap_next[c] = rec_new;
+                if (STRIP && (hd.w & (NLF_PUSH_L | NLF_PUSH_R))) {   // a neighbour rank keeps this collider as a ghost: store the record there too
+                    if (hd.w & NLF_PUSH_L) L.peer_next[0][c] = rec_new;
+                    if (hd.w & NLF_PUSH_R) L.peer_next[1][c] = rec_new;
+                    __threadfence_system();   // ordered before this rank's end-of-substep flag (k_nls_publish)
+                }
                 nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), ccx, ccy, na);
             }
         } else {
@@ -350,4 +374,118 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
         unsigned int o = __reduce_add_sync(0xffffffffu, n_over);
         if ((threadIdx.x & 31) == 0 && o) atomicAdd(&stats->list_overflow, o);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The list pipeline on a strip-decomposed world (BASELINE config #5; peer-memory exchange only).
+// Between two rebuilds nothing structural crosses a strip edge: ownership is fixed, and so is the set of colliders each rank
+// keeps as ghosts of its neighbours. k_step stores every new snapshot record of a collider flagged NLF_PUSH_L / _R straight into
+// the neighbour's slot-indexed array (arrays are indexed by GLOBAL slot on every rank) - the "exchange" of a substep is those
+// 16-byte peer stores plus one 32-byte flag per rank pair:
+//   end of substep   k_nls_publish: this rank's displacement accumulators + a sequence number go to EVERY rank;
+//   start of substep k_nls_decide: waits for every rank's flag of the previous substep (which also means their ghost records
+//                    have landed), combines them in rank order and takes the rebuild decision - the same on every rank.
+// A rebuild is collective: migrants change owner and the ghost sets are re-selected with the message exchange of the grid
+// pipeline (k_strip_push), all of it gated by the device-side decision like the single-GPU rebuild kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_nls_publish(NlCtl* ctl, NlStripDev X) {
+    const uint32_t lane = threadIdx.x;
+    const unsigned int seq = ctl->pub_seq + 1u;
+    if (lane < (uint32_t)X.nranks) {
+        volatile NlFlag* f = X.peer[lane] + (size_t)(seq & 1u) * NL_MAX_RANKS + X.rank;
+        f->max_m = ctl->max_m;
+        f->sum_x = ctl->sum_x;
+        f->sum_y = ctl->sum_y;
+        f->n_sum = ctl->n_sum;
+        __threadfence_system();   // the numbers before the sequence number that announces them
+        f->seq = seq;
+    }
+    __syncwarp();
+    if (lane == 0u) {
+        ctl->pub_seq = seq;
+        ctl->published = 1u;
+        ctl->max_m = 0u;
+        ctl->sum_x = 0.f; ctl->sum_y = 0.f;
+        ctl->n_sum = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, float lim, float xlim, void* send_l, void* send_r, uint32_t in_step,
+                                                   DeviceStats* stats) {
+    const uint32_t lane = threadIdx.x;
+    unsigned int M = 0u, N = 0u;
+    float SX = 0.f, SY = 0.f;
+    if (ctl->published) {
+        const unsigned int seq = ctl->pub_seq;
+        const volatile NlFlag* f = X.mine + (size_t)(seq & 1u) * NL_MAX_RANKS;
+        if (lane < (uint32_t)X.nranks) {
+            const long long t0 = clock64();
+            while (f[lane].seq != seq) {
+                if (clock64() - t0 > STRIP_WAIT_TICKS) { atomicOr(&stats->nan_flag, 8u); break; }
+            }
+            __threadfence_system();
+        }
+        __syncwarp();
+        if (lane == 0u) {   // combined in rank order: every rank computes the very same numbers
+            for (int r = 0; r < X.nranks; ++r) {
+                M = max(M, f[r].max_m);
+                SX += f[r].sum_x;
+                SY += f[r].sum_y;
+                N += f[r].n_sum;
+            }
+        }
+    }
+    if (lane == 0u) {
+        nl_decide_from(ctl, M, SX, SY, N, lim, xlim, in_step);
+        if (ctl->need) {   // the rebuild packs migrants and ghost candidates into these messages
+            StripHeader* hl = reinterpret_cast<StripHeader*>(send_l);
+            StripHeader* hr = reinterpret_cast<StripHeader*>(send_r);
+            hl->n_ghost = hl->n_mig = hl->overflow = 0u;
+            hr->n_ghost = hr->n_mig = hr->overflow = 0u;
+        }
+    }
+}
+
+// rebuild, strips: ghost candidates (and leavers) of all owned colliders into the two outgoing messages
+__global__ void __launch_bounds__(256) k_nls_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, const uint8_t* __restrict__ cowned, void* send_l,
+                                                  void* send_r, uint32_t n_colliders, const NlCtl* ctl) {
+    if (ctl->need == 0u) return;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
+        if (!cowned[c]) continue;
+        const uint4 cc = Cc.cconst[c];
+        if (!(cc.y & CF_ACTIVE)) continue;
+        strip_pack_one(B, Cc, S, c, cc.y, Cc.cabs[c], __uint_as_float(cc.x), send_l, send_r);
+    }
+}
+
+// which receive buffers the exchange with sequence number `seq` uses (k_strip_push layout: [from left / from right][parity])
+__device__ __forceinline__ const void* nls_recv(const NlStripDev& X, int side, unsigned int seq) {
+    return X.recv_block + ((size_t)side * 2u + (seq & 1u)) * X.stride;
+}
+
+__global__ void __launch_bounds__(256) k_nls_push(StripDesc S, const void* send_l, const void* send_r, NlStripDev X, const NlCtl* ctl,
+                                                  DeviceStats* stats) {
+    if (ctl->need == 0u) return;
+    const uint32_t seq = *reinterpret_cast<volatile unsigned int*>(X.xseq) + 1u;
+    const size_t par = seq & 1u;
+    void* peer_l = S.has_left ? X.peer_block[0] + (1u * 2u + par) * X.stride : nullptr;    // I am my left neighbour's RIGHT
+    void* peer_r = S.has_right ? X.peer_block[1] + (0u * 2u + par) * X.stride : nullptr;   // and my right neighbour's LEFT
+    strip_push_body(S, send_l, send_r, peer_l, peer_r, nls_recv(X, 0, seq), nls_recv(X, 1, seq), seq, X.xseq, X.push_done, stats);
+}
+
+__global__ void __launch_bounds__(256) k_nls_bin_ghosts(GridDesc g, StripDesc S, NlStripDev X, NlView L, uint2* gcell, DeviceStats* stats) {
+    if (L.ctl->need == 0u) return;
+    const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
+    const unsigned int seq = *X.xseq;   // k_nls_push has completed this exchange
+    strip_bin_ghosts_body(g, S, nls_recv(X, 0, seq), nls_recv(X, 1, seq), nl_tab(L, nx), nl_tile(L, nx), gcell, stats);
+}
+
+__global__ void __launch_bounds__(256) k_nls_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r, NlStripDev X,
+                                                    NlView L, const uint2* __restrict__ gcell, uint8_t* owned, uint8_t* cowned, uint32_t* olist,
+                                                    uint32_t* ocount, uint32_t* opos, uint32_t olist_cap, DeviceStats* stats, float4* snap_cur) {
+    if (L.ctl->need == 0u) return;
+    const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
+    const unsigned int seq = *X.xseq;
+    strip_finish_body(B, Cc, S, send_l, send_r, nls_recv(X, 0, seq), nls_recv(X, 1, seq), nl_tab(L, nx), gcell, L.hot, owned, cowned, olist, ocount, opos,
+                      olist_cap, stats, snap_cur);
 }

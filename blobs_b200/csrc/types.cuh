@@ -132,6 +132,10 @@ constexpr int NL_CAP = 32;                       // list rows; entry k of collid
 constexpr int NL_SPEC = 4;                       // rows fetched together with the body state (before the count is known)
 constexpr uint32_t NL_OVER = 0xffffffffu;        // NlView::hdr[c].z: more than NL_CAP neighbours -> the body goes to k_crowded
 constexpr uint32_t NL_INACTIVE = 0xfffffffeu;    // NlView::hdr[c].z: collider slot is free / parentless / not owned by this rank
+// NlView::hdr[c].w = CF_* flags | (strip-decomposed world) which neighbour rank keeps this collider as a ghost: every new snapshot
+// record of such a collider is also stored straight into that neighbour's slot-indexed array (peer memory, NVLink)
+constexpr uint32_t NLF_PUSH_L = 1u << 8, NLF_PUSH_R = 1u << 9;
+constexpr int NL_MAX_RANKS = 16;
 struct NlCtl {                 // device-resident control block
     unsigned int need;         // the lists are rebuilt before this substep's contact pass (decided by k_nl_decide)
     unsigned int force;        // host request: topology / table / staged collider writes changed
@@ -144,6 +148,8 @@ struct NlCtl {                 // device-resident control block
     unsigned int done;         // CTA arrival counter of k_nl_build
     unsigned int step_done;    // CTA arrival counter of k_step (its last CTA takes the decision for the next substep)
     unsigned int decided;      // the decision for the coming substep has been taken already (by k_step's last CTA)
+    unsigned int pub_seq;      // strip-decomposed world: sequence number of this rank's last k_nls_publish
+    unsigned int published;    //                         ... and whether there has been one since the lists were (re)initialised
     unsigned long long rebuilds, substeps;   // statistics
 };
 struct NlView {
@@ -158,6 +164,23 @@ struct NlView {
     uint32_t* tab[2];          // the two cell-start tables / scan-tile totals; [ctl->parity] is current
     uint32_t* tile[2];
     float4* hot;               // cell-sorted records of the last rebuild (their POSITIONS are stale: only the slot word is used)
+    // strip-decomposed world (nullptr / unused otherwise)
+    float4* peer_next[2];      // the left / right neighbour rank's snap_next (CUDA IPC mapping)
+    const uint32_t* olist;     // compact list of the body slots this rank owns; k_step enumerates it
+    const uint32_t* ocount;
+};
+// What a rank tells every other rank at the end of a substep (list pipeline on strips): its displacement-tracking accumulators.
+// Every rank then takes the SAME rebuild decision from the same numbers (k_nls_decide).
+struct NlFlag { unsigned int max_m; float sum_x, sum_y; unsigned int n_sum; unsigned int seq; unsigned int pad[3]; };
+struct NlStripDev {
+    int rank, nranks;
+    NlFlag* mine;                  // [2][NL_MAX_RANKS]: slot [seq & 1][r] = what rank r published with sequence number seq
+    NlFlag* peer[NL_MAX_RANKS];    // the same block on every rank (peer[rank] == mine)
+    char* recv_block;              // rebuild-time ghost / migrant exchange: my receive block (k_strip_push layout: [side][parity] messages)
+    char* peer_block[2];           // ... and the neighbours'
+    size_t stride;
+    unsigned int* xseq;            // exchange sequence number and CTA arrival counter of that exchange
+    unsigned int* push_done;
 };
 
 struct Broadphase {

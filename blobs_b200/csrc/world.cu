@@ -149,6 +149,10 @@ World::~World() {
     if (d_ocount) cudaFree(d_ocount);
     if (d_io_count) cudaFree(d_io_count);
     if (nccl_comm && g_nccl_destroy) g_nccl_destroy(nccl_comm);
+    if (nls_snap_block) { snap_a.d = snap_b.d = nullptr; snap_a.cap = snap_b.cap = 0; blobs_ipc_free(nls_snap_block); }
+    for (int i = 0; i < 2; ++i) if (nls_peer_snap[i]) cudaIpcCloseMemHandle(nls_peer_snap[i]);
+    for (int r = 0; r < NL_MAX_RANKS; ++r) if (nls_peer_flags[r] && nls_peer_flags[r] != nls_flags) cudaIpcCloseMemHandle(nls_peer_flags[r]);
+    if (nls_flags) blobs_ipc_free(reinterpret_cast<char*>(nls_flags));
     snap_a.release(); snap_b.release(); nl_hdr.release(); nl_idx.release();
     if (d_nlctl) cudaFree(d_nlctl);
     if (h_nlctl) cudaFreeHost(h_nlctl);
@@ -910,7 +914,7 @@ int World::choose_grid(bool) {
     const size_t nc = cols.slots();
     // list pipeline: the rebuild collects every collider within r_a + r_b + skin, so the search reach (and the cell that keeps it
     // inside a 3x3 neighbourhood) grows by the skin
-    nl_on = (list_mode == 1 || (list_mode == 2 && nl_grid_hold == 0)) && !strip_on;
+    nl_on = (list_mode == 1 || (list_mode == 2 && nl_grid_hold == 0)) && (!strip_on || nls_ready);
     nl_skin = nl_on ? skin_frac * r_max : 0.f;
     float cs = bp_cell_override > 0.f ? bp_cell_override : (r_max > 0.f ? 2.0f * r_max + nl_skin : 1.0f);
     if (!(cs > 0.f) || !std::isfinite(cs)) cs = 1.0f;
@@ -948,6 +952,7 @@ int World::choose_grid(bool) {
     grid.cell = cs;
     grid.inv_cell = 1.0f / cs;
     grid.rmax = nl_on ? (r_max + nl_skin) * 1.000001f : r_max;
+    strip.rmax = grid.rmax;   // ghost selection reaches as far as the contact search does
     grid.MW = ~0ull / grid.W + 1ull;
     grid.MH = ~0ull / grid.H + 1ull;
     bb[0] = h_stats->bb_min_x; bb[1] = h_stats->bb_min_y; bb[2] = h_stats->bb_max_x; bb[3] = h_stats->bb_max_y;
@@ -983,6 +988,7 @@ int World::rebuild_broadphase() {
         init.force = 1u;
         init.rebuilds = h_nlctl->rebuilds;
         init.substeps = h_nlctl->substeps;
+        init.pub_seq = h_nlctl->pub_seq;   // (strips) sequence numbers stay monotonic: the flag slots still hold the old ones
         *h_nlctl = init;
         CU(cudaMemcpyAsync(d_nlctl, h_nlctl, sizeof(NlCtl), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));
@@ -1019,7 +1025,29 @@ NlView World::nl_view() {
     L.tab[0] = tab_a.d; L.tab[1] = tab_b.d;
     L.tile[0] = tile_a.d; L.tile[1] = tile_b.d;
     L.hot = hot_a.d;
+    if (strip_on) {
+        const size_t off = cur_is_a ? nls_snap_cap * sizeof(float4) : 0;   // the neighbours' snap_next: buffers flip in lock step on every rank
+        L.peer_next[0] = nls_peer_snap[0] ? reinterpret_cast<float4*>(nls_peer_snap[0] + off) : nullptr;
+        L.peer_next[1] = nls_peer_snap[1] ? reinterpret_cast<float4*>(nls_peer_snap[1] + off) : nullptr;
+        L.olist = olist.d;
+        L.ocount = d_ocount;
+    }
     return L;
+}
+
+NlStripDev World::nls_dev() {
+    NlStripDev X{};
+    X.rank = s_rank;
+    X.nranks = s_nranks;
+    X.mine = nls_flags;
+    for (int r = 0; r < NL_MAX_RANKS; ++r) X.peer[r] = nls_peer_flags[r];
+    X.recv_block = p2p_block;
+    X.peer_block[0] = p2p_peer[0];
+    X.peer_block[1] = p2p_peer[1];
+    X.stride = p2p_stride;
+    X.xseq = d_push_done + 1;
+    X.push_done = d_push_done;
+    return X;
 }
 
 // First launches of every substep in list mode: the decision kernel, then the four rebuild kernels, which return at once unless
@@ -1037,6 +1065,35 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
         return BLOBS_OK;
     };
     int rc = BLOBS_OK;
+    if (strip_on) {
+        // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records); a
+        // rebuild re-selects ghosts and hands migrants over with the message exchange of the grid pipeline, gated like the rest.
+        const NlStripDev X = nls_dev();
+        const BodyArrays B = body_arrays();
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats); });
+        if (rc) return rc;
+        if (!nc) return BLOBS_OK;
+        rc = run(KC_PACK, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nls_pack)(B, C, strip, d_cowned.d, msg[0], msg[1], nc, d_nlctl); });
+        if (rc) return rc;
+        rc = run(KC_NCCL, [&] { BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_nls_push)(strip, msg[0], msg[1], X, d_nlctl, d_stats); });
+        if (rc) return rc;
+        rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, d_cowned.d); });
+        if (rc) return rc;
+        rc = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_nls_bin_ghosts)(grid, strip, X, L, gcell.d, d_stats); });
+        if (rc) return rc;
+        rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
+        if (rc) return rc;
+        rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, d_cowned.d); });
+        if (rc) return rc;
+        rc = run(KC_GHOST, [&] {
+            BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_nls_finish)(B, C, strip, msg[0], msg[1], X, L, gcell.d, d_owned.d, d_cowned.d, olist.d, d_ocount,
+                                                                                                         opos.d, (uint32_t)olist.cap, d_stats, cur_is_a ? snap_a.d : snap_b.d);
+        });
+        if (rc) return rc;
+        return run(KC_NLBUILD, [&] {
+            BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, d_cowned.d, strip);
+        });
+    }
     if (decide) rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u); });
     if (rc) return rc;
     if (!nc) return BLOBS_OK;
@@ -1047,7 +1104,7 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, nullptr); });
     if (rc) return rc;
     rc = run(KC_NLBUILD, [&] {
-        BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr);
+        BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr, strip);
     });
     return rc;
 }
@@ -1162,7 +1219,7 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
     // measured on 2x B200: replaying a graph that contains the grouped ncclSend/ncclRecv is ~25 % SLOWER than plain launches,
     // so strip mode keeps plain launches
     // (with the peer-memory exchange the substep holds no NCCL call; replaying it is opt-in until measured: BLOBS_B200_STRIP_GRAPH=1)
-    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || (strip_on && !(p2p_on && strip_graph))) return integrate(nsub, delta, last);
+    if (!graphs_on || !allow_graph || nsub == 0 || rec_mode != BLOBS_RECORD_OFF || (strip_on && !(p2p_on && (strip_graph || nl_on)))) return integrate(nsub, delta, last);
     const uint64_t key = step_key(nsub, delta, last);
     GraphSlot& gs = gslot[last ? 1 : 0];
     const float step_delta = delta / (float)nsub;
@@ -1251,7 +1308,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     int rc;
     if (lists) {   // decide on the device whether the lists are still supersets of the contact set; rebuild them if not
         // k_step takes the decision for the NEXT substep itself when nothing else publishes snapshots after it
-        P.nl_tail_decide = (fused && nb && !n_islands && !n_multi && !crowded) ? 1u : 0u;
+        P.nl_tail_decide = (fused && nb && !n_islands && !n_multi && !crowded && !strip_on) ? 1u : 0u;
         rc = nl_rebuild_chain(true, !nl_prev_tail);
         if (rc) return rc;
         nl_prev_tail = P.nl_tail_decide != 0u;
@@ -1260,16 +1317,17 @@ int World::launch_substep(const SubstepParams& P_in) {
         rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
         if (rc) return rc;
     }
-    if (strip_on) {
+    if (strip_on && !lists) {
         CU(cudaMemsetAsync(msg[0], 0, sizeof(StripHeader), stream));
         CU(cudaMemsetAsync(msg[1], 0, sizeof(StripHeader), stream));
     }
     if (nb && lists) {
         rc = timed(KC_MAIN, [&] {
             // BLOBS_PARAM_TUNE 1: 3 CTAs per SM (85 registers, no spills) instead of 4 (64 registers)
-            if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3>)(P, grid, K, B, C, bp, R, d_stats);
-            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4>)(P, grid, K, B, C, bp, R, d_stats);
-            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4>)(P, grid, K, B, C, bp, R, d_stats);
+            if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, 4, true>)(P, grid, K, B, C, bp, R, d_stats);
+            else if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3, false>)(P, grid, K, B, C, bp, R, d_stats);
+            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4, false>)(P, grid, K, B, C, bp, R, d_stats);
+            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4, false>)(P, grid, K, B, C, bp, R, d_stats);
         });
         if (rc) return rc;
     } else if (nb) {
@@ -1277,7 +1335,10 @@ int World::launch_substep(const SubstepParams& P_in) {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
 #define BLOBS_LAUNCH_MAIN(F, O, PL) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<F, O, 4, 4, PL>)(P, grid, K, B, C, bp, R, d_stats, sv)
-            if (pooled) {   // contact-rich state: warp-pooled resolution
+            if (pooled && tune == 2) {   // BLOBS_PARAM_TUNE 2: cooperative gather with 2 instead of 4 candidates per lane in flight
+                if (fused) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<true, true, 2, 4, true>)(P, grid, K, B, C, bp, R, d_stats, sv);
+                else BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<false, true, 2, 4, true>)(P, grid, K, B, C, bp, R, d_stats, sv);
+            } else if (pooled) {   // contact-rich state: warp-cooperative resolution
                 if (fused) BLOBS_LAUNCH_MAIN(true, true, true);
                 else BLOBS_LAUNCH_MAIN(false, true, true);
             } else if (fused) {
@@ -1306,7 +1367,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     }
     if (crowded && nb) {
         rc = timed(KC_CROWDED, [&] {
-            const StripView sv = strip_view();
+            const StripView sv = lists ? StripView{} : strip_view();   // list pipeline: nothing is packed per substep (peer stores instead)
             if (fused) BLOBS_LAUNCH(CROWD_GRID, 32 * CROWD_WARPS, 0, stream, k_crowded<true>)(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
             else BLOBS_LAUNCH(CROWD_GRID, 32 * CROWD_WARPS, 0, stream, k_crowded<false>)(P, grid, K, B, C, bp, R, d_stats, sv, mb_body.d, mb_off.d, mb_cols.d);
         });
@@ -1342,6 +1403,9 @@ int World::launch_substep(const SubstepParams& P_in) {
     }
     if (!lists) {
         rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
+        if (rc) return rc;
+    } else if (strip_on) {   // end of the substep: this rank's displacement numbers + "my ghost records are out" go to every rank
+        rc = timed(KC_GHOST, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_publish)(d_nlctl, nls_dev()); });
         if (rc) return rc;
     }
     cur_is_a = !cur_is_a;   // list pipeline: swaps the slot-indexed snapshot buffers
@@ -2099,6 +2163,10 @@ int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const u
     if (nranks > 1 && p2p_request) {
         rc = strip_p2p_setup();
         if (rc) return rc;
+        if (p2p_on && list_mode != 0) {   // neighbour lists on strips need the peer mappings as well
+            rc = nls_setup();
+            if (rc) return rc;
+        }
     }
     CU(gcell.ensure(2 * (size_t)strip.gcap, stream));
     const size_t nb = bodies.slots(), nc = cols.slots();
@@ -2196,6 +2264,78 @@ int World::strip_p2p_setup() {
     }
     cudaFree(d_h);
     p2p_on = ok != 0;
+    return BLOBS_OK;
+}
+
+// List pipeline on strips: the two slot-indexed snapshot arrays and a small flag block become CUDA-IPC memory; every rank maps
+// every other rank's flag block (the rebuild decision combines all ranks' numbers) and its neighbours' snapshot arrays (ghost
+// records are stored there directly). All-or-nothing across ranks, like the peer-memory exchange itself.
+int World::nls_setup() {
+    nls_ready = false;
+    if (s_nranks > NL_MAX_RANKS || !p2p_on) return BLOBS_OK;
+    ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+    struct Card { cudaIpcMemHandle_t snap, flags; int ok; int pad[15]; };
+    static_assert(sizeof(Card) == 192, "Card layout");
+    Card mine{};
+    mine.ok = 1;
+    nls_snap_cap = std::max<size_t>(cabs.cap, 1);
+    const size_t fbytes = 2 * (size_t)NL_MAX_RANKS * sizeof(NlFlag);
+    char* fl = nullptr;
+    if (blobs_ipc_alloc(&nls_snap_block, 2 * nls_snap_cap * sizeof(float4)) != cudaSuccess) { cudaGetLastError(); nls_snap_block = nullptr; mine.ok = 0; }
+    if (mine.ok && blobs_ipc_alloc(&fl, fbytes) != cudaSuccess) { cudaGetLastError(); fl = nullptr; mine.ok = 0; }
+    nls_flags = reinterpret_cast<NlFlag*>(fl);
+    if (mine.ok) {
+        CU(cudaMemsetAsync(nls_snap_block, 0, 2 * nls_snap_cap * sizeof(float4), stream));
+        CU(cudaMemsetAsync(fl, 0, fbytes, stream));
+        if (cudaIpcGetMemHandle(&mine.snap, nls_snap_block) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, fl) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    }
+    char* d_cards = nullptr;
+    CU(cudaMalloc(&d_cards, (size_t)s_nranks * sizeof(Card)));
+    std::vector<Card> cards(s_nranks);
+    auto allgather = [&]() -> int {   // grouped point-to-point: NCCL is only the rendezvous here
+        CU(cudaMemcpyAsync(d_cards + (size_t)s_rank * sizeof(Card), &mine, sizeof(Card), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+        if (s_nranks > 1) {
+            NC(g_nccl.GroupStart());
+            for (int r = 0; r < s_nranks; ++r) {
+                if (r == s_rank) continue;
+                NC(g_nccl.Send(d_cards + (size_t)s_rank * sizeof(Card), sizeof(Card), ncclInt8, r, comm, stream));
+                NC(g_nccl.Recv(d_cards + (size_t)r * sizeof(Card), sizeof(Card), ncclInt8, r, comm, stream));
+            }
+            NC(g_nccl.GroupEnd());
+        }
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaMemcpy(cards.data(), d_cards, (size_t)s_nranks * sizeof(Card), cudaMemcpyDeviceToHost));
+        return BLOBS_OK;
+    };
+    int rc = allgather();
+    if (rc) return rc;
+    int all_ok = 1;
+    for (const Card& c : cards) all_ok = std::min(all_ok, c.ok);
+    if (all_ok) {
+        for (int r = 0; r < s_nranks && mine.ok; ++r) {
+            if (r == s_rank) { nls_peer_flags[r] = nls_flags; continue; }
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, cards[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; break; }
+            nls_peer_flags[r] = static_cast<NlFlag*>(q);
+        }
+        for (int side = 0; side < 2 && mine.ok; ++side) {
+            if (!(side ? strip.has_right : strip.has_left)) continue;
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, cards[side ? s_rank + 1 : s_rank - 1].snap, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; break; }
+            nls_peer_snap[side] = static_cast<char*>(q);
+        }
+        rc = allgather();   // did every rank manage to map what it needs?
+        if (rc) return rc;
+        for (const Card& c : cards) all_ok = std::min(all_ok, c.ok);
+    }
+    cudaFree(d_cards);
+    if (all_ok) {
+        snap_a.release(); snap_b.release();   // from here on the two arrays live in the IPC block
+        snap_a.d = reinterpret_cast<float4*>(nls_snap_block); snap_a.cap = nls_snap_cap;
+        snap_b.d = snap_a.d + nls_snap_cap; snap_b.cap = nls_snap_cap;
+        nls_ready = true;
+    }
     return BLOBS_OK;
 }
 

@@ -347,6 +347,15 @@ class World {
     uint32_t nl_stride = 0;
     NlCtl* d_nlctl = nullptr;
     NlCtl* h_nlctl = nullptr;          // pinned copy, refreshed with the step statistics
+    // ... on a strip-decomposed world: the snapshot arrays and a flag block are CUDA-IPC memory mapped by the other ranks
+    bool nls_ready = false;            // every rank mapped what it needs: lists may be used while strips are on
+    char* nls_snap_block = nullptr;    // snap_a | snap_b (then owned by this block, not by the DevBufs)
+    char* nls_peer_snap[2] = {nullptr, nullptr};      // left / right neighbour's block
+    NlFlag* nls_flags = nullptr;
+    NlFlag* nls_peer_flags[NL_MAX_RANKS] = {};
+    size_t nls_snap_cap = 0;
+    int nls_setup();
+    NlStripDev nls_dev();
     NlView nl_view();
     int nl_rebuild_chain(bool timed_launch, bool decide);
     bool nl_prev_tail = false;         // the previous substep's k_step already took the rebuild decision for this one

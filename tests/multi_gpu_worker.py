@@ -57,6 +57,9 @@ def run(rank, world, local):
     p2p = int(w.get_param(A.PARAM_STRIP_P2P))   # 1 = ghosts / migrants travel by peer-memory stores (k_strip_push), 0 = ncclSend/ncclRecv
     if os.environ.get("STRIP_TEST_EXPECT_P2P"):
         assert p2p == int(os.environ["STRIP_TEST_EXPECT_P2P"]), f"rank {rank}: peer-memory exchange active={p2p}"
+    lists = int(w.get_param(A.PARAM_LIST_ACTIVE))   # 1 = neighbour lists on the strips (ghost records by peer stores from k_step)
+    if os.environ.get("STRIP_TEST_EXPECT_LISTS"):
+        assert lists == int(os.environ["STRIP_TEST_EXPECT_LISTS"]), f"rank {rank}: list pipeline active={lists}"
     collisions = overflow = 0
     if os.environ.get("STRIP_TEST_IO") == "pipelined":
         # the frame loop of bench.py at N > 1 (pipelined distributed host I/O), with zero forces so that the world still has to
@@ -133,7 +136,8 @@ def run(rank, world, local):
                                rc["desc"]["absolute_transform"]["translation"]["x"], rc["desc"]["absolute_transform"]["translation"]["y"]]).astype(np.float32)
         bad = np.nonzero(merged.view(np.uint32) != want.view(np.uint32))[0]
         print(f"[strip test] ranks={world} spheres={n} steps={steps} migrated={migrated} collisions strips={int(t_col)} single={ref_col} "
-              f"list_overflow rank0={overflow} p2p={p2p} mismatches={len(bad)}")
+              f"list_overflow rank0={overflow} p2p={p2p} lists={lists} list_rebuilds={int(w.get_param(A.PARAM_LIST_REBUILDS))}/{int(w.get_param(A.PARAM_LIST_SUBSTEPS))} "
+              f"mismatches={len(bad)}")
         ok = len(bad) == 0 and int(t_col) == ref_col and (world == 1 or migrated > 0)
         if len(bad):
             print("first mismatches (field*n + slot):", bad[:10], merged[bad[:10]], want[bad[:10]])

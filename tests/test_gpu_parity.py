@@ -499,11 +499,12 @@ def test_events_partial_drains_lose_nothing():
         ws[1]._ck(ws[1]._lib.blobs_events_drain(ws[1]._h, A.ptr(buf), 7, C.byref(n)))
         parts.append(buf[: min(n.value, 7)])
     got = np.concatenate(parts)
-    assert got.tobytes() == whole.tobytes()
+    canon = lambda e: np.sort(e.view(np.dtype((np.void, e.dtype.itemsize))))   # recording order depends on which thread got there first
+    assert len(got) == len(whole) and np.array_equal(canon(got), canon(whole))
     assert len(ws[1].events_drain()) == 0
     ws[1].step(1 / 60)   # recording restarts cleanly
     ws[0].step(1 / 60)
-    assert ws[1].events_drain().tobytes() == ws[0].events_drain().tobytes()
+    assert np.array_equal(canon(ws[1].events_drain()), canon(ws[0].events_drain()))
 
 
 def test_full_size_cfg2_one_step_vs_grid_oracle():

@@ -45,7 +45,26 @@ def test_strip_world_peer_memory_exchange_matches_single_gpu():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     n = 2 if n < 4 else 4
-    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", STRIP_TEST_IO="pipelined")   # + bench.py's pipelined frame loop
+    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", STRIP_TEST_IO="pipelined", BLOBS_B200_LIST="0", STRIP_TEST_EXPECT_LISTS="0")   # + bench.py's pipelined frame loop
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(REPO, "tests", "multi_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+
+
+@pytest.mark.gpu
+def test_strip_world_neighbour_lists_match_single_gpu():
+    """The neighbour-list pipeline on strips (the library default when the peer mappings are available): k_step stores the ghost
+    records straight into the neighbours' arrays, every rank takes the same rebuild decision from all ranks' numbers, bodies
+    change owner at rebuilds only. Merged strips == the single-GPU world, bit for bit."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", BLOBS_B200_LIST="1", STRIP_TEST_EXPECT_LISTS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -58,13 +77,20 @@ _SHELL = {"STRIP_TEST_SCENE": "shell", "STRIP_TEST_STEPS": "8"}
 _P2P = {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"}
 # the combinations that add nothing new to the ones below only run with BLOBS_TEST_SLOW=1 (each costs ~40 s of emulation)
 _slow = pytest.mark.skipif(os.environ.get("BLOBS_TEST_SLOW") != "1", reason="redundant combination; set BLOBS_TEST_SLOW=1")
+_LISTS = {"BLOBS_B200_LIST": "1", "STRIP_TEST_EXPECT_LISTS": "1"}
 _STRIP_CASES = [
     pytest.param({}, id="gas-default"),
     pytest.param(dict(_FORCED), id="gas-forced-pool-crowded", marks=_slow),
     pytest.param({**_SHELL, **_FORCED}, id="shell-forced-pool-crowded"),
     pytest.param(dict(_SHELL), id="shell-default", marks=_slow),
-    pytest.param(dict(_P2P), id="gas-p2p", marks=_slow),   # the 3-rank case below goes through the same exchange
-    pytest.param({**_SHELL, **_P2P, **_FORCED, "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-forced"),
+    # neighbour lists on strips: ghost records stored straight into the neighbour's arrays by k_step, rebuild decision combined
+    # over all ranks, migration at rebuilds only (needs the peer-memory mappings)
+    pytest.param({**_P2P, **_LISTS}, id="gas-p2p-lists"),
+    pytest.param({**_SHELL, **_P2P, **_LISTS, "BLOBS_B200_CROWDED": "1", "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-lists-crowded"),
+    pytest.param({**_P2P, **_LISTS, "STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-p2p-lists-pipelined-host-io", marks=_slow),
+    # the cell-grid pipeline with the peer-memory exchange (k_strip_push every substep)
+    pytest.param({**_P2P, "BLOBS_B200_LIST": "0", "STRIP_TEST_EXPECT_LISTS": "0"}, id="gas-p2p-grid", marks=_slow),
+    pytest.param({**_SHELL, **_P2P, **_FORCED, "BLOBS_B200_LIST": "0", "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-grid-forced", marks=_slow),
     pytest.param({"STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-pipelined-host-io"),
 ]
 

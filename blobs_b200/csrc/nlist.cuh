@@ -51,7 +51,17 @@ __device__ __forceinline__ void nl_decide(volatile NlCtl* ctl, float lim, uint32
     nl_decide_from(ctl, ctl->max_m, ctl->sum_x, ctl->sum_y, ctl->n_sum, lim, 3.4e38f, in_step);
 }
 
-__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step) {
+// Inside a captured CUDA graph the rebuild kernels of a substep sit in the body of a conditional (IF) node: the kernel that takes
+// the decision also hands it to that node (cudaGraphSetConditional), so a substep that keeps its lists launches nothing at all for
+// the rebuild. With plain launches (no graph, profiling, the host-compiled test build) the same kernels are launched
+// unconditionally and return at once when NlCtl::need is not set.
+__device__ __forceinline__ void nl_set_cond(unsigned long long handle, unsigned int need) {
+#ifndef BLOBS_EMU
+    if (handle != 0ull) cudaGraphSetConditional((cudaGraphConditionalHandle)handle, need);
+#endif
+}
+
+__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step, unsigned long long cond) {
     if (threadIdx.x != 0u || blockIdx.x != 0u) return;
     if (ctl->decided) {   // k_step's last CTA has decided already; only a host request can still change the verdict
         ctl->decided = 0u;
@@ -64,9 +74,11 @@ __global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_
                 ctl->rebuilds += in_step;
             }
         }
+        nl_set_cond(cond, ctl->need);
         return;
     }
     nl_decide(ctl, lim, in_step);
+    nl_set_cond(cond, ctl->need);
 }
 
 // the two tables are picked by ternaries (a runtime index into a kernel-parameter array would copy the struct to local memory)
@@ -367,6 +379,7 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
             __threadfence();
             nl_decide(L.ctl, L.lim, 1u);
             L.ctl->decided = 1u;
+            nl_set_cond(P.nl_cond_next, L.ctl->need);
         }
     }
     if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(32) k_nls_publish(NlCtl* ctl, NlStripDev X) {
 }
 
 __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, float lim, float xlim, void* send_l, void* send_r, uint32_t in_step,
-                                                   DeviceStats* stats) {
+                                                   DeviceStats* stats, unsigned long long cond) {
     const uint32_t lane = threadIdx.x;
     unsigned int M = 0u, N = 0u;
     float SX = 0.f, SY = 0.f;
@@ -443,6 +456,7 @@ __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, flo
             hl->n_ghost = hl->n_mig = hl->overflow = 0u;
             hr->n_ghost = hr->n_mig = hr->overflow = 0u;
         }
+        nl_set_cond(cond, ctl->need);
     }
 }
 

@@ -95,6 +95,7 @@ struct SubstepParams {
     uint32_t over_parity;           // which DeviceStats::over_count entry this substep appends to
     uint32_t pool_min;              // (unused since the cooperative gather; kept for the parameter's ABI)
     uint32_t nl_tail_decide;        // list pipeline: k_step is this substep's only publisher, so its last CTA decides for the next substep
+    unsigned long long nl_cond_next; // ... and, inside a captured graph, tells the IF node that wraps the next substep's rebuild kernels (0 = none)
     uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list
 };
 

@@ -247,6 +247,8 @@ int World::reset() {
     pending_col.clear();
     topo_dirty = bp_dirty = true;
     shadow_valid = false;
+    n_worlds = 1;        // the batched-world partition goes with the bodies
+    cur_world = 0;
     return BLOBS_OK;
 }
 
@@ -1131,13 +1133,14 @@ int World::timed(KClass k, F&& f) {
     Span span(kclass_span[k]);
     EvPair* ep = nullptr;
     EvPair cap{};
-    if (profiling && capturing) {
+    const bool timed_here = profiling && (!profile_main_only || k == KC_MAIN || k == KC_CROWDED);
+    if (timed_here && capturing) {
         // inside a graph capture: timing events become external event-record nodes, re-recorded by every replay
         CU(cudaEventCreate(&cap.a));
         CU(cudaEventCreate(&cap.b));
         cap.k = k;
         CU(cudaEventRecordWithFlags(cap.a, stream, cudaEventRecordExternal));
-    } else if (profiling) {
+    } else if (timed_here) {
         if (ev_used == ev_pool.size()) {
             EvPair p{};
             CU(cudaEventCreate(&p.a));
@@ -1151,7 +1154,7 @@ int World::timed(KClass k, F&& f) {
     f();
     launches++;
     if (ep) CU(cudaEventRecord(ep->b, stream));
-    if (profiling && capturing) {
+    if (timed_here && capturing) {
         CU(cudaEventRecordWithFlags(cap.b, stream, cudaEventRecordExternal));
         cap_evs->push_back(cap);
     }
@@ -1198,7 +1201,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     };
 #define MIXV(v) { auto t__ = (v); mix(&t__, sizeof(t__)); }
     MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
-    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling)
+    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling) MIXV(profile_main_only)
     MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
     MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim) MIXV(n_loose) MIXV(n_active_cols)
     const BodyArrays B = body_arrays();
@@ -1477,7 +1480,8 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     // automatic broadphase choice (BLOBS_PARAM_LIST 2): neighbour lists pay while they survive several substeps; when the scene is
     // so agitated that they are rebuilt (almost) every substep, sorting straight into cells every substep is the cheaper way to the
     // same contact set. Lists are tried again after a hold that doubles each time they turn out to be still too short-lived.
-    if (list_mode == 2 && !strip_on && substeps_run) {
+    // (strips: every rank sees the same rebuild counts - the decision is collective - so all ranks switch in the same call)
+    if (list_mode == 2 && (!strip_on || nls_ready) && substeps_run) {
         if (nl_on) {
             const double dr = (double)(h_nlctl->rebuilds - nl_seen_rebuilds), ds = (double)(h_nlctl->substeps - nl_seen_substeps);
             if (ds > 0 && dr > 0.5 * ds + 1.0) {
@@ -1506,6 +1510,10 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
         if ((aliased || oversized) && !strip_on) bp_dirty = true;  // strip mode: a rebuild is a collective, keep the table
     }
     if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");
+    // strip mode: results are not valid after either of these. The statistics above are complete, and every rank sees the flag in
+    // the same call (a rank that returned early would leave its neighbours waiting), so the call itself has run to its end.
+    if (h_stats->nan_flag & 8u) return fail(BLOBS_ERR_CUDA, "strip exchange: a neighbour's message did not arrive in time (stale ghosts were used); results are invalid");
+    if (h_stats->nan_flag & 4u) return fail(BLOBS_ERR_CAPACITY, "strip exchange: ghost / migration message or owned-body list overflowed (raise ghost_capacity / migrate_capacity); results are invalid");
     return BLOBS_OK;
 }
 
@@ -2496,6 +2504,7 @@ int World::kernel_info(BlobsKernelInfo* out) const {
 int World::profile_enable(int on) {
     CU(cudaStreamSynchronize(stream));
     profiling = on != 0;
+    profile_main_only = on == 2;   // 2: events around the dominant kernel only (its roofline number, with the rest of the step unperturbed)
     ev_used = 0;
     for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0.f; prof_launches[i] = 0; }
     return BLOBS_OK;

@@ -71,12 +71,13 @@ struct DevBuf {
         if (e != cudaSuccess) return e;
         if (cap) {
             e = cudaMemcpyAsync(nd, d, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) { cudaFree(nd); return e; }
         }
         e = cudaMemsetAsync(nd + cap, 0, (ncap - cap) * sizeof(T), st);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) { cudaFree(nd); return e; }
         if (d) {
-            cudaStreamSynchronize(st);
+            e = cudaStreamSynchronize(st);   // the copy out of the old block must have finished before it is freed
+            if (e != cudaSuccess) { cudaFree(nd); return e; }
             cudaFree(d);
         }
         d = nd;
@@ -409,7 +410,7 @@ class World {
 
     // profiling
     uint64_t launches = 0;
-    bool profiling = false;
+    bool profiling = false, profile_main_only = false;
     struct EvPair { cudaEvent_t a, b; int k; };
     // one captured CUDA graph per (last-step-of-call?) flavour of Physics::integrate; replayed while its key matches
     struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t key = 0, launches = 0; std::vector<EvPair> evs; bool profiled = false; };

@@ -153,18 +153,25 @@ class World:
         self._ck(self._lib.blobs_constraint_clear(self._h))
 
     # ---- stepping
+    def _step_rc(self, rc, st):
+        """A strip-decomposed world reports an overflowed message / a neighbour that did not answer through the return code AND
+        bits 2 / 3 of nan_detected. Ranks must keep stepping together (one that raised here would leave its peers waiting for its
+        messages), so those two are returned in the stats (key "strip_error") instead of raised; everything else raises."""
+        d = st.as_dict()
+        if rc in (A.ERR_CAPACITY, A.ERR_CUDA) and (d["nan_detected"] & 12):
+            d["strip_error"] = (self._lib.blobs_last_error(self._h) or b"").decode()
+            return d
+        self._ck(rc)
+        return d
+
     def step(self, delta=1.0 / 60.0, n=1):
         st = A.StepStats()
-        if n == 1:
-            self._ck(self._lib.blobs_step(self._h, delta, C.byref(st)))
-        else:
-            self._ck(self._lib.blobs_step_n(self._h, delta, n, C.byref(st)))
-        return st.as_dict()
+        rc = self._lib.blobs_step(self._h, delta, C.byref(st)) if n == 1 else self._lib.blobs_step_n(self._h, delta, n, C.byref(st))
+        return self._step_rc(rc, st)
 
     def fixed_step(self, frame_time):
         st = A.StepStats()
-        self._ck(self._lib.blobs_fixed_step(self._h, frame_time, C.byref(st)))
-        return st.as_dict()
+        return self._step_rc(self._lib.blobs_fixed_step(self._h, frame_time, C.byref(st)), st)
 
     # ---- state
     def _u64(self, fn):
@@ -344,6 +351,7 @@ class World:
         return out
 
     def profile_enable(self, on=True):
+        """0 / False off, 1 / True every kernel class, 2 the dominant kernel only"""
         self._ck(self._lib.blobs_profile_enable(self._h, int(on)))
 
     def profile_read(self):

@@ -323,10 +323,11 @@ typedef struct BlobsKernelInfo {
     uint32_t n_simple_bodies, n_multi_bodies, n_spring_bodies, n_islands;
 } BlobsKernelInfo;
 int32_t blobs_kernel_info(const BlobsWorld* w, BlobsKernelInfo* out);
-/* CUDA-event timing of individual kernel classes during the next steps (0 = off). Used for the roofline. */
+/* CUDA-event timing of individual kernel classes during the next steps (0 = off, 1 = every kernel class, 2 = the dominant kernel
+ * (contact + update kernel and k_crowded) only, so that the rest of the step runs unperturbed). Used for the roofline. */
 int32_t blobs_profile_enable(BlobsWorld* w, int32_t on);
 /* ms accumulated per kernel class since enable: [0]=main/contacts, [1]=scan, [2]=scatter, [3]=springs, [4]=joints, [5]=integrate, [6]=other,
- * [7]=strip pack, [8]=strip ghost binning/scatter/hand-over, [9]=NCCL ghost exchange */
+ * [7]=strip pack, [8]=strip ghost binning/scatter/hand-over, [9]=ghost exchange, [10]=k_crowded, [11]=neighbour-list build, [12]=list decision */
 int32_t blobs_profile_read(BlobsWorld* w, float* ms, uint64_t* launches, size_t n);
 
 /* ---- perf counters: the reference's process-global registry (perf_counters.rs:3-87). blobs_step* feeds "collisions"

@@ -73,6 +73,7 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_CROWDED")) crowded_mode = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_TUNE")) tune = std::atoi(e);
     if (const char* e = std::getenv("BLOBS_B200_LIST")) list_mode = std::atoi(e);
+    if (const char* e = std::getenv("BLOBS_B200_COND")) cond_nodes = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_SKIN")) skin_frac = (float)std::atof(e);
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
@@ -121,6 +122,7 @@ int World::init() {
 World::~World() {
     // strip mode: the stream may be parked inside a collective whose peer is gone — never block process exit on it
     if (stream && !strip_on) cudaStreamSynchronize(stream);
+    if (s_body) cudaStreamDestroy(s_body);
     if (io_ready) { cudaStreamSynchronize(s_h2d); cudaStreamDestroy(s_h2d); cudaStreamSynchronize(s_d2h); cudaStreamDestroy(s_d2h); }
     for (cudaEvent_t e : {ev_up_done[0], ev_up_done[1], ev_up_free[0], ev_up_free[1], ev_snap_ready, ev_snap_free}) if (e) cudaEventDestroy(e);
     d_forces_up[0].release(); d_forces_up[1].release(); d_pos_snap.release();
@@ -1057,6 +1059,7 @@ NlStripDev World::nls_dev() {
 int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     const NlView L = nl_view();
     const ColliderArrays C = col_arrays();
+    const BodyArrays B = body_arrays();
     const uint32_t nc = (uint32_t)cols.slots();
     const size_t tn = table_entries();
     auto run = [&](KClass k, auto&& f) -> int {
@@ -1067,48 +1070,99 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
         return BLOBS_OK;
     };
     int rc = BLOBS_OK;
-    if (strip_on) {
-        // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records); a
-        // rebuild re-selects ghosts and hands migrants over with the message exchange of the grid pipeline, gated like the rest.
-        const NlStripDev X = nls_dev();
-        const BodyArrays B = body_arrays();
-        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats); });
-        if (rc) return rc;
-        if (!nc) return BLOBS_OK;
-        rc = run(KC_PACK, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nls_pack)(B, C, strip, d_cowned.d, msg[0], msg[1], nc, d_nlctl); });
-        if (rc) return rc;
-        rc = run(KC_NCCL, [&] { BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_nls_push)(strip, msg[0], msg[1], X, d_nlctl, d_stats); });
-        if (rc) return rc;
-        rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, d_cowned.d); });
-        if (rc) return rc;
-        rc = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_nls_bin_ghosts)(grid, strip, X, L, gcell.d, d_stats); });
-        if (rc) return rc;
-        rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
-        if (rc) return rc;
-        rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, d_cowned.d); });
-        if (rc) return rc;
-        rc = run(KC_GHOST, [&] {
-            BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_nls_finish)(B, C, strip, msg[0], msg[1], X, L, gcell.d, d_owned.d, d_cowned.d, olist.d, d_ocount,
-                                                                                                         opos.d, (uint32_t)olist.cap, d_stats, cur_is_a ? snap_a.d : snap_b.d);
-        });
-        if (rc) return rc;
-        return run(KC_NLBUILD, [&] {
-            BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, d_cowned.d, strip);
-        });
+    // Inside a graph capture the rebuild kernels go into the body of an IF node whose condition the deciding kernel sets on the
+    // device (cudaGraphSetConditional); otherwise they are launched unconditionally and return at once when NlCtl::need is 0.
+    unsigned long long h_cur = 0ull;
+    bool use_cond = false;
+#ifndef BLOBS_EMU
+    cudaGraph_t cap_graph = nullptr;
+    use_cond = capturing && cond_nodes && !profiling && timed_launch && nc != 0;
+    if (use_cond) {
+        cudaStreamCaptureStatus cs;
+        CU(cudaStreamGetCaptureInfo(stream, &cs, nullptr, &cap_graph, nullptr, nullptr));
+        if (nl_cond_pending) {   // created by the previous substep, whose k_step sets it
+            h_cur = nl_cond_pending;
+            nl_cond_pending = 0ull;
+        } else {
+            cudaGraphConditionalHandle h;
+            CU(cudaGraphConditionalHandleCreate(&h, cap_graph, 0, cudaGraphCondAssignDefault));
+            h_cur = (unsigned long long)h;
+        }
     }
-    if (decide) rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u); });
+#endif
+    const NlStripDev X = nls_dev();
+    if (strip_on) {
+        // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records)
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats, h_cur); });
+    } else if (decide) {
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u, h_cur); });
+    }
     if (rc) return rc;
     if (!nc) return BLOBS_OK;
-    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, nullptr); });
-    if (rc) return rc;
-    rc = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
-    if (rc) return rc;
-    rc = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, nullptr); });
-    if (rc) return rc;
-    rc = run(KC_NLBUILD, [&] {
-        BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, nullptr, strip);
-    });
-    return rc;
+    const uint8_t* cown = strip_on ? d_cowned.d : nullptr;
+    auto rebuild = [&]() -> int {
+        int r;
+        if (strip_on) {   // a rebuild re-selects ghosts and hands migrants over with the message exchange of the grid pipeline
+            r = run(KC_PACK, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nls_pack)(B, C, strip, d_cowned.d, msg[0], msg[1], nc, d_nlctl); });
+            if (r) return r;
+            r = run(KC_NCCL, [&] { BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_nls_push)(strip, msg[0], msg[1], X, d_nlctl, d_stats); });
+            if (r) return r;
+        }
+        r = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, cown); });
+        if (r) return r;
+        if (strip_on) {
+            r = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_nls_bin_ghosts)(grid, strip, X, L, gcell.d, d_stats); });
+            if (r) return r;
+        }
+        r = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
+        if (r) return r;
+        r = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, cown); });
+        if (r) return r;
+        if (strip_on) {
+            r = run(KC_GHOST, [&] {
+                BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap + 4 * (size_t)strip.mcap, 256), 256, 0, stream, k_nls_finish)(B, C, strip, msg[0], msg[1], X, L, gcell.d, d_owned.d, d_cowned.d, olist.d, d_ocount,
+                                                                                                             opos.d, (uint32_t)olist.cap, d_stats, cur_is_a ? snap_a.d : snap_b.d);
+            });
+            if (r) return r;
+        }
+        return run(KC_NLBUILD, [&] {
+            BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, cown, strip);
+        });
+    };
+#ifndef BLOBS_EMU
+    if (use_cond) {
+        cudaStreamCaptureStatus cs;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        CU(cudaStreamGetCaptureInfo(stream, &cs, nullptr, &cap_graph, &deps, &nd));
+        cudaGraphNodeParams np = {};   // (a union with non-trivial members: value-initialised, then the fields that matter)
+        std::memset(static_cast<void*>(&np), 0, sizeof(np));
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = (cudaGraphConditionalHandle)h_cur;
+        np.conditional.type = cudaGraphCondTypeIf;
+        np.conditional.size = 1;
+        cudaGraphNode_t cnode = nullptr;
+        CU(cudaGraphAddNode(&cnode, cap_graph, deps, nd, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        CU(cudaStreamUpdateCaptureDependencies(stream, &cnode, 1, cudaStreamSetCaptureDependencies));
+        // the body: the very same (still self-gating) rebuild kernels, captured into the IF node's graph through a second stream
+        if (!s_body) CU(cudaStreamCreateWithFlags(&s_body, cudaStreamNonBlocking));
+        CU(cudaStreamBeginCaptureToGraph(s_body, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        std::swap(stream, s_body);
+        const uint64_t l0 = launches;
+        rc = rebuild();
+        cond_launches += launches - l0;
+        launches = l0;   // counted per executed rebuild (finish_stats), not per replay
+        std::swap(stream, s_body);
+        cudaGraph_t out = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s_body, &out);
+        if (rc) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture (IF-node body)");
+        cond_nodes_built++;
+        return BLOBS_OK;
+    }
+#endif
+    return rebuild();
 }
 
 // Outside a step (scene queries): bring the cell grid up to date with the current snapshots, and learn which table holds it.
@@ -1233,12 +1287,15 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
         if (nsub & 1u) cur_is_a = !cur_is_a;
         if (strip_on) nccl_exchanges += nsub;   // one exchange per substep; its parity picks the receive buffers baked into the graph
         launches += gs.launches;
+        cond_per_rebuild_live = gs.cond_per_rebuild;
         graph_replays++;
         graphs_launched.push_back(&gs);
         return BLOBS_OK;
     }
     destroy_graph(gs);
     const uint64_t l0 = launches;
+    cond_launches = 0;
+    cond_nodes_built = 0;
     capturing = true;
     cap_evs = &gs.evs;
     cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
@@ -1254,8 +1311,10 @@ int World::run_step(uint32_t nsub, float delta, bool last, bool allow_graph) {
     if (e != cudaSuccess) { gs.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
     gs.key = key;
     gs.launches = launches - l0;
+    gs.cond_per_rebuild = cond_nodes_built ? cond_launches / cond_nodes_built : 0;
     gs.profiled = profiling;
     graph_captures++;
+    cond_per_rebuild_live = gs.cond_per_rebuild;
     CU(cudaGraphLaunch(gs.exec, stream));
     graphs_launched.push_back(&gs);
     return BLOBS_OK;
@@ -1315,6 +1374,18 @@ int World::launch_substep(const SubstepParams& P_in) {
         rc = nl_rebuild_chain(true, !nl_prev_tail);
         if (rc) return rc;
         nl_prev_tail = P.nl_tail_decide != 0u;
+        P.nl_cond_next = 0ull;
+#ifndef BLOBS_EMU
+        if (capturing && cond_nodes && !profiling && P.nl_tail_decide && nl_sub_i + 1 < nl_sub_n && cols.slots()) {
+            // this substep's k_step decides for the next one: the IF node of the next substep needs its handle now
+            cudaStreamCaptureStatus cs;
+            cudaGraph_t cg = nullptr;
+            CU(cudaStreamGetCaptureInfo(stream, &cs, nullptr, &cg, nullptr, nullptr));
+            cudaGraphConditionalHandle h;
+            CU(cudaGraphConditionalHandleCreate(&h, cg, 0, cudaGraphCondAssignDefault));
+            P.nl_cond_next = nl_cond_pending = (unsigned long long)h;
+        }
+#endif
     }
     if (n_sb) {
         rc = timed(KC_SPRINGS, [&] { BLOBS_LAUNCH(cdiv(n_sb, 128), 128, 0, stream, k_springs)(P, B, sb_body.d, sb_off.d, sb_edge.d, d_springs.d, n_sb); });
@@ -1338,12 +1409,9 @@ int World::launch_substep(const SubstepParams& P_in) {
             const unsigned gdim = cdiv(strip_on ? std::max<uint32_t>(olaunch_dim, 1) : nb, 256);
             const StripView sv = strip_view();
 #define BLOBS_LAUNCH_MAIN(F, O, PL) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<F, O, 4, 4, PL>)(P, grid, K, B, C, bp, R, d_stats, sv)
-            if (pooled && tune == 2) {   // BLOBS_PARAM_TUNE 2: cooperative gather with 2 instead of 4 candidates per lane in flight
+            if (pooled) {   // contact-rich state: warp-cooperative resolution (2 candidates per lane in flight; 4 measured the same)
                 if (fused) BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<true, true, 2, 4, true>)(P, grid, K, B, C, bp, R, d_stats, sv);
                 else BLOBS_LAUNCH(gdim, 256, 0, stream, k_main<false, true, 2, 4, true>)(P, grid, K, B, C, bp, R, d_stats, sv);
-            } else if (pooled) {   // contact-rich state: warp-cooperative resolution
-                if (fused) BLOBS_LAUNCH_MAIN(true, true, true);
-                else BLOBS_LAUNCH_MAIN(false, true, true);
             } else if (fused) {
                 if (ordered) BLOBS_LAUNCH_MAIN(true, true, false);
                 else BLOBS_LAUNCH_MAIN(true, false, false);
@@ -1423,9 +1491,13 @@ int World::launch_substep(const SubstepParams& P_in) {
 int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
     const float step_delta = delta / (float)nsub;
     nl_prev_tail = false;   // the first substep of a call always runs k_nl_decide (host requests are honoured there)
+    nl_cond_pending = 0ull;
     for (uint32_t i = 0; i < nsub; ++i) {
         SubstepParams P;
         P.nl_tail_decide = 0u;
+        P.nl_cond_next = 0ull;
+        nl_sub_i = i;
+        nl_sub_n = nsub;
         P.dt = step_delta;
         P.ratio_first = step_delta / old_dt;        // physics.rs:338
         P.ratio_rest = step_delta / step_delta;     // every later body sees old_dt == dt (Q2)
@@ -1495,6 +1567,8 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
             bp_dirty = true;
         }
     }
+    if (nl_on && cond_per_rebuild_live) launches += (h_nlctl->rebuilds - nl_seen_rebuilds) * cond_per_rebuild_live;   // IF-node bodies that ran
+    cond_per_rebuild_live = 0;
     nl_seen_rebuilds = h_nlctl->rebuilds;
     nl_seen_substeps = h_nlctl->substeps;
     // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep

@@ -337,7 +337,7 @@ class World {
     int list_mode = 2;                 // BLOBS_PARAM_LIST: 0 = cell grid rebuilt every substep (k_main), 1 = neighbour lists (k_step), 2 = automatic
     int nl_grid_hold = 0, nl_next_hold = 32;   // automatic mode: step calls left on the grid pipeline before lists are tried again
     unsigned long long nl_seen_rebuilds = 0, nl_seen_substeps = 0;
-    float skin_frac = 0.4f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
+    float skin_frac = 0.6f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
     float nl_skin = 0.f;
     bool nl_on = false;                // the current broadphase is the list pipeline
     bool nl_force_pending = false;     // host-side changes since the last step that invalidate the lists
@@ -359,6 +359,12 @@ class World {
     NlStripDev nls_dev();
     NlView nl_view();
     int nl_rebuild_chain(bool timed_launch, bool decide);
+    // captured steps: the rebuild kernels of a substep live in the body of a conditional (IF) graph node
+    bool cond_nodes = true;            // BLOBS_B200_COND=0: launch them unconditionally (self-gating) inside graphs too
+    cudaStream_t s_body = nullptr;     // capture stream for the IF-node bodies
+    unsigned long long nl_cond_pending = 0ull;   // handle created for the NEXT substep's IF node (set by this substep's k_step)
+    uint32_t nl_sub_i = 0, nl_sub_n = 0;
+    uint64_t cond_launches = 0, cond_nodes_built = 0, cond_per_rebuild_live = 0;
     bool nl_prev_tail = false;         // the previous substep's k_step already took the rebuild decision for this one
     int nl_rebuild_now();
 
@@ -413,7 +419,7 @@ class World {
     bool profiling = false, profile_main_only = false;
     struct EvPair { cudaEvent_t a, b; int k; };
     // one captured CUDA graph per (last-step-of-call?) flavour of Physics::integrate; replayed while its key matches
-    struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t key = 0, launches = 0; std::vector<EvPair> evs; bool profiled = false; };
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; uint64_t key = 0, launches = 0, cond_per_rebuild = 0; std::vector<EvPair> evs; bool profiled = false; };
     GraphSlot gslot[2];
     bool graphs_on = true, capturing = false;
     std::vector<EvPair>* cap_evs = nullptr;

@@ -535,7 +535,7 @@ def test_full_size_cfg2_one_step_vs_grid_oracle():
     assert np.isfinite(p1).all()
 
 
-def _vs_cpu_checker(scene, checkpoints, **params):
+def _vs_cpu_checker(scene, checkpoints, params=None):
     """GPU world vs the all-cores CPU checker (oracle/grid_omp.cpp, pinned to the sequential oracle by tests/test_grid_omp.py):
     state bit-equal at every checkpoint, same pair count."""
     import blobs_b200
@@ -543,7 +543,7 @@ def _vs_cpu_checker(scene, checkpoints, **params):
 
     g = blobs_b200.World(gravity=scene.gravity)
     S.build(g, scene)
-    for k, v in params.items():
+    for k, v in (params or {}).items():
         g.set_param(k, v)
     o = grid_omp.GridOmpWorld(scene)
     done = coll_g = coll_o = 0
@@ -572,7 +572,7 @@ def test_full_size_cfg2_twelve_steps_vs_cpu_checker():
 def test_full_size_contact_rich_start_vs_cpu_checker(pipeline):
     """1 048 576 spheres on a pitch-0.9 lattice (every sphere overlaps its four neighbours from the first substep on, ~2 M pairs per
     substep): the contact-rich paths - cooperative gather, k_crowded hand-over, list rebuilds - checked at scale, 6 steps."""
-    g, coll = _vs_cpu_checker(S.cfg2_dense(seed=1, side=1024), (1, 6), **_PIPELINES[pipeline])
+    g, coll = _vs_cpu_checker(S.cfg2_dense(seed=1, side=1024), (1, 6), params=_PIPELINES[pipeline])
     assert coll > 6 * 8 * 1_000_000
 
 

@@ -631,6 +631,12 @@ __device__ __forceinline__ bool gather_coop(const GridDesc& g, const Broadphase&
 // latency overlaps the contact pass. Returns the pre-clamp position in (sx, sy): that is what the collider snapshot is
 // built from (physics.rs:360-366 runs before apply_constraints).
 // ------------------------------------------------------------------------------------------------
+// acceleration / pending velocity_request of a body as update_objects will see them (SubstepParams::acc_zero: known to be none)
+__device__ __forceinline__ float2 load_acc(const SubstepParams& P, const BodyArrays& B, uint32_t b) {
+    return P.acc_zero ? make_float2(0.f, 0.f) : B.acc[b];
+}
+__device__ __forceinline__ bool load_hv(const SubstepParams& P, const BodyArrays& B, uint32_t b) { return P.acc_zero ? false : B.has_vreq[b] != 0; }
+
 __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Constraints& K, const BodyArrays& B, uint32_t b,
                                                uint32_t flags, float gmod, float px, float py, float2 po, float2 a, bool hv,
                                                float& sx, float& sy, float& rot_out, DeviceStats* stats) {
@@ -638,7 +644,7 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
     if (flags & BF_ROT) rot = B.rot[b];
     if (flags & BF_STATIC) {                                     // physics.rs:327-332
         B.pos_old[b] = make_float2(px, py);
-        B.acc[b] = make_float2(0.f, 0.f);
+        if (!P.acc_zero) B.acc[b] = make_float2(0.f, 0.f);
         if (P.write_vel) B.vel[b] = make_float2(0.f, 0.f);
     } else {
         if (hv) {                                                // physics.rs:334-336
@@ -664,7 +670,7 @@ __device__ __forceinline__ void integrate_body(const SubstepParams& P, const Con
             B.rot[b] = rot;
             B.torque[b] = 0.0f;
         }
-        B.acc[b] = make_float2(0.f, 0.f);
+        if (!P.acc_zero) B.acc[b] = make_float2(0.f, 0.f);
         // calculated_velocity (physics.rs:357) is only observable through springs, events and host reads, so it is
         // materialised on the substeps where one of those can see it (host sets write_vel)
         if (P.write_vel) B.vel[b] = make_float2(fdiv(dx, P.dt), fdiv(dy, P.dt));
@@ -858,8 +864,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_main(SubstepParams P, GridDes
     const float2 mg = B.bmg[bl];
     float2 p = B.pos[bl];
     const float2 po = B.pos_old[bl];
-    const float2 acc0 = B.acc[bl];
-    const bool hv = B.has_vreq[bl] != 0;
+    const float2 acc0 = load_acc(P, B, bl);
+    const bool hv = load_hv(P, B, bl);
     const uint32_t wbase = g.n_worlds > 1u ? B.bworld[bl] * g.ncells : 0u;
     uint32_t cs = 0;
     uint4 cc = make_uint4(0u, 0u, 0u, 0u);
@@ -1102,8 +1108,8 @@ __global__ void __launch_bounds__(128) k_multi(SubstepParams P, GridDesc g, Cons
         const uint32_t c0 = mb_off[i], c1 = mb_off[i + 1];
         float2 p = B.pos[b];
         const float2 po = B.pos_old[b];
-        const float2 acc0 = B.acc[b];
-        const bool hv = B.has_vreq[b] != 0;
+        const float2 acc0 = load_acc(P, B, b);
+        const bool hv = load_hv(P, B, b);
         const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
         bool deferred = false;
         if (P.collisions_enabled) {
@@ -1277,8 +1283,8 @@ __global__ void __launch_bounds__(32 * CROWD_WARPS) k_crowded(SubstepParams P, G
         if (lane == 0) {
             if (FUSED && !(flags & BF_JOINTED)) {
                 const float2 po = B.pos_old[b];
-                const float2 acc0 = B.acc[b];
-                const bool hv = B.has_vreq[b] != 0;
+                const float2 acc0 = load_acc(P, B, b);
+                const bool hv = load_hv(P, B, b);
                 float sx, sy, rot;
                 integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
                 for (uint32_t k = c0; k < c1; ++k) {
@@ -1317,7 +1323,7 @@ __global__ void __launch_bounds__(256) k_integrate(SubstepParams P, GridDesc g, 
         const float2 p = B.pos[b];
         const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
         float sx, sy, rot;
-        integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], B.acc[b], B.has_vreq[b] != 0, sx, sy, rot, stats);
+        integrate_body(P, K, B, b, flags, B.bmg[b].y, p.x, p.y, B.pos_old[b], load_acc(P, B, b), load_hv(P, B, b), sx, sy, rot, stats);
         if (col >= 0) {
             const uint32_t cf = Cc.cconst[col].y;
             if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, (uint32_t)col, cf, wbase, sx, sy, rot, na);

@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
     const float2 mg = B.bmg[bl];
     float2 p = B.pos[bl];
     const float2 po = B.pos_old[bl];
-    const float2 acc0 = B.acc[bl];
-    const bool hv = B.has_vreq[bl] != 0;
+    const float2 acc0 = load_acc(P, B, bl);
+    const bool hv = load_hv(P, B, bl);
     uint32_t cs = 0;
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 hd = make_uint4(0u, 0u, NL_INACTIVE, 0u);

@@ -94,6 +94,8 @@ struct SubstepParams {
     uint32_t crowded;               // bodies whose contact list overflows are deferred to k_crowded (else resolved inline)
     uint32_t over_parity;           // which DeviceStats::over_count entry this substep appends to
     uint32_t pool_min;              // (unused since the cooperative gather; kept for the parameter's ABI)
+    uint32_t acc_zero;              // every body's acceleration is zero and no velocity_request is pending (any substep after the first of a call
+                                    // in a world without springs: update_objects consumed both, physics.rs:334-336,350-355): neither is read or rewritten
     uint32_t nl_tail_decide;        // list pipeline: k_step is this substep's only publisher, so its last CTA decides for the next substep
     unsigned long long nl_cond_next; // ... and, inside a captured graph, tells the IF node that wraps the next substep's rebuild kernels (0 = none)
     uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list

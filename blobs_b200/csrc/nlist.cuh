@@ -84,20 +84,37 @@ __global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_
 // the two tables are picked by ternaries (a runtime index into a kernel-parameter array would copy the struct to local memory)
 __device__ __forceinline__ uint32_t* nl_tab(const NlView& L, uint32_t which) { return which ? L.tab[1] : L.tab[0]; }
 __device__ __forceinline__ uint32_t* nl_tile(const NlView& L, uint32_t which) { return which ? L.tile[1] : L.tile[0]; }
-constexpr unsigned NL_GATED_CTAS = 148 * 8;   // the gated kernels run grid-stride loops on a fixed grid: returning at once costs ~2 us
+constexpr unsigned NL_GATED_CTAS = 148 * 8;
+// Which colliders a rebuild kernel visits: every slot - or, on a strip-decomposed world (arrays are indexed by GLOBAL slot there,
+// 16 M slots for 2 M owned), the colliders of the bodies in the owned list. Returns NO_SLOT for "nothing at index i".
+struct NlEnum {
+    const uint32_t* olist;     // nullptr = all collider slots
+    const uint32_t* ocount;
+    const uint2* binfo;
+    uint32_t n;                // collider slots (all-slot mode) / launch bound of the owned list
+    __device__ __forceinline__ uint32_t limit() const { return olist != nullptr ? min(n, __ldg(ocount)) : n; }
+    __device__ __forceinline__ uint32_t at(uint32_t i) const {
+        if (olist == nullptr) return i;
+        const uint32_t b = olist[i];
+        if (b == NO_SLOT) return NO_SLOT;
+        const int32_t col = (int32_t)binfo[b].y;
+        return col >= 0 ? (uint32_t)col : NO_SLOT;
+    }
+};   // the gated kernels run grid-stride loops on a fixed grid: returning at once costs ~2 us
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Rebuild, step 1-3: counting sort of the current snapshots into cells (the grid pipeline's k_count / k_scan / k_scatter, gated
 // by the device flag and addressing the table pair by the device parity).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_nl_count(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L, uint32_t n_colliders,
-                                                  const uint8_t* __restrict__ cowned) {
+__global__ void __launch_bounds__(256) k_nl_count(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L, NlEnum E) {
     if (L.ctl->need == 0u) return;
     const uint32_t nx = (L.ctl->parity & 1u) ^ 1u;
     uint32_t* const tab_next = nl_tab(L, nx);
     uint32_t* const tile_next = nl_tile(L, nx);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
-        if (cowned != nullptr && !cowned[c]) continue;
+    const uint32_t lim = E.limit();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < lim; i += gridDim.x * blockDim.x) {
+        const uint32_t c = E.at(i);
+        if (c == NO_SLOT) continue;
         if (!(Cc.cconst[c].y & CF_ACTIVE)) continue;
         const float2 a = Cc.cabs[c];
         const uint32_t wbase = g.n_worlds > 1u ? bworld[Cc.cparent[c]] * g.ncells : 0u;
@@ -113,11 +130,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_nl_scan(NlView L, uint32_t n) 
     scan_tile(nl_tab(L, nx), n, nl_tab(L, cur), n, nl_tile(L, nx), nl_tile(L, cur));
 }
 
-__global__ void __launch_bounds__(256) k_nl_scatter(ColliderArrays Cc, NlView L, uint32_t n_colliders, const uint8_t* __restrict__ cowned) {
+__global__ void __launch_bounds__(256) k_nl_scatter(ColliderArrays Cc, NlView L, NlEnum E) {
     if (L.ctl->need == 0u) return;
     const uint32_t* __restrict__ tab = nl_tab(L, (L.ctl->parity & 1u) ^ 1u);
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
-        if (cowned != nullptr && !cowned[c]) continue;
+    const uint32_t lim = E.limit();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < lim; i += gridDim.x * blockDim.x) {
+        const uint32_t c = E.at(i);
+        if (c == NO_SLOT) continue;
         const uint4 cc = Cc.cconst[c];
         if (!(cc.y & CF_ACTIVE)) continue;
         const uint2 cr = Cc.ccell[c];
@@ -136,8 +155,8 @@ __global__ void __launch_bounds__(256) k_nl_scatter(ColliderArrays Cc, NlView L,
 constexpr int NL_BUILD_THREADS = 128;
 
 __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, ColliderArrays Cc, const uint32_t* __restrict__ bworld, NlView L,
-                                                               float4* __restrict__ snap_cur, uint32_t n_colliders,
-                                                               const uint8_t* __restrict__ cowned, StripDesc S) {
+                                                               float4* __restrict__ snap_cur, NlEnum E, const uint8_t* __restrict__ cowned,
+                                                               StripDesc S) {
     __shared__ uint32_t keep[NL_CAP * NL_BUILD_THREADS];
     NlCtl* const ctl = L.ctl;
     if (ctl->need == 0u) return;   // grid-uniform
@@ -145,7 +164,10 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
     const uint32_t* __restrict__ tab = nl_tab(L, nx);
     const float4* __restrict__ hot = L.hot;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t c = blockIdx.x * (uint32_t)NL_BUILD_THREADS + tid; c < n_colliders; c += gridDim.x * (uint32_t)NL_BUILD_THREADS) {
+    const uint32_t lim = E.limit();
+    for (uint32_t i = blockIdx.x * (uint32_t)NL_BUILD_THREADS + tid; i < lim; i += gridDim.x * (uint32_t)NL_BUILD_THREADS) {
+        const uint32_t c = E.at(i);
+        if (c == NO_SLOT) continue;
         const uint4 cc = Cc.cconst[c];
         uint4 hd = make_uint4(0u, 0u, NL_INACTIVE, cc.y);
         if ((cc.y & CF_ACTIVE) && (cowned == nullptr || cowned[c])) {
@@ -461,11 +483,12 @@ __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, flo
 }
 
 // rebuild, strips: ghost candidates (and leavers) of all owned colliders into the two outgoing messages
-__global__ void __launch_bounds__(256) k_nls_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, const uint8_t* __restrict__ cowned, void* send_l,
-                                                  void* send_r, uint32_t n_colliders, const NlCtl* ctl) {
+__global__ void __launch_bounds__(256) k_nls_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, NlEnum E, void* send_l, void* send_r, const NlCtl* ctl) {
     if (ctl->need == 0u) return;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_colliders; c += gridDim.x * blockDim.x) {
-        if (!cowned[c]) continue;
+    const uint32_t lim = E.limit();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < lim; i += gridDim.x * blockDim.x) {
+        const uint32_t c = E.at(i);
+        if (c == NO_SLOT) continue;
         const uint4 cc = Cc.cconst[c];
         if (!(cc.y & CF_ACTIVE)) continue;
         strip_pack_one(B, Cc, S, c, cc.y, Cc.cabs[c], __uint_as_float(cc.x), send_l, send_r);

@@ -1100,15 +1100,20 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     if (rc) return rc;
     if (!nc) return BLOBS_OK;
     const uint8_t* cown = strip_on ? d_cowned.d : nullptr;
+    // strips: the rebuild kernels enumerate the owned-body list (work proportional to the strip, not to the world's slot count)
+    NlEnum E{};
+    E.n = nc;
+    if (strip_on) { E.olist = olist.d; E.ocount = d_ocount; E.binfo = binfo.d.d; E.n = std::max<uint32_t>(olaunch_dim, 1); }
+    const uint32_t ne = E.n;
     auto rebuild = [&]() -> int {
         int r;
         if (strip_on) {   // a rebuild re-selects ghosts and hands migrants over with the message exchange of the grid pipeline
-            r = run(KC_PACK, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nls_pack)(B, C, strip, d_cowned.d, msg[0], msg[1], nc, d_nlctl); });
+            r = run(KC_PACK, [&] { BLOBS_LAUNCH(std::min(cdiv(ne, 256), NL_GATED_CTAS), 256, 0, stream, k_nls_pack)(B, C, strip, E, msg[0], msg[1], d_nlctl); });
             if (r) return r;
             r = run(KC_NCCL, [&] { BLOBS_LAUNCH(STRIP_PUSH_CTAS, 256, 0, stream, k_nls_push)(strip, msg[0], msg[1], X, d_nlctl, d_stats); });
             if (r) return r;
         }
-        r = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, nc, cown); });
+        r = run(KC_SCAN, [&] { BLOBS_LAUNCH(std::min(cdiv(ne, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_count)(grid, C, bworld.d.d, L, E); });
         if (r) return r;
         if (strip_on) {
             r = run(KC_GHOST, [&] { BLOBS_LAUNCH(cdiv(2 * (size_t)strip.gcap, 256), 256, 0, stream, k_nls_bin_ghosts)(grid, strip, X, L, gcell.d, d_stats); });
@@ -1116,7 +1121,7 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
         }
         r = run(KC_SCAN, [&] { BLOBS_LAUNCH(cdiv(tn, SCAN_TILE), SCAN_THREADS, 0, stream, k_nl_scan)(L, (uint32_t)tn); });
         if (r) return r;
-        r = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(nc, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, nc, cown); });
+        r = run(KC_SCATTER, [&] { BLOBS_LAUNCH(std::min(cdiv(ne, 256), NL_GATED_CTAS), 256, 0, stream, k_nl_scatter)(C, L, E); });
         if (r) return r;
         if (strip_on) {
             r = run(KC_GHOST, [&] {
@@ -1126,7 +1131,7 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
             if (r) return r;
         }
         return run(KC_NLBUILD, [&] {
-            BLOBS_LAUNCH(std::min(cdiv(nc, NL_BUILD_THREADS), NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, nc, cown, strip);
+            BLOBS_LAUNCH(std::min(cdiv(ne, NL_BUILD_THREADS), 2 * NL_GATED_CTAS), NL_BUILD_THREADS, 0, stream, k_nl_build)(grid, C, bworld.d.d, L, cur_is_a ? snap_a.d : snap_b.d, E, cown, strip);
         });
     };
 #ifndef BLOBS_EMU

@@ -360,7 +360,8 @@ class World {
     NlView nl_view();
     int nl_rebuild_chain(bool timed_launch, bool decide);
     // captured steps: the rebuild kernels of a substep live in the body of a conditional (IF) graph node
-    bool cond_nodes = true;            // BLOBS_B200_COND=0: launch them unconditionally (self-gating) inside graphs too
+    bool cond_nodes = false;           // BLOBS_B200_COND=1: opt-in. Measured on B200 (profiles/r2_notes.md): an IF node costs MORE than the four
+                                       // self-gating launches it replaces (0.586 vs 0.546 ms per step on config #2), so it is off by default
     cudaStream_t s_body = nullptr;     // capture stream for the IF-node bodies
     unsigned long long nl_cond_pending = 0ull;   // handle created for the NEXT substep's IF node (set by this substep's k_step)
     uint32_t nl_sub_i = 0, nl_sub_n = 0;

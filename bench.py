@@ -463,6 +463,27 @@ def run_ours(args):
                              "main_kernel_avg_launch_ms": mm / max(mn, 1), "roofline_frac": (B_MAIN * n / 1e9) / (mm / max(mn, 1) / 1e3) / measured_peak()[0] if mn else None,
                              "kernel_ms_per_step": {k: v[0] / 20 for k, v in p["prof"].items() if v[1]}}
 
+    # ---- the N > 1 family's per-GPU problem on ONE GPU (2 097 152 spheres, same lattice and circle as one strip of the 8-GPU world):
+    # the denominator a weak-scaling efficiency needs (the N = 1 line itself is config #2, half that size) ----------------------
+    same_size = None
+    if not args.no_late and world == 1 and args.workload == "cfg2":
+        sc2 = S.lattice_scene(512, 4096, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * 4096, name="cfg5-one-strip", cell_size=1.0)
+        w2 = blobs_b200.World(gravity=sc2.gravity, device=local, body_capacity=sc2.n_bodies, collider_capacity=sc2.n_colliders)
+        S.build(w2, sc2)
+        if args.list is not None:
+            w2.set_param(A.PARAM_LIST, args.list)
+        w2.step(DT, n=W)
+        ms2 = 0.0
+        for _ in range(K):
+            if flush is not None:
+                flush.zero_()
+                torch.cuda.synchronize()
+            ms2 += w2.step(DT)["gpu_ms"]
+        same_size = {"value": sc2.n_bodies * K / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2 / K, "spheres": sc2.n_bodies, "sim_steps": [W, W + K],
+                     "what": "one GPU, 512 x 4096 lattice (the per-GPU share of the N > 1 strip worlds), same timing method as `value`"}
+        w2.close()
+        del w2, sc2
+
     t = torch.tensor([main["ms"], t_e2e], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n), float(main["collisions"]), float(launches), float(io_bytes), float(bad[0])], dtype=torch.float64, device="cuda")
     mx = torch.tensor([w.get_param(A.PARAM_STRIP_MAX_GHOSTS), w.get_param(A.PARAM_STRIP_MAX_MIGRANTS)], dtype=torch.float64, device="cuda")
@@ -499,7 +520,7 @@ def run_ours(args):
                        "pipeline_algorithmic_gbps": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9,
                        "pipeline_frac_of_peak": B_PIPELINE * n_total * substeps * K / (t_dev_ms / 1e3) / 1e9 / (peak * world),
                        "ms_per_step_with_kernel_events": profd["ms"] / K, "cuda_graph_replays": int(w.get_param(A.PARAM_GRAPH_REPLAYS)),
-                       **windows},
+                       **windows, **({"one_gpu_at_strip_size": same_size} if same_size else {})},
             "clocks": clocks,
             "e2e": {"value": n_total * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": float(tot[3]) / K / 2, "d2h_bytes_per_step": float(tot[3]) / K / 2,
                     "ms_per_step": t_e2e / K * 1e3, "checksum_mean_y": checksum, "host_io": e2e_mode, "sync_value": n_total * sync_sample[0] / sync_sample[1]},

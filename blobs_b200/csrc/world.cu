@@ -1501,7 +1501,7 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
         SubstepParams P;
         P.nl_tail_decide = 0u;
         P.nl_cond_next = 0ull;
-        P.acc_zero = (i > 0 && n_sb == 0 && !strip_on) ? 1u : 0u;   // (strips: a migrant arrives with its own acceleration)
+        P.acc_zero = (i > 0 && n_sb == 0) ? 1u : 0u;   // (strips: a migrant was advanced by its previous owner in the same substeps, so the same holds for it)
         nl_sub_i = i;
         nl_sub_n = nsub;
         P.dt = step_delta;

@@ -337,7 +337,7 @@ class World {
     int list_mode = 2;                 // BLOBS_PARAM_LIST: 0 = cell grid rebuilt every substep (k_main), 1 = neighbour lists (k_step), 2 = automatic
     int nl_grid_hold = 0, nl_next_hold = 32;   // automatic mode: step calls left on the grid pipeline before lists are tried again
     unsigned long long nl_seen_rebuilds = 0, nl_seen_substeps = 0;
-    float skin_frac = 0.6f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
+    float skin_frac = 0.8f;            // BLOBS_PARAM_SKIN: skin as a fraction of the largest collider radius
     float nl_skin = 0.f;
     bool nl_on = false;                // the current broadphase is the list pipeline
     bool nl_force_pending = false;     // host-side changes since the last step that invalidate the lists

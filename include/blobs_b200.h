@@ -100,7 +100,7 @@ typedef enum BlobsParamId {
                                             substep; 2 (default) = lists, falling back to 0 for a while whenever the scene is so agitated that the
                                             lists are rebuilt almost every substep. The contact set of every substep is the reference's either way
                                             (physics.rs:241-317): never changes results. */
-    ,BLOBS_PARAM_SKIN = 24               /* neighbour-list skin as a fraction of the largest collider radius (default 0.6) */
+    ,BLOBS_PARAM_SKIN = 24               /* neighbour-list skin as a fraction of the largest collider radius (default 0.8) */
     ,BLOBS_PARAM_LIST_REBUILDS = 25      /* read-only: list rebuilds / substeps run so far (as of the last blobs_step* call) */
     ,BLOBS_PARAM_LIST_SUBSTEPS = 26
     ,BLOBS_PARAM_LIST_ACTIVE = 27        /* read-only: 1 while the neighbour-list pipeline is the one in use */

@@ -80,6 +80,7 @@ extern "C" {
     pub fn blobs_collider_remove(w: *mut BlobsWorld, h: BlobsHandle) -> i32;
     pub fn blobs_collider_get(w: *mut BlobsWorld, h: BlobsHandle, out: *mut BlobsColliderState) -> i32;
     pub fn blobs_spring_insert(w: *mut BlobsWorld, a: BlobsHandle, b: BlobsHandle, rest: c_float, k: c_float, c: c_float, out: *mut BlobsHandle) -> i32;
+    pub fn blobs_spring_remove(w: *mut BlobsWorld, h: BlobsHandle) -> i32;                                            // physics.springs.remove(index) demos/joints.rs:79
     pub fn blobs_joint_insert(w: *mut BlobsWorld, a: BlobsHandle, b: BlobsHandle, aa: BlobsVec2, ab: BlobsVec2, dist_or_nan: c_float, out: *mut BlobsHandle) -> i32;
     pub fn blobs_constraint_push(w: *mut BlobsWorld, p: BlobsVec2, r: c_float) -> i32;
     pub fn blobs_constraint_clear(w: *mut BlobsWorld) -> i32;

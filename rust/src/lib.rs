@@ -25,9 +25,33 @@ fn idx(h: u64) -> Index { Index::from_bits(h).expect("valid handle bits") }
 
 pub struct Physics {
     w: *mut BlobsWorld,
+    /// The reference's `pub` tuning fields (physics.rs:6-27) stay plain fields, so `&mut physics.substeps` (the egui DragValue of
+    /// demo/src/main.rs:263-273) compiles unchanged; `step` / `fixed_step` push them to the library before stepping.
+    pub substeps: u32,
+    pub joint_iterations: u32,
+    pub gravity: Vec2,
+    pub collisions_enabled: bool,
+    /// `physics.springs.insert(Spring { .. })` / `.remove(index)` (demo/src/demos/joints.rs:59-66,79) on the library's spring arena
+    pub springs: SpringArena,
     pub collision_send: Sender<CollisionEvent>,
     pub collision_recv: Receiver<CollisionEvent>,
 }
+
+/// Stand-in for `Arena<Spring>` (physics.rs:13): same `insert` / `remove` surface, same thunderdome indices.
+pub struct SpringArena { w: *mut BlobsWorld }
+impl SpringArena {
+    pub fn insert(&mut self, s: Spring) -> Index {
+        let mut h = 0u64;
+        let rc = unsafe { blobs_spring_insert(self.w, s.rigid_body_a.0.to_bits(), s.rigid_body_b.0.to_bits(), s.rest_length, s.stiffness, s.damping, &mut h) };
+        assert!(rc == BLOBS_OK, "{}", unsafe { CStr::from_ptr(blobs_last_error(self.w)) }.to_string_lossy());
+        idx(h)
+    }
+    pub fn remove(&mut self, i: Index) -> Option<()> { (unsafe { blobs_spring_remove(self.w, i.to_bits()) } == BLOBS_OK).then_some(()) }
+}
+
+/// rigid_body.rs:19-26
+#[derive(Copy, Clone, Debug, Default)]
+pub struct RigidBodyData { pub position: Vec2, pub velocity: Vec2, pub angular_velocity: f32, pub center_of_mass: Vec2, pub mass: f32, pub rotation: f32 }
 
 impl Physics {
     /// Physics::new (physics.rs:37-69)
@@ -38,18 +62,22 @@ impl Physics {
         assert!(rc == BLOBS_OK, "blobs_world_create failed: {}", unsafe { CStr::from_ptr(blobs_last_error(std::ptr::null())) }.to_string_lossy());
         unsafe { blobs_record_contacts(w, BLOBS_RECORD_EVENTS, 1 << 20) }; // the reference always feeds collision_send
         let (collision_send, collision_recv) = channel();
-        Self { w, collision_send, collision_recv }
+        Self { w, substeps: 8, joint_iterations: 4, gravity, collisions_enabled: true, springs: SpringArena { w }, collision_send, collision_recv }   // physics.rs:46-47
+    }
+    /// the `pub` fields above -> library parameters (called by step / fixed_step)
+    fn sync_params(&mut self) {
+        unsafe {
+            blobs_world_set_param(self.w, BLOBS_PARAM_SUBSTEPS, self.substeps as f64);
+            blobs_world_set_param(self.w, BLOBS_PARAM_JOINT_ITERATIONS, self.joint_iterations as f64);
+            blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_X, self.gravity.x as f64);
+            blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_Y, self.gravity.y as f64);
+            blobs_world_set_param(self.w, BLOBS_PARAM_COLLISIONS_ENABLED, self.collisions_enabled as i32 as f64);
+        }
     }
     fn ck(&self, rc: i32) { if rc != BLOBS_OK { panic!("{}", unsafe { CStr::from_ptr(blobs_last_error(self.w)) }.to_string_lossy()); } }
     fn param(&self, id: i32) -> f64 { let mut x = 0.0; unsafe { blobs_world_get_param(self.w, id, &mut x) }; x }
 
-    // pub fields of the reference become accessor pairs (physics.rs:6-33)
-    pub fn substeps(&self) -> u32 { self.param(BLOBS_PARAM_SUBSTEPS) as u32 }
-    pub fn set_substeps(&mut self, n: u32) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_SUBSTEPS, n as f64) }; }
-    pub fn joint_iterations(&self) -> u32 { self.param(BLOBS_PARAM_JOINT_ITERATIONS) as u32 }
-    pub fn set_joint_iterations(&mut self, n: u32) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_JOINT_ITERATIONS, n as f64) }; }
-    pub fn set_gravity(&mut self, gv: Vec2) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_X, gv.x as f64); blobs_world_set_param(self.w, BLOBS_PARAM_GRAVITY_Y, gv.y as f64) }; }
-    pub fn set_collisions_enabled(&mut self, on: bool) { unsafe { blobs_world_set_param(self.w, BLOBS_PARAM_COLLISIONS_ENABLED, on as i32 as f64) }; }
+    // `time` / `accumulator` (physics.rs:30-31) are advanced by the library: read-only here
     pub fn time(&self) -> f64 { self.param(BLOBS_PARAM_TIME) }
     pub fn push_constraint(&mut self, c: Constraint) { self.ck(unsafe { blobs_constraint_push(self.w, v(c.position), c.radius) }); }
 
@@ -74,9 +102,9 @@ impl Physics {
         self.pump_events();
     }
     /// Physics::step (physics.rs:78-82)
-    pub fn step(&mut self, delta: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_step(self.w, delta, &mut st) }); self.after_step(&st); }
+    pub fn step(&mut self, delta: f64) { let mut st = BlobsStepStats::default(); self.sync_params(); self.ck(unsafe { blobs_step(self.w, delta, &mut st) }); self.after_step(&st); }
     /// Physics::fixed_step (physics.rs:84-99)
-    pub fn fixed_step(&mut self, frame_time: f64) { let mut st = BlobsStepStats::default(); self.ck(unsafe { blobs_fixed_step(self.w, frame_time, &mut st) }); self.after_step(&st); }
+    pub fn fixed_step(&mut self, frame_time: f64) { let mut st = BlobsStepStats::default(); self.sync_params(); self.ck(unsafe { blobs_fixed_step(self.w, frame_time, &mut st) }); self.after_step(&st); }
 
     /// insert_rbd (physics.rs:121-128); `RigidBody` is the builder output (rigid_body.rs:376-400)
     pub fn insert_rbd(&mut self, rbd: RigidBody) -> RigidBodyHandle {
@@ -134,6 +162,25 @@ impl Physics {
     }
     pub fn rbd_count(&self) -> usize { let mut n = 0u64; unsafe { blobs_body_count(self.w, &mut n) }; n as usize }
     pub fn get_rbd_state(&mut self, h: RigidBodyHandle) -> Option<BlobsBodyState> { let mut s = BlobsBodyState::default(); (unsafe { blobs_body_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then_some(s) }
+    /// get_rbd (physics.rs:105-107): the reference hands out `&RigidBody`; the body lives in HBM, so this is a snapshot BY VALUE with the
+    /// same `pub` fields and read-only methods (`physics.get_rbd(h).unwrap().position` reads the same either way)
+    pub fn get_rbd(&mut self, h: RigidBodyHandle) -> Option<RigidBodyMirror> { self.get_rbd_state(h).map(|s| RigidBodyMirror::from_state(&s)) }
+    /// get_rbd_data (physics.rs:101-103)
+    pub fn get_rbd_data(&mut self, h: RigidBodyHandle) -> Option<RigidBodyData> {
+        self.get_rbd_state(h).map(|s| RigidBodyData { position: g(s.position), velocity: g(s.calculated_velocity), angular_velocity: s.angular_velocity,
+                                                      center_of_mass: g(s.center_of_mass), mass: s.calculated_mass, rotation: s.rotation })
+    }
+    /// get_col (physics.rs:117-119), by value like get_rbd
+    pub fn get_col(&mut self, h: ColliderHandle) -> Option<Collider> {
+        let mut s = BlobsColliderState::default();
+        (unsafe { blobs_collider_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then(|| {
+            let a = |t: BlobsAffine2| Affine2 { matrix2: Mat2::from_cols(g(t.x_axis), g(t.y_axis)), translation: g(t.translation) };
+            Collider { offset: a(s.desc.offset), absolute_transform: a(s.desc.absolute_transform), user_data: (s.desc.user_data_lo as u128) | ((s.desc.user_data_hi as u128) << 64),
+                       radius: s.desc.radius, mass_override: (s.desc.has_mass_override != 0).then_some(s.desc.mass_override),
+                       flags: ColliderFlags { is_sensor: s.desc.is_sensor != 0 },
+                       collision_groups: InteractionGroups { memberships: s.desc.memberships, filter: s.desc.filter } }
+        })
+    }
     pub fn rbd_position(&mut self, h: RigidBodyHandle) -> Option<Vec2> { self.get_rbd_state(h).map(|s| g(s.position)) }              // physics.rs:151-153
     pub fn col_position(&mut self, h: ColliderHandle) -> Option<Vec2> { let mut s = BlobsColliderState::default(); (unsafe { blobs_collider_get(self.w, h.0.to_bits(), &mut s) } == BLOBS_OK).then(|| g(s.desc.absolute_transform.translation)) }
     pub fn update_rigid_body_position(&mut self, id: u64, offset: Vec2) { unsafe { blobs_body_translate(self.w, id, v(offset)) }; }   // physics.rs:174-182

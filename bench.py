@@ -286,8 +286,18 @@ def run_ours(args):
 
         nx, ny = 512 * world, 4096
         sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_disc=1.0, constraint_r=0.8 * max(nx, ny), name="cfg5", cell_size=1.0)
+        if os.environ.get("BLOBS_BENCH_STRIP_MAJOR", "1") != "0":
+            # Insert the bodies strip by strip (column block of 512, then row, then column) instead of row by row: every array of a
+            # strip world is indexed by GLOBAL slot on every rank, so this makes a rank's share of each array one contiguous range
+            # instead of 4 KB out of every 32 KB - 8x fewer pages touched per rank at N = 8. Same bodies, same attributes (the
+            # scene's RNG is keyed by the lattice index); only the slot numbering - the order of the reference's pair loop - differs.
+            idx = np.arange(nx * ny)
+            ix, iy = idx % nx, idx // nx
+            perm = np.lexsort((ix % 512, iy, ix // 512))
+            sc.bodies, sc.colliders = sc.bodies[perm], sc.colliders[perm]
+            del idx, ix, iy, perm
         desc = (f"cfg5 family: one world of {nx}x{ny} = {nx * ny} spheres r=0.5 (pitch 1.05, circle R={0.8 * max(nx, ny):.0f}), strip-decomposed over {world} GPUs "
-                f"({nx * ny // world} spheres per GPU), ghost/migration exchange with both neighbours every substep")
+                f"({nx * ny // world} spheres per GPU), bodies inserted strip-major, ghost/migration exchange with both neighbours every substep")
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
         if os.environ.get("BLOBS_B200_STRIP_P2P", "1") != "0":

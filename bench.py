@@ -497,7 +497,9 @@ def run_ours(args):
     t = torch.tensor([main["ms"], t_e2e], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n), float(main["collisions"]), float(launches), float(io_bytes), float(bad[0])], dtype=torch.float64, device="cuda")
     mx = torch.tensor([w.get_param(A.PARAM_STRIP_MAX_GHOSTS), w.get_param(A.PARAM_STRIP_MAX_MIGRANTS)], dtype=torch.float64, device="cuda")
+    t_min = t.clone()
     if dist is not None:
+        dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -519,7 +521,7 @@ def run_ours(args):
             "config": {"workload": desc, "spheres_per_gpu": n, "substeps": substeps, "contact_mode": "ordered (bit-exact summation order)",
                        "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
                        "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
-                       "sim_steps": [W, W + K], "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": main["overflow"],
+                       "sim_steps": [W, W + K], "ms_per_step_fastest_rank": float(t_min[0]) / K, "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": main["overflow"],
                        "broadphase": ("neighbour lists (k_step), %.3f rebuilds per substep" % main["rebuilds_per_substep"]) if main["list_active"]
                                      else "cell grid rebuilt every substep (k_main)",
                        "list_mode": int(w.get_param(A.PARAM_LIST)), "skin": w.get_param(A.PARAM_SKIN),

@@ -98,6 +98,8 @@ def run(rank, world, local):
             assert st["nan_detected"] == 0, st
             collisions += st["collisions"]
             overflow += st["list_overflow"]
+    if os.environ.get("STRIP_TEST_EXPECT_LISTS_AFTER"):
+        assert int(w.get_param(A.PARAM_LIST_ACTIVE)) == int(os.environ["STRIP_TEST_EXPECT_LISTS_AFTER"]), f"rank {rank}: list pipeline active after the run"
     own = w.strip_owned()
     bodies, _ = w.download_bodies()
     cols, _ = w.download_colliders()

@@ -88,6 +88,9 @@ _STRIP_CASES = [
     pytest.param({**_P2P, **_LISTS}, id="gas-p2p-lists"),
     pytest.param({**_SHELL, **_P2P, **_LISTS, "BLOBS_B200_CROWDED": "1", "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-lists-crowded"),
     pytest.param({**_P2P, **_LISTS, "STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-p2p-lists-pipelined-host-io", marks=_slow),
+    # automatic mode on an agitated scene: the ranks start on lists, see them rebuilt every substep and fall back to the grid
+    # pipeline together, in the middle of the run
+    pytest.param({**_SHELL, **_P2P, "BLOBS_B200_LIST": "2", "STRIP_TEST_EXPECT_LISTS": "1", "STRIP_TEST_EXPECT_LISTS_AFTER": "0", "STRIP_TEST_STEPS": "10"}, id="shell-p2p-auto-falls-back-to-grid"),
     # the cell-grid pipeline with the peer-memory exchange (k_strip_push every substep)
     pytest.param({**_P2P, "BLOBS_B200_LIST": "0", "STRIP_TEST_EXPECT_LISTS": "0"}, id="gas-p2p-grid", marks=_slow),
     pytest.param({**_SHELL, **_P2P, **_FORCED, "BLOBS_B200_LIST": "0", "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-grid-forced", marks=_slow),

@@ -332,9 +332,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     K, W = args.steps, max(args.warmup, 3)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None   # one nvidia-smi poller per node: eight of them stall each other's CUDA calls
     w.step(DT, n=max(W - 3, 0))
-    sampler.start()          # nvidia-smi needs ~100 ms to produce its first line: start it under the last warm-up steps (same load)
+    if sampler:
+        sampler.start()      # nvidia-smi needs ~100 ms to produce its first line: start it under the last warm-up steps (same load)
     w.step(DT, n=min(W, 3))
     sim_steps = W
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -371,9 +372,22 @@ def run_ours(args):
 
     # ---- device-timed region ----------------------------------------------------------------------------------------
     barrier()
-    sampler.mark()
+    if sampler:
+        sampler.mark()
     l0 = w.kernel_info()["launches"]
-    main = timed_pass(K)
+    if strips_on:
+        # Strip worlds: the K steps are enqueued by ONE call (blobs_step_n) and timed by its pair of CUDA events. No L2 flush is needed
+        # (2 M spheres per GPU: ~270 MB touched per substep against 126 MB of L2), and without a host round trip per step the ranks
+        # do not pick up each other's host-side launch jitter: the list pipeline synchronises ALL ranks at the start of every substep,
+        # so a rank that enters a step late would stall the seven others inside their timed region.
+        r0 = (w.get_param(A.PARAM_LIST_REBUILDS), w.get_param(A.PARAM_LIST_SUBSTEPS))
+        st = w.step(DT, n=K)
+        bad[0] |= st["nan_detected"] & 12
+        r1 = (w.get_param(A.PARAM_LIST_REBUILDS), w.get_param(A.PARAM_LIST_SUBSTEPS))
+        main = {"ms": st["gpu_ms"], "collisions": st["collisions"], "overflow": st["list_overflow"], "prof": None,
+                "list_active": int(w.get_param(A.PARAM_LIST_ACTIVE)), "rebuilds_per_substep": (r1[0] - r0[0]) / max(r1[1] - r0[1], 1.0)}
+    else:
+        main = timed_pass(K)
     barrier()
     info = w.kernel_info()
     launches = info["launches"] - l0
@@ -385,7 +399,7 @@ def run_ours(args):
     if os.environ.get("BLOBS_BENCH_GRAPH", "1") != "0":
         w.set_param(A.PARAM_GRAPH, 1)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     sim_steps += 3 * K
 
     # ---- end-to-end region (public C ABI, host buffers, copies inside) --------------------------------------------------
@@ -519,7 +533,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_dev_ms / K,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "spheres_per_gpu": n, "substeps": substeps, "contact_mode": "ordered (bit-exact summation order)",
-                       "l2": "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush",
+                       "l2": ("no flush: K steps enqueued by one blobs_step_n call; the per-GPU working set (2 M spheres, ~270 MB per substep) exceeds the 126 MB L2" if strips_on
+                              else "256 MiB buffer rewritten between timed steps, outside the per-step CUDA events" if flush is not None else "no flush"),
                        "grid": [info["grid_w"], info["grid_h"]], "broadphase_cell": info["broadphase_cell"], "fused_path": info["fused_path"],
                        "sim_steps": [W, W + K], "ms_per_step_fastest_rank": float(t_min[0]) / K, "contacts_per_step": coll_total / K / max(world, 1), "list_overflow": main["overflow"],
                        "broadphase": ("neighbour lists (k_step), %.3f rebuilds per substep" % main["rebuilds_per_substep"]) if main["list_active"]

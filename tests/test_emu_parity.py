@@ -44,6 +44,9 @@ CASES = [
     ("pipelined-host-io", T.test_pipelined_host_io_matches_synchronous_calls, {}),
     ("pipelined-indexed-host-io", T.test_pipelined_indexed_host_io_matches_synchronous_calls, {}),
     ("collisions-disabled-variable-delta", T.test_collisions_disabled_and_variable_delta, {}),
+    ("first-non-static-static-in-slot-0", T.test_first_non_static_body_sees_the_old_dt_ratio, dict(first="static")),
+    ("first-non-static-kinematic-in-slot-0", T.test_first_non_static_body_sees_the_old_dt_ratio, dict(first="kinematic")),
+    ("statics-only-keeps-old-dt", T.test_statics_only_world_keeps_old_dt, {}),
     ("events", T.test_events_match_reference_channel, {}),
     ("large-island", T.test_large_island_and_mixed_bodies, {}),
     ("fast-mode", T.test_fast_mode_within_tolerance, {}),

@@ -438,6 +438,45 @@ def test_far_outlier_aliases_harmlessly():
     _compare_step(g, o)
 
 
+@pytest.mark.parametrize("first", ["static", "kinematic", "dynamic"])
+def test_first_non_static_body_sees_the_old_dt_ratio(first):
+    """physics.rs:327-339: `displacement * (dt / old_dt)` - old_dt is overwritten inside the body loop, so only the FIRST NON-STATIC
+    body in arena order sees a ratio != 1, and a static body in slot 0 neither takes that role nor updates old_dt; kinematic bodies
+    count as non-static. Bodies carry velocity requests and the delta varies between steps, so a misplaced ratio shows at once."""
+    import blobs_b200
+    from oracle import oracle_py
+
+    btype = {"static": 1, "kinematic": 2, "dynamic": 0}[first]
+    ws = [blobs_b200.World(gravity=(0.0, -30.0)), oracle_py.OracleWorld(gravity=(0.0, -30.0), maintain_spatial_hash=False, record_events=False)]
+    for w in ws:
+        sphere(w, (0.0, 0.0), r=0.3, body_type=btype, velocity_request=(0.5, 0.25))
+        for i in range(6):
+            sphere(w, (1.0 + 0.9 * i, 0.1 * i), r=0.3, velocity_request=(3.0 - i, 1.0 + 0.5 * i))
+        sphere(w, (-2.0, 0.0), r=0.3, body_type=3, velocity_request=(1.0, 0.0))
+        sphere(w, (-3.0, 1.0), r=0.3, body_type=1)
+    for delta, sub in ((1 / 60, 8), (1 / 30, 8), (1 / 50, 3), (1 / 60, 8)):
+        for w in ws:
+            w.set_param(A.PARAM_SUBSTEPS, sub)
+            w.step(delta)
+        _compare_step(ws[0], ws[1])
+        assert np.float32(ws[0].get_param(A.PARAM_OLD_DT)) == np.float32(ws[1].get_param(A.PARAM_OLD_DT))
+
+
+def test_statics_only_world_keeps_old_dt():
+    """a world without any non-static body never overwrites old_dt (physics.rs:338-339 sits behind the is_static `continue`)"""
+    import blobs_b200
+    from oracle import oracle_py
+
+    ws = [blobs_b200.World(gravity=(0.0, -30.0)), oracle_py.OracleWorld(gravity=(0.0, -30.0), maintain_spatial_hash=False, record_events=False)]
+    for w in ws:
+        sphere(w, (0.0, 0.0), r=0.3, body_type=1)
+        sphere(w, (0.4, 0.0), r=0.3, body_type=1)
+        w.step(1 / 60)
+        w.step(1 / 30)
+    _compare_step(ws[0], ws[1])
+    assert np.float32(ws[0].get_param(A.PARAM_OLD_DT)) == np.float32(ws[1].get_param(A.PARAM_OLD_DT)) == np.float32(1.0)
+
+
 def test_collisions_disabled_and_variable_delta():
     """collisions_enabled=false (physics.rs:25-27) and a delta that changes between steps (Q2 applies to the first body only)."""
     sc = S.cfg1(1)

@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-late", action="store_true", help="skip the steady_state / late_state windows")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the strip-world-vs-one-GPU self-check (parity_vs_single_gpu)")
     ap.add_argument("--tune", type=int, default=0, help="kernel variant selector (BLOBS_PARAM_TUNE)")
     ap.add_argument("--list", type=int, default=None, help="BLOBS_PARAM_LIST: 0 = cell grid every substep, 1 = neighbour lists, 2 = automatic (library default)")
     ap.add_argument("--skin", type=float, default=None, help="BLOBS_PARAM_SKIN (fraction of the largest radius)")
@@ -247,6 +248,72 @@ def strip_pipelined_loop(w, K, forces, sl, xy, cnt, io_cap, on_step=None):
     return io_bytes
 
 
+def strip_parity_probe(dist, rank, world, local, dev, steps=20, ny=192, cols_per_rank=48, params=None):
+    """Parity at N > 1, visible in the bench line: a small strip world (cols_per_rank*world x ny spheres with lateral velocities, so
+    bodies migrate across the edges) stepped on all ranks with the same settings as the timed world, against the same world on rank
+    0's GPU alone; positions, old positions and velocities of every body compared bit for bit. (The test of record is
+    tests/test_multi_gpu.py; this is the same comparison, run by the bench itself.)"""
+    import numpy as np
+    import torch
+
+    import blobs_b200
+    from blobs_b200 import scenes as S
+    from blobs_b200 import strips
+
+    A = blobs_b200.abi
+    nx = cols_per_rank * world
+    sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 5, 0.3, 0.5, jitter=0.04, vel_disc=6.0, constraint_r=0.8 * max(nx, ny), name="strip-probe", cell_size=1.0)
+
+    def make():
+        w = blobs_b200.World(gravity=sc.gravity, device=local)
+        S.build(w, sc)
+        for k, v in (params or {}).items():
+            w.set_param(k, v)
+        return w
+
+    def state(w):
+        b, _ = w.download_bodies()
+        return np.concatenate([b["position"]["x"], b["position"]["y"], b["position_old"]["x"], b["position_old"]["y"],
+                               b["calculated_velocity"]["x"], b["calculated_velocity"]["y"]]).astype(np.float32)
+
+    w = make()
+    edges = strips.strip_edges(float(sc.bodies["position"]["x"].min()), float(sc.bodies["position"]["x"].max()), world)
+    uid = torch.from_numpy(blobs_b200.World.strip_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
+    dist.broadcast(uid, 0)
+    w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.cpu().numpy(), ghost_capacity=1 << 14, migrate_capacity=1 << 10)
+    own0 = w.strip_owned().astype(bool)
+    bad = coll = 0
+    for _ in range(steps):
+        st = w.step(DT)
+        bad |= st["nan_detected"]
+        coll += st["collisions"]
+    own = w.strip_owned().astype(bool)
+    lists = int(w.get_param(A.PARAM_LIST_ACTIVE))
+    mine = np.where(np.tile(own, 6), state(w), np.float32(0)).view(np.int32)   # a body's fields are non-zero on its owner only
+    t = torch.from_numpy(mine.astype(np.int64)).to(dev)
+    o = torch.from_numpy(np.concatenate([own, own0 != own]).astype(np.int64)).to(dev)
+    c = torch.tensor([coll, bad], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)      # exact: every slot has one non-zero contributor (int64 sums of int32 bit patterns)
+    dist.all_reduce(o)
+    dist.all_reduce(c)
+    w.close()               # only now: a neighbour's last substep may still have been storing ghost records into this rank's buffers
+    out = None
+    if rank == 0:
+        n = sc.n_bodies
+        ref = make()
+        ref_coll = 0
+        for _ in range(steps):
+            ref_coll += ref.step(DT)["collisions"]
+        want = state(ref).view(np.int32).astype(np.int64)
+        ref.close()
+        owners = o.cpu().numpy()
+        mism = int((t.cpu().numpy() != want).sum())
+        out = {"spheres": n, "steps": steps, "ranks": world, "list_pipeline_active": lists, "migrated_bodies": int(owners[n:].sum()) // 2,
+               "contacts": int(c[0]), "contacts_single_gpu": ref_coll, "mismatching_words": mism,
+               "bit_identical": bool(mism == 0 and int(c[0]) == ref_coll and int(c[1]) == 0 and (owners[:n] == 1).all())}
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -317,12 +384,15 @@ def run_ours(args):
         w = blobs_b200.World(gravity=sc.gravity, device=local, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
         S.build(w, sc)
         n, nb = sc.n_colliders, sc.n_bodies
+    knobs = {}
     if args.tune:
-        w.set_param(A.PARAM_TUNE, args.tune)
+        knobs[A.PARAM_TUNE] = args.tune
     if args.list is not None:
-        w.set_param(A.PARAM_LIST, args.list)
+        knobs[A.PARAM_LIST] = args.list
     if args.skin is not None:
-        w.set_param(A.PARAM_SKIN, args.skin)
+        knobs[A.PARAM_SKIN] = args.skin
+    for k, v in knobs.items():
+        w.set_param(k, v)
     if os.environ.get("BLOBS_BENCH_GRAPH", "1") == "0":
         w.set_param(A.PARAM_GRAPH, 0)
 
@@ -508,6 +578,13 @@ def run_ours(args):
         w2.close()
         del w2, sc2
 
+    # ---- N > 1: the strip decomposition against one GPU, same settings, small world (bit-exact or the line says so) ------------
+    parity = None
+    if strips_on and not args.no_parity:
+        if os.environ.get("BLOBS_B200_STRIP_P2P", "1") != "0":
+            knobs[A.PARAM_STRIP_P2P] = 1
+        parity = strip_parity_probe(dist, rank, world, local, "cuda", params=knobs)
+
     t = torch.tensor([main["ms"], t_e2e], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n), float(main["collisions"]), float(launches), float(io_bytes), float(bad[0])], dtype=torch.float64, device="cuda")
     mx = torch.tensor([w.get_param(A.PARAM_STRIP_MAX_GHOSTS), w.get_param(A.PARAM_STRIP_MAX_MIGRANTS)], dtype=torch.float64, device="cuda")
@@ -558,6 +635,10 @@ def run_ours(args):
                          "timing": "CUDA events around every launch of this kernel (and no other), plain launches, a third pass over K steps of the same window",
                          "traffic": ncu_traffic(kernel, n)},
         }
+        if parity is not None:
+            line["parity_vs_single_gpu"] = parity
+            if not parity["bit_identical"]:
+                line["invalid"] = "the strip world differs from the same world on one GPU (parity_vs_single_gpu)"
         if float(tot[4]) != 0:
             line["invalid"] = "strip message buffers overflowed (raise ghost_capacity / migrate_capacity) or a peer-memory exchange timed out: results are not valid"
         if world == 1 and not args.no_cpu_baseline:

@@ -61,26 +61,6 @@ __device__ __forceinline__ void nl_set_cond(unsigned long long handle, unsigned 
 #endif
 }
 
-__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step, unsigned long long cond) {
-    if (threadIdx.x != 0u || blockIdx.x != 0u) return;
-    if (ctl->decided) {   // k_step's last CTA has decided already; only a host request can still change the verdict
-        ctl->decided = 0u;
-        if (ctl->force) {
-            ctl->force = 0u;
-            if (!ctl->need) {
-                ctl->need = 1u;
-                ctl->cx -= ctl->mean_x; ctl->cy -= ctl->mean_y;   // the references are about to move to the current snapshots
-                ctl->mean_x = 0.f; ctl->mean_y = 0.f;
-                ctl->rebuilds += in_step;
-            }
-        }
-        nl_set_cond(cond, ctl->need);
-        return;
-    }
-    nl_decide(ctl, lim, in_step);
-    nl_set_cond(cond, ctl->need);
-}
-
 // the two tables are picked by ternaries (a runtime index into a kernel-parameter array would copy the struct to local memory)
 __device__ __forceinline__ uint32_t* nl_tab(const NlView& L, uint32_t which) { return which ? L.tab[1] : L.tab[0]; }
 __device__ __forceinline__ uint32_t* nl_tile(const NlView& L, uint32_t which) { return which ? L.tile[1] : L.tile[0]; }
@@ -235,6 +215,89 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Device-side launch of a rebuild (CUDA dynamic parallelism). The kernel that takes - or, after k_step's tail decision, picks up -
+// the verdict launches the rebuild kernels itself into the tail-launch stream: they run, in launch order, after that kernel and
+// before its successor in the host stream. A substep that keeps its lists then costs ONE tiny kernel in front of k_step instead of
+// four (strips: nine) self-gating launches of ~2.7 us each, inside a captured graph as well as with plain launches.
+// The launched kernels are the very same self-gating ones (NlCtl::need is still set when they run).
+// ---------------------------------------------------------------------------------------------------------------------
+struct NlDev {
+    uint32_t on;               // 0: the host launches the self-gating rebuild kernels after the deciding kernel
+    uint32_t tab_entries;      // length of the cell table (k_nl_scan)
+    GridDesc g;
+    ColliderArrays C;
+    BodyArrays B;
+    NlEnum E;
+    // strips only
+    uint32_t strip_on, gcap, mcap, olist_cap;
+    StripDesc S;
+    void* msg_l;
+    void* msg_r;
+    uint2* gcell;
+    uint8_t* owned;
+    uint8_t* cowned;
+    uint32_t* olist;
+    uint32_t* ocount;
+    uint32_t* opos;
+    DeviceStats* stats;
+};
+
+#ifndef BLOBS_EMU
+__global__ void __launch_bounds__(256) k_nls_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, NlEnum E, void* send_l, void* send_r, const NlCtl* ctl);
+__global__ void __launch_bounds__(256) k_nls_push(StripDesc S, const void* send_l, const void* send_r, NlStripDev X, const NlCtl* ctl, DeviceStats* stats);
+__global__ void __launch_bounds__(256) k_nls_bin_ghosts(GridDesc g, StripDesc S, NlStripDev X, NlView L, uint2* gcell, DeviceStats* stats);
+__global__ void __launch_bounds__(256) k_nls_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r, NlStripDev X, NlView L,
+                                                    const uint2* __restrict__ gcell, uint8_t* owned, uint8_t* cowned, uint32_t* olist, uint32_t* ocount,
+                                                    uint32_t* opos, uint32_t olist_cap, DeviceStats* stats, float4* snap_cur);
+
+// one thread; snap = the snapshot array the coming contact pass reads
+__device__ BLOBS_NOINLINE void nl_dev_rebuild(const NlView& L, const NlDev& D, const NlStripDev& X, float4* snap) {
+    const uint32_t ne = D.E.n;
+    const unsigned ctas = min((ne + 255u) / 256u, NL_GATED_CTAS);
+    if (D.strip_on) {
+        k_nls_pack<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.B, D.C, D.S, D.E, D.msg_l, D.msg_r, L.ctl);
+        k_nls_push<<<STRIP_PUSH_CTAS, 256, 0, cudaStreamTailLaunch>>>(D.S, D.msg_l, D.msg_r, X, L.ctl, D.stats);
+    }
+    k_nl_count<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.g, D.C, D.B.bworld, L, D.E);
+    if (D.strip_on) k_nls_bin_ghosts<<<(2u * D.gcap + 255u) / 256u, 256, 0, cudaStreamTailLaunch>>>(D.g, D.S, X, L, D.gcell, D.stats);
+    k_nl_scan<<<(D.tab_entries + SCAN_TILE - 1u) / SCAN_TILE, SCAN_THREADS, 0, cudaStreamTailLaunch>>>(L, D.tab_entries);
+    k_nl_scatter<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.C, L, D.E);
+    if (D.strip_on)
+        k_nls_finish<<<(2u * D.gcap + 4u * D.mcap + 255u) / 256u, 256, 0, cudaStreamTailLaunch>>>(D.B, D.C, D.S, D.msg_l, D.msg_r, X, L, D.gcell, D.owned, D.cowned,
+                                                                                                D.olist, D.ocount, D.opos, D.olist_cap, D.stats, snap);
+    k_nl_build<<<min((ne + NL_BUILD_THREADS - 1u) / NL_BUILD_THREADS, 2u * NL_GATED_CTAS), NL_BUILD_THREADS, 0, cudaStreamTailLaunch>>>(
+        D.g, D.C, D.B.bworld, L, snap, D.E, D.strip_on ? D.cowned : nullptr, D.S);
+    if (cudaGetLastError() != cudaSuccess) atomicOr(&D.stats->nan_flag, 16u);   // a launch was refused: the lists are stale, the host reports it
+}
+#endif
+
+__device__ __forceinline__ void nl_dev_rebuild_if_needed(const NlView& L, const NlDev& D, const NlStripDev& X) {
+#ifndef BLOBS_EMU
+    if (D.on && L.ctl->need) nl_dev_rebuild(L, D, X, const_cast<float4*>(L.snap_cur));
+#endif
+}
+
+__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step, unsigned long long cond, NlView L, NlDev D) {
+    if (threadIdx.x != 0u || blockIdx.x != 0u) return;
+    if (ctl->decided) {   // k_step's last CTA has decided already; only a host request can still change the verdict
+        ctl->decided = 0u;
+        if (ctl->force) {
+            ctl->force = 0u;
+            if (!ctl->need) {
+                ctl->need = 1u;
+                ctl->cx -= ctl->mean_x; ctl->cy -= ctl->mean_y;   // the references are about to move to the current snapshots
+                ctl->mean_x = 0.f; ctl->mean_y = 0.f;
+                ctl->rebuilds += in_step;
+            }
+        }
+    } else {
+        nl_decide(ctl, lim, in_step);
+    }
+    nl_set_cond(cond, ctl->need);
+    nl_dev_rebuild_if_needed(L, D, NlStripDev{});
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // k_step: one thread per body slot (bodies with zero or one collider; multi-collider bodies go to k_multi).
 // brute_force_collisions restricted to the body's neighbour list + apply_gravity + update_objects + apply_constraints
 // (physics.rs:241-395), then the new snapshot record and its displacement tracking.
@@ -261,9 +324,36 @@ __device__ BLOBS_NOINLINE float2 nl_overflow_inline(GridDesc g, Broadphase bp, c
     return apply_contacts_rescan(g, gb, ccold, &s, 1, p.x, p.y);
 }
 
+// End of a substep on a strip rank (one warp): this rank's displacement accumulators and a sequence number go to EVERY rank's flag
+// block; the sequence number also tells the two neighbours that this substep's ghost records have landed in their arrays.
+__device__ __forceinline__ void nls_publish_warp(NlCtl* ctl, const NlStripDev& X, uint32_t lane) {
+    const volatile NlCtl* vc = ctl;
+    const unsigned int seq = vc->pub_seq + 1u;
+    const unsigned int m = vc->max_m, n = vc->n_sum;
+    const float sx = vc->sum_x, sy = vc->sum_y;
+    __syncwarp();
+    if (lane < (uint32_t)X.nranks) {
+        volatile NlFlag* f = X.peer[lane] + (size_t)(seq & 1u) * NL_MAX_RANKS + X.rank;
+        f->max_m = m;
+        f->sum_x = sx;
+        f->sum_y = sy;
+        f->n_sum = n;
+        __threadfence_system();   // the numbers before the sequence number that announces them
+        f->seq = seq;
+    }
+    __syncwarp();
+    if (lane == 0u) {
+        ctl->pub_seq = seq;
+        ctl->published = 1u;
+        ctl->max_m = 0u;
+        ctl->sum_x = 0.f; ctl->sum_y = 0.f;
+        ctl->n_sum = 0u;
+    }
+}
+
 template <bool FUSED, int MINB, bool STRIP>
 __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
-                                                 Recording rec, DeviceStats* stats) {
+                                                 Recording rec, DeviceStats* stats, NlStripDev X) {
     const NlView& L = bp.nl;
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     bool inb;
@@ -385,7 +475,8 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
                 if (STRIP && (hd.w & (NLF_PUSH_L | NLF_PUSH_R))) {   // a neighbour rank keeps this collider as a ghost: store the record there too
                     if (hd.w & NLF_PUSH_L) L.peer_next[0][c] = rec_new;
                     if (hd.w & NLF_PUSH_R) L.peer_next[1][c] = rec_new;
-                    __threadfence_system();   // ordered before this rank's end-of-substep flag (k_nls_publish)
+                    // no fence here: the end-of-substep flag is written after a system-scope fence that follows the completion of
+                    // every CTA of this kernel (its last CTA, or k_nls_publish) - one GPU-wide flush instead of one per pushing warp
                 }
                 nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), ccx, ccy, na);
             }
@@ -402,6 +493,19 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
             nl_decide(L.ctl, L.lim, 1u);
             L.ctl->decided = 1u;
             nl_set_cond(P.nl_cond_next, L.ctl->need);
+        }
+    }
+    if (STRIP && P.nl_tail_publish && threadIdx.x < 32u) {   // strips, and this kernel is the substep's only publisher: the last CTA sends the flags
+        unsigned int last = 0u;
+        if (threadIdx.x == 0u) {
+            __threadfence();   // this CTA's records and accumulator updates (ordered before thread 0 by nl_commit's barrier) before its arrival
+            last = atomicAdd(&L.ctl->step_done, 1u) == gridDim.x - 1u ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (threadIdx.x == 0u) L.ctl->step_done = 0u;
+            __threadfence_system();   // every CTA's peer stores before the flags that announce them
+            nls_publish_warp(L.ctl, X, threadIdx.x);
         }
     }
     if (__any_sync(0xffffffffu, out.n_coinc | n_over)) {
@@ -424,50 +528,34 @@ __global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g,
 // pipeline (k_strip_push), all of it gated by the device-side decision like the single-GPU rebuild kernels.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_nls_publish(NlCtl* ctl, NlStripDev X) {
-    const uint32_t lane = threadIdx.x;
-    const unsigned int seq = ctl->pub_seq + 1u;
-    if (lane < (uint32_t)X.nranks) {
-        volatile NlFlag* f = X.peer[lane] + (size_t)(seq & 1u) * NL_MAX_RANKS + X.rank;
-        f->max_m = ctl->max_m;
-        f->sum_x = ctl->sum_x;
-        f->sum_y = ctl->sum_y;
-        f->n_sum = ctl->n_sum;
-        __threadfence_system();   // the numbers before the sequence number that announces them
-        f->seq = seq;
-    }
-    __syncwarp();
-    if (lane == 0u) {
-        ctl->pub_seq = seq;
-        ctl->published = 1u;
-        ctl->max_m = 0u;
-        ctl->sum_x = 0.f; ctl->sum_y = 0.f;
-        ctl->n_sum = 0u;
-    }
+    __threadfence_system();   // the previous kernels' peer stores are complete (stream order); flush them before the flags
+    nls_publish_warp(ctl, X, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, float lim, float xlim, void* send_l, void* send_r, uint32_t in_step,
-                                                   DeviceStats* stats, unsigned long long cond) {
+                                                   DeviceStats* stats, unsigned long long cond, NlView L, NlDev D) {
     const uint32_t lane = threadIdx.x;
     unsigned int M = 0u, N = 0u;
     float SX = 0.f, SY = 0.f;
     if (ctl->published) {
         const unsigned int seq = ctl->pub_seq;
         const volatile NlFlag* f = X.mine + (size_t)(seq & 1u) * NL_MAX_RANKS;
+        unsigned int m = 0u, n = 0u;
+        float sx = 0.f, sy = 0.f;
         if (lane < (uint32_t)X.nranks) {
             const long long t0 = clock64();
             while (f[lane].seq != seq) {
                 if (clock64() - t0 > STRIP_WAIT_TICKS) { atomicOr(&stats->nan_flag, 8u); break; }
             }
             __threadfence_system();
+            m = f[lane].max_m; sx = f[lane].sum_x; sy = f[lane].sum_y; n = f[lane].n_sum;
         }
         __syncwarp();
-        if (lane == 0u) {   // combined in rank order: every rank computes the very same numbers
-            for (int r = 0; r < X.nranks; ++r) {
-                M = max(M, f[r].max_m);
-                SX += f[r].sum_x;
-                SY += f[r].sum_y;
-                N += f[r].n_sum;
-            }
+        for (int r = 0; r < X.nranks; ++r) {   // combined in rank order: every rank computes the very same numbers
+            M = max(M, __shfl_sync(0xffffffffu, m, r));
+            SX += __shfl_sync(0xffffffffu, sx, r);
+            SY += __shfl_sync(0xffffffffu, sy, r);
+            N += __shfl_sync(0xffffffffu, n, r);
         }
     }
     if (lane == 0u) {
@@ -479,6 +567,7 @@ __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, flo
             hr->n_ghost = hr->n_mig = hr->overflow = 0u;
         }
         nl_set_cond(cond, ctl->need);
+        nl_dev_rebuild_if_needed(L, D, X);
     }
 }
 

@@ -97,6 +97,7 @@ struct SubstepParams {
     uint32_t acc_zero;              // every body's acceleration is zero and no velocity_request is pending (any substep after the first of a call
                                     // in a world without springs: update_objects consumed both, physics.rs:334-336,350-355): neither is read or rewritten
     uint32_t nl_tail_decide;        // list pipeline: k_step is this substep's only publisher, so its last CTA decides for the next substep
+    uint32_t nl_tail_publish;       // list pipeline on strips: ... and its last CTA publishes this rank's end-of-substep flag to every rank (no k_nls_publish launch)
     unsigned long long nl_cond_next; // ... and, inside a captured graph, tells the IF node that wraps the next substep's rebuild kernels (0 = none)
     uint32_t* over_list;            // deferred bodies: body slot, or OVER_MULTI_BIT | index into the multi-collider body list
 };

@@ -77,6 +77,8 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_SKIN")) skin_frac = (float)std::atof(e);
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BLOBS_B200_NLS_TAIL")) nls_tail_publish = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BLOBS_B200_DEVLAUNCH")) dev_launch = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
     graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
 #endif
@@ -1091,19 +1093,37 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     }
 #endif
     const NlStripDev X = nls_dev();
-    if (strip_on) {
-        // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records)
-        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats, h_cur); });
-    } else if (decide) {
-        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u, h_cur); });
-    }
-    if (rc) return rc;
-    if (!nc) return BLOBS_OK;
     const uint8_t* cown = strip_on ? d_cowned.d : nullptr;
     // strips: the rebuild kernels enumerate the owned-body list (work proportional to the strip, not to the world's slot count)
     NlEnum E{};
     E.n = nc;
     if (strip_on) { E.olist = olist.d; E.ocount = d_ocount; E.binfo = binfo.d.d; E.n = std::max<uint32_t>(olaunch_dim, 1); }
+    // the deciding kernel launches the rebuild itself (device-side tail launch) - not while profiling (per-kernel events), not for the
+    // untimed rebuilds outside a step, not in the host-compiled test build
+    NlDev D{};
+#ifndef BLOBS_EMU
+    D.on = (dev_launch && !profiling && timed_launch && !use_cond && nc != 0) ? 1u : 0u;
+#endif
+    if (D.on) {
+        D.tab_entries = (uint32_t)tn;
+        D.g = grid; D.C = C; D.B = B; D.E = E;
+        D.stats = d_stats;
+        D.strip_on = strip_on ? 1u : 0u;
+        if (strip_on) {
+            D.gcap = strip.gcap; D.mcap = strip.mcap; D.olist_cap = (uint32_t)olist.cap;
+            D.S = strip; D.msg_l = msg[0]; D.msg_r = msg[1]; D.gcell = gcell.d;
+            D.owned = d_owned.d; D.cowned = d_cowned.d; D.olist = olist.d; D.ocount = d_ocount; D.opos = opos.d;
+        }
+    }
+    if (timed_launch) dev_per_rebuild_live = D.on ? (strip_on ? 8 : 4) : 0;   // (kept across graph replays of the same capture)
+    if (strip_on) {
+        // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records)
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats, h_cur, L, D); });
+    } else if (decide || D.on) {
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u, h_cur, L, D); });
+    }
+    if (rc) return rc;
+    if (!nc || D.on) return BLOBS_OK;
     const uint32_t ne = E.n;
     auto rebuild = [&]() -> int {
         int r;
@@ -1376,6 +1396,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (lists) {   // decide on the device whether the lists are still supersets of the contact set; rebuild them if not
         // k_step takes the decision for the NEXT substep itself when nothing else publishes snapshots after it
         P.nl_tail_decide = (fused && nb && !n_islands && !n_multi && !crowded && !strip_on) ? 1u : 0u;
+        P.nl_tail_publish = (fused && nb && !n_islands && !n_multi && !crowded && strip_on && nls_tail_publish) ? 1u : 0u;
         rc = nl_rebuild_chain(true, !nl_prev_tail);
         if (rc) return rc;
         nl_prev_tail = P.nl_tail_decide != 0u;
@@ -1403,10 +1424,10 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (nb && lists) {
         rc = timed(KC_MAIN, [&] {
             // BLOBS_PARAM_TUNE 1: 3 CTAs per SM (85 registers, no spills) instead of 4 (64 registers)
-            if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, 4, true>)(P, grid, K, B, C, bp, R, d_stats);
-            else if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3, false>)(P, grid, K, B, C, bp, R, d_stats);
-            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4, false>)(P, grid, K, B, C, bp, R, d_stats);
-            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4, false>)(P, grid, K, B, C, bp, R, d_stats);
+            if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, 4, true>)(P, grid, K, B, C, bp, R, d_stats, nls_dev());
+            else if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
         });
         if (rc) return rc;
     } else if (nb) {
@@ -1480,7 +1501,7 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (!lists) {
         rc = strip_build_tail(bp.tab_next, tab_cur, bp.tile_next, tile_cur, hot_next, true);
         if (rc) return rc;
-    } else if (strip_on) {   // end of the substep: this rank's displacement numbers + "my ghost records are out" go to every rank
+    } else if (strip_on && !P.nl_tail_publish) {   // end of the substep: this rank's displacement numbers + "my ghost records are out" go to every rank
         rc = timed(KC_GHOST, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_publish)(d_nlctl, nls_dev()); });
         if (rc) return rc;
     }
@@ -1500,6 +1521,7 @@ int World::integrate(uint32_t nsub, float delta, bool last_of_call) {
     for (uint32_t i = 0; i < nsub; ++i) {
         SubstepParams P;
         P.nl_tail_decide = 0u;
+        P.nl_tail_publish = 0u;
         P.nl_cond_next = 0ull;
         P.acc_zero = (i > 0 && n_sb == 0) ? 1u : 0u;   // (strips: a migrant was advanced by its previous owner in the same substeps, so the same holds for it)
         nl_sub_i = i;
@@ -1575,6 +1597,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     }
     if (nl_on && cond_per_rebuild_live) launches += (h_nlctl->rebuilds - nl_seen_rebuilds) * cond_per_rebuild_live;   // IF-node bodies that ran
     cond_per_rebuild_live = 0;
+    if (nl_on && dev_per_rebuild_live) launches += (h_nlctl->rebuilds - nl_seen_rebuilds) * dev_per_rebuild_live;     // device-launched rebuilds that ran
     nl_seen_rebuilds = h_nlctl->rebuilds;
     nl_seen_substeps = h_nlctl->substeps;
     // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep
@@ -1592,6 +1615,7 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");
     // strip mode: results are not valid after either of these. The statistics above are complete, and every rank sees the flag in
     // the same call (a rank that returned early would leave its neighbours waiting), so the call itself has run to its end.
+    if (h_stats->nan_flag & 16u) return fail(BLOBS_ERR_CUDA, "neighbour lists: a device-side launch of the rebuild kernels was refused (stale lists were used); results are invalid");
     if (h_stats->nan_flag & 8u) return fail(BLOBS_ERR_CUDA, "strip exchange: a neighbour's message did not arrive in time (stale ghosts were used); results are invalid");
     if (h_stats->nan_flag & 4u) return fail(BLOBS_ERR_CAPACITY, "strip exchange: ghost / migration message or owned-body list overflowed (raise ghost_capacity / migrate_capacity); results are invalid");
     return BLOBS_OK;
@@ -2248,8 +2272,8 @@ int World::strip_configure(int rank, int nranks, float x_lo, float x_hi, const u
     cur_recv[0] = msg[2];
     cur_recv[1] = msg[3];
     p2p_on = false;
-    if (nranks > 1 && p2p_request) {
-        rc = strip_p2p_setup();
+    if (p2p_request) {
+        rc = strip_p2p_setup();   // a one-rank strip world has nobody to exchange with: the same code paths with no peer (diagnostics)
         if (rc) return rc;
         if (p2p_on && list_mode != 0) {   // neighbour lists on strips need the peer mappings as well
             rc = nls_setup();
@@ -2321,6 +2345,10 @@ int World::strip_p2p_setup() {
         if (cudaIpcGetMemHandle(&hmine, p2p_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     }
     if (!d_push_done) { CU(cudaMalloc(&d_push_done, 2 * sizeof(unsigned int))); CU(cudaMemsetAsync(d_push_done, 0, 2 * sizeof(unsigned int), stream)); }
+    if (s_nranks <= 1) {
+        p2p_on = ok != 0;
+        return BLOBS_OK;
+    }
     char* d_h = nullptr;   // [mine | from left | from right] handles, then [mine | left | right] ok words
     CU(cudaMalloc(&d_h, 3 * 64 + 3 * sizeof(int)));
     int* d_ok = reinterpret_cast<int*>(d_h + 3 * 64);

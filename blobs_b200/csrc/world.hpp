@@ -368,6 +368,9 @@ class World {
     uint64_t cond_launches = 0, cond_nodes_built = 0, cond_per_rebuild_live = 0;
     bool nl_prev_tail = false;         // the previous substep's k_step already took the rebuild decision for this one
     int nl_rebuild_now();
+    // a rebuild is launched from the device by the deciding kernel (nlist.cuh: nl_dev_rebuild) instead of by self-gating host launches
+    bool dev_launch = true;            // BLOBS_B200_DEVLAUNCH=0: host-launched self-gating rebuild kernels
+    uint64_t dev_per_rebuild_live = 0; // kernels a device-launched rebuild consists of (launch accounting, finish_stats)
 
     // stats / recording
     DeviceStats* d_stats = nullptr;
@@ -410,7 +413,9 @@ class World {
     char* p2p_peer[2] = {nullptr, nullptr};   // left / right neighbour's block (IPC mapping)
     size_t p2p_stride = 0;
     unsigned int* d_push_done = nullptr;   // [0] CTA arrival counter, [1] exchange sequence number (device-resident: graph replay)
-    bool strip_graph = false;               // BLOBS_B200_STRIP_GRAPH=1: with the peer-memory exchange, replay whole steps as CUDA graphs
+    bool strip_graph = true;                // with the peer-memory exchange, whole steps are replayed as CUDA graphs (BLOBS_B200_STRIP_GRAPH=0: plain launches)
+    bool nls_tail_publish = false;          // BLOBS_B200_NLS_TAIL=1: k_step's last CTA publishes the end-of-substep flags instead of k_nls_publish. Measured on 2x B200
+                                            // (profiles/r2_notes.md): SLOWER, 1.646 vs 1.464 ms per step - a gpu-scope fence per CTA waits for that CTA's peer stores
     void* cur_recv[2] = {nullptr, nullptr};   // receive buffers of the exchange in flight (== msg[2], msg[3] on the NCCL path)
     int strip_p2p_setup();
     int strip_build_tail(uint32_t* tab_next, uint32_t* tab_cur, uint32_t* tile_next, uint32_t* tile_cur, float4* hot_next, bool timed_launch);

@@ -143,6 +143,16 @@ def run(rank, world, local):
         ok = len(bad) == 0 and int(t_col) == ref_col and (world == 1 or migrated > 0)
         if len(bad):
             print("first mismatches (field*n + slot):", bad[:10], merged[bad[:10]], want[bad[:10]])
+    if os.environ.get("STRIP_TEST_BENCH_PROBE") == "1":
+        # bench.py's own N > 1 self-check (a SECOND strip world in this process, after the first one): must say bit-identical
+        import bench
+
+        w.close()
+        knobs = {A.PARAM_STRIP_P2P: 1} if p2p else {}
+        out = bench.strip_parity_probe(dist, rank, world, local, "cpu", steps=14, ny=48, cols_per_rank=24, params=knobs)
+        if rank == 0:
+            print("[strip test] bench probe:", out)
+            ok = ok and out["bit_identical"] and out["migrated_bodies"] > 0 and out["list_pipeline_active"] == lists
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

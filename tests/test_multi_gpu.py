@@ -64,7 +64,8 @@ def test_strip_world_neighbour_lists_match_single_gpu():
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
     n = 2 if n < 4 else 4
-    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", BLOBS_B200_LIST="1", STRIP_TEST_EXPECT_LISTS="1")
+    env = dict(os.environ, BLOBS_B200_STRIP_P2P="1", STRIP_TEST_EXPECT_P2P="1", BLOBS_B200_LIST="1", STRIP_TEST_EXPECT_LISTS="1",
+               STRIP_TEST_BENCH_PROBE="1")   # + bench.py's own N > 1 self-check (`parity_vs_single_gpu`)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
@@ -85,7 +86,8 @@ _STRIP_CASES = [
     pytest.param(dict(_SHELL), id="shell-default", marks=_slow),
     # neighbour lists on strips: ghost records stored straight into the neighbour's arrays by k_step, rebuild decision combined
     # over all ranks, migration at rebuilds only (needs the peer-memory mappings)
-    pytest.param({**_P2P, **_LISTS}, id="gas-p2p-lists"),
+    pytest.param({**_P2P, **_LISTS, "STRIP_TEST_BENCH_PROBE": "1"}, id="gas-p2p-lists+bench-probe"),   # + bench.py's N > 1 self-check: a second strip world in the same process
+    pytest.param({**_P2P, **_LISTS, "STRIP_TEST_RANKS": "1", "STRIP_TEST_STEPS": "10"}, id="one-rank-strip-lists"),   # the strip code paths with no peer (profiles/r2_scripts/strip_diag.py)
     pytest.param({**_SHELL, **_P2P, **_LISTS, "BLOBS_B200_CROWDED": "1", "STRIP_TEST_RANKS": "3"}, id="shell-p2p-3ranks-lists-crowded"),
     pytest.param({**_P2P, **_LISTS, "STRIP_TEST_IO": "pipelined", "STRIP_TEST_STEPS": "12"}, id="gas-p2p-lists-pipelined-host-io", marks=_slow),
     # automatic mode on an agitated scene: the ranks start on lists, see them rebuilt every substep and fall back to the grid

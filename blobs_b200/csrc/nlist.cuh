@@ -214,70 +214,7 @@ __global__ void __launch_bounds__(NL_BUILD_THREADS) k_nl_build(GridDesc g, Colli
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Device-side launch of a rebuild (CUDA dynamic parallelism). The kernel that takes - or, after k_step's tail decision, picks up -
-// the verdict launches the rebuild kernels itself into the tail-launch stream: they run, in launch order, after that kernel and
-// before its successor in the host stream. A substep that keeps its lists then costs ONE tiny kernel in front of k_step instead of
-// four (strips: nine) self-gating launches of ~2.7 us each, inside a captured graph as well as with plain launches.
-// The launched kernels are the very same self-gating ones (NlCtl::need is still set when they run).
-// ---------------------------------------------------------------------------------------------------------------------
-struct NlDev {
-    uint32_t on;               // 0: the host launches the self-gating rebuild kernels after the deciding kernel
-    uint32_t tab_entries;      // length of the cell table (k_nl_scan)
-    GridDesc g;
-    ColliderArrays C;
-    BodyArrays B;
-    NlEnum E;
-    // strips only
-    uint32_t strip_on, gcap, mcap, olist_cap;
-    StripDesc S;
-    void* msg_l;
-    void* msg_r;
-    uint2* gcell;
-    uint8_t* owned;
-    uint8_t* cowned;
-    uint32_t* olist;
-    uint32_t* ocount;
-    uint32_t* opos;
-    DeviceStats* stats;
-};
-
-#ifndef BLOBS_EMU
-__global__ void __launch_bounds__(256) k_nls_pack(BodyArrays B, ColliderArrays Cc, StripDesc S, NlEnum E, void* send_l, void* send_r, const NlCtl* ctl);
-__global__ void __launch_bounds__(256) k_nls_push(StripDesc S, const void* send_l, const void* send_r, NlStripDev X, const NlCtl* ctl, DeviceStats* stats);
-__global__ void __launch_bounds__(256) k_nls_bin_ghosts(GridDesc g, StripDesc S, NlStripDev X, NlView L, uint2* gcell, DeviceStats* stats);
-__global__ void __launch_bounds__(256) k_nls_finish(BodyArrays B, ColliderArrays Cc, StripDesc S, const void* send_l, const void* send_r, NlStripDev X, NlView L,
-                                                    const uint2* __restrict__ gcell, uint8_t* owned, uint8_t* cowned, uint32_t* olist, uint32_t* ocount,
-                                                    uint32_t* opos, uint32_t olist_cap, DeviceStats* stats, float4* snap_cur);
-
-// one thread; snap = the snapshot array the coming contact pass reads
-__device__ BLOBS_NOINLINE void nl_dev_rebuild(const NlView& L, const NlDev& D, const NlStripDev& X, float4* snap) {
-    const uint32_t ne = D.E.n;
-    const unsigned ctas = min((ne + 255u) / 256u, NL_GATED_CTAS);
-    if (D.strip_on) {
-        k_nls_pack<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.B, D.C, D.S, D.E, D.msg_l, D.msg_r, L.ctl);
-        k_nls_push<<<STRIP_PUSH_CTAS, 256, 0, cudaStreamTailLaunch>>>(D.S, D.msg_l, D.msg_r, X, L.ctl, D.stats);
-    }
-    k_nl_count<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.g, D.C, D.B.bworld, L, D.E);
-    if (D.strip_on) k_nls_bin_ghosts<<<(2u * D.gcap + 255u) / 256u, 256, 0, cudaStreamTailLaunch>>>(D.g, D.S, X, L, D.gcell, D.stats);
-    k_nl_scan<<<(D.tab_entries + SCAN_TILE - 1u) / SCAN_TILE, SCAN_THREADS, 0, cudaStreamTailLaunch>>>(L, D.tab_entries);
-    k_nl_scatter<<<ctas, 256, 0, cudaStreamTailLaunch>>>(D.C, L, D.E);
-    if (D.strip_on)
-        k_nls_finish<<<(2u * D.gcap + 4u * D.mcap + 255u) / 256u, 256, 0, cudaStreamTailLaunch>>>(D.B, D.C, D.S, D.msg_l, D.msg_r, X, L, D.gcell, D.owned, D.cowned,
-                                                                                                D.olist, D.ocount, D.opos, D.olist_cap, D.stats, snap);
-    k_nl_build<<<min((ne + NL_BUILD_THREADS - 1u) / NL_BUILD_THREADS, 2u * NL_GATED_CTAS), NL_BUILD_THREADS, 0, cudaStreamTailLaunch>>>(
-        D.g, D.C, D.B.bworld, L, snap, D.E, D.strip_on ? D.cowned : nullptr, D.S);
-    if (cudaGetLastError() != cudaSuccess) atomicOr(&D.stats->nan_flag, 16u);   // a launch was refused: the lists are stale, the host reports it
-}
-#endif
-
-__device__ __forceinline__ void nl_dev_rebuild_if_needed(const NlView& L, const NlDev& D, const NlStripDev& X) {
-#ifndef BLOBS_EMU
-    if (D.on && L.ctl->need) nl_dev_rebuild(L, D, X, const_cast<float4*>(L.snap_cur));
-#endif
-}
-
-__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step, unsigned long long cond, NlView L, NlDev D) {
+__global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_t in_step, unsigned long long cond) {
     if (threadIdx.x != 0u || blockIdx.x != 0u) return;
     if (ctl->decided) {   // k_step's last CTA has decided already; only a host request can still change the verdict
         ctl->decided = 0u;
@@ -294,7 +231,6 @@ __global__ void __launch_bounds__(32) k_nl_decide(NlCtl* ctl, float lim, uint32_
         nl_decide(ctl, lim, in_step);
     }
     nl_set_cond(cond, ctl->need);
-    nl_dev_rebuild_if_needed(L, D, NlStripDev{});
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -351,8 +287,8 @@ __device__ __forceinline__ void nls_publish_warp(NlCtl* ctl, const NlStripDev& X
     }
 }
 
-template <bool FUSED, int MINB, bool STRIP>
-__global__ void __launch_bounds__(256, MINB) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
+template <bool FUSED, int MINB, bool STRIP, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB) k_step(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp,
                                                  Recording rec, DeviceStats* stats, NlStripDev X) {
     const NlView& L = bp.nl;
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,7 +469,7 @@ __global__ void __launch_bounds__(32) k_nls_publish(NlCtl* ctl, NlStripDev X) {
 }
 
 __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, float lim, float xlim, void* send_l, void* send_r, uint32_t in_step,
-                                                   DeviceStats* stats, unsigned long long cond, NlView L, NlDev D) {
+                                                   DeviceStats* stats, unsigned long long cond) {
     const uint32_t lane = threadIdx.x;
     unsigned int M = 0u, N = 0u;
     float SX = 0.f, SY = 0.f;
@@ -567,7 +503,6 @@ __global__ void __launch_bounds__(32) k_nls_decide(NlCtl* ctl, NlStripDev X, flo
             hr->n_ghost = hr->n_mig = hr->overflow = 0u;
         }
         nl_set_cond(cond, ctl->need);
-        nl_dev_rebuild_if_needed(L, D, X);
     }
 }
 

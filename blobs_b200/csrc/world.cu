@@ -78,7 +78,6 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_NLS_TAIL")) nls_tail_publish = std::atoi(e) != 0;
-    if (const char* e = std::getenv("BLOBS_B200_DEVLAUNCH")) dev_launch = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
     graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
 #endif
@@ -1098,32 +1097,14 @@ int World::nl_rebuild_chain(bool timed_launch, bool decide) {
     NlEnum E{};
     E.n = nc;
     if (strip_on) { E.olist = olist.d; E.ocount = d_ocount; E.binfo = binfo.d.d; E.n = std::max<uint32_t>(olaunch_dim, 1); }
-    // the deciding kernel launches the rebuild itself (device-side tail launch) - not while profiling (per-kernel events), not for the
-    // untimed rebuilds outside a step, not in the host-compiled test build
-    NlDev D{};
-#ifndef BLOBS_EMU
-    D.on = (dev_launch && !profiling && timed_launch && !use_cond && nc != 0) ? 1u : 0u;
-#endif
-    if (D.on) {
-        D.tab_entries = (uint32_t)tn;
-        D.g = grid; D.C = C; D.B = B; D.E = E;
-        D.stats = d_stats;
-        D.strip_on = strip_on ? 1u : 0u;
-        if (strip_on) {
-            D.gcap = strip.gcap; D.mcap = strip.mcap; D.olist_cap = (uint32_t)olist.cap;
-            D.S = strip; D.msg_l = msg[0]; D.msg_r = msg[1]; D.gcell = gcell.d;
-            D.owned = d_owned.d; D.cowned = d_cowned.d; D.olist = olist.d; D.ocount = d_ocount; D.opos = opos.d;
-        }
-    }
-    if (timed_launch) dev_per_rebuild_live = D.on ? (strip_on ? 8 : 4) : 0;   // (kept across graph replays of the same capture)
     if (strip_on) {
         // Strips: the decision combines every rank's numbers of the previous substep (and so waits for their ghost records)
-        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats, h_cur, L, D); });
-    } else if (decide || D.on) {
-        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u, h_cur, L, D); });
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nls_decide)(d_nlctl, X, L.lim, 0.25f * nl_skin, msg[0], msg[1], timed_launch ? 1u : 0u, d_stats, h_cur); });
+    } else if (decide) {
+        rc = run(KC_DECIDE, [&] { BLOBS_LAUNCH(1, 32, 0, stream, k_nl_decide)(d_nlctl, L.lim, timed_launch ? 1u : 0u, h_cur); });
     }
     if (rc) return rc;
-    if (!nc || D.on) return BLOBS_OK;
+    if (!nc) return BLOBS_OK;
     const uint32_t ne = E.n;
     auto rebuild = [&]() -> int {
         int r;
@@ -1426,6 +1407,10 @@ int World::launch_substep(const SubstepParams& P_in) {
             // BLOBS_PARAM_TUNE 1: 3 CTAs per SM (85 registers, no spills) instead of 4 (64 registers)
             if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, 4, true>)(P, grid, K, B, C, bp, R, d_stats, nls_dev());
             else if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else if (fused && tune == 2) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 5, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else if (fused && tune == 3) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 6, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else if (fused && tune == 4) BLOBS_LAUNCH(cdiv(nb, 128), 128, 0, stream, k_step<true, 8, false, 128>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            else if (fused && tune == 5) BLOBS_LAUNCH(cdiv(nb, 128), 128, 0, stream, k_step<true, 10, false, 128>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
             else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
             else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
         });
@@ -1597,7 +1582,6 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     }
     if (nl_on && cond_per_rebuild_live) launches += (h_nlctl->rebuilds - nl_seen_rebuilds) * cond_per_rebuild_live;   // IF-node bodies that ran
     cond_per_rebuild_live = 0;
-    if (nl_on && dev_per_rebuild_live) launches += (h_nlctl->rebuilds - nl_seen_rebuilds) * dev_per_rebuild_live;     // device-launched rebuilds that ran
     nl_seen_rebuilds = h_nlctl->rebuilds;
     nl_seen_substeps = h_nlctl->substeps;
     // same for the warp-pooled k_main: worth it from ~0.25 contact pairs per body-substep
@@ -1615,7 +1599,6 @@ int World::finish_stats(BlobsStepStats* out, uint32_t steps, uint32_t substeps_r
     if (h_stats->nan_flag & 2u) return fail(BLOBS_ERR_NAN, "assertion failed: rotation is finite (physics.rs:471-474)");
     // strip mode: results are not valid after either of these. The statistics above are complete, and every rank sees the flag in
     // the same call (a rank that returned early would leave its neighbours waiting), so the call itself has run to its end.
-    if (h_stats->nan_flag & 16u) return fail(BLOBS_ERR_CUDA, "neighbour lists: a device-side launch of the rebuild kernels was refused (stale lists were used); results are invalid");
     if (h_stats->nan_flag & 8u) return fail(BLOBS_ERR_CUDA, "strip exchange: a neighbour's message did not arrive in time (stale ghosts were used); results are invalid");
     if (h_stats->nan_flag & 4u) return fail(BLOBS_ERR_CAPACITY, "strip exchange: ghost / migration message or owned-body list overflowed (raise ghost_capacity / migrate_capacity); results are invalid");
     return BLOBS_OK;

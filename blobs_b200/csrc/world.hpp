@@ -368,9 +368,6 @@ class World {
     uint64_t cond_launches = 0, cond_nodes_built = 0, cond_per_rebuild_live = 0;
     bool nl_prev_tail = false;         // the previous substep's k_step already took the rebuild decision for this one
     int nl_rebuild_now();
-    // a rebuild is launched from the device by the deciding kernel (nlist.cuh: nl_dev_rebuild) instead of by self-gating host launches
-    bool dev_launch = true;            // BLOBS_B200_DEVLAUNCH=0: host-launched self-gating rebuild kernels
-    uint64_t dev_per_rebuild_live = 0; // kernels a device-launched rebuild consists of (launch accounting, finish_stats)
 
     // stats / recording
     DeviceStats* d_stats = nullptr;

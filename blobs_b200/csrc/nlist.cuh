@@ -249,15 +249,63 @@ __device__ __forceinline__ bool nl_prefilter(const SelfCol& s, float srk, const 
     return !(d2 > mdk * mdk);
 }
 
-// rare path, kept out of line so that its registers and its local-memory window do not weigh on k_step
-__device__ BLOBS_NOINLINE float2 nl_overflow_inline(GridDesc g, Broadphase bp, const uint4* __restrict__ ccold, SelfCol s, GatherOut& out, Recording rec,
-                                                  const float2* __restrict__ vel, DeviceStats* stats, float2 p) {
+// Rare path: a body whose collider has more neighbours than a list holds, met before the host has put k_crowded into the pipeline
+// (that happens from the next call on). One thread does the WHOLE body - serial, exact contact pass over the cell grid of the last
+// rebuild, then the same tail as k_step - out of line and called at the very end of k_step, where nothing else is live: an inlined
+// or mid-kernel call costs every thread of k_step spills and a ~500-byte stack frame.
+template <bool FUSED, bool STRIP>
+__device__ BLOBS_NOINLINE void nl_over_body(SubstepParams P, GridDesc g, Constraints K, BodyArrays B, ColliderArrays Cc, Broadphase bp, Recording rec,
+                                            DeviceStats* stats, uint32_t b) {
+    const NlView& L = bp.nl;
+    const uint2 info = B.binfo[b];
+    const uint32_t flags = info.x;
+    const uint32_t c = info.y;
+    const float2 mg = B.bmg[b];
+    float2 p = B.pos[b];
+    const float2 po = B.pos_old[b];
+    const float2 acc0 = load_acc(P, B, b);
+    const bool hv = load_hv(P, B, b);
+    const float4 me = L.snap_cur[c];
+    const uint4 hd = reinterpret_cast<const uint4*>(L.hdr)[c];
+    const uint32_t word = __float_as_uint(me.w);
+    SelfCol s;
+    s.x = me.x; s.y = me.y; s.r = me.z; s.m = mg.x;
+    s.qx = __uint_as_float(hd.x); s.qy = __uint_as_float(hd.y);
+    s.memb = s.filt = 0xffffffffu;
+    if (word & HOT_COLD_BIT) {
+        const uint4 cc = Cc.cconst[c];
+        s.memb = cc.z; s.filt = cc.w;
+    }
+    s.body = b; s.slot = c; s.sensor = (word & HOT_SENSOR_BIT) != 0u;
+    s.wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
+    GatherOut out;
+    out.fx = out.fy = 0.f;
+    out.n_pairs = out.n_coinc = 0;
     const Broadphase gb = resolve_grid(bp);
-    for_each_candidate(g, gb, ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
+    for_each_candidate(g, gb, Cc.ccold, s.wbase, s.qx, s.qy, s.r, [&](const Rec& o) {
         Contact ct;
-        if (narrowphase(s, o, ct)) note_pair(s, o, ct, out, rec, vel, stats);
+        if (narrowphase(s, o, ct)) note_pair(s, o, ct, out, rec, B.vel, stats);
     });
-    return apply_contacts_rescan(g, gb, ccold, &s, 1, p.x, p.y);
+    p = apply_contacts_rescan(g, gb, Cc.ccold, &s, 1, p.x, p.y);
+    if (out.n_pairs) atomicAdd(&stats->collisions, (unsigned long long)out.n_pairs);
+    if (out.n_coinc) atomicAdd(&stats->coincident, (unsigned long long)out.n_coinc);
+    if (FUSED && !(flags & BF_JOINTED)) {
+        float sx, sy, rot;
+        integrate_body(P, K, B, b, flags, mg.y, p.x, p.y, po, acc0, hv, sx, sy, rot, stats);
+        const float2 a = snapshot_of(Cc, c, hd.w, sx, sy, rot);
+        Cc.cabs[c] = a;
+        const float4 rec_new = make_float4(a.x, a.y, me.z, me.w);
+        L.snap_next[c] = rec_new;
+        if (STRIP) {
+            if (hd.w & NLF_PUSH_L) L.peer_next[0][c] = rec_new;
+            if (hd.w & NLF_PUSH_R) L.peer_next[1][c] = rec_new;
+        }
+        NlAcc na{0.f, 0.f, 0.f, 0u};
+        nl_track(a.x, a.y, __uint_as_float(hd.x), __uint_as_float(hd.y), L.ctl->cx, L.ctl->cy, na);
+        atomicMax(&L.ctl->max_m, __float_as_uint(na.m));   // (not part of the sampled mean displacement: an estimate anyway)
+    } else {
+        B.pos[b] = p;
+    }
 }
 
 // End of a substep on a strip rank (one warp): this rank's displacement accumulators and a sequence number go to EVERY rank's flag
@@ -329,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_step(SubstepParams P, GridDes
     out.fx = out.fy = 0.f;
     out.n_pairs = out.n_coinc = 0;
     unsigned int n_over = 0;
+    bool over_self = false;
     if (inb && (flags & BF_ALIVE) && col >= BODY_NO_COLLIDER) {
         bool active_col = false, deferred = false;
         uint32_t c = 0;
@@ -357,9 +406,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_step(SubstepParams P, GridDes
                     if (P.crowded) {     // a whole warp of k_crowded does this body, pair counting included
                         P.over_list[atomicAdd(&stats->over_count[P.over_parity], 1u)] = OVER_COUNT_BIT | b;
                         deferred = true;
-                    } else {             // first sighting (the host adds k_crowded to the pipeline from the next call on): serial, exact
-                        if (g.n_worlds > 1u) s.wbase = B.bworld[b] * g.ncells;
-                        p = nl_overflow_inline(g, bp, Cc.ccold, s, out, rec, B.vel, stats, p);
+                    } else {             // first sighting (the host adds k_crowded to the pipeline from the next call on): this thread does
+                        over_self = true;   // the whole body serially at the end of the kernel, where nothing else is live (nl_over_body)
+                        deferred = true;
                     }
                 } else {
                     const uint32_t cnt = hd.z;
@@ -420,6 +469,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_step(SubstepParams P, GridDes
             B.pos[b] = p;
         }
     }
+    if (over_self) nl_over_body<FUSED, STRIP>(P, g, K, B, Cc, bp, rec, stats, b);
     nl_commit(L.ctl, na, &stats->collisions, out.n_pairs);
     if (P.nl_tail_decide && threadIdx.x == 0u) {   // this kernel is the substep's only publisher: the last CTA decides for the next substep
         __threadfence();

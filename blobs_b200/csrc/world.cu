@@ -1405,13 +1405,30 @@ int World::launch_substep(const SubstepParams& P_in) {
     if (nb && lists) {
         rc = timed(KC_MAIN, [&] {
             // BLOBS_PARAM_TUNE 1: 3 CTAs per SM (85 registers, no spills) instead of 4 (64 registers)
-            if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, 4, true>)(P, grid, K, B, C, bp, R, d_stats, nls_dev());
-            else if (fused && tune == 1) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 3, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
-            else if (fused && tune == 2) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 5, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
-            else if (fused && tune == 3) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 6, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
-            else if (fused && tune == 4) BLOBS_LAUNCH(cdiv(nb, 128), 128, 0, stream, k_step<true, 8, false, 128>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
-            else if (fused && tune == 5) BLOBS_LAUNCH(cdiv(nb, 128), 128, 0, stream, k_step<true, 10, false, 128>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
-            else if (fused) BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
+            // Register cap of k_step = CTAs of 256 threads per SM. The kernel is latency-bound (dependent 16-byte gathers), so occupancy
+            // pays until the spills bite. Measured on B200 (profiles/r2_notes.md, driver window of config #2 / one strip rank at 2 M):
+            // 4 CTAs (64 registers, no spills) 0.497 / 1.149 ms, 5 (48) 0.464, 6 (40) 0.469 / 1.081, 7-8 (32, ~230 B spilled) 0.496 / 1.125.
+            // BLOBS_PARAM_TUNE overrides: 1 -> 3 CTAs, 2 -> 5, 3 -> 6, 4 -> 7, 5 -> 8, 6 -> 4.
+#define BLOBS_LAUNCH_STEP(MINB)                                                                                                                            \
+    do {                                                                                                                                                   \
+        if (strip_on) BLOBS_LAUNCH(cdiv(std::max<uint32_t>(olaunch_dim, 1), 256), 256, 0, stream, k_step<true, MINB, true>)(P, grid, K, B, C, bp, R, d_stats, nls_dev()); \
+        else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<true, MINB, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});                          \
+    } while (0)
+            if (fused || strip_on) {
+                switch (tune) {
+                    case 1: BLOBS_LAUNCH_STEP(3); break;
+                    case 2: BLOBS_LAUNCH_STEP(5); break;
+                    case 3: BLOBS_LAUNCH_STEP(6); break;
+                    case 4: BLOBS_LAUNCH_STEP(7); break;
+                    case 5: BLOBS_LAUNCH_STEP(8); break;
+                    case 6: BLOBS_LAUNCH_STEP(4); break;
+                    default:
+                        if (strip_on) BLOBS_LAUNCH_STEP(6);
+                        else BLOBS_LAUNCH_STEP(5);
+                        break;
+                }
+            }
+#undef BLOBS_LAUNCH_STEP
             else BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_step<false, 4, false>)(P, grid, K, B, C, bp, R, d_stats, NlStripDev{});
         });
         if (rc) return rc;

@@ -21,6 +21,8 @@ sc = S.lattice_scene(nx, ny, 1.05, (0.0, 0.0), 1, 0.5, 0.5, jitter=0.04, vel_dis
 w = blobs_b200.World(gravity=sc.gravity, device=0, body_capacity=sc.n_bodies, collider_capacity=sc.n_colliders)
 S.build(w, sc)
 w.set_param(A.PARAM_LIST, lst)
+if os.environ.get("DIAG_TUNE"):
+    w.set_param(A.PARAM_TUNE, int(os.environ["DIAG_TUNE"]))
 if mode == "strip":
     w.set_param(A.PARAM_STRIP_P2P, 1)
     w.strip_configure(0, 1, float("-inf"), float("inf"), blobs_b200.World.strip_unique_id(), ghost_capacity=4 * ny, migrate_capacity=2 * ny)
@@ -39,7 +41,7 @@ for _ in range(K):
     w.step(DT)
 pm = w.profile_read()
 w.profile_enable(False)
-print(json.dumps({"mode": mode, "list": lst, "list_active": int(w.get_param(A.PARAM_LIST_ACTIVE)), "spheres": n, "ms_per_step": ms, "value": n / (ms / 1e3),
+print(json.dumps({"tune": int(os.environ.get("DIAG_TUNE", "0")), "mode": mode, "list": lst, "list_active": int(w.get_param(A.PARAM_LIST_ACTIVE)), "spheres": n, "ms_per_step": ms, "value": n / (ms / 1e3),
                   "main_avg_launch_us": 1e3 * pm["main"][0] / max(pm["main"][1], 1),
                   "kernel_ms_per_step": {k: round(v[0] / K, 4) for k, v in prof.items() if v[1]},
                   "rebuilds": [w.get_param(A.PARAM_LIST_REBUILDS), w.get_param(A.PARAM_LIST_SUBSTEPS)]}), flush=True)

@@ -6,7 +6,7 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblobs_b200.so")
+LIB_PATH = os.environ.get("BLOBS_B200_LIBRARY") or os.path.join(_HERE, "libblobs_b200.so")   # (override: A/B of differently compiled builds)
 
 _u64p = C.POINTER(C.c_uint64)
 _vp = C.c_void_p

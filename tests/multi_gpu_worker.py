@@ -149,7 +149,7 @@ def run(rank, world, local):
 
         w.close()
         knobs = {A.PARAM_STRIP_P2P: 1} if p2p else {}
-        out = bench.strip_parity_probe(dist, rank, world, local, "cpu", steps=14, ny=48, cols_per_rank=24, params=knobs)
+        out = bench.strip_parity_probe(dist, rank, world, local, "cpu", steps=10, ny=48, cols_per_rank=24, params=knobs)
         if rank == 0:
             print("[strip test] bench probe:", out)
             ok = ok and out["bit_identical"] and out["migrated_bodies"] > 0 and out["list_pipeline_active"] == lists

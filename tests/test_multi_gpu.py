@@ -80,7 +80,7 @@ _P2P = {"BLOBS_B200_STRIP_P2P": "1", "STRIP_TEST_EXPECT_P2P": "1"}
 _slow = pytest.mark.skipif(os.environ.get("BLOBS_TEST_SLOW") != "1", reason="redundant combination; set BLOBS_TEST_SLOW=1")
 _LISTS = {"BLOBS_B200_LIST": "1", "STRIP_TEST_EXPECT_LISTS": "1"}
 _STRIP_CASES = [
-    pytest.param({}, id="gas-default"),
+    pytest.param({}, id="gas-default", marks=_slow),   # (gas-pipelined-host-io below is the same configuration + the pipelined frame loop)
     pytest.param(dict(_FORCED), id="gas-forced-pool-crowded", marks=_slow),
     pytest.param({**_SHELL, **_FORCED}, id="shell-forced-pool-crowded"),
     pytest.param(dict(_SHELL), id="shell-default", marks=_slow),

@@ -74,7 +74,8 @@ typedef enum BlobsParamId {
     BLOBS_PARAM_BROADPHASE_CELL = 10,    /* GPU grid cell edge; 0 = auto (2 * max collider radius) */
     BLOBS_PARAM_CONTACT_MODE = 11,       /* 0 = ordered (bit-exact summation order), 1 = fast (unordered) */
     BLOBS_PARAM_FUSED = 12,              /* 1 = allow the fused contact+verlet kernel (default), 0 = force split kernels */
-    BLOBS_PARAM_TUNE = 13,               /* kernel-variant selector for benchmarking (0 = default); never changes results */
+    BLOBS_PARAM_TUNE = 13,               /* kernel-variant selector for benchmarking (0 = default); never changes results. List pipeline:
+                                            CTAs of k_step per SM - 1: 3, 2: 5, 3: 6, 4: 7, 5: 8, 6: 4 (default 5; 6 on strips) */
     BLOBS_PARAM_BATCH_WORLD = 14         /* batched independent worlds (BASELINE config #3): bodies inserted from now on belong to this
                                             world id; worlds never interact, each one behaves like its own Physics (gravity, constraints,
                                             substeps are shared). Default 0 = the single world. */

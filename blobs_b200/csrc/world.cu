@@ -2110,6 +2110,8 @@ int World::query_circles(size_t n, const float* centre_xy, const float* radius, 
 // ---------------------------------------------------------------------------------------------- recording
 int World::record_contacts(int mode, size_t cap) {
     if (mode < 0 || mode > 2) return fail(BLOBS_ERR_INVALID, "bad record mode");
+    if (strip_on && mode == BLOBS_RECORD_EVENTS)   // (the other order is refused by strip_configure)
+        return fail(BLOBS_ERR_INVALID, "event recording is not supported on a strip-decomposed world (DESIGN.md 8.1)");
     CU(cudaStreamSynchronize(stream));
     if ((mode == BLOBS_RECORD_EVENTS) != (rec_mode == BLOBS_RECORD_EVENTS)) topo_dirty = bp_dirty = true;  // CF_COLD depends on it
     rec_mode = mode;

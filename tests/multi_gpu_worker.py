@@ -54,6 +54,11 @@ def run(rank, world, local):
     dist.broadcast(uid, 0)
     w.strip_configure(rank, world, float(edges[rank]), float(edges[rank + 1]), uid.numpy(), ghost_capacity=1 << 14, migrate_capacity=1 << 10)
     own0 = w.strip_owned()
+    try:   # events on a strip world are refused in either order (strip_configure refuses a world that already records events)
+        w.record_contacts(A.RECORD_EVENTS, 16)
+        raise AssertionError("record_contacts(EVENTS) must be refused on a strip world")
+    except blobs_b200.BlobsError:
+        pass
     p2p = int(w.get_param(A.PARAM_STRIP_P2P))   # 1 = ghosts / migrants travel by peer-memory stores (k_strip_push), 0 = ncclSend/ncclRecv
     if os.environ.get("STRIP_TEST_EXPECT_P2P"):
         assert p2p == int(os.environ["STRIP_TEST_EXPECT_P2P"]), f"rank {rank}: peer-memory exchange active={p2p}"

@@ -1583,69 +1583,118 @@ constexpr int JOINT_THREADS = 64;
 __global__ void __launch_bounds__(JOINT_THREADS) k_joints_fused(SubstepParams P, BodyArrays B, const uint32_t* __restrict__ isl_off,
                                                                 const float4* __restrict__ jli, uint32_t max_j, const uint32_t* __restrict__ isl_boff,
                                                                 const uint32_t* __restrict__ isl_body, uint32_t n_islands, uint32_t iterations,
-                                                                DeviceStats* stats) {
+                                                                DeviceStats* stats, uint32_t advance, GridDesc g, Constraints K, ColliderArrays Cc,
+                                                                Broadphase bp, const uint32_t* __restrict__ mb_off, const uint32_t* __restrict__ mb_cols) {
 #ifdef BLOBS_EMU   // host-compiled test build (tests/emu): dynamic shared memory comes from the fiber engine
     float4* const sm = static_cast<float4*>(::emu::dynamic_smem());
 #else
     extern __shared__ float4 sm[];  // (pos.x, pos.y, rot, +-1/mass): a negative inverse mass marks a static body
 #endif
+    __shared__ uint32_t s_b0[JOINT_THREADS + 1];   // advance: first entry of each island of this CTA in isl_body (non-decreasing)
     const uint32_t t = threadIdx.x, T = JOINT_THREADS;
     const uint32_t i = blockIdx.x * T + t;
-    if (i >= n_islands) return;
-    const uint32_t b0 = isl_boff[i], nbod = isl_boff[i + 1] - b0;
-    for (uint32_t k = 0; k < nbod; ++k) {
-        const uint32_t slot = isl_body[b0 + k];
-        const float2 p = B.pos[slot];
-        const float m = B.bmg[slot].x;
-        const float im = fdiv(1.0f, m);   // calculated_mass.recip() (physics.rs:450), hoisted: masses do not change inside the solve
-        sm[k * T + t] = make_float4(p.x, p.y, B.rot[slot], (B.binfo[slot].x & BF_STATIC) ? -im : im);
+    const bool live = i < n_islands;
+    uint32_t b0 = 0, nbod = 0;
+    if (live) { b0 = isl_boff[i]; nbod = isl_boff[i + 1] - b0; }
+    if (advance) {
+        const uint32_t end = isl_boff[min(n_islands, (blockIdx.x + 1u) * T)];
+        s_b0[t] = live ? b0 : end;
+        if (t == 0u) s_b0[T] = end;
     }
-    const uint32_t nj = isl_off[i + 1] - isl_off[i];
-    // joints are stored interleaved per CTA: record e of the island handled by thread t sits at ((block * max_j + e) * T + t),
-    // two float4 each, so a warp reads consecutive records (coalesced) and the 4 sweeps re-hit L1
-    const float4* jrow = jli + 2 * ((size_t)blockIdx.x * max_j * T + t);
     bool bad = false;
-    for (uint32_t it = 0; it < iterations; ++it) {
-        for (uint32_t e = 0; e < nj; ++e) {
-            const float4 q0 = __ldg(jrow + 2 * (size_t)e * T), q1 = __ldg(jrow + 2 * (size_t)e * T + 1);
-            JointParams jp;
-            jp.a = __float_as_uint(q0.x); jp.b = __float_as_uint(q0.y); jp.aax = q0.z; jp.aay = q0.w;
-            jp.abx = q1.x; jp.aby = q1.y; jp.distance = q1.z; jp.target = q1.w;
-            float4 A = sm[jp.a * T + t], Bv = sm[jp.b * T + t];
-            const float wax = fadd(A.x, jp.aax), way = fadd(A.y, jp.aay);            // physics.rs:434-435
-            const float wbx = fadd(Bv.x, jp.abx), wby = fadd(Bv.y, jp.aby);
-            const float dx = fsub(wbx, wax), dy = fsub(wby, way);                    // physics.rs:437
-            const float dist = vlen(dx, dy);
-            if (dist < 1e-6f) continue;                                              // physics.rs:440-442
-            const float off_by = fsub(dist, jp.distance);
-            const float cx = fdiv(fmul(off_by, dx), dist), cy = fdiv(fmul(off_by, dy), dist);   // physics.rs:445
-            const float ima = fabsf(A.w), imb = fabsf(Bv.w);
-            const float ims = fadd(ima, imb);                                        // physics.rs:450
-            if (A.w < 0.f) {                                                         // physics.rs:452-453
-                Bv.x = fsub(Bv.x, fmul(ims, cx)); Bv.y = fsub(Bv.y, fmul(ims, cy));
-            } else if (Bv.w < 0.f) {                                                 // physics.rs:454-455
-                A.x = fadd(A.x, fmul(ims, cx)); A.y = fadd(A.y, fmul(ims, cy));
-            } else {                                                                 // physics.rs:456-461
-                const float ratio = fdiv(ima, ims);
-                A.x = fadd(A.x, fmul(ratio, cx)); A.y = fadd(A.y, fmul(ratio, cy));
-                const float r1 = fsub(1.0f, ratio);
-                Bv.x = fsub(Bv.x, fmul(r1, cx)); Bv.y = fsub(Bv.y, fmul(r1, cy));
+    if (live) {
+        for (uint32_t k = 0; k < nbod; ++k) {
+            const uint32_t slot = isl_body[b0 + k];
+            const float2 p = B.pos[slot];
+            const float m = B.bmg[slot].x;
+            const float im = fdiv(1.0f, m);   // calculated_mass.recip() (physics.rs:450), hoisted: masses do not change inside the solve
+            sm[k * T + t] = make_float4(p.x, p.y, B.rot[slot], (B.binfo[slot].x & BF_STATIC) ? -im : im);
+        }
+        const uint32_t nj = isl_off[i + 1] - isl_off[i];
+        // joints are stored interleaved per CTA: record e of the island handled by thread t sits at ((block * max_j + e) * T + t),
+        // two float4 each, so a warp reads consecutive records (coalesced) and the 4 sweeps re-hit L1
+        const float4* jrow = jli + 2 * ((size_t)blockIdx.x * max_j * T + t);
+        for (uint32_t it = 0; it < iterations; ++it) {
+            for (uint32_t e = 0; e < nj; ++e) {
+                const float4 q0 = __ldg(jrow + 2 * (size_t)e * T), q1 = __ldg(jrow + 2 * (size_t)e * T + 1);
+                JointParams jp;
+                jp.a = __float_as_uint(q0.x); jp.b = __float_as_uint(q0.y); jp.aax = q0.z; jp.aay = q0.w;
+                jp.abx = q1.x; jp.aby = q1.y; jp.distance = q1.z; jp.target = q1.w;
+                float4 A = sm[jp.a * T + t], Bv = sm[jp.b * T + t];
+                const float wax = fadd(A.x, jp.aax), way = fadd(A.y, jp.aay);            // physics.rs:434-435
+                const float wbx = fadd(Bv.x, jp.abx), wby = fadd(Bv.y, jp.aby);
+                const float dx = fsub(wbx, wax), dy = fsub(wby, way);                    // physics.rs:437
+                const float dist = vlen(dx, dy);
+                if (dist < 1e-6f) continue;                                              // physics.rs:440-442
+                const float off_by = fsub(dist, jp.distance);
+                const float cx = fdiv(fmul(off_by, dx), dist), cy = fdiv(fmul(off_by, dy), dist);   // physics.rs:445
+                const float ima = fabsf(A.w), imb = fabsf(Bv.w);
+                const float ims = fadd(ima, imb);                                        // physics.rs:450
+                if (A.w < 0.f) {                                                         // physics.rs:452-453
+                    Bv.x = fsub(Bv.x, fmul(ims, cx)); Bv.y = fsub(Bv.y, fmul(ims, cy));
+                } else if (Bv.w < 0.f) {                                                 // physics.rs:454-455
+                    A.x = fadd(A.x, fmul(ims, cx)); A.y = fadd(A.y, fmul(ims, cy));
+                } else {                                                                 // physics.rs:456-461
+                    const float ratio = fdiv(ima, ims);
+                    A.x = fadd(A.x, fmul(ratio, cx)); A.y = fadd(A.y, fmul(ratio, cy));
+                    const float r1 = fsub(1.0f, ratio);
+                    Bv.x = fsub(Bv.x, fmul(r1, cx)); Bv.y = fsub(Bv.y, fmul(r1, cy));
+                }
+                const float rc = fmul(fsub(joint_angle_gap(dx, dy), jp.target), 0.5f);   // physics.rs:463-466
+                A.z = fadd(A.z, fmul(rc, P.dt));                                         // physics.rs:468-469
+                Bv.z = fsub(Bv.z, fmul(rc, P.dt));
+                if (!(fabsf(A.z) <= 3.4028235e38f) || !(fabsf(Bv.z) <= 3.4028235e38f)) bad = true;   // physics.rs:471-474
+                sm[jp.a * T + t] = A;
+                sm[jp.b * T + t] = Bv;
             }
-            const float rc = fmul(fsub(joint_angle_gap(dx, dy), jp.target), 0.5f);   // physics.rs:463-466
-            A.z = fadd(A.z, fmul(rc, P.dt));                                         // physics.rs:468-469
-            Bv.z = fsub(Bv.z, fmul(rc, P.dt));
-            if (!(fabsf(A.z) <= 3.4028235e38f) || !(fabsf(Bv.z) <= 3.4028235e38f)) bad = true;   // physics.rs:471-474
-            sm[jp.a * T + t] = A;
-            sm[jp.b * T + t] = Bv;
         }
     }
     if (bad) atomicOr(&stats->nan_flag, 2u);
-    for (uint32_t k = 0; k < nbod; ++k) {
-        const uint32_t slot = isl_body[b0 + k];
-        const float4 v = sm[k * T + t];
-        B.rot[slot] = v.z;
-        B.pos[slot] = make_float2(v.x, v.y);
+    if (!advance) {   // the bodies are advanced by a separate body-parallel pass (k_integrate)
+        if (live) {
+            for (uint32_t k = 0; k < nbod; ++k) {
+                const uint32_t slot = isl_body[b0 + k];
+                const float4 v = sm[k * T + t];
+                B.rot[slot] = v.z;
+                B.pos[slot] = make_float2(v.x, v.y);
+            }
+        }
+        return;
     }
+    // Advance the CTA's jointed bodies here (update_objects + apply_constraints + snapshot + binning, physics.rs:323-395) instead of
+    // writing them back for k_integrate to re-read: the CTA walks the island-major list of its bodies with consecutive threads on
+    // consecutive entries (= consecutive slots when a soft body's parts were inserted together), solved state out of shared memory.
+    __syncthreads();
+    NlAcc na{0.f, 0.f, 0.f, 0u};
+    const uint32_t first = s_b0[0], end = s_b0[T];
+    for (uint32_t q = first + t; q < end; q += T) {
+        uint32_t lo = 0, hi = T;   // s_b0[lo] <= q < s_b0[hi]; among equal starts (empty islands) the last one owns the entry
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_b0[mid] <= q) lo = mid; else hi = mid;
+        }
+        const uint32_t b = isl_body[q];
+        const float4 v = sm[(q - s_b0[lo]) * T + lo];
+        B.rot[b] = v.z;
+        const uint2 info = B.binfo[b];
+        const uint32_t flags = info.x;
+        const int32_t col = (int32_t)info.y;
+        const uint32_t wbase = g.n_worlds > 1u ? B.bworld[b] * g.ncells : 0u;
+        float sx, sy, rot;
+        integrate_body(P, K, B, b, flags, B.bmg[b].y, v.x, v.y, B.pos_old[b], load_acc(P, B, b), load_hv(P, B, b), sx, sy, rot, stats);
+        if (col >= 0) {
+            const uint32_t cf = Cc.cconst[col].y;
+            if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, (uint32_t)col, cf, wbase, sx, sy, rot, na);
+        } else if (col <= -2) {
+            const uint32_t mi = (uint32_t)(-(col + 2));
+            for (uint32_t k = mb_off[mi]; k < mb_off[mi + 1]; ++k) {
+                const uint32_t c = mb_cols[k];
+                const uint32_t cf = Cc.cconst[c].y;
+                if (cf & CF_ACTIVE) publish_collider(g, Cc, bp, c, cf, wbase, sx, sy, rot, na);
+            }
+        }
+    }
+    if (bp.nl.snap_next != nullptr) nl_commit(bp.nl.ctl, na, &stats->collisions, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------

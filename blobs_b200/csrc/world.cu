@@ -78,6 +78,7 @@ World::World(const BlobsParams& p) : params(p) {
     if (const char* e = std::getenv("BLOBS_B200_STRIP_P2P")) p2p_request = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_STRIP_GRAPH")) strip_graph = std::atoi(e) != 0;
     if (const char* e = std::getenv("BLOBS_B200_NLS_TAIL")) nls_tail_publish = std::atoi(e) != 0;
+    if (const char* e = std::getenv("BLOBS_B200_JADV")) joint_advance = std::atoi(e) != 0;
 #ifdef BLOBS_EMU
     graphs_on = false;   // host-compiled test build (tests/emu): no CUDA graphs there
 #endif
@@ -1261,7 +1262,7 @@ uint64_t World::step_key(uint32_t nsub, float delta, bool last) {
     };
 #define MIXV(v) { auto t__ = (v); mix(&t__, sizeof(t__)); }
     MIXV(nsub) MIXV(delta) MIXV(last) MIXV(old_dt) MIXV(gx) MIXV(gy) MIXV(collisions_enabled) MIXV(joint_iterations) MIXV(contact_mode)
-    MIXV(allow_fused) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling) MIXV(profile_main_only)
+    MIXV(allow_fused) MIXV(joint_advance) MIXV(tune) MIXV(crowded_mode) MIXV(crowded_seen) MIXV(pool_mode) MIXV(pool_seen) MIXV(pool_min) MIXV(over_list.d) MIXV(cur_is_a) MIXV(any_dynamic) MIXV(rec_mode) MIXV(profiling) MIXV(profile_main_only)
     MIXV(bodies.slots()) MIXV(cols.slots()) MIXV(con_pos.size()) MIXV(n_multi) MIXV(n_sb) MIXV(n_islands) MIXV(n_joints_live) MIXV(isl_max_bodies)
     MIXV(isl_max_joints) MIXV(joints_smem_ok) MIXV(grid) MIXV(strip_on) MIXV(strip) MIXV(olaunch_dim) MIXV(n_loose) MIXV(n_active_cols)
     const BodyArrays B = body_arrays();
@@ -1475,20 +1476,23 @@ int World::launch_substep(const SubstepParams& P_in) {
     const size_t jsmem = (size_t)JOINT_THREADS * std::max<uint32_t>(isl_max_bodies, 1) * sizeof(float4);
     if (fused) {
         if (n_islands) {  // joint projection from shared memory, then a body-parallel (coalesced) verlet pass over the jointed bodies
+            // joint_advance: the joint kernel also advances its bodies (no second pass that re-reads them)
             rc = timed(KC_JOINTS, [&] {
                 BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused)(P, B, isl_off.d, d_joints_inter.d, isl_max_joints, isl_boff.d, isl_body.d, n_islands,
-                                                                                                  joint_iterations, d_stats);
+                                                                                                  joint_iterations, d_stats, joint_advance ? 1u : 0u, grid, K, C, bp, mb_off.d, mb_cols.d);
             });
             if (rc) return rc;
-            rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
-            if (rc) return rc;
+            if (!joint_advance) {
+                rc = timed(KC_INTEGRATE, [&] { BLOBS_LAUNCH(cdiv(nb, 256), 256, 0, stream, k_integrate)(P, grid, K, B, C, bp, d_stats, mb_off.d, mb_cols.d, (uint32_t)BF_JOINTED); });
+                if (rc) return rc;
+            }
         }
     } else {
         if (n_islands && joint_iterations) {
             if (joints_smem_ok) {
                 rc = timed(KC_JOINTS, [&] {
                     BLOBS_LAUNCH(cdiv(n_islands, JOINT_THREADS), JOINT_THREADS, jsmem, stream, k_joints_fused)(P, B, isl_off.d, d_joints_inter.d, isl_max_joints, isl_boff.d, isl_body.d, n_islands,
-                                                                                                      joint_iterations, d_stats);
+                                                                                                      joint_iterations, d_stats, 0u, grid, K, C, bp, mb_off.d, mb_cols.d);
                 });
             } else {
                 rc = timed(KC_JOINTS, [&] { BLOBS_LAUNCH(cdiv(n_islands, 128), 128, 0, stream, k_joints)(P, B, isl_off.d, isl_joint.d, d_joints.d, n_islands, joint_iterations, d_stats); });

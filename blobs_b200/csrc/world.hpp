@@ -411,6 +411,8 @@ class World {
     size_t p2p_stride = 0;
     unsigned int* d_push_done = nullptr;   // [0] CTA arrival counter, [1] exchange sequence number (device-resident: graph replay)
     bool strip_graph = true;                // with the peer-memory exchange, whole steps are replayed as CUDA graphs (BLOBS_B200_STRIP_GRAPH=0: plain launches)
+    bool joint_advance = true;              // k_joints_fused advances the jointed bodies itself instead of writing them back for a k_integrate pass to re-read
+                                            // (config #4: 3.31 -> 3.04 ms per step; BLOBS_B200_JADV=0 restores the separate pass)
     bool nls_tail_publish = false;          // BLOBS_B200_NLS_TAIL=1: k_step's last CTA publishes the end-of-substep flags instead of k_nls_publish. Measured on 2x B200
                                             // (profiles/r2_notes.md): SLOWER, 1.646 vs 1.464 ms per step - a gpu-scope fence per CTA waits for that CTA's peer stores
     void* cur_recv[2] = {nullptr, nullptr};   // receive buffers of the exchange in flight (== msg[2], msg[3] on the NCCL path)
